@@ -1,0 +1,94 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes access to oracle/_ref/libdcsref.so (the UNMODIFIED
+reference decoder/encoder compiled by oracle/Makefile).  Only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs may import this module."""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libdcsref.so"))
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(os.path.join(_HERE, "_ref", "libdcsref.so"))
+        L.dcsref_decode_stream.restype = C.c_int
+        L.dcsref_decode_stream.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.dcsref_stream_info.restype = C.c_int
+        L.dcsref_stream_info.argtypes = [C.c_void_p, C.c_size_t, C.c_int] + [C.POINTER(C.c_int)] * 4
+        L.dcsref_probe_frames.restype = C.c_int
+        L.dcsref_probe_frames.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint16, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.dcsref_transform.restype = C.c_int
+        L.dcsref_transform.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.dcsref_encode.restype = C.c_size_t
+        L.dcsref_encode.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_float, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]
+        L.dcsref_decode_batch_timed.restype = C.c_double
+        L.dcsref_decode_batch_timed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                                                C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.dcsref_rom_open_zip.restype = C.c_void_p
+        L.dcsref_rom_open_zip.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
+        L.dcsref_rom_close.argtypes = [C.c_void_p]
+        L.dcsref_rom_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 5
+        L.dcsref_rom_write_port.argtypes = [C.c_void_p, C.c_uint8]
+        L.dcsref_rom_set_master_volume.argtypes = [C.c_void_p, C.c_int]
+        L.dcsref_rom_render.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.dcsref_rom_host_bytes.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.dcsref_rom_list_streams.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        _LIB = L
+    return _LIB
+
+
+def encode(pcm, sample_rate=31250, fmt=0x9400, stype=1, subtype=3, bit_rate=128000, power_cut=0.97):
+    pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+    cap = 64 + pcm.size * 2 + 65536
+    out = np.zeros(cap, dtype=np.uint8)
+    nf = C.c_int(0)
+    n = lib().dcsref_encode(pcm.ctypes.data, pcm.size, sample_rate, fmt, stype, subtype, bit_rate,
+                            power_cut, out.ctypes.data, cap, C.byref(nf))
+    if n == 0:
+        raise RuntimeError("reference encoder refused the stream")
+    return out[:n].tobytes(), nf.value
+
+
+def decode(data, os_version=0x9400, master_volume=255, mixing_level=0x64, n_frames=None):
+    a = np.frombuffer(data, dtype=np.uint8)
+    if n_frames is None:
+        n_frames = ((int(a[0]) << 8) | int(a[1])) + 2
+    pcm = np.zeros(n_frames * 240, dtype=np.int16)
+    lib().dcsref_decode_stream(a.ctypes.data, a.size, os_version, master_volume, mixing_level, n_frames, pcm.ctypes.data)
+    return pcm
+
+
+def stream_info(data, os_version=0x9400):
+    a = np.frombuffer(data, dtype=np.uint8)
+    v = [C.c_int(0) for _ in range(4)]
+    lib().dcsref_stream_info(a.ctypes.data, a.size, os_version, *[C.byref(x) for x in v])
+    return dict(nFrames=v[0].value, nBytes=v[1].value, type=v[2].value, subtype=v[3].value)
+
+
+def probe_frames(data, os_version=0x9400, mix_mult=0x7FFF, max_frames=65535):
+    a = np.frombuffer(data, dtype=np.uint8)
+    nf = min((int(a[0]) << 8) | int(a[1]), max_frames)
+    bitpos = np.zeros(nf + 1, dtype=np.uint32)
+    bt = np.zeros((nf, 16), dtype=np.uint16)
+    bins = np.zeros((nf, 512), dtype=np.uint16)
+    stop = np.zeros(nf, dtype=np.uint8)
+    lib().dcsref_probe_frames(a.ctypes.data, a.size, os_version, mix_mult, nf, bitpos.ctypes.data,
+                              bt.ctypes.data, bins.ctypes.data, stop.ctypes.data)
+    return bitpos, bt, bins, stop
+
+
+def transform(bins, overlap, os_version=0x9400, vol_shift=0):
+    b = np.zeros(512, dtype=np.uint16)
+    b[:len(bins)] = np.asarray(bins).astype(np.uint16)
+    o = np.ascontiguousarray(np.asarray(overlap).astype(np.uint16))
+    pcm = np.zeros(240, dtype=np.int16)
+    lib().dcsref_transform(os_version, vol_shift, b.ctypes.data, o.ctypes.data, pcm.ctypes.data)
+    return pcm, o.astype(np.int16), b
