@@ -1,0 +1,380 @@
+#!/usr/bin/env python3
+"""bench.py -- decoded PCM Msamples/s of the DCS batch decoder (BASELINE.json metric).
+
+A "step" is one pass of the hot path (frame-boundary scan + decode/transform/writeback) over
+one batch of synthetic DCS streams.  At N=1 the workload is BASELINE.json configs[1]: 4,096
+synthetic 1994+ format streams (mixed types / bit rates), 10 s each, produced by the reference's
+own DCSEncoder (oracle/_ref) from generated sources.  With N>1 every rank decodes its own
+4,096 streams (streams are independent: sharded by stream, no data-path collective; weak
+scaling); the only collective is the gather of the per-rank time / checksum.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+`value`  : whole-job Msamples/s with the compressed streams already resident in HBM.
+`e2e`    : same metric through the host-buffer C-ABI call dcsb_decode_streams (pinned host
+           input, H2D, kernels, D2H of all PCM inside the timed region).
+`roofline`: the dominant kernel (decode+transform) against the measured HBM copy bandwidth.
+`cpu_baseline`: the reference DCSDecoderNative (oracle/_ref, kind "reference") -- or the
+           oracle port when the reference did not compile -- on a bounded sample, all host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SAMPLE_RATE = 31250
+FRAME = 240
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic corpus
+def synth_source(seed, seconds):
+    rng = np.random.default_rng(seed)
+    n = int(seconds * SAMPLE_RATE)
+    t = np.arange(n) / SAMPLE_RATE
+    x = np.zeros(n)
+    for _ in range(int(rng.integers(1, 5))):
+        f = float(np.exp(rng.uniform(np.log(50.0), np.log(12000.0))))
+        x += rng.uniform(0.05, 0.4) * np.sin(2 * np.pi * f * t + rng.uniform(0, 6.28))
+    level = 10 ** (rng.uniform(-40, -10) / 20)
+    noise = rng.normal(0, 1, n)
+    if rng.random() < 0.5:                       # pink noise (Kellet's 3-pole approximation)
+        from scipy.signal import lfilter
+        noise = lfilter([0.049922035, -0.095993537, 0.050612699, -0.004408786],
+                        [1, -2.494956002, 2.017265875, -0.522189400], noise)
+        noise /= max(1e-9, noise.std())
+    x += level * noise
+    if rng.random() < 0.05:                      # silent gap
+        g0 = int(rng.integers(0, max(1, n - SAMPLE_RATE // 2)))
+        x[g0:g0 + SAMPLE_RATE // 2] = 0
+    return np.clip(x, -1, 1).astype(np.float32)
+
+
+TYPES = [(0, 0), (1, 0), (1, 3)]
+RATES = [32000, 64000, 96000, 128000, 192000, 256000]
+CUTS = [0.90, 0.97, 1.0]
+
+
+def _encode_one(args):
+    seed, seconds = args
+    from oracle import ref
+    ty, sub = TYPES[seed % 3]
+    rate = RATES[(seed // 3) % 6]
+    cut = CUTS[(seed // 18) % 3]
+    data, nf = ref.encode(synth_source(seed, seconds), fmt=0x9400, stype=ty, subtype=sub, bit_rate=rate, power_cut=cut)
+    return data
+
+
+def build_corpus(n_streams, seconds, seed0, budget_s=75.0, log=None):
+    """Returns (list of stream bytes, n_unique, source description).  Unique streams come from
+    the reference encoder (cached under corpus_cache/); when fewer than n_streams can be made
+    inside the time budget the pool is replicated (every replica gets its own bytes in HBM)."""
+    from oracle import ref
+    cache_dir = os.path.join(ROOT, "corpus_cache")
+    os.makedirs(cache_dir, exist_ok=True)
+    cache = os.path.join(cache_dir, "c2_%d_%gs_seed%d.npz" % (n_streams, seconds, seed0))
+    pool = []
+    if os.path.exists(cache):
+        z = np.load(cache)
+        blob, offs = z["blob"], z["offs"]
+        pool = [blob[offs[i]:offs[i + 1]].tobytes() for i in range(len(offs) - 1)]
+    src = "reference DCSEncoder (oracle/_ref)"
+    if len(pool) < n_streams:
+        if ref.available():
+            import multiprocessing as mp
+            ncpu = len(os.sched_getaffinity(0))
+            t0 = time.time()
+            with mp.get_context("fork").Pool(ncpu) as pool_mp:
+                it = pool_mp.imap(_encode_one, [(seed0 + i, seconds) for i in range(len(pool), n_streams)], chunksize=2)
+                for d in it:
+                    pool.append(d)
+                    if time.time() - t0 > budget_s and len(pool) >= 32:
+                        pool_mp.terminate()
+                        break
+            offs = np.cumsum([0] + [len(p) for p in pool]).astype(np.int64)
+            np.savez(cache, blob=np.frombuffer(b"".join(pool), dtype=np.uint8), offs=offs)
+        else:
+            import dcsfuzz
+            src = "bit-level fuzzer (reference encoder unavailable)"
+            rng = np.random.default_rng(seed0)
+            nf = int(seconds * SAMPLE_RATE / FRAME)
+            pool = [dcsfuzz.fuzz94(rng, nf, type1=i & 1, max_code=9) for i in range(min(n_streams, 32))]
+    n_unique = min(len(pool), n_streams)
+    streams = [pool[i % n_unique] for i in range(n_streams)]
+    return streams, n_unique, src
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_run(streams, vol, lvl, tail, threads, budget_streams):
+    """Times the reference CPU decoder (or the oracle port) on streams[:budget_streams]."""
+    from oracle import ref, orc
+    sample = streams[:budget_streams]
+    nsamp = sum((((s[0] << 8) | s[1]) + tail) * FRAME for s in sample)
+    if ref.available():
+        L = ref.lib()
+        n = len(sample)
+        bufs = [np.frombuffer(s, dtype=np.uint8) for s in sample]
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        nbytes = np.array([b.size for b in bufs], dtype=np.uint32)
+        nfr = np.array([((s[0] << 8) | s[1]) + tail for s in sample], dtype=np.uint32)
+        cs = C.c_uint64(0)
+        secs = L.dcsref_decode_batch_timed(ptrs, nbytes.ctypes.data, nfr.ctypes.data, n, 0x9400, vol, lvl,
+                                           threads, None, C.byref(cs))
+        kind = "reference"
+    else:
+        t0 = time.time()
+        for s in sample:
+            orc.decode(s, 0x9400, vol, lvl, ((s[0] << 8) | s[1]) + tail)
+        secs = time.time() - t0
+        kind, threads = "port", 1
+    return nsamp / secs / 1e6, kind, threads, "%d of the workload's streams (%.1f s of audio each), %.2f s wall" % (
+        len(sample), (((sample[0][0] << 8) | sample[0][1]) * FRAME) / SAMPLE_RATE, secs), secs
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=4096)
+    ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    vol, lvl, tail = 255, 0x64, 2
+    workload = "%d synthetic 1994+ streams x %g s, types {0.0,1.0,1.3} x bit rates 32k..256k x power cut {.90,.97,1}" % (a.streams, a.seconds)
+    ncores = len(os.sched_getaffinity(0))
+
+    # ---------------- reference arm: the reference's own CPU decoder on the host cores
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        streams, n_unique, src = build_corpus(a.streams, a.seconds, 0)
+        per_step = min(max(ncores * 16, 64), len(streams))
+        vals = []
+        for s in range(a.warmup + a.steps):
+            lo = (s * per_step) % max(1, len(streams) - per_step + 1)
+            v, kind, thr, sample, secs = cpu_reference_run(streams[lo:lo + per_step], vol, lvl, tail, ncores, per_step)
+            if s >= a.warmup:
+                vals.append((v, secs))
+        value = float(np.mean([v for v, _ in vals]))
+        line = {"impl": "reference", "metric": "decoded PCM Msamples/s (bit-exact)", "value": value, "unit": "Msamples/s",
+                "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": float(np.mean([s for _, s in vals]) * 1e3), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "int16/int32 fixed point", "data": "synthetic: " + src,
+                "config": {"workload": workload, "step": "%d streams per step (bounded sample)" % per_step,
+                           "unique_streams": n_unique},
+                "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": thr, "kind": kind, "sample": sample},
+                "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ---------------- our arm
+    import torch
+    import dcsexplorer_b200 as dx
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the decoder has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if rank == 0:
+        streams, n_unique, src = build_corpus(a.streams, a.seconds, 0)
+    if world > 1:
+        dist.barrier()
+        if rank != 0:
+            streams, n_unique, src = build_corpus(a.streams, a.seconds, 0)   # cache written by rank 0
+        # every rank decodes its own 4,096 streams: rotate the pool so ranks differ
+        k = (rank * 997) % len(streams)
+        streams = streams[k:] + streams[:k]
+
+    ctx = dx.Context(local_rank)
+    batch = ctx.batch(streams, os_version=dx.OS94, master_volume=vol, mixing_level=lvl, tail_frames=tail)
+    total_samples = batch.total_samples
+    alg_bytes = batch.compressed_bytes + total_samples * 2
+    d_pcm = torch.empty(total_samples, dtype=torch.int16, device="cuda")
+    st = torch.cuda.current_stream()
+
+    def step():
+        batch.decode(d_pcm.data_ptr(), st.cuda_stream)
+
+    for _ in range(max(3, a.warmup)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+    kms = [[], []]
+    torch.cuda.synchronize()
+    ev[0].record(st)
+    for i in range(a.steps):
+        step()
+        ev[i + 1].record(st)
+    torch.cuda.synchronize()
+    # per-kernel times of the last step come from events the library records on the same stream
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.steps)]
+    total_ms = ev[0].elapsed_time(ev[a.steps])
+    # per-kernel average: re-run K steps reading the library's own CUDA-event pairs
+    for i in range(a.steps):
+        step()
+        kms[0].append(batch.kernel_ms(0))
+        kms[1].append(batch.kernel_ms(1))
+    clocks = sampler.stop()
+    res = batch.results(st.cuda_stream)
+    bad = [r["status"] for r in res if r["status"] != 0]
+    xor = 0
+    for r in res:
+        xor ^= r["checksum"]
+
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    cs = torch.tensor([xor & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gathered = [torch.zeros_like(cs) for _ in range(world)]
+        dist.all_gather(gathered, cs)               # the checksum gather: 8 bytes per rank over NCCL
+    total_ms = float(t.item())
+    value = world * total_samples * a.steps / (total_ms * 1e-3) / 1e6
+
+    # ---------------- end-to-end through the host-buffer C-ABI call (rank-local, then max over ranks)
+    descs, keep = dx.make_descs(streams, os_version=dx.OS94, master_volume=vol, mixing_level=lvl, tail_frames=tail)
+    # inputs in pinned host memory: one pinned blob, descriptors point into it
+    blob = torch.empty(sum(len(s) for s in streams), dtype=torch.uint8).pin_memory()
+    off = 0
+    bnp = blob.numpy()
+    for i, s in enumerate(streams):
+        bnp[off:off + len(s)] = np.frombuffer(s, dtype=np.uint8)
+        descs[i].data = blob.data_ptr() + off
+        off += len(s)
+    h_pcm = torch.empty(total_samples, dtype=torch.int16).pin_memory()
+    resarr = (dx.Result * len(streams))()
+    L = ctx._L
+    e2e_ms = []
+    for i in range(1 + a.e2e_steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rc = L.dcsb_decode_streams(ctx._h, descs, len(streams), h_pcm.data_ptr(), None, resarr)
+        t1 = time.perf_counter()
+        if rc != 0:
+            raise SystemExit("dcsb_decode_streams failed: %d" % rc)
+        if i > 0:
+            e2e_ms.append((t1 - t0) * 1e3)
+    e2e_t = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * total_samples / (float(e2e_t.item()) * 1e-3) / 1e6
+    # spot-check the e2e output against the resident-path output
+    same = bool(torch.equal(h_pcm[:FRAME * 64], d_pcm[:FRAME * 64].cpu()))
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        dec_ms = float(np.mean(kms[1]))
+        scan_ms = float(np.mean(kms[0]))
+        achieved = alg_bytes / (dec_ms * 1e-3) / 1e9
+        line = {
+            "metric": "decoded PCM Msamples/s (bit-exact)", "value": value, "unit": "Msamples/s", "n_gpus": world,
+            "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": total_ms / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16/int32 fixed point", "data": "synthetic: " + src,
+            "config": {"workload": workload, "per_gpu_streams": a.streams, "unique_streams": n_unique,
+                       "frames_per_gpu": int(batch.total_frames), "compressed_bytes_per_gpu": int(batch.compressed_bytes),
+                       "pcm_bytes_per_gpu": int(total_samples * 2), "parallelism": "streams sharded by rank, no data-path collective",
+                       "l2": "inputs+outputs (%.2f GB) exceed the 126 MB L2; no flush needed" % (alg_bytes / 1e9),
+                       "master_volume": vol, "mixing_level": lvl, "tail_frames": tail},
+            "kernels_ms": {"scan": scan_ms, "decode_transform": dec_ms},
+            "roofline": {"bound": "hbm", "kernel": "dcsb_decode_kernel<1994>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(alg_bytes),
+                         "whole_step_frac": alg_bytes / (total_ms / a.steps * 1e-3) / 1e9 / peak},
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(batch.compressed_bytes),
+                    "d2h_bytes_per_step": int(total_samples * 2), "ms_per_step": float(e2e_t.item()),
+                    "api": "dcsb_decode_streams (pinned host in/out)", "matches_resident_path": same},
+            "gpu_launches": batch.launches() * a.steps,
+            "clocks": clocks,
+            "status": {"streams_with_errors": len(bad), "checksum_xor": "%016x" % xor},
+        }
+        if not a.no_cpu_baseline:
+            v, kind, thr, sample, secs = cpu_reference_run(streams, vol, lvl, tail, ncores, min(768, len(streams)))
+            line["cpu_baseline"] = {"value": v, "unit": "Msamples/s", "cores": thr, "kind": kind, "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,64 @@
+"""ctypes view of the C-ABI declared in include/dcsb200.h (libdcsb200.so)."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdcsb200.so")
+
+OS93A, OS93B, OS94, OS95 = 0x9301, 0x9302, 0x9400, 0x9500
+OK, E_EMPTY, E_TRUNCATED, E_BANDTYPE, E_SHORT, E_STOPPED = 0, -1, -2, -3, -4, -5
+E_ARG, E_CUDA, E_NOMEM = -16, -17, -18
+
+
+class StreamDesc(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("nbytes", C.c_uint32), ("os_version", C.c_uint16),
+                ("master_volume", C.c_uint8), ("mixing_level", C.c_uint8),
+                ("tail_frames", C.c_uint16), ("reserved", C.c_uint16)]
+
+
+class Result(C.Structure):
+    _fields_ = [("status", C.c_int32), ("frames", C.c_uint32), ("frames_decoded", C.c_uint32),
+                ("stream_bytes", C.c_uint32), ("checksum", C.c_uint64)]
+
+
+SYMBOLS = {
+    "dcsb_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "dcsb_destroy": (None, [C.c_void_p]),
+    "dcsb_last_error": (C.c_char_p, [C.c_void_p]),
+    "dcsb_version": (C.c_char_p, []),
+    "dcsb_decode_streams": (C.c_int, [C.c_void_p, C.POINTER(StreamDesc), C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(Result)]),
+    "dcsb_batch_create": (C.c_int, [C.c_void_p, C.POINTER(StreamDesc), C.c_size_t, C.POINTER(C.c_void_p)]),
+    "dcsb_batch_destroy": (None, [C.c_void_p]),
+    "dcsb_batch_total_samples": (C.c_uint64, [C.c_void_p]),
+    "dcsb_batch_total_frames": (C.c_uint64, [C.c_void_p]),
+    "dcsb_batch_compressed_bytes": (C.c_uint64, [C.c_void_p]),
+    "dcsb_batch_pcm_offset": (C.c_uint64, [C.c_void_p, C.c_size_t]),
+    "dcsb_batch_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcsb_batch_launches": (C.c_int, [C.c_void_p]),
+    "dcsb_batch_results": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Result)]),
+    "dcsb_batch_read_pcm": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "dcsb_batch_device_pcm": (C.c_void_p, [C.c_void_p]),
+    "dcsb_batch_last_kernel_ms": (C.c_float, [C.c_void_p, C.c_int]),
+    "dcsb_batch_read_scan": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "dcsb_master_multiplier": (C.c_uint16, [C.c_int]),
+    "dcsb_level_multiplier": (C.c_uint16, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "dcsb_gain_stage": (C.c_int, [C.POINTER(C.c_uint16), C.c_uint, C.c_uint, C.c_uint16, C.POINTER(C.c_uint16)]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libdcsb200.so; raises (no fallback) when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("dcsexplorer_b200: %s is missing -- run __graft_entry__.build() "
+                               "(there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib

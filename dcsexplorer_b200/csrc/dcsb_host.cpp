@@ -1,0 +1,205 @@
+// dcsb200 host-side control plane that needs no CUDA call: format tables, the gain
+// staging arithmetic, stream validation, slab layout and tiling.  Linked into
+// libdcsb200.so; also compiled on its own by the CPU-side kernel simulator (tests/hostsim).
+#include <stdint.h>
+#include <string.h>
+#include <algorithm>
+#include <thread>
+#include <vector>
+#include "../../include/dcsb200.h"
+#include "dcsb_internal.h"
+#include "dcs_tables.h"
+
+// ======================================================================================
+// tables: prefix-code lists (dcs_tables.h) -> peek LUTs
+static void fill_lut(uint16_t *lut, int peek_bits, const dcs_code_t *codes, int n)
+{
+    for (int i = 0; i < n; ++i) {
+        if (codes[i].len > peek_bits) continue;
+        const int rep = 1 << (peek_bits - codes[i].len);
+        const uint32_t base = codes[i].code << (peek_bits - codes[i].len);
+        for (int r = 0; r < rep; ++r) lut[base + r] = (uint16_t)((codes[i].len << 8) | codes[i].val);
+    }
+}
+#define NCODES(t) ((int)(sizeof(t) / sizeof((t)[0])))
+
+static int rev_bits(int x, int n) { int r = 0; for (int i = 0; i < n; ++i) r |= ((x >> i) & 1) << (n - 1 - i); return r; }
+
+void dcsb_build_tables(DcsbTables *t)
+{
+    memset(t, 0, sizeof(*t));
+    fill_lut(t->lut + DCSB_LUT_HDR94, 8, dcs94_hdr, NCODES(dcs94_hdr));
+    fill_lut(t->lut + DCSB_LUT_CB + 0, 2, dcs94_cb1, NCODES(dcs94_cb1));
+    fill_lut(t->lut + DCSB_LUT_CB + 4, 3, dcs94_cb2, NCODES(dcs94_cb2));
+    fill_lut(t->lut + DCSB_LUT_CB + 12, 5, dcs94_cb3, NCODES(dcs94_cb3));
+    fill_lut(t->lut + DCSB_LUT_CB + 44, 7, dcs94_cb4, NCODES(dcs94_cb4));
+    fill_lut(t->lut + DCSB_LUT_CB + 172, 8, dcs94_cb5, NCODES(dcs94_cb5));
+    fill_lut(t->lut + DCSB_LUT_CB + 428, 9, dcs94_cb6, NCODES(dcs94_cb6));
+    fill_lut(t->lut + DCSB_LUT_HDR93, 8, dcs93_hdr, NCODES(dcs93_hdr));
+    fill_lut(t->lut + DCSB_LUT_BB93A + 0, 4, dcs93a_bandbits0, NCODES(dcs93a_bandbits0));
+    fill_lut(t->lut + DCSB_LUT_BB93A + 16, 4, dcs93a_bandbits1, NCODES(dcs93a_bandbits1));
+    fill_lut(t->lut + DCSB_LUT_BB93A + 32, 4, dcs93a_bandbits2, NCODES(dcs93a_bandbits2));
+    fill_lut(t->lut + DCSB_LUT_BB93A + 48, 4, dcs93a_bandbits3, NCODES(dcs93a_bandbits3));
+    fill_lut(t->lut + DCSB_LUT_SC93A, 8, dcs93a_scale, NCODES(dcs93a_scale));
+    for (int i = 0; i < 16; ++i) {
+        t->lut[DCSB_LUT_XLAT + i] = (uint16_t)((dcs94_xlat_lo[i][0] << 8) | dcs94_xlat_lo[i][1]);
+        t->lut[DCSB_LUT_XLAT + 16 + i] = (uint16_t)((dcs94_xlat_mid[i][0] << 8) | dcs94_xlat_mid[i][1]);
+        t->lut[DCSB_LUT_XLAT + 32 + i] = (uint16_t)((dcs94_xlat_hi[i][0] << 8) | dcs94_xlat_hi[i][1]);
+    }
+    for (int i = 0; i < NCODES(dcs94_hdr); ++i)
+        if (dcs94_hdr[i].len > 8) t->long94[t->n_long94++] = DcsbLongCode{ dcs94_hdr[i].code, dcs94_hdr[i].len, dcs94_hdr[i].val, 0 };
+    for (int i = 0; i < NCODES(dcs93_hdr); ++i)
+        if (dcs93_hdr[i].len > 8) t->long93[t->n_long93++] = DcsbLongCode{ dcs93_hdr[i].code, dcs93_hdr[i].len, dcs93_hdr[i].val, 0 };
+    memcpy(t->overlap, dcs_overlap_win, sizeof(t->overlap));
+    for (int p = 0; p < 128; ++p)
+        t->twiddle[p] = ((uint32_t)dcs_twiddle[128 + p] << 16) | dcs_twiddle[p];
+    for (int i = 0; i < 64; ++i) {
+        // twiddle pass coefficients c0 = table[bitrev9(2+4i)], c1 = table[bitrev9(4i)] (DCSDecoderNative.cpp:428-429)
+        const uint16_t c0 = dcs_twiddle[rev_bits(2 + 4 * i, 9)], c1 = dcs_twiddle[rev_bits(4 * i, 9)];
+        t->pretw[i] = ((uint32_t)c0 << 16) | c1;
+    }
+    memcpy(t->pairs93a, dcs93a_pairs, sizeof(t->pairs93a));
+}
+
+// ======================================================================================
+// gain helpers (host side)
+static int calc_exp32(uint32_t x)      // ADSP-2105 EXP on a 32-bit mantissa (DCSDecoderNative.cpp:3447-3459)
+{
+    int res = 0;
+    if (x & 0x80000000u) { while (x & 0x40000000u) { --res; x <<= 1; } }
+    else { while (res > -31 && !(x & 0x40000000u)) { --res; x <<= 1; } }
+    return res;
+}
+
+extern "C" uint16_t dcsb_master_multiplier(int vol)
+{
+    if (vol > 255) vol = 255;
+    if (vol <= 0) return 0;
+    uint32_t x = 0x3fff, y = 0x7d98;       // 0.5 * 0.981201^(255-vol) in 1.15
+    for (int i = 0; i < 8; ++i, vol >>= 1) {
+        if (!(vol & 1)) x = ((x * y) >> 15) & 0xFFFFu;
+        y = ((y * y) >> 15) & 0xFFFFu;
+    }
+    return (uint16_t)(x << 1);
+}
+
+extern "C" uint16_t dcsb_level_multiplier(int level_sum, int os_version, int channel_volume, int max_override)
+{
+    level_sum = std::max(-8191, std::min(8191, level_sum));
+    const uint32_t e = (uint32_t)((level_sum >> 6) & 0x3FF) + 0x80;
+    uint32_t m = os_version == DCSB_OS93A ? 0x7FFFu : ((uint32_t)channel_volume << 7) & 0xFFFFu;
+    if (max_override) m = 0xFFu << 7;
+    uint32_t p = 0x7C94;                     // 0.9733^(2^j) ladder
+    for (int j = 0; j < 8; ++j) {
+        if (!(e & (1u << j))) m = ((m * p) >> 15) & 0xFFFFu;
+        p = ((p * p) >> 15) & 0xFFFFu;
+    }
+    return (uint16_t)(m << 1);
+}
+
+extern "C" int dcsb_gain_stage(const uint16_t mix_mult[8], unsigned active_mask, unsigned max_override_mask,
+                               uint16_t vol_mult, uint16_t eff_mult[8])
+{
+    uint64_t sum = 0;
+    for (int i = 0; i < 8; ++i) {
+        if (max_override_mask & (1u << i)) sum += (uint64_t)mix_mult[i] * 0x7FFE;
+        else if (active_mask & (1u << i)) sum += (uint64_t)mix_mult[i] * vol_mult;
+    }
+    int vs = -(calc_exp32((uint32_t)(sum >> 2)) + 3);
+    vs = std::max(0, std::min(8, vs));
+    for (int i = 0; i < 8; ++i) {
+        const uint64_t v = (max_override_mask & (1u << i)) ? 0x7FFE : vol_mult;
+        eff_mult[i] = (uint16_t)(((((uint64_t)mix_mult[i] * v) << 1) << vs) >> 16);
+    }
+    return vs;
+}
+
+// Per-stream gain schedule of the single-stream protocol: frame 0 still carries the
+// constructor multiplier 0x7FFF (DCSDecoderNative.h:514); the mixing level only takes
+// effect in UpdateMixingLevels at the end of the first main loop (:3042-3121).
+static void stream_gain(const dcsb_stream_desc &d, DcsbStreamRec &r)
+{
+    const uint16_t vol = dcsb_master_multiplier(d.master_volume);
+    uint16_t mix[8], eff[8];
+    for (int i = 0; i < 8; ++i) mix[i] = 0x7FFF;
+    r.vs0 = (uint8_t)dcsb_gain_stage(mix, 1u, 0u, vol, eff);
+    r.mult0 = eff[0];
+    mix[0] = dcsb_level_multiplier((int)d.mixing_level << 6, d.os_version, 0xFF, 0);
+    for (int i = 1; i < 8; ++i) mix[i] = dcsb_level_multiplier(0, d.os_version, 0xFF, 0);
+    r.vs1 = (uint8_t)dcsb_gain_stage(mix, 1u, 0u, vol, eff);
+    r.mult1 = eff[0];
+    r.vs_idle = (uint8_t)dcsb_gain_stage(mix, 0u, 0u, vol, eff);
+}
+
+
+int dcsb_prepare(const dcsb_stream_desc *descs, size_t n, DcsbPrepared *p)
+{
+    p->recs.resize(n);
+    p->host_status.assign(n, 0);
+    p->tiles.clear();
+    p->compressed_bytes = 0;
+    uint64_t off = 0, frames = 0, pcm = 0;
+    std::vector<DcsbTile> t94, t93;
+    for (size_t i = 0; i < n; ++i) {
+        const dcsb_stream_desc &d = descs[i];
+        DcsbStreamRec &r = p->recs[i];
+        memset(&r, 0, sizeof(r));
+        int fmt;
+        switch (d.os_version) {
+        case DCSB_OS94: case DCSB_OS95: fmt = DCSB_FMT_94; break;
+        case DCSB_OS93B: fmt = DCSB_FMT_93; break;
+        case DCSB_OS93A: fmt = (d.nbytes >= 3 && d.data && (d.data[2] & 0x80)) ? DCSB_FMT_93A1 : DCSB_FMT_93; break;
+        default: return DCSB_E_ARG;
+        }
+        r.fmt = (uint8_t)fmt;
+        r.hdr_len = fmt == DCSB_FMT_93A1 ? 1 : 16;
+        r.data_off = off;
+        r.nbytes = d.nbytes;
+        r.frame_base = (uint32_t)frames;
+        r.pcm_off = pcm;
+        // frames rendered = U16 frame count + tail, whatever happens later (rejected and
+        // failing streams render silence), so callers can lay out PCM from the first 2 bytes
+        uint32_t nf = (d.data && d.nbytes >= 2) ? (((uint32_t)d.data[0] << 8) | d.data[1]) : 0;
+        r.out_frames = nf + d.tail_frames;
+        if (!d.data || d.nbytes < 3 || d.nbytes < 2u + r.hdr_len) { p->host_status[i] = DCSB_E_SHORT; nf = 0; }
+        else {
+            if (nf == 0) p->host_status[i] = DCSB_E_EMPTY;
+            memcpy(r.hdr, d.data + 2, r.hdr_len);
+        }
+        r.nframes = (uint16_t)nf;
+        stream_gain(d, r);
+        auto &tl = fmt == DCSB_FMT_94 ? t94 : t93;
+        for (uint32_t f = 0; f < r.out_frames; f += DCSB_TILE_OUT) tl.push_back(DcsbTile{ (uint32_t)i, f });
+        off += ((uint64_t)d.nbytes + 15 + 16) & ~15ull;     // 16-byte aligned, >= 16 bytes of zero padding
+        frames += nf;
+        pcm += (uint64_t)r.out_frames * 240;
+        p->compressed_bytes += d.nbytes;
+    }
+    if (frames > 0xFFFFFFF0ull || t94.size() + t93.size() > 0x7FFFFFF0ull) return DCSB_E_ARG;
+    p->total_frames_in = frames;
+    p->total_out_frames = pcm / 240;
+    p->slab_bytes = (size_t)off + 64;
+    p->ntiles94 = (int)t94.size();
+    p->ntiles93 = (int)t93.size();
+    p->tiles = std::move(t94);
+    p->tiles.insert(p->tiles.end(), t93.begin(), t93.end());
+    return DCSB_OK;
+}
+
+void dcsb_pack_slab(const dcsb_stream_desc *descs, size_t n, const DcsbPrepared *p, uint8_t *slab)
+{
+    const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    auto work = [&](unsigned t) {
+        for (size_t i = t; i < n; i += nt) {
+            const DcsbStreamRec &r = p->recs[i];
+            const uint64_t span = (i + 1 < n ? p->recs[i + 1].data_off : (uint64_t)p->slab_bytes) - r.data_off;
+            if (descs[i].data && descs[i].nbytes) memcpy(slab + r.data_off, descs[i].data, descs[i].nbytes);
+            memset(slab + r.data_off + descs[i].nbytes, 0, span - descs[i].nbytes);
+        }
+    };
+    if (n < 64 || nt == 1) { for (unsigned t = 0; t < nt; ++t) work(t); return; }
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+}

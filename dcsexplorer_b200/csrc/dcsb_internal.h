@@ -1,0 +1,87 @@
+// dcsb200 internal definitions shared by the host API (dcsb_api.cu) and the kernels.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+// frame layout family of a stream
+enum : uint8_t { DCSB_FMT_94 = 0, DCSB_FMT_93 = 1, DCSB_FMT_93A1 = 2 };
+
+// One stream, as the kernels see it (64 bytes).  Read-only on the device.
+struct DcsbStreamRec {
+    uint64_t data_off;      // byte offset of the stream's first byte in the compressed slab (16-byte aligned)
+    uint64_t pcm_off;       // sample offset of the stream's first PCM sample in the output
+    uint32_t nbytes;        // stream bytes
+    uint32_t frame_base;    // index of frame 0 in the frame-checkpoint arrays
+    uint32_t out_frames;    // frames rendered (nFrames + tail)
+    uint16_t nframes;       // frame count from the stream preamble (0 when rejected on the host)
+    uint8_t  fmt;           // DCSB_FMT_*
+    uint8_t  hdr_len;       // 16, or 1 for OS93a type 1
+    uint16_t mult0, mult1;  // effective channel multiplier for frame 0 / frames >= 1 (host gain staging)
+    uint8_t  vs0, vs1;      // volShift for frame 0 / frames >= 1
+    uint8_t  vs_idle;       // volShift once no stream is active (8)
+    uint8_t  pad[1];
+    uint8_t  hdr[16];       // stream header copy
+    uint32_t pad2[2];
+};
+static_assert(sizeof(DcsbStreamRec) == 64, "DcsbStreamRec layout");
+
+// A tile = up to DCSB_TILE_OUT consecutive output frames of one stream, handled by one warp.
+// Lane 0 re-decodes the frame before the tile so the 16-sample overlap is available.
+#define DCSB_TILE_OUT 31
+struct DcsbTile { uint32_t stream; uint32_t first; };
+
+// Peek-LUT block (uint16 entries: len<<8 | value), copied to shared memory by each CTA.
+#define DCSB_LUT_HDR94   0      // 256: 1994 frame-header delta code, 8-bit peek (0 = longer code)
+#define DCSB_LUT_CB      256    // 940: 1994 sample codebooks 1..6 (4+8+32+128+256+512)
+#define DCSB_LUT_HDR93   1196   // 256: 1993 type-1 band-type delta code, 8-bit peek (0 = longer code)
+#define DCSB_LUT_BB93A   1452   // 64:  OS93a band-bits codes, 4 groups x 4-bit peek
+#define DCSB_LUT_SC93A   1516   // 256: OS93a scale-delta code, 8-bit peek
+#define DCSB_LUT_XLAT    1772   // 48:  1994 type-1 band translation, 3 groups x 16: (codebook/width << 8) | scale adjust
+#define DCSB_LUT_WORDS   1820
+
+struct DcsbLongCode { uint32_t code; uint8_t len; uint8_t val; uint16_t pad; };
+
+struct DcsbTables {
+    uint16_t lut[DCSB_LUT_WORDS];
+    uint16_t overlap[16];
+    uint32_t twiddle[128];     // (cos << 16) | (sin & 0xffff), reference table order (bit-reversed partitions)
+    uint32_t pretw[64];        // twiddle pass of the 1994 transform in natural order i: (c0 << 16) | c1
+    uint16_t pairs93a[2048];
+    DcsbLongCode long94[32];   // 1994 header codes longer than 8 bits
+    DcsbLongCode long93[64];   // 1993 header codes longer than 8 bits
+    int n_long94, n_long93;
+};
+
+struct DcsbScanOut {
+    uint32_t *bitpos;          // [total_frames] frame start, bits from the first byte after the stream header
+    uint2    *bt;              // [total_frames] band-type state carried into the frame, 16 x 4 bits
+    int32_t  *status;          // [nstreams]
+    uint32_t *nplay;           // [nstreams] frames that decode before the channel goes silent
+    uint32_t *endbits;         // [nstreams] bit position after the last decoded frame
+    uint8_t  *stopband;        // [nstreams] band at which the reference's error path fired (else 0xFF)
+};
+
+void dcsb_build_tables(DcsbTables *t);   // host
+
+// host-side batch layout (dcsb_host.cpp)
+#include <vector>
+#include "../../include/dcsb200.h"
+struct DcsbPrepared {
+    std::vector<DcsbStreamRec> recs;
+    std::vector<int32_t> host_status;     // host-side rejections (0 = let the scan decide)
+    std::vector<DcsbTile> tiles;          // 1994-family tiles first, then 1993-family
+    int ntiles94 = 0, ntiles93 = 0;
+    uint64_t total_frames_in = 0, total_out_frames = 0, compressed_bytes = 0;
+    size_t slab_bytes = 0;
+};
+// validate + lay out a batch (no CUDA calls); DCSB_OK or DCSB_E_ARG
+int dcsb_prepare(const dcsb_stream_desc *descs, size_t n, DcsbPrepared *p);
+// copy the streams into `slab` (p->slab_bytes bytes) at their 16-byte aligned offsets, zero padded
+void dcsb_pack_slab(const dcsb_stream_desc *descs, size_t n, const DcsbPrepared *p, uint8_t *slab);
+
+cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, int nstreams,
+                             const DcsbTables *tables, DcsbScanOut out, cudaStream_t st);
+// tiles[0..ntiles94) use the 1994 transform, tiles[ntiles94..ntiles94+ntiles93) the 1993 one
+cudaError_t dcsb_launch_decode(const uint8_t *slab, const DcsbStreamRec *streams, const DcsbTile *tiles,
+                               int ntiles94, int ntiles93, const DcsbTables *tables, DcsbScanOut scan,
+                               int16_t *pcm, unsigned long long *checksums, cudaStream_t st);

@@ -1,0 +1,60 @@
+"""CPU simulation of the CUDA kernel bodies (tests/hostsim) against the oracle and the golden
+fixtures: the same dcsb_scan_stream / dcsb_decode_tile code the GPU runs, compiled as C++."""
+import numpy as np
+from conftest import check_against_golden
+from oracle import orc
+import dcsfuzz
+import simutil
+
+
+def test_sim_matches_golden(built, golden):
+    streams = [(it["stream"], it["os"], it["vol"], it["lvl"], it["nframes_out"] - ((it["stream"][0] << 8) | it["stream"][1]))
+               for it in golden.items]
+    pcm, offs, res, bp, bt = simutil.decode_streams(streams)
+    for i, it in enumerate(golden.items):
+        check_against_golden(it, pcm[offs[i]:offs[i] + it["nframes_out"] * 240])
+        assert res[i]["status"] == (-5 if it["stop"] else 0)
+
+
+def test_sim_fuzz_vs_oracle(built):
+    rng = np.random.default_rng(77)
+    streams = []
+    for seed in range(4):
+        for os_, d, label in dcsfuzz.corpus(seed + 50, n_each=2, nframes=int(rng.integers(1, 80))):
+            streams.append((d, os_, int(rng.integers(0, 256)), int(rng.integers(0, 256)), int(rng.integers(0, 5))))
+    pcm, offs, res, bp, bt = simutil.decode_streams(streams)
+    fbase = 0
+    for i, (d, os_, vol, lvl, tail) in enumerate(streams):
+        nf = (d[0] << 8) | d[1]
+        want, rc = orc.decode(d, os_, vol, lvl, nf + tail)
+        assert np.array_equal(pcm[offs[i]:offs[i] + want.size], want), (i, hex(os_))
+        orc_rc, obp, obt, ostop = orc.scan(d, os_)
+        assert np.array_equal(bp[fbase:fbase + nf], obp[:nf])
+        assert np.array_equal(bt[fbase:fbase + nf], obt[:nf])
+        # checksum definition: sum (uint16)s[i] * (2i+1) mod 2^64
+        s = want.astype(np.uint16).astype(np.uint64)
+        w = (2 * np.arange(s.size, dtype=np.uint64) + 1)
+        assert res[i]["checksum"] == int((s * w).sum(dtype=np.uint64))
+        assert res[i]["stream_bytes"] == 2 + (1 if (os_ == 0x9301 and d[2] & 0x80) else 16) + (int(obp[nf]) + 7) // 8
+        fbase += nf
+
+
+def test_sim_edge_cases(built):
+    empty = bytes([0, 0] + [0x10] * 16)
+    short = bytes([0, 3, 0x10])
+    nobands = bytes([0, 4] + [0x7F] * 16)
+    ok = dcsfuzz.fuzz94(np.random.default_rng(1), 31 * 3, type1=1)       # exactly three tiles
+    one = dcsfuzz.fuzz94(np.random.default_rng(2), 1, type1=0)
+    trunc = ok[: len(ok) // 2]
+    streams = [(empty, 0x9400, 255, 100, 2), (short, 0x9400, 255, 100, 2), (nobands, 0x9400, 255, 100, 1),
+               (ok, 0x9400, 255, 100, 0), (one, 0x9400, 255, 100, 3), (trunc, 0x9400, 255, 100, 2)]
+    pcm, offs, res, bp, bt = simutil.decode_streams(streams)
+    assert [r["status"] for r in res[:5]] == [-1, -4, 0, 0, 0]
+    assert res[5]["status"] in (-2, -3, -5)
+    for i, (d, os_, vol, lvl, tail) in enumerate(streams):
+        nf = ((d[0] << 8) | d[1]) if i != 1 else 3
+        if i == 1:
+            assert not pcm[offs[i]:offs[i] + (nf + tail) * 240].any()
+            continue
+        want, rc = orc.decode(d, os_, vol, lvl, nf + tail)
+        assert np.array_equal(pcm[offs[i]:offs[i] + want.size], want), i
