@@ -329,7 +329,7 @@ DCSB_HD int dcsb_walk93a1(const DcsbWalkCtx &cx, uint32_t &pos, int16_t *row)
         if (DECODE) {
             uint32_t sf = 0x8000u;
             for (int i = 0; i < (sc & 3); ++i) sf = (sf * 0x9838u) >> 15;    // :2986-2991
-            sf <<= (sc >> 2);
+            sf <<= ((sc >> 2) & 31);    // count >= 32 only on malformed streams: follow the x86 build of the reference
             sf = ((sf >> 16) * cx.mult) >> 15;                           // :2995
             const int sfs = dcsb_s16(sf);
             const uint16_t *base = cx.tab->pairs93a + (2 << bits);

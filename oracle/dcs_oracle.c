@@ -283,7 +283,7 @@ static int walk93a1(const uint8_t *s, uint32_t *ppos, uint16_t mult, uint16_t *f
         prvscale = sc - bits * 2;
         uint32_t sf = 0x8000;
         for (int i = 0; i < (sc & 3); ++i) sf = (sf * 0x9838u) >> 15;    /* :2986-2991 */
-        sf <<= (sc >> 2);
+        sf <<= ((sc >> 2) & 31);   /* x86 shift-count masking = the reference as compiled (count >= 32 only on malformed streams) */
         sf = ((sf >> 16) * mult) >> 15;                              /* :2995 */
         const uint16_t *base = &dcs93a_pairs[2 << bits];
         for (int i = 0; i < ninputs; ++i) {
