@@ -324,7 +324,7 @@ def main():
     resarr = (dx.Result * len(streams))()
     L = ctx._L
     e2e_ms = []
-    for i in range(1 + a.e2e_steps):
+    for i in range((1 + a.e2e_steps) if a.e2e_steps > 0 else 0):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         rc = L.dcsb_decode_streams(ctx._h, descs, len(streams), h_pcm.data_ptr(), None, resarr)
@@ -333,12 +333,12 @@ def main():
             raise SystemExit("dcsb_decode_streams failed: %d" % rc)
         if i > 0:
             e2e_ms.append((t1 - t0) * 1e3)
-    e2e_t = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device="cuda")
+    e2e_t = torch.tensor([float(np.mean(e2e_ms)) if e2e_ms else float("inf")], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = world * total_samples / (float(e2e_t.item()) * 1e-3) / 1e6
     # spot-check the e2e output against the resident-path output
-    same = bool(torch.equal(h_pcm[:FRAME * 64], d_pcm[:FRAME * 64].cpu()))
+    same = bool(torch.equal(h_pcm[:FRAME * 64], d_pcm[:FRAME * 64].cpu())) if e2e_ms else None
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()

@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdcsb200.so")
+LIB_PATH = os.environ.get("DCSB200_LIB") or os.path.join(HERE, "libdcsb200.so")
 
 OS93A, OS93B, OS94, OS95 = 0x9301, 0x9302, 0x9400, 0x9500
 OK, E_EMPTY, E_TRUNCATED, E_BANDTYPE, E_SHORT, E_STOPPED = 0, -1, -2, -3, -4, -5

@@ -66,7 +66,20 @@ struct DcsbBits {
 };
 
 DCSB_HD int dcsb_sext(uint32_t v, int n) { return (int)(v << (32 - n)) >> (32 - n); }
-DCSB_HD int dcsb_sat16(int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); }
+// 16-bit saturation.  On the device the clamp goes through opaque min/max PTX: written as
+// plain C++ on values that came from int16, nvcc 12.9 narrows `sat16(x + (-sat16(y)))` to a
+// 16-bit ssub.sat whose negated operand wraps at -32768 (wrong PCM on loud frames; the -G
+// build was right).  ptxas still fuses add + min into VIADDMNMX.
+DCSB_HD int dcsb_sat16(int v)
+{
+#if DCSB_DEVICE_PASS
+    int r;
+    asm("min.s32 %0, %1, 32767;\n\tmax.s32 %0, %0, -32768;" : "=r"(r) : "r"(v));
+    return r;
+#else
+    return v < -32768 ? -32768 : (v > 32767 ? 32767 : v);
+#endif
+}
 DCSB_HD int dcsb_s16(uint32_t v) { return (int)(int16_t)(uint16_t)v; }
 
 // ADSP-2105 multiply/accumulate + round in 32-bit wrap-around arithmetic:
@@ -487,7 +500,7 @@ DCSB_HD void dcsb_transform93_warp(uint32_t *c, const DcsbTables *tab)
             unsigned long long mr = 0x0D490000ull;
             int mf = dcsb_s16(AR);
             for (int t = 0; t < 5; ++t) {
-                mr += (unsigned long long)(((long long)k[t] * (long long)mf) << 1);
+                mr += (unsigned long long)((long long)k[t] * (long long)mf * 2);
                 if (t < 4) mf = dcsb_mac_round<false>(0, 0, dcsb_s16(AR), mf);
             }
             if (exponent & 1) {

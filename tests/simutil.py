@@ -15,7 +15,7 @@ def lib():
     if _LIB is None:
         d = os.path.join(_HERE, "hostsim")
         subprocess.check_call(["make", "-s", "-C", d])
-        L = C.CDLL(os.path.join(d, "libhostsim.so"))
+        L = C.CDLL(os.environ.get("HOSTSIM_LIB", os.path.join(d, "libhostsim.so")))
         L.hostsim_decode_streams.restype = C.c_int
         L.hostsim_decode_streams.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB = L

@@ -1,0 +1,18 @@
+#!/bin/bash
+# Run on the GPU box (under gpurun): parity tests, bench line, ncu launch list and one
+# `--set full` capture of each kernel.  Everything lands in gpurun_out/<tag>_*.
+# usage: tools/gpu_profile.sh <tag> [bench args...]
+set -u
+TAG=${1:-run}; shift || true
+OUT=gpurun_out
+mkdir -p $OUT
+python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee $OUT/${TAG}_pytest.txt
+python bench.py --steps 10 --warmup 3 "$@" > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+tail -c 2500 $OUT/${TAG}_bench.json; tail -3 $OUT/${TAG}_bench.err
+# launch list (cold-cache, serialised: compare shares)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/${TAG}_launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 0 "$@" > $OUT/${TAG}_ncu_launch.log 2>&1
+# full capture of our kernels (skip the warm-up launches)
+ncu --set full --clock-control none --import-source on -k regex:dcsb_ -s 6 -c 3 -f -o $OUT/${TAG}_prof \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 0 "$@" > $OUT/${TAG}_ncu_full.log 2>&1
+ls -la $OUT | tail -12
