@@ -12,9 +12,39 @@
 #include "dcsb_internal.h"
 
 // ======================================================================================
+// grow-only buffer (device or pinned host) owned by a context
+struct DcsbBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes, bool host)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { if (host) cudaFreeHost(p); else cudaFree(p); p = nullptr; cap = 0; }
+        const size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = host ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release(bool host) { if (p) { if (host) cudaFreeHost(p); else cudaFree(p); } p = nullptr; cap = 0; }
+};
+
+// One pipeline lane of dcsb_decode_streams: a CUDA stream plus everything one chunk of
+// streams needs, kept across calls so that the steady state does no allocation.
+#define DCSB_MAX_LANES 8
+struct DcsbLane {
+    cudaStream_t st = nullptr;
+    DcsbBuf h_slab, h_res;                                   // pinned
+    DcsbBuf d_slab, d_recs, d_tiles, d_bitpos, d_bt, d_hdrbits, d_status, d_nplay, d_endbits, d_stopband, d_csum, d_pcm;
+    DcsbPrepared prep;
+    size_t first = 0, count = 0;
+    uint64_t pcm_base = 0;                                   // sample offset of the chunk in the packed output
+    bool direct_pcm = false;
+};
+
 struct dcsb_ctx {
     int device = 0;
     DcsbTables *d_tables = nullptr;
+    DcsbLane lanes[DCSB_MAX_LANES];
     std::string err;
 };
 
@@ -78,6 +108,12 @@ extern "C" void dcsb_destroy(dcsb_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    for (DcsbLane &l : ctx->lanes) {
+        if (l.st) { cudaStreamSynchronize(l.st); cudaStreamDestroy(l.st); }
+        l.h_slab.release(true); l.h_res.release(true);
+        for (DcsbBuf *b : { &l.d_slab, &l.d_recs, &l.d_tiles, &l.d_bitpos, &l.d_bt, &l.d_hdrbits, &l.d_status, &l.d_nplay,
+                            &l.d_endbits, &l.d_stopband, &l.d_csum, &l.d_pcm }) b->release(false);
+    }
     cudaFree(ctx->d_tables);
     delete ctx;
 }
@@ -89,7 +125,7 @@ extern "C" void dcsb_batch_destroy(dcsb_batch *b)
     if (!b) return;
     cudaSetDevice(b->ctx->device);
     cudaFree(b->d_slab); cudaFree(b->d_recs); cudaFree(b->d_tiles);
-    cudaFree(b->scan.bitpos); cudaFree(b->scan.bt); cudaFree(b->scan.status); cudaFree(b->scan.nplay);
+    cudaFree(b->scan.bitpos); cudaFree(b->scan.bt); cudaFree(b->scan.hdrbits); cudaFree(b->scan.status); cudaFree(b->scan.nplay);
     cudaFree(b->scan.endbits); cudaFree(b->scan.stopband);
     cudaFree(b->d_pcm); cudaFree(b->d_checksums);
     for (auto &e : b->ev) if (e) cudaEventDestroy(e);
@@ -107,7 +143,7 @@ extern "C" int dcsb_batch_create(dcsb_ctx *ctx, const dcsb_stream_desc *descs, s
 
     DcsbPrepared prep;
     {
-        int rc = dcsb_prepare(descs, n, &prep);
+        int rc = dcsb_prepare(descs, n, &prep, nullptr, 0);
         if (rc != DCSB_OK) { delete b; return fail(ctx, rc, "dcsb_batch_create: unknown os_version or batch too large"); }
     }
     b->recs = prep.recs;
@@ -119,7 +155,7 @@ extern "C" int dcsb_batch_create(dcsb_ctx *ctx, const dcsb_stream_desc *descs, s
     b->total_out_frames = prep.total_out_frames;
     b->compressed_bytes = prep.compressed_bytes;
     b->slab_bytes = prep.slab_bytes;
-    const uint64_t frames = b->total_frames_in;
+    const uint64_t frames = prep.total_checkpoints;
 
     // pack the compressed slab in pinned memory (multi-threaded), one H2D copy
     uint8_t *h_slab = nullptr;
@@ -137,6 +173,7 @@ extern "C" int dcsb_batch_create(dcsb_ctx *ctx, const dcsb_stream_desc *descs, s
     CKB(cudaMemcpy(b->d_tiles, b->tiles.data(), b->tiles.size() * sizeof(DcsbTile), cudaMemcpyHostToDevice), "H2D tiles");
     CKB(cudaMalloc(&b->scan.bitpos, std::max<uint64_t>(1, frames) * sizeof(uint32_t)), "cudaMalloc(bitpos)");
     CKB(cudaMalloc(&b->scan.bt, std::max<uint64_t>(1, frames) * sizeof(uint2)), "cudaMalloc(bt)");
+    CKB(cudaMalloc(&b->scan.hdrbits, std::max<uint64_t>(1, frames) * sizeof(uint16_t)), "cudaMalloc(hdrbits)");
     CKB(cudaMalloc(&b->scan.status, std::max<size_t>(1, n) * sizeof(int32_t)), "cudaMalloc(status)");
     CKB(cudaMalloc(&b->scan.nplay, std::max<size_t>(1, n) * sizeof(uint32_t)), "cudaMalloc(nplay)");
     CKB(cudaMalloc(&b->scan.endbits, std::max<size_t>(1, n) * sizeof(uint32_t)), "cudaMalloc(endbits)");
@@ -173,7 +210,7 @@ extern "C" int dcsb_batch_decode(dcsb_batch *b, void *d_pcm, void *cuda_stream)
     if (b->n == 0) return DCSB_OK;
     CK(cudaMemsetAsync(b->d_checksums, 0, b->n * sizeof(unsigned long long), st), "memset checksums");
     CK(cudaEventRecord(b->ev[0], st), "event");
-    CK(dcsb_launch_scan(b->d_slab, b->d_recs, (int)b->n, ctx->d_tables, b->scan, st), "scan kernel launch");
+    CK(dcsb_launch_scan(b->d_slab, b->d_recs, (int)b->n, 0, ctx->d_tables, b->scan, st), "scan kernel launch");
     CK(cudaEventRecord(b->ev[1], st), "event");
     CK(dcsb_launch_decode(b->d_slab, b->d_recs, b->d_tiles, b->ntiles94, b->ntiles93, ctx->d_tables, b->scan,
                           pcm, b->d_checksums, st), "decode kernel launch");
@@ -245,28 +282,152 @@ extern "C" int dcsb_batch_read_scan(dcsb_batch *b, size_t i, uint32_t *bitpos, u
     return (int)nf;
 }
 
+// ---- one-shot decode with host buffers: a pipeline of stream chunks -------------------
+// Each chunk runs on its own lane (CUDA stream): [pack ->] H2D -> scan -> decode -> D2H.
+// Chunks overlap freely: while chunk c's PCM drains over PCIe, chunk c+1 decodes and c+2
+// uploads.  Inputs that already sit together in pinned host memory are uploaded straight
+// from where they are (the kernels accept any byte alignment); everything else is packed
+// into the lane's pinned staging slab by a few host threads.  PCM goes straight into the
+// caller's buffer when that is pinned and tightly packed.
+static bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static int lane_submit(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs, int16_t *pcm_out, bool pcm_pinned_packed, int scan_lanes)
+{
+    const size_t n = l.count;
+    const dcsb_stream_desc *d = descs + l.first;
+    if (!l.st) CK(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking), "cudaStreamCreate");
+    // in-place upload? (all streams close together inside one pinned host allocation)
+    const uint8_t *lo = nullptr, *hi = nullptr;
+    uint64_t sum = 0;
+    bool have_all = true;
+    for (size_t i = 0; i < n; ++i) {
+        if (!d[i].data || !d[i].nbytes) { have_all = false; break; }
+        if (!lo || d[i].data < lo) lo = d[i].data;
+        if (!hi || d[i].data + d[i].nbytes > hi) hi = d[i].data + d[i].nbytes;
+        sum += d[i].nbytes;
+    }
+    const bool in_place = have_all && n && (uint64_t)(hi - lo) <= sum + sum / 4 + 4096 && is_pinned(lo) && is_pinned(hi - 1);
+    int rc = dcsb_prepare(d, n, &l.prep, in_place ? lo : nullptr, in_place ? (size_t)(hi - lo) : 0);
+    if (rc != DCSB_OK) return fail(ctx, rc, "dcsb_decode_streams: unknown os_version or batch too large");
+    const DcsbPrepared &p = l.prep;
+    const uint64_t ck = std::max<uint64_t>(1, p.total_checkpoints), nn = std::max<size_t>(1, n);
+#define ENS(buf, bytes, host, what) do { cudaError_t e_ = (buf).ensure((bytes), (host)); if (e_ != cudaSuccess) return fail(ctx, DCSB_E_NOMEM, what, e_); } while (0)
+    ENS(l.d_slab, p.slab_bytes, false, "cudaMalloc(slab)");
+    ENS(l.d_recs, nn * sizeof(DcsbStreamRec), false, "cudaMalloc(recs)");
+    ENS(l.d_tiles, std::max<size_t>(1, p.tiles.size()) * sizeof(DcsbTile), false, "cudaMalloc(tiles)");
+    ENS(l.d_bitpos, ck * 4, false, "cudaMalloc(bitpos)");
+    ENS(l.d_bt, ck * 8, false, "cudaMalloc(bt)");
+    ENS(l.d_hdrbits, ck * 2, false, "cudaMalloc(hdrbits)");
+    ENS(l.d_status, nn * 4, false, "cudaMalloc(status)");
+    ENS(l.d_nplay, nn * 4, false, "cudaMalloc(nplay)");
+    ENS(l.d_endbits, nn * 4, false, "cudaMalloc(endbits)");
+    ENS(l.d_stopband, nn, false, "cudaMalloc(stopband)");
+    ENS(l.d_csum, nn * 8, false, "cudaMalloc(checksums)");
+    ENS(l.d_pcm, std::max<uint64_t>(2, p.total_out_frames * 480), false, "cudaMalloc(pcm)");
+    ENS(l.h_res, nn * 20, true, "cudaMallocHost(results)");
+    if (n == 0) return DCSB_OK;
+    if (in_place) {
+        const size_t span = (size_t)(hi - lo);
+        CK(cudaMemcpyAsync(l.d_slab.p, lo, span, cudaMemcpyHostToDevice, l.st), "H2D streams (in place)");
+        CK(cudaMemsetAsync((uint8_t *)l.d_slab.p + span, 0, p.slab_bytes - span, l.st), "memset slab tail");
+    } else {
+        ENS(l.h_slab, p.slab_bytes, true, "cudaMallocHost(slab)");
+        dcsb_pack_slab(d, n, &p, (uint8_t *)l.h_slab.p);
+        CK(cudaMemcpyAsync(l.d_slab.p, l.h_slab.p, p.slab_bytes, cudaMemcpyHostToDevice, l.st), "H2D slab");
+    }
+#undef ENS
+    CK(cudaMemcpyAsync(l.d_recs.p, p.recs.data(), n * sizeof(DcsbStreamRec), cudaMemcpyHostToDevice, l.st), "H2D recs");
+    CK(cudaMemcpyAsync(l.d_tiles.p, p.tiles.data(), p.tiles.size() * sizeof(DcsbTile), cudaMemcpyHostToDevice, l.st), "H2D tiles");
+    CK(cudaMemsetAsync(l.d_csum.p, 0, n * 8, l.st), "memset checksums");
+    DcsbScanOut so{ (uint32_t *)l.d_bitpos.p, (uint2 *)l.d_bt.p, (uint16_t *)l.d_hdrbits.p, (int32_t *)l.d_status.p,
+                    (uint32_t *)l.d_nplay.p, (uint32_t *)l.d_endbits.p, (uint8_t *)l.d_stopband.p };
+    CK(dcsb_launch_scan((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p, (int)n, scan_lanes, ctx->d_tables, so, l.st), "scan kernel launch");
+    CK(dcsb_launch_decode((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p, (const DcsbTile *)l.d_tiles.p,
+                          p.ntiles94, p.ntiles93, ctx->d_tables, so, (int16_t *)l.d_pcm.p, (unsigned long long *)l.d_csum.p, l.st),
+       "decode kernel launch");
+    l.direct_pcm = pcm_pinned_packed;
+    if (l.direct_pcm)
+        CK(cudaMemcpyAsync(pcm_out + l.pcm_base, l.d_pcm.p, p.total_out_frames * 480, cudaMemcpyDeviceToHost, l.st), "D2H pcm");
+    uint8_t *hr = (uint8_t *)l.h_res.p;
+    CK(cudaMemcpyAsync(hr, l.d_status.p, n * 4, cudaMemcpyDeviceToHost, l.st), "D2H status");
+    CK(cudaMemcpyAsync(hr + nn * 4, l.d_nplay.p, n * 4, cudaMemcpyDeviceToHost, l.st), "D2H nplay");
+    CK(cudaMemcpyAsync(hr + nn * 8, l.d_endbits.p, n * 4, cudaMemcpyDeviceToHost, l.st), "D2H endbits");
+    CK(cudaMemcpyAsync(hr + nn * 12, l.d_csum.p, n * 8, cudaMemcpyDeviceToHost, l.st), "D2H checksums");
+    return DCSB_OK;
+}
+
 extern "C" int dcsb_decode_streams(dcsb_ctx *ctx, const dcsb_stream_desc *descs, size_t n,
                                    int16_t *pcm_out, const uint64_t *pcm_offsets, dcsb_result *results)
 {
     if (!ctx || (!descs && n) || (!pcm_out && n)) return fail(ctx, DCSB_E_ARG, "dcsb_decode_streams: bad argument");
-    dcsb_batch *b = nullptr;
-    int rc = dcsb_batch_create(ctx, descs, n, &b);
-    if (rc != DCSB_OK) return rc;
-    rc = dcsb_batch_decode(b, nullptr, nullptr);
-    if (rc == DCSB_OK) rc = dcsb_batch_results(b, nullptr, results);
-    if (rc == DCSB_OK && n) {
-        bool packed = true;
-        if (pcm_offsets)
-            for (size_t i = 0; i < n && packed; ++i) packed = pcm_offsets[i] == b->recs[i].pcm_off;
-        cudaError_t e = cudaSuccess;
-        if (packed) e = cudaMemcpy(pcm_out, b->d_pcm, b->total_out_frames * 480, cudaMemcpyDeviceToHost);
-        else
-            for (size_t i = 0; i < n && e == cudaSuccess; ++i)
-                e = cudaMemcpyAsync(pcm_out + pcm_offsets[i], b->d_pcm + b->recs[i].pcm_off,
-                                    (size_t)b->recs[i].out_frames * 480, cudaMemcpyDeviceToHost, nullptr);
-        if (e == cudaSuccess) e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) rc = fail(ctx, DCSB_E_CUDA, "D2H pcm", e);
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (n == 0) return DCSB_OK;
+    // output layout: tightly packed unless the caller's offsets say otherwise
+    std::vector<uint64_t> off(n + 1, 0);
+    bool packed = true;
+    for (size_t i = 0; i < n; ++i) {
+        if (descs[i].os_version != DCSB_OS94 && descs[i].os_version != DCSB_OS95 && descs[i].os_version != DCSB_OS93A &&
+            descs[i].os_version != DCSB_OS93B)
+            return fail(ctx, DCSB_E_ARG, "dcsb_decode_streams: unknown os_version");
+        const uint32_t nf = (descs[i].data && descs[i].nbytes >= 2) ? (((uint32_t)descs[i].data[0] << 8) | descs[i].data[1]) : 0;
+        off[i + 1] = off[i] + (uint64_t)(nf + descs[i].tail_frames) * 240;
+        if (pcm_offsets && pcm_offsets[i] != off[i]) packed = false;
     }
-    dcsb_batch_destroy(b);
+    const bool direct = packed && off[n] && is_pinned(pcm_out) && is_pinned(pcm_out + off[n] - 1);
+    // chunks of about equal PCM size; few enough that every chunk still fills the GPU
+    const uint64_t total = off[n];
+    int nchunks = (int)std::min<uint64_t>(DCSB_MAX_LANES, std::max<uint64_t>(1, total / (48ull << 20)));
+    nchunks = (int)std::min<size_t>((size_t)nchunks, std::max<size_t>(1, n / 64));
+    int used = 0, rc = DCSB_OK;
+    size_t i0 = 0;
+    for (int c = 0; c < nchunks && i0 < n && rc == DCSB_OK; ++c) {
+        const uint64_t goal = total * (uint64_t)(c + 1) / (uint64_t)nchunks;
+        size_t i1 = i0 + 1;
+        while (i1 < n && (c == nchunks - 1 || off[i1] < goal)) ++i1;
+        DcsbLane &l = ctx->lanes[used++];
+        l.first = i0;
+        l.count = i1 - i0;
+        l.pcm_base = off[i0];
+        rc = lane_submit(ctx, l, descs, pcm_out, direct, dcsb_scan_lanes((int)std::min<size_t>(n, 0x7FFFFFFF)));
+        i0 = i1;
+    }
+    // drain
+    for (int c = 0; c < used; ++c) {
+        DcsbLane &l = ctx->lanes[c];
+        cudaError_t e = cudaStreamSynchronize(l.st);
+        if (e != cudaSuccess && rc == DCSB_OK) rc = fail(ctx, DCSB_E_CUDA, "dcsb_decode_streams: stream sync (kernel failure?)", e);
+        if (rc != DCSB_OK) continue;
+        const size_t nn = std::max<size_t>(1, l.count);
+        if (!l.direct_pcm) {
+            if (packed) e = cudaMemcpy(pcm_out + l.pcm_base, l.d_pcm.p, l.prep.total_out_frames * 480, cudaMemcpyDeviceToHost);
+            else
+                for (size_t i = 0; i < l.count && e == cudaSuccess; ++i)
+                    e = cudaMemcpy(pcm_out + pcm_offsets[l.first + i], (int16_t *)l.d_pcm.p + l.prep.recs[i].pcm_off,
+                                   (size_t)l.prep.recs[i].out_frames * 480, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) { rc = fail(ctx, DCSB_E_CUDA, "D2H pcm", e); continue; }
+        }
+        if (results) {
+            const uint8_t *hr = (const uint8_t *)l.h_res.p;
+            const int32_t *st = (const int32_t *)hr;
+            const uint32_t *np = (const uint32_t *)(hr + nn * 4), *eb = (const uint32_t *)(hr + nn * 8);
+            const unsigned long long *cs = (const unsigned long long *)(hr + nn * 12);
+            for (size_t i = 0; i < l.count; ++i) {
+                dcsb_result &r = results[l.first + i];
+                const int32_t hs = l.prep.host_status[i];
+                r.status = hs ? hs : st[i];
+                r.frames = l.prep.recs[i].out_frames;
+                r.frames_decoded = np[i];
+                r.stream_bytes = hs ? 0 : 2 + l.prep.recs[i].hdr_len + (eb[i] + 7) / 8;
+                unsigned long long c8;
+                memcpy(&c8, cs + i, 8);
+                r.checksum = c8;
+            }
+        }
+    }
     return rc;
 }

@@ -141,82 +141,6 @@ struct DcsbWalkCtx {
     int zero_from;             // bands >= this contribute nothing (the reference's error path)
 };
 
-// ======================= 1994+ frame (:1679-2261) =====================================
-// DECODE=false: advance pos/bt only (frame-boundary scan).  stop_band receives the band
-// index at which the reference raises channel.stop (:2213-2218), else stays untouched.
-template <bool DECODE>
-DCSB_HD int dcsb_walk94(const DcsbWalkCtx &cx, uint32_t &pos, uint64_t &bt, int16_t *row, int &stop_band)
-{
-    const uint8_t *hdr = cx.hdr;
-    const uint16_t *lut = cx.lut;
-    const int type1 = hdr[0] >> 7;
-    const int sub = ((hdr[1] & 0x80) >> 6) | ((hdr[2] & 0x80) >> 7);
-    // scale pre-adjust for bands 0..2 comes from the PREVIOUS frame's band types (:1744-1773)
-    int preadj[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        int t = (int)((bt >> (4 * i)) & 15);
-        preadj[i] = t < 4 ? 0 : (sub == 0 ? 1 : (t > 7 ? 4 : t - 3));
-    }
-    // frame header: one Huffman-coded delta per populated band (:1780-1834)
-    for (int i = 0; i < 16 && (hdr[i] & 0x7F) != 0x7F; ++i) {
-        uint32_t e = lut[DCSB_LUT_HDR94 + cx.rd.peek(pos, 8)];
-        int v;
-        if (e) { pos += e >> 8; v = (int)(e & 0xFF); }
-        else v = dcsb_long_code(cx.rd, pos, cx.tab->long94, cx.tab->n_long94);
-        int nbt = (int)((bt >> (4 * i)) & 15) + v - 0x2E;
-        if (v < 0 || nbt < 0 || nbt > 15) return DCSB_WALK_BANDTYPE;
-        bt = (bt & ~(15ull << (4 * i))) | ((uint64_t)nbt << (4 * i));
-    }
-    int old1 = 0;
-    if (DECODE) old1 = row[1];
-    int idx = 1;
-    for (int b = 0; b < 16; ++b) {
-        int hb = hdr[b] & 0x7F;
-        if (hb == 0x7F) break;
-        int count = b == 0 ? 7 : (b == 1 ? 8 : (b == 15 ? 32 : 16));    // :1848-1850
-        int inc = 1;
-        if (hb & 0x40) { inc = 2; count >>= 1; }                         // :1858-1862
-        int code = (int)((bt >> (4 * b)) & 15);
-        if (code == 0) { idx += count; continue; }                       // :1878-1887
-        int sc = hb;
-        if (type1) {                                                     // :1907-1961
-            uint32_t x = lut[DCSB_LUT_XLAT + (b < 3 ? 0 : (b < 6 ? 16 : 32)) + code];
-            if (b < 3) hb += preadj[b];
-            sc = hb + (int)(x & 0xFF);
-            code = (int)(x >> 8);
-        }
-        const uint32_t scale = dcsb_scale_factor(sc);
-        const bool add = DECODE && b < cx.zero_from;
-        if (code <= 6) {                                                 // :1992-2226
-            const int maxw = code <= 2 ? code + 1 : (code == 3 ? 5 : code + 3);       // 2,3,5,7,8,9
-            const int ofs = DCSB_LUT_CB + (code == 1 ? 0 : code == 2 ? 4 : code == 3 ? 12 : code == 4 ? 44 : code == 5 ? 172 : 428);
-            const int ref = 1 << (code - 1);
-            for (int i = count; i > 0; --i) {
-                uint32_t e = lut[ofs + cx.rd.peek(pos, maxw)];
-                pos += e >> 8;
-                int v = (int)(e & 0xFF);
-                if (v & 0x80) {
-                    if (i >= 2) { idx += 2 * inc; --i; }
-                    else { if (stop_band > b) stop_band = b; idx += inc; }
-                } else {
-                    if (add) dcsb_add_bin(row, idx, v - ref, scale, cx.mult);
-                    idx += inc;
-                }
-            }
-        } else {                                                         // :2227-2234
-            for (int i = 0; i < count; ++i) {
-                int v = (int)(int16_t)dcsb_sext(cx.rd.peek(pos, code), code);
-                pos += code;
-                if (add) dcsb_add_bin(row, idx, v, scale, cx.mult);
-                idx += inc;
-            }
-        }
-    }
-    if (DECODE) dcsb_fix_bin01(row, old1);
-    return DCSB_WALK_OK;
-}
-
 // ======================= 1993 frame (:2293-2684) =======================================
 // `row` is only touched in DECODE mode.
 template <bool DECODE>
@@ -369,7 +293,7 @@ DCSB_HD int dcsb_walk93a1(const DcsbWalkCtx &cx, uint32_t &pos, int16_t *row)
 template <bool DECODE>
 DCSB_HD int dcsb_walk(int fmt, const DcsbWalkCtx &cx, uint32_t &pos, uint64_t &bt, int16_t *row, int &stop_band)
 {
-    if (fmt == DCSB_FMT_94) return dcsb_walk94<DECODE>(cx, pos, bt, row, stop_band);
+    // (the 1994 layout never comes here: dcsb_fast94.cuh)
     if (fmt == DCSB_FMT_93) return dcsb_walk93<DECODE>(cx, pos, bt, row);
     return dcsb_walk93a1<DECODE>(cx, pos, row);
 }
@@ -562,7 +486,8 @@ DCSB_HD DcsbBits dcsb_make_reader(const uint8_t *slab, const DcsbStreamRec &s)
     return rd;
 }
 
-// K1 body: one thread walks one stream (lengths only) and writes a checkpoint per frame.
+// K1 body (1993 family; the 1994 layout has its own fast walker in dcsb_fast94.cuh): one
+// thread walks one stream (lengths only) and writes a checkpoint per frame + the end entry.
 DCSB_HD void dcsb_scan_stream(const uint8_t *slab, const DcsbStreamRec *streams, int si,
                               const DcsbTables *tab, const uint16_t *lut, const DcsbScanOut &out)
 {
@@ -583,14 +508,20 @@ DCSB_HD void dcsb_scan_stream(const uint8_t *slab, const DcsbStreamRec *streams,
         const uint32_t nbits = (s.nbytes - 2 - s.hdr_len) * 8u;
         uint64_t bt = 0;                           // InitStreamPlayback zeroes the band types (:1640)
         nplay = s.nframes;
-        for (uint32_t f = 0; f < s.nframes; ++f) {
+        uint32_t f = 0;
+        for (; f < s.nframes; ++f) {
             out.bitpos[s.frame_base + f] = pos;
             out.bt[s.frame_base + f] = make_uint2((uint32_t)bt, (uint32_t)(bt >> 32));
+            out.hdrbits[s.frame_base + f] = 0;
             int sb = 99;
             int rc = dcsb_walk<false>(s.fmt, cx, pos, bt, nullptr, sb);
             if (rc == 0 && pos > nbits) rc = -2;   // DCSB_E_TRUNCATED
             if (rc) { status = rc; nplay = f; break; }
-            if (sb != 99) { status = -5; nplay = f + 1; stopband = sb; break; }   // DCSB_E_STOPPED
+            if (sb != 99) { status = -5; nplay = f + 1; stopband = sb; ++f; break; }   // DCSB_E_STOPPED
+        }
+        if (status == 0 || status == -5) {
+            out.bitpos[s.frame_base + f] = pos;
+            out.bt[s.frame_base + f] = make_uint2((uint32_t)bt, (uint32_t)(bt >> 32));
         }
     }
     out.status[si] = status;

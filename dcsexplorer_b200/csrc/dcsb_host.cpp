@@ -12,6 +12,18 @@
 
 // ======================================================================================
 // tables: prefix-code lists (dcs_tables.h) -> peek LUTs
+// 1994 sample codebook k: entry = code length << 12 | 'two zeros' flag << 11 | signed value (raw - 2^(k-1))
+static void fill_cb94(uint16_t *lut, int peek_bits, const dcs_code_t *codes, int n, int k)
+{
+    for (int i = 0; i < n; ++i) {
+        const int rep = 1 << (peek_bits - codes[i].len);
+        const uint32_t base = codes[i].code << (peek_bits - codes[i].len);
+        const bool dz = (codes[i].val & 0x80) != 0;
+        const int v = dz ? 0 : (int)codes[i].val - (1 << (k - 1));
+        for (int r = 0; r < rep; ++r) lut[base + r] = (uint16_t)((codes[i].len << 12) | (dz ? 0x800 : 0) | (v & 0xFF));
+    }
+}
+
 static void fill_lut(uint16_t *lut, int peek_bits, const dcs_code_t *codes, int n)
 {
     for (int i = 0; i < n; ++i) {
@@ -29,12 +41,12 @@ void dcsb_build_tables(DcsbTables *t)
 {
     memset(t, 0, sizeof(*t));
     fill_lut(t->lut + DCSB_LUT_HDR94, 8, dcs94_hdr, NCODES(dcs94_hdr));
-    fill_lut(t->lut + DCSB_LUT_CB + 0, 2, dcs94_cb1, NCODES(dcs94_cb1));
-    fill_lut(t->lut + DCSB_LUT_CB + 4, 3, dcs94_cb2, NCODES(dcs94_cb2));
-    fill_lut(t->lut + DCSB_LUT_CB + 12, 5, dcs94_cb3, NCODES(dcs94_cb3));
-    fill_lut(t->lut + DCSB_LUT_CB + 44, 7, dcs94_cb4, NCODES(dcs94_cb4));
-    fill_lut(t->lut + DCSB_LUT_CB + 172, 8, dcs94_cb5, NCODES(dcs94_cb5));
-    fill_lut(t->lut + DCSB_LUT_CB + 428, 9, dcs94_cb6, NCODES(dcs94_cb6));
+    fill_cb94(t->lut + DCSB_LUT_CB + 0, 2, dcs94_cb1, NCODES(dcs94_cb1), 1);
+    fill_cb94(t->lut + DCSB_LUT_CB + 4, 3, dcs94_cb2, NCODES(dcs94_cb2), 2);
+    fill_cb94(t->lut + DCSB_LUT_CB + 12, 5, dcs94_cb3, NCODES(dcs94_cb3), 3);
+    fill_cb94(t->lut + DCSB_LUT_CB + 44, 7, dcs94_cb4, NCODES(dcs94_cb4), 4);
+    fill_cb94(t->lut + DCSB_LUT_CB + 172, 8, dcs94_cb5, NCODES(dcs94_cb5), 5);
+    fill_cb94(t->lut + DCSB_LUT_CB + 428, 9, dcs94_cb6, NCODES(dcs94_cb6), 6);
     fill_lut(t->lut + DCSB_LUT_HDR93, 8, dcs93_hdr, NCODES(dcs93_hdr));
     fill_lut(t->lut + DCSB_LUT_BB93A + 0, 4, dcs93a_bandbits0, NCODES(dcs93a_bandbits0));
     fill_lut(t->lut + DCSB_LUT_BB93A + 16, 4, dcs93a_bandbits1, NCODES(dcs93a_bandbits1));
@@ -59,6 +71,38 @@ void dcsb_build_tables(DcsbTables *t)
         t->pretw[i] = ((uint32_t)c0 << 16) | c1;
     }
     memcpy(t->pairs93a, dcs93a_pairs, sizeof(t->pairs93a));
+    // 1994 fast path: pre-doubled coefficients (a multiply-accumulate then yields the ADSP's
+    // left-shifted MR directly)
+    for (int p = 0; p < 64; ++p) {
+        t->tw_c2[p] = 2 * (int)(int16_t)dcs_twiddle[128 + p];
+        t->tw_s2[p] = 2 * (int)(int16_t)dcs_twiddle[p];
+        t->pre_c0[p] = 2 * (int)(int16_t)(t->pretw[p] >> 16);
+        t->pre_c1[p] = 2 * (int)(int16_t)(t->pretw[p] & 0xFFFFu);
+    }
+    // multi-symbol length tables for the scan: greedily chain whole codewords inside a 12-bit
+    // peek without covering more than `cap` output slots; cap 1 = exactly one codeword
+    const dcs_code_t *cbs[6] = { dcs94_cb1, dcs94_cb2, dcs94_cb3, dcs94_cb4, dcs94_cb5, dcs94_cb6 };
+    const int ncb[6] = { NCODES(dcs94_cb1), NCODES(dcs94_cb2), NCODES(dcs94_cb3), NCODES(dcs94_cb4), NCODES(dcs94_cb5), NCODES(dcs94_cb6) };
+    for (int ci = 0; ci < 4; ++ci)
+        for (int k = 0; k < 6; ++k)
+            for (int x = 0; x < DCSB_MLUT_CB; ++x) {
+                const int cap = 1 << ci, P = DCSB_MLUT_PEEK;
+                int used = 0, slots = 0;
+                for (;;) {
+                    int hit = -1;
+                    for (int i = 0; i < ncb[k] && hit < 0; ++i) {
+                        const int len = cbs[k][i].len;
+                        if (used + len <= P && (uint32_t)((x >> (P - used - len)) & ((1 << len) - 1)) == cbs[k][i].code) hit = i;
+                    }
+                    if (hit < 0) break;
+                    const int add = (cbs[k][hit].val & 0x80) ? 2 : 1;
+                    if (slots && slots + add > cap) break;      // the first codeword is always taken
+                    used += cbs[k][hit].len;
+                    slots += add;
+                    if (slots >= cap) break;
+                }
+                t->mlut[(ci * 6 + k) * DCSB_MLUT_CB + x] = (uint8_t)((slots << 4) | used);
+            }
 }
 
 // ======================================================================================
@@ -132,14 +176,22 @@ static void stream_gain(const dcsb_stream_desc &d, DcsbStreamRec &r)
 }
 
 
-int dcsb_prepare(const dcsb_stream_desc *descs, size_t n, DcsbPrepared *p)
+int dcsb_prepare(const dcsb_stream_desc *descs, size_t n, DcsbPrepared *p, const uint8_t *in_place_base, size_t in_place_span)
 {
     p->recs.resize(n);
     p->host_status.assign(n, 0);
     p->tiles.clear();
     p->compressed_bytes = 0;
-    uint64_t off = 0, frames = 0, pcm = 0;
+    uint64_t off = 0, frames = 0, ckpt = 0, pcm = 0;
     std::vector<DcsbTile> t94, t93;
+    // 1994 work items: long enough that the one warm-up frame per item is noise, short enough
+    // that the batch spreads over every resident warp of the chip several times
+    uint64_t est_frames = 0;
+    for (size_t i = 0; i < n; ++i)
+        if (descs[i].data && descs[i].nbytes >= 2) est_frames += (((uint32_t)descs[i].data[0] << 8) | descs[i].data[1]) + descs[i].tail_frames;
+    uint32_t item_len = (uint32_t)std::min<uint64_t>(255, std::max<uint64_t>(31, est_frames / 8192));
+    item_len = item_len < 63 ? 31 : 31 + ((item_len - 31) / 32) * 32;       // 31 + whole 32-frame tiles
+    size_t items94 = 0;
     for (size_t i = 0; i < n; ++i) {
         const dcsb_stream_desc &d = descs[i];
         DcsbStreamRec &r = p->recs[i];
@@ -153,9 +205,9 @@ int dcsb_prepare(const dcsb_stream_desc *descs, size_t n, DcsbPrepared *p)
         }
         r.fmt = (uint8_t)fmt;
         r.hdr_len = fmt == DCSB_FMT_93A1 ? 1 : 16;
-        r.data_off = off;
+        r.data_off = in_place_base ? (uint64_t)(d.data - in_place_base) : off;
         r.nbytes = d.nbytes;
-        r.frame_base = (uint32_t)frames;
+        r.frame_base = (uint32_t)ckpt;
         r.pcm_off = pcm;
         // frames rendered = U16 frame count + tail, whatever happens later (rejected and
         // failing streams render silence), so callers can lay out PCM from the first 2 bytes
@@ -168,17 +220,27 @@ int dcsb_prepare(const dcsb_stream_desc *descs, size_t n, DcsbPrepared *p)
         }
         r.nframes = (uint16_t)nf;
         stream_gain(d, r);
-        auto &tl = fmt == DCSB_FMT_94 ? t94 : t93;
-        for (uint32_t f = 0; f < r.out_frames; f += DCSB_TILE_OUT) tl.push_back(DcsbTile{ (uint32_t)i, f });
+        if (fmt == DCSB_FMT_94) items94 += (r.out_frames + item_len - 1) / item_len;
+        else for (uint32_t f = 0; f < r.out_frames; f += DCSB_TILE_OUT)
+            t93.push_back(DcsbTile{ (uint32_t)i, f, std::min<uint32_t>(DCSB_TILE_OUT, r.out_frames - f) });
         off += ((uint64_t)d.nbytes + 15 + 16) & ~15ull;     // 16-byte aligned, >= 16 bytes of zero padding
         frames += nf;
+        ckpt += (uint64_t)nf + 1;
         pcm += (uint64_t)r.out_frames * 240;
         p->compressed_bytes += d.nbytes;
     }
-    if (frames > 0xFFFFFFF0ull || t94.size() + t93.size() > 0x7FFFFFF0ull) return DCSB_E_ARG;
+    t94.reserve(items94);
+    for (size_t i = 0; i < n; ++i) {
+        const DcsbStreamRec &r = p->recs[i];
+        if (r.fmt != DCSB_FMT_94) continue;
+        for (uint32_t f = 0; f < r.out_frames; f += item_len)
+            t94.push_back(DcsbTile{ (uint32_t)i, f, std::min<uint32_t>(item_len, r.out_frames - f) });
+    }
+    if (ckpt > 0xFFFFFFF0ull || t94.size() + t93.size() > 0x7FFFFFF0ull) return DCSB_E_ARG;
     p->total_frames_in = frames;
+    p->total_checkpoints = ckpt;
     p->total_out_frames = pcm / 240;
-    p->slab_bytes = (size_t)off + 64;
+    p->slab_bytes = (in_place_base ? in_place_span : (size_t)off) + 1024;     // slack: window prefetch + L2 prefetch run ahead of the data
     p->ntiles94 = (int)t94.size();
     p->ntiles93 = (int)t93.size();
     p->tiles = std::move(t94);

@@ -25,19 +25,27 @@ struct DcsbStreamRec {
 };
 static_assert(sizeof(DcsbStreamRec) == 64, "DcsbStreamRec layout");
 
-// A tile = up to DCSB_TILE_OUT consecutive output frames of one stream, handled by one warp.
-// Lane 0 re-decodes the frame before the tile so the 16-sample overlap is available.
+// A work item = `count` consecutive output frames of one stream starting at `first`, handled by
+// one warp.  1993-family items are single tiles of <= DCSB_TILE_OUT frames (lane 0 re-decodes
+// the frame before the tile so the 16-sample overlap is available); 1994-family items span
+// several 32-frame tiles and carry the overlap from tile to tile (one warm-up frame per item).
 #define DCSB_TILE_OUT 31
-struct DcsbTile { uint32_t stream; uint32_t first; };
+struct DcsbTile { uint32_t stream; uint32_t first; uint32_t count; };
 
 // Peek-LUT block (uint16 entries: len<<8 | value), copied to shared memory by each CTA.
 #define DCSB_LUT_HDR94   0      // 256: 1994 frame-header delta code, 8-bit peek (0 = longer code)
-#define DCSB_LUT_CB      256    // 940: 1994 sample codebooks 1..6 (4+8+32+128+256+512)
+#define DCSB_LUT_CB      256    // 940: 1994 sample codebooks 1..6 (4+8+32+128+256+512): len<<12 | two-zeros<<11 | signed value
 #define DCSB_LUT_HDR93   1196   // 256: 1993 type-1 band-type delta code, 8-bit peek (0 = longer code)
 #define DCSB_LUT_BB93A   1452   // 64:  OS93a band-bits codes, 4 groups x 4-bit peek
 #define DCSB_LUT_SC93A   1516   // 256: OS93a scale-delta code, 8-bit peek
 #define DCSB_LUT_XLAT    1772   // 48:  1994 type-1 band translation, 3 groups x 16: (codebook/width << 8) | scale adjust
 #define DCSB_LUT_WORDS   1820
+
+// scan: multi-symbol length tables (dcsb_fast94.cuh)
+#define DCSB_MLUT_PEEK 13
+#define DCSB_MLUT_CB   (1 << DCSB_MLUT_PEEK)        // entries per (cap, codebook)
+#define DCSB_MLUT_CAP  (6 * DCSB_MLUT_CB)           // entries per cap
+#define DCSB_MLUT_SIZE (4 * DCSB_MLUT_CAP)
 
 struct DcsbLongCode { uint32_t code; uint8_t len; uint8_t val; uint16_t pad; };
 
@@ -50,11 +58,18 @@ struct DcsbTables {
     DcsbLongCode long94[32];   // 1994 header codes longer than 8 bits
     DcsbLongCode long93[64];   // 1993 header codes longer than 8 bits
     int n_long94, n_long93;
+    // 1994 fast path
+    int tw_c2[64], tw_s2[64];      // butterfly twiddles pre-doubled (2cos, 2sin), partition order
+    int pre_c0[64], pre_c1[64];    // pre-pass coefficients pre-doubled, natural order
+    uint8_t mlut[DCSB_MLUT_SIZE];  // scan: multi-symbol length tables [cap 1,2,4,8][codebook][next 13 bits]:
+                                   // low nibble = bits consumed, high nibble = output slots covered
 };
 
 struct DcsbScanOut {
-    uint32_t *bitpos;          // [total_frames] frame start, bits from the first byte after the stream header
-    uint2    *bt;              // [total_frames] band-type state carried into the frame, 16 x 4 bits
+    // checkpoints: one per stream frame plus one end entry per stream (frame_base counts both)
+    uint32_t *bitpos;          // frame start, bits from the first byte after the stream header
+    uint2    *bt;              // band-type state carried into the frame, 16 x 4 bits
+    uint16_t *hdrbits;         // 1994 layout: length of the frame header in bits
     int32_t  *status;          // [nstreams]
     uint32_t *nplay;           // [nstreams] frames that decode before the channel goes silent
     uint32_t *endbits;         // [nstreams] bit position after the last decoded frame
@@ -69,18 +84,27 @@ void dcsb_build_tables(DcsbTables *t);   // host
 struct DcsbPrepared {
     std::vector<DcsbStreamRec> recs;
     std::vector<int32_t> host_status;     // host-side rejections (0 = let the scan decide)
-    std::vector<DcsbTile> tiles;          // 1994-family tiles first, then 1993-family
+    std::vector<DcsbTile> tiles;          // 1994-family items first, then 1993-family tiles
     int ntiles94 = 0, ntiles93 = 0;
-    uint64_t total_frames_in = 0, total_out_frames = 0, compressed_bytes = 0;
+    uint64_t total_frames_in = 0;         // stream frames
+    uint64_t total_checkpoints = 0;       // stream frames + one end entry per stream
+    uint64_t total_out_frames = 0, compressed_bytes = 0;
     size_t slab_bytes = 0;
 };
-// validate + lay out a batch (no CUDA calls); DCSB_OK or DCSB_E_ARG
-int dcsb_prepare(const dcsb_stream_desc *descs, size_t n, DcsbPrepared *p);
+// validate + lay out a batch (no CUDA calls); DCSB_OK or DCSB_E_ARG.  With in_place_base the
+// device slab is a verbatim copy of host bytes [in_place_base, in_place_base + in_place_span)
+// and each stream keeps its position inside it (any byte alignment); otherwise streams are laid
+// out back to back, 16-byte aligned and zero padded, for dcsb_pack_slab.
+int dcsb_prepare(const dcsb_stream_desc *descs, size_t n, DcsbPrepared *p, const uint8_t *in_place_base, size_t in_place_span);
 // copy the streams into `slab` (p->slab_bytes bytes) at their 16-byte aligned offsets, zero padded
 void dcsb_pack_slab(const dcsb_stream_desc *descs, size_t n, const DcsbPrepared *p, uint8_t *slab);
 
-cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, int nstreams,
+// lanes_hint: streams per warp (0 = choose from nstreams).  A caller that launches several scans
+// side by side passes dcsb_scan_lanes(total streams) so that all of them fit on the chip at once
+// (a scan CTA's tables fill an SM's shared memory).
+cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, int nstreams, int lanes_hint,
                              const DcsbTables *tables, DcsbScanOut out, cudaStream_t st);
+int dcsb_scan_lanes(int nstreams);       // streams per warp the scan launch uses (1..32)
 // tiles[0..ntiles94) use the 1994 transform, tiles[ntiles94..ntiles94+ntiles93) the 1993 one
 cudaError_t dcsb_launch_decode(const uint8_t *slab, const DcsbStreamRec *streams, const DcsbTile *tiles,
                                int ntiles94, int ntiles93, const DcsbTables *tables, DcsbScanOut scan,

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "dcsb_core.cuh"
+#include "dcsb_fast94.cuh"
 
 #define DCSB_WARPS_PER_CTA 4
 
@@ -24,16 +25,37 @@ __device__ __forceinline__ void dcsb_load_lut(uint16_t *s_lut, const DcsbTables 
 }
 
 // ------------------------------------------------------------------------------------
-// K1: frame-boundary scan
-__global__ void __launch_bounds__(128)
-dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restrict__ streams, int nstreams,
+// K1: frame-boundary scan, one thread per stream.  A warp takes `lanes` streams (the scan is a
+// dependent chain per stream: with few streams, few lanes per warp put every chain on its own
+// warp scheduler and shorten the per-warp "slowest lane" loops); the CTA's warps share the
+// tables and walk stream groups grid-stride.
+struct DcsbSmemScan {
+    uint16_t lut[DCSB_LUT_WORDS];
+    __align__(16) uint8_t mlut[DCSB_MLUT_SIZE];
+};
+
+__global__ void __launch_bounds__(1024, 1)
+dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restrict__ streams, int nstreams, int lanes,
                  const DcsbTables *__restrict__ tab, DcsbScanOut out)
 {
-    __shared__ uint16_t s_lut[DCSB_LUT_WORDS];
-    dcsb_load_lut(s_lut, tab);
-    const int si = blockIdx.x * blockDim.x + threadIdx.x;
-    if (si >= nstreams) return;
-    dcsb_scan_stream(slab, streams, si, tab, s_lut, out);
+    extern __shared__ __align__(16) uint32_t smem[];
+    DcsbSmemScan &sm = *reinterpret_cast<DcsbSmemScan *>(smem);
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(tab->mlut);
+        uint4 *dst = reinterpret_cast<uint4 *>(sm.mlut);
+        for (int i = threadIdx.x; i < DCSB_MLUT_SIZE / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    dcsb_load_lut(sm.lut, tab);
+    const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+    if (lane >= lanes) return;
+    const DcsbSmemU8 mlut = DCSB_SMEM_U8(sm.mlut);
+    for (int g = blockIdx.x * warps + (threadIdx.x >> 5);; g += gridDim.x * warps) {
+        const int si = g * lanes + lane;
+        if (g * lanes >= nstreams) break;
+        if (si >= nstreams) continue;
+        if (streams[si].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab, streams, si, tab, sm.lut, mlut, out);
+        else dcsb_scan_stream(slab, streams, si, tab, sm.lut, out);
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -64,35 +86,97 @@ dcsb_decode_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__rest
 }
 
 // ------------------------------------------------------------------------------------
-cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, int nstreams,
+// K2, 1994 layout: one warp per work item, one lane per frame (dcsb_fast94.cuh)
+#define DCSB_WARPS94 4
+struct DcsbSmem94 {
+    uint16_t lut[DCSB_LUT_WORDS];
+    DcsbTw94 tw;
+    uint8_t hdr[DCSB_WARPS94][16];
+    uint32_t rows[DCSB_WARPS94][DCSB_WARP94_WORDS];
+};
+
+__global__ void __launch_bounds__(DCSB_WARPS94 * 32, 3)
+dcsb_decode94_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restrict__ streams,
+                     const DcsbTile *__restrict__ items, int nitems, const DcsbTables *__restrict__ tab,
+                     DcsbScanOut scan, int16_t *__restrict__ pcm, unsigned long long *__restrict__ checksums)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    DcsbSmem94 &sm = *reinterpret_cast<DcsbSmem94 *>(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * DCSB_WARPS94 + warp;
+    {
+        int *dst = reinterpret_cast<int *>(&sm.tw);
+        for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+            dst[i] = tab->tw_c2[i]; dst[64 + i] = tab->tw_s2[i]; dst[128 + i] = tab->pre_c0[i]; dst[192 + i] = tab->pre_c1[i];
+        }
+        if (item < nitems && lane < 16) sm.hdr[warp][lane] = streams[items[item].stream].hdr[lane];
+    }
+    dcsb_load_lut(sm.lut, tab);
+    if (item >= nitems) return;
+    const DcsbTile it = items[item];
+    unsigned long long csum = dcsb_decode94_item(slab, streams, it, tab, sm.lut, &sm.tw, sm.hdr[warp], scan, pcm, sm.rows[warp]);
+    if (checksums) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+        if (lane == 0) atomicAdd(checksums + it.stream, csum);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// streams per warp: aim at one warp per warp scheduler (148 SMs x 4) before filling warps up
+int dcsb_scan_lanes(int nstreams)
+{
+    int lanes = 1;
+    while (lanes < 32 && (nstreams + lanes - 1) / lanes > 148 * 4) lanes *= 2;
+    return lanes;
+}
+
+cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, int nstreams, int lanes_hint,
                              const DcsbTables *tables, DcsbScanOut out, cudaStream_t st)
 {
     if (nstreams <= 0) return cudaSuccess;
-    const int threads = 128;      // few threads per CTA spreads the latency-bound walkers over all SMs
-    dcsb_scan_kernel<<<(nstreams + threads - 1) / threads, threads, 0, st>>>(slab, streams, nstreams, tables, out);
+    const int lanes = lanes_hint > 0 ? lanes_hint : dcsb_scan_lanes(nstreams);
+    const int warps = (nstreams + lanes - 1) / lanes;
+    // one CTA per SM (the tables fill its shared memory); its warps share them: one per warp
+    // scheduler when streams are few, up to 32 when the batch is large enough to need the
+    // latency hiding
+    int wpc = (warps + 147) / 148;
+    wpc = wpc < 4 ? 4 : (wpc > 32 ? 32 : wpc);
+    int grid = (warps + wpc - 1) / wpc;
+    if (grid > 148) grid = 148;
+    const size_t smem = sizeof(DcsbSmemScan);
+    cudaError_t e = cudaFuncSetAttribute(dcsb_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dcsb_scan_kernel<<<grid, wpc * 32, smem, st>>>(slab, streams, nstreams, lanes, tables, out);
     return cudaGetLastError();
 }
 
-template <bool T93>
-static cudaError_t launch_decode_t(const uint8_t *slab, const DcsbStreamRec *streams, const DcsbTile *tiles,
+static cudaError_t launch_decode93(const uint8_t *slab, const DcsbStreamRec *streams, const DcsbTile *tiles,
                                    int ntiles, const DcsbTables *tables, DcsbScanOut scan, int16_t *pcm,
                                    unsigned long long *checksums, cudaStream_t st)
 {
     if (ntiles <= 0) return cudaSuccess;
-    const size_t smem = (DCSB_LUT_WORDS / 2 + DCSB_WARPS_PER_CTA * DcsbWarpSmem<T93>::WORDS) * sizeof(uint32_t);
-    cudaError_t e = cudaFuncSetAttribute(dcsb_decode_kernel<T93>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (DCSB_LUT_WORDS / 2 + DCSB_WARPS_PER_CTA * DcsbWarpSmem<true>::WORDS) * sizeof(uint32_t);
+    cudaError_t e = cudaFuncSetAttribute(dcsb_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (ntiles + DCSB_WARPS_PER_CTA - 1) / DCSB_WARPS_PER_CTA;
-    dcsb_decode_kernel<T93><<<grid, DCSB_WARPS_PER_CTA * 32, smem, st>>>(slab, streams, tiles, ntiles, tables, scan, pcm, checksums);
+    dcsb_decode_kernel<true><<<grid, DCSB_WARPS_PER_CTA * 32, smem, st>>>(slab, streams, tiles, ntiles, tables, scan, pcm, checksums);
     return cudaGetLastError();
 }
 
-// tiles[0..ntiles94) are 1994-family tiles, tiles[ntiles94..ntiles) 1993-family tiles
+// tiles[0..ntiles94) are 1994-family work items, tiles[ntiles94..ntiles94+ntiles93) 1993-family tiles
 cudaError_t dcsb_launch_decode(const uint8_t *slab, const DcsbStreamRec *streams, const DcsbTile *tiles,
                                int ntiles94, int ntiles93, const DcsbTables *tables, DcsbScanOut scan,
                                int16_t *pcm, unsigned long long *checksums, cudaStream_t st)
 {
-    cudaError_t e = launch_decode_t<false>(slab, streams, tiles, ntiles94, tables, scan, pcm, checksums, st);
-    if (e != cudaSuccess) return e;
-    return launch_decode_t<true>(slab, streams, tiles + ntiles94, ntiles93, tables, scan, pcm, checksums, st);
+    if (ntiles94 > 0) {
+        const size_t smem = sizeof(DcsbSmem94);
+        cudaError_t e = cudaFuncSetAttribute(dcsb_decode94_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        const int grid = (ntiles94 + DCSB_WARPS94 - 1) / DCSB_WARPS94;
+        dcsb_decode94_kernel<<<grid, DCSB_WARPS94 * 32, smem, st>>>(slab, streams, tiles, ntiles94, tables, scan, pcm, checksums);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return launch_decode93(slab, streams, tiles + ntiles94, ntiles93, tables, scan, pcm, checksums, st);
 }

@@ -113,3 +113,67 @@ def test_gpu_many_streams_checksum_of_checksums(ctx):
         cs = int((s * (2 * np.arange(s.size, dtype=np.uint64) + 1)).sum(dtype=np.uint64))
         assert all(res[j]["checksum"] == cs for j in range(i, 2048, 8))
     b.close()
+
+
+def _many_streams(seed, n, nframes):
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        for os_, d, _ in dcsfuzz.corpus(int(rng.integers(0, 1 << 30)), n_each=1, nframes=nframes):
+            out.append((d, os_, 255, 0x64, 2))
+    return out[:n]
+
+
+def test_gpu_decode_streams_pipeline_lanes_pinned_in_place(ctx):
+    """Enough PCM that dcsb_decode_streams splits the batch over several pipeline lanes; inputs in
+    one pinned blob (uploaded in place, arbitrary byte alignment) and a pinned output buffer
+    (PCM lands by DMA), against the same call on pageable memory and against the oracle."""
+    import ctypes as C
+    import torch
+    import dcsexplorer_b200 as dx
+    streams = _many_streams(11, 520, 1000)           # ~125 M samples -> 2+ lanes
+    descs, keep = dx.make_descs(streams)
+    n = len(streams)
+    blob = torch.empty(sum(len(s[0]) for s in streams) + n, dtype=torch.uint8).pin_memory()
+    bnp = blob.numpy()
+    off = 0
+    for i, s in enumerate(streams):                  # odd gaps: streams start at arbitrary byte offsets
+        bnp[off:off + len(s[0])] = np.frombuffer(s[0], dtype=np.uint8)
+        descs[i].data = blob.data_ptr() + off
+        off += len(s[0]) + (i & 1)
+    total = sum((((s[0][0] << 8) | s[0][1]) + 2) * 240 for s in streams)
+    h_pcm = torch.zeros(total, dtype=torch.int16).pin_memory()
+    res = (dx.Result * n)()
+    for _ in range(2):                               # second call reuses the lanes' buffers
+        rc = ctx._L.dcsb_decode_streams(ctx._h, descs, n, h_pcm.data_ptr(), None, res)
+        assert rc == 0, ctx._L.dcsb_last_error(ctx._h)
+    pcm2, offs, res2 = ctx.decode_streams(streams)   # pageable in / out, packed by the library
+    assert np.array_equal(h_pcm.numpy(), pcm2)
+    for i in range(n):
+        assert res[i].checksum == res2[i]["checksum"] and res[i].status == res2[i]["status"]
+    for i in list(range(0, n, 37)) + [n - 1]:
+        d, os_, vol, lvl, tail = streams[i]
+        want, rc = _expect(d, os_, vol, lvl, tail)
+        assert np.array_equal(pcm2[offs[i]:offs[i] + want.size], want), (i, hex(os_))
+
+
+def test_gpu_decode_streams_custom_offsets(ctx):
+    import ctypes as C
+    import dcsexplorer_b200 as dx
+    streams = _many_streams(5, 9, 20)
+    descs, keep = dx.make_descs(streams)
+    n = len(streams)
+    sizes = [(((s[0][0] << 8) | s[0][1]) + 2) * 240 for s in streams]
+    offs = np.zeros(n, dtype=np.uint64)
+    pos = 7
+    for i in reversed(range(n)):                     # reversed order with gaps
+        offs[i] = pos
+        pos += sizes[i] + 13
+    out = np.full(pos, 0x5A5A, dtype=np.int16)
+    res = (dx.Result * n)()
+    rc = ctx._L.dcsb_decode_streams(ctx._h, descs, n, out.ctypes.data, offs.ctypes.data, res)
+    assert rc == 0
+    for i, (d, os_, vol, lvl, tail) in enumerate(streams):
+        want, _ = _expect(d, os_, vol, lvl, tail)
+        assert np.array_equal(out[int(offs[i]):int(offs[i]) + want.size], want), i
+    assert out[0] == 0x5A5A and out[int(offs[0]) + sizes[0]] == 0x5A5A
