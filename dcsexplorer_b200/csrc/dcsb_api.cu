@@ -126,7 +126,7 @@ extern "C" void dcsb_batch_destroy(dcsb_batch *b)
     cudaSetDevice(b->ctx->device);
     cudaFree(b->d_slab); cudaFree(b->d_recs); cudaFree(b->d_tiles);
     cudaFree(b->scan.bitpos); cudaFree(b->scan.bt); cudaFree(b->scan.hdrbits); cudaFree(b->scan.status); cudaFree(b->scan.nplay);
-    cudaFree(b->scan.endbits); cudaFree(b->scan.stopband);
+    cudaFree(b->scan.endbits); cudaFree(b->scan.stopband); cudaFree(b->scan.dbg);
     cudaFree(b->d_pcm); cudaFree(b->d_checksums);
     for (auto &e : b->ev) if (e) cudaEventDestroy(e);
     delete b;
@@ -178,6 +178,10 @@ extern "C" int dcsb_batch_create(dcsb_ctx *ctx, const dcsb_stream_desc *descs, s
     CKB(cudaMalloc(&b->scan.nplay, std::max<size_t>(1, n) * sizeof(uint32_t)), "cudaMalloc(nplay)");
     CKB(cudaMalloc(&b->scan.endbits, std::max<size_t>(1, n) * sizeof(uint32_t)), "cudaMalloc(endbits)");
     CKB(cudaMalloc(&b->scan.stopband, std::max<size_t>(1, n)), "cudaMalloc(stopband)");
+#ifdef DCSB_SCAN_DEBUG
+    CKB(cudaMalloc(&b->scan.dbg, std::max<size_t>(1, n) * 16), "cudaMalloc(dbg)");
+    CKB(cudaMemset(b->scan.dbg, 0, std::max<size_t>(1, n) * 16), "memset(dbg)");
+#endif
     CKB(cudaMalloc(&b->d_checksums, std::max<size_t>(1, n) * sizeof(unsigned long long)), "cudaMalloc(checksums)");
     for (auto &ev : b->ev) CKB(cudaEventCreate(&ev), "cudaEventCreate");
 #undef CKB
@@ -263,6 +267,15 @@ extern "C" int dcsb_batch_read_pcm(dcsb_batch *b, size_t i, int16_t *pcm, size_t
     return (int)std::min<size_t>(ns, 0x7FFFFFFF);
 }
 
+#ifdef DCSB_SCAN_DEBUG
+// tuning builds only: per-stream {cycles lo, cycles hi, table steps, header steps} of the last scan
+extern "C" int dcsb_batch_scan_debug(dcsb_batch *b, uint32_t *out4)
+{
+    if (!b || !out4) return DCSB_E_ARG;
+    return cudaMemcpy(out4, b->scan.dbg, b->n * 16, cudaMemcpyDeviceToHost) == cudaSuccess ? DCSB_OK : DCSB_E_CUDA;
+}
+#endif
+
 extern "C" int dcsb_batch_read_scan(dcsb_batch *b, size_t i, uint32_t *bitpos, uint8_t *bandtypes, size_t max_frames)
 {
     if (!b || i >= b->n) return DCSB_E_ARG;
@@ -345,7 +358,7 @@ static int lane_submit(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs
     CK(cudaMemcpyAsync(l.d_tiles.p, p.tiles.data(), p.tiles.size() * sizeof(DcsbTile), cudaMemcpyHostToDevice, l.st), "H2D tiles");
     CK(cudaMemsetAsync(l.d_csum.p, 0, n * 8, l.st), "memset checksums");
     DcsbScanOut so{ (uint32_t *)l.d_bitpos.p, (uint2 *)l.d_bt.p, (uint16_t *)l.d_hdrbits.p, (int32_t *)l.d_status.p,
-                    (uint32_t *)l.d_nplay.p, (uint32_t *)l.d_endbits.p, (uint8_t *)l.d_stopband.p };
+                    (uint32_t *)l.d_nplay.p, (uint32_t *)l.d_endbits.p, (uint8_t *)l.d_stopband.p, nullptr };
     CK(dcsb_launch_scan((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p, (int)n, scan_lanes, ctx->d_tables, so, l.st), "scan kernel launch");
     CK(dcsb_launch_decode((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p, (const DcsbTile *)l.d_tiles.p,
                           p.ntiles94, p.ntiles93, ctx->d_tables, so, (int16_t *)l.d_pcm.p, (unsigned long long *)l.d_csum.p, l.st),

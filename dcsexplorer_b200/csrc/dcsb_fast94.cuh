@@ -1,8 +1,5 @@
 // dcsb200 fast path for the 1994+ frame layout (the format BASELINE.json's metric is quoted on).
 //
-//   dcsb_scan94_stream     K1 body: one thread walks one stream with a register bit window,
-//                          a leading-ones skip over unchanged frame-header codes and a
-//                          multi-symbol length LUT for the Huffman bands (lengths only).
 //   dcsb_lane_decode94     K2 phase A: one LANE decodes one frame from its checkpoint into
 //                          16-bit frequency bins in its own shared-memory row.
 //   dcsb_lane_transform94  K2 phase B: the same lane runs the exact fixed-point inverse
@@ -115,147 +112,7 @@ DCSB_HD int dcsb_band_count94(int b) { return b == 0 ? 7 : (b == 1 ? 8 : (b == 1
 DCSB_HD int dcsb_cb_maxw(int k) { return k <= 2 ? k + 1 : (k == 3 ? 5 : k + 3); }
 DCSB_HD int dcsb_cb_ofs(int k) { return k == 1 ? 0 : k == 2 ? 4 : k == 3 ? 12 : k == 4 ? 44 : k == 5 ? 172 : 428; }
 
-// =======================================================================================
-// K1 body, 1994 layout.  Writes one checkpoint per frame plus the end checkpoint:
-//   bitpos[f]  bit position of the frame start,   bt[f] band types carried INTO frame f,
-//   hdrbits[f] length of the frame header (so the decode lanes start at the first band and
-//              take the frame's own band types from bt[f + 1]).
-//
-// The scan is one dependent chain per stream (position -> bits at that position -> next
-// position), so what counts is the length of that chain, and -- 32 streams sharing a warp --
-// that every lane runs the same instruction stream.  Hence:
-//  * Huffman bands use multi-symbol length tables mlut[cap][codebook][next 13 bits] =
-//    {bits consumed, output slots covered} that chain as many whole codewords as fit in the
-//    peek without covering more than `cap` slots (cap = 1, 2, 4, 8).  A step picks the table
-//    for the largest cap <= remaining slots, so it can never overrun the band and needs no
-//    fallback or check on the chain.  (cap 1 is the plain codeword table; its 'two zeros'
-//    entry covers 2 slots, which is how the reference's error case shows up: rem < 0.)
-//  * the frame header's 1-bit "unchanged" codes are skipped as a run (count leading ones);
-//  * fixed-width bands advance in closed form, 32 bits per step;
-//  * step bodies are written select-style so they compile to predication, not branches.
-// The table lives in shared memory; the kernel hands over its 32-bit shared-window address so
-// that the inner loop is one add + LDS (a generic pointer makes ptxas re-derive the window base
-// inside the loop).  The simulator passes a plain pointer.
-#if DCSB_DEVICE_PASS
-typedef uint32_t DcsbSmemU8;
-#define DCSB_SMEM_U8(ptr) ((uint32_t)__cvta_generic_to_shared(ptr))
-DCSB_HD uint32_t dcsb_lds8(DcsbSmemU8 base, uint32_t idx)
-{
-    uint32_t v;
-    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + idx));
-    return v;
-}
-#else
-typedef const uint8_t *DcsbSmemU8;
-#define DCSB_SMEM_U8(ptr) (ptr)
-DCSB_HD uint32_t dcsb_lds8(DcsbSmemU8 base, uint32_t idx) { return base[idx]; }
-#endif
-
-DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *streams, int si, const DcsbTables *tab,
-                                const uint16_t *lut, DcsbSmemU8 mlut, const DcsbScanOut &out)
-{
-    const DcsbStreamRec s = streams[si];
-    const uint8_t *hdr = streams[si].hdr;
-    const int type1 = hdr[0] >> 7;
-    int nb = 0;
-    while (nb < 16 && (hdr[nb] & 0x7F) != 0x7F) ++nb;
-    // per-band slot count, 6 bits each (:1848-1862)
-    uint64_t cnt_lo = 0, cnt_hi = 0;
-    for (int b = 0; b < nb; ++b) {
-        uint64_t c = (uint64_t)(dcsb_band_count94(b) >> ((hdr[b] >> 6) & 1));
-        if (b < 8) cnt_lo |= c << (8 * b); else cnt_hi |= c << (8 * (b - 8));
-    }
-    const uint32_t nbits = (s.nbytes - 2 - s.hdr_len) * 8u;
-    DcsbWin win = dcsb_make_window(slab, s, 0);
-    uint64_t bt = 0;                               // InitStreamPlayback zeroes the band types (:1640)
-    int status = s.nframes ? 0 : -1, stopband = 0xFF;    // -1 = DCSB_E_EMPTY (the host refines DCSB_E_SHORT)
-    uint32_t nplay = s.nframes, f = 0;
-    uint32_t pos = 0;
-    for (; f < s.nframes; ++f) {
-        out.bitpos[s.frame_base + f] = pos;
-        out.bt[s.frame_base + f] = make_uint2((uint32_t)bt, (uint32_t)(bt >> 32));
-#if DCSB_DEVICE_PASS
-        // pull the lines of the next frames towards L2 while this one is walked
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(win.p + 96));
-#endif
-        // ---- frame header (:1780-1834)
-        int rc = 0;
-        for (int b = 0; b < nb;) {
-            const uint32_t v = win.peek32();
-            const int ones = dcsb_clz(~v);
-            const uint32_t e = lut[DCSB_LUT_HDR94 + (v >> 24)];
-            if (ones == 0 && e == 0) {
-                // codes longer than 8 bits: rare, matched bit-serially on a plain reader
-                DcsbBits rd;
-                rd.w = win.base;
-                rd.bias = win.bias;
-                uint32_t q = win.pos();
-                const int val = dcsb_long_code(rd, q, tab->long94, tab->n_long94);
-                win.seek(q);
-                const int nbt = dcsb_nib(bt, b) + val - 0x2E;
-                if (val < 0 || nbt < 0 || nbt > 15) { rc = DCSB_WALK_BANDTYPE; break; }
-                bt = (bt & ~(15ull << (4 * b))) | ((uint64_t)nbt << (4 * b));
-                ++b;
-                continue;
-            }
-            const int left = nb - b;
-            const int run = ones < left ? ones : left;
-            const bool unchanged = ones > 0;
-            win.skip(unchanged ? (uint32_t)run : (e >> 8));
-            const int nbt = dcsb_nib(bt, b) + (unchanged ? 0 : (int)(e & 0xFF) - 0x2E);
-            if (nbt < 0 || nbt > 15) { rc = DCSB_WALK_BANDTYPE; break; }
-            bt = (bt & ~(15ull << (4 * b))) | ((uint64_t)nbt << (4 * b));
-            b += unchanged ? run : 1;
-        }
-        if (rc) { status = rc; nplay = f; break; }
-        const uint32_t hpos = win.pos();
-        out.hdrbits[s.frame_base + f] = (uint16_t)(hpos - pos);
-        // ---- bands: lengths only
-        int sb = 99;
-        for (int b = 0; b < nb; ++b) {
-            int code = dcsb_nib(bt, b);
-            const int count = (int)(((b < 8 ? cnt_lo >> (8 * b) : cnt_hi >> (8 * (b - 8)))) & 0xFF);
-            if (type1) code = (int)(lut[DCSB_LUT_XLAT + (b < 3 ? 0 : (b < 6 ? 16 : 32)) + code] >> 8);
-            const bool huff = code >= 1 && code <= 6;
-            // Huffman band (:2186-2225): steps of up to `cap` slots
-            int rem = huff ? count : 0;
-            const uint32_t ml = (uint32_t)(huff ? code - 1 : 0) * DCSB_MLUT_CB;
-            while (rem > 0) {
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    if (rem > 0) {
-                        const int lg = 31 - dcsb_clz((uint32_t)rem);             // cap = largest power of two <= rem, at most 8
-                        const uint32_t m = dcsb_lds8(mlut, ml + (uint32_t)(lg < 3 ? lg : 3) * DCSB_MLUT_CAP +
-                                                               (win.peek_wide() >> (32 - DCSB_MLUT_PEEK)));
-                        win.advance(m & 15);
-                        rem -= (int)(m >> 4);
-                    }
-                }
-                win.refill();
-            }
-            if (rem < 0 && sb > b) sb = b;          // 'two zeros' with one slot left (:2213-2218)
-            // fixed-width band (:2227-2234): count * code bits, closed form
-            if (code > 6) {
-                const uint32_t fbits = (uint32_t)(count * code);
-                if (fbits <= 32) win.skip(fbits);
-                else win.seek(win.pos() + fbits);
-            }
-        }
-        pos = win.pos();
-        if (pos > nbits) { status = -2; nplay = f; break; }                       // DCSB_E_TRUNCATED
-        if (sb != 99) { status = -5; nplay = f + 1; stopband = sb; ++f; break; }    // DCSB_E_STOPPED
-    }
-    // end checkpoint: band types after the last decodable frame (decode lanes read bt[f + 1]).
-    // After a truncated / undecodable frame f the checkpoint of f itself already is the end.
-    if ((status == 0 && s.nframes) || status == -5) {
-        out.bitpos[s.frame_base + f] = pos;
-        out.bt[s.frame_base + f] = make_uint2((uint32_t)bt, (uint32_t)(bt >> 32));
-    }
-    out.status[si] = status;
-    out.nplay[si] = nplay;
-    out.endbits[si] = pos;
-    out.stopband[si] = (uint8_t)stopband;
-}
+// (K1, the frame-boundary scan of the 1994 layout, lives in dcsb_scan94.cuh)
 
 // =======================================================================================
 // K2 phase A: decode the bands of one 1994 frame (DCSDecoderNative.cpp:1836-2257).

@@ -79,14 +79,15 @@ void dcsb_build_tables(DcsbTables *t)
         t->pre_c0[p] = 2 * (int)(int16_t)(t->pretw[p] >> 16);
         t->pre_c1[p] = 2 * (int)(int16_t)(t->pretw[p] & 0xFFFFu);
     }
-    // multi-symbol length tables for the scan: greedily chain whole codewords inside a 12-bit
-    // peek without covering more than `cap` output slots; cap 1 = exactly one codeword
+    // length tables for the scan: greedily chain whole codewords inside the peek without covering
+    // more than `cap` output slots (the first codeword is always taken)
     const dcs_code_t *cbs[6] = { dcs94_cb1, dcs94_cb2, dcs94_cb3, dcs94_cb4, dcs94_cb5, dcs94_cb6 };
     const int ncb[6] = { NCODES(dcs94_cb1), NCODES(dcs94_cb2), NCODES(dcs94_cb3), NCODES(dcs94_cb4), NCODES(dcs94_cb5), NCODES(dcs94_cb6) };
-    for (int ci = 0; ci < 4; ++ci)
+    for (int which = 0; which < 2; ++which) {
+        const int P = which ? DCSB_T1_PEEK : DCSB_T8_PEEK, cap = which ? 1 : 8;
+        uint8_t *dst = which ? t->t1 : t->t8;
         for (int k = 0; k < 6; ++k)
-            for (int x = 0; x < DCSB_MLUT_CB; ++x) {
-                const int cap = 1 << ci, P = DCSB_MLUT_PEEK;
+            for (int x = 0; x < (1 << P); ++x) {
                 int used = 0, slots = 0;
                 for (;;) {
                     int hit = -1;
@@ -96,13 +97,14 @@ void dcsb_build_tables(DcsbTables *t)
                     }
                     if (hit < 0) break;
                     const int add = (cbs[k][hit].val & 0x80) ? 2 : 1;
-                    if (slots && slots + add > cap) break;      // the first codeword is always taken
+                    if (slots && slots + add > cap) break;
                     used += cbs[k][hit].len;
                     slots += add;
                     if (slots >= cap) break;
                 }
-                t->mlut[(ci * 6 + k) * DCSB_MLUT_CB + x] = (uint8_t)((slots << 4) | used);
+                dst[(k << P) + x] = (uint8_t)((slots << 4) | used);
             }
+    }
 }
 
 // ======================================================================================

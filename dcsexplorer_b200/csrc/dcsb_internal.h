@@ -41,11 +41,11 @@ struct DcsbTile { uint32_t stream; uint32_t first; uint32_t count; };
 #define DCSB_LUT_XLAT    1772   // 48:  1994 type-1 band translation, 3 groups x 16: (codebook/width << 8) | scale adjust
 #define DCSB_LUT_WORDS   1820
 
-// scan: multi-symbol length tables (dcsb_fast94.cuh)
-#define DCSB_MLUT_PEEK 13
-#define DCSB_MLUT_CB   (1 << DCSB_MLUT_PEEK)        // entries per (cap, codebook)
-#define DCSB_MLUT_CAP  (6 * DCSB_MLUT_CB)           // entries per cap
-#define DCSB_MLUT_SIZE (4 * DCSB_MLUT_CAP)
+// scan: length tables of the 1994 sample codebooks (dcsb_scan94.cuh); entry = slots << 4 | bits
+#define DCSB_T8_PEEK 13
+#define DCSB_T8_CB   (1 << DCSB_T8_PEEK)            // multi-symbol table: entries per codebook
+#define DCSB_T1_PEEK 9
+#define DCSB_T1_CB   (1 << DCSB_T1_PEEK)            // single-codeword table: entries per codebook
 
 struct DcsbLongCode { uint32_t code; uint8_t len; uint8_t val; uint16_t pad; };
 
@@ -61,8 +61,11 @@ struct DcsbTables {
     // 1994 fast path
     int tw_c2[64], tw_s2[64];      // butterfly twiddles pre-doubled (2cos, 2sin), partition order
     int pre_c0[64], pre_c1[64];    // pre-pass coefficients pre-doubled, natural order
-    uint8_t mlut[DCSB_MLUT_SIZE];  // scan: multi-symbol length tables [cap 1,2,4,8][codebook][next 13 bits]:
-                                   // low nibble = bits consumed, high nibble = output slots covered
+    // scan: t8[codebook][next 13 bits] = as many whole codewords as fit (at most 8 output slots),
+    // t1[codebook][next 9 bits] = exactly one codeword; low nibble = bits consumed, high nibble =
+    // output slots covered
+    uint8_t t8[6 * DCSB_T8_CB];
+    uint8_t t1[6 * DCSB_T1_CB];
 };
 
 struct DcsbScanOut {
@@ -74,6 +77,7 @@ struct DcsbScanOut {
     uint32_t *nplay;           // [nstreams] frames that decode before the channel goes silent
     uint32_t *endbits;         // [nstreams] bit position after the last decoded frame
     uint8_t  *stopband;        // [nstreams] band at which the reference's error path fired (else 0xFF)
+    uint32_t *dbg;             // tuning builds (-DDCSB_SCAN_DEBUG): [nstreams][4] cycles lo/hi, table steps, header steps; else NULL
 };
 
 void dcsb_build_tables(DcsbTables *t);   // host

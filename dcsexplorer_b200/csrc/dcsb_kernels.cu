@@ -11,8 +11,10 @@
 // The arithmetic lives in dcsb_core.cuh (shared with the CPU-side kernel simulator).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "dcsb_core.cuh"
 #include "dcsb_fast94.cuh"
+#include "dcsb_scan94.cuh"
 
 #define DCSB_WARPS_PER_CTA 4
 
@@ -25,35 +27,41 @@ __device__ __forceinline__ void dcsb_load_lut(uint16_t *s_lut, const DcsbTables 
 }
 
 // ------------------------------------------------------------------------------------
-// K1: frame-boundary scan, one thread per stream.  A warp takes `lanes` streams (the scan is a
-// dependent chain per stream: with few streams, few lanes per warp put every chain on its own
-// warp scheduler and shorten the per-warp "slowest lane" loops); the CTA's warps share the
-// tables and walk stream groups grid-stride.
+// K1: frame-boundary scan, one thread per stream.  A CTA takes up to DCSB_SCAN_SPC streams (one
+// 1 KB ring each); a warp takes `lanes` of them (the scan is a dependent chain per stream: few
+// lanes per warp keep the chains from serialising on each other's branches, while several warps
+// per scheduler fill the latency of each chain); the CTA's warps share the tables and walk
+// stream groups grid-stride.
+#define DCSB_SCAN_SPC 28
 struct DcsbSmemScan {
+    __align__(16) uint8_t ring[DCSB_SCAN_SPC][DCSB_RING_BYTES];
+    __align__(16) uint8_t t8[6 * DCSB_T8_CB];
+    __align__(16) uint8_t t1[6 * DCSB_T1_CB];
     uint16_t lut[DCSB_LUT_WORDS];
-    __align__(16) uint8_t mlut[DCSB_MLUT_SIZE];
 };
 
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(DCSB_SCAN_SPC * 32, 1)
 dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restrict__ streams, int nstreams, int lanes,
-                 const DcsbTables *__restrict__ tab, DcsbScanOut out)
+                 int spc, const DcsbTables *__restrict__ tab, DcsbScanOut out)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     DcsbSmemScan &sm = *reinterpret_cast<DcsbSmemScan *>(smem);
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(tab->mlut);
-        uint4 *dst = reinterpret_cast<uint4 *>(sm.mlut);
-        for (int i = threadIdx.x; i < DCSB_MLUT_SIZE / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+        const uint4 *src = reinterpret_cast<const uint4 *>(tab->t8);
+        uint4 *dst = reinterpret_cast<uint4 *>(sm.t8);
+        for (int i = threadIdx.x; i < 6 * DCSB_T8_CB / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+        src = reinterpret_cast<const uint4 *>(tab->t1);
+        dst = reinterpret_cast<uint4 *>(sm.t1);
+        for (int i = threadIdx.x; i < 6 * DCSB_T1_CB / 16; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     dcsb_load_lut(sm.lut, tab);
-    const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
-    if (lane >= lanes) return;
-    const DcsbSmemU8 mlut = DCSB_SMEM_U8(sm.mlut);
-    for (int g = blockIdx.x * warps + (threadIdx.x >> 5);; g += gridDim.x * warps) {
-        const int si = g * lanes + lane;
-        if (g * lanes >= nstreams) break;
-        if (si >= nstreams) continue;
-        if (streams[si].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab, streams, si, tab, sm.lut, mlut, out);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = warp * lanes + lane;              // stream slot inside the CTA
+    if (lane >= lanes || slot >= spc) return;
+    const DcsbSmemU8 t8 = DCSB_SMEM_U8(sm.t8), t1 = DCSB_SMEM_U8(sm.t1);
+    const DcsbRingPtr ring = DCSB_SMEM_U8(sm.ring[slot]);
+    for (int si = blockIdx.x * spc + slot; si < nstreams; si += gridDim.x * spc) {
+        if (streams[si].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab, streams, si, tab, sm.lut, t8, t1, ring, out);
         else dcsb_scan_stream(slab, streams, si, tab, sm.lut, out);
     }
 }
@@ -123,12 +131,15 @@ dcsb_decode94_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__re
 }
 
 // ------------------------------------------------------------------------------------
-// streams per warp: aim at one warp per warp scheduler (148 SMs x 4) before filling warps up
+// streams per warp in the scan
 int dcsb_scan_lanes(int nstreams)
 {
-    int lanes = 1;
-    while (lanes < 32 && (nstreams + lanes - 1) / lanes > 148 * 4) lanes *= 2;
-    return lanes;
+    if (const char *e = getenv("DCSB_SCAN_LANES")) {       // tuning override (tools/scan_sweep.py)
+        const int v = atoi(e);
+        if (v >= 1 && v <= 32) return v;
+    }
+    (void)nstreams;
+    return 2;
 }
 
 cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, int nstreams, int lanes_hint,
@@ -136,18 +147,16 @@ cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, 
 {
     if (nstreams <= 0) return cudaSuccess;
     const int lanes = lanes_hint > 0 ? lanes_hint : dcsb_scan_lanes(nstreams);
-    const int warps = (nstreams + lanes - 1) / lanes;
-    // one CTA per SM (the tables fill its shared memory); its warps share them: one per warp
-    // scheduler when streams are few, up to 32 when the batch is large enough to need the
-    // latency hiding
-    int wpc = (warps + 147) / 148;
-    wpc = wpc < 4 ? 4 : (wpc > 32 ? 32 : wpc);
-    int grid = (warps + wpc - 1) / wpc;
+    // spread the streams over the SMs first (one CTA per SM), then fill the CTAs up
+    int spc = (nstreams + 147) / 148;
+    spc = spc > DCSB_SCAN_SPC ? DCSB_SCAN_SPC : spc;
+    int grid = (nstreams + spc - 1) / spc;
     if (grid > 148) grid = 148;
+    const int warps = (spc + lanes - 1) / lanes;
     const size_t smem = sizeof(DcsbSmemScan);
     cudaError_t e = cudaFuncSetAttribute(dcsb_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    dcsb_scan_kernel<<<grid, wpc * 32, smem, st>>>(slab, streams, nstreams, lanes, tables, out);
+    dcsb_scan_kernel<<<grid, warps * 32, smem, st>>>(slab, streams, nstreams, lanes, spc, tables, out);
     return cudaGetLastError();
 }
 

@@ -11,6 +11,7 @@
 #include <vector>
 #include "../../dcsexplorer_b200/csrc/dcsb_core.cuh"
 #include "../../dcsexplorer_b200/csrc/dcsb_fast94.cuh"
+#include "../../dcsexplorer_b200/csrc/dcsb_scan94.cuh"
 
 extern "C" int hostsim_decode_streams(const dcsb_stream_desc *descs, size_t n, int16_t *pcm_out,
                                       dcsb_result *results, uint32_t *bitpos_out, uint8_t *bt_out)
@@ -28,9 +29,10 @@ extern "C" int hostsim_decode_streams(const dcsb_stream_desc *descs, size_t n, i
     std::vector<uint16_t> hdrbits(p.total_checkpoints + 1);
     std::vector<int32_t> status(n + 1);
     std::vector<uint8_t> stopband(n + 1);
-    DcsbScanOut so{ bitpos.data(), bt.data(), hdrbits.data(), status.data(), nplay.data(), endbits.data(), stopband.data() };
+    DcsbScanOut so{ bitpos.data(), bt.data(), hdrbits.data(), status.data(), nplay.data(), endbits.data(), stopband.data(), nullptr };
+    std::vector<uint8_t> ring(DCSB_RING_BYTES, 0xA5);                // one K1 thread's shared-memory ring
     for (size_t i = 0; i < n; ++i)                                   // K1 grid
-        if (p.recs[i].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, tab.mlut, so);
+        if (p.recs[i].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, tab.t8, tab.t1, ring.data(), so);
         else dcsb_scan_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, so);
 
     std::vector<unsigned long long> csum(n + 1, 0);
