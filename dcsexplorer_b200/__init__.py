@@ -11,7 +11,9 @@ from . import _capi
 from ._capi import (OS93A, OS93B, OS94, OS95, OK, E_EMPTY, E_TRUNCATED, E_BANDTYPE, E_SHORT,
                     E_STOPPED, E_ARG, E_CUDA, E_NOMEM, StreamDesc, Result)
 
-__all__ = ["Context", "Batch", "make_descs", "OS93A", "OS93B", "OS94", "OS95"]
+from ._capi import RomInfo, TrackInfo, PortWrite, Timeline, TimelineResult
+
+__all__ = ["Context", "Batch", "Rom", "Player", "make_descs", "make_timelines", "OS93A", "OS93B", "OS94", "OS95"]
 
 
 class DcsbError(RuntimeError):
@@ -148,3 +150,131 @@ class Batch:
 
     def kernel_ms(self, which):
         return self._L.dcsb_batch_last_kernel_ms(self._h, which)
+
+
+def make_timelines(timelines):
+    """timelines: list of (writes [(frame, byte)], n_frames, master_volume) -> (ctypes array, keepalive)"""
+    arr = (Timeline * max(1, len(timelines)))()
+    keep = []
+    for i, (writes, n_frames, vol) in enumerate(timelines):
+        w = (PortWrite * max(1, len(writes)))()
+        for k, (f, b) in enumerate(writes):
+            w[k].frame, w[k].byte = f, b
+        keep.append(w)
+        arr[i].writes = w
+        arr[i].n_writes = len(writes)
+        arr[i].n_frames = n_frames
+        arr[i].master_volume = vol
+    return arr, keep
+
+
+class Rom:
+    """dcsb_rom_*: a ROM set (host side: AddROM / LoadROMFromZipFile / CheckROMs / track and stream lookup)."""
+
+    def __init__(self, images=None, zip_path=None):
+        self._L = _capi.lib()
+        h = C.c_void_p()
+        if self._L.dcsb_rom_create(C.byref(h)) != OK:
+            raise DcsbError("dcsb_rom_create failed")
+        self._h = h
+        if images:
+            for chip, data in images.items():
+                buf = np.frombuffer(bytes(data), dtype=np.uint8)
+                rc = self._L.dcsb_rom_add(h, chip, buf.ctypes.data, buf.size)
+                if rc != OK:
+                    raise DcsbError("dcsb_rom_add(U%d) failed: %d" % (chip, rc))
+        if zip_path:
+            rc = self._L.dcsb_rom_load_zip(h, str(zip_path).encode(), None)
+            if rc != 0:
+                raise DcsbError("dcsb_rom_load_zip: %d %s" % (rc, self._L.dcsb_rom_last_error(h).decode()))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.dcsb_rom_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def check(self):
+        return self._L.dcsb_rom_check(self._h)
+
+    def info(self):
+        i = RomInfo()
+        self._L.dcsb_rom_get_info(self._h, C.byref(i))
+        return dict(os=i.os_version, hw=i.hw_version, channels=i.n_channels, version=i.version_number,
+                    n_tracks=i.n_tracks, catalog=i.catalog_offset, post=i.post_code, signature=i.signature.decode())
+
+    def track_info(self, track):
+        t = TrackInfo()
+        if not self._L.dcsb_rom_track_info(self._h, track, C.byref(t)):
+            return None
+        return dict(address=t.address, channel=t.channel, type=t.type, defer_code=t.defer_code,
+                    looping=bool(t.looping), time=t.time)
+
+    def list_streams(self):
+        n = self._L.dcsb_rom_list_streams(self._h, None, 0)
+        out = np.zeros(max(1, n), dtype=np.uint32)
+        self._L.dcsb_rom_list_streams(self._h, out.ctypes.data, n)
+        return [int(x) for x in out[:n]]
+
+    def stream_bytes(self, address, nbytes):
+        left = C.c_uint32(0)
+        p = self._L.dcsb_rom_pointer(self._h, address, C.byref(left))
+        if not p:
+            return b""
+        return C.string_at(p, min(nbytes, left.value))
+
+
+class Player:
+    """dcsb_player_*: one decoder instance on a ROM set."""
+
+    def __init__(self, ctx, rom):
+        self.ctx, self.rom, self._L = ctx, rom, ctx._L
+        h = C.c_void_p()
+        ctx._check(self._L.dcsb_player_create(ctx._h, rom._h, C.byref(h)), "dcsb_player_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.dcsb_player_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_master_volume(self, v): self._L.dcsb_player_set_master_volume(self._h, v)
+    def write_data_port(self, b): self._L.dcsb_player_write_data_port(self._h, b)
+    def add_track_command(self, t): self._L.dcsb_player_add_track_command(self._h, t)
+    def clear_tracks(self): self._L.dcsb_player_clear_tracks(self._h)
+    def is_stream_playing(self, ch): return bool(self._L.dcsb_player_is_stream_playing(self._h, ch))
+
+    def load_audio_stream(self, ch, address, level):
+        self.ctx._check(self._L.dcsb_player_load_audio_stream(self._h, ch, address, level), "dcsb_player_load_audio_stream")
+
+    def render(self, n_frames):
+        pcm = np.zeros(max(1, n_frames * 240), dtype=np.int16)
+        self.ctx._check(self._L.dcsb_player_render(self._h, n_frames, pcm.ctypes.data), "dcsb_player_render")
+        return pcm[:n_frames * 240]
+
+    def host_bytes(self):
+        out = np.zeros(65536, dtype=np.uint8)
+        n = self._L.dcsb_player_host_bytes(self._h, out.ctypes.data, out.size)
+        return out[:n].tobytes()
+
+
+def _render_timelines(self, rom, timelines):
+    """dcsb_render_timelines: list of (writes, n_frames, master_volume) -> (list of pcm arrays, results)"""
+    tl, keep = make_timelines(timelines)
+    total = sum(t[1] for t in timelines)
+    pcm = np.zeros(max(1, total * 240), dtype=np.int16)
+    res = (TimelineResult * max(1, len(timelines)))()
+    self._check(self._L.dcsb_render_timelines(self._h, rom._h, tl, len(timelines), pcm.ctypes.data, None, res),
+                "dcsb_render_timelines")
+    out, o = [], 0
+    for t in timelines:
+        out.append(pcm[o:o + t[1] * 240])
+        o += t[1] * 240
+    return out, [dict(status=res[i].status, frames=res[i].frames, checksum=res[i].checksum,
+                      n_host_bytes=res[i].n_host_bytes) for i in range(len(timelines))]
+
+
+Context.render_timelines = _render_timelines

@@ -21,7 +21,54 @@ class Result(C.Structure):
                 ("stream_bytes", C.c_uint32), ("checksum", C.c_uint64)]
 
 
+class RomInfo(C.Structure):
+    _fields_ = [("os_version", C.c_uint16), ("hw_version", C.c_uint8), ("n_channels", C.c_uint8),
+                ("version_number", C.c_uint16), ("n_tracks", C.c_uint16), ("catalog_offset", C.c_uint32),
+                ("post_code", C.c_int32), ("signature", C.c_char * 128)]
+
+
+class TrackInfo(C.Structure):
+    _fields_ = [("address", C.c_uint32), ("channel", C.c_int32), ("type", C.c_int32), ("defer_code", C.c_uint16),
+                ("looping", C.c_uint8), ("reserved", C.c_uint8), ("time", C.c_uint32)]
+
+
+class PortWrite(C.Structure):
+    _fields_ = [("frame", C.c_uint32), ("byte", C.c_uint8), ("pad", C.c_uint8 * 3)]
+
+
+class Timeline(C.Structure):
+    _fields_ = [("writes", C.POINTER(PortWrite)), ("n_writes", C.c_uint32), ("n_frames", C.c_uint32),
+                ("master_volume", C.c_uint8), ("pad", C.c_uint8 * 3)]
+
+
+class TimelineResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("frames", C.c_uint32), ("checksum", C.c_uint64),
+                ("n_host_bytes", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 SYMBOLS = {
+    "dcsb_rom_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "dcsb_rom_destroy": (None, [C.c_void_p]),
+    "dcsb_rom_add": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "dcsb_rom_load_zip": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
+    "dcsb_rom_check": (C.c_int, [C.c_void_p]),
+    "dcsb_rom_get_info": (C.c_int, [C.c_void_p, C.POINTER(RomInfo)]),
+    "dcsb_rom_track_info": (C.c_int, [C.c_void_p, C.c_uint16, C.POINTER(TrackInfo)]),
+    "dcsb_rom_list_streams": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "dcsb_rom_pointer": (C.c_void_p, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "dcsb_rom_last_error": (C.c_char_p, [C.c_void_p]),
+    "dcsb_player_create": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "dcsb_player_destroy": (None, [C.c_void_p]),
+    "dcsb_player_set_master_volume": (None, [C.c_void_p, C.c_int]),
+    "dcsb_player_write_data_port": (None, [C.c_void_p, C.c_uint8]),
+    "dcsb_player_add_track_command": (None, [C.c_void_p, C.c_uint16]),
+    "dcsb_player_load_audio_stream": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_int]),
+    "dcsb_player_clear_tracks": (None, [C.c_void_p]),
+    "dcsb_player_is_stream_playing": (C.c_int, [C.c_void_p, C.c_int]),
+    "dcsb_player_render": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "dcsb_player_host_bytes": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "dcsb_render_timelines": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Timeline), C.c_size_t, C.c_void_p, C.c_void_p,
+                                        C.POINTER(TimelineResult)]),
     "dcsb_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "dcsb_destroy": (None, [C.c_void_p]),
     "dcsb_last_error": (C.c_char_p, [C.c_void_p]),

@@ -11,76 +11,7 @@
 #include "../../include/dcsb200.h"
 #include "dcsb_internal.h"
 
-// ======================================================================================
-// grow-only buffer (device or pinned host) owned by a context
-struct DcsbBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    cudaError_t ensure(size_t bytes, bool host)
-    {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) { if (host) cudaFreeHost(p); else cudaFree(p); p = nullptr; cap = 0; }
-        const size_t want = bytes + bytes / 8 + 4096;
-        cudaError_t e = host ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release(bool host) { if (p) { if (host) cudaFreeHost(p); else cudaFree(p); } p = nullptr; cap = 0; }
-};
-
-// One pipeline lane of dcsb_decode_streams: a CUDA stream plus everything one chunk of
-// streams needs, kept across calls so that the steady state does no allocation.
-#define DCSB_MAX_LANES 8
-struct DcsbLane {
-    cudaStream_t st = nullptr;
-    DcsbBuf h_slab, h_res;                                   // pinned
-    DcsbBuf d_slab, d_recs, d_tiles, d_bitpos, d_bt, d_hdrbits, d_status, d_nplay, d_endbits, d_stopband, d_csum, d_pcm;
-    DcsbPrepared prep;
-    size_t first = 0, count = 0;
-    uint64_t pcm_base = 0;                                   // sample offset of the chunk in the packed output
-    bool direct_pcm = false;
-};
-
-struct dcsb_ctx {
-    int device = 0;
-    DcsbTables *d_tables = nullptr;
-    DcsbLane lanes[DCSB_MAX_LANES];
-    std::string err;
-};
-
-struct dcsb_batch {
-    dcsb_ctx *ctx = nullptr;
-    size_t n = 0;
-    std::vector<DcsbStreamRec> recs;
-    std::vector<int32_t> host_status;        // host-side rejections (0 = let the scan decide)
-    std::vector<DcsbTile> tiles;
-    int ntiles94 = 0, ntiles93 = 0;
-    uint64_t total_frames_in = 0;            // stream frames (checkpoint entries)
-    uint64_t total_out_frames = 0;
-    uint64_t compressed_bytes = 0;
-    size_t slab_bytes = 0;
-    // device
-    uint8_t *d_slab = nullptr;
-    DcsbStreamRec *d_recs = nullptr;
-    DcsbTile *d_tiles = nullptr;
-    DcsbScanOut scan{};
-    int16_t *d_pcm = nullptr;                // internal PCM buffer (lazy)
-    unsigned long long *d_checksums = nullptr;
-    cudaEvent_t ev[3] = { nullptr, nullptr, nullptr };
-    bool timed = false;
-};
-
-static int fail(dcsb_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess)
-{
-    if (ctx) {
-        char buf[512];
-        if (e != cudaSuccess) snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
-        else snprintf(buf, sizeof(buf), "%s", what);
-        ctx->err = buf;
-    }
-    return code;
-}
-#define CK(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, DCSB_E_CUDA, what, e_); } while (0)
+#include "dcsb_ctx.h"
 
 extern "C" const char *dcsb_version(void) { return "dcsb200 0.1 (sm_100a)"; }
 
@@ -134,6 +65,14 @@ extern "C" void dcsb_batch_destroy(dcsb_batch *b)
 
 extern "C" int dcsb_batch_create(dcsb_ctx *ctx, const dcsb_stream_desc *descs, size_t n, dcsb_batch **out)
 {
+    return dcsb_batch_create_impl(ctx, descs, n, nullptr, 0, out);
+}
+
+// in_place_base != NULL: the streams all lie inside host bytes [in_place_base, +in_place_span),
+// which become the device slab verbatim (ROM images: streams keep their chip positions)
+int dcsb_batch_create_impl(dcsb_ctx *ctx, const dcsb_stream_desc *descs, size_t n, const uint8_t *in_place_base,
+                           size_t in_place_span, dcsb_batch **out)
+{
     if (!ctx || !out || (!descs && n)) return fail(ctx, DCSB_E_ARG, "dcsb_batch_create: bad argument");
     *out = nullptr;
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
@@ -143,7 +82,7 @@ extern "C" int dcsb_batch_create(dcsb_ctx *ctx, const dcsb_stream_desc *descs, s
 
     DcsbPrepared prep;
     {
-        int rc = dcsb_prepare(descs, n, &prep, nullptr, 0);
+        int rc = dcsb_prepare(descs, n, &prep, in_place_base, in_place_span);
         if (rc != DCSB_OK) { delete b; return fail(ctx, rc, "dcsb_batch_create: unknown os_version or batch too large"); }
     }
     b->recs = prep.recs;
@@ -161,7 +100,10 @@ extern "C" int dcsb_batch_create(dcsb_ctx *ctx, const dcsb_stream_desc *descs, s
     uint8_t *h_slab = nullptr;
     cudaError_t e = cudaMallocHost(&h_slab, b->slab_bytes);
     if (e != cudaSuccess) { delete b; return fail(ctx, DCSB_E_NOMEM, "cudaMallocHost(slab)", e); }
-    dcsb_pack_slab(descs, n, &prep, h_slab);
+    if (in_place_base) {
+        memcpy(h_slab, in_place_base, in_place_span);
+        memset(h_slab + in_place_span, 0, b->slab_bytes - in_place_span);
+    } else dcsb_pack_slab(descs, n, &prep, h_slab);
 #define CKB(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cudaFreeHost(h_slab); dcsb_batch_destroy(b); return fail(ctx, DCSB_E_CUDA, what, e_); } } while (0)
     CKB(cudaMalloc(&b->d_slab, b->slab_bytes), "cudaMalloc(slab)");
     CKB(cudaMemcpy(b->d_slab, h_slab, b->slab_bytes, cudaMemcpyHostToDevice), "H2D slab");

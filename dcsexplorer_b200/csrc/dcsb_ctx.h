@@ -1,0 +1,85 @@
+// dcsb200 internal: context / batch objects shared by the C-ABI translation units
+// (dcsb_api.cu: streams and batches, dcsb_player.cu: ROM sets, players, timelines).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/dcsb200.h"
+#include "dcsb_internal.h"
+
+// ======================================================================================
+// grow-only buffer (device or pinned host) owned by a context
+struct DcsbBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes, bool host)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { if (host) cudaFreeHost(p); else cudaFree(p); p = nullptr; cap = 0; }
+        const size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = host ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release(bool host) { if (p) { if (host) cudaFreeHost(p); else cudaFree(p); } p = nullptr; cap = 0; }
+};
+
+// One pipeline lane of dcsb_decode_streams: a CUDA stream plus everything one chunk of
+// streams needs, kept across calls so that the steady state does no allocation.
+#define DCSB_MAX_LANES 8
+struct DcsbLane {
+    cudaStream_t st = nullptr;
+    DcsbBuf h_slab, h_res;                                   // pinned
+    DcsbBuf d_slab, d_recs, d_tiles, d_bitpos, d_bt, d_hdrbits, d_status, d_nplay, d_endbits, d_stopband, d_csum, d_pcm;
+    DcsbPrepared prep;
+    size_t first = 0, count = 0;
+    uint64_t pcm_base = 0;                                   // sample offset of the chunk in the packed output
+    bool direct_pcm = false;
+};
+
+struct dcsb_ctx {
+    int device = 0;
+    DcsbTables *d_tables = nullptr;
+    DcsbLane lanes[DCSB_MAX_LANES];
+    std::string err;
+};
+
+struct dcsb_batch {
+    dcsb_ctx *ctx = nullptr;
+    size_t n = 0;
+    std::vector<DcsbStreamRec> recs;
+    std::vector<int32_t> host_status;        // host-side rejections (0 = let the scan decide)
+    std::vector<DcsbTile> tiles;
+    int ntiles94 = 0, ntiles93 = 0;
+    uint64_t total_frames_in = 0;            // stream frames (checkpoint entries)
+    uint64_t total_out_frames = 0;
+    uint64_t compressed_bytes = 0;
+    size_t slab_bytes = 0;
+    // device
+    uint8_t *d_slab = nullptr;
+    DcsbStreamRec *d_recs = nullptr;
+    DcsbTile *d_tiles = nullptr;
+    DcsbScanOut scan{};
+    int16_t *d_pcm = nullptr;                // internal PCM buffer (lazy)
+    unsigned long long *d_checksums = nullptr;
+    cudaEvent_t ev[3] = { nullptr, nullptr, nullptr };
+    bool timed = false;
+};
+
+static inline int fail(dcsb_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (ctx) {
+        char buf[512];
+        if (e != cudaSuccess) snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+        else snprintf(buf, sizeof(buf), "%s", what);
+        ctx->err = buf;
+    }
+    return code;
+}
+#define CK(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, DCSB_E_CUDA, what, e_); } while (0)
+
+
+int dcsb_batch_create_impl(dcsb_ctx *ctx, const dcsb_stream_desc *descs, size_t n, const uint8_t *in_place_base,
+                           size_t in_place_span, dcsb_batch **out);

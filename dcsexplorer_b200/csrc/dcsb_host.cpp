@@ -214,13 +214,15 @@ int dcsb_prepare(const dcsb_stream_desc *descs, size_t n, DcsbPrepared *p, const
         // frames rendered = U16 frame count + tail, whatever happens later (rejected and
         // failing streams render silence), so callers can lay out PCM from the first 2 bytes
         uint32_t nf = (d.data && d.nbytes >= 2) ? (((uint32_t)d.data[0] << 8) | d.data[1]) : 0;
+        const bool wrap = (d.reserved & DCSB_STREAM_WRAP_EMPTY) != 0;
         r.out_frames = nf + d.tail_frames;
         if (!d.data || d.nbytes < 3 || d.nbytes < 2u + r.hdr_len) { p->host_status[i] = DCSB_E_SHORT; nf = 0; }
         else {
-            if (nf == 0) p->host_status[i] = DCSB_E_EMPTY;
+            if (nf == 0 && wrap) { nf = 65536; r.out_frames = nf + d.tail_frames; }      // the reference's uint16 counter wraps (:1411-1415, :1565)
+            else if (nf == 0) p->host_status[i] = DCSB_E_EMPTY;
             memcpy(r.hdr, d.data + 2, r.hdr_len);
         }
-        r.nframes = (uint16_t)nf;
+        r.nframes = nf;
         stream_gain(d, r);
         if (fmt == DCSB_FMT_94) items94 += (r.out_frames + item_len - 1) / item_len;
         else for (uint32_t f = 0; f < r.out_frames; f += DCSB_TILE_OUT)

@@ -13,7 +13,7 @@ struct DcsbStreamRec {
     uint32_t nbytes;        // stream bytes
     uint32_t frame_base;    // index of frame 0 in the frame-checkpoint arrays
     uint32_t out_frames;    // frames rendered (nFrames + tail)
-    uint16_t nframes;       // frame count from the stream preamble (0 when rejected on the host)
+    uint16_t pad0;
     uint8_t  fmt;           // DCSB_FMT_*
     uint8_t  hdr_len;       // 16, or 1 for OS93a type 1
     uint16_t mult0, mult1;  // effective channel multiplier for frame 0 / frames >= 1 (host gain staging)
@@ -21,7 +21,9 @@ struct DcsbStreamRec {
     uint8_t  vs_idle;       // volShift once no stream is active (8)
     uint8_t  pad[1];
     uint8_t  hdr[16];       // stream header copy
-    uint32_t pad2[2];
+    uint32_t nframes;       // frames to walk: the preamble's count (0 when rejected on the host; 65536 for a
+                            // zero count under DCSB_STREAM_WRAP_EMPTY)
+    uint32_t pad2;
 };
 static_assert(sizeof(DcsbStreamRec) == 64, "DcsbStreamRec layout");
 
@@ -113,3 +115,9 @@ int dcsb_scan_lanes(int nstreams);       // streams per warp the scan launch use
 cudaError_t dcsb_launch_decode(const uint8_t *slab, const DcsbStreamRec *streams, const DcsbTile *tiles,
                                int ntiles94, int ntiles93, const DcsbTables *tables, DcsbScanOut scan,
                                int16_t *pcm, unsigned long long *checksums, cudaStream_t st);
+
+// K4 launch (dcsb_mix.cuh): items = DcsbMixItem[], frames = DcsbSchedFrame[], entries = DcsbSchedEntry[]
+// (device pointers; the types live in dcsb_rom.h / dcsb_mix.cuh).  family93 selects the 1993 transform.
+cudaError_t dcsb_launch_mix(bool family93, const uint8_t *slab, const DcsbStreamRec *streams, const void *items, int nitems,
+                            const void *frames, const void *entries, const DcsbTables *tables, DcsbScanOut scan,
+                            int16_t *pcm, unsigned long long *checksums, cudaStream_t st);

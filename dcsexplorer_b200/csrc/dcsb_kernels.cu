@@ -15,6 +15,7 @@
 #include "dcsb_core.cuh"
 #include "dcsb_fast94.cuh"
 #include "dcsb_scan94.cuh"
+#include "dcsb_mix.cuh"
 
 #define DCSB_WARPS_PER_CTA 4
 
@@ -128,6 +129,86 @@ dcsb_decode94_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__re
         for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
         if (lane == 0) atomicAdd(checksums + it.stream, csum);
     }
+}
+
+// ------------------------------------------------------------------------------------
+// K4: channel mix for track playback (dcsb_mix.cuh).  Same shapes as the single-stream decode
+// kernels: 1994 layout one lane per output frame, 1993 layouts one warp-cooperative tile.
+struct DcsbSmemMix94 {
+    uint16_t lut[DCSB_LUT_WORDS];
+    DcsbTw94 tw;
+    uint8_t hdr[DCSB_WARPS94][32][16];
+    uint32_t rows[DCSB_WARPS94][DCSB_WARP94_WORDS];
+};
+
+__global__ void __launch_bounds__(DCSB_WARPS94 * 32, 3)
+dcsb_mix94_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restrict__ streams,
+                  const DcsbMixItem *__restrict__ items, int nitems, DcsbMixSched sched, const DcsbTables *__restrict__ tab,
+                  DcsbScanOut scan, int16_t *__restrict__ pcm, unsigned long long *__restrict__ checksums)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    DcsbSmemMix94 &sm = *reinterpret_cast<DcsbSmemMix94 *>(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * DCSB_WARPS94 + warp;
+    {
+        int *dst = reinterpret_cast<int *>(&sm.tw);
+        for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+            dst[i] = tab->tw_c2[i]; dst[64 + i] = tab->tw_s2[i]; dst[128 + i] = tab->pre_c0[i]; dst[192 + i] = tab->pre_c1[i];
+        }
+    }
+    dcsb_load_lut(sm.lut, tab);
+    if (item >= nitems) return;
+    const DcsbMixItem it = items[item];
+    unsigned long long csum = dcsb_mix94_item(slab, streams, it, sched, tab, sm.lut, &sm.tw, scan, pcm, sm.rows[warp], &sm.hdr[warp][0][0]);
+    if (checksums) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+        if (lane == 0) atomicAdd(checksums + it.timeline, csum);
+    }
+}
+
+__global__ void __launch_bounds__(DCSB_WARPS_PER_CTA * 32)
+dcsb_mix93_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restrict__ streams,
+                  const DcsbMixItem *__restrict__ items, int nitems, DcsbMixSched sched, const DcsbTables *__restrict__ tab,
+                  DcsbScanOut scan, int16_t *__restrict__ pcm, unsigned long long *__restrict__ checksums)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(smem);
+    uint32_t *s_rows = smem + DCSB_LUT_WORDS / 2;
+    dcsb_load_lut(s_lut, tab);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * DCSB_WARPS_PER_CTA + warp;
+    if (item >= nitems) return;
+    const DcsbMixItem it = items[item];
+    unsigned long long csum = dcsb_mix93_tile(slab, streams, it, sched, tab, s_lut, scan, pcm, s_rows + warp * DcsbWarpSmem<true>::WORDS);
+    if (checksums) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+        if (lane == 0) atomicAdd(checksums + it.timeline, csum);
+    }
+}
+
+cudaError_t dcsb_launch_mix(bool family93, const uint8_t *slab, const DcsbStreamRec *streams, const void *items, int nitems,
+                            const void *frames, const void *entries, const DcsbTables *tables, DcsbScanOut scan,
+                            int16_t *pcm, unsigned long long *checksums, cudaStream_t st)
+{
+    if (nitems <= 0) return cudaSuccess;
+    DcsbMixSched sc{ static_cast<const DcsbSchedFrame *>(frames), static_cast<const DcsbSchedEntry *>(entries) };
+    const DcsbMixItem *it = static_cast<const DcsbMixItem *>(items);
+    if (family93) {
+        const size_t smem = (DCSB_LUT_WORDS / 2 + DCSB_WARPS_PER_CTA * DcsbWarpSmem<true>::WORDS) * sizeof(uint32_t);
+        cudaError_t e = cudaFuncSetAttribute(dcsb_mix93_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        const int grid = (nitems + DCSB_WARPS_PER_CTA - 1) / DCSB_WARPS_PER_CTA;
+        dcsb_mix93_kernel<<<grid, DCSB_WARPS_PER_CTA * 32, smem, st>>>(slab, streams, it, nitems, sc, tables, scan, pcm, checksums);
+    } else {
+        const size_t smem = sizeof(DcsbSmemMix94);
+        cudaError_t e = cudaFuncSetAttribute(dcsb_mix94_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        const int grid = (nitems + DCSB_WARPS94 - 1) / DCSB_WARPS94;
+        dcsb_mix94_kernel<<<grid, DCSB_WARPS94 * 32, smem, st>>>(slab, streams, it, nitems, sc, tables, scan, pcm, checksums);
+    }
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------

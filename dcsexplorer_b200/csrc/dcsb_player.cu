@@ -1,0 +1,370 @@
+// dcsb200 C-ABI, part 2: ROM sets, players and timelines (include/dcsb200.h).  The host runs the
+// reference's control plane (dcsb_rom.cpp); this file uploads the ROM's streams once, scans them
+// on the GPU, turns sequencer output into mix work items and launches K4 (dcsb_mix.cuh).
+#include <string.h>
+#include <algorithm>
+#include <thread>
+#include "dcsb_ctx.h"
+#include "dcsb_rom.h"
+#include "dcsb_mix.cuh"
+
+// ======================================================================================
+// ROM object
+extern "C" int dcsb_rom_create(dcsb_rom **out)
+{
+    if (!out) return DCSB_E_ARG;
+    *out = new dcsb_rom();
+    return DCSB_OK;
+}
+
+static void rom_drop_batch(dcsb_rom *rom)
+{
+    if (rom->batch) { dcsb_batch_destroy(rom->batch); rom->batch = nullptr; }
+    rom->streams.clear();
+    rom->stream_by_addr.clear();
+}
+
+extern "C" void dcsb_rom_destroy(dcsb_rom *rom)
+{
+    if (!rom) return;
+    rom_drop_batch(rom);
+    delete rom;
+}
+
+extern "C" int dcsb_rom_add(dcsb_rom *rom, int chip_number, const uint8_t *image, size_t nbytes)
+{
+    if (!rom || !image || chip_number < 2 || chip_number > 9 || nbytes == 0 || (nbytes & (nbytes - 1))) return DCSB_E_ARG;
+    rom_drop_batch(rom);
+    rom->add(chip_number, image, nbytes);
+    rom->hw = DCSB_HW_UNKNOWN;          // versions are re-detected by the next check
+    return DCSB_OK;
+}
+
+extern "C" int dcsb_rom_load_zip(dcsb_rom *rom, const char *zip_path, const char *explicit_u2)
+{
+    if (!rom || !zip_path) return DCSB_ZIP_E_OPEN;
+    rom_drop_batch(rom);
+    const int rc = dcsb_rom_load_zip_impl(rom, zip_path, explicit_u2);
+    rom->hw = DCSB_HW_UNKNOWN;
+    return rc;
+}
+
+extern "C" int dcsb_rom_check(dcsb_rom *rom) { return rom ? rom->check() : 2; }
+extern "C" const char *dcsb_rom_last_error(const dcsb_rom *rom) { return rom ? rom->err.c_str() : "no rom"; }
+
+extern "C" int dcsb_rom_get_info(const dcsb_rom *rom, dcsb_rom_info *info)
+{
+    if (!rom || !info) return DCSB_E_ARG;
+    memset(info, 0, sizeof(*info));
+    info->os_version = rom->os > 1 ? (uint16_t)rom->os : 0;
+    info->hw_version = (uint8_t)rom->hw;
+    info->n_channels = (uint8_t)rom->num_channels();
+    // GetVersionNumber (DCSDecoder.cpp:506-512)
+    info->version_number = rom->nominal_version ? rom->nominal_version
+                           : (rom->os == DCSB_OS93A || rom->os == DCSB_OS93B) ? 0x0100 : rom->os == DCSB_OS94 ? 0x0101 : 0;
+    info->n_tracks = rom->n_tracks;
+    info->catalog_offset = rom->catalog_ofs;
+    info->post_code = rom->post;
+    snprintf(info->signature, sizeof(info->signature), "%s", rom->signature.c_str());
+    return DCSB_OK;
+}
+
+extern "C" int dcsb_rom_track_info(const dcsb_rom *rom, uint16_t track, dcsb_track_info *info)
+{
+    if (!rom || !info) return 0;
+    return rom->track_info(track, info) ? 1 : 0;
+}
+
+extern "C" size_t dcsb_rom_list_streams(const dcsb_rom *rom, uint32_t *addresses, size_t max)
+{
+    if (!rom) return 0;
+    const std::vector<uint32_t> l = rom->list_streams();
+    for (size_t i = 0; i < l.size() && i < max && addresses; ++i) addresses[i] = l[i];
+    return l.size();
+}
+
+extern "C" const uint8_t *dcsb_rom_pointer(const dcsb_rom *rom, uint32_t linear_address, uint32_t *bytes_left)
+{
+    if (bytes_left) *bytes_left = 0;
+    if (!rom) return nullptr;
+    const DcsbRomPtr p = rom->make_ptr(linear_address);
+    const dcsb_rom::Chip &c = rom->chip[p.chip];
+    if (!c.present || p.ofs >= c.size) return nullptr;
+    if (bytes_left) *bytes_left = c.size - p.ofs;
+    return c.bytes.data() + p.ofs;
+}
+
+// ======================================================================================
+// stream table: every stream of the ROM resident in HBM + scanned once
+static int rom_prepare(dcsb_ctx *ctx, dcsb_rom *rom)
+{
+    if (rom->batch && rom->batch->ctx == ctx) return DCSB_OK;
+    rom_drop_batch(rom);
+    if (rom->hw == DCSB_HW_UNKNOWN) rom->check();          // SoftBoot detects the versions if nobody has (DCSDecoder.cpp:1533-1534)
+    if (rom->os <= 1) return fail(ctx, DCSB_E_ARG, "ROM set not recognised (no catalog / checksum match in U2)");
+    std::vector<uint32_t> addrs = rom->list_streams(true);
+    {   // (plus whatever only the reference's own listing finds: dcsb_player_load_audio_stream accepts those too)
+        const std::vector<uint32_t> more = rom->list_streams(false);
+        addrs.insert(addrs.end(), more.begin(), more.end());
+        std::sort(addrs.begin(), addrs.end());
+        addrs.erase(std::unique(addrs.begin(), addrs.end()), addrs.end());
+    }
+    // all chips back to back, 1 KB of zeros behind each
+    rom->image.clear();
+    for (int c = 0; c < 8; ++c) {
+        rom->image_ofs[c] = (uint32_t)rom->image.size();
+        if (!rom->chip[c].present) continue;
+        rom->image.insert(rom->image.end(), rom->chip[c].bytes.begin(), rom->chip[c].bytes.begin() + rom->chip[c].size);
+        rom->image.resize(rom->image.size() + 1024, 0);
+    }
+    if (rom->image.empty()) rom->image.resize(1024, 0);
+    std::vector<dcsb_stream_desc> descs;
+    for (uint32_t a : addrs) {
+        const DcsbRomPtr p = rom->make_ptr(a);
+        DcsbStreamFacts sf;
+        sf.linear = a;
+        sf.at = p;
+        dcsb_stream_desc d;
+        memset(&d, 0, sizeof(d));
+        d.os_version = (uint16_t)rom->os;
+        d.master_volume = 255;
+        d.mixing_level = 0x64;
+        d.reserved = DCSB_STREAM_WRAP_EMPTY;
+        if (rom->chip[p.chip].present && p.ofs < rom->chip[p.chip].size) {
+            d.data = rom->image.data() + rom->image_ofs[p.chip] + p.ofs;
+            d.nbytes = rom->chip[p.chip].size - p.ofs;
+            sf.nframes = (uint16_t)rom->be(p, 2);
+        } else {
+            d.data = rom->image.data();         // stream in a missing chip: rejected as too short
+            d.nbytes = 0;
+        }
+        rom->stream_by_addr[a & 0xFFFFFFu] = (uint32_t)rom->streams.size();
+        rom->streams.push_back(sf);
+        descs.push_back(d);
+    }
+    int rc = dcsb_batch_create_impl(ctx, descs.data(), descs.size(), rom->image.data(), rom->image.size(), &rom->batch);
+    if (rc != DCSB_OK) return rc;
+    dcsb_batch *b = rom->batch;
+    if (b->n) {
+        CK(dcsb_launch_scan(b->d_slab, b->d_recs, (int)b->n, 0, ctx->d_tables, b->scan, nullptr), "scan kernel launch");
+        CK(cudaDeviceSynchronize(), "ROM stream scan");
+        std::vector<int32_t> st(b->n);
+        std::vector<uint32_t> np(b->n);
+        CK(cudaMemcpy(st.data(), b->scan.status, b->n * 4, cudaMemcpyDeviceToHost), "D2H status");
+        CK(cudaMemcpy(np.data(), b->scan.nplay, b->n * 4, cudaMemcpyDeviceToHost), "D2H nplay");
+        for (size_t i = 0; i < b->n; ++i) {
+            rom->streams[i].status = b->host_status[i] ? b->host_status[i] : st[i];
+            rom->streams[i].nplay = b->host_status[i] ? 0 : np[i];
+        }
+    }
+    return DCSB_OK;
+}
+
+// ======================================================================================
+// rendering a schedule
+struct DcsbRenderBufs {
+    DcsbBuf d_frames, d_entries, d_items, d_pcm, d_csum, h_pcm;
+    void release()
+    {
+        for (DcsbBuf *b : { &d_frames, &d_entries, &d_items, &d_pcm, &d_csum }) b->release(false);
+        h_pcm.release(true);
+    }
+};
+
+// frames / entries: the whole schedule; tl_first[t], tl_frames[t]: each timeline's slice; skip[t]:
+// leading frames that are only there to warm the overlap up (not rendered).  PCM lands in
+// bufs.d_pcm at 240 * (global frame index) samples.
+static int render_schedule(dcsb_ctx *ctx, dcsb_rom *rom, DcsbRenderBufs &bufs, const std::vector<DcsbSchedFrame> &frames,
+                           const std::vector<DcsbSchedEntry> &entries, const std::vector<uint32_t> &tl_first,
+                           const std::vector<uint32_t> &tl_frames, const std::vector<uint32_t> &skip, cudaStream_t st)
+{
+    dcsb_batch *b = rom->batch;
+    const bool fam93 = rom->os == DCSB_OS93A || rom->os == DCSB_OS93B;
+    const size_t nt = tl_first.size();
+    // work items: 1994 layout 31 + 32k frames per warp, 1993 layouts tiles of 31
+    uint64_t total = 0;
+    for (size_t t = 0; t < nt; ++t) total += tl_frames[t];
+    uint32_t item_len = DCSB_TILE_OUT;
+    if (!fam93) {
+        item_len = (uint32_t)std::min<uint64_t>(255, std::max<uint64_t>(31, total / 8192));
+        item_len = item_len < 63 ? 31 : 31 + ((item_len - 31) / 32) * 32;
+    }
+    std::vector<DcsbMixItem> items;
+    for (size_t t = 0; t < nt; ++t)
+        for (uint32_t f = skip[t]; f < tl_frames[t]; f += item_len)
+            items.push_back(DcsbMixItem{ tl_first[t] + f, std::min<uint32_t>(item_len, tl_frames[t] - f), tl_first[t], (uint32_t)t });
+    if (items.empty()) return DCSB_OK;
+#define ENS(buf, bytes, what) do { cudaError_t e_ = (buf).ensure((bytes), false); if (e_ != cudaSuccess) return fail(ctx, DCSB_E_NOMEM, what, e_); } while (0)
+    ENS(bufs.d_frames, frames.size() * sizeof(DcsbSchedFrame), "cudaMalloc(schedule frames)");
+    ENS(bufs.d_entries, std::max<size_t>(1, entries.size()) * sizeof(DcsbSchedEntry), "cudaMalloc(schedule entries)");
+    ENS(bufs.d_items, items.size() * sizeof(DcsbMixItem), "cudaMalloc(mix items)");
+    ENS(bufs.d_pcm, frames.size() * 480, "cudaMalloc(pcm)");
+    ENS(bufs.d_csum, nt * 8, "cudaMalloc(checksums)");
+#undef ENS
+    CK(cudaMemcpyAsync(bufs.d_frames.p, frames.data(), frames.size() * sizeof(DcsbSchedFrame), cudaMemcpyHostToDevice, st), "H2D frames");
+    if (!entries.empty())
+        CK(cudaMemcpyAsync(bufs.d_entries.p, entries.data(), entries.size() * sizeof(DcsbSchedEntry), cudaMemcpyHostToDevice, st), "H2D entries");
+    CK(cudaMemcpyAsync(bufs.d_items.p, items.data(), items.size() * sizeof(DcsbMixItem), cudaMemcpyHostToDevice, st), "H2D items");
+    CK(cudaMemsetAsync(bufs.d_csum.p, 0, nt * 8, st), "memset checksums");
+    CK(dcsb_launch_mix(fam93, b->d_slab, b->d_recs, bufs.d_items.p, (int)items.size(), bufs.d_frames.p, bufs.d_entries.p,
+                       ctx->d_tables, b->scan, (int16_t *)bufs.d_pcm.p, (unsigned long long *)bufs.d_csum.p, st), "mix kernel launch");
+    return DCSB_OK;
+}
+
+// ======================================================================================
+// player
+struct dcsb_player {
+    dcsb_ctx *ctx;
+    dcsb_rom *rom;
+    DcsbSequencer seq;
+    DcsbRenderBufs bufs;
+    std::vector<DcsbSchedEntry> prev_entries;       // the last rendered frame: warms the overlap of the next chunk up
+    DcsbSchedFrame prev_frame{ 0, 0, 8, 0, 0 };
+    bool have_prev = false;
+    size_t host_read = 0;
+    dcsb_player(dcsb_ctx *c, dcsb_rom *r) : ctx(c), rom(r), seq(r) {}
+};
+
+extern "C" int dcsb_player_create(dcsb_ctx *ctx, dcsb_rom *rom, dcsb_player **out)
+{
+    if (!ctx || !rom || !out) return DCSB_E_ARG;
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const int rc = rom_prepare(ctx, rom);
+    if (rc != DCSB_OK) return rc;
+    dcsb_player *p = new dcsb_player(ctx, rom);
+    p->seq.soft_boot();
+    *out = p;
+    return DCSB_OK;
+}
+
+extern "C" void dcsb_player_destroy(dcsb_player *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    p->bufs.release();
+    delete p;
+}
+
+extern "C" void dcsb_player_set_master_volume(dcsb_player *p, int vol) { if (p) p->seq.set_master_volume(vol); }
+extern "C" void dcsb_player_write_data_port(dcsb_player *p, uint8_t byte) { if (p) p->seq.write_port(byte); }
+extern "C" void dcsb_player_add_track_command(dcsb_player *p, uint16_t track) { if (p) p->seq.add_track_command(track); }
+extern "C" void dcsb_player_clear_tracks(dcsb_player *p) { if (p) p->seq.clear_tracks(); }
+extern "C" int dcsb_player_is_stream_playing(const dcsb_player *p, int channel) { return p && p->seq.stream_playing(channel) ? 1 : 0; }
+
+extern "C" int dcsb_player_load_audio_stream(dcsb_player *p, int channel, uint32_t stream_address, int mixing_level)
+{
+    if (!p || channel < 0 || channel >= DCSB_MAX_CHANNELS) return DCSB_E_ARG;
+    if (p->rom->stream_by_addr.find(stream_address & 0xFFFFFFu) == p->rom->stream_by_addr.end())
+        return fail(p->ctx, DCSB_E_ARG, "dcsb_player_load_audio_stream: not a stream any track of this ROM plays");
+    p->seq.load_stream(channel, stream_address, mixing_level);
+    return DCSB_OK;
+}
+
+extern "C" size_t dcsb_player_host_bytes(dcsb_player *p, uint8_t *out, size_t max)
+{
+    if (!p) return 0;
+    size_t n = 0;
+    while (p->host_read < p->seq.host_bytes.size() && n < max) out[n++] = p->seq.host_bytes[p->host_read++];
+    return n;
+}
+
+extern "C" int dcsb_player_render(dcsb_player *p, uint32_t n_frames, int16_t *pcm_out)
+{
+    if (!p || (!pcm_out && n_frames)) return DCSB_E_ARG;
+    dcsb_ctx *ctx = p->ctx;
+    if (n_frames == 0) return DCSB_OK;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    std::vector<DcsbSchedFrame> frames;
+    std::vector<DcsbSchedEntry> entries;
+    const uint32_t lead = p->have_prev ? 1u : 0u;
+    if (lead) {
+        entries = p->prev_entries;
+        frames.push_back(DcsbSchedFrame{ 0, (uint8_t)entries.size(), p->prev_frame.vs, p->prev_frame.flags, 0 });
+    }
+    for (uint32_t f = 0; f < n_frames; ++f) p->seq.frame(frames, entries);
+    const DcsbSchedFrame last = frames.back();
+    p->prev_entries.assign(entries.begin() + last.first_entry, entries.begin() + last.first_entry + last.n_entries);
+    p->prev_frame = last;
+    p->have_prev = true;
+    std::vector<uint32_t> first{ 0 }, count{ n_frames + lead }, skip{ lead };
+    int rc = render_schedule(ctx, p->rom, p->bufs, frames, entries, first, count, skip, nullptr);
+    if (rc != DCSB_OK) return rc;
+    CK(cudaMemcpy(pcm_out, (const int16_t *)p->bufs.d_pcm.p + (size_t)lead * 240, (size_t)n_frames * 480, cudaMemcpyDeviceToHost), "D2H pcm");
+    return DCSB_OK;
+}
+
+// ======================================================================================
+// many timelines at once
+extern "C" int dcsb_render_timelines(dcsb_ctx *ctx, dcsb_rom *rom, const dcsb_timeline *timelines, size_t n,
+                                     int16_t *pcm_out, const uint64_t *pcm_offsets, dcsb_timeline_result *results)
+{
+    if (!ctx || !rom || (!timelines && n) || (!pcm_out && n)) return fail(ctx, DCSB_E_ARG, "dcsb_render_timelines: bad argument");
+    if (n == 0) return DCSB_OK;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    int rc = rom_prepare(ctx, rom);
+    if (rc != DCSB_OK) return rc;
+    // host: one sequencer per timeline, a few threads
+    struct Part { std::vector<DcsbSchedFrame> frames; std::vector<DcsbSchedEntry> entries; bool fatal = false; uint32_t nhost = 0; };
+    std::vector<Part> parts(n);
+    auto work = [&](size_t t) {
+        const dcsb_timeline &tl = timelines[t];
+        Part &pt = parts[t];
+        DcsbSequencer seq(rom);
+        seq.soft_boot();
+        seq.set_master_volume(tl.master_volume);
+        uint32_t w = 0;
+        pt.frames.reserve(tl.n_frames);
+        for (uint32_t f = 0; f < tl.n_frames; ++f) {
+            while (w < tl.n_writes && tl.writes[w].frame <= f) seq.write_port(tl.writes[w++].byte);
+            seq.frame(pt.frames, pt.entries);
+        }
+        pt.fatal = seq.fatal;
+        pt.nhost = (uint32_t)seq.host_bytes.size();
+    };
+    const unsigned nth = (unsigned)std::min<size_t>(n, std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
+    if (nth <= 1) for (size_t t = 0; t < n; ++t) work(t);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned k = 0; k < nth; ++k) th.emplace_back([&, k] { for (size_t t = k; t < n; t += nth) work(t); });
+        for (auto &x : th) x.join();
+    }
+    std::vector<DcsbSchedFrame> frames;
+    std::vector<DcsbSchedEntry> entries;
+    std::vector<uint32_t> first(n), count(n), skip(n, 0);
+    for (size_t t = 0; t < n; ++t) {
+        first[t] = (uint32_t)frames.size();
+        count[t] = (uint32_t)parts[t].frames.size();
+        const uint32_t ebase = (uint32_t)entries.size();
+        for (DcsbSchedFrame fr : parts[t].frames) { fr.first_entry += ebase; frames.push_back(fr); }
+        entries.insert(entries.end(), parts[t].entries.begin(), parts[t].entries.end());
+    }
+    if (frames.empty()) return DCSB_OK;
+    DcsbRenderBufs bufs;
+    rc = render_schedule(ctx, rom, bufs, frames, entries, first, count, skip, nullptr);
+    cudaError_t e = cudaSuccess;
+    if (rc == DCSB_OK) {
+        bool packed = true;
+        for (size_t t = 0; t < n && pcm_offsets; ++t) if (pcm_offsets[t] != (uint64_t)first[t] * 240) packed = false;
+        if (packed) e = cudaMemcpy(pcm_out, bufs.d_pcm.p, frames.size() * 480, cudaMemcpyDeviceToHost);
+        else
+            for (size_t t = 0; t < n && e == cudaSuccess; ++t)
+                if (count[t]) e = cudaMemcpy(pcm_out + pcm_offsets[t], (const int16_t *)bufs.d_pcm.p + (size_t)first[t] * 240,
+                                             (size_t)count[t] * 480, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && results) {
+            std::vector<unsigned long long> cs(n);
+            e = cudaMemcpy(cs.data(), bufs.d_csum.p, n * 8, cudaMemcpyDeviceToHost);
+            for (size_t t = 0; t < n; ++t) {
+                results[t].status = parts[t].fatal ? DCSB_E_STOPPED : DCSB_OK;
+                results[t].frames = count[t];
+                results[t].checksum = cs[t];
+                results[t].n_host_bytes = parts[t].nhost;
+                results[t].reserved = 0;
+            }
+        }
+    }
+    bufs.release();
+    if (rc != DCSB_OK) return rc;
+    if (e != cudaSuccess) return fail(ctx, DCSB_E_CUDA, "dcsb_render_timelines: D2H", e);
+    return DCSB_OK;
+}

@@ -1,0 +1,761 @@
+// dcsb200 host control plane for ROM sets -- see dcsb_rom.h for the map to the reference.
+#include <ctype.h>
+#include <stdio.h>
+#include <string.h>
+#include <strings.h>
+#include <algorithm>
+#include <set>
+#include <zlib.h>
+#include "dcsb_rom.h"
+
+// ======================================================================================
+// ROM model
+static const uint32_t kCatalogOffsets[3] = { 0x3000, 0x4000, 0x6000 };
+
+static bool is_jump(const uint8_t *p) { return (p[0] & 0xFC) == 0x18 && (p[2] & 0x0F) == 0x0F; }   // ADSP-2105 JUMP
+
+static std::string read_signature(const uint8_t *u2, size_t size)
+{
+    // JUMP at offset 0, printable text from offset 4 up to a NUL (DCSDecoder.cpp:100-127)
+    if (size < 8 || !is_jump(u2)) return "";
+    size_t len = 0;
+    while (len < 120 && 4 + len < size && u2[4 + len] >= 32 && u2[4 + len] < 127) ++len;
+    if (4 + len >= size || u2[4 + len] != 0) return "";
+    return std::string(reinterpret_cast<const char *>(u2 + 4), len);
+}
+
+static bool contains_nocase(const std::string &hay, const char *needle)
+{
+    const size_t n = strlen(needle);
+    for (size_t i = 0; i + n <= hay.size(); ++i)
+        if (strncasecmp(hay.c_str() + i, needle, n) == 0) return true;
+    return false;
+}
+
+void dcsb_rom::add(int n, const uint8_t *data, size_t size)
+{
+    if (n < 2 || n > 9 || size == 0 || !data) return;
+    Chip &c = chip[n - 2];
+    c.bytes.assign(data, data + size);
+    c.bytes.resize(size + 64, 0xFF);
+    c.size = (uint32_t)size;
+    c.mask = (uint32_t)(size - 1);
+    c.present = true;
+    batch = nullptr;        // (an already prepared stream table belongs to the old images; dcsb_api.cu frees it)
+    if (n != 2) return;
+    // the catalog: first entry describes U2 itself -- its size in 4 KB units, chip select 0,
+    // checksum 0 (DCSDecoder.cpp:207-234)
+    catalog_ofs = 0;
+    for (uint32_t ofs : kCatalogOffsets) {
+        if (ofs + 0x48 > size) continue;
+        const uint32_t sz = u2_be(ofs, 2) * 4096u, sel = u2_be(ofs + 2, 2) >> 8, ck = u2_be(ofs + 4, 2);
+        if (sel == 0 && ck == 0 && sz == size) { catalog_ofs = ofs; break; }
+    }
+    track_index = indirect_index = 0;
+    n_tracks = 0;
+    if (catalog_ofs) {
+        track_index = u2_be(catalog_ofs + 0x40, 3);
+        indirect_index = u2_be(catalog_ofs + 0x43, 3);
+        n_tracks = (uint16_t)u2_be(catalog_ofs + 0x46, 2);
+    }
+    signature = read_signature(data, size);
+    totan = contains_nocase(signature, "Arabian Nights");       // game-specific data port quirk (DCSDecoderNative.cpp:3345)
+}
+
+uint32_t dcsb_rom::u2_be(uint32_t ofs, int nbytes) const
+{
+    uint32_t v = 0;
+    for (int i = 0; i < nbytes; ++i) v = (v << 8) | (ofs + i < chip[0].size ? chip[0].bytes[ofs + i] : 0xFFu);
+    return v;
+}
+
+DcsbRomPtr dcsb_rom::make_ptr(uint32_t linear) const
+{
+    // chip select in bits 21-23 on the DCS-95 board, 20-22 on the original one (DCSDecoder.cpp:67-76)
+    DcsbRomPtr p;
+    p.chip = (int)((linear >> (hw == DCSB_HW_DCS95 ? 21 : 20)) & 7);
+    p.ofs = linear & (chip[p.chip].present ? chip[p.chip].mask : 0x1FFFu);     // absent chips read as 8 KB of $FF
+    return p;
+}
+
+uint8_t dcsb_rom::u8(const DcsbRomPtr &p, uint32_t d) const
+{
+    if (p.chip < 0) return 0xFF;
+    const Chip &c = chip[p.chip];
+    const uint64_t o = (uint64_t)p.ofs + d;
+    return (c.present && o < c.size) ? c.bytes[o] : 0xFF;
+}
+
+uint32_t dcsb_rom::be(const DcsbRomPtr &p, int nbytes, uint32_t d) const
+{
+    uint32_t v = 0;
+    for (int i = 0; i < nbytes; ++i) v = (v << 8) | u8(p, d + i);
+    return v;
+}
+
+// Opcode pattern search over U2: 24-bit big-endian opcodes in 4-byte slots; pattern digits are
+// literal hex, '*' is a wildcard nibble, any other letter names a variable (DCSDecoder.cpp:1734-1908)
+int dcsb_rom::search_opcodes(const char *pattern, uint32_t from, uint32_t nbytes, std::unordered_map<char, uint32_t> *vars) const
+{
+    struct Op { uint32_t value, mask; };
+    struct Var { char name; int op; int shift; uint32_t mask; };
+    std::vector<Op> ops;
+    std::vector<Var> vlist;
+    for (const char *p = pattern; *p;) {
+        while (*p == ' ') ++p;
+        if (!*p) break;
+        Op op{ 0, 0 };
+        Var cur{ 0, 0, 0, 0 };
+        for (int i = 0; i < 6 && *p && *p != ' '; ++i, ++p) {
+            const char c = *p;
+            const bool hex = isdigit((unsigned char)c) || (c >= 'a' && c <= 'f') || (c >= 'A' && c <= 'F');
+            if (hex || c == '*') {
+                const uint32_t d = !hex ? 0 : (uint32_t)(isdigit((unsigned char)c) ? c - '0' : (tolower(c) - 'a' + 10));
+                op.value = (op.value << 4) | d;
+                op.mask = (op.mask << 4) | (hex ? 0xFu : 0u);
+                if (cur.name) { vlist.push_back(cur); cur = Var{ 0, 0, 0, 0 }; }
+            } else {
+                if (cur.name && cur.name != c) { vlist.push_back(cur); cur = Var{ 0, 0, 0, 0 }; }
+                cur.name = c;
+                cur.op = (int)ops.size();
+                cur.shift = 20 - 4 * i;
+                cur.mask = (cur.mask << 4) | 0xFu;
+                op.value <<= 4;
+                op.mask <<= 4;
+            }
+        }
+        if (cur.name) vlist.push_back(cur);
+        ops.push_back(op);
+    }
+    const uint32_t nops = nbytes / 4;
+    auto fetch = [&](uint32_t i) { return u2_be(from + 4 * i, 3); };
+    for (uint32_t a = 0; a + ops.size() < nops; ++a) {
+        bool ok = true;
+        for (size_t k = 0; k < ops.size() && ok; ++k) ok = (fetch(a + (uint32_t)k) & ops[k].mask) == ops[k].value;
+        if (!ok) continue;
+        if (vars)
+            for (const Var &v : vlist) (*vars)[v.name] = (fetch(a + (uint32_t)v.op) >> v.shift) & v.mask;
+        return (int)(a * 4);
+    }
+    return -1;
+}
+
+static uint16_t chip_checksum(const uint8_t *p, size_t n)
+{
+    // sum of even-offset bytes in the high byte, of odd-offset bytes in the low byte (DCSDecoder.cpp:653-669)
+    unsigned even = 0, odd = 0;
+    for (size_t i = 0; i + 1 < n + 1 && i < n; i += 2) { even += p[i]; if (i + 1 < n) odd += p[i + 1]; }
+    return (uint16_t)(((even << 8) & 0xFF00u) | (odd & 0xFFu));
+}
+
+int dcsb_rom::check()
+{
+    hw = DCSB_HW_INVALID;
+    os = 1;
+    nominal_version = 0;
+    if (!chip[0].present) return post = 2;
+    uint16_t sums[8] = { 0 };
+    int populated = 0;
+    for (int i = 0; i < 8; ++i)
+        if (chip[i].present) { sums[i] = chip_checksum(chip[i].bytes.data(), chip[i].size); ++populated; }
+    for (uint32_t ofs : kCatalogOffsets) {
+        if (ofs + 9 * 6 > chip[0].size) continue;
+        int in_table = 0, validated = 0, first_failed = -1;
+        for (int e = 0; e < 9; ++e) {
+            const uint32_t size = u2_be(ofs + 6 * e, 2) * 4096u;
+            uint32_t sel = u2_be(ofs + 6 * e + 2, 2) >> 8;
+            const uint32_t ck = u2_be(ofs + 6 * e + 4, 2);
+            if (size == 0) break;
+            ++in_table;
+            if (ofs == 0x6000) sel >>= 1;                       // DCS-95 bank numbers carry one more bit
+            if (sel < 8 && chip[sel].present && chip[sel].size == size && sums[sel] == ck) ++validated;
+            else { first_failed = e; break; }
+        }
+        if (validated == 0) continue;
+        if (ofs == 0x6000) {
+            hw = DCSB_HW_DCS95;
+            os = DCSB_OS95;
+            std::unordered_map<char, uint32_t> v;
+            if (search_opcodes("4vvvvE 0F16F8 93300E 18***F 4wwwwE 0F1608 0F16F8 93300E 18***F", 0x2000 + 0x300 * 4, 0x180 * 4, &v) >= 0)
+                nominal_version = (uint16_t)v['v'];
+        } else {
+            hw = DCSB_HW_DCS93;
+            os = DCSB_OS94;
+            if (search_opcodes("380026 3C1005 0C00C0", 0x1000 + 0x100 * 4, 0x180 * 4, nullptr) >= 0) {
+                os = DCSB_OS93B;
+                if (search_opcodes("47FFF2 47C946", 0x2000 + 0x200 * 4, 0x100 * 4, nullptr) >= 0) os = DCSB_OS93A;
+            }
+        }
+        if (validated == populated && populated == in_table) return post = 1;
+        return post = (uint8_t)(first_failed + 2);
+    }
+    return post = 2;
+}
+
+int dcsb_rom::num_channels() const
+{
+    std::unordered_map<char, uint32_t> v;
+    if (chip[0].present &&
+        search_opcodes("22200F 4000n4 26E20F 221800 9****A 8****A 400mm4 26E20F 18***1", 0, 0x6000, &v) >= 0) {
+        const int n = (int)v['n'];
+        if (v['m'] == (uint32_t)((1 << n) - 1)) return n;
+    }
+    return 0;
+}
+
+// operand bytes per opcode as the reference's track scanners count them (DCSDecoder.cpp:836-866)
+int dcsb_rom::opcode_operand_bytes(int opcode) const
+{
+    switch (opcode) {
+    case 0x01: return 5;
+    case 0x02: case 0x05: case 0x0E: return 1;
+    case 0x03: case 0x06: case 0x07: case 0x08: case 0x09: case 0x11: case 0x12: return 2;
+    case 0x0A: case 0x0B: case 0x0C: return 4;
+    case 0x04: return os == DCSB_OS93A ? 3 : 1;
+    default: return 0;
+    }
+}
+
+bool dcsb_rom::track_info(uint16_t track, dcsb_track_info *ti) const
+{
+    memset(ti, 0, sizeof(*ti));
+    ti->defer_code = 0xFFFF;
+    if (track >= n_tracks) return false;
+    const uint32_t addr = u2_be(track_index + 3u * track, 3);
+    if ((addr & 0xFF0000u) == 0xFF0000u) return false;
+    DcsbRomPtr p = make_ptr(addr);
+    const int type = u8(p), ch = u8(p, 1);
+    p.ofs += 2;
+    if (ch > 7) return false;
+    bool done = false;
+    uint16_t defer = 0xFFFF;
+    if (type == 2 || type == 3) { defer = (uint16_t)be(p, 2); done = true; }
+    else if (type != 1) return false;
+    // playing time: wait prefixes summed over nested loops (DCSDecoder.cpp:727-884)
+    struct Level { uint32_t time = 0, loop_stream = 0; uint8_t n = 1; bool forever = false; };
+    std::vector<Level> st(1);
+    for (int guard = 0; !done && guard < 100000; ++guard) {
+        const uint32_t wait = be(p, 2);
+        const int op = u8(p, 2);
+        p.ofs += 3;
+        if (wait == 0xFFFF) {                       // waits forever: what stays audible is the looping stream
+            st.back().forever = true;
+            st.back().time += st.back().loop_stream;
+            break;
+        }
+        st.back().time += wait;
+        if (op == 0x00) break;
+        if (op == 0x01) {
+            const DcsbRomPtr sp = make_ptr(be(p, 3, 1));
+            const int repeat = u8(p, 4);
+            st.back().loop_stream = repeat == 0 ? be(sp, 2) : 0;
+        } else if (op == 0x0E) {
+            Level l;
+            l.n = u8(p);
+            l.forever = l.n == 0;
+            st.push_back(l);
+        } else if (op == 0x0F && st.size() > 1) {
+            const Level l = st.back();
+            st.pop_back();
+            st.back().time += (l.forever ? 1u : l.n) * l.time;
+            if (l.forever) { st.back().forever = true; break; }
+        }
+        p.ofs += (uint32_t)opcode_operand_bytes(op);
+    }
+    while (st.size() > 1) {
+        const Level l = st.back();
+        st.pop_back();
+        st.back().time += (l.n == 0 ? 1u : l.n) * l.time;
+        if (l.forever) st.back().forever = true;
+    }
+    ti->address = addr;
+    ti->channel = ch;
+    ti->type = type;
+    ti->defer_code = defer;
+    ti->time = st.back().time;
+    ti->looping = st.back().forever;
+    return true;
+}
+
+// every stream a Play opcode (0x01) of a type-1 track refers to, ascending.
+// as_executed = false: the reference's ListStreams (DCSDecoder.cpp:1248-1293), which walks the
+// programs with DecompileTrackProgram's operand sizes (:886-1126) -- on 1993 software that
+// miscounts opcode 6 (no operands there) and can miss streams behind it.
+// as_executed = true: operand sizes as ExecTrack consumes them (DCSDecoderNative.cpp:848-1228);
+// this is what the player's stream table is built from.
+std::vector<uint32_t> dcsb_rom::list_streams(bool as_executed) const
+{
+    std::set<uint32_t> found;
+    const bool os93 = os == DCSB_OS93A || os == DCSB_OS93B;
+    for (uint32_t t = 0; t < n_tracks; ++t) {
+        dcsb_track_info ti;
+        if (!track_info((uint16_t)t, &ti) || ti.type != 1) continue;
+        DcsbRomPtr p = make_ptr(ti.address);
+        p.ofs += 2;
+        for (int guard = 0; guard < 100000; ++guard) {
+            const uint32_t wait = be(p, 2);
+            const int op = u8(p, 2);
+            p.ofs += 3;
+            if (op == 0x01) found.insert(be(p, 3, 1));
+            if (op == 0x00 || op > 0x12 || wait == 0xFFFF) break;
+            static const uint8_t operands[0x13] = { 0, 5, 1, 2, 1, 1, 2, 2, 2, 2, 4, 4, 4, 0, 1, 0, 2, 4, 4 };
+            uint32_t n = operands[op];
+            if (op == 0x04 && os == DCSB_OS93A) n = 3;
+            if (op == 0x06 && as_executed && os93) n = 0;
+            p.ofs += n;
+        }
+    }
+    return std::vector<uint32_t>(found.begin(), found.end());
+}
+
+// ======================================================================================
+// zip container
+static uint32_t le32(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+static uint32_t le16(const uint8_t *p) { return p[0] | (p[1] << 8); }
+
+bool dcsb_unzip(const char *path, std::vector<DcsbZipEntry> &out, std::string &err)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) { err = std::string("cannot open ") + path; return false; }
+    std::vector<uint8_t> z;
+    uint8_t buf[65536];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof(buf), f)) > 0) z.insert(z.end(), buf, buf + n);
+    fclose(f);
+    // end-of-central-directory record: last occurrence of PK\5\6
+    if (z.size() < 22) { err = "not a zip file"; return false; }
+    size_t eocd = std::string::npos;
+    for (size_t i = z.size() - 22; i + 1 > 0 && z.size() - i < 66000; --i) {
+        if (le32(&z[i]) == 0x06054b50u) { eocd = i; break; }
+        if (i == 0) break;
+    }
+    if (eocd == std::string::npos) { err = "zip directory not found"; return false; }
+    const uint32_t count = le16(&z[eocd + 10]);
+    size_t p = le32(&z[eocd + 16]);
+    for (uint32_t e = 0; e < count; ++e) {
+        if (p + 46 > z.size() || le32(&z[p]) != 0x02014b50u) { err = "corrupt zip directory"; return false; }
+        const uint32_t method = le16(&z[p + 10]), csize = le32(&z[p + 20]), usize = le32(&z[p + 24]);
+        const uint32_t nlen = le16(&z[p + 28]), xlen = le16(&z[p + 30]), clen = le16(&z[p + 32]), lho = le32(&z[p + 42]);
+        std::string name(reinterpret_cast<const char *>(&z[p + 46]), nlen);
+        p += 46 + nlen + xlen + clen;
+        if (!name.empty() && name.back() == '/') continue;      // directory
+        if ((size_t)lho + 30 > z.size() || le32(&z[lho]) != 0x04034b50u) { err = "corrupt zip entry " + name; return false; }
+        const size_t data = (size_t)lho + 30 + le16(&z[lho + 26]) + le16(&z[lho + 28]);
+        if (data + csize > z.size()) { err = "truncated zip entry " + name; return false; }
+        DcsbZipEntry ent;
+        ent.name = name;
+        ent.data.resize(usize);
+        if (method == 0) {
+            if (csize != usize) { err = "bad stored entry " + name; return false; }
+            memcpy(ent.data.data(), &z[data], usize);
+        } else if (method == 8) {
+            z_stream zs;
+            memset(&zs, 0, sizeof(zs));
+            if (inflateInit2(&zs, -15) != Z_OK) { err = "inflateInit2 failed"; return false; }
+            zs.next_in = &z[data];
+            zs.avail_in = csize;
+            zs.next_out = ent.data.data();
+            zs.avail_out = usize;
+            const int rc = inflate(&zs, Z_FINISH);
+            inflateEnd(&zs);
+            if (rc != Z_STREAM_END || zs.total_out != usize) { err = "error uncompressing " + name; return false; }
+        } else { err = "unsupported compression method in " + name; return false; }
+        out.push_back(std::move(ent));
+    }
+    return true;
+}
+
+// "[SU]<non-digits><digit> ... <ws>dd/dd/dd" at the start of a sound ROM image names its chip
+// (DCSDecoderZipLoader.cpp:168-186)
+static int image_chip_digit(const std::vector<uint8_t> &d)
+{
+    size_t n = 0;
+    while (n < d.size() && n < 256 && d[n]) ++n;
+    if (n == d.size() || n == 256) return 0;
+    const char *s = reinterpret_cast<const char *>(d.data());
+    if (s[0] != 'S' && s[0] != 'U') return 0;
+    size_t i = 1;
+    while (i < n && !isdigit((unsigned char)s[i])) ++i;
+    if (i >= n) return 0;
+    const int digit = s[i];
+    // the text must end with whitespace + a dd/dd/dd date
+    if (n < i + 1 + 9) return 0;
+    const char *t = s + n - 8;
+    const bool date = isdigit((unsigned char)t[0]) && isdigit((unsigned char)t[1]) && t[2] == '/' && isdigit((unsigned char)t[3]) &&
+                      isdigit((unsigned char)t[4]) && t[5] == '/' && isdigit((unsigned char)t[6]) && isdigit((unsigned char)t[7]);
+    if (!date || !isspace((unsigned char)t[-1])) return 0;
+    return digit;
+}
+
+int dcsb_rom_load_zip_impl(dcsb_rom *rom, const char *path, const char *explicit_u2)
+{
+    std::vector<DcsbZipEntry> files;
+    FILE *probe = fopen(path, "rb");
+    if (!probe) { rom->err = std::string("Error opening ROM Zip file \"") + path + "\""; return DCSB_ZIP_E_OPEN; }
+    fclose(probe);
+    if (!dcsb_unzip(path, files, rom->err)) return DCSB_ZIP_E_EXTRACT;
+    // U2: the image that starts with a JUMP and has a '2' in its name, or the one named explicitly
+    int u2 = -1;
+    for (size_t i = 0; i < files.size() && u2 < 0; ++i) {
+        const DcsbZipEntry &f = files[i];
+        if ((f.data.size() >= 4 && is_jump(f.data.data()) && f.name.find('2') != std::string::npos) ||
+            (explicit_u2 && strcasecmp(f.name.c_str(), explicit_u2) == 0))
+            u2 = (int)i;
+    }
+    if (u2 < 0) { rom->err = std::string("No file in ") + path + " could be identified as ROM U2"; return DCSB_ZIP_E_NOU2; }
+    std::vector<int> used(files.size(), 0);
+    used[u2] = 2;
+    rom->add(2, files[u2].data.data(), files[u2].data.size());
+    std::string base = path;
+    const size_t slash = base.find_last_of("/\\");
+    if (slash != std::string::npos) base = base.substr(slash + 1);
+    const bool cactus = base.size() >= 4 && strncasecmp(base.c_str(), "cc_", 3) == 0 && isdigit((unsigned char)base[3]);
+    for (int n = 3; n <= 9; ++n)
+        for (size_t i = 0; i < files.size(); ++i) {
+            if (used[i] || files[i].name.find((char)('0' + n)) == std::string::npos) continue;
+            const int digit = image_chip_digit(files[i].data);
+            bool load = digit == '0' + n;
+            if (cactus && digit && n == 7 && digit == '6') load = true;     // mislabelled chip in the cc_ sets
+            if (load) { rom->add(n, files[i].data.data(), files[i].data.size()); used[i] = n; break; }
+        }
+    return DCSB_ZIP_OK;
+}
+
+// ======================================================================================
+// sequencer
+DcsbSequencer::DcsbSequencer(const dcsb_rom *r) : rom(r) { memset(vars, 0, sizeof(vars)); }
+
+void DcsbSequencer::soft_boot()
+{
+    for (Channel &c : chan) { c.stop = false; c.volume = 0xFF; }
+    set_master_volume(0x67);            // DCSDecoder's default volume until the host says otherwise
+    port_bytes = 0;
+}
+
+void DcsbSequencer::set_master_volume(int vol) { vol_mult = dcsb_master_multiplier(vol); }
+
+void DcsbSequencer::reset_mix(int ch)
+{
+    for (Channel &c : chan) c.mixer[ch].reset();
+}
+
+void DcsbSequencer::clear_tracks()
+{
+    for (Channel &c : chan) { c.track.clear(); c.st.active = false; }
+}
+
+void DcsbSequencer::write_port(uint8_t data)
+{
+    if (port_timeout >= 13) port_bytes = 0;
+    switch (port_bytes) {
+    case 0:
+        port_word = (uint16_t)(data << 8);
+        port_bytes = 1;
+        break;
+    case 1:
+        port_word |= data;
+        if ((port_word >= 0x55AA && port_word <= 0x55B2) || (port_word >= 0x55BA && port_word <= 0x55C1)) {
+            port_ext = port_word;
+            port_bytes = 2;
+        } else if (port_word > 0x55B2 && port_word < 0x55BA) port_bytes = 0;
+        else if (port_word == 0x55C2 || port_word == 0x55C3) {
+            const uint16_t rep = reported_version;
+            to_host((uint8_t)((port_word == 0x55C2 ? rep >> 8 : rep) & 0xFF));
+            port_bytes = 0;
+        } else if (port_word & 0x8000) port_bytes = 0;
+        else if (port_word == 0x03E7 && rom->totan) { to_host(0x11); port_bytes = 0; }
+        else { cmdq.push_back(port_word); port_bytes = 0; }
+        break;
+    case 2:
+        port_word = data;
+        port_bytes = 3;
+        break;
+    default:
+        if (port_word == (uint16_t)(data ^ 0xFF)) {
+            if (port_ext == 0x55AA) set_master_volume((uint8_t)port_word);
+            else if (port_ext <= 0x55B2) { const int ch = port_ext - 0x55AB; if (ch >= 0 && ch < DCSB_MAX_CHANNELS) chan[ch].volume = (uint8_t)port_word; }
+            // 55BA..55C1 only touch state no audio path reads
+        }
+        port_bytes = 0;
+        break;
+    }
+    port_timeout = 0;
+}
+
+void DcsbSequencer::load_track(int ch, DcsbRomPtr p)
+{
+    Channel &c = chan[ch];
+    c.track = p;
+    c.st.active = false;
+    c.track_counter = 0;
+    c.timer.clear();
+    c.loops.clear();
+    done_mask &= ~(1u << ch);
+    reset_mix(ch);
+}
+
+void DcsbSequencer::start_stream(int sch, int source, int loops, uint32_t linear)
+{
+    Channel &c = chan[sch];
+    const DcsbRomPtr sp = rom->make_ptr(linear);
+    Stream &s = c.st;
+    s.nframes = s.counter = (uint16_t)rom->be(sp, 2);
+    s.active = true;
+    s.at_start = true;
+    s.pos = 0;
+    auto it = rom->stream_by_addr.find(linear & 0xFFFFFFu);
+    s.id = it == rom->stream_by_addr.end() ? 0xFFFFFFFFu : it->second;
+    if (s.nframes == 0) return;             // the reference leaves such a stream playing: its uint16 counter wraps to 65,536 frames
+    s.loops = (uint16_t)loops;
+    if (c.source >= 0 && c.source != source) c.mixer[c.source].reset();
+    c.source = source;
+}
+
+void DcsbSequencer::load_stream(int ch, uint32_t linear, int level)
+{
+    if (ch < 0 || ch >= DCSB_MAX_CHANNELS) return;
+    chan[ch].track.clear();
+    start_stream(ch, ch, 1, linear);
+    Mixer &m = chan[ch].mixer[ch];
+    m.reset();
+    m.cur = m.target = level << 6;
+}
+
+void DcsbSequencer::mix_op(int cur, DcsbRomPtr &p, int mode, bool fade)
+{
+    const int target_ch = rom->u8(p) & 7;       // (the reference indexes with the raw byte)
+    const int param = (int)(int8_t)rom->u8(p, 1) << 6;
+    p.ofs += 2;
+    int steps = 0;
+    if (fade) { steps = (int)rom->be(p, 2); p.ofs += 2; }
+    Mixer &m = chan[target_ch].mixer[cur];
+    m.steps = steps;
+    const int old = m.cur;
+    int lvl = mode == 0 ? param : (mode == 1 ? old + param : old - param);
+    const int delta = lvl - old;                // taken before the range limit, as the original does
+    lvl = std::max(-8191, std::min(8191, lvl));
+    m.target = lvl;
+    if (steps != 0) m.delta = delta / steps;
+    else m.cur = lvl;
+}
+
+void DcsbSequencer::exec_track(int cur)
+{
+    Channel &me = chan[cur];
+    DcsbRomPtr p = me.track;
+    if (p.null()) return;
+    for (;;) {
+        const uint32_t wait = rom->be(p, 2);
+        if (wait == 0xFFFF || me.track_counter != wait) { me.track = p; return; }
+        p.ofs += 2;
+        me.track_counter = 0;
+        const int op = rom->u8(p);
+        p.ofs += 1;
+        switch (op) {
+        case 0x00:
+            me.track.clear();
+            me.st.active = false;
+            me.loops.clear();
+            me.timer.clear();
+            reset_mix(cur);
+            return;
+        case 0x01: {
+            const int sch = rom->u8(p) & 7;
+            if (sch == 5) chan[5].max_override = false;
+            const uint32_t addr = rom->be(p, 3, 1);
+            const int loops = rom->u8(p, 4);
+            p.ofs += 5;
+            start_stream(sch, cur, loops, addr);
+            break;
+        }
+        case 0x02: {
+            const int t = rom->u8(p) & 7;
+            p.ofs += 1;
+            if (chan[t].st.active) { chan[t].st.active = false; reset_mix(t); }
+            chan[t].track.clear();
+            chan[t].timer.clear();
+            if (me.track.null()) return;
+            break;
+        }
+        case 0x03:
+            cmdq.push_back((uint16_t)rom->be(p, 2));
+            p.ofs += 2;
+            break;
+        case 0x04:
+            if (rom->os == DCSB_OS93A) {
+                const uint8_t b = rom->u8(p);
+                const uint16_t counter = (uint16_t)rom->be(p, 2, 1);
+                p.ofs += 3;
+                if (b == 0) me.timer.clear();
+                else {
+                    to_host(b);
+                    if (counter) { me.timer.data = b; me.timer.interval = me.timer.counter = counter; }
+                    else me.timer.clear();
+                }
+            } else {
+                const uint8_t b = rom->u8(p);
+                p.ofs += 1;
+                to_host(b);
+                if (rom->nominal_version == 0x0105) {
+                    if (b == 0x69) chan[5].max_override = true;
+                    else if (b == 0x6A) chan[5].max_override = false;
+                }
+            }
+            break;
+        case 0x05: {
+            const int t = rom->u8(p) & 7;
+            p.ofs += 1;
+            const int type = chan[t].next_type;
+            if (type == 0) break;
+            chan[t].next_type = 0;
+            if (type == 2) cmdq.push_back(chan[t].next_link);
+            else if (type == 3) {
+                // Catalog[$43][low byte][variables[high byte]] -> track number
+                const uint16_t link = chan[t].next_link;
+                const uint32_t table = rom->u2_be(rom->indirect_index + 3u * (link & 0xFF), 3);
+                DcsbRomPtr tp = rom->make_ptr(table);
+                cmdq.push_back((uint16_t)rom->be(tp, 2, 2u * vars[(link >> 8) & 0xFF]));
+            }
+            break;
+        }
+        case 0x06:
+            if (rom->os != DCSB_OS93A && rom->os != DCSB_OS93B) {
+                vars[rom->u8(p)] = rom->u8(p, 1);
+                p.ofs += 2;
+            }
+            break;
+        case 0x07: case 0x08: case 0x09: mix_op(cur, p, op - 0x07, false); break;
+        case 0x0A: case 0x0B: case 0x0C: mix_op(cur, p, op - 0x0A, true); break;
+        case 0x0D: break;
+        case 0x0E: {
+            const uint16_t n = rom->u8(p);
+            p.ofs += 1;
+            me.loops.push_back(Loop{ n, p });
+            break;
+        }
+        case 0x0F:
+            if (!me.loops.empty()) {
+                Loop &l = me.loops.back();
+                if (l.counter == 0) p = l.pos;
+                else if (l.counter == 1) me.loops.pop_back();
+                else { --l.counter; p = l.pos; }
+            }
+            break;
+        case 0x10: p.ofs += 2; break;           // 0x10-0x12 set parameters nothing audible reads
+        case 0x11: case 0x12: p.ofs += 4; break;
+        default: throw Reset();
+        }
+    }
+}
+
+void DcsbSequencer::update_levels()
+{
+    for (Channel &c : chan)
+        for (Mixer &m : c.mixer) {
+            if (m.steps == 1) { m.steps = 0; m.cur = m.target; }
+            else if (m.steps > 1) {
+                --m.steps;
+                m.cur = std::max(-8191, std::min(8191, m.cur + m.delta));
+            }
+        }
+    for (Channel &c : chan) {
+        int sum = 0;
+        for (const Mixer &m : c.mixer) sum += m.cur;
+        c.mult = dcsb_level_multiplier(sum, rom->os, c.volume, c.max_override ? 1 : 0);
+    }
+    for (Channel &c : chan) {
+        c.track_counter += 1;
+        if (c.timer.interval != 0 && --c.timer.counter == 0) { c.timer.counter = c.timer.interval; to_host(c.timer.data); }
+    }
+}
+
+void DcsbSequencer::main_loop(std::vector<DcsbSchedEntry> &entries, DcsbSchedFrame &fr)
+{
+    // channels the decoder's error path flagged last frame
+    for (int ch = 0; ch < DCSB_MAX_CHANNELS; ++ch) {
+        Channel &c = chan[ch];
+        if (!c.stop) continue;
+        c.stop = false;
+        if (c.st.active) { c.st.active = false; reset_mix(ch); }
+        c.timer.clear();
+        c.track.clear();
+    }
+    // pending commands = indices into the track index
+    while (!cmdq.empty()) {
+        const uint16_t cmd = cmdq.front();
+        cmdq.pop_front();
+        if (cmd >= rom->n_tracks) continue;
+        const uint32_t ofs = rom->u2_be(rom->track_index + 3u * cmd, 3);
+        if ((ofs & 0xFF0000u) == 0xFF0000u) continue;
+        DcsbRomPtr tp = rom->make_ptr(ofs);
+        const int type = rom->u8(tp), ch = rom->u8(tp, 1) & 7;
+        tp.ofs += 2;
+        if (type == 1) load_track(ch, tp);
+        else if (type <= 3) { chan[ch].next_type = (uint8_t)type; chan[ch].next_link = (uint16_t)rom->be(tp, 2); }
+        else throw Reset();
+    }
+    // run the track programs until every channel has had its turn
+    done_mask = 0;
+    for (int ch = 0; done_mask != 0xFFu; ch = (ch + 1) % DCSB_MAX_CHANNELS)
+        if (!(done_mask & (1u << ch))) { exec_track(ch); done_mask |= 1u << ch; }
+    // gain staging (MainLoop :227-269)
+    uint16_t mix[8], eff[8];
+    unsigned active = 0, maxo = 0;
+    for (int i = 0; i < DCSB_MAX_CHANNELS; ++i) {
+        mix[i] = chan[i].mult;
+        if (chan[i].st.active) active |= 1u << i;
+        if (chan[i].max_override) maxo |= 1u << i;
+    }
+    fr.vs = (uint8_t)dcsb_gain_stage(mix, active, maxo, vol_mult, eff);
+    for (int i = 0; i < DCSB_MAX_CHANNELS; ++i) chan[i].mult = eff[i];
+    // one frame from each active stream, channel order (DecodeStream :1546-1589)
+    for (int ch = 0; ch < DCSB_MAX_CHANNELS; ++ch) {
+        Channel &c = chan[ch];
+        Stream &s = c.st;
+        if (!s.active) continue;
+        s.at_start = false;
+        bool decodes = false;
+        if (s.id != 0xFFFFFFFFu) {
+            const DcsbStreamFacts &sf = rom->streams[s.id];
+            if (s.pos < sf.nplay) {
+                decodes = true;
+                if (sf.status == DCSB_E_STOPPED && s.pos + 1u == sf.nplay) c.stop = true;      // decoder error path: partial frame, channel stops
+            } else c.stop = true;               // frame cannot be decoded (truncated / invalid band type): silence, channel stops
+        } else c.stop = true;                   // a stream the ROM scan never saw: nothing to decode
+        if (decodes) entries.push_back(DcsbSchedEntry{ s.id, s.pos, c.mult });
+        ++s.pos;
+        if (--s.counter != 0) continue;
+        s.counter = s.nframes;
+        s.pos = 0;
+        s.at_start = true;
+        if (s.loops == 0) continue;
+        if (--s.loops != 0) continue;
+        s.active = false;
+        c.source = -1;
+    }
+    update_levels();
+    if (++port_timeout > 13) port_timeout = 13;
+}
+
+bool DcsbSequencer::frame(std::vector<DcsbSchedFrame> &frames, std::vector<DcsbSchedEntry> &entries)
+{
+    DcsbSchedFrame fr{ (uint32_t)entries.size(), 0, 8, 0, 0 };
+    if (!fatal) {
+        // a self-reset (bad track type / opcode) is retried; four in a row are fatal (DCSDecoder.cpp:1631-1668)
+        for (int tries = 0;; ++tries) {
+            const size_t mark = entries.size();
+            try {
+                main_loop(entries, fr);
+                break;
+            } catch (const Reset &) {
+                entries.resize(mark);
+                if (tries >= 3) { fatal = true; break; }
+            }
+        }
+    }
+    if (fatal) { entries.resize(fr.first_entry); fr.vs = 8; fr.flags = DCSB_FRAME_MUTE; }
+    fr.n_entries = (uint8_t)(entries.size() - fr.first_entry);
+    frames.push_back(fr);
+    ++frame_no;
+    return !fatal;
+}

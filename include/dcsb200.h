@@ -54,8 +54,12 @@ typedef struct {
     uint8_t  master_volume;     /* DCSDecoder::SetMasterVolume, DCSDecoder.h:546 */
     uint8_t  mixing_level;      /* DCSDecoderNative::LoadAudioStream mixing level, DCSDecoderNative.h:98 */
     uint16_t tail_frames;       /* frames rendered after the last stream frame (DCSExplorer uses 2) */
-    uint16_t reserved;
+    uint16_t reserved;          /* flags: DCSB_STREAM_WRAP_EMPTY, else 0 */
 } dcsb_stream_desc;
+/* a zero frame count plays 65,536 frames, as the reference's wrapped 16-bit frame counter makes it
+ * (DCSDecoderNative.cpp:1411-1415, :1565) -- what track playback from a ROM does; without the flag
+ * such a stream is rejected with DCSB_E_EMPTY */
+#define DCSB_STREAM_WRAP_EMPTY 1
 
 typedef struct {
     int32_t  status;            /* DCSB_OK or the DCSB_E_* that ended the stream early */
@@ -111,6 +115,95 @@ float dcsb_batch_last_kernel_ms(dcsb_batch *b, int which);
  * GetStreamInfo / the per-frame bit pointer (DCSDecoderNative.cpp:1486-1537):
  * bitpos[f] for f < nFrames, band types (16 bytes per frame) carried INTO each frame. */
 int dcsb_batch_read_scan(dcsb_batch *b, size_t i, uint32_t *bitpos, uint8_t *bandtypes, size_t max_frames);
+
+/* ---- ROM sets: load, look up tracks and streams (host side) ------------------------ */
+/* Replaces the ROM half of the DCSDecoder API: AddROM (DCSDecoder.h:324), LoadROMFromZipFile
+ * (:285, DCSDecoderZipLoader.cpp), CheckROMs (:347), GetVersionInfo / GetVersionNumber /
+ * GetNumChannels (:1081-1110), GetMaxTrackNumber (:360), GetTrackInfo (:416), ListStreams
+ * (:486), MakeROMPointer (:792).  A dcsb_rom copies the images it is given. */
+typedef struct dcsb_rom dcsb_rom;
+
+#define DCSB_ZIP_OK        0    /* ZipLoadStatus::Success (DCSDecoder.h:278-284) */
+#define DCSB_ZIP_E_OPEN    1    /* OpenFileError */
+#define DCSB_ZIP_E_EXTRACT 2    /* ExtractError */
+#define DCSB_ZIP_E_NOU2    3    /* NoU2 */
+
+typedef struct {
+    uint16_t os_version;        /* DCSB_OS93A / OS93B / OS94 / OS95; 0 = not detected */
+    uint8_t  hw_version;        /* 2 = DCS audio board (1993), 3 = DCS-95 A/V board, 1 = not detected, 0 = not checked */
+    uint8_t  n_channels;        /* GetNumChannels(): 0 when the code pattern is absent */
+    uint16_t version_number;    /* GetVersionNumber(): 0x0100, 0x0101, 0x0103..0x0105, 0 */
+    uint16_t n_tracks;          /* entries in the track index = GetMaxTrackNumber() + 1 */
+    uint32_t catalog_offset;    /* offset of the catalog inside U2 (0 = not found) */
+    int32_t  post_code;         /* CheckROMs(): 1 = all chips verified, 2..9 = first failing chip U2..U9 */
+    char     signature[128];    /* U2 signature string */
+} dcsb_rom_info;
+
+typedef struct {                /* DCSDecoder::TrackInfo (DCSDecoder.h:384-414) */
+    uint32_t address;           /* 24-bit linear ROM address of the track */
+    int32_t  channel;
+    int32_t  type;              /* 1 = byte-code program, 2 = deferred, 3 = deferred indirect */
+    uint16_t defer_code;        /* types 2/3; 0xFFFF otherwise */
+    uint8_t  looping;
+    uint8_t  reserved;
+    uint32_t time;              /* playing time in frames (7.68 ms) */
+} dcsb_track_info;
+
+int  dcsb_rom_create(dcsb_rom **out);
+void dcsb_rom_destroy(dcsb_rom *rom);
+int  dcsb_rom_add(dcsb_rom *rom, int chip_number /* 2..9 */, const uint8_t *image, size_t nbytes);
+/* returns DCSB_ZIP_*; explicit_u2 may be NULL; details in dcsb_rom_last_error */
+int  dcsb_rom_load_zip(dcsb_rom *rom, const char *zip_path, const char *explicit_u2);
+int  dcsb_rom_check(dcsb_rom *rom);                                    /* CheckROMs(): POST code */
+int  dcsb_rom_get_info(const dcsb_rom *rom, dcsb_rom_info *info);
+int  dcsb_rom_track_info(const dcsb_rom *rom, uint16_t track, dcsb_track_info *info);   /* 1 = valid track, 0 = not */
+/* distinct stream addresses referenced by Play opcodes, ascending; returns how many exist */
+size_t dcsb_rom_list_streams(const dcsb_rom *rom, uint32_t *addresses, size_t max);
+/* MakeROMPointer: pointer into the rom's own copy of the chip + bytes left in that chip */
+const uint8_t *dcsb_rom_pointer(const dcsb_rom *rom, uint32_t linear_address, uint32_t *bytes_left);
+const char *dcsb_rom_last_error(const dcsb_rom *rom);
+
+/* ---- track playback: one decoder instance = one player ------------------------------ */
+/* A player is the control state of one DCSDecoderNative (channels, track programs, command
+ * queue, mixer levels and fades, master volume) plus the 16-sample overlap carried from frame to
+ * frame.  The host runs the byte-code and gain staging; the GPU decodes, mixes (channels 0..7 in
+ * order, in the frequency domain, DCSDecoderNative.cpp:272-278), transforms and writes PCM.
+ * dcsb_player_create = construct + SoftBoot() (DCSDecoder.h:594); the ROM's streams are uploaded
+ * and scanned on first use of the rom with a context. */
+typedef struct dcsb_player dcsb_player;
+int  dcsb_player_create(dcsb_ctx *ctx, dcsb_rom *rom, dcsb_player **out);
+void dcsb_player_destroy(dcsb_player *p);
+void dcsb_player_set_master_volume(dcsb_player *p, int vol);          /* SetMasterVolume, DCSDecoder.h:546 */
+void dcsb_player_write_data_port(dcsb_player *p, uint8_t byte);       /* WriteDataPort, DCSDecoder.h:663 */
+void dcsb_player_add_track_command(dcsb_player *p, uint16_t track);   /* AddTrackCommand, DCSDecoderNative.h:129 */
+int  dcsb_player_load_audio_stream(dcsb_player *p, int channel, uint32_t stream_address, int mixing_level); /* :98 */
+void dcsb_player_clear_tracks(dcsb_player *p);                        /* ClearTracks, DCSDecoderNative.h:126 */
+int  dcsb_player_is_stream_playing(const dcsb_player *p, int channel);/* IsStreamPlaying, DCSDecoderNative.h:101 */
+/* render the next n_frames * 240 samples into HOST memory (the GetNextSample pump,
+ * DCSDecoder.cpp:1579-1690, n_frames main-loop passes at once) */
+int  dcsb_player_render(dcsb_player *p, uint32_t n_frames, int16_t *pcm_out);
+/* bytes the decoder sent to the host since the last call (Host::ReceiveDataPort); returns count */
+size_t dcsb_player_host_bytes(dcsb_player *p, uint8_t *out, size_t max);
+
+/* One timeline = a fresh player fed data-port bytes at given frame numbers.  Many timelines are
+ * rendered in one launch; timeline t's PCM starts at pcm_offsets[t] samples (NULL = packed). */
+typedef struct { uint32_t frame; uint8_t byte; uint8_t pad[3]; } dcsb_port_write;   /* byte is written before frame `frame` renders */
+typedef struct {
+    const dcsb_port_write *writes;      /* sorted by frame */
+    uint32_t n_writes;
+    uint32_t n_frames;                  /* frames to render */
+    uint8_t  master_volume;             /* SetMasterVolume after SoftBoot */
+    uint8_t  pad[3];
+} dcsb_timeline;
+typedef struct {
+    int32_t  status;                    /* DCSB_OK, or DCSB_E_STOPPED-class: the decoder hit its fatal-error state */
+    uint32_t frames;
+    uint64_t checksum;                  /* same definition as dcsb_result::checksum */
+    uint32_t n_host_bytes;              /* bytes sent to the host during the timeline */
+    uint32_t reserved;
+} dcsb_timeline_result;
+int dcsb_render_timelines(dcsb_ctx *ctx, dcsb_rom *rom, const dcsb_timeline *timelines, size_t n,
+                          int16_t *pcm_out, const uint64_t *pcm_offsets, dcsb_timeline_result *results);
 
 /* ---- gain helpers (host side) ------------------------------------ */
 uint16_t dcsb_master_multiplier(int vol);                                  /* SetMasterVolume, :3250-3282 */

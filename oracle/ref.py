@@ -41,6 +41,8 @@ def lib():
         L.dcsref_rom_render.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.dcsref_rom_host_bytes.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.dcsref_rom_list_streams.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.dcsref_rom_open_images.restype = C.c_void_p
+        L.dcsref_rom_open_images.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         _LIB = L
     return _LIB
 
@@ -92,3 +94,57 @@ def transform(bins, overlap, os_version=0x9400, vol_shift=0):
     pcm = np.zeros(240, dtype=np.int16)
     lib().dcsref_transform(os_version, vol_shift, b.ctypes.data, o.ctypes.data, pcm.ctypes.data)
     return pcm, o.astype(np.int16), b
+
+
+class RomPlayer:
+    """The reference decoder on a ROM set: images = {chip number: bytes}.  SoftBoot +
+    SetMasterVolume(master_volume), then write_port / render as the host would."""
+
+    def __init__(self, images, master_volume=255):
+        self._keep = [np.frombuffer(bytes(v), dtype=np.uint8) for v in images.values()]
+        n = len(self._keep)
+        ptrs = (C.c_void_p * n)(*[k.ctypes.data for k in self._keep])
+        sizes = (C.c_size_t * n)(*[k.size for k in self._keep])
+        chips = (C.c_int * n)(*list(images.keys()))
+        self._h = lib().dcsref_rom_open_images(ptrs, sizes, chips, n, master_volume)
+
+    def info(self):
+        v = [C.c_int(0) for _ in range(5)]
+        lib().dcsref_rom_info(self._h, *[C.byref(x) for x in v])
+        return dict(os=v[0].value, hw=v[1].value, max_track=v[2].value, channels=v[3].value, check=v[4].value)
+
+    def write_port(self, b):
+        lib().dcsref_rom_write_port(self._h, b)
+
+    def render(self, n_frames):
+        pcm = np.zeros(n_frames * 240, dtype=np.int16)
+        lib().dcsref_rom_render(self._h, n_frames, pcm.ctypes.data)
+        return pcm
+
+    def host_bytes(self):
+        out = np.zeros(65536, dtype=np.uint8)
+        n = lib().dcsref_rom_host_bytes(self._h, out.ctypes.data, out.size)
+        return out[:n].tobytes()
+
+    def list_streams(self):
+        out = np.zeros(4096, dtype=np.uint32)
+        n = lib().dcsref_rom_list_streams(self._h, out.ctypes.data, out.size)
+        return [int(x) for x in out[:n]]
+
+    def render_timeline(self, writes, n_frames):
+        """writes: list of (frame, byte), sorted by frame"""
+        out = np.zeros(n_frames * 240, dtype=np.int16)
+        w = 0
+        for f in range(n_frames):
+            while w < len(writes) and writes[w][0] <= f:
+                self.write_port(writes[w][1])
+                w += 1
+            out[f * 240:(f + 1) * 240] = self.render(1)
+        return out
+
+    def close(self):
+        if self._h:
+            lib().dcsref_rom_close(self._h)
+            self._h = None
+
+    __del__ = close

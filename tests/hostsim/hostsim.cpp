@@ -9,9 +9,11 @@
 #include <stdint.h>
 #include <string.h>
 #include <vector>
+#include <algorithm>
 #include "../../dcsexplorer_b200/csrc/dcsb_core.cuh"
 #include "../../dcsexplorer_b200/csrc/dcsb_fast94.cuh"
 #include "../../dcsexplorer_b200/csrc/dcsb_scan94.cuh"
+#include "../../dcsexplorer_b200/csrc/dcsb_mix.cuh"
 
 extern "C" int hostsim_decode_streams(const dcsb_stream_desc *descs, size_t n, int16_t *pcm_out,
                                       dcsb_result *results, uint32_t *bitpos_out, uint8_t *bt_out)
@@ -66,6 +68,127 @@ extern "C" int hostsim_decode_streams(const dcsb_stream_desc *descs, size_t n, i
                 for (int k = 0; k < 16; ++k) bt_out[o * 16 + k] = (uint8_t)((v >> (4 * k)) & 15);
             }
         }
+    }
+    return DCSB_OK;
+}
+
+// ---- track playback: the host sequencer (product code, dcsb_rom.cpp) + K1 / K4 bodies on the CPU ----
+extern "C" int hostsim_rom_render(const uint8_t *const *imgs, const size_t *sizes, const int *chipnos, int nchips,
+                                  const dcsb_timeline *timelines, size_t n, int16_t *pcm_out, dcsb_timeline_result *results,
+                                  dcsb_rom_info *info_out, uint8_t *host_bytes_out, size_t host_bytes_cap)
+{
+    dcsb_rom rom;
+    for (int i = 0; i < nchips; ++i) rom.add(chipnos[i], imgs[i], sizes[i]);
+    rom.check();
+    if (info_out) {
+        memset(info_out, 0, sizeof(*info_out));
+        info_out->os_version = rom.os > 1 ? (uint16_t)rom.os : 0;
+        info_out->hw_version = (uint8_t)rom.hw;
+        info_out->n_channels = (uint8_t)rom.num_channels();
+        info_out->n_tracks = rom.n_tracks;
+        info_out->catalog_offset = rom.catalog_ofs;
+        info_out->post_code = rom.post;
+        info_out->version_number = rom.nominal_version;
+    }
+    if (rom.os <= 1) return DCSB_E_ARG;
+    // stream table, as rom_prepare (dcsb_player.cu) builds it
+    std::vector<uint32_t> addrs = rom.list_streams(true);
+    {
+        const std::vector<uint32_t> more = rom.list_streams(false);
+        addrs.insert(addrs.end(), more.begin(), more.end());
+        std::sort(addrs.begin(), addrs.end());
+        addrs.erase(std::unique(addrs.begin(), addrs.end()), addrs.end());
+    }
+    for (int c = 0; c < 8; ++c) {
+        rom.image_ofs[c] = (uint32_t)rom.image.size();
+        if (!rom.chip[c].present) continue;
+        rom.image.insert(rom.image.end(), rom.chip[c].bytes.begin(), rom.chip[c].bytes.begin() + rom.chip[c].size);
+        rom.image.resize(rom.image.size() + 1024, 0);
+    }
+    if (rom.image.empty()) rom.image.resize(1024, 0);
+    std::vector<dcsb_stream_desc> descs;
+    for (uint32_t a : addrs) {
+        const DcsbRomPtr p = rom.make_ptr(a);
+        DcsbStreamFacts sf;
+        sf.linear = a;
+        sf.at = p;
+        dcsb_stream_desc d;
+        memset(&d, 0, sizeof(d));
+        d.os_version = (uint16_t)rom.os;
+        d.reserved = DCSB_STREAM_WRAP_EMPTY;
+        if (rom.chip[p.chip].present && p.ofs < rom.chip[p.chip].size) {
+            d.data = rom.image.data() + rom.image_ofs[p.chip] + p.ofs;
+            d.nbytes = rom.chip[p.chip].size - p.ofs;
+            sf.nframes = (uint16_t)rom.be(p, 2);
+        } else { d.data = rom.image.data(); d.nbytes = 0; }
+        rom.stream_by_addr[a & 0xFFFFFFu] = (uint32_t)rom.streams.size();
+        rom.streams.push_back(sf);
+        descs.push_back(d);
+    }
+    DcsbPrepared p;
+    int rc = dcsb_prepare(descs.data(), descs.size(), &p, rom.image.data(), rom.image.size());
+    if (rc != DCSB_OK) return rc;
+    std::vector<uint8_t> slab(p.slab_bytes + 64, 0);
+    memcpy(slab.data(), rom.image.data(), rom.image.size());
+    static DcsbTables tab;
+    dcsb_build_tables(&tab);
+    const size_t ns = descs.size();
+    std::vector<uint32_t> bitpos(p.total_checkpoints + 1), nplay(ns + 1), endbits(ns + 1);
+    std::vector<uint2> bt(p.total_checkpoints + 1);
+    std::vector<uint16_t> hdrbits(p.total_checkpoints + 1);
+    std::vector<int32_t> status(ns + 1);
+    std::vector<uint8_t> stopband(ns + 1);
+    DcsbScanOut so{ bitpos.data(), bt.data(), hdrbits.data(), status.data(), nplay.data(), endbits.data(), stopband.data(), nullptr };
+    std::vector<uint8_t> ring(DCSB_RING_BYTES, 0xA5);
+    for (size_t i = 0; i < ns; ++i) {
+        if (p.recs[i].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, tab.t8, tab.t1, ring.data(), so);
+        else dcsb_scan_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, so);
+        rom.streams[i].status = p.host_status[i] ? p.host_status[i] : status[i];
+        rom.streams[i].nplay = p.host_status[i] ? 0 : nplay[i];
+        if (p.host_status[i]) nplay[i] = 0;
+    }
+    // schedules
+    std::vector<DcsbSchedFrame> frames;
+    std::vector<DcsbSchedEntry> entries;
+    std::vector<uint32_t> first(n), count(n);
+    size_t nhost = 0;
+    for (size_t t = 0; t < n; ++t) {
+        const dcsb_timeline &tl = timelines[t];
+        DcsbSequencer seq(&rom);
+        seq.soft_boot();
+        seq.set_master_volume(tl.master_volume);
+        first[t] = (uint32_t)frames.size();
+        uint32_t w = 0;
+        for (uint32_t f = 0; f < tl.n_frames; ++f) {
+            while (w < tl.n_writes && tl.writes[w].frame <= f) seq.write_port(tl.writes[w++].byte);
+            seq.frame(frames, entries);
+        }
+        count[t] = tl.n_frames;
+        if (results) {
+            results[t].status = seq.fatal ? DCSB_E_STOPPED : DCSB_OK;
+            results[t].frames = tl.n_frames;
+            results[t].n_host_bytes = (uint32_t)seq.host_bytes.size();
+            results[t].checksum = 0;
+        }
+        for (uint8_t hb : seq.host_bytes) if (host_bytes_out && nhost < host_bytes_cap) host_bytes_out[nhost++] = hb;
+    }
+    // K4 grid
+    const bool fam93 = rom.os == DCSB_OS93A || rom.os == DCSB_OS93B;
+    DcsbMixSched sc{ frames.data(), entries.data() };
+    static DcsbTw94 tw;
+    memcpy(tw.tw_c2, tab.tw_c2, sizeof(tw.tw_c2)); memcpy(tw.tw_s2, tab.tw_s2, sizeof(tw.tw_s2));
+    memcpy(tw.pre_c0, tab.pre_c0, sizeof(tw.pre_c0)); memcpy(tw.pre_c1, tab.pre_c1, sizeof(tw.pre_c1));
+    std::vector<uint32_t> rows(DcsbWarpSmem<true>::WORDS + DCSB_WARP94_WORDS);
+    std::vector<uint8_t> hdrs(32 * 16);
+    for (size_t t = 0; t < n; ++t) {
+        const uint32_t item_len = fam93 ? DCSB_TILE_OUT : 63;          // (63: exercises the tile-to-tile tail carry)
+        unsigned long long cs = 0;
+        for (uint32_t f = 0; f < count[t]; f += item_len) {
+            DcsbMixItem it{ first[t] + f, std::min<uint32_t>(item_len, count[t] - f), first[t], (uint32_t)t };
+            if (fam93) cs += dcsb_mix93_tile(slab.data(), p.recs.data(), it, sc, &tab, tab.lut, so, pcm_out, rows.data());
+            else cs += dcsb_mix94_item(slab.data(), p.recs.data(), it, sc, &tab, tab.lut, &tw, so, pcm_out, rows.data(), hdrs.data());
+        }
+        if (results) results[t].checksum = cs;
     }
     return DCSB_OK;
 }

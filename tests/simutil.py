@@ -41,3 +41,71 @@ def decode_streams(streams, **kw):
     results = [dict(status=res[i].status, frames=res[i].frames, frames_decoded=res[i].frames_decoded,
                     stream_bytes=res[i].stream_bytes, checksum=res[i].checksum) for i in range(n)]
     return pcm[:total], offs, results, bitpos, bt
+
+
+class PortWrite(C.Structure):
+    _fields_ = [("frame", C.c_uint32), ("byte", C.c_uint8), ("pad", C.c_uint8 * 3)]
+
+
+class Timeline(C.Structure):
+    _fields_ = [("writes", C.POINTER(PortWrite)), ("n_writes", C.c_uint32), ("n_frames", C.c_uint32),
+                ("master_volume", C.c_uint8), ("pad", C.c_uint8 * 3)]
+
+
+class TimelineResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("frames", C.c_uint32), ("checksum", C.c_uint64),
+                ("n_host_bytes", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class RomInfo(C.Structure):
+    _fields_ = [("os_version", C.c_uint16), ("hw_version", C.c_uint8), ("n_channels", C.c_uint8),
+                ("version_number", C.c_uint16), ("n_tracks", C.c_uint16), ("catalog_offset", C.c_uint32),
+                ("post_code", C.c_int32), ("signature", C.c_char * 128)]
+
+
+def make_timelines(timelines):
+    """timelines: list of (writes [(frame, byte)], n_frames, master_volume) -> (ctypes array, keepalive)"""
+    arr = (Timeline * max(1, len(timelines)))()
+    keep = []
+    for i, (writes, n_frames, vol) in enumerate(timelines):
+        w = (PortWrite * max(1, len(writes)))()
+        for k, (f, b) in enumerate(writes):
+            w[k].frame, w[k].byte = f, b
+        keep.append(w)
+        arr[i].writes = w
+        arr[i].n_writes = len(writes)
+        arr[i].n_frames = n_frames
+        arr[i].master_volume = vol
+    return arr, keep
+
+
+def rom_render(images, timelines):
+    """The product's host sequencer + the K1/K4 kernel bodies, executed on the CPU.
+    Returns (list of pcm arrays, results, rom info dict, host bytes)."""
+    L = lib()
+    n = len(images)
+    bufs = [np.frombuffer(bytes(v), dtype=np.uint8) for v in images.values()]
+    ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+    sizes = (C.c_size_t * n)(*[b.size for b in bufs])
+    chips = (C.c_int * n)(*list(images.keys()))
+    tl, keep = make_timelines(timelines)
+    total = sum(t[1] for t in timelines)
+    pcm = np.zeros(max(1, total) * 240, dtype=np.int16)
+    res = (TimelineResult * max(1, len(timelines)))()
+    info = RomInfo()
+    hb = np.zeros(1 << 16, dtype=np.uint8)
+    L.hostsim_rom_render.restype = C.c_int
+    L.hostsim_rom_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    rc = L.hostsim_rom_render(ptrs, sizes, chips, n, tl, len(timelines), pcm.ctypes.data, res, C.byref(info), hb.ctypes.data, hb.size)
+    assert rc == 0, rc
+    out, o = [], 0
+    for t in timelines:
+        out.append(pcm[o:o + t[1] * 240])
+        o += t[1] * 240
+    nh = sum(res[i].n_host_bytes for i in range(len(timelines)))
+    results = [dict(status=res[i].status, frames=res[i].frames, checksum=res[i].checksum, n_host_bytes=res[i].n_host_bytes)
+               for i in range(len(timelines))]
+    inf = dict(os=info.os_version, hw=info.hw_version, channels=info.n_channels, n_tracks=info.n_tracks,
+               catalog=info.catalog_offset, post=info.post_code, version=info.version_number)
+    return out, results, inf, hb[:nh].tobytes()

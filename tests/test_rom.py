@@ -1,0 +1,172 @@
+"""ROM sets and track playback (BASELINE config 4), CPU side: the product's host control plane
+(ROM model, version detection, track / stream lookup, zip loader, sequencer) through the C-ABI
+where no GPU is needed, and the sequencer + K1/K4 kernel bodies in the CPU-side simulator against
+the golden fixtures frozen from the reference (tests/golden/rom_golden.npz) and -- in the build
+container -- against the reference itself on fresh scenarios."""
+import hashlib
+import os
+import zipfile
+import numpy as np
+import pytest
+from oracle import orc, ref
+import rombuild as rb
+import romscen
+import simutil
+
+needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (reference tree absent)")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def rom_golden():
+    return np.load(os.path.join(HERE, "golden", "rom_golden.npz"))
+
+
+def images_digest(images):
+    h = hashlib.sha256()
+    for chip in sorted(images):
+        h.update(bytes([chip]))
+        h.update(images[chip])
+    return h.hexdigest()
+
+
+def frame_sums(pcm):
+    return pcm.reshape(-1, 240).astype(np.int64).sum(axis=1).astype(np.uint32)
+
+
+def check_rom_golden(g, name, pcm, host_bytes):
+    sums = frame_sums(pcm)
+    want = g[name + "/sums"]
+    assert sums.size == want.size
+    bad = np.nonzero(sums != want)[0]
+    assert bad.size == 0, "%s: first differing frame %d" % (name, bad[0])
+    assert np.array_equal(pcm[:240 * 20], g[name + "/head"]) and np.array_equal(pcm[-240 * 20:], g[name + "/tail"])
+    assert orc.fnv1a(pcm) == int(g[name + "/fnv"]), name
+    assert host_bytes == g[name + "/host"].tobytes(), name
+
+
+@pytest.mark.parametrize("name,kw", romscen.SCENARIOS)
+def test_sim_rom_matches_golden(built, rom_golden, name, kw):
+    sc = romscen.make_scenario(**kw)
+    assert images_digest(sc["images"]) == str(rom_golden[name + "/digest"]), "scenario generator drifted: regenerate the fixture"
+    pcm, res, info, hb = simutil.rom_render(sc["images"], [(sc["writes"], sc["n_frames"], sc["master_volume"])])
+    check_rom_golden(rom_golden, name, pcm[0], hb)
+    assert info["post"] == 1 and info["os"] == kw["os_version"] and info["channels"] == 6
+    assert res[0]["status"] == 0 and res[0]["n_host_bytes"] == len(hb)
+    s = pcm[0].astype(np.uint16).astype(np.uint64)
+    assert res[0]["checksum"] == int((s * (2 * np.arange(s.size, dtype=np.uint64) + 1)).sum(dtype=np.uint64))
+
+
+@pytest.mark.parametrize("name,kw", romscen.SCENARIOS)
+def test_rom_model_through_the_c_abi(built, rom_golden, name, kw):
+    """dcsb_rom_*: no GPU needed.  Version detection, catalog, track info, stream list."""
+    import dcsexplorer_b200 as dx
+    sc = romscen.make_scenario(**kw)
+    rom = dx.Rom(sc["images"])
+    assert rom.check() == 1
+    info = rom.info()
+    os_ref, hw_ref, max_track, nch = [int(v) for v in rom_golden[name + "/info"]]
+    assert info["os"] == kw["os_version"] and info["hw"] == hw_ref and info["channels"] == nch == 6
+    assert info["n_tracks"] == max_track + 1 == sc["n_tracks"]
+    assert info["catalog"] == (0x6000 if kw["os_version"] == rb.OS95 else 0x4000)
+    assert info["version"] == {rb.OS93A: 0x100, rb.OS93B: 0x100, rb.OS94: 0x101}.get(kw["os_version"], kw.get("version") or 0)
+    assert "synthetic test ROM" in info["signature"]
+    # ListStreams: same list as the reference produced (incl. its opcode-6 quirk on 1993 software)
+    assert rom.list_streams() == [int(a) for a in rom_golden[name + "/streams"]]
+    assert set(rom.list_streams()) <= set(sc["stream_addr"].values())
+    # track table
+    ti = rom.track_info(0)
+    assert ti["type"] == 1 and ti["channel"] == 0 and ti["looping"]
+    assert rom.track_info(6) == dict(address=ti6(rom)["address"], channel=2, type=2, defer_code=2, looping=False, time=0)
+    assert rom.track_info(8)["type"] == 3 and rom.track_info(8)["defer_code"] == 0x0300
+    assert rom.track_info(12) is None and rom.track_info(sc["n_tracks"]) is None
+    t3 = rom.track_info(3)                      # loop(3){play; play @25; } @20, stop @5
+    assert t3["time"] == 3 * (25 + 20) + 5 and not t3["looping"]
+    assert rom.track_info(11)["looping"]
+    # MakeROMPointer: stream bytes come back as stored
+    a0 = sorted(sc["stream_addr"].values())[0]
+    assert len(rom.stream_bytes(a0, 18)) == 18
+    rom.close()
+
+
+def ti6(rom):
+    return rom.track_info(6)
+
+
+def test_rom_check_detects_bad_chips(built):
+    import dcsexplorer_b200 as dx
+    sc = romscen.make_scenario(os_version=rb.OS94, seed=5)
+    imgs = dict(sc["images"])
+    bad = bytearray(imgs[3]); bad[1000] ^= 0x40
+    rom = dx.Rom({2: imgs[2], 3: bytes(bad), 4: imgs[4]})
+    assert rom.check() == 3                      # first failing chip (POST code, DCSDecoder.h:326-347)
+    rom.close()
+    rom = dx.Rom({3: imgs[3]})
+    assert rom.check() == 2 and rom.info()["os"] == 0
+    rom.close()
+    rom = dx.Rom({2: imgs[2], 3: imgs[3]})      # a chip of the catalog is missing
+    assert rom.check() != 1
+    rom.close()
+
+
+def test_zip_loader(built, tmp_path):
+    """LoadROMFromZipFile: U2 = image starting with a JUMP with '2' in its name; U3.. by the
+    signature text at the start of the image (DCSDecoderZipLoader.cpp:134-203)."""
+    import dcsexplorer_b200 as dx
+    sc = romscen.make_scenario(os_version=rb.OS95, seed=9)
+    z = tmp_path / "synth_95.zip"
+    with zipfile.ZipFile(z, "w", zipfile.ZIP_DEFLATED) as f:
+        f.writestr("readme.txt", "not a rom")
+        f.writestr("snd_u4.rom", sc["images"][4])
+        f.writestr("snd_u2.rom", sc["images"][2])
+        with f.open("snd_u3.rom", "w") as w:    # stored + deflated members both work
+            w.write(sc["images"][3])
+    rom = dx.Rom(zip_path=z)
+    assert rom.check() == 1 and rom.info()["os"] == rb.OS95
+    direct = dx.Rom(sc["images"])
+    direct.check()
+    assert rom.list_streams() == direct.list_streams()
+    rom.close(); direct.close()
+    with pytest.raises(dx.DcsbError):
+        dx.Rom(zip_path=tmp_path / "missing.zip")
+    z2 = tmp_path / "nou2.zip"
+    with zipfile.ZipFile(z2, "w") as f:
+        f.writestr("snd_u3.rom", sc["images"][3])
+    with pytest.raises(dx.DcsbError):
+        dx.Rom(zip_path=z2)
+
+
+@needs_ref
+@pytest.mark.parametrize("os_version,seed", [(rb.OS94, 201), (rb.OS95, 202), (rb.OS93B, 203), (rb.OS93A, 204), (rb.OS94, 205)])
+def test_sim_rom_vs_reference_fresh_scenarios(built, os_version, seed):
+    sc = romscen.make_scenario(os_version=os_version, seed=seed, n_frames=500, with_errors=(seed == 205),
+                               version=0x0104 if os_version == rb.OS95 else None)
+    rp = ref.RomPlayer(sc["images"], sc["master_volume"])
+    want = rp.render_timeline(sc["writes"], sc["n_frames"])
+    got, res, info, hb = simutil.rom_render(sc["images"], [(sc["writes"], sc["n_frames"], sc["master_volume"])])
+    bad = np.nonzero(got[0] != want)[0]
+    assert bad.size == 0, "first differing frame %d" % (bad[0] // 240)
+    assert hb == rp.host_bytes()
+
+
+def test_sim_rom_bad_track_type_is_fatal(built):
+    """A track whose type byte is > 3 makes the decoder reset itself; four resets in a row put it
+    into its fatal-error state: silence from then on (DCSDecoder.cpp:1631-1668)."""
+    t0 = rb.Track(0).mix(0, 0, 100).play("a").wait_forever()
+    bad = rb.Track(1)
+    bad.type = 7
+    rng = np.random.default_rng(3)
+    import dcsfuzz
+    images, _ = rb.build_rom(rb.OS94, [t0, bad], {"a": dcsfuzz.fuzz94(rng, 50, type1=1)}, n_chips=1)
+    # the bad command alone is consumed by the first (aborted) pass: playback continues
+    writes = [(1, 0), (1, 0), (10, 0), (10, 1)]
+    pcm, res, info, hb = simutil.rom_render(images, [(writes, 40, 255)])
+    assert res[0]["status"] == 0 and pcm[0][240 * 12:240 * 30].any()
+    # four bad commands queued at once: every retry pops one and resets again -> fatal
+    writes = [(1, 0), (1, 0)] + [(10, b) for b in (0, 1) * 4]
+    pcm, res, info, hb = simutil.rom_render(images, [(writes, 40, 255)])
+    assert res[0]["status"] == -5
+    assert pcm[0][240 * 2:240 * 10].any() and not pcm[0][240 * 10:].any()
+    if ref.available():
+        rp = ref.RomPlayer(images, 255)
+        assert np.array_equal(rp.render_timeline(writes, 40), pcm[0])
