@@ -255,6 +255,12 @@ class Player:
         self.ctx._check(self._L.dcsb_player_render(self._h, n_frames, pcm.ctypes.data), "dcsb_player_render")
         return pcm[:n_frames * 240]
 
+    def stream_info(self, address):
+        si = _capi.StreamInfo()
+        self.ctx._check(self._L.dcsb_player_stream_info(self._h, address, C.byref(si)), "dcsb_player_stream_info")
+        return dict(nFrames=si.n_frames, nBytes=si.n_bytes, type=si.stream_type, subtype=si.stream_subtype,
+                    status=si.status, header=bytes(si.header))
+
     def host_bytes(self):
         out = np.zeros(65536, dtype=np.uint8)
         n = self._L.dcsb_player_host_bytes(self._h, out.ctypes.data, out.size)
@@ -278,3 +284,19 @@ def _render_timelines(self, rom, timelines):
 
 
 Context.render_timelines = _render_timelines
+
+
+def partition_streams(frames, n_parts):
+    """dcsb_partition_streams: returns (part index per stream, load per part).  Host side, no GPU."""
+    f = np.ascontiguousarray(frames, dtype=np.uint32)
+    part = np.zeros(max(1, f.size), dtype=np.uint32)
+    load = np.zeros(n_parts, dtype=np.uint64)
+    rc = _capi.lib().dcsb_partition_streams(f.ctypes.data, f.size, n_parts, part.ctypes.data, load.ctypes.data)
+    if rc != OK:
+        raise DcsbError("dcsb_partition_streams failed: %d" % rc)
+    return part[:f.size], load
+
+
+def stream_frames(data):
+    """frame count in a stream's preamble"""
+    return ((data[0] << 8) | data[1]) if len(data) >= 2 else 0

@@ -46,7 +46,14 @@ class TimelineResult(C.Structure):
                 ("n_host_bytes", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class StreamInfo(C.Structure):
+    _fields_ = [("n_frames", C.c_int32), ("n_bytes", C.c_int32), ("stream_type", C.c_int32), ("stream_subtype", C.c_int32),
+                ("status", C.c_int32), ("header", C.c_uint8 * 16)]
+
+
 SYMBOLS = {
+    "dcsb_partition_streams": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
+    "dcsb_player_stream_info": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(StreamInfo)]),
     "dcsb_rom_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "dcsb_rom_destroy": (None, [C.c_void_p]),
     "dcsb_rom_add": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),

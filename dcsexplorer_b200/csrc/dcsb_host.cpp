@@ -269,3 +269,22 @@ void dcsb_pack_slab(const dcsb_stream_desc *descs, size_t n, const DcsbPrepared 
     work(0);
     for (auto &x : th) x.join();
 }
+
+// ======================================================================================
+// multi-GPU sharding: longest-processing-time greedy on frame counts
+extern "C" int dcsb_partition_streams(const uint32_t *frames, size_t n, int n_parts, uint32_t *part_out, uint64_t *frames_per_part)
+{
+    if ((!frames && n) || (!part_out && n) || n_parts < 1) return DCSB_E_ARG;
+    std::vector<uint32_t> order(n);
+    for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return frames[a] > frames[b]; });
+    std::vector<uint64_t> load((size_t)n_parts, 0);
+    for (uint32_t i : order) {
+        int best = 0;
+        for (int p = 1; p < n_parts; ++p) if (load[p] < load[best]) best = p;
+        part_out[i] = (uint32_t)best;
+        load[best] += (uint64_t)frames[i] + 1;          // + 1: per-stream fixed cost (an empty stream is not free)
+    }
+    if (frames_per_part) for (int p = 0; p < n_parts; ++p) frames_per_part[p] = load[p];
+    return DCSB_OK;
+}

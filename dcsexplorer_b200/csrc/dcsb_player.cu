@@ -149,12 +149,14 @@ static int rom_prepare(dcsb_ctx *ctx, dcsb_rom *rom)
         CK(dcsb_launch_scan(b->d_slab, b->d_recs, (int)b->n, 0, ctx->d_tables, b->scan, nullptr), "scan kernel launch");
         CK(cudaDeviceSynchronize(), "ROM stream scan");
         std::vector<int32_t> st(b->n);
-        std::vector<uint32_t> np(b->n);
+        std::vector<uint32_t> np(b->n), eb(b->n);
         CK(cudaMemcpy(st.data(), b->scan.status, b->n * 4, cudaMemcpyDeviceToHost), "D2H status");
         CK(cudaMemcpy(np.data(), b->scan.nplay, b->n * 4, cudaMemcpyDeviceToHost), "D2H nplay");
+        CK(cudaMemcpy(eb.data(), b->scan.endbits, b->n * 4, cudaMemcpyDeviceToHost), "D2H endbits");
         for (size_t i = 0; i < b->n; ++i) {
             rom->streams[i].status = b->host_status[i] ? b->host_status[i] : st[i];
             rom->streams[i].nplay = b->host_status[i] ? 0 : np[i];
+            rom->streams[i].nbytes = b->host_status[i] ? 0 : 2 + b->recs[i].hdr_len + (eb[i] + 7) / 8;
         }
     }
     return DCSB_OK;
@@ -258,6 +260,23 @@ extern "C" int dcsb_player_load_audio_stream(dcsb_player *p, int channel, uint32
     if (p->rom->stream_by_addr.find(stream_address & 0xFFFFFFu) == p->rom->stream_by_addr.end())
         return fail(p->ctx, DCSB_E_ARG, "dcsb_player_load_audio_stream: not a stream any track of this ROM plays");
     p->seq.load_stream(channel, stream_address, mixing_level);
+    return DCSB_OK;
+}
+
+extern "C" int dcsb_player_stream_info(const dcsb_player *p, uint32_t stream_address, dcsb_stream_info *info)
+{
+    if (!p || !info) return DCSB_E_ARG;
+    memset(info, 0, sizeof(*info));
+    auto it = p->rom->stream_by_addr.find(stream_address & 0xFFFFFFu);
+    if (it == p->rom->stream_by_addr.end()) return DCSB_E_ARG;
+    const DcsbStreamFacts &sf = p->rom->streams[it->second];
+    const DcsbStreamRec &r = p->rom->batch->recs[it->second];
+    info->n_frames = sf.nframes;
+    info->n_bytes = (int32_t)sf.nbytes;
+    info->status = sf.status;
+    memcpy(info->header, r.hdr, r.hdr_len);
+    info->stream_type = r.hdr[0] >> 7;
+    if (r.fmt == DCSB_FMT_94) info->stream_subtype = ((r.hdr[1] & 0x80) >> 6) | ((r.hdr[1] & 0x80) >> 7);   // as the reference computes it (:1516)
     return DCSB_OK;
 }
 

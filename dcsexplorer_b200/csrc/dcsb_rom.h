@@ -40,6 +40,7 @@ struct DcsbStreamFacts {
     uint16_t nframes = 0;       // frame count from the stream preamble
     int32_t status = 0;         // scan status (DCSB_OK, DCSB_E_STOPPED, DCSB_E_TRUNCATED, DCSB_E_BANDTYPE)
     uint32_t nplay = 0;         // frames that decode (the last one partially when status == DCSB_E_STOPPED)
+    uint32_t nbytes = 0;        // stream size: count + header + frame bits, rounded up to a byte
 };
 
 struct dcsb_rom {

@@ -179,6 +179,15 @@ void dcsb_player_add_track_command(dcsb_player *p, uint16_t track);   /* AddTrac
 int  dcsb_player_load_audio_stream(dcsb_player *p, int channel, uint32_t stream_address, int mixing_level); /* :98 */
 void dcsb_player_clear_tracks(dcsb_player *p);                        /* ClearTracks, DCSDecoderNative.h:126 */
 int  dcsb_player_is_stream_playing(const dcsb_player *p, int channel);/* IsStreamPlaying, DCSDecoderNative.h:101 */
+/* GetStreamInfo (DCSDecoderNative.h:106-123) from the GPU scan of the ROM's streams.  n_bytes is the
+ * exact size of the stream (count + header + frame bits rounded up to a byte); the reference reports
+ * up to 2 bytes more, depending on how far its bit reader had prefetched at the last sample. */
+typedef struct {
+    int32_t n_frames, n_bytes, stream_type, stream_subtype;
+    int32_t status;                     /* DCSB_OK or the DCSB_E_* the scan found */
+    uint8_t header[16];
+} dcsb_stream_info;
+int  dcsb_player_stream_info(const dcsb_player *p, uint32_t stream_address, dcsb_stream_info *info);
 /* render the next n_frames * 240 samples into HOST memory (the GetNextSample pump,
  * DCSDecoder.cpp:1579-1690, n_frames main-loop passes at once) */
 int  dcsb_player_render(dcsb_player *p, uint32_t n_frames, int16_t *pcm_out);
@@ -204,6 +213,13 @@ typedef struct {
 } dcsb_timeline_result;
 int dcsb_render_timelines(dcsb_ctx *ctx, dcsb_rom *rom, const dcsb_timeline *timelines, size_t n,
                           int16_t *pcm_out, const uint64_t *pcm_offsets, dcsb_timeline_result *results);
+
+/* ---- multi-GPU work partitioning (host side) ---------------------------------------- */
+/* Streams are independent (one DCSDecoderNative instance each in the reference), so a batch is
+ * sharded by stream with no data-path collective: longest-processing-time greedy on the frame
+ * counts, ties broken by index, so every rank computes the same assignment.  part_out[i] =
+ * the part (0..n_parts-1) stream i goes to; frames_per_part (may be NULL) receives the load. */
+int dcsb_partition_streams(const uint32_t *frames, size_t n, int n_parts, uint32_t *part_out, uint64_t *frames_per_part);
 
 /* ---- gain helpers (host side) ------------------------------------ */
 uint16_t dcsb_master_multiplier(int vol);                                  /* SetMasterVolume, :3250-3282 */

@@ -1,0 +1,60 @@
+// TEST: drives the DCSDecoder-compatible C++ front (include/DCSDecoderB200.h) the way a client
+// of the reference drives DCSDecoderNative (DCSExplorer.cpp:1308-1341): load a ROM zip, soft-boot,
+// write data-port bytes at given frames, pull samples one at a time, dump raw PCM.
+//   decoder_b200_demo <rom.zip> <timeline.txt> <n_frames> <master_volume> <chunk_frames> <out.pcm>
+// timeline.txt: lines "<frame> <byte>" sorted by frame.  Exit code 3 = no usable GPU.
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+#include "../../include/DCSDecoderB200.h"
+
+struct RecHost : DCSDecoderB200::Host {
+    std::vector<uint8_t> bytes;
+    void ReceiveDataPort(uint8_t b) override { bytes.push_back(b); }
+};
+
+int main(int argc, char **argv)
+{
+    if (argc < 7) { fprintf(stderr, "usage: %s rom.zip timeline.txt n_frames volume chunk out.pcm\n", argv[0]); return 2; }
+    RecHost host;
+    DCSDecoderB200 dec(&host, 0, atoi(argv[5]));
+    if (!dec.IsOK()) { fprintf(stderr, "%s\n", dec.GetErrorMessage().c_str()); return 3; }
+    std::string err;
+    if (dec.LoadROMFromZipFile(argv[1], nullptr, &err) != DCSDecoderB200::ZipLoadStatus::Success) { fprintf(stderr, "%s\n", err.c_str()); return 4; }
+    if (dec.CheckROMs() != 1) { fprintf(stderr, "ROM check failed\n"); return 5; }
+    dec.SoftBoot();
+    if (!dec.IsOK()) { fprintf(stderr, "%s\n", dec.GetErrorMessage().c_str()); return 6; }
+    dec.SetMasterVolume(atoi(argv[4]));
+    std::vector<std::pair<unsigned, unsigned>> writes;
+    if (FILE *f = fopen(argv[2], "r")) {
+        unsigned fr, b;
+        while (fscanf(f, "%u %u", &fr, &b) == 2) writes.emplace_back(fr, b);
+        fclose(f);
+    }
+    const unsigned nframes = (unsigned)atoi(argv[3]);
+    std::vector<int16_t> pcm((size_t)nframes * 240);
+    size_t w = 0;
+    for (unsigned fr = 0; fr < nframes; ++fr) {
+        while (w < writes.size() && writes[w].first <= fr) dec.WriteDataPort((uint8_t)writes[w++].second);
+        for (int i = 0; i < 240; ++i) pcm[(size_t)fr * 240 + i] = dec.GetNextSample();
+    }
+    FILE *o = fopen(argv[6], "wb");
+    fwrite(pcm.data(), 2, pcm.size(), o);
+    fclose(o);
+    DCSDecoderB200::HWVersion hw; DCSDecoderB200::OSVersion os;
+    printf("%s | tracks 0..%u | %d channels | %zu streams | host bytes", dec.GetVersionInfo(&hw, &os).c_str(), dec.GetMaxTrackNumber(),
+           dec.GetNumChannels(), dec.ListStreams().size());
+    for (uint8_t b : host.bytes) printf(" %02x", b);
+    printf("\n");
+    DCSDecoderB200::TrackInfo ti;
+    if (dec.GetTrackInfo(0, ti)) {
+        auto rp = dec.MakeROMPointer(ti.address);
+        printf("track 0: type %d channel %d time %u looping %d first byte %02x\n", ti.type, ti.channel, ti.time, (int)ti.looping, rp.p ? rp.p[0] : 0);
+    }
+    for (uint32_t a : dec.ListStreams()) {
+        auto si = dec.GetStreamInfo(dec.MakeROMPointer(a));
+        printf("stream $%06x: %d frames, %d bytes, type %d.%d\n", a, si.nFrames, si.nBytes, si.streamType, si.streamSubType);
+        break;
+    }
+    return 0;
+}
