@@ -75,6 +75,9 @@ class Context:
         if rc != OK:
             raise DcsbError("%s failed (%d): %s" % (what, rc, self._L.dcsb_last_error(self._h).decode()))
 
+    def set_overlap(self, on):
+        self._L.dcsb_set_overlap(self._h, 1 if on else 0)
+
     def decode_streams(self, streams, pcm_out=None, **kw):
         """dcsb_decode_streams with host buffers.  Returns (pcm int16 array, offsets, results)."""
         descs, keep = make_descs(streams, **kw)

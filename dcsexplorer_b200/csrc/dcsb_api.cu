@@ -41,12 +41,24 @@ extern "C" void dcsb_destroy(dcsb_ctx *ctx)
     cudaSetDevice(ctx->device);
     for (DcsbLane &l : ctx->lanes) {
         if (l.st) { cudaStreamSynchronize(l.st); cudaStreamDestroy(l.st); }
+        if (l.aux) { cudaStreamSynchronize(l.aux); cudaStreamDestroy(l.aux); }
+        if (l.ev_go) cudaEventDestroy(l.ev_go);
+        if (l.ev_scan) cudaEventDestroy(l.ev_scan);
+        l.d_progress.release(false);
         l.h_slab.release(true); l.h_res.release(true);
         for (DcsbBuf *b : { &l.d_slab, &l.d_recs, &l.d_tiles, &l.d_bitpos, &l.d_bt, &l.d_hdrbits, &l.d_status, &l.d_nplay,
-                            &l.d_endbits, &l.d_stopband, &l.d_csum, &l.d_pcm }) b->release(false);
+                            &l.d_endbits, &l.d_stopband, &l.d_csum, &l.d_pcm, &l.d_queue }) b->release(false);
     }
+    if (ctx->aux) { cudaStreamSynchronize(ctx->aux); cudaStreamDestroy(ctx->aux); }
     cudaFree(ctx->d_tables);
     delete ctx;
+}
+
+extern "C" int dcsb_set_overlap(dcsb_ctx *ctx, int on)
+{
+    if (!ctx) return DCSB_E_ARG;
+    ctx->overlap = on != 0;
+    return DCSB_OK;
 }
 
 extern "C" const char *dcsb_last_error(const dcsb_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
@@ -58,7 +70,7 @@ extern "C" void dcsb_batch_destroy(dcsb_batch *b)
     cudaFree(b->d_slab); cudaFree(b->d_recs); cudaFree(b->d_tiles);
     cudaFree(b->scan.bitpos); cudaFree(b->scan.bt); cudaFree(b->scan.hdrbits); cudaFree(b->scan.status); cudaFree(b->scan.nplay);
     cudaFree(b->scan.endbits); cudaFree(b->scan.stopband); cudaFree(b->scan.dbg);
-    cudaFree(b->d_pcm); cudaFree(b->d_checksums);
+    cudaFree(b->d_pcm); cudaFree(b->d_checksums); cudaFree(b->d_progress); cudaFree(b->d_queue);
     for (auto &e : b->ev) if (e) cudaEventDestroy(e);
     delete b;
 }
@@ -90,6 +102,7 @@ int dcsb_batch_create_impl(dcsb_ctx *ctx, const dcsb_stream_desc *descs, size_t 
     b->tiles = prep.tiles;
     b->ntiles94 = prep.ntiles94;
     b->ntiles93 = prep.ntiles93;
+    b->nqueue94 = prep.nqueue94;
     b->total_frames_in = prep.total_frames_in;
     b->total_out_frames = prep.total_out_frames;
     b->compressed_bytes = prep.compressed_bytes;
@@ -121,10 +134,12 @@ int dcsb_batch_create_impl(dcsb_ctx *ctx, const dcsb_stream_desc *descs, size_t 
     CKB(cudaMalloc(&b->scan.endbits, std::max<size_t>(1, n) * sizeof(uint32_t)), "cudaMalloc(endbits)");
     CKB(cudaMalloc(&b->scan.stopband, std::max<size_t>(1, n)), "cudaMalloc(stopband)");
 #ifdef DCSB_SCAN_DEBUG
-    CKB(cudaMalloc(&b->scan.dbg, std::max<size_t>(1, n) * 16), "cudaMalloc(dbg)");
-    CKB(cudaMemset(b->scan.dbg, 0, std::max<size_t>(1, n) * 16), "memset(dbg)");
+    CKB(cudaMalloc(&b->scan.dbg, std::max<size_t>(2048, n) * 32), "cudaMalloc(dbg)");
+    CKB(cudaMemset(b->scan.dbg, 0, std::max<size_t>(2048, n) * 32), "memset(dbg)");
 #endif
     CKB(cudaMalloc(&b->d_checksums, std::max<size_t>(1, n) * sizeof(unsigned long long)), "cudaMalloc(checksums)");
+    CKB(cudaMalloc(&b->d_progress, (n + 4) * sizeof(uint32_t)), "cudaMalloc(progress)");
+    CKB(cudaMalloc(&b->d_queue, std::max<size_t>(1, (size_t)b->nqueue94) * sizeof(unsigned long long)), "cudaMalloc(queue)");
     for (auto &ev : b->ev) CKB(cudaEventCreate(&ev), "cudaEventCreate");
 #undef CKB
     *out = b;
@@ -139,7 +154,8 @@ extern "C" void *dcsb_batch_device_pcm(dcsb_batch *b) { return b ? b->d_pcm : nu
 extern "C" int dcsb_batch_launches(const dcsb_batch *b)
 {
     if (!b) return 0;
-    return (b->n ? 1 : 0) + (b->ntiles94 ? 1 : 0) + (b->ntiles93 ? 1 : 0);   // scan + one decode launch per transform family
+    // scan (+ the one-thread gate when scan and decode overlap) + one decode launch per transform family
+    return (b->n ? 1 : 0) + (b->n && b->ctx->overlap ? 1 : 0) + (b->ntiles94 ? 1 : 0) + (b->ntiles93 ? 1 : 0);
 }
 
 extern "C" int dcsb_batch_decode(dcsb_batch *b, void *d_pcm, void *cuda_stream)
@@ -155,22 +171,53 @@ extern "C" int dcsb_batch_decode(dcsb_batch *b, void *d_pcm, void *cuda_stream)
     }
     if (b->n == 0) return DCSB_OK;
     CK(cudaMemsetAsync(b->d_checksums, 0, b->n * sizeof(unsigned long long), st), "memset checksums");
-    CK(cudaEventRecord(b->ev[0], st), "event");
-    CK(dcsb_launch_scan(b->d_slab, b->d_recs, (int)b->n, 0, ctx->d_tables, b->scan, st), "scan kernel launch");
-    CK(cudaEventRecord(b->ev[1], st), "event");
-    CK(dcsb_launch_decode(b->d_slab, b->d_recs, b->d_tiles, b->ntiles94, b->ntiles93, ctx->d_tables, b->scan,
-                          pcm, b->d_checksums, st), "decode kernel launch");
-    CK(cudaEventRecord(b->ev[2], st), "event");
+    if (!ctx->overlap) {
+        // one kernel after the other on the caller's stream
+        DcsbScanOut so = b->scan;
+        so.progress = so.started = so.qctl = nullptr;
+        so.queue = nullptr;
+        CK(cudaEventRecord(b->ev[0], st), "event");
+        CK(dcsb_launch_scan(b->d_slab, b->d_recs, (int)b->n, 0, ctx->d_tables, so, st), "scan kernel launch");
+        CK(cudaEventRecord(b->ev[1], st), "event");
+        CK(cudaEventRecord(b->ev[3], st), "event");
+        CK(dcsb_launch_decode(b->d_slab, b->d_recs, b->d_tiles, b->ntiles94, b->ntiles93, ctx->d_tables, so,
+                              pcm, b->d_checksums, st), "decode kernel launch");
+        CK(cudaEventRecord(b->ev[2], st), "event");
+    } else {
+        // the scan (a few latency-bound warps per SM) runs on its own stream BESIDE the decode kernel,
+        // whose warps wait per work item for the checkpoints they need (dcsb_await)
+        if (!ctx->aux) CK(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking), "cudaStreamCreate");
+        DcsbScanOut so = b->scan;
+        so.progress = b->d_progress;
+        so.started = b->d_progress + b->n;
+        so.qctl = b->d_progress + b->n + 1;
+        so.queue = b->d_queue;
+        CK(cudaMemsetAsync(b->d_progress, 0, (b->n + 4) * sizeof(uint32_t), st), "memset progress");
+        if (b->nqueue94) CK(cudaMemsetAsync(b->d_queue, 0, (size_t)b->nqueue94 * sizeof(unsigned long long), st), "memset queue");
+        CK(cudaEventRecord(b->ev[0], st), "event");
+        CK(cudaStreamWaitEvent(ctx->aux, b->ev[0], 0), "stream wait");
+        CK(dcsb_launch_scan(b->d_slab, b->d_recs, (int)b->n, 0, ctx->d_tables, so, ctx->aux), "scan kernel launch");
+        CK(cudaEventRecord(b->ev[1], ctx->aux), "event");
+        CK(dcsb_launch_gate(so, dcsb_scan_grid((int)b->n), st), "gate kernel launch");
+        CK(cudaEventRecord(b->ev[3], st), "event");
+        CK(dcsb_launch_decode_queue(b->d_slab, b->d_recs, b->nqueue94, ctx->d_tables, so, pcm, b->d_checksums, st), "decode kernel launch");
+        CK(dcsb_launch_decode(b->d_slab, b->d_recs, b->d_tiles + b->ntiles94, 0, b->ntiles93, ctx->d_tables, so,
+                              pcm, b->d_checksums, st), "decode kernel launch");
+        CK(cudaStreamWaitEvent(st, b->ev[1], 0), "stream wait");
+        CK(cudaEventRecord(b->ev[2], st), "event");
+    }
     b->timed = true;
     return DCSB_OK;
 }
 
 extern "C" float dcsb_batch_last_kernel_ms(dcsb_batch *b, int which)
 {
-    if (!b || !b->timed || which < 0 || which > 1) return -1.f;
+    // 0 = scan span, 1 = decode span (from its launch; overlaps the scan unless dcsb_set_overlap(ctx, 0)), 2 = whole step
+    if (!b || !b->timed || which < 0 || which > 2) return -1.f;
     float ms = -1.f;
-    if (cudaEventSynchronize(b->ev[which + 1]) != cudaSuccess) return -1.f;
-    if (cudaEventElapsedTime(&ms, b->ev[which], b->ev[which + 1]) != cudaSuccess) return -1.f;
+    cudaEvent_t a = which == 1 ? b->ev[3] : b->ev[0], z = which == 0 ? b->ev[1] : b->ev[2];
+    if (cudaEventSynchronize(b->ev[2]) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, a, z) != cudaSuccess) return -1.f;
     return ms;
 }
 
@@ -214,7 +261,7 @@ extern "C" int dcsb_batch_read_pcm(dcsb_batch *b, size_t i, int16_t *pcm, size_t
 extern "C" int dcsb_batch_scan_debug(dcsb_batch *b, uint32_t *out4)
 {
     if (!b || !out4) return DCSB_E_ARG;
-    return cudaMemcpy(out4, b->scan.dbg, b->n * 16, cudaMemcpyDeviceToHost) == cudaSuccess ? DCSB_OK : DCSB_E_CUDA;
+    return cudaMemcpy(out4, b->scan.dbg, std::max<size_t>(2048, b->n) * 32, cudaMemcpyDeviceToHost) == cudaSuccess ? DCSB_OK : DCSB_E_CUDA;
 }
 #endif
 
@@ -256,6 +303,11 @@ static int lane_submit(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs
     const size_t n = l.count;
     const dcsb_stream_desc *d = descs + l.first;
     if (!l.st) CK(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (!l.aux) {
+        CK(cudaStreamCreateWithFlags(&l.aux, cudaStreamNonBlocking), "cudaStreamCreate");
+        CK(cudaEventCreateWithFlags(&l.ev_go, cudaEventDisableTiming), "cudaEventCreate");
+        CK(cudaEventCreateWithFlags(&l.ev_scan, cudaEventDisableTiming), "cudaEventCreate");
+    }
     // in-place upload? (all streams close together inside one pinned host allocation)
     const uint8_t *lo = nullptr, *hi = nullptr;
     uint64_t sum = 0;
@@ -283,6 +335,8 @@ static int lane_submit(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs
     ENS(l.d_endbits, nn * 4, false, "cudaMalloc(endbits)");
     ENS(l.d_stopband, nn, false, "cudaMalloc(stopband)");
     ENS(l.d_csum, nn * 8, false, "cudaMalloc(checksums)");
+    ENS(l.d_progress, (nn + 4) * 4, false, "cudaMalloc(progress)");
+    ENS(l.d_queue, std::max<size_t>(1, (size_t)p.nqueue94) * 8, false, "cudaMalloc(queue)");
     ENS(l.d_pcm, std::max<uint64_t>(2, p.total_out_frames * 480), false, "cudaMalloc(pcm)");
     ENS(l.h_res, nn * 20, true, "cudaMallocHost(results)");
     if (n == 0) return DCSB_OK;
@@ -300,11 +354,29 @@ static int lane_submit(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs
     CK(cudaMemcpyAsync(l.d_tiles.p, p.tiles.data(), p.tiles.size() * sizeof(DcsbTile), cudaMemcpyHostToDevice, l.st), "H2D tiles");
     CK(cudaMemsetAsync(l.d_csum.p, 0, n * 8, l.st), "memset checksums");
     DcsbScanOut so{ (uint32_t *)l.d_bitpos.p, (uint2 *)l.d_bt.p, (uint16_t *)l.d_hdrbits.p, (int32_t *)l.d_status.p,
-                    (uint32_t *)l.d_nplay.p, (uint32_t *)l.d_endbits.p, (uint8_t *)l.d_stopband.p, nullptr };
-    CK(dcsb_launch_scan((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p, (int)n, scan_lanes, ctx->d_tables, so, l.st), "scan kernel launch");
-    CK(dcsb_launch_decode((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p, (const DcsbTile *)l.d_tiles.p,
-                          p.ntiles94, p.ntiles93, ctx->d_tables, so, (int16_t *)l.d_pcm.p, (unsigned long long *)l.d_csum.p, l.st),
+                    (uint32_t *)l.d_nplay.p, (uint32_t *)l.d_endbits.p, (uint8_t *)l.d_stopband.p, nullptr, nullptr, nullptr, nullptr, nullptr };
+    if (ctx->overlap) {
+        so.progress = (uint32_t *)l.d_progress.p;
+        so.started = so.progress + n;
+        so.qctl = so.progress + n + 1;
+        so.queue = (unsigned long long *)l.d_queue.p;
+        CK(cudaMemsetAsync(l.d_progress.p, 0, (n + 4) * 4, l.st), "memset progress");
+        if (p.nqueue94) CK(cudaMemsetAsync(l.d_queue.p, 0, (size_t)p.nqueue94 * 8, l.st), "memset queue");
+        CK(cudaEventRecord(l.ev_go, l.st), "event");
+        CK(cudaStreamWaitEvent(l.aux, l.ev_go, 0), "stream wait");
+        CK(dcsb_launch_scan((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p, (int)n, scan_lanes, ctx->d_tables, so, l.aux), "scan kernel launch");
+        CK(cudaEventRecord(l.ev_scan, l.aux), "event");
+        CK(dcsb_launch_gate(so, dcsb_scan_grid((int)n), l.st), "gate kernel launch");
+    } else
+        CK(dcsb_launch_scan((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p, (int)n, scan_lanes, ctx->d_tables, so, l.st), "scan kernel launch");
+    if (ctx->overlap)
+        CK(dcsb_launch_decode_queue((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p, p.nqueue94, ctx->d_tables, so,
+                                    (int16_t *)l.d_pcm.p, (unsigned long long *)l.d_csum.p, l.st), "decode kernel launch");
+    CK(dcsb_launch_decode((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p,
+                          (const DcsbTile *)l.d_tiles.p + (ctx->overlap ? p.ntiles94 : 0), ctx->overlap ? 0 : p.ntiles94, p.ntiles93,
+                          ctx->d_tables, so, (int16_t *)l.d_pcm.p, (unsigned long long *)l.d_csum.p, l.st),
        "decode kernel launch");
+    if (ctx->overlap) CK(cudaStreamWaitEvent(l.st, l.ev_scan, 0), "stream wait");
     l.direct_pcm = pcm_pinned_packed;
     if (l.direct_pcm)
         CK(cudaMemcpyAsync(pcm_out + l.pcm_base, l.d_pcm.p, p.total_out_frames * 480, cudaMemcpyDeviceToHost, l.st), "D2H pcm");

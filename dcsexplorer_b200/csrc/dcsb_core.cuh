@@ -129,6 +129,56 @@ DCSB_HD int dcsb_long_code(const DcsbBits &rd, uint32_t &pos, const DcsbLongCode
     return -1;
 }
 
+// ---------------------------------------------------------------------------------------
+// scan -> decode hand-off (both kernels resident at the same time): the scan publishes how many
+// checkpoints of a stream are valid, the decode warps wait for the ones they need and read them
+// past L1 (a line fetched earlier may predate the scan's later writes to it).
+#if DCSB_DEVICE_PASS
+DCSB_HD void dcsb_publish(uint32_t *progress, int si, uint32_t v)
+{
+    if (!progress) return;
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(progress + si), "r"(v) : "memory");
+}
+// returns true when the stream's scan is finished (nplay / stopband are final)
+__device__ __forceinline__ bool dcsb_await(const uint32_t *progress, uint32_t stream, uint32_t need)
+{
+    if (!progress) return true;
+    uint32_t v = 0;
+    if ((threadIdx.x & 31) == 0) {
+        const long long t0 = clock64();
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(progress + stream) : "memory");
+            if ((v & DCSB_SCAN_DONE) || v >= need) break;
+            if (clock64() - t0 > 4000000000ll) break;        // ~2 s: never hang the GPU on a lost producer
+            __nanosleep(256);
+        }
+    }
+    v = __shfl_sync(0xffffffffu, v, 0);
+    return (v & DCSB_SCAN_DONE) != 0;
+}
+#define DCSB_LDCG(p) __ldcg(p)
+// append the stream's work items covering output frames [from, to) to the ready queue
+__device__ __forceinline__ void dcsb_queue_push(const DcsbScanOut &out, int si, uint32_t from, uint32_t to, bool fin)
+{
+    if (!out.queue || from >= to) return;
+    __threadfence();
+    const uint32_t n = (to - from + DCSB_QITEM - 1) / DCSB_QITEM;
+    const uint32_t slot = atomicAdd(out.qctl, n);
+    for (uint32_t k = 0; k < n; ++k) {
+        const unsigned long long e = DCSB_Q_VALID | (fin ? DCSB_Q_FINAL : 0ull) | ((unsigned long long)(uint32_t)si << 24) |
+                                     (unsigned long long)(from + k * DCSB_QITEM);
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(out.queue + slot + k), "l"(e) : "memory");
+    }
+}
+#else
+struct DcsbScanOut;
+DCSB_HD void dcsb_queue_push(const DcsbScanOut &, int, uint32_t, uint32_t, bool) {}
+DCSB_HD void dcsb_publish(uint32_t *, int, uint32_t) {}
+DCSB_HD bool dcsb_await(const uint32_t *, uint32_t, uint32_t) { return true; }
+#define DCSB_LDCG(p) (*(p))
+#endif
+
 #define DCSB_WALK_OK        0
 #define DCSB_WALK_BANDTYPE -3
 
@@ -518,6 +568,11 @@ DCSB_HD void dcsb_scan_stream(const uint8_t *slab, const DcsbStreamRec *streams,
             if (rc == 0 && pos > nbits) rc = -2;   // DCSB_E_TRUNCATED
             if (rc) { status = rc; nplay = f; break; }
             if (sb != 99) { status = -5; nplay = f + 1; stopband = sb; ++f; break; }   // DCSB_E_STOPPED
+            if ((f & 15) == 15) {
+                out.bitpos[s.frame_base + f + 1] = pos;
+                out.bt[s.frame_base + f + 1] = make_uint2((uint32_t)bt, (uint32_t)(bt >> 32));
+                dcsb_publish(out.progress, si, f + 2);
+            }
         }
         if (status == 0 || status == -5) {
             out.bitpos[s.frame_base + f] = pos;
@@ -528,6 +583,7 @@ DCSB_HD void dcsb_scan_stream(const uint8_t *slab, const DcsbStreamRec *streams,
     out.nplay[si] = nplay;
     out.endbits[si] = pos;
     out.stopband[si] = (uint8_t)stopband;
+    dcsb_publish(out.progress, si, DCSB_SCAN_DONE);
 }
 
 template <bool T93> struct DcsbRow { static constexpr int WORDS = T93 ? 257 : 129; };
@@ -543,7 +599,9 @@ DCSB_HD unsigned long long dcsb_decode_tile(const uint8_t *slab, const DcsbStrea
     constexpr int ROWW = DcsbRow<T93>::WORDS;
     const DcsbStreamRec *sp = streams + tl.stream;
     const long long out_frames = sp->out_frames;
-    const long long nplay = scan.nplay[tl.stream];
+    // checkpoints first-1 .. first+count-1 (walkers of this layout need no look-ahead entry)
+    const bool fin = dcsb_await(scan.progress, tl.stream, tl.first + tl.count < sp->nframes ? tl.first + tl.count : sp->nframes);
+    const long long nplay = fin ? (long long)DCSB_LDCG(scan.nplay + tl.stream) : (long long)sp->nframes;
     const int fmt = sp->fmt;
     uint32_t *tails = rows + 32 * ROWW;             // two 8-word overlap buffers (ping-pong)
 
@@ -562,11 +620,11 @@ DCSB_HD unsigned long long dcsb_decode_tile(const uint8_t *slab, const DcsbStrea
             cx.mult = f == 0 ? sp->mult0 : sp->mult1;
             cx.zero_from = 16;
             if (f == nplay - 1) {
-                const int sb = scan.stopband[tl.stream];
+                const int sb = fin ? DCSB_LDCG(scan.stopband + tl.stream) : 0xFF;
                 if (sb != 0xFF) cx.zero_from = sb;
             }
-            uint32_t pos = scan.bitpos[sp->frame_base + (uint32_t)f];
-            const uint2 b2 = scan.bt[sp->frame_base + (uint32_t)f];
+            uint32_t pos = DCSB_LDCG(scan.bitpos + sp->frame_base + (uint32_t)f);
+            const uint2 b2 = DCSB_LDCG(scan.bt + sp->frame_base + (uint32_t)f);
             uint64_t bt = ((uint64_t)b2.y << 32) | b2.x;
             int sb = 99;
             dcsb_walk<true>(fmt, cx, pos, bt, reinterpret_cast<int16_t *>(rows + l * ROWW), sb);

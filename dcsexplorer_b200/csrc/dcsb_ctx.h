@@ -30,7 +30,9 @@ struct DcsbBuf {
 // streams needs, kept across calls so that the steady state does no allocation.
 #define DCSB_MAX_LANES 8
 struct DcsbLane {
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, aux = nullptr;                // aux: the scan runs beside the decode
+    cudaEvent_t ev_go = nullptr, ev_scan = nullptr;
+    DcsbBuf d_progress, d_queue;
     DcsbBuf h_slab, h_res;                                   // pinned
     DcsbBuf d_slab, d_recs, d_tiles, d_bitpos, d_bt, d_hdrbits, d_status, d_nplay, d_endbits, d_stopband, d_csum, d_pcm;
     DcsbPrepared prep;
@@ -42,6 +44,8 @@ struct DcsbLane {
 struct dcsb_ctx {
     int device = 0;
     DcsbTables *d_tables = nullptr;
+    cudaStream_t aux = nullptr;              // resident batches: stream the scan runs on beside the decode
+    bool overlap = true;                     // scan and decode kernels resident together (dcsb_set_overlap)
     DcsbLane lanes[DCSB_MAX_LANES];
     std::string err;
 };
@@ -64,7 +68,10 @@ struct dcsb_batch {
     DcsbScanOut scan{};
     int16_t *d_pcm = nullptr;                // internal PCM buffer (lazy)
     unsigned long long *d_checksums = nullptr;
-    cudaEvent_t ev[3] = { nullptr, nullptr, nullptr };
+    int nqueue94 = 0;
+    uint32_t *d_progress = nullptr;          // [n] scan progress + [1] resident scan CTAs + [2] queue tail / head
+    unsigned long long *d_queue = nullptr;   // [nqueue94] ready queue scan -> decode
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };    // step start, scan end, decode end, decode start
     bool timed = false;
 };
 

@@ -392,15 +392,14 @@ DCSB_HD void dcsb_frame_output94(const int16_t *r16, uint32_t *pcm32, uint32_t f
 
 DCSB_HD unsigned long long dcsb_decode94_item(const uint8_t *slab, const DcsbStreamRec *streams, DcsbTile it,
                                               const DcsbTables *tab, const uint16_t *lut, const DcsbTw94 *tw,
-                                              const uint8_t *hdr, const DcsbScanOut &scan, int16_t *pcm, uint32_t *rows)
+                                              const uint8_t *hdr, const DcsbScanOut &scan, uint32_t nplay, int stopband,
+                                              int16_t *pcm, uint32_t *rows)
 {
     const DcsbStreamRec *sp = streams + it.stream;
-    const uint32_t nplay = scan.nplay[it.stream];
     const uint32_t fb = sp->frame_base;
     const uint32_t fend = it.first + it.count;
     int16_t *tail = reinterpret_cast<int16_t *>(rows + 32 * DCSB_ROW94_WORDS);   // re[0..8), im[8..16)
     uint32_t *pcm32 = reinterpret_cast<uint32_t *>(pcm + sp->pcm_off);
-    const int stopband = scan.stopband[it.stream];
     unsigned long long csum = 0;
 
     uint32_t cur = it.first;
@@ -421,8 +420,8 @@ DCSB_HD unsigned long long dcsb_decode94_item(const uint8_t *slab, const DcsbStr
                 for (int i = 0; i < 128; ++i) row[i] = 0;
                 if (f < nplay) {
                     int16_t *r16 = reinterpret_cast<int16_t *>(row);
-                    const uint2 bp = scan.bt[fb + f], bc = scan.bt[fb + f + 1];
-                    DcsbWin win = dcsb_make_window(slab, *sp, scan.bitpos[fb + f] + scan.hdrbits[fb + f]);
+                    const uint2 bp = DCSB_LDCG(scan.bt + fb + f), bc = DCSB_LDCG(scan.bt + fb + f + 1);
+                    DcsbWin win = dcsb_make_window(slab, *sp, DCSB_LDCG(scan.bitpos + fb + f) + DCSB_LDCG(scan.hdrbits + fb + f));
                     const int zero_from = (f == nplay - 1 && stopband != 0xFF) ? stopband : 16;
                     dcsb_lane_decode94<false>(hdr, lut, win, ((uint64_t)bp.y << 32) | bp.x, ((uint64_t)bc.y << 32) | bc.x,
                                               f == 0 ? sp->mult0 : sp->mult1, zero_from, r16);

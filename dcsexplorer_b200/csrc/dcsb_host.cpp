@@ -191,9 +191,12 @@ int dcsb_prepare(const dcsb_stream_desc *descs, size_t n, DcsbPrepared *p, const
     uint64_t est_frames = 0;
     for (size_t i = 0; i < n; ++i)
         if (descs[i].data && descs[i].nbytes >= 2) est_frames += (((uint32_t)descs[i].data[0] << 8) | descs[i].data[1]) + descs[i].tail_frames;
-    uint32_t item_len = (uint32_t)std::min<uint64_t>(255, std::max<uint64_t>(31, est_frames / 8192));
+    // (and short enough that the decode kernel follows the scan running beside it closely: an item
+    // can only start once the scan has passed its last frame)
+    uint32_t item_len = (uint32_t)std::min<uint64_t>(63, std::max<uint64_t>(31, est_frames / 8192));
     item_len = item_len < 63 ? 31 : 31 + ((item_len - 31) / 32) * 32;       // 31 + whole 32-frame tiles
-    size_t items94 = 0;
+    size_t items94 = 0, items93 = 0;
+    uint64_t nq94 = 0;
     for (size_t i = 0; i < n; ++i) {
         const dcsb_stream_desc &d = descs[i];
         DcsbStreamRec &r = p->recs[i];
@@ -224,23 +227,37 @@ int dcsb_prepare(const dcsb_stream_desc *descs, size_t n, DcsbPrepared *p, const
         }
         r.nframes = nf;
         stream_gain(d, r);
-        if (fmt == DCSB_FMT_94) items94 += (r.out_frames + item_len - 1) / item_len;
-        else for (uint32_t f = 0; f < r.out_frames; f += DCSB_TILE_OUT)
-            t93.push_back(DcsbTile{ (uint32_t)i, f, std::min<uint32_t>(DCSB_TILE_OUT, r.out_frames - f) });
+        if (fmt == DCSB_FMT_94) { items94 += (r.out_frames + item_len - 1) / item_len; nq94 += (r.out_frames + DCSB_QITEM - 1) / DCSB_QITEM; }
+        else items93 += (r.out_frames + DCSB_TILE_OUT - 1) / DCSB_TILE_OUT;
         off += ((uint64_t)d.nbytes + 15 + 16) & ~15ull;     // 16-byte aligned, >= 16 bytes of zero padding
         frames += nf;
         ckpt += (uint64_t)nf + 1;
         pcm += (uint64_t)r.out_frames * 240;
         p->compressed_bytes += d.nbytes;
     }
+    // work items in frame-major order (item k of every stream before item k + 1 of any): CTAs are
+    // dispatched in index order, so the decode kernel works its way through the streams at the pace
+    // the scan running beside it delivers their checkpoints
     t94.reserve(items94);
-    for (size_t i = 0; i < n; ++i) {
-        const DcsbStreamRec &r = p->recs[i];
-        if (r.fmt != DCSB_FMT_94) continue;
-        for (uint32_t f = 0; f < r.out_frames; f += item_len)
-            t94.push_back(DcsbTile{ (uint32_t)i, f, std::min<uint32_t>(item_len, r.out_frames - f) });
+    t93.reserve(items93);
+    for (int fam = 0; fam < 2; ++fam) {
+        const uint32_t len = fam ? (uint32_t)DCSB_TILE_OUT : item_len;
+        std::vector<DcsbTile> &dst = fam ? t93 : t94;
+        std::vector<uint32_t> live;
+        for (size_t i = 0; i < n; ++i)
+            if ((p->recs[i].fmt != DCSB_FMT_94) == (fam == 1) && p->recs[i].out_frames) live.push_back((uint32_t)i);
+        for (uint32_t f = 0; !live.empty(); f += len) {
+            size_t keep = 0;
+            for (uint32_t i : live) {
+                const uint32_t of = p->recs[i].out_frames;
+                dst.push_back(DcsbTile{ i, f, std::min<uint32_t>(len, of - f) });
+                if (f + len < of) live[keep++] = i;
+            }
+            live.resize(keep);
+        }
     }
-    if (ckpt > 0xFFFFFFF0ull || t94.size() + t93.size() > 0x7FFFFFF0ull) return DCSB_E_ARG;
+    if (ckpt > 0xFFFFFFF0ull || t94.size() + t93.size() > 0x7FFFFFF0ull || nq94 > 0x7FFFFFF0ull || n > 0x3FFFFFF0ull) return DCSB_E_ARG;
+    p->nqueue94 = (int)nq94;
     p->total_frames_in = frames;
     p->total_checkpoints = ckpt;
     p->total_out_frames = pcm / 240;

@@ -70,6 +70,10 @@ struct DcsbTables {
     uint8_t t1[6 * DCSB_T1_CB];
 };
 
+#define DCSB_SCAN_DONE 0x80000000u
+#define DCSB_QITEM 64u                      // frames per queued work item
+#define DCSB_Q_VALID (1ull << 63)           // queue entry: VALID | FINAL? | stream << 24 | first frame
+#define DCSB_Q_FINAL (1ull << 62)           // the stream's scan is finished: nplay / stopband are final
 struct DcsbScanOut {
     // checkpoints: one per stream frame plus one end entry per stream (frame_base counts both)
     uint32_t *bitpos;          // frame start, bits from the first byte after the stream header
@@ -79,6 +83,17 @@ struct DcsbScanOut {
     uint32_t *nplay;           // [nstreams] frames that decode before the channel goes silent
     uint32_t *endbits;         // [nstreams] bit position after the last decoded frame
     uint8_t  *stopband;        // [nstreams] band at which the reference's error path fired (else 0xFF)
+    // scan -> decode hand-off while both kernels run (NULL = the scan has finished before the decode
+    // starts): progress[s] = checkpoints of stream s that are valid so far, DCSB_SCAN_DONE once the
+    // stream is finished and status / nplay / stopband are final; started[0] counts resident scan CTAs
+    uint32_t *progress;
+    uint32_t *started;
+    // 1994 layout, overlapped mode: the scan appends a work item to `queue` every DCSB_QITEM frames
+    // of a stream (and the rest of the stream when it finishes it); the persistent decode kernel
+    // takes the items in that order, so it always works on frames whose checkpoints exist.
+    // qctl[0] = tail (scan side), qctl[1] = head (decode side).
+    unsigned long long *queue;
+    uint32_t *qctl;
     uint32_t *dbg;             // tuning builds (-DDCSB_SCAN_DEBUG): [nstreams][4] cycles lo/hi, table steps, header steps; else NULL
 };
 
@@ -92,6 +107,7 @@ struct DcsbPrepared {
     std::vector<int32_t> host_status;     // host-side rejections (0 = let the scan decide)
     std::vector<DcsbTile> tiles;          // 1994-family items first, then 1993-family tiles
     int ntiles94 = 0, ntiles93 = 0;
+    int nqueue94 = 0;                     // work items the scan queues for the 1994-layout streams (overlapped mode)
     uint64_t total_frames_in = 0;         // stream frames
     uint64_t total_checkpoints = 0;       // stream frames + one end entry per stream
     uint64_t total_out_frames = 0, compressed_bytes = 0;
@@ -112,6 +128,13 @@ cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, 
                              const DcsbTables *tables, DcsbScanOut out, cudaStream_t st);
 int dcsb_scan_lanes(int nstreams);       // streams per warp the scan launch uses (1..32)
 // tiles[0..ntiles94) use the 1994 transform, tiles[ntiles94..ntiles94+ntiles93) the 1993 one
+// enqueue a one-thread kernel that returns once `ctas` scan CTAs are resident (scan.started)
+cudaError_t dcsb_launch_gate(DcsbScanOut scan, int ctas, cudaStream_t st);
+int dcsb_scan_grid(int nstreams);        // CTAs dcsb_launch_scan uses
+// persistent decode over the scan's ready queue (1994-layout streams, overlapped mode)
+cudaError_t dcsb_launch_decode_queue(const uint8_t *slab, const DcsbStreamRec *streams, int nitems,
+                                     const DcsbTables *tables, DcsbScanOut scan, int16_t *pcm,
+                                     unsigned long long *checksums, cudaStream_t st);
 cudaError_t dcsb_launch_decode(const uint8_t *slab, const DcsbStreamRec *streams, const DcsbTile *tiles,
                                int ntiles94, int ntiles93, const DcsbTables *tables, DcsbScanOut scan,
                                int16_t *pcm, unsigned long long *checksums, cudaStream_t st);

@@ -55,6 +55,7 @@ dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restri
         dst = reinterpret_cast<uint4 *>(sm.t1);
         for (int i = threadIdx.x; i < 6 * DCSB_T1_CB / 16; i += blockDim.x) dst[i] = __ldg(src + i);
     }
+    if (threadIdx.x == 0 && out.started) atomicAdd(out.started, 1u);       // this CTA is resident (dcsb_gate_kernel)
     dcsb_load_lut(sm.lut, tab);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = warp * lanes + lane;              // stream slot inside the CTA
@@ -123,12 +124,107 @@ dcsb_decode94_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__re
     dcsb_load_lut(sm.lut, tab);
     if (item >= nitems) return;
     const DcsbTile it = items[item];
-    unsigned long long csum = dcsb_decode94_item(slab, streams, it, tab, sm.lut, &sm.tw, sm.hdr[warp], scan, pcm, sm.rows[warp]);
+    // checkpoints first-1 .. first+count (a frame's own band types are the NEXT entry)
+    const uint32_t nfr = streams[it.stream].nframes;
+    const bool fin = dcsb_await(scan.progress, it.stream, it.first + it.count + 1 < nfr + 1 ? it.first + it.count + 1 : nfr + 1);
+    const uint32_t nplay = fin ? __ldcg(scan.nplay + it.stream) : nfr;
+    const int stopband = fin ? __ldcg(scan.stopband + it.stream) : 0xFF;
+    unsigned long long csum = dcsb_decode94_item(slab, streams, it, tab, sm.lut, &sm.tw, sm.hdr[warp], scan, nplay, stopband, pcm, sm.rows[warp]);
     if (checksums) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
         if (lane == 0) atomicAdd(checksums + it.stream, csum);
     }
+}
+
+// K2, 1994 layout, overlapped mode: persistent warps take work items from the queue the scan
+// running beside them fills (dcsb_queue_push), in the order the checkpoints become available.
+__global__ void __launch_bounds__(DCSB_WARPS94 * 32, 3)
+dcsb_decode94_queue_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restrict__ streams, int nitems,
+                           const DcsbTables *__restrict__ tab, DcsbScanOut scan, int16_t *__restrict__ pcm,
+                           unsigned long long *__restrict__ checksums)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    DcsbSmem94 &sm = *reinterpret_cast<DcsbSmem94 *>(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {
+        int *dst = reinterpret_cast<int *>(&sm.tw);
+        for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+            dst[i] = tab->tw_c2[i]; dst[64 + i] = tab->tw_s2[i]; dst[128 + i] = tab->pre_c0[i]; dst[192 + i] = tab->pre_c1[i];
+        }
+    }
+    dcsb_load_lut(sm.lut, tab);
+#ifdef DCSB_SCAN_DEBUG
+    unsigned long long t_first = 0, t_last = 0, t_wait = 0, n_items = 0;
+#define DCSB_NOW(v) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v))
+#endif
+    for (;;) {
+        unsigned long long e = 0;
+#ifdef DCSB_SCAN_DEBUG
+        unsigned long long t_a, t_b;
+        DCSB_NOW(t_a);
+#endif
+        if (lane == 0) {
+            const uint32_t q = atomicAdd(scan.qctl + 1, 1u);
+            if (q < (uint32_t)nitems) {
+                const long long t0 = clock64();
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(e) : "l"(scan.queue + q) : "memory");
+                    if (e & DCSB_Q_VALID) break;
+                    if (clock64() - t0 > 4000000000ll) { e = 0; break; }     // never hang the GPU on a lost producer
+                    __nanosleep(256);
+                }
+            }
+        }
+        e = __shfl_sync(0xffffffffu, e, 0);
+#ifdef DCSB_SCAN_DEBUG
+        DCSB_NOW(t_b);
+        if (!(e & DCSB_Q_VALID) && lane == 0 && scan.dbg) {
+            unsigned long long *d = reinterpret_cast<unsigned long long *>(scan.dbg) + 4ull * (blockIdx.x * DCSB_WARPS94 + warp);
+            d[0] = t_first; d[1] = t_last; d[2] = t_wait; d[3] = n_items;
+        }
+        if (e & DCSB_Q_VALID) { t_wait += t_b - t_a; if (!t_first) t_first = t_b; ++n_items; }
+#endif
+        if (!(e & DCSB_Q_VALID)) return;
+        DcsbTile it;
+        it.stream = (uint32_t)((e >> 24) & 0x3FFFFFFFull);
+        it.first = (uint32_t)(e & 0xFFFFFFull);
+        const DcsbStreamRec *sp = streams + it.stream;
+        it.count = sp->out_frames - it.first < DCSB_QITEM ? sp->out_frames - it.first : DCSB_QITEM;
+        const bool fin = (e & DCSB_Q_FINAL) != 0;
+        const uint32_t nplay = fin ? __ldcg(scan.nplay + it.stream) : sp->nframes;
+        const int stopband = fin ? __ldcg(scan.stopband + it.stream) : 0xFF;
+        if (lane < 16) sm.hdr[warp][lane] = sp->hdr[lane];
+        __syncwarp();
+        unsigned long long csum = dcsb_decode94_item(slab, streams, it, tab, sm.lut, &sm.tw, sm.hdr[warp], scan, nplay, stopband, pcm, sm.rows[warp]);
+        if (checksums) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+            if (lane == 0) atomicAdd(checksums + it.stream, csum);
+        }
+        __syncwarp();
+#ifdef DCSB_SCAN_DEBUG
+        DCSB_NOW(t_last);
+#endif
+    }
+}
+
+cudaError_t dcsb_launch_decode_queue(const uint8_t *slab, const DcsbStreamRec *streams, int nitems,
+                                     const DcsbTables *tables, DcsbScanOut scan, int16_t *pcm,
+                                     unsigned long long *checksums, cudaStream_t st)
+{
+    if (nitems <= 0) return cudaSuccess;
+    const size_t smem = sizeof(DcsbSmem94);
+    cudaError_t e = cudaFuncSetAttribute(dcsb_decode94_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    // keep the SM at its largest shared-memory split, so that CTAs of the other kernel can join
+    // this one (the split only changes on an idle SM)
+    e = cudaFuncSetAttribute(dcsb_decode94_queue_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    int grid = (nitems + DCSB_WARPS94 - 1) / DCSB_WARPS94;
+    if (grid > 148 * 3) grid = 148 * 3;             // persistent: what fits on the chip at once
+    dcsb_decode94_queue_kernel<<<grid, DCSB_WARPS94 * 32, smem, st>>>(slab, streams, nitems, tables, scan, pcm, checksums);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------
@@ -199,11 +295,19 @@ cudaError_t dcsb_launch_mix(bool family93, const uint8_t *slab, const DcsbStream
         const size_t smem = (DCSB_LUT_WORDS / 2 + DCSB_WARPS_PER_CTA * DcsbWarpSmem<true>::WORDS) * sizeof(uint32_t);
         cudaError_t e = cudaFuncSetAttribute(dcsb_mix93_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        // keep the SM at its largest shared-memory split, so that CTAs of the other kernel can join
+        // this one (the split only changes on an idle SM)
+        e = cudaFuncSetAttribute(dcsb_mix93_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
         const int grid = (nitems + DCSB_WARPS_PER_CTA - 1) / DCSB_WARPS_PER_CTA;
         dcsb_mix93_kernel<<<grid, DCSB_WARPS_PER_CTA * 32, smem, st>>>(slab, streams, it, nitems, sc, tables, scan, pcm, checksums);
     } else {
         const size_t smem = sizeof(DcsbSmemMix94);
         cudaError_t e = cudaFuncSetAttribute(dcsb_mix94_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        // keep the SM at its largest shared-memory split, so that CTAs of the other kernel can join
+        // this one (the split only changes on an idle SM)
+        e = cudaFuncSetAttribute(dcsb_mix94_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         const int grid = (nitems + DCSB_WARPS94 - 1) / DCSB_WARPS94;
         dcsb_mix94_kernel<<<grid, DCSB_WARPS94 * 32, smem, st>>>(slab, streams, it, nitems, sc, tables, scan, pcm, checksums);
@@ -223,19 +327,57 @@ int dcsb_scan_lanes(int nstreams)
     return 2;
 }
 
+static void scan_shape(int nstreams, int &spc, int &grid)
+{
+    // spread the streams over the SMs first (one CTA per SM), then fill the CTAs up
+    spc = (nstreams + 147) / 148;
+    spc = spc > DCSB_SCAN_SPC ? DCSB_SCAN_SPC : (spc < 1 ? 1 : spc);
+    grid = (nstreams + spc - 1) / spc;
+    if (grid > 148) grid = 148;
+}
+
+int dcsb_scan_grid(int nstreams)
+{
+    int spc, grid;
+    scan_shape(nstreams, spc, grid);
+    return nstreams > 0 ? grid : 0;
+}
+
+// The decode kernel may only start filling the SMs once every scan CTA is resident: its warps
+// wait for scan progress, and a scan CTA that could not get onto the chip behind them would
+// never deliver it.  One thread polls the counter the scan CTAs bump on entry.
+__global__ void dcsb_gate_kernel(const uint32_t *started, uint32_t ctas)
+{
+    const long long t0 = clock64();
+    uint32_t v;
+    do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(started) : "memory");
+        if (v >= ctas) break;
+        __nanosleep(128);
+    } while (clock64() - t0 < 4000000000ll);
+}
+
+cudaError_t dcsb_launch_gate(DcsbScanOut scan, int ctas, cudaStream_t st)
+{
+    if (!scan.started || ctas <= 0) return cudaSuccess;
+    dcsb_gate_kernel<<<1, 1, 0, st>>>(scan.started, (uint32_t)ctas);
+    return cudaGetLastError();
+}
+
 cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, int nstreams, int lanes_hint,
                              const DcsbTables *tables, DcsbScanOut out, cudaStream_t st)
 {
     if (nstreams <= 0) return cudaSuccess;
     const int lanes = lanes_hint > 0 ? lanes_hint : dcsb_scan_lanes(nstreams);
-    // spread the streams over the SMs first (one CTA per SM), then fill the CTAs up
-    int spc = (nstreams + 147) / 148;
-    spc = spc > DCSB_SCAN_SPC ? DCSB_SCAN_SPC : spc;
-    int grid = (nstreams + spc - 1) / spc;
-    if (grid > 148) grid = 148;
+    int spc, grid;
+    scan_shape(nstreams, spc, grid);
     const int warps = (spc + lanes - 1) / lanes;
     const size_t smem = sizeof(DcsbSmemScan);
     cudaError_t e = cudaFuncSetAttribute(dcsb_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    // keep the SM at its largest shared-memory split, so that CTAs of the other kernel can join
+    // this one (the split only changes on an idle SM)
+    e = cudaFuncSetAttribute(dcsb_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     dcsb_scan_kernel<<<grid, warps * 32, smem, st>>>(slab, streams, nstreams, lanes, spc, tables, out);
     return cudaGetLastError();
@@ -248,6 +390,10 @@ static cudaError_t launch_decode93(const uint8_t *slab, const DcsbStreamRec *str
     if (ntiles <= 0) return cudaSuccess;
     const size_t smem = (DCSB_LUT_WORDS / 2 + DCSB_WARPS_PER_CTA * DcsbWarpSmem<true>::WORDS) * sizeof(uint32_t);
     cudaError_t e = cudaFuncSetAttribute(dcsb_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    // keep the SM at its largest shared-memory split, so that CTAs of the other kernel can join
+    // this one (the split only changes on an idle SM)
+    e = cudaFuncSetAttribute(dcsb_decode_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     const int grid = (ntiles + DCSB_WARPS_PER_CTA - 1) / DCSB_WARPS_PER_CTA;
     dcsb_decode_kernel<true><<<grid, DCSB_WARPS_PER_CTA * 32, smem, st>>>(slab, streams, tiles, ntiles, tables, scan, pcm, checksums);
@@ -262,6 +408,10 @@ cudaError_t dcsb_launch_decode(const uint8_t *slab, const DcsbStreamRec *streams
     if (ntiles94 > 0) {
         const size_t smem = sizeof(DcsbSmem94);
         cudaError_t e = cudaFuncSetAttribute(dcsb_decode94_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        // keep the SM at its largest shared-memory split, so that CTAs of the other kernel can join
+        // this one (the split only changes on an idle SM)
+        e = cudaFuncSetAttribute(dcsb_decode94_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         const int grid = (ntiles94 + DCSB_WARPS94 - 1) / DCSB_WARPS94;
         dcsb_decode94_kernel<<<grid, DCSB_WARPS94 * 32, smem, st>>>(slab, streams, tiles, ntiles94, tables, scan, pcm, checksums);

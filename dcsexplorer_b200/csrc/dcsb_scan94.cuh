@@ -109,16 +109,19 @@ struct DcsbRingWin {
     // valid while s + bits <= 64: two short reads (<= 15 bits each) per refill
     DCSB_HD uint32_t peek_wide() const { return (uint32_t)((((((uint64_t)w0) << 32) | w1) << s) >> 32); }
     DCSB_HD void advance(uint32_t n) { s += n; }
+    // select-style on purpose: a compare + predicated block costs a 13-cycle predicate latency on
+    // the position chain; masks cost one ALU hop (the ring is always readable, so the load is
+    // unconditional)
     DCSB_HD void refill()
     {
-        const bool r = s >= 32u;
-        if (r) {
-            s -= 32u;
-            w0 = w1;
-            w1 = DcsbBits::be(nx);
-            nx = ring_word(wa);
-            wa += 4u;
-        }
+        const uint32_t r = s >> 5;                  // 0 or 1
+        const uint32_t mask = 0u - r;
+        const uint32_t nw1 = DcsbBits::be(nx), ld = ring_word(wa);
+        s &= 31u;
+        w0 ^= (w0 ^ w1) & mask;
+        w1 ^= (w1 ^ nw1) & mask;
+        nx ^= (nx ^ ld) & mask;
+        wa += 4u * r;
     }
     DCSB_HD void skip(uint32_t n) { s += n; refill(); }      // n <= 32
 };
@@ -187,6 +190,7 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
 #define DCSB_DBG(x)
 #define DCSB_DBG_LAP(k)
 #endif
+    uint32_t queued = 0;                           // output frames already handed to the decode kernel
     uint64_t bt = 0;                               // InitStreamPlayback zeroes the band types (:1640)
     int status = s.nframes ? 0 : -1, stopband = 0xFF;    // -1 = DCSB_E_EMPTY (the host refines DCSB_E_SHORT)
     uint32_t nplay = s.nframes, f = 0;
@@ -243,19 +247,18 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
                 while (R > 15) {
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
-                        if (R > 15) {
-                            DCSB_DBG(++dbg_steps;)
-                            const uint32_t x = win.peek_wide();
-                            const uint32_t m8 = dcsb_lds8(b8, x >> (32 - DCSB_T8_PEEK));
-                            const uint32_t m1 = dcsb_lds8(b1, x >> (32 - DCSB_T1_PEEK));
-                            const uint32_t m = (int)m8 > R ? m1 : m8;
-                            win.advance(m & 15u);
-                            R -= (int)(m & 0xF0u);
-                        }
+                        DCSB_DBG(++dbg_steps;)
+                        const uint32_t x = win.peek_wide();
+                        const uint32_t m8 = dcsb_lds8(b8, x >> (32 - DCSB_T8_PEEK));
+                        const uint32_t m1 = dcsb_lds8(b1, x >> (32 - DCSB_T1_PEEK));
+                        const int active = (15 - R) >> 31;                  // all ones while slots are left
+                        const int over = (R - (int)m8) >> 31;               // all ones: the multi-symbol step would overrun
+                        const uint32_t m = (m8 ^ ((m8 ^ m1) & (uint32_t)over)) & (uint32_t)active;
+                        win.advance(m & 15u);
+                        R -= (int)(m & 0xF0u);
                     }
                     win.refill();
                 }
-                DCSB_DBG_LAP(2)
                 if (R < 0 && sb > b) sb = b;        // 'two zeros' with one slot left (:2213-2218)
             } else if (code > 6) {
                 // fixed-width band (:2227-2234): count * code bits, closed form
@@ -267,6 +270,13 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
         pos = win.pos();
         if (pos > nbits) { status = -2; nplay = f; break; }                       // DCSB_E_TRUNCATED
         if (sb != 99) { status = -5; nplay = f + 1; stopband = sb; ++f; break; }    // DCSB_E_STOPPED
+        if ((f & 15) == 15) {
+            // let the decode warps have the frames so far (entry f + 1 = this frame's own band types)
+            out.bitpos[s.frame_base + f + 1] = pos;
+            out.bt[s.frame_base + f + 1] = make_uint2((uint32_t)bt, (uint32_t)(bt >> 32));
+            dcsb_publish(out.progress, si, f + 2);
+            if (((f + 1) & (DCSB_QITEM - 1)) == 0) { dcsb_queue_push(out, si, queued, f + 1, false); queued = f + 1; }
+        }
     }
     // end checkpoint: band types after the last decodable frame (decode lanes read bt[f + 1]).
     // After a truncated / undecodable frame f the checkpoint of f itself already is the end.
@@ -290,4 +300,6 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
     out.nplay[si] = nplay;
     out.endbits[si] = pos;
     out.stopband[si] = (uint8_t)stopband;
+    dcsb_publish(out.progress, si, DCSB_SCAN_DONE);
+    dcsb_queue_push(out, si, queued, s.out_frames, true);
 }

@@ -75,6 +75,10 @@ int  dcsb_create(int cuda_device, dcsb_ctx **out);
 void dcsb_destroy(dcsb_ctx *ctx);
 const char *dcsb_last_error(const dcsb_ctx *ctx);    /* DCSDecoder::GetErrorMessage, DCSDecoder.h:213-222 */
 const char *dcsb_version(void);
+/* on (default): the frame-boundary scan runs on an internal stream beside the decode kernel, whose
+ * warps wait for the checkpoints they need; off: one kernel after the other on the caller's stream
+ * (what a profiler sees anyway, and what per-kernel timings should be read from) */
+int dcsb_set_overlap(dcsb_ctx *ctx, int on);
 
 /* ---- one-shot batch decode with HOST buffers ------------------------------------- */
 /* Replaces: the per-stream loop in DCSExplorer ExtractTracksOrStreams (DCSExplorer.cpp:1628-1939).
@@ -107,8 +111,9 @@ int dcsb_batch_results(dcsb_batch *b, void *cuda_stream, dcsb_result *results);
 int dcsb_batch_read_pcm(dcsb_batch *b, size_t i, int16_t *pcm, size_t max_samples);
 /* device pointer of the internal PCM buffer (NULL until first decode into it) */
 void *dcsb_batch_device_pcm(dcsb_batch *b);
-/* time of the most recent dcsb_batch_decode per kernel, measured with CUDA events on the
- * launching stream (ms); which: 0 = scan, 1 = decode+transform */
+/* time of the most recent dcsb_batch_decode, measured with CUDA events on the launching streams
+ * (ms); which: 0 = scan span, 1 = decode+transform span (overlaps the scan unless
+ * dcsb_set_overlap(ctx, 0)), 2 = the whole step */
 float dcsb_batch_last_kernel_ms(dcsb_batch *b, int which);
 
 /* Frame checkpoints produced by the scan kernel, for stage-level parity tests against

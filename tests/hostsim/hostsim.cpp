@@ -31,7 +31,7 @@ extern "C" int hostsim_decode_streams(const dcsb_stream_desc *descs, size_t n, i
     std::vector<uint16_t> hdrbits(p.total_checkpoints + 1);
     std::vector<int32_t> status(n + 1);
     std::vector<uint8_t> stopband(n + 1);
-    DcsbScanOut so{ bitpos.data(), bt.data(), hdrbits.data(), status.data(), nplay.data(), endbits.data(), stopband.data(), nullptr };
+    DcsbScanOut so{ bitpos.data(), bt.data(), hdrbits.data(), status.data(), nplay.data(), endbits.data(), stopband.data(), nullptr, nullptr, nullptr, nullptr, nullptr };
     std::vector<uint8_t> ring(DCSB_RING_BYTES, 0xA5);                // one K1 thread's shared-memory ring
     for (size_t i = 0; i < n; ++i)                                   // K1 grid
         if (p.recs[i].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, tab.t8, tab.t1, ring.data(), so);
@@ -45,7 +45,8 @@ extern "C" int hostsim_decode_streams(const dcsb_stream_desc *descs, size_t n, i
     for (size_t t = 0; t < p.tiles.size(); ++t) {                    // K2 grid, one warp per tile
         if ((int)t < p.ntiles94)
             csum[p.tiles[t].stream] += dcsb_decode94_item(slab.data(), p.recs.data(), p.tiles[t], &tab, tab.lut, &tw,
-                                                          p.recs[p.tiles[t].stream].hdr, so, pcm_out, rows.data());
+                                                          p.recs[p.tiles[t].stream].hdr, so, nplay[p.tiles[t].stream],
+                                                          stopband[p.tiles[t].stream], pcm_out, rows.data());
         else
             csum[p.tiles[t].stream] += dcsb_decode_tile<true>(slab.data(), p.recs.data(), p.tiles[t], &tab, tab.lut, so, pcm_out, rows.data());
     }
@@ -138,7 +139,7 @@ extern "C" int hostsim_rom_render(const uint8_t *const *imgs, const size_t *size
     std::vector<uint16_t> hdrbits(p.total_checkpoints + 1);
     std::vector<int32_t> status(ns + 1);
     std::vector<uint8_t> stopband(ns + 1);
-    DcsbScanOut so{ bitpos.data(), bt.data(), hdrbits.data(), status.data(), nplay.data(), endbits.data(), stopband.data(), nullptr };
+    DcsbScanOut so{ bitpos.data(), bt.data(), hdrbits.data(), status.data(), nplay.data(), endbits.data(), stopband.data(), nullptr, nullptr, nullptr, nullptr, nullptr };
     std::vector<uint8_t> ring(DCSB_RING_BYTES, 0xA5);
     for (size_t i = 0; i < ns; ++i) {
         if (p.recs[i].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, tab.t8, tab.t1, ring.data(), so);

@@ -6,13 +6,21 @@ set -u
 TAG=${1:-run}; shift || true
 OUT=gpurun_out
 mkdir -p $OUT
-python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee $OUT/${TAG}_pytest.txt
-python bench.py --steps 10 --warmup 3 "$@" > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
-tail -c 2500 $OUT/${TAG}_bench.json; tail -3 $OUT/${TAG}_bench.err
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee $OUT/${TAG}_pytest.txt
+timeout 900 python bench.py --steps 10 --warmup 3 "$@" > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+tail -c 3500 $OUT/${TAG}_bench.json; tail -3 $OUT/${TAG}_bench.err
 # launch list (cold-cache, serialised: compare shares)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/${TAG}_launches.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 0 "$@" > $OUT/${TAG}_ncu_launch.log 2>&1
 # full capture of our kernels (skip the warm-up launches)
-ncu --set full --clock-control none --import-source on -k regex:dcsb_ -s 6 -c 3 -f -o $OUT/${TAG}_prof \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"dcsb_(scan|decode)" -s 6 -c 4 -f -o $OUT/${TAG}_prof \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 0 "$@" > $OUT/${TAG}_ncu_full.log 2>&1
+python - <<'PY'
+import torch, time
+n = 1 << 30
+h = torch.empty(n, dtype=torch.uint8).pin_memory(); d = torch.empty(n, dtype=torch.uint8, device="cuda")
+for name, a, b in (("H2D", d, h), ("D2H", h, d)):
+    a.copy_(b); torch.cuda.synchronize(); t = time.perf_counter(); a.copy_(b); torch.cuda.synchronize()
+    print("pinned %s %.1f GB/s" % (name, n / (time.perf_counter() - t) / 1e9))
+PY
 ls -la $OUT | tail -12

@@ -18,20 +18,23 @@ batch = ctx.batch(streams, os_version=dx.OS94, master_volume=255, mixing_level=0
 d_pcm = torch.empty(batch.total_samples, dtype=torch.int16, device="cuda")
 st = torch.cuda.current_stream()
 ref = None
-for lanes in sys.argv[2:] or ["0", "1", "2", "4", "8", "16", "32"]:
+for overlap in (0, 1):
+  ctx.set_overlap(overlap)
+  for lanes in sys.argv[2:] or ["2"]:
     if lanes == "0":
         os.environ.pop("DCSB_SCAN_LANES", None)
     else:
         os.environ["DCSB_SCAN_LANES"] = lanes
-    ks, kd = [], []
+    ks, kd, kt = [], [], []
     for i in range(6):
         batch.decode(d_pcm.data_ptr(), st.cuda_stream)
         torch.cuda.synchronize()
         if i >= 2:
-            ks.append(batch.kernel_ms(0)); kd.append(batch.kernel_ms(1))
+            ks.append(batch.kernel_ms(0)); kd.append(batch.kernel_ms(1)); kt.append(batch.kernel_ms(2))
     res = batch.results(st.cuda_stream)
     x = 0
     for r in res:
         x ^= r["checksum"]
     ref = x if ref is None else ref
-    print("lanes=%s scan %.3f ms decode %.3f ms  xor %016x %s" % (lanes, np.mean(ks), np.mean(kd), x, "OK" if x == ref else "MISMATCH"), flush=True)
+    print("overlap=%d lanes=%s scan %.3f ms decode %.3f ms step %.3f ms  xor %016x %s" % (
+        overlap, lanes, np.mean(ks), np.mean(kd), np.mean(kt), x, "OK" if x == ref else "MISMATCH"), flush=True)
