@@ -303,3 +303,29 @@ def partition_streams(frames, n_parts):
 def stream_frames(data):
     """frame count in a stream's preamble"""
     return ((data[0] << 8) | data[1]) if len(data) >= 2 else 0
+
+
+def write_wav(path, pcm):
+    """dcsb_write_wav: mono 16-bit 31,250 Hz"""
+    a = np.ascontiguousarray(pcm, dtype=np.int16)
+    if _capi.lib().dcsb_write_wav(str(path).encode(), a.ctypes.data, a.size) != OK:
+        raise DcsbError("dcsb_write_wav(%s) failed" % path)
+
+
+def write_dcs_file(path, os_version, stream):
+    b = np.frombuffer(bytes(stream), dtype=np.uint8)
+    if _capi.lib().dcsb_write_dcs_file(str(path).encode(), os_version, b.ctypes.data, b.size) != OK:
+        raise DcsbError("dcsb_write_dcs_file(%s) failed" % path)
+
+
+def read_dcs_file(path):
+    """dcsb_read_dcs_file -> (format version, stream bytes)"""
+    L = _capi.lib()
+    osv = C.c_uint16(0)
+    n = L.dcsb_read_dcs_file(str(path).encode(), C.byref(osv), None, 0)
+    if n < 0:
+        raise DcsbError("dcsb_read_dcs_file(%s): not a DCSa file (%d)" % (path, n))
+    out = np.zeros(max(1, n), dtype=np.uint8)
+    if L.dcsb_read_dcs_file(str(path).encode(), C.byref(osv), out.ctypes.data, n) != n:
+        raise DcsbError("dcsb_read_dcs_file(%s): short read" % path)
+    return osv.value, out[:n].tobytes()

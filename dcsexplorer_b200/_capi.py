@@ -52,6 +52,9 @@ class StreamInfo(C.Structure):
 
 
 SYMBOLS = {
+    "dcsb_write_wav": (C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t]),
+    "dcsb_write_dcs_file": (C.c_int, [C.c_char_p, C.c_uint16, C.c_void_p, C.c_size_t]),
+    "dcsb_read_dcs_file": (C.c_longlong, [C.c_char_p, C.POINTER(C.c_uint16), C.c_void_p, C.c_size_t]),
     "dcsb_partition_streams": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
     "dcsb_player_stream_info": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(StreamInfo)]),
     "dcsb_rom_create": (C.c_int, [C.POINTER(C.c_void_p)]),

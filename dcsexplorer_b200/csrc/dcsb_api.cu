@@ -200,7 +200,7 @@ extern "C" int dcsb_batch_decode(dcsb_batch *b, void *d_pcm, void *cuda_stream)
         CK(cudaEventRecord(b->ev[1], ctx->aux), "event");
         CK(dcsb_launch_gate(so, dcsb_scan_grid((int)b->n), st), "gate kernel launch");
         CK(cudaEventRecord(b->ev[3], st), "event");
-        CK(dcsb_launch_decode_queue(b->d_slab, b->d_recs, b->nqueue94, ctx->d_tables, so, pcm, b->d_checksums, st), "decode kernel launch");
+        CK(dcsb_launch_decode_queue(b->d_slab, b->d_recs, (int)b->n, b->nqueue94, ctx->d_tables, so, pcm, b->d_checksums, st), "decode kernel launch");
         CK(dcsb_launch_decode(b->d_slab, b->d_recs, b->d_tiles + b->ntiles94, 0, b->ntiles93, ctx->d_tables, so,
                               pcm, b->d_checksums, st), "decode kernel launch");
         CK(cudaStreamWaitEvent(st, b->ev[1], 0), "stream wait");
@@ -337,6 +337,8 @@ static int lane_submit(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs
     ENS(l.d_csum, nn * 8, false, "cudaMalloc(checksums)");
     ENS(l.d_progress, (nn + 4) * 4, false, "cudaMalloc(progress)");
     ENS(l.d_queue, std::max<size_t>(1, (size_t)p.nqueue94) * 8, false, "cudaMalloc(queue)");
+    // (PCM goes to a device buffer and is copied by the DMA engine afterwards: letting the decode
+    // warps store straight into the caller's pinned buffer over PCIe measured 86 ms against 70 ms)
     ENS(l.d_pcm, std::max<uint64_t>(2, p.total_out_frames * 480), false, "cudaMalloc(pcm)");
     ENS(l.h_res, nn * 20, true, "cudaMallocHost(results)");
     if (n == 0) return DCSB_OK;
@@ -370,7 +372,7 @@ static int lane_submit(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs
     } else
         CK(dcsb_launch_scan((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p, (int)n, scan_lanes, ctx->d_tables, so, l.st), "scan kernel launch");
     if (ctx->overlap)
-        CK(dcsb_launch_decode_queue((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p, p.nqueue94, ctx->d_tables, so,
+        CK(dcsb_launch_decode_queue((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p, (int)n, p.nqueue94, ctx->d_tables, so,
                                     (int16_t *)l.d_pcm.p, (unsigned long long *)l.d_csum.p, l.st), "decode kernel launch");
     CK(dcsb_launch_decode((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p,
                           (const DcsbTile *)l.d_tiles.p + (ctx->overlap ? p.ntiles94 : 0), ctx->overlap ? 0 : p.ntiles94, p.ntiles93,

@@ -2,6 +2,7 @@
 // staging arithmetic, stream validation, slab layout and tiling.  Linked into
 // libdcsb200.so; also compiled on its own by the CPU-side kernel simulator (tests/hostsim).
 #include <stdint.h>
+#include <stdio.h>
 #include <string.h>
 #include <algorithm>
 #include <thread>
@@ -304,4 +305,76 @@ extern "C" int dcsb_partition_streams(const uint32_t *frames, size_t n, int n_pa
     }
     if (frames_per_part) for (int p = 0; p < n_parts; ++p) frames_per_part[p] = load[p];
     return DCSB_OK;
+}
+
+// ======================================================================================
+// output containers
+static void put_le32(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
+static void put_le16(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
+
+extern "C" int dcsb_write_wav(const char *path, const int16_t *pcm, size_t n_samples)
+{
+    if (!path || (!pcm && n_samples) || n_samples > 0x7FFFFFF0u / 2) return DCSB_E_ARG;
+    FILE *f = fopen(path, "wb");
+    if (!f) return DCSB_E_ARG;
+    uint8_t h[44];
+    memset(h, 0, sizeof(h));
+    const uint32_t bytes = (uint32_t)(n_samples * 2);
+    memcpy(h, "RIFF", 4);
+    put_le32(h + 4, bytes + 44 - 8);
+    memcpy(h + 8, "WAVEfmt ", 8);
+    put_le32(h + 16, 16);            // fmt chunk length
+    put_le16(h + 20, 1);             // PCM
+    put_le16(h + 22, 1);             // mono
+    put_le32(h + 24, 31250);
+    put_le32(h + 28, 31250 * 2);     // bytes per second
+    put_le16(h + 32, 2);             // block align
+    put_le16(h + 34, 16);            // bits per sample
+    memcpy(h + 36, "data", 4);
+    put_le32(h + 40, bytes);
+    bool ok = fwrite(h, 1, 44, f) == 44;
+    // samples are little-endian on disk; the hosts this library runs on are little-endian
+    if (ok && n_samples) ok = fwrite(pcm, 2, n_samples, f) == n_samples;
+    if (fclose(f) != 0) ok = false;
+    return ok ? DCSB_OK : DCSB_E_ARG;
+}
+
+extern "C" int dcsb_write_dcs_file(const char *path, uint16_t os_version, const uint8_t *stream, size_t nbytes)
+{
+    if (!path || !stream || nbytes == 0 || nbytes > 0xFFFFFFFFull) return DCSB_E_ARG;
+    uint8_t h[36];
+    memset(h, 0, sizeof(h));
+    memcpy(h, "DCSa", 4);
+    const bool os93 = os_version == DCSB_OS93A || os_version == DCSB_OS93B;
+    h[4] = os93 ? 0x93 : 0x94;
+    h[5] = os_version == DCSB_OS93A ? 0x01 : os_version == DCSB_OS93B ? 0x02 : 0x00;
+    h[7] = 0x01;                     // channels
+    h[8] = 0x7A; h[9] = 0x12;        // 31,250 Hz
+    h[32] = (uint8_t)(nbytes >> 24); h[33] = (uint8_t)(nbytes >> 16); h[34] = (uint8_t)(nbytes >> 8); h[35] = (uint8_t)nbytes;
+    FILE *f = fopen(path, "wb");
+    if (!f) return DCSB_E_ARG;
+    bool ok = fwrite(h, 1, 36, f) == 36 && fwrite(stream, 1, nbytes, f) == nbytes;
+    if (fclose(f) != 0) ok = false;
+    return ok ? DCSB_OK : DCSB_E_ARG;
+}
+
+extern "C" long long dcsb_read_dcs_file(const char *path, uint16_t *os_version, uint8_t *out, size_t max)
+{
+    if (!path) return DCSB_E_ARG;
+    FILE *f = fopen(path, "rb");
+    if (!f) return DCSB_E_ARG;
+    uint8_t h[36];
+    long long rc = DCSB_E_ARG;
+    if (fread(h, 1, 36, f) == 36 && memcmp(h, "DCSa", 4) == 0 && (h[4] == 0x93 || h[4] == 0x94) && h[6] == 0 && h[7] == 1 &&
+        h[8] == 0x7A && h[9] == 0x12) {
+        const uint32_t n = ((uint32_t)h[32] << 24) | (h[33] << 16) | (h[34] << 8) | h[35];
+        if (os_version) *os_version = (uint16_t)((h[4] << 8) | h[5]);
+        rc = n;
+        if (out && max) {
+            const size_t want = n < max ? n : max;
+            if (fread(out, 1, want, f) != want) rc = DCSB_E_TRUNCATED;
+        }
+    }
+    fclose(f);
+    return rc;
 }

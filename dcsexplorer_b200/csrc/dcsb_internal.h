@@ -71,7 +71,7 @@ struct DcsbTables {
 };
 
 #define DCSB_SCAN_DONE 0x80000000u
-#define DCSB_QITEM 64u                      // frames per queued work item
+#define DCSB_QITEM 63u                      // frames per queued work item: with the warm-up frame, two full 32-lane tiles
 #define DCSB_Q_VALID (1ull << 63)           // queue entry: VALID | FINAL? | stream << 24 | first frame
 #define DCSB_Q_FINAL (1ull << 62)           // the stream's scan is finished: nplay / stopband are final
 struct DcsbScanOut {
@@ -132,7 +132,7 @@ int dcsb_scan_lanes(int nstreams);       // streams per warp the scan launch use
 cudaError_t dcsb_launch_gate(DcsbScanOut scan, int ctas, cudaStream_t st);
 int dcsb_scan_grid(int nstreams);        // CTAs dcsb_launch_scan uses
 // persistent decode over the scan's ready queue (1994-layout streams, overlapped mode)
-cudaError_t dcsb_launch_decode_queue(const uint8_t *slab, const DcsbStreamRec *streams, int nitems,
+cudaError_t dcsb_launch_decode_queue(const uint8_t *slab, const DcsbStreamRec *streams, int nstreams, int nitems,
                                      const DcsbTables *tables, DcsbScanOut scan, int16_t *pcm,
                                      unsigned long long *checksums, cudaStream_t st);
 cudaError_t dcsb_launch_decode(const uint8_t *slab, const DcsbStreamRec *streams, const DcsbTile *tiles,

@@ -209,7 +209,7 @@ dcsb_decode94_queue_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec
     }
 }
 
-cudaError_t dcsb_launch_decode_queue(const uint8_t *slab, const DcsbStreamRec *streams, int nitems,
+cudaError_t dcsb_launch_decode_queue(const uint8_t *slab, const DcsbStreamRec *streams, int nstreams, int nitems,
                                      const DcsbTables *tables, DcsbScanOut scan, int16_t *pcm,
                                      unsigned long long *checksums, cudaStream_t st)
 {
@@ -222,7 +222,13 @@ cudaError_t dcsb_launch_decode_queue(const uint8_t *slab, const DcsbStreamRec *s
     e = cudaFuncSetAttribute(dcsb_decode94_queue_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     int grid = (nitems + DCSB_WARPS94 - 1) / DCSB_WARPS94;
-    if (grid > 148 * 3) grid = 148 * 3;             // persistent: what fits on the chip at once
+    // persistent CTAs per SM.  When every stream's scan is resident at once (one wave), the step is
+    // as long as the slowest scan chain and the decode only has to keep up with it: one CTA per SM
+    // does (measured 19.7 ms against 21.0 ms with three, whose warps take issue slots from the
+    // chains).  With more streams than that the decode is the larger part: fill the SMs.
+    int per_sm = nstreams <= 148 * DCSB_SCAN_SPC ? 1 : 3;
+    if (const char *e = getenv("DCSB_DECODE_CTAS")) { const int v = atoi(e); if (v >= 1 && v <= 3) per_sm = v; }   // tuning override
+    if (grid > 148 * per_sm) grid = 148 * per_sm;
     dcsb_decode94_queue_kernel<<<grid, DCSB_WARPS94 * 32, smem, st>>>(slab, streams, nitems, tables, scan, pcm, checksums);
     return cudaGetLastError();
 }

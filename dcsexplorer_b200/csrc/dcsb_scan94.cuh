@@ -190,7 +190,7 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
 #define DCSB_DBG(x)
 #define DCSB_DBG_LAP(k)
 #endif
-    uint32_t queued = 0;                           // output frames already handed to the decode kernel
+    uint32_t queued = 0, qnext = DCSB_QITEM;       // output frames already handed to the decode kernel / next hand-over
     uint64_t bt = 0;                               // InitStreamPlayback zeroes the band types (:1640)
     int status = s.nframes ? 0 : -1, stopband = 0xFF;    // -1 = DCSB_E_EMPTY (the host refines DCSB_E_SHORT)
     uint32_t nplay = s.nframes, f = 0;
@@ -275,7 +275,13 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
             out.bitpos[s.frame_base + f + 1] = pos;
             out.bt[s.frame_base + f + 1] = make_uint2((uint32_t)bt, (uint32_t)(bt >> 32));
             dcsb_publish(out.progress, si, f + 2);
-            if (((f + 1) & (DCSB_QITEM - 1)) == 0) { dcsb_queue_push(out, si, queued, f + 1, false); queued = f + 1; }
+        }
+        if (f + 1 == qnext) {
+            out.bitpos[s.frame_base + f + 1] = pos;
+            out.bt[s.frame_base + f + 1] = make_uint2((uint32_t)bt, (uint32_t)(bt >> 32));
+            dcsb_queue_push(out, si, queued, f + 1, false);
+            queued = f + 1;
+            qnext += DCSB_QITEM;
         }
     }
     // end checkpoint: band types after the last decodable frame (decode lanes read bt[f + 1]).

@@ -219,6 +219,18 @@ typedef struct {
 int dcsb_render_timelines(dcsb_ctx *ctx, dcsb_rom *rom, const dcsb_timeline *timelines, size_t n,
                           int16_t *pcm_out, const uint64_t *pcm_offsets, dcsb_timeline_result *results);
 
+/* ---- output containers (host side): the step after the decode path ------------------ */
+/* 44-byte RIFF/WAVE header + mono 16-bit PCM at 31,250 Hz, as ExtractToWAV writes it
+ * (DCSExplorer.cpp:1686-1712).  Returns DCSB_OK or DCSB_E_ARG (cannot create / write). */
+int dcsb_write_wav(const char *path, const int16_t *pcm, size_t n_samples);
+/* Raw stream container: 36-byte "DCSa" header (format version $9301 / $9302 / $9400, 1 channel, 31,250 Hz,
+ * 22 reserved bytes, U32BE data size) + the stream bytes (DCSExplorer.cpp:1831-1871; read back by
+ * DCSEncoder::IsDCSFile / EncodeDCSFile, DCSEncoder.cpp:369-399). */
+int dcsb_write_dcs_file(const char *path, uint16_t os_version, const uint8_t *stream, size_t nbytes);
+/* Reads a "DCSa" file: *os_version = format version (DCSB_OS94 for $9400), stream bytes copied to out
+ * (up to max); returns the stream size in bytes, or a negative DCSB_E_* (not a DCSa file / unreadable). */
+long long dcsb_read_dcs_file(const char *path, uint16_t *os_version, uint8_t *out, size_t max);
+
 /* ---- multi-GPU work partitioning (host side) ---------------------------------------- */
 /* Streams are independent (one DCSDecoderNative instance each in the reference), so a batch is
  * sharded by stream with no data-path collective: longest-processing-time greedy on the frame
