@@ -47,7 +47,7 @@ extern "C" void dcsb_destroy(dcsb_ctx *ctx)
         l.d_progress.release(false);
         l.h_slab.release(true); l.h_res.release(true);
         for (DcsbBuf *b : { &l.d_slab, &l.d_recs, &l.d_tiles, &l.d_bitpos, &l.d_bt, &l.d_hdrbits, &l.d_status, &l.d_nplay,
-                            &l.d_endbits, &l.d_stopband, &l.d_csum, &l.d_pcm, &l.d_queue }) b->release(false);
+                            &l.d_endbits, &l.d_stopband, &l.d_csum, &l.d_pcm, &l.d_queue, &l.d_order }) b->release(false);
     }
     if (ctx->aux) { cudaStreamSynchronize(ctx->aux); cudaStreamDestroy(ctx->aux); }
     cudaFree(ctx->d_tables);
@@ -67,7 +67,7 @@ extern "C" void dcsb_batch_destroy(dcsb_batch *b)
 {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
-    cudaFree(b->d_slab); cudaFree(b->d_recs); cudaFree(b->d_tiles);
+    cudaFree(b->d_slab); cudaFree(b->d_recs); cudaFree(b->d_tiles); cudaFree(b->d_order);
     cudaFree(b->scan.bitpos); cudaFree(b->scan.bt); cudaFree(b->scan.hdrbits); cudaFree(b->scan.status); cudaFree(b->scan.nplay);
     cudaFree(b->scan.endbits); cudaFree(b->scan.stopband); cudaFree(b->scan.dbg);
     cudaFree(b->d_pcm); cudaFree(b->d_checksums); cudaFree(b->d_progress); cudaFree(b->d_queue);
@@ -126,6 +126,8 @@ int dcsb_batch_create_impl(dcsb_ctx *ctx, const dcsb_stream_desc *descs, size_t 
     CKB(cudaMemcpy(b->d_recs, b->recs.data(), n * sizeof(DcsbStreamRec), cudaMemcpyHostToDevice), "H2D recs");
     CKB(cudaMalloc(&b->d_tiles, std::max<size_t>(1, b->tiles.size()) * sizeof(DcsbTile)), "cudaMalloc(tiles)");
     CKB(cudaMemcpy(b->d_tiles, b->tiles.data(), b->tiles.size() * sizeof(DcsbTile), cudaMemcpyHostToDevice), "H2D tiles");
+    CKB(cudaMalloc(&b->d_order, std::max<size_t>(1, n) * sizeof(uint32_t)), "cudaMalloc(order)");
+    CKB(cudaMemcpy(b->d_order, prep.scan_order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice), "H2D order");
     CKB(cudaMalloc(&b->scan.bitpos, std::max<uint64_t>(1, frames) * sizeof(uint32_t)), "cudaMalloc(bitpos)");
     CKB(cudaMalloc(&b->scan.bt, std::max<uint64_t>(1, frames) * sizeof(uint2)), "cudaMalloc(bt)");
     CKB(cudaMalloc(&b->scan.hdrbits, std::max<uint64_t>(1, frames) * sizeof(uint16_t)), "cudaMalloc(hdrbits)");
@@ -177,7 +179,7 @@ extern "C" int dcsb_batch_decode(dcsb_batch *b, void *d_pcm, void *cuda_stream)
         so.progress = so.started = so.qctl = nullptr;
         so.queue = nullptr;
         CK(cudaEventRecord(b->ev[0], st), "event");
-        CK(dcsb_launch_scan(b->d_slab, b->d_recs, (int)b->n, 0, ctx->d_tables, so, st), "scan kernel launch");
+        CK(dcsb_launch_scan(b->d_slab, b->d_recs, b->d_order, (int)b->n, 0, ctx->d_tables, so, st), "scan kernel launch");
         CK(cudaEventRecord(b->ev[1], st), "event");
         CK(cudaEventRecord(b->ev[3], st), "event");
         CK(dcsb_launch_decode(b->d_slab, b->d_recs, b->d_tiles, b->ntiles94, b->ntiles93, ctx->d_tables, so,
@@ -196,7 +198,7 @@ extern "C" int dcsb_batch_decode(dcsb_batch *b, void *d_pcm, void *cuda_stream)
         if (b->nqueue94) CK(cudaMemsetAsync(b->d_queue, 0, (size_t)b->nqueue94 * sizeof(unsigned long long), st), "memset queue");
         CK(cudaEventRecord(b->ev[0], st), "event");
         CK(cudaStreamWaitEvent(ctx->aux, b->ev[0], 0), "stream wait");
-        CK(dcsb_launch_scan(b->d_slab, b->d_recs, (int)b->n, 0, ctx->d_tables, so, ctx->aux), "scan kernel launch");
+        CK(dcsb_launch_scan(b->d_slab, b->d_recs, b->d_order, (int)b->n, 0, ctx->d_tables, so, ctx->aux), "scan kernel launch");
         CK(cudaEventRecord(b->ev[1], ctx->aux), "event");
         CK(dcsb_launch_gate(so, dcsb_scan_grid((int)b->n), st), "gate kernel launch");
         CK(cudaEventRecord(b->ev[3], st), "event");
@@ -327,6 +329,7 @@ static int lane_submit(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs
     ENS(l.d_slab, p.slab_bytes, false, "cudaMalloc(slab)");
     ENS(l.d_recs, nn * sizeof(DcsbStreamRec), false, "cudaMalloc(recs)");
     ENS(l.d_tiles, std::max<size_t>(1, p.tiles.size()) * sizeof(DcsbTile), false, "cudaMalloc(tiles)");
+    ENS(l.d_order, nn * sizeof(uint32_t), false, "cudaMalloc(order)");
     ENS(l.d_bitpos, ck * 4, false, "cudaMalloc(bitpos)");
     ENS(l.d_bt, ck * 8, false, "cudaMalloc(bt)");
     ENS(l.d_hdrbits, ck * 2, false, "cudaMalloc(hdrbits)");
@@ -354,6 +357,7 @@ static int lane_submit(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs
 #undef ENS
     CK(cudaMemcpyAsync(l.d_recs.p, p.recs.data(), n * sizeof(DcsbStreamRec), cudaMemcpyHostToDevice, l.st), "H2D recs");
     CK(cudaMemcpyAsync(l.d_tiles.p, p.tiles.data(), p.tiles.size() * sizeof(DcsbTile), cudaMemcpyHostToDevice, l.st), "H2D tiles");
+    CK(cudaMemcpyAsync(l.d_order.p, p.scan_order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, l.st), "H2D order");
     CK(cudaMemsetAsync(l.d_csum.p, 0, n * 8, l.st), "memset checksums");
     DcsbScanOut so{ (uint32_t *)l.d_bitpos.p, (uint2 *)l.d_bt.p, (uint16_t *)l.d_hdrbits.p, (int32_t *)l.d_status.p,
                     (uint32_t *)l.d_nplay.p, (uint32_t *)l.d_endbits.p, (uint8_t *)l.d_stopband.p, nullptr, nullptr, nullptr, nullptr, nullptr };
@@ -366,11 +370,11 @@ static int lane_submit(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs
         if (p.nqueue94) CK(cudaMemsetAsync(l.d_queue.p, 0, (size_t)p.nqueue94 * 8, l.st), "memset queue");
         CK(cudaEventRecord(l.ev_go, l.st), "event");
         CK(cudaStreamWaitEvent(l.aux, l.ev_go, 0), "stream wait");
-        CK(dcsb_launch_scan((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p, (int)n, scan_lanes, ctx->d_tables, so, l.aux), "scan kernel launch");
+        CK(dcsb_launch_scan((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p, (const uint32_t *)l.d_order.p, (int)n, scan_lanes, ctx->d_tables, so, l.aux), "scan kernel launch");
         CK(cudaEventRecord(l.ev_scan, l.aux), "event");
         CK(dcsb_launch_gate(so, dcsb_scan_grid((int)n), l.st), "gate kernel launch");
     } else
-        CK(dcsb_launch_scan((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p, (int)n, scan_lanes, ctx->d_tables, so, l.st), "scan kernel launch");
+        CK(dcsb_launch_scan((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p, (const uint32_t *)l.d_order.p, (int)n, scan_lanes, ctx->d_tables, so, l.st), "scan kernel launch");
     if (ctx->overlap)
         CK(dcsb_launch_decode_queue((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p, (int)n, p.nqueue94, ctx->d_tables, so,
                                     (int16_t *)l.d_pcm.p, (unsigned long long *)l.d_csum.p, l.st), "decode kernel launch");

@@ -32,7 +32,7 @@ struct DcsbBuf {
 struct DcsbLane {
     cudaStream_t st = nullptr, aux = nullptr;                // aux: the scan runs beside the decode
     cudaEvent_t ev_go = nullptr, ev_scan = nullptr;
-    DcsbBuf d_progress, d_queue;
+    DcsbBuf d_progress, d_queue, d_order;
     DcsbBuf h_slab, h_res;                                   // pinned
     DcsbBuf d_slab, d_recs, d_tiles, d_bitpos, d_bt, d_hdrbits, d_status, d_nplay, d_endbits, d_stopband, d_csum, d_pcm;
     DcsbPrepared prep;
@@ -65,6 +65,7 @@ struct dcsb_batch {
     uint8_t *d_slab = nullptr;
     DcsbStreamRec *d_recs = nullptr;
     DcsbTile *d_tiles = nullptr;
+    uint32_t *d_order = nullptr;             // scan order (dcsb_prepare)
     DcsbScanOut scan{};
     int16_t *d_pcm = nullptr;                // internal PCM buffer (lazy)
     unsigned long long *d_checksums = nullptr;

@@ -257,6 +257,16 @@ int dcsb_prepare(const dcsb_stream_desc *descs, size_t n, DcsbPrepared *p, const
             live.resize(keep);
         }
     }
+    // the scan walks 2 streams per warp in lockstep per band: put streams side by side that take the
+    // same branches and about as many table steps (same layout, same stream type, similar bits per frame)
+    p->scan_order.resize(n);
+    for (size_t i = 0; i < n; ++i) p->scan_order[i] = (uint32_t)i;
+    std::stable_sort(p->scan_order.begin(), p->scan_order.end(), [&](uint32_t a, uint32_t b) {
+        const DcsbStreamRec &x = p->recs[a], &y = p->recs[b];
+        const uint64_t kx = ((uint64_t)x.fmt << 40) | ((uint64_t)(x.hdr[0] >> 7) << 32) | (x.nframes ? (uint64_t)x.nbytes * 8 / x.nframes : 0);
+        const uint64_t ky = ((uint64_t)y.fmt << 40) | ((uint64_t)(y.hdr[0] >> 7) << 32) | (y.nframes ? (uint64_t)y.nbytes * 8 / y.nframes : 0);
+        return kx < ky;
+    });
     if (ckpt > 0xFFFFFFF0ull || t94.size() + t93.size() > 0x7FFFFFF0ull || nq94 > 0x7FFFFFF0ull || n > 0x3FFFFFF0ull) return DCSB_E_ARG;
     p->nqueue94 = (int)nq94;
     p->total_frames_in = frames;

@@ -106,6 +106,7 @@ struct DcsbPrepared {
     std::vector<DcsbStreamRec> recs;
     std::vector<int32_t> host_status;     // host-side rejections (0 = let the scan decide)
     std::vector<DcsbTile> tiles;          // 1994-family items first, then 1993-family tiles
+    std::vector<uint32_t> scan_order;     // streams in the order the scan assigns them to lanes: alike streams side by side
     int ntiles94 = 0, ntiles93 = 0;
     int nqueue94 = 0;                     // work items the scan queues for the 1994-layout streams (overlapped mode)
     uint64_t total_frames_in = 0;         // stream frames
@@ -124,7 +125,8 @@ void dcsb_pack_slab(const dcsb_stream_desc *descs, size_t n, const DcsbPrepared 
 // lanes_hint: streams per warp (0 = choose from nstreams).  A caller that launches several scans
 // side by side passes dcsb_scan_lanes(total streams) so that all of them fit on the chip at once
 // (a scan CTA's tables fill an SM's shared memory).
-cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, int nstreams, int lanes_hint,
+// order: device array of nstreams stream indices (NULL = identity): which stream each scan lane takes
+cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, const uint32_t *order, int nstreams, int lanes_hint,
                              const DcsbTables *tables, DcsbScanOut out, cudaStream_t st);
 int dcsb_scan_lanes(int nstreams);       // streams per warp the scan launch uses (1..32)
 // tiles[0..ntiles94) use the 1994 transform, tiles[ntiles94..ntiles94+ntiles93) the 1993 one

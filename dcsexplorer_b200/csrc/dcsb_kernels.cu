@@ -42,8 +42,8 @@ struct DcsbSmemScan {
 };
 
 __global__ void __launch_bounds__(DCSB_SCAN_SPC * 32, 1)
-dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restrict__ streams, int nstreams, int lanes,
-                 int spc, const DcsbTables *__restrict__ tab, DcsbScanOut out)
+dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restrict__ streams, const uint32_t *__restrict__ order,
+                 int nstreams, int lanes, int spc, const DcsbTables *__restrict__ tab, DcsbScanOut out)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     DcsbSmemScan &sm = *reinterpret_cast<DcsbSmemScan *>(smem);
@@ -62,7 +62,8 @@ dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restri
     if (lane >= lanes || slot >= spc) return;
     const DcsbSmemU8 t8 = DCSB_SMEM_U8(sm.t8), t1 = DCSB_SMEM_U8(sm.t1);
     const DcsbRingPtr ring = DCSB_SMEM_U8(sm.ring[slot]);
-    for (int si = blockIdx.x * spc + slot; si < nstreams; si += gridDim.x * spc) {
+    for (int k = blockIdx.x * spc + slot; k < nstreams; k += gridDim.x * spc) {
+        const int si = order ? (int)order[k] : k;
         if (streams[si].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab, streams, si, tab, sm.lut, t8, t1, ring, out);
         else dcsb_scan_stream(slab, streams, si, tab, sm.lut, out);
     }
@@ -370,7 +371,7 @@ cudaError_t dcsb_launch_gate(DcsbScanOut scan, int ctas, cudaStream_t st)
     return cudaGetLastError();
 }
 
-cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, int nstreams, int lanes_hint,
+cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, const uint32_t *order, int nstreams, int lanes_hint,
                              const DcsbTables *tables, DcsbScanOut out, cudaStream_t st)
 {
     if (nstreams <= 0) return cudaSuccess;
@@ -385,7 +386,7 @@ cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, 
     // this one (the split only changes on an idle SM)
     e = cudaFuncSetAttribute(dcsb_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    dcsb_scan_kernel<<<grid, warps * 32, smem, st>>>(slab, streams, nstreams, lanes, spc, tables, out);
+    dcsb_scan_kernel<<<grid, warps * 32, smem, st>>>(slab, streams, order, nstreams, lanes, spc, tables, out);
     return cudaGetLastError();
 }
 

@@ -177,3 +177,33 @@ def test_gpu_decode_streams_custom_offsets(ctx):
         want, _ = _expect(d, os_, vol, lvl, tail)
         assert np.array_equal(out[int(offs[i]):int(offs[i]) + want.size], want), i
     assert out[0] == 0x5A5A and out[int(offs[0]) + sizes[0]] == 0x5A5A
+
+
+def test_gpu_config5_shape_many_short_streams(ctx):
+    """BASELINE config 5 in miniature: tens of thousands of ~1 s streams (a pool replicated so that
+    every replica has its own bytes in HBM).  More streams than one scan wave holds, so the scan
+    CTAs walk stream groups grid-stride while the persistent decode kernel drains the ready queue.
+    Size-independent checks: replicas agree, the checksum of checksums matches the oracle's."""
+    rng = np.random.default_rng(2026)
+    pool = [dcsfuzz.fuzz94(rng, int(rng.integers(100, 140)), type1=i % 3 != 0, max_code=15 if i % 3 == 0 else 9) for i in range(48)]
+    pool += [dcsfuzz.fuzz94(rng, 60, type1=1, max_code=6, error_frame=31, escape_p=0.2), bytes([0, 0] + [0x10] * 16)]
+    n = 24000
+    streams = [(pool[i % len(pool)], 0x9400, 255, 100, 2) for i in range(n)]
+    want = []
+    for d in pool:
+        pcm, rc = _expect(d, 0x9400, 255, 100, 2)
+        s = pcm.astype(np.uint16).astype(np.uint64)
+        want.append(int((s * (2 * np.arange(s.size, dtype=np.uint64) + 1)).sum(dtype=np.uint64)))
+    for overlap in (True, False):
+        ctx.set_overlap(overlap)
+        b = ctx.batch(streams)
+        b.decode()
+        res = b.results()
+        for i in range(n):
+            assert res[i]["checksum"] == want[i % len(pool)], (overlap, i)
+        assert res[len(pool) - 2]["status"] == -5 and res[len(pool) - 1]["status"] == -1
+        k = 17 * len(pool) + 5
+        pcm, _ = _expect(pool[5], 0x9400, 255, 100, 2)
+        assert np.array_equal(b.read_pcm(k, pcm.size), pcm)
+        b.close()
+    ctx.set_overlap(True)
