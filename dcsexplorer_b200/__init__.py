@@ -96,6 +96,33 @@ class Context:
         self._check(rc, "dcsb_decode_streams")
         return pcm_out[:total], offs, _results_to_list(res, n)
 
+    def set_pipeline(self, max_chunks=0, slice_frames=0):
+        """dcsb_set_pipeline: chunks / frames per time slice of decode_streams (0 = choose)."""
+        self._check(self._L.dcsb_set_pipeline(self._h, max_chunks, slice_frames), "dcsb_set_pipeline")
+
+    def decode_streams_pinned(self, streams, **kw):
+        """decode_streams with the streams packed into one pinned host blob and a pinned PCM buffer
+        (what a throughput-minded caller does): uploads happen in place, PCM is copied straight
+        into the output, uniform chunks are time-sliced.  Returns (pcm, offsets, results)."""
+        import torch
+        descs, keep = make_descs(streams, **kw)
+        n = len(streams)
+        blob = torch.empty(max(1, sum(int(k.size) for k in keep)), dtype=torch.uint8).pin_memory()
+        bnp = blob.numpy()
+        offs, total, o = [], 0, 0
+        for i, s in enumerate(keep):
+            bnp[o:o + s.size] = s
+            descs[i].data = blob.data_ptr() + o
+            o += int(s.size)
+            nf = ((int(s[0]) << 8) | int(s[1])) if s.size >= 2 else 0
+            offs.append(total)
+            total += (nf + descs[i].tail_frames) * 240
+        h_pcm = torch.zeros(max(total, 1), dtype=torch.int16).pin_memory()
+        res = (Result * max(1, n))()
+        rc = self._L.dcsb_decode_streams(self._h, descs, n, h_pcm.data_ptr(), None, res)
+        self._check(rc, "dcsb_decode_streams")
+        return h_pcm.numpy()[:total].copy(), offs, _results_to_list(res, n)
+
     def batch(self, streams, **kw):
         return Batch(self, streams, **kw)
 

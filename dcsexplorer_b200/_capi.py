@@ -84,6 +84,7 @@ SYMBOLS = {
     "dcsb_last_error": (C.c_char_p, [C.c_void_p]),
     "dcsb_version": (C.c_char_p, []),
     "dcsb_set_overlap": (C.c_int, [C.c_void_p, C.c_int]),
+    "dcsb_set_pipeline": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "dcsb_decode_streams": (C.c_int, [C.c_void_p, C.POINTER(StreamDesc), C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(Result)]),
     "dcsb_batch_create": (C.c_int, [C.c_void_p, C.POINTER(StreamDesc), C.c_size_t, C.POINTER(C.c_void_p)]),
     "dcsb_batch_destroy": (None, [C.c_void_p]),

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <thread>
@@ -44,12 +45,15 @@ extern "C" void dcsb_destroy(dcsb_ctx *ctx)
         if (l.aux) { cudaStreamSynchronize(l.aux); cudaStreamDestroy(l.aux); }
         if (l.ev_go) cudaEventDestroy(l.ev_go);
         if (l.ev_scan) cudaEventDestroy(l.ev_scan);
+        for (cudaEvent_t e : l.ev_slices) cudaEventDestroy(e);
         l.d_progress.release(false);
-        l.h_slab.release(true); l.h_res.release(true);
+        l.h_slab.release(true); l.h_res.release(true); l.h_meta.release(true);
         for (DcsbBuf *b : { &l.d_slab, &l.d_recs, &l.d_tiles, &l.d_bitpos, &l.d_bt, &l.d_hdrbits, &l.d_status, &l.d_nplay,
                             &l.d_endbits, &l.d_stopband, &l.d_csum, &l.d_pcm, &l.d_queue, &l.d_order }) b->release(false);
     }
     if (ctx->aux) { cudaStreamSynchronize(ctx->aux); cudaStreamDestroy(ctx->aux); }
+    if (ctx->up) { cudaStreamSynchronize(ctx->up); cudaStreamDestroy(ctx->up); }
+    if (ctx->down) { cudaStreamSynchronize(ctx->down); cudaStreamDestroy(ctx->down); }
     cudaFree(ctx->d_tables);
     delete ctx;
 }
@@ -58,6 +62,14 @@ extern "C" int dcsb_set_overlap(dcsb_ctx *ctx, int on)
 {
     if (!ctx) return DCSB_E_ARG;
     ctx->overlap = on != 0;
+    return DCSB_OK;
+}
+
+extern "C" int dcsb_set_pipeline(dcsb_ctx *ctx, int max_chunks, int slice_frames)
+{
+    if (!ctx || max_chunks < 0 || max_chunks > DCSB_MAX_LANES) return DCSB_E_ARG;
+    ctx->max_chunks = max_chunks;
+    ctx->slice_frames = slice_frames;
     return DCSB_OK;
 }
 
@@ -287,12 +299,20 @@ extern "C" int dcsb_batch_read_scan(dcsb_batch *b, size_t i, uint32_t *bitpos, u
 }
 
 // ---- one-shot decode with host buffers: a pipeline of stream chunks -------------------
-// Each chunk runs on its own lane (CUDA stream): [pack ->] H2D -> scan -> decode -> D2H.
-// Chunks overlap freely: while chunk c's PCM drains over PCIe, chunk c+1 decodes and c+2
-// uploads.  Inputs that already sit together in pinned host memory are uploaded straight
-// from where they are (the kernels accept any byte alignment); everything else is packed
-// into the lane's pinned staging slab by a few host threads.  PCM goes straight into the
-// caller's buffer when that is pinned and tightly packed.
+// The batch is cut into chunks of streams (one lane each) and, where a chunk's streams all render
+// the same number of frames into a packed pinned buffer, every chunk also into time slices:
+//
+//   upload stream   H2D chunk 0 | H2D chunk 1 | ...                       (in place from pinned memory,
+//                                                                          or from the lane's packed staging slab)
+//   lane c stream   scan(c, slice 0) decode(c, 0) scan(c, 1) decode(c, 1) ...   (resumed scans)
+//   copy stream     PCM(0, 0) PCM(1, 0) ... PCM(0, 1) PCM(1, 1) ...       (one strided copy per chunk and slice)
+//
+// The scan of a 10 s stream is a 10+ ms dependent chain whatever the chunk size; sliced, the first
+// PCM leaves after 1/8 of it and the copy engine -- the bottleneck of the whole call: PCM is 4.7x
+// the compressed bytes -- stays busy from then on.  Everything is submitted slice-major, the order
+// in which the work becomes ready: the copy engine takes its copies in submission order, so a copy
+// queued behind one that still waits for its kernels would wait with it.  Streams are few (lanes +
+// 2) so that they do not alias on the device's hardware queues.
 static bool is_pinned(const void *p)
 {
     cudaPointerAttributes a;
@@ -300,13 +320,46 @@ static bool is_pinned(const void *p)
     return a.type == cudaMemoryTypeHost;
 }
 
-static int lane_submit(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs, int16_t *pcm_out, bool pcm_pinned_packed, int scan_lanes)
+// DCSB_TRACE=1: device-side timeline of one dcsb_decode_streams call (CUDA events on the lanes'
+// streams, printed to stderr after the call) -- a tuning aid, off by default
+struct DcsbTrace {
+    bool on = false;
+    cudaEvent_t t0 = nullptr;
+    struct Mark { int lane; int slice; const char *what; cudaEvent_t ev; };
+    std::vector<Mark> marks;
+    void mark(int lane, int slice, const char *what, cudaStream_t st)
+    {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        marks.push_back(Mark{ lane, slice, what, e });
+    }
+    void dump()
+    {
+        if (!on) return;
+        for (const Mark &m : marks) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, t0, m.ev);
+            fprintf(stderr, "[dcsb trace] lane %d slice %2d %-10s %8.3f ms\n", m.lane, m.slice, m.what, ms);
+            cudaEventDestroy(m.ev);
+        }
+        marks.clear();
+        cudaEventDestroy(t0);
+    }
+};
+static DcsbTrace g_trace;
+
+#define ENS(buf, bytes, host, what) do { cudaError_t e_ = (buf).ensure((bytes), (host)); if (e_ != cudaSuccess) return fail(ctx, DCSB_E_NOMEM, what, e_); } while (0)
+
+// phase 1 of a lane: lay the chunk out, plan its time slices, upload it (on the context's upload stream)
+static int lane_upload(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs, bool pcm_pinned_packed)
 {
     const size_t n = l.count;
     const dcsb_stream_desc *d = descs + l.first;
-    if (!l.st) CK(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking), "cudaStreamCreate");
-    if (!l.aux) {
-        CK(cudaStreamCreateWithFlags(&l.aux, cudaStreamNonBlocking), "cudaStreamCreate");
+    const int lane_id = (int)(&l - ctx->lanes);
+    if (!l.st) {
+        CK(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking), "cudaStreamCreate");
         CK(cudaEventCreateWithFlags(&l.ev_go, cudaEventDisableTiming), "cudaEventCreate");
         CK(cudaEventCreateWithFlags(&l.ev_scan, cudaEventDisableTiming), "cudaEventCreate");
     }
@@ -325,10 +378,44 @@ static int lane_submit(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs
     if (rc != DCSB_OK) return fail(ctx, rc, "dcsb_decode_streams: unknown os_version or batch too large");
     const DcsbPrepared &p = l.prep;
     const uint64_t ck = std::max<uint64_t>(1, p.total_checkpoints), nn = std::max<size_t>(1, n);
-#define ENS(buf, bytes, host, what) do { cudaError_t e_ = (buf).ensure((bytes), (host)); if (e_ != cudaSuccess) return fail(ctx, DCSB_E_NOMEM, what, e_); } while (0)
+    // time slices
+    l.slice = 0;
+    l.nslices = 1;
+    l.direct_pcm = pcm_pinned_packed;
+    if (pcm_pinned_packed && n && ctx->slice_frames >= 0) {
+        const uint32_t U = p.recs[0].out_frames;
+        bool uniform = U > 1 && (uint64_t)U * 480 <= 0x7FFFFFFFull;
+        for (size_t i = 1; i < n && uniform; ++i) uniform = p.recs[i].out_frames == U;
+        if (uniform) {
+            if (ctx->slice_frames > 0) l.slice = (uint32_t)ctx->slice_frames;
+            else if (U >= 256) l.slice = (((U + 7) / 8 + p.item_len - 1) / p.item_len) * p.item_len;     // ~8 slices of whole work items
+            if (l.slice >= U) l.slice = 0;
+            if (l.slice) l.nslices = (U + l.slice - 1) / l.slice;
+            if (l.nslices > 64) { l.slice = (U + 63) / 64; l.nslices = (U + l.slice - 1) / l.slice; }
+        }
+    }
+    l.sl_off.clear();
+    if (l.slice) {
+        l.slice_tiles.clear();
+        std::vector<DcsbTile> t93;
+        for (uint32_t k = 0; k < l.nslices; ++k) {
+            t93.clear();
+            l.sl_off.push_back(l.slice_tiles.size());
+            dcsb_build_tiles(&p, k * l.slice, k + 1 == l.nslices ? 0xFFFFFFFFu : (k + 1) * l.slice, &l.slice_tiles, &t93);
+            l.sl_off.push_back(l.slice_tiles.size());
+            l.slice_tiles.insert(l.slice_tiles.end(), t93.begin(), t93.end());
+        }
+        l.sl_off.push_back(l.slice_tiles.size());
+    }
+    while (l.ev_slices.size() < l.nslices) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+        l.ev_slices.push_back(e);
+    }
+    const std::vector<DcsbTile> &tiles = l.slice ? l.slice_tiles : p.tiles;
     ENS(l.d_slab, p.slab_bytes, false, "cudaMalloc(slab)");
     ENS(l.d_recs, nn * sizeof(DcsbStreamRec), false, "cudaMalloc(recs)");
-    ENS(l.d_tiles, std::max<size_t>(1, p.tiles.size()) * sizeof(DcsbTile), false, "cudaMalloc(tiles)");
+    ENS(l.d_tiles, std::max<size_t>(1, tiles.size()) * sizeof(DcsbTile), false, "cudaMalloc(tiles)");
     ENS(l.d_order, nn * sizeof(uint32_t), false, "cudaMalloc(order)");
     ENS(l.d_bitpos, ck * 4, false, "cudaMalloc(bitpos)");
     ENS(l.d_bt, ck * 8, false, "cudaMalloc(bt)");
@@ -345,47 +432,107 @@ static int lane_submit(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs
     ENS(l.d_pcm, std::max<uint64_t>(2, p.total_out_frames * 480), false, "cudaMalloc(pcm)");
     ENS(l.h_res, nn * 20, true, "cudaMallocHost(results)");
     if (n == 0) return DCSB_OK;
+    cudaStream_t up = ctx->up;
     if (in_place) {
         const size_t span = (size_t)(hi - lo);
-        CK(cudaMemcpyAsync(l.d_slab.p, lo, span, cudaMemcpyHostToDevice, l.st), "H2D streams (in place)");
-        CK(cudaMemsetAsync((uint8_t *)l.d_slab.p + span, 0, p.slab_bytes - span, l.st), "memset slab tail");
+        // (the 1 KB of slack behind the span is not cleared: nothing read from there can reach the output --
+        // look-ahead bits only select among table entries that share the valid prefix, and a frame that
+        // consumes bits behind its stream is a truncation whatever those bits are.  A memset here is a
+        // kernel that would queue behind the other lanes' decode grids and hold the next upload back.)
+        CK(cudaMemcpyAsync(l.d_slab.p, lo, span, cudaMemcpyHostToDevice, up), "H2D streams (in place)");
     } else {
         ENS(l.h_slab, p.slab_bytes, true, "cudaMallocHost(slab)");
         dcsb_pack_slab(d, n, &p, (uint8_t *)l.h_slab.p);
-        CK(cudaMemcpyAsync(l.d_slab.p, l.h_slab.p, p.slab_bytes, cudaMemcpyHostToDevice, l.st), "H2D slab");
+        CK(cudaMemcpyAsync(l.d_slab.p, l.h_slab.p, p.slab_bytes, cudaMemcpyHostToDevice, up), "H2D slab");
     }
-#undef ENS
-    CK(cudaMemcpyAsync(l.d_recs.p, p.recs.data(), n * sizeof(DcsbStreamRec), cudaMemcpyHostToDevice, l.st), "H2D recs");
-    CK(cudaMemcpyAsync(l.d_tiles.p, p.tiles.data(), p.tiles.size() * sizeof(DcsbTile), cudaMemcpyHostToDevice, l.st), "H2D tiles");
-    CK(cudaMemcpyAsync(l.d_order.p, p.scan_order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, l.st), "H2D order");
+    // descriptors, work items and scan order go through pinned staging: a copy from pageable memory
+    // would make the host wait for everything queued on the upload stream before it
+    const size_t b_recs = n * sizeof(DcsbStreamRec), b_tiles = tiles.size() * sizeof(DcsbTile), b_order = n * sizeof(uint32_t);
+    ENS(l.h_meta, b_recs + b_tiles + b_order + 64, true, "cudaMallocHost(meta)");
+    uint8_t *hm = (uint8_t *)l.h_meta.p;
+    memcpy(hm, p.recs.data(), b_recs);
+    memcpy(hm + b_recs, tiles.data(), b_tiles);
+    memcpy(hm + b_recs + b_tiles, p.scan_order.data(), b_order);
+    CK(cudaMemcpyAsync(l.d_recs.p, hm, b_recs, cudaMemcpyHostToDevice, up), "H2D recs");
+    if (b_tiles) CK(cudaMemcpyAsync(l.d_tiles.p, hm + b_recs, b_tiles, cudaMemcpyHostToDevice, up), "H2D tiles");
+    CK(cudaMemcpyAsync(l.d_order.p, hm + b_recs + b_tiles, b_order, cudaMemcpyHostToDevice, up), "H2D order");
+    CK(cudaEventRecord(l.ev_go, up), "event");
+    g_trace.mark(lane_id, -1, "h2d", up);
+    // (memsets are kernels: they go on the lane's own stream, not between the uploads)
     CK(cudaMemsetAsync(l.d_csum.p, 0, n * 8, l.st), "memset checksums");
+    if (!l.slice && ctx->overlap) {
+        CK(cudaMemsetAsync(l.d_progress.p, 0, (n + 4) * 4, l.st), "memset progress");
+        if (p.nqueue94) CK(cudaMemsetAsync(l.d_queue.p, 0, (size_t)p.nqueue94 * 8, l.st), "memset queue");
+        CK(cudaEventRecord(l.ev_scan, l.st), "event");       // (re-recorded after the scan; here: the memsets are done)
+    }
+    CK(cudaStreamWaitEvent(l.st, l.ev_go, 0), "stream wait");
+    return DCSB_OK;
+}
+
+// phase 2 of a lane: kernels of slice k (the whole chunk when it is not sliced) and the copy of its PCM
+static int lane_slice(dcsb_ctx *ctx, DcsbLane &l, uint32_t k, int16_t *pcm_out, int scan_lanes)
+{
+    const size_t n = l.count;
+    if (n == 0 || k >= l.nslices) return DCSB_OK;
+    const DcsbPrepared &p = l.prep;
+    const int lane_id = (int)(&l - ctx->lanes);
+    const uint8_t *slab = (const uint8_t *)l.d_slab.p;
+    const DcsbStreamRec *recs = (const DcsbStreamRec *)l.d_recs.p;
+    const DcsbTile *tiles = (const DcsbTile *)l.d_tiles.p;
+    int16_t *d_pcm = (int16_t *)l.d_pcm.p;
+    unsigned long long *d_csum = (unsigned long long *)l.d_csum.p;
     DcsbScanOut so{ (uint32_t *)l.d_bitpos.p, (uint2 *)l.d_bt.p, (uint16_t *)l.d_hdrbits.p, (int32_t *)l.d_status.p,
                     (uint32_t *)l.d_nplay.p, (uint32_t *)l.d_endbits.p, (uint8_t *)l.d_stopband.p, nullptr, nullptr, nullptr, nullptr, nullptr };
+    if (l.slice) {
+        const uint32_t U = p.recs[0].out_frames;
+        const uint32_t fa = k * l.slice, fb = k + 1 == l.nslices ? U : (k + 1) * l.slice;
+        CK(dcsb_launch_scan(slab, recs, (const uint32_t *)l.d_order.p, (int)n, scan_lanes, ctx->d_tables, so, l.st, fa,
+                            k + 1 == l.nslices ? 0xFFFFFFFFu : fb), "scan kernel launch");
+        g_trace.mark(lane_id, (int)k, "scan", l.st);
+        CK(dcsb_launch_decode(slab, recs, tiles + l.sl_off[2 * k], (int)(l.sl_off[2 * k + 1] - l.sl_off[2 * k]),
+                              (int)(l.sl_off[2 * k + 2] - l.sl_off[2 * k + 1]), ctx->d_tables, so, d_pcm, d_csum, l.st), "decode kernel launch");
+        g_trace.mark(lane_id, (int)k, "decode", l.st);
+        CK(cudaEventRecord(l.ev_slices[k], l.st), "event");
+        CK(cudaStreamWaitEvent(ctx->down, l.ev_slices[k], 0), "stream wait");
+        CK(cudaMemcpy2DAsync(pcm_out + l.pcm_base + (uint64_t)fa * 240, (size_t)U * 480, d_pcm + (uint64_t)fa * 240, (size_t)U * 480,
+                             (size_t)(fb - fa) * 480, n, cudaMemcpyDeviceToHost, ctx->down), "D2H pcm slice");
+        g_trace.mark(lane_id, (int)k, "d2h", ctx->down);
+        return DCSB_OK;
+    }
     if (ctx->overlap) {
+        // the scan (a few latency-bound warps per SM) runs on a second stream BESIDE the persistent decode kernel
+        if (!l.aux) CK(cudaStreamCreateWithFlags(&l.aux, cudaStreamNonBlocking), "cudaStreamCreate");
         so.progress = (uint32_t *)l.d_progress.p;
         so.started = so.progress + n;
         so.qctl = so.progress + n + 1;
         so.queue = (unsigned long long *)l.d_queue.p;
-        CK(cudaMemsetAsync(l.d_progress.p, 0, (n + 4) * 4, l.st), "memset progress");
-        if (p.nqueue94) CK(cudaMemsetAsync(l.d_queue.p, 0, (size_t)p.nqueue94 * 8, l.st), "memset queue");
-        CK(cudaEventRecord(l.ev_go, l.st), "event");
         CK(cudaStreamWaitEvent(l.aux, l.ev_go, 0), "stream wait");
-        CK(dcsb_launch_scan((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p, (const uint32_t *)l.d_order.p, (int)n, scan_lanes, ctx->d_tables, so, l.aux), "scan kernel launch");
+        CK(cudaStreamWaitEvent(l.aux, l.ev_scan, 0), "stream wait");
+        CK(dcsb_launch_scan(slab, recs, (const uint32_t *)l.d_order.p, (int)n, scan_lanes, ctx->d_tables, so, l.aux), "scan kernel launch");
         CK(cudaEventRecord(l.ev_scan, l.aux), "event");
         CK(dcsb_launch_gate(so, dcsb_scan_grid((int)n), l.st), "gate kernel launch");
-    } else
-        CK(dcsb_launch_scan((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p, (const uint32_t *)l.d_order.p, (int)n, scan_lanes, ctx->d_tables, so, l.st), "scan kernel launch");
-    if (ctx->overlap)
-        CK(dcsb_launch_decode_queue((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p, (int)n, p.nqueue94, ctx->d_tables, so,
-                                    (int16_t *)l.d_pcm.p, (unsigned long long *)l.d_csum.p, l.st), "decode kernel launch");
-    CK(dcsb_launch_decode((const uint8_t *)l.d_slab.p, (const DcsbStreamRec *)l.d_recs.p,
-                          (const DcsbTile *)l.d_tiles.p + (ctx->overlap ? p.ntiles94 : 0), ctx->overlap ? 0 : p.ntiles94, p.ntiles93,
-                          ctx->d_tables, so, (int16_t *)l.d_pcm.p, (unsigned long long *)l.d_csum.p, l.st),
-       "decode kernel launch");
-    if (ctx->overlap) CK(cudaStreamWaitEvent(l.st, l.ev_scan, 0), "stream wait");
-    l.direct_pcm = pcm_pinned_packed;
-    if (l.direct_pcm)
-        CK(cudaMemcpyAsync(pcm_out + l.pcm_base, l.d_pcm.p, p.total_out_frames * 480, cudaMemcpyDeviceToHost, l.st), "D2H pcm");
+        CK(dcsb_launch_decode_queue(slab, recs, (int)n, p.nqueue94, ctx->d_tables, so, d_pcm, d_csum, l.st), "decode kernel launch");
+        CK(dcsb_launch_decode(slab, recs, tiles + p.ntiles94, 0, p.ntiles93, ctx->d_tables, so, d_pcm, d_csum, l.st), "decode kernel launch");
+        CK(cudaStreamWaitEvent(l.st, l.ev_scan, 0), "stream wait");
+    } else {
+        CK(dcsb_launch_scan(slab, recs, (const uint32_t *)l.d_order.p, (int)n, scan_lanes, ctx->d_tables, so, l.st), "scan kernel launch");
+        CK(dcsb_launch_decode(slab, recs, tiles, p.ntiles94, p.ntiles93, ctx->d_tables, so, d_pcm, d_csum, l.st), "decode kernel launch");
+    }
+    g_trace.mark(lane_id, -1, "kernels", l.st);
+    if (l.direct_pcm) {
+        CK(cudaEventRecord(l.ev_slices[0], l.st), "event");
+        CK(cudaStreamWaitEvent(ctx->down, l.ev_slices[0], 0), "stream wait");
+        CK(cudaMemcpyAsync(pcm_out + l.pcm_base, d_pcm, p.total_out_frames * 480, cudaMemcpyDeviceToHost, ctx->down), "D2H pcm");
+        g_trace.mark(lane_id, -1, "d2h", ctx->down);
+    }
+    return DCSB_OK;
+}
+
+// phase 3 of a lane: per-stream results into the lane's pinned block
+static int lane_results(dcsb_ctx *ctx, DcsbLane &l)
+{
+    const size_t n = l.count, nn = std::max<size_t>(1, n);
+    if (n == 0) return DCSB_OK;
     uint8_t *hr = (uint8_t *)l.h_res.p;
     CK(cudaMemcpyAsync(hr, l.d_status.p, n * 4, cudaMemcpyDeviceToHost, l.st), "D2H status");
     CK(cudaMemcpyAsync(hr + nn * 4, l.d_nplay.p, n * 4, cudaMemcpyDeviceToHost, l.st), "D2H nplay");
@@ -393,6 +540,7 @@ static int lane_submit(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs
     CK(cudaMemcpyAsync(hr + nn * 12, l.d_csum.p, n * 8, cudaMemcpyDeviceToHost, l.st), "D2H checksums");
     return DCSB_OK;
 }
+#undef ENS
 
 extern "C" int dcsb_decode_streams(dcsb_ctx *ctx, const dcsb_stream_desc *descs, size_t n,
                                    int16_t *pcm_out, const uint64_t *pcm_offsets, dcsb_result *results)
@@ -412,12 +560,20 @@ extern "C" int dcsb_decode_streams(dcsb_ctx *ctx, const dcsb_stream_desc *descs,
         if (pcm_offsets && pcm_offsets[i] != off[i]) packed = false;
     }
     const bool direct = packed && off[n] && is_pinned(pcm_out) && is_pinned(pcm_out + off[n] - 1);
+    if (!ctx->up) {
+        CK(cudaStreamCreateWithFlags(&ctx->up, cudaStreamNonBlocking), "cudaStreamCreate");
+        CK(cudaStreamCreateWithFlags(&ctx->down, cudaStreamNonBlocking), "cudaStreamCreate");
+    }
+    g_trace.on = getenv("DCSB_TRACE") != nullptr;
+    if (g_trace.on) { cudaEventCreate(&g_trace.t0); cudaEventRecord(g_trace.t0, ctx->up); }
     // chunks of about equal PCM size; few enough that every chunk still fills the GPU
     const uint64_t total = off[n];
-    int nchunks = (int)std::min<uint64_t>(DCSB_MAX_LANES, std::max<uint64_t>(1, total / (48ull << 20)));
+    int nchunks = (int)std::min<uint64_t>(DCSB_DEFAULT_LANES, std::max<uint64_t>(1, total / (48ull << 20)));
     nchunks = (int)std::min<size_t>((size_t)nchunks, std::max<size_t>(1, n / 64));
+    if (ctx->max_chunks > 0) nchunks = (int)std::min<size_t>((size_t)ctx->max_chunks, n);
     int used = 0, rc = DCSB_OK;
     size_t i0 = 0;
+    uint32_t max_slices = 0;
     for (int c = 0; c < nchunks && i0 < n && rc == DCSB_OK; ++c) {
         const uint64_t goal = total * (uint64_t)(c + 1) / (uint64_t)nchunks;
         size_t i1 = i0 + 1;
@@ -426,12 +582,40 @@ extern "C" int dcsb_decode_streams(dcsb_ctx *ctx, const dcsb_stream_desc *descs,
         l.first = i0;
         l.count = i1 - i0;
         l.pcm_base = off[i0];
-        rc = lane_submit(ctx, l, descs, pcm_out, direct, dcsb_scan_lanes((int)std::min<size_t>(n, 0x7FFFFFFF)));
+        rc = lane_upload(ctx, l, descs, direct);
+        max_slices = std::max(max_slices, l.nslices);
         i0 = i1;
     }
+    const int scan_lanes = dcsb_scan_lanes((int)std::min<size_t>(n, 0x7FFFFFFF));
+    // submit the (chunk, slice) work in the order it is expected to become ready: chunk c is uploaded
+    // after the chunks before it (~45 GB/s), its slices then follow each other at the pace of the scan
+    // chain (~14 us per frame with the chip full)
+    struct Job { double ready; int c; uint32_t k; };
+    std::vector<Job> jobs;
+    double up_ms = 0.2;
+    for (int c = 0; c < used; ++c) {
+        const DcsbLane &l = ctx->lanes[c];
+        up_ms += (double)l.prep.slab_bytes / 45e6;
+        const double frames = l.slice ? (double)l.slice : (l.count ? (double)l.prep.total_frames_in / (double)l.count : 0.0);
+        for (uint32_t k = 0; k < l.nslices; ++k) jobs.push_back(Job{ up_ms + (k + 1) * (frames * 0.014 + 0.3), c, k });
+    }
+    std::stable_sort(jobs.begin(), jobs.end(), [](const Job &a, const Job &b) { return a.ready < b.ready; });
+    (void)max_slices;
+    for (const Job &j : jobs) {
+        if (rc != DCSB_OK) break;
+        rc = lane_slice(ctx, ctx->lanes[j.c], j.k, pcm_out, scan_lanes);
+    }
+    for (int c = 0; c < used && rc == DCSB_OK; ++c) rc = lane_results(ctx, ctx->lanes[c]);
     // drain
+    {
+        cudaError_t e = cudaStreamSynchronize(ctx->down);
+        if (e != cudaSuccess && rc == DCSB_OK) rc = fail(ctx, DCSB_E_CUDA, "dcsb_decode_streams: stream sync (copy failure?)", e);
+        e = cudaStreamSynchronize(ctx->up);
+        if (e != cudaSuccess && rc == DCSB_OK) rc = fail(ctx, DCSB_E_CUDA, "dcsb_decode_streams: stream sync (copy failure?)", e);
+    }
     for (int c = 0; c < used; ++c) {
         DcsbLane &l = ctx->lanes[c];
+        if (!l.st) continue;
         cudaError_t e = cudaStreamSynchronize(l.st);
         if (e != cudaSuccess && rc == DCSB_OK) rc = fail(ctx, DCSB_E_CUDA, "dcsb_decode_streams: stream sync (kernel failure?)", e);
         if (rc != DCSB_OK) continue;
@@ -462,5 +646,6 @@ extern "C" int dcsb_decode_streams(dcsb_ctx *ctx, const dcsb_stream_desc *descs,
             }
         }
     }
+    g_trace.dump();
     return rc;
 }

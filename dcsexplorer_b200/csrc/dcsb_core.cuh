@@ -538,9 +538,13 @@ DCSB_HD DcsbBits dcsb_make_reader(const uint8_t *slab, const DcsbStreamRec &s)
 
 // K1 body (1993 family; the 1994 layout has its own fast walker in dcsb_fast94.cuh): one
 // thread walks one stream (lengths only) and writes a checkpoint per frame + the end entry.
+// [f0, f1): the frames this call walks; f0 > 0 resumes from the checkpoint an earlier call left
+// (see dcsb_scan94_stream)
 DCSB_HD void dcsb_scan_stream(const uint8_t *slab, const DcsbStreamRec *streams, int si,
-                              const DcsbTables *tab, const uint16_t *lut, const DcsbScanOut &out)
+                              const DcsbTables *tab, const uint16_t *lut, const DcsbScanOut &out,
+                              uint32_t f0 = 0, uint32_t f1 = 0xFFFFFFFFu)
 {
+    if (f0 && out.status[si] != DCSB_SCAN_RUNNING) return;
     const DcsbStreamRec s = streams[si];
     int status = 0;
     uint32_t nplay = 0, pos = 0;
@@ -558,14 +562,20 @@ DCSB_HD void dcsb_scan_stream(const uint8_t *slab, const DcsbStreamRec *streams,
         const uint32_t nbits = (s.nbytes - 2 - s.hdr_len) * 8u;
         uint64_t bt = 0;                           // InitStreamPlayback zeroes the band types (:1640)
         nplay = s.nframes;
-        uint32_t f = 0;
-        for (; f < s.nframes; ++f) {
+        uint32_t f = f0;
+        if (f0) {
+            pos = out.bitpos[s.frame_base + f0];
+            const uint2 b2 = out.bt[s.frame_base + f0];
+            bt = ((uint64_t)b2.y << 32) | b2.x;
+        }
+        const uint32_t fe = f1 < s.nframes ? f1 : s.nframes;
+        for (; f < fe; ++f) {
             out.bitpos[s.frame_base + f] = pos;
             out.bt[s.frame_base + f] = make_uint2((uint32_t)bt, (uint32_t)(bt >> 32));
             out.hdrbits[s.frame_base + f] = 0;
             int sb = 99;
             int rc = dcsb_walk<false>(s.fmt, cx, pos, bt, nullptr, sb);
-            if (rc == 0 && pos > nbits) rc = -2;   // DCSB_E_TRUNCATED
+            if (pos > nbits) rc = -2;              // DCSB_E_TRUNCATED (whatever the bytes behind the stream made of the frame)
             if (rc) { status = rc; nplay = f; break; }
             if (sb != 99) { status = -5; nplay = f + 1; stopband = sb; ++f; break; }   // DCSB_E_STOPPED
             if ((f & 15) == 15) {
@@ -578,11 +588,13 @@ DCSB_HD void dcsb_scan_stream(const uint8_t *slab, const DcsbStreamRec *streams,
             out.bitpos[s.frame_base + f] = pos;
             out.bt[s.frame_base + f] = make_uint2((uint32_t)bt, (uint32_t)(bt >> 32));
         }
+        if (status == 0 && f < s.nframes) status = DCSB_SCAN_RUNNING;   // the next slice carries on from checkpoint f
     }
     out.status[si] = status;
     out.nplay[si] = nplay;
-    out.endbits[si] = pos;
+    out.endbits[si] = status == -2 ? (s.nbytes - 2 - s.hdr_len) * 8u : pos;     // a truncated stream occupies all of its bytes
     out.stopband[si] = (uint8_t)stopband;
+    if (status == DCSB_SCAN_RUNNING) return;
     dcsb_publish(out.progress, si, DCSB_SCAN_DONE);
 }
 
@@ -611,7 +623,7 @@ DCSB_HD unsigned long long dcsb_decode_tile(const uint8_t *slab, const DcsbStrea
     // ---- phase A: lane l decodes frame first-1+l (lane 0 = warm-up frame for the overlap)
     DCSB_FOR_LANES(l, 32) {
         const long long f = (long long)tl.first - 1 + l;
-        if (f >= 0 && f < nplay) {
+        if (f >= 0 && f < nplay && l <= (int)tl.count) {
             DcsbWalkCtx cx;
             cx.rd = dcsb_make_reader(slab, *sp);
             cx.hdr = sp->hdr;
@@ -639,7 +651,7 @@ DCSB_HD unsigned long long dcsb_decode_tile(const uint8_t *slab, const DcsbStrea
     for (int k = 0; k < 32; ++k) {
         const long long f = (long long)tl.first - 1 + k;
         if (f < 0) continue;                          // first tile of a stream: the overlap buffer starts at zero
-        if (f >= out_frames) break;
+        if (f >= out_frames || k > (int)tl.count) break;
         uint32_t *c = rows + k * ROWW;
         if (f < nplay) {                              // silent frames transform to silence
             if (T93) dcsb_transform93_warp(c, tab);

@@ -20,6 +20,7 @@ struct DcsbBuf {
         if (p) { if (host) cudaFreeHost(p); else cudaFree(p); p = nullptr; cap = 0; }
         const size_t want = bytes + bytes / 8 + 4096;
         cudaError_t e = host ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+        if (e == cudaSuccess && !host) e = cudaMemset(p, 0, want);     // no buffer is ever read uninitialised
         if (e == cudaSuccess) cap = want;
         return e;
     }
@@ -29,13 +30,18 @@ struct DcsbBuf {
 // One pipeline lane of dcsb_decode_streams: a CUDA stream plus everything one chunk of
 // streams needs, kept across calls so that the steady state does no allocation.
 #define DCSB_MAX_LANES 8
+#define DCSB_DEFAULT_LANES 6     // + the upload and the download stream = 8 streams: one per hardware queue of the device
 struct DcsbLane {
     cudaStream_t st = nullptr, aux = nullptr;                // aux: the scan runs beside the decode
     cudaEvent_t ev_go = nullptr, ev_scan = nullptr;
     DcsbBuf d_progress, d_queue, d_order;
-    DcsbBuf h_slab, h_res;                                   // pinned
+    DcsbBuf h_slab, h_res, h_meta;                           // pinned
     DcsbBuf d_slab, d_recs, d_tiles, d_bitpos, d_bt, d_hdrbits, d_status, d_nplay, d_endbits, d_stopband, d_csum, d_pcm;
     DcsbPrepared prep;
+    std::vector<DcsbTile> slice_tiles;                       // time-sliced chunk: work items of every slice, slice after slice
+    std::vector<cudaEvent_t> ev_slices;                      // slice k decoded (the PCM copy of the slice waits for it)
+    std::vector<size_t> sl_off;                              // first work item of slice k in slice_tiles: 2 entries per slice (1994, 1993 family) + end
+    uint32_t slice = 0, nslices = 1;                         // frames per time slice (0 = not sliced)
     size_t first = 0, count = 0;
     uint64_t pcm_base = 0;                                   // sample offset of the chunk in the packed output
     bool direct_pcm = false;
@@ -45,7 +51,10 @@ struct dcsb_ctx {
     int device = 0;
     DcsbTables *d_tables = nullptr;
     cudaStream_t aux = nullptr;              // resident batches: stream the scan runs on beside the decode
+    cudaStream_t up = nullptr, down = nullptr;   // dcsb_decode_streams: all uploads / all PCM downloads, in submission order
     bool overlap = true;                     // scan and decode kernels resident together (dcsb_set_overlap)
+    int max_chunks = 0;                      // dcsb_set_pipeline: chunks of dcsb_decode_streams (0 = choose)
+    int slice_frames = 0;                    // dcsb_set_pipeline: frames per time slice (0 = choose, < 0 = never slice)
     DcsbLane lanes[DCSB_MAX_LANES];
     std::string err;
 };

@@ -179,6 +179,30 @@ static void stream_gain(const dcsb_stream_desc &d, DcsbStreamRec &r)
 }
 
 
+// Work items covering output frames [fa, fb) of every stream, in frame-major order (item k of every
+// stream before item k + 1 of any): CTAs are dispatched in index order, so the decode kernel works
+// its way through the streams at the pace the scan running beside it delivers their checkpoints.
+void dcsb_build_tiles(const DcsbPrepared *p, uint32_t fa, uint32_t fb, std::vector<DcsbTile> *t94, std::vector<DcsbTile> *t93)
+{
+    const size_t n = p->recs.size();
+    for (int fam = 0; fam < 2; ++fam) {
+        const uint32_t len = fam ? (uint32_t)DCSB_TILE_OUT : p->item_len;
+        std::vector<DcsbTile> &dst = fam ? *t93 : *t94;
+        std::vector<uint32_t> live;
+        for (size_t i = 0; i < n; ++i)
+            if ((p->recs[i].fmt != DCSB_FMT_94) == (fam == 1) && p->recs[i].out_frames > fa) live.push_back((uint32_t)i);
+        for (uint32_t f = fa; !live.empty(); f += len) {
+            size_t keep = 0;
+            for (uint32_t i : live) {
+                const uint32_t of = std::min(p->recs[i].out_frames, fb);
+                dst.push_back(DcsbTile{ i, f, std::min<uint32_t>(len, of - f) });
+                if (f + len < of) live[keep++] = i;
+            }
+            live.resize(keep);
+        }
+    }
+}
+
 int dcsb_prepare(const dcsb_stream_desc *descs, size_t n, DcsbPrepared *p, const uint8_t *in_place_base, size_t in_place_span)
 {
     p->recs.resize(n);
@@ -236,27 +260,10 @@ int dcsb_prepare(const dcsb_stream_desc *descs, size_t n, DcsbPrepared *p, const
         pcm += (uint64_t)r.out_frames * 240;
         p->compressed_bytes += d.nbytes;
     }
-    // work items in frame-major order (item k of every stream before item k + 1 of any): CTAs are
-    // dispatched in index order, so the decode kernel works its way through the streams at the pace
-    // the scan running beside it delivers their checkpoints
+    p->item_len = item_len;
     t94.reserve(items94);
     t93.reserve(items93);
-    for (int fam = 0; fam < 2; ++fam) {
-        const uint32_t len = fam ? (uint32_t)DCSB_TILE_OUT : item_len;
-        std::vector<DcsbTile> &dst = fam ? t93 : t94;
-        std::vector<uint32_t> live;
-        for (size_t i = 0; i < n; ++i)
-            if ((p->recs[i].fmt != DCSB_FMT_94) == (fam == 1) && p->recs[i].out_frames) live.push_back((uint32_t)i);
-        for (uint32_t f = 0; !live.empty(); f += len) {
-            size_t keep = 0;
-            for (uint32_t i : live) {
-                const uint32_t of = p->recs[i].out_frames;
-                dst.push_back(DcsbTile{ i, f, std::min<uint32_t>(len, of - f) });
-                if (f + len < of) live[keep++] = i;
-            }
-            live.resize(keep);
-        }
-    }
+    dcsb_build_tiles(p, 0, 0xFFFFFFFFu, &t94, &t93);
     // the scan walks 2 streams per warp in lockstep per band: put streams side by side that take the
     // same branches and about as many table steps (same layout, same stream type, similar bits per frame)
     p->scan_order.resize(n);

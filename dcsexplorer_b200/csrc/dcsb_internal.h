@@ -71,6 +71,7 @@ struct DcsbTables {
 };
 
 #define DCSB_SCAN_DONE 0x80000000u
+#define DCSB_SCAN_RUNNING 1                 // DcsbScanOut::status between two time slices of a stream (never seen by callers)
 #define DCSB_QITEM 63u                      // frames per queued work item: with the warm-up frame, two full 32-lane tiles
 #define DCSB_Q_VALID (1ull << 63)           // queue entry: VALID | FINAL? | stream << 24 | first frame
 #define DCSB_Q_FINAL (1ull << 62)           // the stream's scan is finished: nplay / stopband are final
@@ -108,6 +109,7 @@ struct DcsbPrepared {
     std::vector<DcsbTile> tiles;          // 1994-family items first, then 1993-family tiles
     std::vector<uint32_t> scan_order;     // streams in the order the scan assigns them to lanes: alike streams side by side
     int ntiles94 = 0, ntiles93 = 0;
+    uint32_t item_len = 31;               // output frames per 1994-family work item
     int nqueue94 = 0;                     // work items the scan queues for the 1994-layout streams (overlapped mode)
     uint64_t total_frames_in = 0;         // stream frames
     uint64_t total_checkpoints = 0;       // stream frames + one end entry per stream
@@ -119,6 +121,8 @@ struct DcsbPrepared {
 // and each stream keeps its position inside it (any byte alignment); otherwise streams are laid
 // out back to back, 16-byte aligned and zero padded, for dcsb_pack_slab.
 int dcsb_prepare(const dcsb_stream_desc *descs, size_t n, DcsbPrepared *p, const uint8_t *in_place_base, size_t in_place_span);
+// work items covering output frames [fa, fb) of every stream (appended to t94 / t93), frame-major
+void dcsb_build_tiles(const DcsbPrepared *p, uint32_t fa, uint32_t fb, std::vector<DcsbTile> *t94, std::vector<DcsbTile> *t93);
 // copy the streams into `slab` (p->slab_bytes bytes) at their 16-byte aligned offsets, zero padded
 void dcsb_pack_slab(const dcsb_stream_desc *descs, size_t n, const DcsbPrepared *p, uint8_t *slab);
 
@@ -126,8 +130,10 @@ void dcsb_pack_slab(const dcsb_stream_desc *descs, size_t n, const DcsbPrepared 
 // side by side passes dcsb_scan_lanes(total streams) so that all of them fit on the chip at once
 // (a scan CTA's tables fill an SM's shared memory).
 // order: device array of nstreams stream indices (NULL = identity): which stream each scan lane takes
+// [f0, f1): frames of every stream this launch walks; f0 > 0 resumes from the checkpoints the launch
+// for [.., f0) left (time-sliced chunks of dcsb_decode_streams)
 cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, const uint32_t *order, int nstreams, int lanes_hint,
-                             const DcsbTables *tables, DcsbScanOut out, cudaStream_t st);
+                             const DcsbTables *tables, DcsbScanOut out, cudaStream_t st, uint32_t f0 = 0, uint32_t f1 = 0xFFFFFFFFu);
 int dcsb_scan_lanes(int nstreams);       // streams per warp the scan launch uses (1..32)
 // tiles[0..ntiles94) use the 1994 transform, tiles[ntiles94..ntiles94+ntiles93) the 1993 one
 // enqueue a one-thread kernel that returns once `ctas` scan CTAs are resident (scan.started)

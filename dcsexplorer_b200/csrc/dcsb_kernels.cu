@@ -43,7 +43,7 @@ struct DcsbSmemScan {
 
 __global__ void __launch_bounds__(DCSB_SCAN_SPC * 32, 1)
 dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restrict__ streams, const uint32_t *__restrict__ order,
-                 int nstreams, int lanes, int spc, const DcsbTables *__restrict__ tab, DcsbScanOut out)
+                 int nstreams, int lanes, int spc, const DcsbTables *__restrict__ tab, DcsbScanOut out, uint32_t f0, uint32_t f1)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     DcsbSmemScan &sm = *reinterpret_cast<DcsbSmemScan *>(smem);
@@ -64,8 +64,8 @@ dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restri
     const DcsbRingPtr ring = DCSB_SMEM_U8(sm.ring[slot]);
     for (int k = blockIdx.x * spc + slot; k < nstreams; k += gridDim.x * spc) {
         const int si = order ? (int)order[k] : k;
-        if (streams[si].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab, streams, si, tab, sm.lut, t8, t1, ring, out);
-        else dcsb_scan_stream(slab, streams, si, tab, sm.lut, out);
+        if (streams[si].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab, streams, si, tab, sm.lut, t8, t1, ring, out, f0, f1);
+        else dcsb_scan_stream(slab, streams, si, tab, sm.lut, out, f0, f1);
     }
 }
 
@@ -372,7 +372,7 @@ cudaError_t dcsb_launch_gate(DcsbScanOut scan, int ctas, cudaStream_t st)
 }
 
 cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, const uint32_t *order, int nstreams, int lanes_hint,
-                             const DcsbTables *tables, DcsbScanOut out, cudaStream_t st)
+                             const DcsbTables *tables, DcsbScanOut out, cudaStream_t st, uint32_t f0, uint32_t f1)
 {
     if (nstreams <= 0) return cudaSuccess;
     const int lanes = lanes_hint > 0 ? lanes_hint : dcsb_scan_lanes(nstreams);
@@ -386,7 +386,7 @@ cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, 
     // this one (the split only changes on an idle SM)
     e = cudaFuncSetAttribute(dcsb_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    dcsb_scan_kernel<<<grid, warps * 32, smem, st>>>(slab, streams, order, nstreams, lanes, spc, tables, out);
+    dcsb_scan_kernel<<<grid, warps * 32, smem, st>>>(slab, streams, order, nstreams, lanes, spc, tables, out, f0, f1);
     return cudaGetLastError();
 }
 

@@ -147,9 +147,15 @@ DCSB_HD uint32_t dcsb_lds8(DcsbSmemU8 base, uint32_t idx) { return base[idx]; }
 typedef uint8_t *DcsbRingPtr;
 #endif
 
+// [f0, f1) = the frames this call walks (0, ~0u = the whole stream).  A call with f0 > 0 resumes
+// from the end checkpoint the previous call left at frame f0 (status DCSB_SCAN_RUNNING); that is
+// what lets dcsb_decode_streams cut a chunk into time slices whose PCM drains over PCIe while
+// the later slices are still being scanned.
 DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *streams, int si, const DcsbTables *tab,
-                                const uint16_t *lut, DcsbSmemU8 t8, DcsbSmemU8 t1, DcsbRingPtr ring, const DcsbScanOut &out)
+                                const uint16_t *lut, DcsbSmemU8 t8, DcsbSmemU8 t1, DcsbRingPtr ring, const DcsbScanOut &out,
+                                uint32_t f0 = 0, uint32_t f1 = 0xFFFFFFFFu)
 {
+    if (f0 && out.status[si] != DCSB_SCAN_RUNNING) return;      // finished (or failed) in an earlier slice
     const DcsbStreamRec s = streams[si];
     const uint8_t *hdr = streams[si].hdr;
     const int type1 = hdr[0] >> 7;
@@ -173,8 +179,18 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
     // reach into the zero padding (the slab keeps >= 1 KB of slack behind the last stream)
     win.limit = s.nframes ? (uint32_t)(((start & 15) + dbytes + 64u + 15u) >> 4) : 0u;
     win.wa = 12u;
+    uint32_t pos = 0;
+    uint64_t bt = 0;                               // InitStreamPlayback zeroes the band types (:1640)
+    if (f0) {
+        pos = out.bitpos[s.frame_base + f0];
+        const uint2 b2 = out.bt[s.frame_base + f0];
+        bt = ((uint64_t)b2.y << 32) | b2.x;
+        const uint32_t off = ((pos + win.bias) >> 5) * 4u;
+        win.wa = off + 12u;
+        win.fill = off >> 4;
+    }
     win.topup();
-    win.seek(0);
+    win.seek(pos);
     // plain reader on global memory for the rare long header codes
     DcsbBits rd;
     rd.w = reinterpret_cast<const uint32_t *>(slab + (start & ~3ull));
@@ -191,15 +207,14 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
 #define DCSB_DBG_LAP(k)
 #endif
     uint32_t queued = 0, qnext = DCSB_QITEM;       // output frames already handed to the decode kernel / next hand-over
-    uint64_t bt = 0;                               // InitStreamPlayback zeroes the band types (:1640)
     int status = s.nframes ? 0 : -1, stopband = 0xFF;    // -1 = DCSB_E_EMPTY (the host refines DCSB_E_SHORT)
-    uint32_t nplay = s.nframes, f = 0;
-    uint32_t pos = 0;
-    for (; f < s.nframes; ++f) {
+    uint32_t nplay = s.nframes, f = f0;
+    const uint32_t fe = f1 < s.nframes ? f1 : s.nframes;
+    for (; f < fe; ++f) {
         out.bitpos[s.frame_base + f] = pos;
         out.bt[s.frame_base + f] = make_uint2((uint32_t)bt, (uint32_t)(bt >> 32));
         DCSB_DBG_LAP(3)
-        if (f) win.topup();
+        if (f != f0) win.topup();
         DCSB_DBG_LAP(0)
         // ---- frame header (:1780-1834)
         int rc = 0;
@@ -228,7 +243,8 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
             bt = (bt & ~(15ull << (4 * b))) | ((uint64_t)nbt << (4 * b));
             b += unchanged ? run : 1;
         }
-        if (rc) { status = rc; nplay = f; break; }
+        // (a code that reaches into the bytes behind the stream is a truncation, whatever those bytes are)
+        if (rc) { status = win.pos() > nbits ? -2 : rc; nplay = f; break; }
         DCSB_DBG_LAP(1)
         const uint32_t hpos = win.pos();
         out.hdrbits[s.frame_base + f] = (uint16_t)(hpos - pos);
@@ -293,6 +309,7 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
 #if DCSB_DEVICE_PASS
     asm volatile("cp.async.wait_group 0;" ::: "memory");    // nothing in flight when the ring is reused
 #endif
+    if (status == 0 && f < s.nframes) status = DCSB_SCAN_RUNNING;       // the next slice carries on from checkpoint f
 #if defined(DCSB_SCAN_DEBUG) && DCSB_DEVICE_PASS
     if (out.dbg) {
         const long long dt = clock64() - dbg_t0;
@@ -304,8 +321,9 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
 #endif
     out.status[si] = status;
     out.nplay[si] = nplay;
-    out.endbits[si] = pos;
+    out.endbits[si] = status == -2 ? nbits : pos;      // a truncated stream occupies all of its bytes
     out.stopband[si] = (uint8_t)stopband;
+    if (status == DCSB_SCAN_RUNNING) return;
     dcsb_publish(out.progress, si, DCSB_SCAN_DONE);
     dcsb_queue_push(out, si, queued, s.out_frames, true);
 }

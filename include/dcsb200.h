@@ -80,6 +80,15 @@ const char *dcsb_version(void);
  * (what a profiler sees anyway, and what per-kernel timings should be read from) */
 int dcsb_set_overlap(dcsb_ctx *ctx, int on);
 
+/* Tuning of dcsb_decode_streams' pipeline (defaults: 0, 0).  max_chunks: how many chunks of streams
+ * the batch is cut into (1..8; each chunk is uploaded, decoded and downloaded on its own CUDA
+ * stream).  slice_frames: a chunk whose streams all render the same number of frames into a packed,
+ * pinned output is also cut in TIME -- frames [k*slice, (k+1)*slice) of every stream are scanned
+ * (resuming from the previous slice's checkpoints), decoded and copied out as one strided copy while
+ * the next slice is being scanned, so the PCM starts to drain over PCIe after a fraction of the
+ * per-stream scan chain; > 0 = that many frames per slice, 0 = choose, < 0 = never slice. */
+int dcsb_set_pipeline(dcsb_ctx *ctx, int max_chunks, int slice_frames);
+
 /* ---- one-shot batch decode with HOST buffers ------------------------------------- */
 /* Replaces: the per-stream loop in DCSExplorer ExtractTracksOrStreams (DCSExplorer.cpp:1628-1939).
  * pcm_offsets[i] is the sample offset of stream i inside pcm_out (NULL = tightly packed in

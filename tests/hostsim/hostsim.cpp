@@ -15,8 +15,11 @@
 #include "../../dcsexplorer_b200/csrc/dcsb_scan94.cuh"
 #include "../../dcsexplorer_b200/csrc/dcsb_mix.cuh"
 
-extern "C" int hostsim_decode_streams(const dcsb_stream_desc *descs, size_t n, int16_t *pcm_out,
-                                      dcsb_result *results, uint32_t *bitpos_out, uint8_t *bt_out)
+// slice_frames > 0: the time-sliced form dcsb_decode_streams uses for uniform chunks -- scan frames
+// [k * slice, (k + 1) * slice) of every stream (resuming from the previous slice's end checkpoint),
+// then decode the work items of that slice, slice after slice
+static int sim_decode_streams(const dcsb_stream_desc *descs, size_t n, int16_t *pcm_out,
+                              dcsb_result *results, uint32_t *bitpos_out, uint8_t *bt_out, uint32_t slice_frames)
 {
     DcsbPrepared p;
     int rc = dcsb_prepare(descs, n, &p, nullptr, 0);
@@ -33,22 +36,27 @@ extern "C" int hostsim_decode_streams(const dcsb_stream_desc *descs, size_t n, i
     std::vector<uint8_t> stopband(n + 1);
     DcsbScanOut so{ bitpos.data(), bt.data(), hdrbits.data(), status.data(), nplay.data(), endbits.data(), stopband.data(), nullptr, nullptr, nullptr, nullptr, nullptr };
     std::vector<uint8_t> ring(DCSB_RING_BYTES, 0xA5);                // one K1 thread's shared-memory ring
-    for (size_t i = 0; i < n; ++i)                                   // K1 grid
-        if (p.recs[i].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, tab.t8, tab.t1, ring.data(), so);
-        else dcsb_scan_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, so);
-
     std::vector<unsigned long long> csum(n + 1, 0);
     std::vector<uint32_t> rows(DcsbWarpSmem<true>::WORDS + DCSB_WARP94_WORDS);
     static DcsbTw94 tw;
     memcpy(tw.tw_c2, tab.tw_c2, sizeof(tw.tw_c2)); memcpy(tw.tw_s2, tab.tw_s2, sizeof(tw.tw_s2));
     memcpy(tw.pre_c0, tab.pre_c0, sizeof(tw.pre_c0)); memcpy(tw.pre_c1, tab.pre_c1, sizeof(tw.pre_c1));
-    for (size_t t = 0; t < p.tiles.size(); ++t) {                    // K2 grid, one warp per tile
-        if ((int)t < p.ntiles94)
-            csum[p.tiles[t].stream] += dcsb_decode94_item(slab.data(), p.recs.data(), p.tiles[t], &tab, tab.lut, &tw,
-                                                          p.recs[p.tiles[t].stream].hdr, so, nplay[p.tiles[t].stream],
-                                                          stopband[p.tiles[t].stream], pcm_out, rows.data());
-        else
-            csum[p.tiles[t].stream] += dcsb_decode_tile<true>(slab.data(), p.recs.data(), p.tiles[t], &tab, tab.lut, so, pcm_out, rows.data());
+    uint32_t max_out = 0;
+    for (size_t i = 0; i < n; ++i) max_out = std::max(max_out, p.recs[i].out_frames);
+    for (uint32_t fa = 0; fa == 0 || fa < max_out; fa += slice_frames ? slice_frames : 0xFFFFFFFFu) {
+        const uint32_t fb = slice_frames && fa + slice_frames < max_out ? fa + slice_frames : 0xFFFFFFFFu;
+        for (size_t i = 0; i < n; ++i)                                   // K1 grid
+            if (p.recs[i].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, tab.t8, tab.t1, ring.data(), so, fa, fb);
+            else dcsb_scan_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, so, fa, fb);
+        std::vector<DcsbTile> t94, t93;
+        if (slice_frames) dcsb_build_tiles(&p, fa, fb, &t94, &t93);
+        else { t94.assign(p.tiles.begin(), p.tiles.begin() + p.ntiles94); t93.assign(p.tiles.begin() + p.ntiles94, p.tiles.end()); }
+        for (const DcsbTile &tl : t94)                                   // K2 grid, one warp per item
+            csum[tl.stream] += dcsb_decode94_item(slab.data(), p.recs.data(), tl, &tab, tab.lut, &tw, p.recs[tl.stream].hdr, so,
+                                                  nplay[tl.stream], stopband[tl.stream], pcm_out, rows.data());
+        for (const DcsbTile &tl : t93)
+            csum[tl.stream] += dcsb_decode_tile<true>(slab.data(), p.recs.data(), tl, &tab, tab.lut, so, pcm_out, rows.data());
+        if (fb == 0xFFFFFFFFu) break;
     }
     for (size_t i = 0; i < n; ++i) {
         if (results) {
@@ -71,6 +79,17 @@ extern "C" int hostsim_decode_streams(const dcsb_stream_desc *descs, size_t n, i
         }
     }
     return DCSB_OK;
+}
+
+extern "C" int hostsim_decode_streams(const dcsb_stream_desc *descs, size_t n, int16_t *pcm_out,
+                                      dcsb_result *results, uint32_t *bitpos_out, uint8_t *bt_out)
+{
+    return sim_decode_streams(descs, n, pcm_out, results, bitpos_out, bt_out, 0);
+}
+extern "C" int hostsim_decode_streams_sliced(const dcsb_stream_desc *descs, size_t n, int16_t *pcm_out,
+                                             dcsb_result *results, uint32_t *bitpos_out, uint8_t *bt_out, uint32_t slice_frames)
+{
+    return sim_decode_streams(descs, n, pcm_out, results, bitpos_out, bt_out, slice_frames);
 }
 
 // ---- track playback: the host sequencer (product code, dcsb_rom.cpp) + K1 / K4 bodies on the CPU ----

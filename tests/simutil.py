@@ -22,8 +22,9 @@ def lib():
     return _LIB
 
 
-def decode_streams(streams, **kw):
-    """Same contract as dcsexplorer_b200.Context.decode_streams, executed by the simulator."""
+def decode_streams(streams, slice_frames=0, **kw):
+    """Same contract as dcsexplorer_b200.Context.decode_streams, executed by the simulator.
+    slice_frames > 0: time-sliced (resumed scans), as dcsb_decode_streams does for uniform chunks."""
     descs, keep = make_descs(streams, **kw)
     n = len(streams)
     offs, total, nframes = [], 0, 0
@@ -36,7 +37,13 @@ def decode_streams(streams, **kw):
     res = (Result * max(1, n))()
     bitpos = np.zeros(max(nframes, 1), dtype=np.uint32)
     bt = np.zeros((max(nframes, 1), 16), dtype=np.uint8)
-    rc = lib().hostsim_decode_streams(descs, n, pcm.ctypes.data, res, bitpos.ctypes.data, bt.ctypes.data)
+    if slice_frames:
+        L = lib()
+        L.hostsim_decode_streams_sliced.restype = C.c_int
+        L.hostsim_decode_streams_sliced.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        rc = L.hostsim_decode_streams_sliced(descs, n, pcm.ctypes.data, res, bitpos.ctypes.data, bt.ctypes.data, slice_frames)
+    else:
+        rc = lib().hostsim_decode_streams(descs, n, pcm.ctypes.data, res, bitpos.ctypes.data, bt.ctypes.data)
     assert rc == 0, rc
     results = [dict(status=res[i].status, frames=res[i].frames, frames_decoded=res[i].frames_decoded,
                     stream_bytes=res[i].stream_bytes, checksum=res[i].checksum) for i in range(n)]

@@ -207,3 +207,35 @@ def test_gpu_config5_shape_many_short_streams(ctx):
         assert np.array_equal(b.read_pcm(k, pcm.size), pcm)
         b.close()
     ctx.set_overlap(True)
+
+
+def test_gpu_decode_streams_time_slices(ctx):
+    """Uniform chunks (every stream renders the same number of frames into a packed pinned buffer)
+    are cut in time: resumed scans + per-slice work items + strided PCM copies.  Same PCM, statuses
+    and checksums as the one-pass form, for slice lengths that do and do not divide the streams,
+    for all layouts, and with streams that fail in the middle of a slice."""
+    rng = np.random.default_rng(99)
+    nf = 150
+    streams = []
+    for k in range(12):
+        streams.append((dcsfuzz.fuzz94(rng, nf, type1=k & 1, max_code=15 if k % 3 == 0 else 9), 0x9400, 255, 100, 2))
+    streams.append((dcsfuzz.fuzz94(rng, nf, type1=1, max_code=6, error_frame=77, escape_p=0.2), 0x9400, 200, 64, 2))
+    ok = dcsfuzz.fuzz94(rng, nf, type1=1)
+    streams.append((ok[: len(ok) // 2], 0x9400, 255, 100, 2))                # truncated half way
+    for os_, d, label in dcsfuzz.corpus(seed=3, n_each=1, nframes=nf):
+        streams.append((d, os_, 220, 0x64, 2))
+    ctx.set_pipeline(0, -1)
+    want, offs, wres = ctx.decode_streams_pinned(streams)
+    for i in (0, 5, 12, 13, len(streams) - 1):
+        d, os_, vol, lvl, tail = streams[i]
+        exp, _ = _expect(d, os_, vol, lvl, tail)
+        assert np.array_equal(want[offs[i]:offs[i] + exp.size], exp), i
+    try:
+        for chunks, sl in ((1, 31), (1, 40), (2, 63), (1, 151), (3, 7)):
+            ctx.set_pipeline(chunks, sl)
+            got, offs2, res = ctx.decode_streams_pinned(streams)
+            assert offs2 == offs
+            assert np.array_equal(got, want), (chunks, sl)
+            assert res == wres, (chunks, sl, [(i, a, b) for i, (a, b) in enumerate(zip(res, wres)) if a != b][:3])
+    finally:
+        ctx.set_pipeline(0, 0)

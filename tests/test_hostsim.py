@@ -58,3 +58,22 @@ def test_sim_edge_cases(built):
             continue
         want, rc = orc.decode(d, os_, vol, lvl, nf + tail)
         assert np.array_equal(pcm[offs[i]:offs[i] + want.size], want), i
+
+
+def test_sim_time_slices(built):
+    """Resumed scans (frames [k*slice, (k+1)*slice) per launch) + per-slice work items give the
+    same PCM, checkpoints, statuses and checksums as the one-pass form."""
+    rng = np.random.default_rng(5)
+    streams = []
+    for seed in range(3):
+        for os_, d, label in dcsfuzz.corpus(seed + 90, n_each=2, nframes=int(rng.integers(40, 150))):
+            streams.append((d, os_, int(rng.integers(0, 256)), int(rng.integers(0, 256)), int(rng.integers(0, 4))))
+    ok = dcsfuzz.fuzz94(np.random.default_rng(1), 100, type1=1)
+    streams.append((ok[: len(ok) // 2], 0x9400, 255, 100, 2))           # truncated: fails in some slice
+    streams.append((bytes([0, 0] + [0x10] * 16), 0x9400, 255, 100, 2))  # empty
+    want = simutil.decode_streams(streams)
+    for sl in (1, 7, 31, 64, 1000):
+        got = simutil.decode_streams(streams, slice_frames=sl)
+        assert np.array_equal(got[0], want[0]), sl
+        assert got[2] == want[2], sl
+        assert np.array_equal(got[3], want[3]) and np.array_equal(got[4], want[4]), sl
