@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <thread>
 #include <vector>
@@ -179,6 +180,79 @@ static void stream_gain(const dcsb_stream_desc &d, DcsbStreamRec &r)
 }
 
 
+// ---- scan launch shape (shared by the launcher in dcsb_kernels.cu and the stream -> lane assignment below)
+// spread the streams over the SMs first (one CTA per SM), then fill the CTAs up
+void dcsb_scan_shape(int nstreams, int *spc, int *grid)
+{
+    int s = (nstreams + 147) / 148;
+    s = s > DCSB_SCAN_SPC ? DCSB_SCAN_SPC : (s < 1 ? 1 : s);
+    int g = (nstreams + s - 1) / s;
+    *spc = s;
+    *grid = g > 148 ? 148 : g;
+}
+// streams per warp in the scan's shared warps
+int dcsb_scan_lanes(int nstreams)
+{
+    if (const char *e = getenv("DCSB_SCAN_LANES")) {       // tuning override (tools/scan_sweep.py)
+        const int v = atoi(e);
+        if (v >= 1 && v <= 32) return v;
+    }
+    (void)nstreams;
+    return 2;
+}
+// how many of a CTA's stream slots get a warp of their own (the most expensive streams of the CTA;
+// the others share warps).  Measured on the bench workload: no gain -- 7 solo + 21 shared slots scan
+// in 17.5-18.1 ms against 16.4 ms with every warp shared by two streams: at 28 streams per SM the
+// scan is bound by the instructions all chains issue together as much as by the slowest chain
+// (13.1 ms alone), and more warps issue more.  Kept as a tuning knob, off by default.
+int dcsb_scan_solo(int nstreams, int spc)
+{
+    if (nstreams > 148 * DCSB_SCAN_SPC) return 0;
+    int v = 0;
+    if (const char *e = getenv("DCSB_SCAN_SOLO")) v = atoi(e);     // tuning override
+    return v < 0 ? 0 : (v > spc ? spc : v);
+}
+
+// Which stream each scan slot takes.  Slot j of CTA c is order[c * spc + j] (then grid-stride).
+// One wave: streams ranked by cost (compressed bytes ~ table steps), dealt round-robin over the
+// CTAs, so every CTA gets the same mix and its slots run from expensive to cheap -- the first
+// dcsb_scan_solo() slots walk alone, and the shared warps hold streams of about the same cost.
+// Several waves: alike streams side by side (same layout, same stream type, similar bits per frame).
+void dcsb_scan_order(DcsbPrepared *p)
+{
+    const size_t n = p->recs.size();
+    p->scan_order.resize(n);
+    std::vector<uint32_t> rank(n);
+    for (size_t i = 0; i < n; ++i) rank[i] = (uint32_t)i;
+    int spc, grid;
+    dcsb_scan_shape((int)std::min<size_t>(n, 0x7FFFFFFF), &spc, &grid);
+    if (n <= (size_t)148 * DCSB_SCAN_SPC && n > 0) {
+        std::stable_sort(rank.begin(), rank.end(), [&](uint32_t a, uint32_t b) {
+            const DcsbStreamRec &x = p->recs[a], &y = p->recs[b];
+            const uint64_t kx = x.nframes ? x.nbytes : 0, ky = y.nframes ? y.nbytes : 0;
+            return kx > ky;
+        });
+        // rank r -> CTA r % grid, slot r / grid; CTA c holds order[c * spc .. c * spc + spc) (the last CTAs may hold fewer)
+        std::vector<uint32_t> fill((size_t)grid, 0);
+        std::vector<size_t> base((size_t)grid + 1, 0);
+        for (int c = 0; c < grid; ++c) base[c + 1] = std::min(n, (size_t)(c + 1) * (size_t)spc);
+        int c = 0;
+        for (size_t r = 0; r < n; ++r) {
+            while (base[c] + fill[c] >= base[c + 1]) c = (c + 1) % grid;      // CTA full (short last CTAs): next
+            p->scan_order[base[c] + fill[c]++] = rank[r];
+            c = (c + 1) % grid;
+        }
+        return;
+    }
+    std::stable_sort(rank.begin(), rank.end(), [&](uint32_t a, uint32_t b) {
+        const DcsbStreamRec &x = p->recs[a], &y = p->recs[b];
+        const uint64_t kx = ((uint64_t)x.fmt << 40) | ((uint64_t)(x.hdr[0] >> 7) << 32) | (x.nframes ? (uint64_t)x.nbytes * 8 / x.nframes : 0);
+        const uint64_t ky = ((uint64_t)y.fmt << 40) | ((uint64_t)(y.hdr[0] >> 7) << 32) | (y.nframes ? (uint64_t)y.nbytes * 8 / y.nframes : 0);
+        return kx < ky;
+    });
+    p->scan_order = rank;
+}
+
 // Work items covering output frames [fa, fb) of every stream, in frame-major order (item k of every
 // stream before item k + 1 of any): CTAs are dispatched in index order, so the decode kernel works
 // its way through the streams at the pace the scan running beside it delivers their checkpoints.
@@ -264,16 +338,7 @@ int dcsb_prepare(const dcsb_stream_desc *descs, size_t n, DcsbPrepared *p, const
     t94.reserve(items94);
     t93.reserve(items93);
     dcsb_build_tiles(p, 0, 0xFFFFFFFFu, &t94, &t93);
-    // the scan walks 2 streams per warp in lockstep per band: put streams side by side that take the
-    // same branches and about as many table steps (same layout, same stream type, similar bits per frame)
-    p->scan_order.resize(n);
-    for (size_t i = 0; i < n; ++i) p->scan_order[i] = (uint32_t)i;
-    std::stable_sort(p->scan_order.begin(), p->scan_order.end(), [&](uint32_t a, uint32_t b) {
-        const DcsbStreamRec &x = p->recs[a], &y = p->recs[b];
-        const uint64_t kx = ((uint64_t)x.fmt << 40) | ((uint64_t)(x.hdr[0] >> 7) << 32) | (x.nframes ? (uint64_t)x.nbytes * 8 / x.nframes : 0);
-        const uint64_t ky = ((uint64_t)y.fmt << 40) | ((uint64_t)(y.hdr[0] >> 7) << 32) | (y.nframes ? (uint64_t)y.nbytes * 8 / y.nframes : 0);
-        return kx < ky;
-    });
+    dcsb_scan_order(p);
     if (ckpt > 0xFFFFFFF0ull || t94.size() + t93.size() > 0x7FFFFFF0ull || nq94 > 0x7FFFFFF0ull || n > 0x3FFFFFF0ull) return DCSB_E_ARG;
     p->nqueue94 = (int)nq94;
     p->total_frames_in = frames;

@@ -99,6 +99,7 @@ struct DcsbScanOut {
 };
 
 void dcsb_build_tables(DcsbTables *t);   // host
+#define DCSB_SCAN_SPC 28                 // most stream slots (1 KB ring each) a scan CTA holds
 
 // host-side batch layout (dcsb_host.cpp)
 #include <vector>
@@ -123,6 +124,10 @@ struct DcsbPrepared {
 int dcsb_prepare(const dcsb_stream_desc *descs, size_t n, DcsbPrepared *p, const uint8_t *in_place_base, size_t in_place_span);
 // work items covering output frames [fa, fb) of every stream (appended to t94 / t93), frame-major
 void dcsb_build_tiles(const DcsbPrepared *p, uint32_t fa, uint32_t fb, std::vector<DcsbTile> *t94, std::vector<DcsbTile> *t93);
+// scan launch shape and stream -> slot assignment (dcsb_host.cpp)
+void dcsb_scan_shape(int nstreams, int *spc, int *grid);
+int dcsb_scan_solo(int nstreams, int spc);
+void dcsb_scan_order(DcsbPrepared *p);
 // copy the streams into `slab` (p->slab_bytes bytes) at their 16-byte aligned offsets, zero padded
 void dcsb_pack_slab(const dcsb_stream_desc *descs, size_t n, const DcsbPrepared *p, uint8_t *slab);
 

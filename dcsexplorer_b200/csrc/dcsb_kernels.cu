@@ -33,7 +33,6 @@ __device__ __forceinline__ void dcsb_load_lut(uint16_t *s_lut, const DcsbTables 
 // lanes per warp keep the chains from serialising on each other's branches, while several warps
 // per scheduler fill the latency of each chain); the CTA's warps share the tables and walk
 // stream groups grid-stride.
-#define DCSB_SCAN_SPC 28
 struct DcsbSmemScan {
     __align__(16) uint8_t ring[DCSB_SCAN_SPC][DCSB_RING_BYTES];
     __align__(16) uint8_t t8[6 * DCSB_T8_CB];
@@ -43,7 +42,7 @@ struct DcsbSmemScan {
 
 __global__ void __launch_bounds__(DCSB_SCAN_SPC * 32, 1)
 dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restrict__ streams, const uint32_t *__restrict__ order,
-                 int nstreams, int lanes, int spc, const DcsbTables *__restrict__ tab, DcsbScanOut out, uint32_t f0, uint32_t f1)
+                 int nstreams, int lanes, int spc, int nsolo, const DcsbTables *__restrict__ tab, DcsbScanOut out, uint32_t f0, uint32_t f1)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     DcsbSmemScan &sm = *reinterpret_cast<DcsbSmemScan *>(smem);
@@ -58,8 +57,9 @@ dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restri
     if (threadIdx.x == 0 && out.started) atomicAdd(out.started, 1u);       // this CTA is resident (dcsb_gate_kernel)
     dcsb_load_lut(sm.lut, tab);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int slot = warp * lanes + lane;              // stream slot inside the CTA
-    if (lane >= lanes || slot >= spc) return;
+    // stream slot inside the CTA: the first nsolo slots have a warp each, the others share warps
+    const int slot = warp < nsolo ? warp : nsolo + (warp - nsolo) * lanes + lane;
+    if (lane >= (warp < nsolo ? 1 : lanes) || slot >= spc) return;
     const DcsbSmemU8 t8 = DCSB_SMEM_U8(sm.t8), t1 = DCSB_SMEM_U8(sm.t1);
     const DcsbRingPtr ring = DCSB_SMEM_U8(sm.ring[slot]);
     for (int k = blockIdx.x * spc + slot; k < nstreams; k += gridDim.x * spc) {
@@ -323,25 +323,7 @@ cudaError_t dcsb_launch_mix(bool family93, const uint8_t *slab, const DcsbStream
 }
 
 // ------------------------------------------------------------------------------------
-// streams per warp in the scan
-int dcsb_scan_lanes(int nstreams)
-{
-    if (const char *e = getenv("DCSB_SCAN_LANES")) {       // tuning override (tools/scan_sweep.py)
-        const int v = atoi(e);
-        if (v >= 1 && v <= 32) return v;
-    }
-    (void)nstreams;
-    return 2;
-}
-
-static void scan_shape(int nstreams, int &spc, int &grid)
-{
-    // spread the streams over the SMs first (one CTA per SM), then fill the CTAs up
-    spc = (nstreams + 147) / 148;
-    spc = spc > DCSB_SCAN_SPC ? DCSB_SCAN_SPC : (spc < 1 ? 1 : spc);
-    grid = (nstreams + spc - 1) / spc;
-    if (grid > 148) grid = 148;
-}
+static void scan_shape(int nstreams, int &spc, int &grid) { dcsb_scan_shape(nstreams, &spc, &grid); }
 
 int dcsb_scan_grid(int nstreams)
 {
@@ -378,7 +360,8 @@ cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, 
     const int lanes = lanes_hint > 0 ? lanes_hint : dcsb_scan_lanes(nstreams);
     int spc, grid;
     scan_shape(nstreams, spc, grid);
-    const int warps = (spc + lanes - 1) / lanes;
+    const int nsolo = dcsb_scan_solo(nstreams, spc);
+    const int warps = nsolo + (spc - nsolo + lanes - 1) / lanes;
     const size_t smem = sizeof(DcsbSmemScan);
     cudaError_t e = cudaFuncSetAttribute(dcsb_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -386,7 +369,7 @@ cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, 
     // this one (the split only changes on an idle SM)
     e = cudaFuncSetAttribute(dcsb_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    dcsb_scan_kernel<<<grid, warps * 32, smem, st>>>(slab, streams, order, nstreams, lanes, spc, tables, out, f0, f1);
+    dcsb_scan_kernel<<<grid, warps * 32, smem, st>>>(slab, streams, order, nstreams, lanes, spc, nsolo, tables, out, f0, f1);
     return cudaGetLastError();
 }
 

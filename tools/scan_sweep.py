@@ -18,10 +18,17 @@ batch = ctx.batch(streams, os_version=dx.OS94, master_volume=255, mixing_level=0
 d_pcm = torch.empty(batch.total_samples, dtype=torch.int16, device="cuda")
 st = torch.cuda.current_stream()
 ref = None
-for overlap, ctas in ((0, 3), (1, 3), (1, 2), (1, 1)):
+for overlap, ctas in ((0, 3), (1, 1)):
   ctx.set_overlap(overlap)
   os.environ["DCSB_DECODE_CTAS"] = str(ctas)
   for lanes in sys.argv[2:] or ["2"]:
+    if "s" in lanes:                  # "<solo>s<lanes>": slots with a warp of their own + streams per shared warp
+        solo, lanes = lanes.split("s")
+        os.environ["DCSB_SCAN_SOLO"] = solo
+        lanes_label = solo + "s" + lanes
+    else:
+        os.environ.pop("DCSB_SCAN_SOLO", None)
+        lanes_label = lanes
     if lanes == "0":
         os.environ.pop("DCSB_SCAN_LANES", None)
     else:
@@ -39,4 +46,4 @@ for overlap, ctas in ((0, 3), (1, 3), (1, 2), (1, 1)):
     ref = x if ref is None else ref
     print("decode CTAs/SM %d " % ctas, end="")
     print("overlap=%d lanes=%s scan %.3f ms decode %.3f ms step %.3f ms  xor %016x %s" % (
-        overlap, lanes, np.mean(ks), np.mean(kd), np.mean(kt), x, "OK" if x == ref else "MISMATCH"), flush=True)
+        overlap, lanes_label, np.mean(ks), np.mean(kd), np.mean(kt), x, "OK" if x == ref else "MISMATCH"), flush=True)
