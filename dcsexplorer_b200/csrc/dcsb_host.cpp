@@ -85,17 +85,18 @@ void dcsb_build_tables(DcsbTables *t)
     // more than `cap` output slots (the first codeword is always taken)
     const dcs_code_t *cbs[6] = { dcs94_cb1, dcs94_cb2, dcs94_cb3, dcs94_cb4, dcs94_cb5, dcs94_cb6 };
     const int ncb[6] = { NCODES(dcs94_cb1), NCODES(dcs94_cb2), NCODES(dcs94_cb3), NCODES(dcs94_cb4), NCODES(dcs94_cb5), NCODES(dcs94_cb6) };
-    for (int which = 0; which < 2; ++which) {
-        const int P = which ? DCSB_T1_PEEK : DCSB_T8_PEEK, cap = which ? 1 : 8;
-        uint8_t *dst = which ? t->t1 : t->t8;
-        for (int k = 0; k < 6; ++k)
-            for (int x = 0; x < (1 << P); ++x) {
+    for (int k = 0; k < 6; ++k)
+        for (int x = 0; x < DCSB_T8_CB; ++x) {
+            uint32_t m[2];
+            for (int which = 0; which < 2; ++which) {
+                const int P = which ? DCSB_T1_PEEK : DCSB_T8_PEEK, cap = which ? 1 : 8;
+                const int xp = x >> (DCSB_T8_PEEK - P);
                 int used = 0, slots = 0;
                 for (;;) {
                     int hit = -1;
                     for (int i = 0; i < ncb[k] && hit < 0; ++i) {
                         const int len = cbs[k][i].len;
-                        if (used + len <= P && (uint32_t)((x >> (P - used - len)) & ((1 << len) - 1)) == cbs[k][i].code) hit = i;
+                        if (used + len <= P && (uint32_t)((xp >> (P - used - len)) & ((1 << len) - 1)) == cbs[k][i].code) hit = i;
                     }
                     if (hit < 0) break;
                     const int add = (cbs[k][hit].val & 0x80) ? 2 : 1;
@@ -104,9 +105,10 @@ void dcsb_build_tables(DcsbTables *t)
                     slots += add;
                     if (slots >= cap) break;
                 }
-                dst[(k << P) + x] = (uint8_t)((slots << 4) | used);
+                m[which] = (uint32_t)((slots << 4) | used);
             }
-    }
+            t->tx[(k << DCSB_T8_PEEK) + x] = (uint16_t)((m[0] << 8) | m[1]);
+        }
 }
 
 // ======================================================================================

@@ -43,11 +43,10 @@ struct DcsbTile { uint32_t stream; uint32_t first; uint32_t count; };
 #define DCSB_LUT_XLAT    1772   // 48:  1994 type-1 band translation, 3 groups x 16: (codebook/width << 8) | scale adjust
 #define DCSB_LUT_WORDS   1820
 
-// scan: length tables of the 1994 sample codebooks (dcsb_scan94.cuh); entry = slots << 4 | bits
+// scan: length table of the 1994 sample codebooks (dcsb_scan94.cuh); entry = m8 << 8 | m1, each slots << 4 | bits
 #define DCSB_T8_PEEK 13
-#define DCSB_T8_CB   (1 << DCSB_T8_PEEK)            // multi-symbol table: entries per codebook
-#define DCSB_T1_PEEK 9
-#define DCSB_T1_CB   (1 << DCSB_T1_PEEK)            // single-codeword table: entries per codebook
+#define DCSB_T8_CB   (1 << DCSB_T8_PEEK)            // entries per codebook (16 KB)
+#define DCSB_T1_PEEK 9                              // the single-codeword part depends on the first 9 bits only
 
 struct DcsbLongCode { uint32_t code; uint8_t len; uint8_t val; uint16_t pad; };
 
@@ -63,11 +62,9 @@ struct DcsbTables {
     // 1994 fast path
     int tw_c2[64], tw_s2[64];      // butterfly twiddles pre-doubled (2cos, 2sin), partition order
     int pre_c0[64], pre_c1[64];    // pre-pass coefficients pre-doubled, natural order
-    // scan: t8[codebook][next 13 bits] = as many whole codewords as fit (at most 8 output slots),
-    // t1[codebook][next 9 bits] = exactly one codeword; low nibble = bits consumed, high nibble =
-    // output slots covered
-    uint8_t t8[6 * DCSB_T8_CB];
-    uint8_t t1[6 * DCSB_T1_CB];
+    // scan: tx[codebook][next 13 bits] = m8 << 8 | m1; m8 = as many whole codewords as fit (at most 8
+    // output slots), m1 = exactly one codeword; low nibble = bits consumed, high nibble = output slots covered
+    uint16_t tx[6 * DCSB_T8_CB];
 };
 
 #define DCSB_SCAN_DONE 0x80000000u

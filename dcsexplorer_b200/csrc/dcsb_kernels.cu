@@ -35,10 +35,13 @@ __device__ __forceinline__ void dcsb_load_lut(uint16_t *s_lut, const DcsbTables 
 // stream groups grid-stride.
 struct DcsbSmemScan {
     __align__(16) uint8_t ring[DCSB_SCAN_SPC][DCSB_RING_BYTES];
-    __align__(16) uint8_t t8[6 * DCSB_T8_CB];
-    __align__(16) uint8_t t1[6 * DCSB_T1_CB];
     uint16_t lut[DCSB_LUT_WORDS];
+    uint32_t dtab[DCSB_DTAB_WORDS];            // band descriptors by (stream type, half density, band, band type)
+    uint32_t desc[DCSB_SCAN_SPC][17];          // per stream slot: band descriptors of the current frame (+ a zero sentinel)
 };
+// the length table follows at the next multiple of 16 KB of the shared window (dcsb_tx_load)
+#define DCSB_TX_BYTES (6 * DCSB_T8_CB * 2)
+#define DCSB_SCAN_SMEM (sizeof(DcsbSmemScan) + DCSB_TX_BYTES + 16384)
 
 __global__ void __launch_bounds__(DCSB_SCAN_SPC * 32, 1)
 dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restrict__ streams, const uint32_t *__restrict__ order,
@@ -46,25 +49,31 @@ dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restri
 {
     extern __shared__ __align__(16) uint32_t smem[];
     DcsbSmemScan &sm = *reinterpret_cast<DcsbSmemScan *>(smem);
+    const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t tx = (s_base + (uint32_t)sizeof(DcsbSmemScan) + 16383u) & ~16383u;
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(tab->t8);
-        uint4 *dst = reinterpret_cast<uint4 *>(sm.t8);
-        for (int i = threadIdx.x; i < 6 * DCSB_T8_CB / 16; i += blockDim.x) dst[i] = __ldg(src + i);
-        src = reinterpret_cast<const uint4 *>(tab->t1);
-        dst = reinterpret_cast<uint4 *>(sm.t1);
-        for (int i = threadIdx.x; i < 6 * DCSB_T1_CB / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+        const uint4 *src = reinterpret_cast<const uint4 *>(tab->tx);
+        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(smem) + (tx - s_base));
+        for (int i = threadIdx.x; i < DCSB_TX_BYTES / 16; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     if (threadIdx.x == 0 && out.started) atomicAdd(out.started, 1u);       // this CTA is resident (dcsb_gate_kernel)
     dcsb_load_lut(sm.lut, tab);
+    for (int i = threadIdx.x; i < DCSB_DTAB_WORDS; i += blockDim.x) sm.dtab[i] = dcsb_dtab_entry(sm.lut, i);
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // stream slot inside the CTA: the first nsolo slots have a warp each, the others share warps
     const int slot = warp < nsolo ? warp : nsolo + (warp - nsolo) * lanes + lane;
     if (lane >= (warp < nsolo ? 1 : lanes) || slot >= spc) return;
-    const DcsbSmemU8 t8 = DCSB_SMEM_U8(sm.t8), t1 = DCSB_SMEM_U8(sm.t1);
-    const DcsbRingPtr ring = DCSB_SMEM_U8(sm.ring[slot]);
+#if DCSB_DEVICE_PASS
+    const DcsbRingPtr ring = (uint32_t)__cvta_generic_to_shared(sm.ring[slot]);
+    const DcsbTxBase txb = tx;
+#else       // (nvcc's host pass only type-checks this body)
+    const DcsbRingPtr ring = sm.ring[slot];
+    const DcsbTxBase txb = reinterpret_cast<const uint8_t *>(smem) + (tx - s_base);
+#endif
     for (int k = blockIdx.x * spc + slot; k < nstreams; k += gridDim.x * spc) {
         const int si = order ? (int)order[k] : k;
-        if (streams[si].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab, streams, si, tab, sm.lut, t8, t1, ring, out, f0, f1);
+        if (streams[si].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab, streams, si, tab, sm.lut, txb, sm.dtab, ring, sm.desc[slot], out, f0, f1);
         else dcsb_scan_stream(slab, streams, si, tab, sm.lut, out, f0, f1);
     }
 }
@@ -362,7 +371,7 @@ cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, 
     scan_shape(nstreams, spc, grid);
     const int nsolo = dcsb_scan_solo(nstreams, spc);
     const int warps = nsolo + (spc - nsolo + lanes - 1) / lanes;
-    const size_t smem = sizeof(DcsbSmemScan);
+    const size_t smem = DCSB_SCAN_SMEM;
     cudaError_t e = cudaFuncSetAttribute(dcsb_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     // keep the SM at its largest shared-memory split, so that CTAs of the other kernel can join
