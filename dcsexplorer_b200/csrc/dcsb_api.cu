@@ -212,7 +212,7 @@ extern "C" int dcsb_batch_decode(dcsb_batch *b, void *d_pcm, void *cuda_stream)
         CK(cudaStreamWaitEvent(ctx->aux, b->ev[0], 0), "stream wait");
         CK(dcsb_launch_scan(b->d_slab, b->d_recs, b->d_order, (int)b->n, 0, ctx->d_tables, so, ctx->aux), "scan kernel launch");
         CK(cudaEventRecord(b->ev[1], ctx->aux), "event");
-        CK(dcsb_launch_gate(so, dcsb_scan_grid((int)b->n), st), "gate kernel launch");
+        CK(dcsb_launch_gate(so, dcsb_scan_grid((int)b->n, 0), st), "gate kernel launch");
         CK(cudaEventRecord(b->ev[3], st), "event");
         CK(dcsb_launch_decode_queue(b->d_slab, b->d_recs, (int)b->n, b->nqueue94, ctx->d_tables, so, pcm, b->d_checksums, st), "decode kernel launch");
         CK(dcsb_launch_decode(b->d_slab, b->d_recs, b->d_tiles + b->ntiles94, 0, b->ntiles93, ctx->d_tables, so,
@@ -353,7 +353,7 @@ static DcsbTrace g_trace;
 #define ENS(buf, bytes, host, what) do { cudaError_t e_ = (buf).ensure((bytes), (host)); if (e_ != cudaSuccess) return fail(ctx, DCSB_E_NOMEM, what, e_); } while (0)
 
 // phase 1 of a lane: lay the chunk out, plan its time slices, upload it (on the context's upload stream)
-static int lane_upload(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs, bool pcm_pinned_packed)
+static int lane_upload(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs, bool pcm_pinned_packed, size_t total_streams)
 {
     const size_t n = l.count;
     const dcsb_stream_desc *d = descs + l.first;
@@ -374,6 +374,7 @@ static int lane_upload(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs
         sum += d[i].nbytes;
     }
     const bool in_place = have_all && n && (uint64_t)(hi - lo) <= sum + sum / 4 + 4096 && is_pinned(lo) && is_pinned(hi - 1);
+    l.prep.concurrent_streams = total_streams;
     int rc = dcsb_prepare(d, n, &l.prep, in_place ? lo : nullptr, in_place ? (size_t)(hi - lo) : 0);
     if (rc != DCSB_OK) return fail(ctx, rc, "dcsb_decode_streams: unknown os_version or batch too large");
     const DcsbPrepared &p = l.prep;
@@ -470,7 +471,7 @@ static int lane_upload(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs
 }
 
 // phase 2 of a lane: kernels of slice k (the whole chunk when it is not sliced) and the copy of its PCM
-static int lane_slice(dcsb_ctx *ctx, DcsbLane &l, uint32_t k, int16_t *pcm_out, int scan_lanes)
+static int lane_slice(dcsb_ctx *ctx, DcsbLane &l, uint32_t k, int16_t *pcm_out, int concurrent)
 {
     const size_t n = l.count;
     if (n == 0 || k >= l.nslices) return DCSB_OK;
@@ -486,7 +487,7 @@ static int lane_slice(dcsb_ctx *ctx, DcsbLane &l, uint32_t k, int16_t *pcm_out, 
     if (l.slice) {
         const uint32_t U = p.recs[0].out_frames;
         const uint32_t fa = k * l.slice, fb = k + 1 == l.nslices ? U : (k + 1) * l.slice;
-        CK(dcsb_launch_scan(slab, recs, (const uint32_t *)l.d_order.p, (int)n, scan_lanes, ctx->d_tables, so, l.st, fa,
+        CK(dcsb_launch_scan(slab, recs, (const uint32_t *)l.d_order.p, (int)n, concurrent, ctx->d_tables, so, l.st, fa,
                             k + 1 == l.nslices ? 0xFFFFFFFFu : fb), "scan kernel launch");
         g_trace.mark(lane_id, (int)k, "scan", l.st);
         CK(dcsb_launch_decode(slab, recs, tiles + l.sl_off[2 * k], (int)(l.sl_off[2 * k + 1] - l.sl_off[2 * k]),
@@ -508,14 +509,14 @@ static int lane_slice(dcsb_ctx *ctx, DcsbLane &l, uint32_t k, int16_t *pcm_out, 
         so.queue = (unsigned long long *)l.d_queue.p;
         CK(cudaStreamWaitEvent(l.aux, l.ev_go, 0), "stream wait");
         CK(cudaStreamWaitEvent(l.aux, l.ev_scan, 0), "stream wait");
-        CK(dcsb_launch_scan(slab, recs, (const uint32_t *)l.d_order.p, (int)n, scan_lanes, ctx->d_tables, so, l.aux), "scan kernel launch");
+        CK(dcsb_launch_scan(slab, recs, (const uint32_t *)l.d_order.p, (int)n, concurrent, ctx->d_tables, so, l.aux), "scan kernel launch");
         CK(cudaEventRecord(l.ev_scan, l.aux), "event");
-        CK(dcsb_launch_gate(so, dcsb_scan_grid((int)n), l.st), "gate kernel launch");
+        CK(dcsb_launch_gate(so, dcsb_scan_grid((int)n, concurrent), l.st), "gate kernel launch");
         CK(dcsb_launch_decode_queue(slab, recs, (int)n, p.nqueue94, ctx->d_tables, so, d_pcm, d_csum, l.st), "decode kernel launch");
         CK(dcsb_launch_decode(slab, recs, tiles + p.ntiles94, 0, p.ntiles93, ctx->d_tables, so, d_pcm, d_csum, l.st), "decode kernel launch");
         CK(cudaStreamWaitEvent(l.st, l.ev_scan, 0), "stream wait");
     } else {
-        CK(dcsb_launch_scan(slab, recs, (const uint32_t *)l.d_order.p, (int)n, scan_lanes, ctx->d_tables, so, l.st), "scan kernel launch");
+        CK(dcsb_launch_scan(slab, recs, (const uint32_t *)l.d_order.p, (int)n, concurrent, ctx->d_tables, so, l.st), "scan kernel launch");
         CK(dcsb_launch_decode(slab, recs, tiles, p.ntiles94, p.ntiles93, ctx->d_tables, so, d_pcm, d_csum, l.st), "decode kernel launch");
     }
     g_trace.mark(lane_id, -1, "kernels", l.st);
@@ -568,25 +569,34 @@ extern "C" int dcsb_decode_streams(dcsb_ctx *ctx, const dcsb_stream_desc *descs,
     if (g_trace.on) { cudaEventCreate(&g_trace.t0); cudaEventRecord(g_trace.t0, ctx->up); }
     // chunks of about equal PCM size; few enough that every chunk still fills the GPU
     const uint64_t total = off[n];
-    int nchunks = (int)std::min<uint64_t>(DCSB_DEFAULT_LANES, std::max<uint64_t>(1, total / (48ull << 20)));
+    // (a batch that cannot be cut in time -- streams of different lengths, or a pageable output -- gets
+    // more, smaller chunks instead: the first PCM copy can only start when a whole chunk is decoded)
+    bool all_uniform = direct && ctx->slice_frames >= 0;
+    for (size_t i = 1; i < n && all_uniform; ++i) all_uniform = off[i + 1] - off[i] == off[1] - off[0];
+    int nchunks = (int)std::min<uint64_t>(all_uniform ? DCSB_DEFAULT_LANES : DCSB_MAX_LANES, std::max<uint64_t>(1, total / (48ull << 20)));
     nchunks = (int)std::min<size_t>((size_t)nchunks, std::max<size_t>(1, n / 64));
     if (ctx->max_chunks > 0) nchunks = (int)std::min<size_t>((size_t)ctx->max_chunks, n);
     int used = 0, rc = DCSB_OK;
     size_t i0 = 0;
     uint32_t max_slices = 0;
+    // the first chunks are smaller (weights 1, 2, 3, 3, ...): the first PCM can only leave once a chunk is
+    // uploaded and its first slice scanned, and until then the copy engine idles
+    uint64_t wsum = 0, wacc = 0;
+    for (int c = 0; c < nchunks; ++c) wsum += (uint64_t)std::min(c + 1, 3);
     for (int c = 0; c < nchunks && i0 < n && rc == DCSB_OK; ++c) {
-        const uint64_t goal = total * (uint64_t)(c + 1) / (uint64_t)nchunks;
+        wacc += (uint64_t)std::min(c + 1, 3);
+        const uint64_t goal = total / wsum * wacc;
         size_t i1 = i0 + 1;
         while (i1 < n && (c == nchunks - 1 || off[i1] < goal)) ++i1;
         DcsbLane &l = ctx->lanes[used++];
         l.first = i0;
         l.count = i1 - i0;
         l.pcm_base = off[i0];
-        rc = lane_upload(ctx, l, descs, direct);
+        rc = lane_upload(ctx, l, descs, direct, n);
         max_slices = std::max(max_slices, l.nslices);
         i0 = i1;
     }
-    const int scan_lanes = dcsb_scan_lanes((int)std::min<size_t>(n, 0x7FFFFFFF));
+    const int concurrent = (int)std::min<size_t>(n, 0x7FFFFFFF);     // (concurrent streams: all chunks scan side by side)
     // submit the (chunk, slice) work in the order it is expected to become ready: chunk c is uploaded
     // after the chunks before it (~45 GB/s), its slices then follow each other at the pace of the scan
     // chain (~14 us per frame with the chip full)
@@ -603,7 +613,7 @@ extern "C" int dcsb_decode_streams(dcsb_ctx *ctx, const dcsb_stream_desc *descs,
     (void)max_slices;
     for (const Job &j : jobs) {
         if (rc != DCSB_OK) break;
-        rc = lane_slice(ctx, ctx->lanes[j.c], j.k, pcm_out, scan_lanes);
+        rc = lane_slice(ctx, ctx->lanes[j.c], j.k, pcm_out, concurrent);
     }
     for (int c = 0; c < used && rc == DCSB_OK; ++c) rc = lane_results(ctx, ctx->lanes[c]);
     // drain

@@ -183,16 +183,23 @@ static void stream_gain(const dcsb_stream_desc &d, DcsbStreamRec &r)
 
 
 // ---- scan launch shape (shared by the launcher in dcsb_kernels.cu and the stream -> lane assignment below)
-// spread the streams over the SMs first (one CTA per SM), then fill the CTAs up
-void dcsb_scan_shape(int nstreams, int *spc, int *grid)
+// spread the streams over the SMs first (one CTA per SM), then fill the CTAs up.  `concurrent` = the
+// streams of all the scans that run side by side (a scan CTA's tables fill most of an SM's shared
+// memory: there is room for one per SM, so the launches of a pipelined call share the 148 between them)
+void dcsb_scan_shape(int nstreams, int concurrent, int *spc, int *grid)
 {
-    int s = (nstreams + 147) / 148;
+    if (concurrent < nstreams) concurrent = nstreams;
+    int s = (concurrent + 147) / 148;
     s = s > DCSB_SCAN_SPC ? DCSB_SCAN_SPC : (s < 1 ? 1 : s);
     int g = (nstreams + s - 1) / s;
     *spc = s;
     *grid = g > 148 ? 148 : g;
 }
-// streams per warp in the scan's shared warps
+// streams per warp in the scan.  Every stream is its own dependent chain and issues its own
+// instructions (the lanes of a warp take different branches almost all the time), so this only
+// trades warps per scheduler against the cost of switching between a warp's diverged lanes.
+// Measured on the bench workload (28 streams per SM), scan alone / beside the decode kernel:
+// 2: 14.6 / 17.8 ms, 3: 14.2 / 17.1, 4: 14.2 / 16.8, 5: 14.8 / 17.6, 6: 14.6 / 17.1, 8: 15.5 / 18.6.
 int dcsb_scan_lanes(int nstreams)
 {
     if (const char *e = getenv("DCSB_SCAN_LANES")) {       // tuning override (tools/scan_sweep.py)
@@ -200,7 +207,7 @@ int dcsb_scan_lanes(int nstreams)
         if (v >= 1 && v <= 32) return v;
     }
     (void)nstreams;
-    return 2;
+    return 4;
 }
 // how many of a CTA's stream slots get a warp of their own (the most expensive streams of the CTA;
 // the others share warps).  Measured on the bench workload: no gain -- 7 solo + 21 shared slots scan
@@ -227,7 +234,7 @@ void dcsb_scan_order(DcsbPrepared *p)
     std::vector<uint32_t> rank(n);
     for (size_t i = 0; i < n; ++i) rank[i] = (uint32_t)i;
     int spc, grid;
-    dcsb_scan_shape((int)std::min<size_t>(n, 0x7FFFFFFF), &spc, &grid);
+    dcsb_scan_shape((int)std::min<size_t>(n, 0x7FFFFFFF), (int)std::min<size_t>(p->concurrent_streams, 0x7FFFFFFF), &spc, &grid);
     if (n <= (size_t)148 * DCSB_SCAN_SPC && n > 0) {
         std::stable_sort(rank.begin(), rank.end(), [&](uint32_t a, uint32_t b) {
             const DcsbStreamRec &x = p->recs[a], &y = p->recs[b];
@@ -281,6 +288,7 @@ void dcsb_build_tiles(const DcsbPrepared *p, uint32_t fa, uint32_t fb, std::vect
 
 int dcsb_prepare(const dcsb_stream_desc *descs, size_t n, DcsbPrepared *p, const uint8_t *in_place_base, size_t in_place_span)
 {
+    if (p->concurrent_streams < n) p->concurrent_streams = n;
     p->recs.resize(n);
     p->host_status.assign(n, 0);
     p->tiles.clear();

@@ -105,6 +105,7 @@ struct DcsbPrepared {
     std::vector<DcsbStreamRec> recs;
     std::vector<int32_t> host_status;     // host-side rejections (0 = let the scan decide)
     std::vector<DcsbTile> tiles;          // 1994-family items first, then 1993-family tiles
+    size_t concurrent_streams = 0;        // in: streams of all scans running side by side (0 = this batch alone)
     std::vector<uint32_t> scan_order;     // streams in the order the scan assigns them to lanes: alike streams side by side
     int ntiles94 = 0, ntiles93 = 0;
     uint32_t item_len = 31;               // output frames per 1994-family work item
@@ -122,25 +123,23 @@ int dcsb_prepare(const dcsb_stream_desc *descs, size_t n, DcsbPrepared *p, const
 // work items covering output frames [fa, fb) of every stream (appended to t94 / t93), frame-major
 void dcsb_build_tiles(const DcsbPrepared *p, uint32_t fa, uint32_t fb, std::vector<DcsbTile> *t94, std::vector<DcsbTile> *t93);
 // scan launch shape and stream -> slot assignment (dcsb_host.cpp)
-void dcsb_scan_shape(int nstreams, int *spc, int *grid);
+void dcsb_scan_shape(int nstreams, int concurrent, int *spc, int *grid);
 int dcsb_scan_solo(int nstreams, int spc);
 void dcsb_scan_order(DcsbPrepared *p);
 // copy the streams into `slab` (p->slab_bytes bytes) at their 16-byte aligned offsets, zero padded
 void dcsb_pack_slab(const dcsb_stream_desc *descs, size_t n, const DcsbPrepared *p, uint8_t *slab);
 
-// lanes_hint: streams per warp (0 = choose from nstreams).  A caller that launches several scans
-// side by side passes dcsb_scan_lanes(total streams) so that all of them fit on the chip at once
-// (a scan CTA's tables fill an SM's shared memory).
+// concurrent: streams of all the scans launched side by side (0 = this launch alone), see dcsb_scan_shape
 // order: device array of nstreams stream indices (NULL = identity): which stream each scan lane takes
 // [f0, f1): frames of every stream this launch walks; f0 > 0 resumes from the checkpoints the launch
 // for [.., f0) left (time-sliced chunks of dcsb_decode_streams)
-cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, const uint32_t *order, int nstreams, int lanes_hint,
+cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, const uint32_t *order, int nstreams, int concurrent,
                              const DcsbTables *tables, DcsbScanOut out, cudaStream_t st, uint32_t f0 = 0, uint32_t f1 = 0xFFFFFFFFu);
 int dcsb_scan_lanes(int nstreams);       // streams per warp the scan launch uses (1..32)
 // tiles[0..ntiles94) use the 1994 transform, tiles[ntiles94..ntiles94+ntiles93) the 1993 one
 // enqueue a one-thread kernel that returns once `ctas` scan CTAs are resident (scan.started)
 cudaError_t dcsb_launch_gate(DcsbScanOut scan, int ctas, cudaStream_t st);
-int dcsb_scan_grid(int nstreams);        // CTAs dcsb_launch_scan uses
+int dcsb_scan_grid(int nstreams, int concurrent);   // CTAs dcsb_launch_scan uses
 // persistent decode over the scan's ready queue (1994-layout streams, overlapped mode)
 cudaError_t dcsb_launch_decode_queue(const uint8_t *slab, const DcsbStreamRec *streams, int nstreams, int nitems,
                                      const DcsbTables *tables, DcsbScanOut scan, int16_t *pcm,

@@ -332,12 +332,12 @@ cudaError_t dcsb_launch_mix(bool family93, const uint8_t *slab, const DcsbStream
 }
 
 // ------------------------------------------------------------------------------------
-static void scan_shape(int nstreams, int &spc, int &grid) { dcsb_scan_shape(nstreams, &spc, &grid); }
+static void scan_shape(int nstreams, int concurrent, int &spc, int &grid) { dcsb_scan_shape(nstreams, concurrent, &spc, &grid); }
 
-int dcsb_scan_grid(int nstreams)
+int dcsb_scan_grid(int nstreams, int concurrent)
 {
     int spc, grid;
-    scan_shape(nstreams, spc, grid);
+    scan_shape(nstreams, concurrent, spc, grid);
     return nstreams > 0 ? grid : 0;
 }
 
@@ -362,13 +362,13 @@ cudaError_t dcsb_launch_gate(DcsbScanOut scan, int ctas, cudaStream_t st)
     return cudaGetLastError();
 }
 
-cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, const uint32_t *order, int nstreams, int lanes_hint,
+cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, const uint32_t *order, int nstreams, int concurrent,
                              const DcsbTables *tables, DcsbScanOut out, cudaStream_t st, uint32_t f0, uint32_t f1)
 {
     if (nstreams <= 0) return cudaSuccess;
-    const int lanes = lanes_hint > 0 ? lanes_hint : dcsb_scan_lanes(nstreams);
+    const int lanes = dcsb_scan_lanes(nstreams);
     int spc, grid;
-    scan_shape(nstreams, spc, grid);
+    scan_shape(nstreams, concurrent, spc, grid);
     const int nsolo = dcsb_scan_solo(nstreams, spc);
     const int warps = nsolo + (spc - nsolo + lanes - 1) / lanes;
     const size_t smem = DCSB_SCAN_SMEM;
