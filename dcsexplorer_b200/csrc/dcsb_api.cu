@@ -391,9 +391,23 @@ static int lane_upload(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs
             if (ctx->slice_frames > 0) l.slice = (uint32_t)ctx->slice_frames;
             else if (U >= 256) l.slice = (((U + 7) / 8 + p.item_len - 1) / p.item_len) * p.item_len;     // ~8 slices of whole work items
             if (l.slice >= U) l.slice = 0;
-            if (l.slice) l.nslices = (U + l.slice - 1) / l.slice;
-            if (l.nslices > 64) { l.slice = (U + 63) / 64; l.nslices = (U + l.slice - 1) / l.slice; }
+            if (l.slice && (U + l.slice - 1) / l.slice > 64) l.slice = (U + 63) / 64;
         }
+    }
+    // slice boundaries.  Automatic slicing starts with short slices (32, 32, 64, 64, 128 frames): the rate at
+    // which PCM is produced is set by how many streams are being scanned, not by the slice length, so short
+    // first slices only bring the first copies forward while the later chunks are still being uploaded
+    l.sl_bound.clear();
+    l.sl_bound.push_back(0);
+    if (l.slice) {
+        const uint32_t U = p.recs[0].out_frames;
+        uint32_t f = 0;
+        if (ctx->slice_frames == 0)
+            for (uint32_t len : { 32u, 32u, 64u, 64u, 128u })
+                if (f + len + l.slice <= U) { f += len; l.sl_bound.push_back(f); }
+        while (f + l.slice < U) { f += l.slice; l.sl_bound.push_back(f); }
+        l.sl_bound.push_back(U);
+        l.nslices = (uint32_t)l.sl_bound.size() - 1;
     }
     l.sl_off.clear();
     if (l.slice) {
@@ -402,7 +416,7 @@ static int lane_upload(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs
         for (uint32_t k = 0; k < l.nslices; ++k) {
             t93.clear();
             l.sl_off.push_back(l.slice_tiles.size());
-            dcsb_build_tiles(&p, k * l.slice, k + 1 == l.nslices ? 0xFFFFFFFFu : (k + 1) * l.slice, &l.slice_tiles, &t93);
+            dcsb_build_tiles(&p, l.sl_bound[k], k + 1 == l.nslices ? 0xFFFFFFFFu : l.sl_bound[k + 1], &l.slice_tiles, &t93);
             l.sl_off.push_back(l.slice_tiles.size());
             l.slice_tiles.insert(l.slice_tiles.end(), t93.begin(), t93.end());
         }
@@ -486,7 +500,7 @@ static int lane_slice(dcsb_ctx *ctx, DcsbLane &l, uint32_t k, int16_t *pcm_out, 
                     (uint32_t *)l.d_nplay.p, (uint32_t *)l.d_endbits.p, (uint8_t *)l.d_stopband.p, nullptr, nullptr, nullptr, nullptr, nullptr };
     if (l.slice) {
         const uint32_t U = p.recs[0].out_frames;
-        const uint32_t fa = k * l.slice, fb = k + 1 == l.nslices ? U : (k + 1) * l.slice;
+        const uint32_t fa = l.sl_bound[k], fb = l.sl_bound[k + 1];
         CK(dcsb_launch_scan(slab, recs, (const uint32_t *)l.d_order.p, (int)n, concurrent, ctx->d_tables, so, l.st, fa,
                             k + 1 == l.nslices ? 0xFFFFFFFFu : fb), "scan kernel launch");
         g_trace.mark(lane_id, (int)k, "scan", l.st);
@@ -600,20 +614,36 @@ extern "C" int dcsb_decode_streams(dcsb_ctx *ctx, const dcsb_stream_desc *descs,
     // submit the (chunk, slice) work in the order it is expected to become ready: chunk c is uploaded
     // after the chunks before it (~45 GB/s), its slices then follow each other at the pace of the scan
     // chain (~14 us per frame with the chip full)
-    struct Job { double ready; int c; uint32_t k; };
+    struct Job { double ready, start; int c; uint32_t k; int concurrent; };
     std::vector<Job> jobs;
+    std::vector<double> up_done((size_t)used, 0.0);
     double up_ms = 0.2;
     for (int c = 0; c < used; ++c) {
         const DcsbLane &l = ctx->lanes[c];
         up_ms += (double)l.prep.slab_bytes / 45e6;
-        const double frames = l.slice ? (double)l.slice : (l.count ? (double)l.prep.total_frames_in / (double)l.count : 0.0);
-        for (uint32_t k = 0; k < l.nslices; ++k) jobs.push_back(Job{ up_ms + (k + 1) * (frames * 0.014 + 0.3), c, k });
+        up_done[c] = up_ms;
+        double t = up_ms;
+        for (uint32_t k = 0; k < l.nslices; ++k) {
+            const double frames = l.slice ? (double)(l.sl_bound[k + 1] - l.sl_bound[k]) : (l.count ? (double)l.prep.total_frames_in / (double)l.count : 0.0);
+            const double t_slice = frames * 0.012 + 0.15;
+            jobs.push_back(Job{ t + t_slice, t, c, k, 0 });
+            t += t_slice;
+        }
     }
     std::stable_sort(jobs.begin(), jobs.end(), [](const Job &a, const Job &b) { return a.ready < b.ready; });
+    // a scan launch shares the SMs (one scan CTA each) with the scans of the chunks that are on the device by
+    // then: the first chunks' first slices spread over the whole chip (short chains: the first PCM leaves early),
+    // later launches pack their streams so that all chunks fit side by side
+    for (Job &j : jobs) {
+        size_t live = 0;
+        for (int c = 0; c < used; ++c) if (up_done[c] <= j.start + 1e-9) live += ctx->lanes[c].count;
+        j.concurrent = (int)std::min<size_t>(std::max(live, ctx->lanes[j.c].count), 0x7FFFFFFF);
+    }
     (void)max_slices;
+    (void)concurrent;
     for (const Job &j : jobs) {
         if (rc != DCSB_OK) break;
-        rc = lane_slice(ctx, ctx->lanes[j.c], j.k, pcm_out, concurrent);
+        rc = lane_slice(ctx, ctx->lanes[j.c], j.k, pcm_out, j.concurrent);
     }
     for (int c = 0; c < used && rc == DCSB_OK; ++c) rc = lane_results(ctx, ctx->lanes[c]);
     // drain

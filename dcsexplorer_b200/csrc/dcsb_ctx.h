@@ -42,6 +42,7 @@ struct DcsbLane {
     std::vector<cudaEvent_t> ev_slices;                      // slice k decoded (the PCM copy of the slice waits for it)
     std::vector<size_t> sl_off;                              // first work item of slice k in slice_tiles: 2 entries per slice (1994, 1993 family) + end
     uint32_t slice = 0, nslices = 1;                         // frames per time slice (0 = not sliced)
+    std::vector<uint32_t> sl_bound;                          // slice k = output frames [sl_bound[k], sl_bound[k + 1])
     size_t first = 0, count = 0;
     uint64_t pcm_base = 0;                                   // sample offset of the chunk in the packed output
     bool direct_pcm = false;
