@@ -201,6 +201,18 @@ def cpu_reference_run(streams, vol, lvl, tail, threads, budget_streams):
 
 # ------------------------------------------------------------------------------------------
 def main():
+    # the contract is ONE JSON line on stdout: libraries that write to fd 1 themselves (NCCL prints its
+    # version there) are sent to stderr, the line goes to the real stdout
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    try:
+        _main(real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -241,7 +253,7 @@ def main():
                 "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": thr, "kind": kind, "sample": sample},
                 "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out)
         return
 
     # ---------------- our arm
@@ -415,7 +427,8 @@ def main():
         if not a.no_cpu_baseline:
             v, kind, thr, sample, secs = cpu_reference_run(streams, vol, lvl, tail, ncores, min(768, len(streams)))
             line["cpu_baseline"] = {"value": v, "unit": "Msamples/s", "cores": thr, "kind": kind, "sample": sample}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out)
+        out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
