@@ -353,7 +353,10 @@ static DcsbTrace g_trace;
 #define ENS(buf, bytes, host, what) do { cudaError_t e_ = (buf).ensure((bytes), (host)); if (e_ != cudaSuccess) return fail(ctx, DCSB_E_NOMEM, what, e_); } while (0)
 
 // phase 1 of a lane: lay the chunk out, plan its time slices, upload it (on the context's upload stream)
-static int lane_upload(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs, bool pcm_pinned_packed, size_t total_streams)
+// pcm_pinned: the caller's PCM buffer is page-locked (PCM is copied straight into it); pcm_packed: stream
+// i's PCM starts where stream i - 1's ends; dst_off[i] = sample offset of stream i in the caller's buffer
+static int lane_upload(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs, bool pcm_pinned, bool pcm_packed,
+                       const uint64_t *dst_off, size_t total_streams)
 {
     const size_t n = l.count;
     const dcsb_stream_desc *d = descs + l.first;
@@ -379,19 +382,29 @@ static int lane_upload(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs
     if (rc != DCSB_OK) return fail(ctx, rc, "dcsb_decode_streams: unknown os_version or batch too large");
     const DcsbPrepared &p = l.prep;
     const uint64_t ck = std::max<uint64_t>(1, p.total_checkpoints), nn = std::max<size_t>(1, n);
-    // time slices
+    // Time slices.  Frames [a, b) of every stream of the chunk are scanned, decoded and copied out together:
+    // when all streams render the same number of frames into a packed buffer that is ONE strided copy
+    // (pitch = stream length), otherwise one batched copy (cudaMemcpyBatchAsync) of a piece per stream.
+    // The scan of a 10 s stream is a 10+ ms dependent chain whatever the chunk size; sliced, the first PCM
+    // leaves after a fraction of it and the copy engine stays busy from then on.
     l.slice = 0;
     l.nslices = 1;
-    l.direct_pcm = pcm_pinned_packed;
-    if (pcm_pinned_packed && n && ctx->slice_frames >= 0) {
-        const uint32_t U = p.recs[0].out_frames;
-        bool uniform = U > 1 && (uint64_t)U * 480 <= 0x7FFFFFFFull;
-        for (size_t i = 1; i < n && uniform; ++i) uniform = p.recs[i].out_frames == U;
-        if (uniform) {
-            if (ctx->slice_frames > 0) l.slice = (uint32_t)ctx->slice_frames;
-            else if (U >= 256) l.slice = (((U + 7) / 8 + p.item_len - 1) / p.item_len) * p.item_len;     // ~8 slices of whole work items
-            if (l.slice >= U) l.slice = 0;
-            if (l.slice && (U + l.slice - 1) / l.slice > 64) l.slice = (U + 63) / 64;
+    l.direct_pcm = pcm_pinned && pcm_packed;
+    l.copy2d = false;
+    l.dst_off.clear();
+    uint32_t U = 0;                               // longest stream of the chunk, in output frames
+    for (size_t i = 0; i < n; ++i) U = std::max(U, p.recs[i].out_frames);
+    if (pcm_pinned && n && ctx->slice_frames >= 0 && U > 1) {
+        bool uniform = pcm_packed && (uint64_t)U * 480 <= 0x7FFFFFFFull;
+        for (size_t i = 0; i < n && uniform; ++i) uniform = p.recs[i].out_frames == U;
+        if (ctx->slice_frames > 0) l.slice = (uint32_t)ctx->slice_frames;
+        else if (U >= 256) l.slice = (((U + 7) / 8 + p.item_len - 1) / p.item_len) * p.item_len;     // ~8 slices of whole work items
+        if (l.slice >= U) l.slice = 0;
+        if (l.slice && (U + l.slice - 1) / l.slice > 64) l.slice = (U + 63) / 64;
+        if (l.slice) {
+            l.copy2d = uniform;
+            l.direct_pcm = true;
+            if (!uniform) l.dst_off.assign(dst_off + l.first, dst_off + l.first + n);
         }
     }
     // slice boundaries.  Automatic slicing starts with short slices (32, 32, 64, 64, 128 frames): the rate at
@@ -400,7 +413,6 @@ static int lane_upload(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs
     l.sl_bound.clear();
     l.sl_bound.push_back(0);
     if (l.slice) {
-        const uint32_t U = p.recs[0].out_frames;
         uint32_t f = 0;
         if (ctx->slice_frames == 0)
             for (uint32_t len : { 32u, 32u, 64u, 64u, 128u })
@@ -499,7 +511,7 @@ static int lane_slice(dcsb_ctx *ctx, DcsbLane &l, uint32_t k, int16_t *pcm_out, 
     DcsbScanOut so{ (uint32_t *)l.d_bitpos.p, (uint2 *)l.d_bt.p, (uint16_t *)l.d_hdrbits.p, (int32_t *)l.d_status.p,
                     (uint32_t *)l.d_nplay.p, (uint32_t *)l.d_endbits.p, (uint8_t *)l.d_stopband.p, nullptr, nullptr, nullptr, nullptr, nullptr };
     if (l.slice) {
-        const uint32_t U = p.recs[0].out_frames;
+        const uint32_t U = l.sl_bound.back();
         const uint32_t fa = l.sl_bound[k], fb = l.sl_bound[k + 1];
         CK(dcsb_launch_scan(slab, recs, (const uint32_t *)l.d_order.p, (int)n, concurrent, ctx->d_tables, so, l.st, fa,
                             k + 1 == l.nslices ? 0xFFFFFFFFu : fb), "scan kernel launch");
@@ -509,8 +521,28 @@ static int lane_slice(dcsb_ctx *ctx, DcsbLane &l, uint32_t k, int16_t *pcm_out, 
         g_trace.mark(lane_id, (int)k, "decode", l.st);
         CK(cudaEventRecord(l.ev_slices[k], l.st), "event");
         CK(cudaStreamWaitEvent(ctx->down, l.ev_slices[k], 0), "stream wait");
-        CK(cudaMemcpy2DAsync(pcm_out + l.pcm_base + (uint64_t)fa * 240, (size_t)U * 480, d_pcm + (uint64_t)fa * 240, (size_t)U * 480,
-                             (size_t)(fb - fa) * 480, n, cudaMemcpyDeviceToHost, ctx->down), "D2H pcm slice");
+        if (l.copy2d) {
+            CK(cudaMemcpy2DAsync(pcm_out + l.pcm_base + (uint64_t)fa * 240, (size_t)U * 480, d_pcm + (uint64_t)fa * 240, (size_t)U * 480,
+                                 (size_t)(fb - fa) * 480, n, cudaMemcpyDeviceToHost, ctx->down), "D2H pcm slice");
+        } else {
+            // one piece per stream that reaches into the slice
+            l.cp_dst.clear(); l.cp_src.clear(); l.cp_size.clear();
+            for (size_t i = 0; i < n; ++i) {
+                const uint32_t of = p.recs[i].out_frames;
+                if (of <= fa) continue;
+                l.cp_dst.push_back(pcm_out + l.dst_off[i] + (uint64_t)fa * 240);
+                l.cp_src.push_back(d_pcm + p.recs[i].pcm_off + (uint64_t)fa * 240);
+                l.cp_size.push_back((size_t)(std::min(of, fb) - fa) * 480);
+            }
+            if (!l.cp_dst.empty()) {
+                cudaMemcpyAttributes at;
+                memset(&at, 0, sizeof(at));
+                at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+                size_t at_idx = 0, fail_idx = 0;
+                CK(cudaMemcpyBatchAsync(l.cp_dst.data(), l.cp_src.data(), l.cp_size.data(), l.cp_dst.size(), &at, &at_idx, 1, &fail_idx,
+                                        ctx->down), "D2H pcm slice (batched copy)");
+            }
+        }
         g_trace.mark(lane_id, (int)k, "d2h", ctx->down);
         return DCSB_OK;
     }
@@ -574,7 +606,9 @@ extern "C" int dcsb_decode_streams(dcsb_ctx *ctx, const dcsb_stream_desc *descs,
         off[i + 1] = off[i] + (uint64_t)(nf + descs[i].tail_frames) * 240;
         if (pcm_offsets && pcm_offsets[i] != off[i]) packed = false;
     }
-    const bool direct = packed && off[n] && is_pinned(pcm_out) && is_pinned(pcm_out + off[n] - 1);
+    uint64_t extent = off[n];                      // samples of pcm_out the call may write
+    if (!packed) { extent = 0; for (size_t i = 0; i < n; ++i) extent = std::max(extent, pcm_offsets[i] + (off[i + 1] - off[i])); }
+    const bool pinned = extent && is_pinned(pcm_out) && is_pinned(pcm_out + extent - 1);
     if (!ctx->up) {
         CK(cudaStreamCreateWithFlags(&ctx->up, cudaStreamNonBlocking), "cudaStreamCreate");
         CK(cudaStreamCreateWithFlags(&ctx->down, cudaStreamNonBlocking), "cudaStreamCreate");
@@ -583,11 +617,10 @@ extern "C" int dcsb_decode_streams(dcsb_ctx *ctx, const dcsb_stream_desc *descs,
     if (g_trace.on) { cudaEventCreate(&g_trace.t0); cudaEventRecord(g_trace.t0, ctx->up); }
     // chunks of about equal PCM size; few enough that every chunk still fills the GPU
     const uint64_t total = off[n];
-    // (a batch that cannot be cut in time -- streams of different lengths, or a pageable output -- gets
-    // more, smaller chunks instead: the first PCM copy can only start when a whole chunk is decoded)
-    bool all_uniform = direct && ctx->slice_frames >= 0;
-    for (size_t i = 1; i < n && all_uniform; ++i) all_uniform = off[i + 1] - off[i] == off[1] - off[0];
-    int nchunks = (int)std::min<uint64_t>(all_uniform ? DCSB_DEFAULT_LANES : DCSB_MAX_LANES, std::max<uint64_t>(1, total / (48ull << 20)));
+    // (a batch that cannot be cut in time -- a pageable output -- gets more, smaller chunks instead: the
+    // first PCM copy can only start when a whole chunk is decoded)
+    const bool sliceable = pinned && ctx->slice_frames >= 0;
+    int nchunks = (int)std::min<uint64_t>(sliceable ? DCSB_DEFAULT_LANES : DCSB_MAX_LANES, std::max<uint64_t>(1, total / (48ull << 20)));
     nchunks = (int)std::min<size_t>((size_t)nchunks, std::max<size_t>(1, n / 64));
     if (ctx->max_chunks > 0) nchunks = (int)std::min<size_t>((size_t)ctx->max_chunks, n);
     int used = 0, rc = DCSB_OK;
@@ -606,7 +639,7 @@ extern "C" int dcsb_decode_streams(dcsb_ctx *ctx, const dcsb_stream_desc *descs,
         l.first = i0;
         l.count = i1 - i0;
         l.pcm_base = off[i0];
-        rc = lane_upload(ctx, l, descs, direct, n);
+        rc = lane_upload(ctx, l, descs, pinned, packed, packed ? off.data() : pcm_offsets, n);
         max_slices = std::max(max_slices, l.nslices);
         i0 = i1;
     }

@@ -45,7 +45,11 @@ struct DcsbLane {
     std::vector<uint32_t> sl_bound;                          // slice k = output frames [sl_bound[k], sl_bound[k + 1])
     size_t first = 0, count = 0;
     uint64_t pcm_base = 0;                                   // sample offset of the chunk in the packed output
-    bool direct_pcm = false;
+    bool direct_pcm = false;                                 // PCM is copied straight into the caller's (pinned) buffer
+    bool copy2d = false;                                     // ... one strided copy per slice (else one batched copy of a piece per stream)
+    std::vector<uint64_t> dst_off;                           // batched copies: sample offset of each stream in the caller's buffer
+    std::vector<void *> cp_dst, cp_src;                      // operands of the batched copy being submitted
+    std::vector<size_t> cp_size;
 };
 
 struct dcsb_ctx {

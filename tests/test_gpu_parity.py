@@ -239,3 +239,30 @@ def test_gpu_decode_streams_time_slices(ctx):
             assert res == wres, (chunks, sl, [(i, a, b) for i, (a, b) in enumerate(zip(res, wres)) if a != b][:3])
     finally:
         ctx.set_pipeline(0, 0)
+
+
+def test_gpu_decode_streams_time_slices_mixed_lengths(ctx):
+    """Chunks whose streams differ in length are cut in time as well: one batched copy per slice with a
+    piece per stream that reaches into it (short streams drop out of the later slices)."""
+    rng = np.random.default_rng(123)
+    streams = []
+    for k in range(40):
+        nf = int(rng.integers(1, 400))
+        streams.append((dcsfuzz.fuzz94(rng, nf, type1=k & 1, max_code=15 if k % 3 == 0 else 9), 0x9400, 255, 100, int(rng.integers(0, 4))))
+    for os_, d, label in dcsfuzz.corpus(seed=11, n_each=1, nframes=90):
+        streams.append((d, os_, 220, 0x64, 2))
+    streams.append((bytes([0, 0] + [0x10] * 16), 0x9400, 255, 100, 2))
+    ctx.set_pipeline(0, -1)
+    want, offs, wres = ctx.decode_streams_pinned(streams)
+    for i in range(0, len(streams), 7):
+        d, os_, vol, lvl, tail = streams[i]
+        exp, _ = _expect(d, os_, vol, lvl, tail)
+        assert np.array_equal(want[offs[i]:offs[i] + exp.size], exp), i
+    try:
+        for chunks, sl in ((1, 31), (2, 50), (3, 64), (1, 333)):
+            ctx.set_pipeline(chunks, sl)
+            got, offs2, res = ctx.decode_streams_pinned(streams)
+            assert np.array_equal(got, want), (chunks, sl)
+            assert res == wres, (chunks, sl, [(i, a, b) for i, (a, b) in enumerate(zip(res, wres)) if a != b][:3])
+    finally:
+        ctx.set_pipeline(0, 0)

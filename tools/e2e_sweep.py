@@ -14,6 +14,15 @@ import dcsexplorer_b200 as dx
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 streams, n_unique, src = bench.build_corpus(n, 10.0, 0)
+if os.environ.get("MIXED"):
+    # streams of different lengths: cut every stream after a random number of frames (the frame count
+    # in the preamble is patched; the bytes behind the last frame are simply never read)
+    rng = np.random.default_rng(1)
+    cut = []
+    for s in streams:
+        nf = int(rng.integers(200, ((s[0] << 8) | s[1]) + 1))
+        cut.append(bytes([nf >> 8, nf & 255]) + s[2:])
+    streams = cut
 ctx = dx.Context(0)
 descs, keep = dx.make_descs(streams, os_version=dx.OS94, master_volume=255, mixing_level=0x64, tail_frames=2)
 blob = torch.empty(sum(len(s) for s in streams), dtype=torch.uint8).pin_memory()
