@@ -264,5 +264,24 @@ def test_gpu_decode_streams_time_slices_mixed_lengths(ctx):
             got, offs2, res = ctx.decode_streams_pinned(streams)
             assert np.array_equal(got, want), (chunks, sl)
             assert res == wres, (chunks, sl, [(i, a, b) for i, (a, b) in enumerate(zip(res, wres)) if a != b][:3])
+        # the caller's own offsets (reversed order, gaps) in a pinned buffer: same pieces, other destinations
+        import torch
+        import dcsexplorer_b200 as dx
+        descs, keep = dx.make_descs(streams)
+        n = len(streams)
+        sizes = [(offs[i + 1] if i + 1 < n else want.size) - offs[i] for i in range(n)]
+        coffs = np.zeros(n, dtype=np.uint64)
+        pos = 5
+        for i in reversed(range(n)):
+            coffs[i] = pos
+            pos += sizes[i] + 11
+        out = torch.full((pos,), 0x5A5A, dtype=torch.int16).pin_memory()
+        res2 = (dx.Result * n)()
+        ctx.set_pipeline(2, 40)
+        assert ctx._L.dcsb_decode_streams(ctx._h, descs, n, out.data_ptr(), coffs.ctypes.data, res2) == 0
+        o = out.numpy()
+        for i in range(n):
+            assert np.array_equal(o[int(coffs[i]):int(coffs[i]) + sizes[i]], want[offs[i]:offs[i] + sizes[i]]), i
+        assert o[0] == 0x5A5A and o[int(coffs[0]) + sizes[0]] == 0x5A5A
     finally:
         ctx.set_pipeline(0, 0)
