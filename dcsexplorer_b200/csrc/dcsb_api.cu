@@ -625,7 +625,6 @@ extern "C" int dcsb_decode_streams(dcsb_ctx *ctx, const dcsb_stream_desc *descs,
     if (ctx->max_chunks > 0) nchunks = (int)std::min<size_t>((size_t)ctx->max_chunks, n);
     int used = 0, rc = DCSB_OK;
     size_t i0 = 0;
-    uint32_t max_slices = 0;
     // the first chunks are smaller (weights 1, 2, 3, 3, ...): the first PCM can only leave once a chunk is
     // uploaded and its first slice scanned, and until then the copy engine idles
     uint64_t wsum = 0, wacc = 0;
@@ -640,10 +639,8 @@ extern "C" int dcsb_decode_streams(dcsb_ctx *ctx, const dcsb_stream_desc *descs,
         l.count = i1 - i0;
         l.pcm_base = off[i0];
         rc = lane_upload(ctx, l, descs, pinned, packed, packed ? off.data() : pcm_offsets, n);
-        max_slices = std::max(max_slices, l.nslices);
         i0 = i1;
     }
-    const int concurrent = (int)std::min<size_t>(n, 0x7FFFFFFF);     // (concurrent streams: all chunks scan side by side)
     // submit the (chunk, slice) work in the order it is expected to become ready: chunk c is uploaded
     // after the chunks before it (~45 GB/s), its slices then follow each other at the pace of the scan
     // chain (~14 us per frame with the chip full)
@@ -672,8 +669,6 @@ extern "C" int dcsb_decode_streams(dcsb_ctx *ctx, const dcsb_stream_desc *descs,
         for (int c = 0; c < used; ++c) if (up_done[c] <= j.start + 1e-9) live += ctx->lanes[c].count;
         j.concurrent = (int)std::min<size_t>(std::max(live, ctx->lanes[j.c].count), 0x7FFFFFFF);
     }
-    (void)max_slices;
-    (void)concurrent;
     for (const Job &j : jobs) {
         if (rc != DCSB_OK) break;
         rc = lane_slice(ctx, ctx->lanes[j.c], j.k, pcm_out, j.concurrent);
