@@ -1,14 +1,19 @@
 // dcsb200 kernels (sm_100a).
-//   K1 dcsb_scan_kernel    -- frame-boundary scan: one thread walks one stream's bit stream
-//                             (lengths only) and emits a checkpoint {bit offset, band types}
-//                             per frame, which is what makes frames independently decodable.
-//   K2 dcsb_decode_kernel  -- one warp per tile of 31 consecutive output frames of a stream:
-//                             lanes decode one frame each from its checkpoint into 16-bit
-//                             frequency bins in shared memory, then the warp runs the exact
-//                             fixed-point inverse transform frame by frame, applies the volume
-//                             shift + 16-sample overlap-add, and writes PCM with coalesced
-//                             32-bit stores.  Bins never touch HBM.
-// The arithmetic lives in dcsb_core.cuh (shared with the CPU-side kernel simulator).
+//   K1 dcsb_scan_kernel           -- frame-boundary scan: one thread walks one stream's bit stream
+//                                    (lengths only) and emits a checkpoint {bit offset, band types}
+//                                    per frame, which is what makes frames independently decodable
+//                                    (dcsb_scan94.cuh for the 1994+ layout, dcsb_core.cuh for the others).
+//   K2+K3 dcsb_decode94_kernel /  -- 1994+ layout: one warp per work item of consecutive output frames,
+//         dcsb_decode94_queue_kernel one LANE per frame: bit unpack from the checkpoint, dequantise, exact
+//                                    fixed-point inverse transform in the lane's shared-memory row,
+//                                    overlap-add, coalesced PCM stores (dcsb_fast94.cuh).  The queue
+//                                    variant is persistent and takes its items from the scan running
+//                                    beside it.
+//         dcsb_decode_kernel<true>  -- 1993 layouts: one warp per tile of 31 output frames, lanes decode
+//                                    a frame each into shared memory, the warp transforms frame by frame.
+//   K4 dcsb_mix94/93_kernel       -- track playback: the channels of the host's mix schedule decoded in
+//                                    order into the same bins, one transform per output frame (dcsb_mix.cuh).
+// Bins never touch HBM.  The arithmetic lives in the .cuh files, shared with the CPU-side kernel simulator.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -29,9 +34,8 @@ __device__ __forceinline__ void dcsb_load_lut(uint16_t *s_lut, const DcsbTables 
 
 // ------------------------------------------------------------------------------------
 // K1: frame-boundary scan, one thread per stream.  A CTA takes up to DCSB_SCAN_SPC streams (one
-// 1 KB ring each); a warp takes `lanes` of them (the scan is a dependent chain per stream: few
-// lanes per warp keep the chains from serialising on each other's branches, while several warps
-// per scheduler fill the latency of each chain); the CTA's warps share the tables and walk
+// 1 KB ring each); a warp takes `lanes` of them (every stream is its own dependent chain and its
+// lanes diverge almost always, see dcsb_scan_lanes); the CTA's warps share the tables and walk
 // stream groups grid-stride.
 struct DcsbSmemScan {
     __align__(16) uint8_t ring[DCSB_SCAN_SPC][DCSB_RING_BYTES];
