@@ -449,50 +449,57 @@ DCSB_HD void dcsb_transform94_warp(uint32_t *c, const DcsbTables *tab)
     }
 }
 
+// magnitude of (bin0 + i bin1) by the 1.15 Taylor series (:633-710); returns the new bin 0
+DCSB_HD uint32_t dcsb_magnitude93(uint32_t c0)
+{
+    uint32_t AR = c0 & 0xFFFFu;
+    const int b1 = dcsb_im(c0);
+    const bool neg = dcsb_s16(AR) < 0;
+    if (neg) AR = (uint32_t)(-dcsb_s16(AR)) & 0xFFFFu;
+    long long MR = (((long long)b1 * b1) << 1) + (((long long)dcsb_s16(AR) * dcsb_s16(AR)) << 1);
+    uint32_t SR = (uint32_t)(MR & 0xFFFFFFFFll);
+    int exponent = 0;                                              // CalcExp32 (:3447-3459)
+    {
+        uint32_t x = SR;
+        if (x & 0x80000000u) { for (; x & 0x40000000u; --exponent, x <<= 1) ; }
+        else { for (; exponent > -31 && !(x & 0x40000000u); --exponent, x <<= 1) ; }
+    }
+    if (exponent < 0) SR <<= -exponent;
+    AR = SR >> 16;
+    if (AR != 0) {
+        const int k[5] = { 0x5D1D, -22035, 0x46D6, -8790, 0x072D };
+        unsigned long long mr = 0x0D490000ull;
+        int mf = dcsb_s16(AR);
+        for (int t = 0; t < 5; ++t) {
+            mr += (unsigned long long)((long long)k[t] * (long long)mf * 2);
+            if (t < 4) mf = dcsb_mac_round<false>(0, 0, dcsb_s16(AR), mf);
+        }
+        if (exponent & 1) {
+            int prod = (int)((uint32_t)(dcsb_s16((uint32_t)(mr >> 16)) * 0x5A82) << 1);
+            long long r = (long long)prod + 0x8000;
+            if ((prod & 0xFFFF) == 0x8000) r &= ~0x10000ll;
+            mr = (unsigned long long)r;
+            exponent += 1;
+        }
+        exponent = exponent / 2 + 1;
+        const int v = (int)(uint32_t)(mr & 0xFFFFFFFFull);
+        uint32_t sr;                                                // BitShiftSigned32 (:3486-3501)
+        if (exponent >= 0) sr = (uint32_t)v << exponent;
+        else if (v >= 0) sr = (uint32_t)v >> -exponent;
+        else sr = ((uint32_t)v >> -exponent) | (~0u << (32 + exponent));
+        AR = sr >> 16;
+        if (neg) AR = (uint32_t)(-dcsb_s16(AR)) & 0xFFFFu;
+    }
+    return AR;
+}
+
 // 1993 transform on c[0..257] (256 complex points + the wrap-around element 128 the
 // reference writes at frameBuffer[0x100]) (:614-813).  Leaves the IFFT in c[0..255].
+// One warp per frame (the first path's form; the tile kernel now uses the lane-private one below).
 DCSB_HD void dcsb_transform93_warp(uint32_t *c, const DcsbTables *tab)
 {
-    // magnitude of (bin0 + i bin1) by the 1.15 Taylor series; scalar, lane 0 (:633-710)
     DCSB_FOR_LANES(l, 1) {
-        uint32_t AR = c[0] & 0xFFFFu;
-        const int b1 = dcsb_im(c[0]);
-        const bool neg = dcsb_s16(AR) < 0;
-        if (neg) AR = (uint32_t)(-dcsb_s16(AR)) & 0xFFFFu;
-        long long MR = (((long long)b1 * b1) << 1) + (((long long)dcsb_s16(AR) * dcsb_s16(AR)) << 1);
-        uint32_t SR = (uint32_t)(MR & 0xFFFFFFFFll);
-        int exponent = 0;                                              // CalcExp32 (:3447-3459)
-        {
-            uint32_t x = SR;
-            if (x & 0x80000000u) { for (; x & 0x40000000u; --exponent, x <<= 1) ; }
-            else { for (; exponent > -31 && !(x & 0x40000000u); --exponent, x <<= 1) ; }
-        }
-        if (exponent < 0) SR <<= -exponent;
-        AR = SR >> 16;
-        if (AR != 0) {
-            const int k[5] = { 0x5D1D, -22035, 0x46D6, -8790, 0x072D };
-            unsigned long long mr = 0x0D490000ull;
-            int mf = dcsb_s16(AR);
-            for (int t = 0; t < 5; ++t) {
-                mr += (unsigned long long)((long long)k[t] * (long long)mf * 2);
-                if (t < 4) mf = dcsb_mac_round<false>(0, 0, dcsb_s16(AR), mf);
-            }
-            if (exponent & 1) {
-                int prod = (int)((uint32_t)(dcsb_s16((uint32_t)(mr >> 16)) * 0x5A82) << 1);
-                long long r = (long long)prod + 0x8000;
-                if ((prod & 0xFFFF) == 0x8000) r &= ~0x10000ll;
-                mr = (unsigned long long)r;
-                exponent += 1;
-            }
-            exponent = exponent / 2 + 1;
-            const int v = (int)(uint32_t)(mr & 0xFFFFFFFFull);
-            uint32_t sr;                                                // BitShiftSigned32 (:3486-3501)
-            if (exponent >= 0) sr = (uint32_t)v << exponent;
-            else if (v >= 0) sr = (uint32_t)v >> -exponent;
-            else sr = ((uint32_t)v >> -exponent) | (~0u << (32 + exponent));
-            AR = sr >> 16;
-            if (neg) AR = (uint32_t)(-dcsb_s16(AR)) & 0xFFFFu;
-        }
+        const uint32_t AR = dcsb_magnitude93(c[0]);
         c[0] = AR;          // imaginary part zero
         c[128] = AR;
     }
@@ -520,6 +527,68 @@ DCSB_HD void dcsb_transform93_warp(uint32_t *c, const DcsbTables *tab)
             c[e0 + span] = a;
         }
         DCSB_SYNCWARP();
+    }
+}
+
+// The same transform with one LANE per frame: every lane works on its own row (row stride 257 words,
+// so equal offsets in different rows hit different banks), no warp synchronisation; three radix-2
+// stages at a time on 8 points held in registers (stages 0-2, 3-5), then stage 6.
+DCSB_HD void dcsb_transform93_lane(uint32_t *c, const uint32_t *twiddle)
+{
+    {
+        const uint32_t AR = dcsb_magnitude93(c[0]);
+        c[0] = AR;
+        c[128] = AR;
+    }
+    for (int i = 0; i < 64; ++i) {
+        const int k0 = 1 + i, k1 = 127 - i;
+        const uint32_t X = c[k0], Y = c[k1];
+        const int xr = dcsb_re(X), xi = dcsb_im(X), yr = dcsb_re(Y), yi = dcsb_im(Y);
+        c[129 + i] = dcsb_pack(xr - yr, xi + yi);
+        c[255 - i] = dcsb_pack(yr - xr, xi + yi);
+        c[k0] = dcsb_pack(xr + yr, xi - yi);
+        c[k1] = dcsb_pack(xr + yr, yi - xi);
+    }
+    // stage st pairs e and e + (64 >> st) inside partitions of 128 >> st elements; twiddle = partition index.
+    // Pass over stages s0..s0+2: elements  base + k * (span >> 2), k = 0..7, span = 64 >> s0 (the first stage's
+    // distance), for every base = partition start + j, j < span >> 2.
+#pragma unroll 1
+    for (int s0 = 0; s0 < 6; s0 += 3) {
+        const int span = 64 >> s0, step = span >> 2;          // 64,16 / 8,2
+        const int nparts = 1 << s0;                           // partitions at stage s0
+#pragma unroll 1
+        for (int g = 0; g < 32; ++g) {                        // 32 groups of 8 points
+            const int p = g / step, j = g - p * step;         // partition at stage s0, offset inside the quarter-span
+            const int base = p * 2 * span + j;
+            uint32_t x[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = c[base + k * step];
+            {   // stage s0: pairs (k, k + 4), twiddle p
+                const uint32_t tw = twiddle[p];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dcsb_butterfly<false>(x[k], x[k + 4], tw);
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {   // stage s0 + 1: pairs (4q + k, 4q + k + 2), twiddle 2p + q
+                const uint32_t tw = twiddle[2 * p + q];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) dcsb_butterfly<false>(x[4 * q + k], x[4 * q + k + 2], tw);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)     // stage s0 + 2: pairs (2q, 2q + 1), twiddle 4p + q
+                dcsb_butterfly<false>(x[2 * q], x[2 * q + 1], twiddle[4 * p + q]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) c[base + k * step] = x[k];
+            (void)nparts;
+        }
+    }
+    // stage 6: pairs (2p, 2p + 1), twiddle p
+#pragma unroll 4
+    for (int p = 0; p < 128; ++p) {
+        uint32_t u = c[2 * p], a = c[2 * p + 1];
+        dcsb_butterfly<false>(u, a, twiddle[p]);
+        c[2 * p] = u;
+        c[2 * p + 1] = a;
     }
 }
 
@@ -606,8 +675,9 @@ template <bool T93> struct DcsbWarpSmem { static constexpr int WORDS = 32 * Dcsb
 template <bool T93>
 DCSB_HD unsigned long long dcsb_decode_tile(const uint8_t *slab, const DcsbStreamRec *streams, DcsbTile tl,
                                             const DcsbTables *tab, const uint16_t *lut, const DcsbScanOut &scan,
-                                            int16_t *pcm, uint32_t *rows)
+                                            int16_t *pcm, uint32_t *rows, const uint32_t *twiddle = nullptr)
 {
+    if (!twiddle) twiddle = tab->twiddle;           // (the kernel passes a shared-memory copy)
     constexpr int ROWW = DcsbRow<T93>::WORDS;
     const DcsbStreamRec *sp = streams + tl.stream;
     const long long out_frames = sp->out_frames;
@@ -644,7 +714,15 @@ DCSB_HD unsigned long long dcsb_decode_tile(const uint8_t *slab, const DcsbStrea
     }
     DCSB_SYNCWARP();
 
-    // ---- phase B: transform the frames in order, carrying the 16-sample tail
+    // ---- phase B (1993 layouts): every lane transforms its own frame
+    if (T93) {
+        DCSB_FOR_LANES(l, 32) {
+            const long long f = (long long)tl.first - 1 + l;
+            if (f >= 0 && f < nplay && f < out_frames && l <= (int)tl.count) dcsb_transform93_lane(rows + l * ROWW, twiddle);
+        }
+        DCSB_SYNCWARP();
+    }
+    // ---- phase C: the frames in order, carrying the 16-sample tail
     unsigned long long csum = 0;
     const int vs0 = sp->vs0, vs1 = sp->vs1, vsi = sp->vs_idle;
     uint32_t *pcm32 = reinterpret_cast<uint32_t *>(pcm + sp->pcm_off);
@@ -653,10 +731,7 @@ DCSB_HD unsigned long long dcsb_decode_tile(const uint8_t *slab, const DcsbStrea
         if (f < 0) continue;                          // first tile of a stream: the overlap buffer starts at zero
         if (f >= out_frames || k > (int)tl.count) break;
         uint32_t *c = rows + k * ROWW;
-        if (f < nplay) {                              // silent frames transform to silence
-            if (T93) dcsb_transform93_warp(c, tab);
-            else dcsb_transform94_warp(c, tab);
-        }
+        if (!T93 && f < nplay) dcsb_transform94_warp(c, tab);       // silent frames transform to silence
         const int vs = f == 0 ? vs0 : (f < nplay ? vs1 : vsi);
         const uint32_t *tin = tails + (k & 1) * 8;
         uint32_t *tout = tails + ((k + 1) & 1) * 8;

@@ -22,7 +22,7 @@
 #include "dcsb_scan94.cuh"
 #include "dcsb_mix.cuh"
 
-#define DCSB_WARPS_PER_CTA 4
+#define DCSB_WARPS_PER_CTA 2      // 1993 layouts: 33 KB of rows per warp; 70 KB CTAs: three per SM, or one beside a scan CTA
 
 __device__ __forceinline__ void dcsb_load_lut(uint16_t *s_lut, const DcsbTables *tab)
 {
