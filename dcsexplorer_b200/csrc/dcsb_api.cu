@@ -320,36 +320,6 @@ static bool is_pinned(const void *p)
     return a.type == cudaMemoryTypeHost;
 }
 
-// DCSB_TRACE=1: device-side timeline of one dcsb_decode_streams call (CUDA events on the lanes'
-// streams, printed to stderr after the call) -- a tuning aid, off by default
-struct DcsbTrace {
-    bool on = false;
-    cudaEvent_t t0 = nullptr;
-    struct Mark { int lane; int slice; const char *what; cudaEvent_t ev; };
-    std::vector<Mark> marks;
-    void mark(int lane, int slice, const char *what, cudaStream_t st)
-    {
-        if (!on) return;
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        cudaEventRecord(e, st);
-        marks.push_back(Mark{ lane, slice, what, e });
-    }
-    void dump()
-    {
-        if (!on) return;
-        for (const Mark &m : marks) {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, t0, m.ev);
-            fprintf(stderr, "[dcsb trace] lane %d slice %2d %-10s %8.3f ms\n", m.lane, m.slice, m.what, ms);
-            cudaEventDestroy(m.ev);
-        }
-        marks.clear();
-        cudaEventDestroy(t0);
-    }
-};
-static DcsbTrace g_trace;
-
 #define ENS(buf, bytes, host, what) do { cudaError_t e_ = (buf).ensure((bytes), (host)); if (e_ != cudaSuccess) return fail(ctx, DCSB_E_NOMEM, what, e_); } while (0)
 
 // phase 1 of a lane: lay the chunk out, plan its time slices, upload it (on the context's upload stream)
@@ -484,7 +454,7 @@ static int lane_upload(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs
     if (b_tiles) CK(cudaMemcpyAsync(l.d_tiles.p, hm + b_recs, b_tiles, cudaMemcpyHostToDevice, up), "H2D tiles");
     CK(cudaMemcpyAsync(l.d_order.p, hm + b_recs + b_tiles, b_order, cudaMemcpyHostToDevice, up), "H2D order");
     CK(cudaEventRecord(l.ev_go, up), "event");
-    g_trace.mark(lane_id, -1, "h2d", up);
+    ctx->trace.mark(lane_id, -1, "h2d", up);
     // (memsets are kernels: they go on the lane's own stream, not between the uploads)
     CK(cudaMemsetAsync(l.d_csum.p, 0, n * 8, l.st), "memset checksums");
     if (!l.slice && ctx->overlap) {
@@ -515,10 +485,10 @@ static int lane_slice(dcsb_ctx *ctx, DcsbLane &l, uint32_t k, int16_t *pcm_out, 
         const uint32_t fa = l.sl_bound[k], fb = l.sl_bound[k + 1];
         CK(dcsb_launch_scan(slab, recs, (const uint32_t *)l.d_order.p, (int)n, concurrent, ctx->d_tables, so, l.st, fa,
                             k + 1 == l.nslices ? 0xFFFFFFFFu : fb), "scan kernel launch");
-        g_trace.mark(lane_id, (int)k, "scan", l.st);
+        ctx->trace.mark(lane_id, (int)k, "scan", l.st);
         CK(dcsb_launch_decode(slab, recs, tiles + l.sl_off[2 * k], (int)(l.sl_off[2 * k + 1] - l.sl_off[2 * k]),
                               (int)(l.sl_off[2 * k + 2] - l.sl_off[2 * k + 1]), ctx->d_tables, so, d_pcm, d_csum, l.st), "decode kernel launch");
-        g_trace.mark(lane_id, (int)k, "decode", l.st);
+        ctx->trace.mark(lane_id, (int)k, "decode", l.st);
         CK(cudaEventRecord(l.ev_slices[k], l.st), "event");
         CK(cudaStreamWaitEvent(ctx->down, l.ev_slices[k], 0), "stream wait");
         if (l.copy2d) {
@@ -543,7 +513,7 @@ static int lane_slice(dcsb_ctx *ctx, DcsbLane &l, uint32_t k, int16_t *pcm_out, 
                                         ctx->down), "D2H pcm slice (batched copy)");
             }
         }
-        g_trace.mark(lane_id, (int)k, "d2h", ctx->down);
+        ctx->trace.mark(lane_id, (int)k, "d2h", ctx->down);
         return DCSB_OK;
     }
     if (ctx->overlap) {
@@ -565,12 +535,12 @@ static int lane_slice(dcsb_ctx *ctx, DcsbLane &l, uint32_t k, int16_t *pcm_out, 
         CK(dcsb_launch_scan(slab, recs, (const uint32_t *)l.d_order.p, (int)n, concurrent, ctx->d_tables, so, l.st), "scan kernel launch");
         CK(dcsb_launch_decode(slab, recs, tiles, p.ntiles94, p.ntiles93, ctx->d_tables, so, d_pcm, d_csum, l.st), "decode kernel launch");
     }
-    g_trace.mark(lane_id, -1, "kernels", l.st);
+    ctx->trace.mark(lane_id, -1, "kernels", l.st);
     if (l.direct_pcm) {
         CK(cudaEventRecord(l.ev_slices[0], l.st), "event");
         CK(cudaStreamWaitEvent(ctx->down, l.ev_slices[0], 0), "stream wait");
         CK(cudaMemcpyAsync(pcm_out + l.pcm_base, d_pcm, p.total_out_frames * 480, cudaMemcpyDeviceToHost, ctx->down), "D2H pcm");
-        g_trace.mark(lane_id, -1, "d2h", ctx->down);
+        ctx->trace.mark(lane_id, -1, "d2h", ctx->down);
     }
     return DCSB_OK;
 }
@@ -613,8 +583,8 @@ extern "C" int dcsb_decode_streams(dcsb_ctx *ctx, const dcsb_stream_desc *descs,
         CK(cudaStreamCreateWithFlags(&ctx->up, cudaStreamNonBlocking), "cudaStreamCreate");
         CK(cudaStreamCreateWithFlags(&ctx->down, cudaStreamNonBlocking), "cudaStreamCreate");
     }
-    g_trace.on = getenv("DCSB_TRACE") != nullptr;
-    if (g_trace.on) { cudaEventCreate(&g_trace.t0); cudaEventRecord(g_trace.t0, ctx->up); }
+    ctx->trace.on = getenv("DCSB_TRACE") != nullptr;
+    if (ctx->trace.on) { cudaEventCreate(&ctx->trace.t0); cudaEventRecord(ctx->trace.t0, ctx->up); }
     // chunks of about equal PCM size; few enough that every chunk still fills the GPU
     const uint64_t total = off[n];
     // (a batch that cannot be cut in time -- a pageable output -- gets more, smaller chunks instead: the
@@ -714,6 +684,6 @@ extern "C" int dcsb_decode_streams(dcsb_ctx *ctx, const dcsb_stream_desc *descs,
             }
         }
     }
-    g_trace.dump();
+    ctx->trace.dump();
     return rc;
 }

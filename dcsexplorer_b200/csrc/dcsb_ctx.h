@@ -52,6 +52,34 @@ struct DcsbLane {
     std::vector<size_t> cp_size;
 };
 
+// DCSB_TRACE=1: device-side timeline of one dcsb_decode_streams call (CUDA events on the lanes'
+// streams, printed to stderr after the call) -- a tuning aid, off by default
+struct DcsbTrace {
+    bool on = false;
+    cudaEvent_t t0 = nullptr;
+    struct Mark { int lane; int slice; const char *what; cudaEvent_t ev; };
+    std::vector<Mark> marks;
+    void mark(int lane, int slice, const char *what, cudaStream_t st)
+    {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        marks.push_back(Mark{ lane, slice, what, e });
+    }
+    void dump()
+    {
+        if (!on) return;
+        for (const Mark &m : marks) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, t0, m.ev);
+            fprintf(stderr, "[dcsb trace] lane %d slice %2d %-10s %8.3f ms\n", m.lane, m.slice, m.what, ms);
+            cudaEventDestroy(m.ev);
+        }
+        marks.clear();
+        cudaEventDestroy(t0);
+    }
+};
 struct dcsb_ctx {
     int device = 0;
     DcsbTables *d_tables = nullptr;
@@ -61,6 +89,7 @@ struct dcsb_ctx {
     int max_chunks = 0;                      // dcsb_set_pipeline: chunks of dcsb_decode_streams (0 = choose)
     int slice_frames = 0;                    // dcsb_set_pipeline: frames per time slice (0 = choose, < 0 = never slice)
     DcsbLane lanes[DCSB_MAX_LANES];
+    DcsbTrace trace;
     std::string err;
 };
 
