@@ -35,9 +35,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 SAMPLE_RATE = 31250
 FRAME = 240
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
-# capture of this workload (profiles/r01k_ncu_full.txt): scan 551.5 MB read + 71.8 MB written
-# (checkpoints); decode (captured as the persistent queue variant, same work) 674.4 MB read + 2514.2 MB written
-TRAFFIC = {"dcsb_scan_kernel": 623.3e6, "dcsb_decode94_kernel": 3188.6e6}
+# capture of this workload (profiles/r01m_ncu_full.txt): scan 550.3 MB read + 72.4 MB written
+# (checkpoints); decode (captured as the persistent queue variant, same work) 673.6 MB read + 2512.8 MB written
+TRAFFIC = {"dcsb_scan_kernel": 622.7e6, "dcsb_decode94_kernel": 3186.4e6}
 
 
 # ------------------------------------------------------------------------------------------
