@@ -251,24 +251,9 @@ void dcsb_scan_order(DcsbPrepared *p)
             p->scan_order[base[c] + fill[c]++] = rank[r];
             c = (c + 1) % grid;
         }
-        // inside a CTA: the k-th most expensive stream goes to lane k / warps of warp k % warps, so every
-        // warp holds one of the expensive streams and fills up with cheaper ones (which finish early and
-        // leave the warp to it) instead of the expensive ones sharing a warp
-        if (getenv("DCSB_SCAN_INTERLEAVE")) {
-            const int lanes = dcsb_scan_lanes((int)std::min<size_t>(n, 0x7FFFFFFF));
-            std::vector<uint32_t> tmp;
-            for (int cc = 0; cc < grid; ++cc) {
-                const uint32_t cnt = fill[cc];
-                const uint32_t nw = (cnt + (uint32_t)lanes - 1) / (uint32_t)lanes;
-                tmp.assign(p->scan_order.begin() + base[cc], p->scan_order.begin() + base[cc] + cnt);
-                uint32_t k = 0;
-                for (uint32_t l = 0; l < (uint32_t)lanes; ++l)
-                    for (uint32_t w = 0; w < nw; ++w) {
-                        const uint32_t slot = w * (uint32_t)lanes + l;
-                        if (slot < cnt) p->scan_order[base[cc] + slot] = tmp[k++];
-                    }
-            }
-        }
+        // (inside a CTA the slots run from expensive to cheap, so a warp holds streams of about the same cost.
+        // Dealing the expensive streams out over the warps instead -- one per warp, filled up with cheap ones --
+        // measured 14.6 ms against 14.2 ms: alike streams in a warp diverge less.)
         return;
     }
     std::stable_sort(rank.begin(), rank.end(), [&](uint32_t a, uint32_t b) {
