@@ -43,6 +43,7 @@ def lib():
         L.dcsref_rom_list_streams.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.dcsref_rom_open_images.restype = C.c_void_p
         L.dcsref_rom_open_images.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.dcsref_rom_track_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -130,6 +131,11 @@ class RomPlayer:
         out = np.zeros(4096, dtype=np.uint32)
         n = lib().dcsref_rom_list_streams(self._h, out.ctypes.data, out.size)
         return [int(x) for x in out[:n]]
+
+    def track_info(self, track):
+        out = np.zeros(7, dtype=np.uint32)
+        lib().dcsref_rom_track_info(self._h, track, out.ctypes.data)
+        return [int(x) for x in out]
 
     def render_timeline(self, writes, n_frames):
         """writes: list of (frame, byte), sorted by frame"""

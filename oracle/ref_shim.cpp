@@ -308,4 +308,15 @@ int dcsref_rom_list_streams(void *h, uint32_t *addrs, int cap)
     return n;
 }
 
+// GetTrackInfo (DCSDecoder.h:416): out = {valid, address, channel, type, deferCode, time, looping}
+int dcsref_rom_track_info(void *h, int track, uint32_t *out)
+{
+    auto *c = static_cast<RomCtx *>(h);
+    DCSDecoder::TrackInfo ti;
+    const bool ok = c->dec->GetTrackInfo(static_cast<uint16_t>(track), ti);
+    out[0] = ok; out[1] = ti.address; out[2] = (uint32_t)ti.channel; out[3] = (uint32_t)ti.type;
+    out[4] = ti.deferCode; out[5] = ti.time; out[6] = ti.looping;
+    return ok;
+}
+
 } // extern "C"

@@ -137,6 +137,36 @@ def test_zip_loader(built, tmp_path):
 
 
 @needs_ref
+def test_zip_loader_vs_reference_zip_loader(built, tmp_path):
+    """The same zip through the reference's LoadROMFromZipFile (DCSDecoderZipLoader.cpp, miniz) and
+    through dcsb_rom_load_zip: same chips identified, same version info, same stream list; odd
+    member names (a '2' only in the directory part, upper case, U2 under an unusual name)."""
+    import ctypes as C
+    import dcsexplorer_b200 as dx
+    sc = romscen.make_scenario(os_version=rb.OS94, seed=12)
+    z = tmp_path / "zip_2_ref.zip"
+    with zipfile.ZipFile(z, "w", zipfile.ZIP_DEFLATED) as f:
+        f.writestr("notes/readme2.txt", "not a rom 2")
+        f.writestr("SOUND/TZ_U4.L1", sc["images"][4])
+        f.writestr("sound/tz_u3.l1", sc["images"][3])
+        f.writestr("sound/tzu2_10.rom", sc["images"][2])
+    err = C.create_string_buffer(256)
+    h = ref.lib().dcsref_rom_open_zip(str(z).encode(), 255, err, 256)
+    assert h, err.value
+    rp = ref.RomPlayer.__new__(ref.RomPlayer)
+    rp._h = h
+    want_info, want_streams = rp.info(), rp.list_streams()
+    rp.close()
+    assert want_info["check"] == 1
+    rom = dx.Rom(zip_path=z)
+    assert rom.check() == 1
+    info = rom.info()
+    assert info["n_tracks"] - 1 == want_info["max_track"] and info["channels"] == want_info["channels"]
+    assert rom.list_streams() == want_streams
+    rom.close()
+
+
+@needs_ref
 @pytest.mark.parametrize("os_version,seed", [(rb.OS94, 201), (rb.OS95, 202), (rb.OS93B, 203), (rb.OS93A, 204), (rb.OS94, 205)])
 def test_sim_rom_vs_reference_fresh_scenarios(built, os_version, seed):
     sc = romscen.make_scenario(os_version=os_version, seed=seed, n_frames=500, with_errors=(seed == 205),
