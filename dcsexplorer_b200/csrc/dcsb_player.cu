@@ -3,6 +3,7 @@
 // on the GPU, turns sequencer output into mix work items and launches K4 (dcsb_mix.cuh).
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <thread>
 #include "dcsb_ctx.h"
 #include "dcsb_rom.h"
@@ -323,6 +324,13 @@ extern "C" int dcsb_render_timelines(dcsb_ctx *ctx, dcsb_rom *rom, const dcsb_ti
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     int rc = rom_prepare(ctx, rom);
     if (rc != DCSB_OK) return rc;
+    const auto t_begin = std::chrono::steady_clock::now();
+    const bool trace = getenv("DCSB_TRACE") != nullptr;
+    auto lap = [&](const char *what) {      // DCSB_TRACE=1: host-side phases of the call
+        if (trace)
+            fprintf(stderr, "[dcsb trace] render_timelines %-22s at %8.3f ms\n", what,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
     // host: one sequencer per timeline, a few threads
     struct Part { std::vector<DcsbSchedFrame> frames; std::vector<DcsbSchedEntry> entries; bool fatal = false; uint32_t nhost = 0; };
     std::vector<Part> parts(n);
@@ -348,6 +356,7 @@ extern "C" int dcsb_render_timelines(dcsb_ctx *ctx, dcsb_rom *rom, const dcsb_ti
         for (unsigned k = 0; k < nth; ++k) th.emplace_back([&, k] { for (size_t t = k; t < n; t += nth) work(t); });
         for (auto &x : th) x.join();
     }
+    lap("sequencers done");
     std::vector<DcsbSchedFrame> frames;
     std::vector<DcsbSchedEntry> entries;
     std::vector<uint32_t> first(n), count(n), skip(n, 0);
@@ -360,9 +369,12 @@ extern "C" int dcsb_render_timelines(dcsb_ctx *ctx, dcsb_rom *rom, const dcsb_ti
     }
     if (frames.empty()) return DCSB_OK;
     DcsbRenderBufs bufs;
+    lap("schedule merged");
     rc = render_schedule(ctx, rom, bufs, frames, entries, first, count, skip, nullptr);
+    lap("uploads + launch queued");
     cudaError_t e = cudaSuccess;
-    if (rc == DCSB_OK) {
+    if (rc == DCSB_OK && trace) { e = cudaDeviceSynchronize(); lap("mix kernel done"); }
+    if (rc == DCSB_OK && e == cudaSuccess) {
         bool packed = true;
         for (size_t t = 0; t < n && pcm_offsets; ++t) if (pcm_offsets[t] != (uint64_t)first[t] * 240) packed = false;
         if (packed) e = cudaMemcpy(pcm_out, bufs.d_pcm.p, frames.size() * 480, cudaMemcpyDeviceToHost);
@@ -382,7 +394,9 @@ extern "C" int dcsb_render_timelines(dcsb_ctx *ctx, dcsb_rom *rom, const dcsb_ti
             }
         }
     }
+    lap("PCM on the host");
     bufs.release();
+    lap("buffers released");
     if (rc != DCSB_OK) return rc;
     if (e != cudaSuccess) return fail(ctx, DCSB_E_CUDA, "dcsb_render_timelines: D2H", e);
     return DCSB_OK;

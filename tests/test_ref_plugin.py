@@ -70,4 +70,4 @@ def test_b200_plugin_equals_native_behind_the_reference_base_class(built, tmp_pa
     assert hb_n == hb_b
     # the base class's own lookups (version, tracks, channels, streams) see the same ROM set
     assert rn.stdout.split("|", 1)[1] == rb_.stdout.split("|", 1)[1]
-    assert rb_.stdout.startswith("b200 |") and rn.stdout.startswith("native |")
+    assert rb_.stdout.startswith("b200 |") and rn.stdout.startswith("Universal native decoder |")      # Name() of each
