@@ -51,6 +51,7 @@ extern "C" void dcsb_destroy(dcsb_ctx *ctx)
         for (DcsbBuf *b : { &l.d_slab, &l.d_recs, &l.d_tiles, &l.d_bitpos, &l.d_bt, &l.d_hdrbits, &l.d_status, &l.d_nplay,
                             &l.d_endbits, &l.d_stopband, &l.d_csum, &l.d_pcm, &l.d_queue, &l.d_order }) b->release(false);
     }
+    if (ctx->timeline_cache && ctx->timeline_cache_free) ctx->timeline_cache_free(ctx->timeline_cache);
     if (ctx->aux) { cudaStreamSynchronize(ctx->aux); cudaStreamDestroy(ctx->aux); }
     if (ctx->up) { cudaStreamSynchronize(ctx->up); cudaStreamDestroy(ctx->up); }
     if (ctx->down) { cudaStreamSynchronize(ctx->down); cudaStreamDestroy(ctx->down); }

@@ -90,6 +90,9 @@ struct dcsb_ctx {
     int slice_frames = 0;                    // dcsb_set_pipeline: frames per time slice (0 = choose, < 0 = never slice)
     DcsbLane lanes[DCSB_MAX_LANES];
     DcsbTrace trace;
+    // dcsb_render_timelines: stream, device buffers and pinned staging kept for the next call (dcsb_player.cu owns the type)
+    void *timeline_cache = nullptr;
+    void (*timeline_cache_free)(void *) = nullptr;
     std::string err;
 };
 

@@ -47,7 +47,6 @@ struct DcsbSmemScan {
 #define DCSB_TX_BYTES (6 * DCSB_T8_CB * 2)
 #define DCSB_SCAN_SMEM (sizeof(DcsbSmemScan) + DCSB_TX_BYTES + 16384)
 
-template <int VAR>
 __global__ void __launch_bounds__(DCSB_SCAN_SPC * 32, 1)
 dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restrict__ streams, const uint32_t *__restrict__ order,
                  int nstreams, int lanes, int spc, int nsolo, const DcsbTables *__restrict__ tab, DcsbScanOut out, uint32_t f0, uint32_t f1)
@@ -78,7 +77,7 @@ dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restri
 #endif
     for (int k = blockIdx.x * spc + slot; k < nstreams; k += gridDim.x * spc) {
         const int si = order ? (int)order[k] : k;
-        if (streams[si].fmt == DCSB_FMT_94) dcsb_scan94_stream<VAR>(slab, streams, si, tab, sm.lut, txb, sm.dtab, ring, sm.desc[slot], out, f0, f1);
+        if (streams[si].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab, streams, si, tab, sm.lut, txb, sm.dtab, ring, sm.desc[slot], out, f0, f1);
         else dcsb_scan_stream(slab, streams, si, tab, sm.lut, out, f0, f1);
     }
 }
@@ -367,22 +366,6 @@ cudaError_t dcsb_launch_gate(DcsbScanOut scan, int ctas, cudaStream_t st)
     return cudaGetLastError();
 }
 
-template <int VAR>
-static cudaError_t launch_scan_variant(const uint8_t *slab, const DcsbStreamRec *streams, const uint32_t *order, int nstreams, int lanes,
-                                       int spc, int nsolo, int warps, int grid, const DcsbTables *tables, DcsbScanOut out,
-                                       uint32_t f0, uint32_t f1, cudaStream_t st)
-{
-    const size_t smem = DCSB_SCAN_SMEM;
-    cudaError_t e = cudaFuncSetAttribute(dcsb_scan_kernel<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    // keep the SM at its largest shared-memory split, so that CTAs of the other kernel can join
-    // this one (the split only changes on an idle SM)
-    e = cudaFuncSetAttribute(dcsb_scan_kernel<VAR>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    dcsb_scan_kernel<VAR><<<grid, warps * 32, smem, st>>>(slab, streams, order, nstreams, lanes, spc, nsolo, tables, out, f0, f1);
-    return cudaGetLastError();
-}
-
 cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, const uint32_t *order, int nstreams, int concurrent,
                              const DcsbTables *tables, DcsbScanOut out, cudaStream_t st, uint32_t f0, uint32_t f1)
 {
@@ -392,10 +375,15 @@ cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, 
     scan_shape(nstreams, concurrent, spc, grid);
     const int nsolo = dcsb_scan_solo(nstreams, spc);
     const int warps = nsolo + (spc - nsolo + lanes - 1) / lanes;
-    int var = DCSB_SCAN_VARIANT_DEFAULT;
-    if (const char *ev = getenv("DCSB_SCAN_VARIANT")) var = atoi(ev) ? 1 : 0;      // tuning override (tools/scan_sweep.py)
-    return var ? launch_scan_variant<1>(slab, streams, order, nstreams, lanes, spc, nsolo, warps, grid, tables, out, f0, f1, st)
-               : launch_scan_variant<0>(slab, streams, order, nstreams, lanes, spc, nsolo, warps, grid, tables, out, f0, f1, st);
+    const size_t smem = DCSB_SCAN_SMEM;
+    cudaError_t e = cudaFuncSetAttribute(dcsb_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    // keep the SM at its largest shared-memory split, so that CTAs of the other kernel can join
+    // this one (the split only changes on an idle SM)
+    e = cudaFuncSetAttribute(dcsb_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    dcsb_scan_kernel<<<grid, warps * 32, smem, st>>>(slab, streams, order, nstreams, lanes, spc, nsolo, tables, out, f0, f1);
+    return cudaGetLastError();
 }
 
 static cudaError_t launch_decode93(const uint8_t *slab, const DcsbStreamRec *streams, const DcsbTile *tiles,

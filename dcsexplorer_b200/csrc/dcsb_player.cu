@@ -4,6 +4,7 @@
 #include <string.h>
 #include <algorithm>
 #include <chrono>
+#include <functional>
 #include <thread>
 #include "dcsb_ctx.h"
 #include "dcsb_rom.h"
@@ -177,6 +178,17 @@ struct DcsbRenderBufs {
 // frames / entries: the whole schedule; tl_first[t], tl_frames[t]: each timeline's slice; skip[t]:
 // leading frames that are only there to warm the overlap up (not rendered).  PCM lands in
 // bufs.d_pcm at 240 * (global frame index) samples.
+// work items: 1994 layout 31 + 32k frames per warp, 1993 layouts tiles of 31
+static uint32_t mix_item_len(bool fam93, uint64_t total_frames)
+{
+    uint32_t item_len = DCSB_TILE_OUT;
+    if (!fam93) {
+        item_len = (uint32_t)std::min<uint64_t>(255, std::max<uint64_t>(31, total_frames / 8192));
+        item_len = item_len < 63 ? 31 : 31 + ((item_len - 31) / 32) * 32;
+    }
+    return item_len;
+}
+
 static int render_schedule(dcsb_ctx *ctx, dcsb_rom *rom, DcsbRenderBufs &bufs, const std::vector<DcsbSchedFrame> &frames,
                            const std::vector<DcsbSchedEntry> &entries, const std::vector<uint32_t> &tl_first,
                            const std::vector<uint32_t> &tl_frames, const std::vector<uint32_t> &skip, cudaStream_t st)
@@ -184,14 +196,9 @@ static int render_schedule(dcsb_ctx *ctx, dcsb_rom *rom, DcsbRenderBufs &bufs, c
     dcsb_batch *b = rom->batch;
     const bool fam93 = rom->os == DCSB_OS93A || rom->os == DCSB_OS93B;
     const size_t nt = tl_first.size();
-    // work items: 1994 layout 31 + 32k frames per warp, 1993 layouts tiles of 31
     uint64_t total = 0;
     for (size_t t = 0; t < nt; ++t) total += tl_frames[t];
-    uint32_t item_len = DCSB_TILE_OUT;
-    if (!fam93) {
-        item_len = (uint32_t)std::min<uint64_t>(255, std::max<uint64_t>(31, total / 8192));
-        item_len = item_len < 63 ? 31 : 31 + ((item_len - 31) / 32) * 32;
-    }
+    const uint32_t item_len = mix_item_len(fam93, total);
     std::vector<DcsbMixItem> items;
     for (size_t t = 0; t < nt; ++t)
         for (uint32_t f = skip[t]; f < tl_frames[t]; f += item_len)
@@ -316,6 +323,38 @@ extern "C" int dcsb_player_render(dcsb_player *p, uint32_t n_frames, int16_t *pc
 
 // ======================================================================================
 // many timelines at once
+// The call is a pipeline over chunks of timelines: host threads run the sequencers of chunk k + 1
+// (the reference's MainLoop control plane, one instance per timeline) while the GPU renders chunk k
+// and its PCM goes down the link.  Per chunk: schedules -> pinned staging (every thread copies its
+// own timelines into place) -> one upload -> K4 mix kernel -> one PCM download (asynchronous into
+// a page-locked pcm_out, else a blocking copy).  Device and staging buffers live in the context
+// and are reused by the next call (no allocation in the steady state).
+static bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+#define DCSB_RT_MAX_CHUNKS 8
+struct DcsbTimelineCache {
+    cudaStream_t st = nullptr;
+    DcsbBuf d_frames, d_pcm, d_csum, h_frames;
+    DcsbBuf d_entries[DCSB_RT_MAX_CHUNKS], d_items[DCSB_RT_MAX_CHUNKS], h_entries[DCSB_RT_MAX_CHUNKS], h_items[DCSB_RT_MAX_CHUNKS];
+};
+static void timeline_cache_free(void *p)
+{
+    DcsbTimelineCache *c = static_cast<DcsbTimelineCache *>(p);
+    if (!c) return;
+    if (c->st) { cudaStreamSynchronize(c->st); cudaStreamDestroy(c->st); }
+    for (DcsbBuf *b : { &c->d_frames, &c->d_pcm, &c->d_csum }) b->release(false);
+    c->h_frames.release(true);
+    for (int k = 0; k < DCSB_RT_MAX_CHUNKS; ++k) {
+        c->d_entries[k].release(false); c->d_items[k].release(false);
+        c->h_entries[k].release(true); c->h_items[k].release(true);
+    }
+    delete c;
+}
+
 extern "C" int dcsb_render_timelines(dcsb_ctx *ctx, dcsb_rom *rom, const dcsb_timeline *timelines, size_t n,
                                      int16_t *pcm_out, const uint64_t *pcm_offsets, dcsb_timeline_result *results)
 {
@@ -326,78 +365,140 @@ extern "C" int dcsb_render_timelines(dcsb_ctx *ctx, dcsb_rom *rom, const dcsb_ti
     if (rc != DCSB_OK) return rc;
     const auto t_begin = std::chrono::steady_clock::now();
     const bool trace = getenv("DCSB_TRACE") != nullptr;
-    auto lap = [&](const char *what) {      // DCSB_TRACE=1: host-side phases of the call
+    auto lap = [&](const char *what, int k) {      // DCSB_TRACE=1: host-side phases of the call
         if (trace)
-            fprintf(stderr, "[dcsb trace] render_timelines %-22s at %8.3f ms\n", what,
+            fprintf(stderr, "[dcsb trace] render_timelines chunk %d %-20s at %8.3f ms\n", k, what,
                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
     };
-    // host: one sequencer per timeline, a few threads
+    if (!ctx->timeline_cache) { ctx->timeline_cache = new DcsbTimelineCache(); ctx->timeline_cache_free = timeline_cache_free; }
+    DcsbTimelineCache &tc = *static_cast<DcsbTimelineCache *>(ctx->timeline_cache);
+    if (!tc.st) CK(cudaStreamCreateWithFlags(&tc.st, cudaStreamNonBlocking), "cudaStreamCreate");
+    const bool fam93 = rom->os == DCSB_OS93A || rom->os == DCSB_OS93B;
+    dcsb_batch *b = rom->batch;
+
+    // every timeline yields exactly n_frames schedule frames: the layout of frames and PCM is known up front
+    std::vector<uint64_t> first(n + 1, 0);
+    for (size_t t = 0; t < n; ++t) first[t + 1] = first[t] + timelines[t].n_frames;
+    const uint64_t total = first[n];
+    if (total == 0) return DCSB_OK;
+    if (total >= 0xFFFFFFFFull) return fail(ctx, DCSB_E_ARG, "dcsb_render_timelines: more than 2^32 frames in one call");
+    bool packed = true;
+    for (size_t t = 0; t < n && pcm_offsets; ++t) if (pcm_offsets[t] != first[t] * 240) packed = false;
+    const bool pinned = packed && is_pinned_host(pcm_out) && is_pinned_host(pcm_out + total * 240 - 1);
+    const uint32_t item_len = mix_item_len(fam93, total);
+#define ENS(buf, bytes, host, what) do { cudaError_t e_ = (buf).ensure((bytes), (host)); if (e_ != cudaSuccess) return fail(ctx, DCSB_E_NOMEM, what, e_); } while (0)
+    ENS(tc.d_frames, total * sizeof(DcsbSchedFrame), false, "cudaMalloc(schedule frames)");
+    ENS(tc.h_frames, total * sizeof(DcsbSchedFrame), true, "cudaMallocHost(schedule frames)");
+    ENS(tc.d_pcm, total * 480, false, "cudaMalloc(pcm)");
+    ENS(tc.d_csum, n * 8, false, "cudaMalloc(checksums)");
+    CK(cudaMemsetAsync(tc.d_csum.p, 0, n * 8, tc.st), "memset checksums");
+    DcsbSchedFrame *hf = static_cast<DcsbSchedFrame *>(tc.h_frames.p);
+
+    // chunks of about equal frame counts; small calls are one chunk
+    const size_t nchunks = (size_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(DCSB_RT_MAX_CHUNKS, n), total / 65536));
+    std::vector<size_t> cut(nchunks + 1, n);
+    cut[0] = 0;
+    for (size_t k = 1, t = 0; k < nchunks; ++k) {
+        while (t < n && first[t] < total * k / nchunks) ++t;
+        cut[k] = t;
+    }
     struct Part { std::vector<DcsbSchedFrame> frames; std::vector<DcsbSchedEntry> entries; bool fatal = false; uint32_t nhost = 0; };
     std::vector<Part> parts(n);
-    auto work = [&](size_t t) {
-        const dcsb_timeline &tl = timelines[t];
-        Part &pt = parts[t];
-        DcsbSequencer seq(rom);
-        seq.soft_boot();
-        seq.set_master_volume(tl.master_volume);
-        uint32_t w = 0;
-        pt.frames.reserve(tl.n_frames);
-        for (uint32_t f = 0; f < tl.n_frames; ++f) {
-            while (w < tl.n_writes && tl.writes[w].frame <= f) seq.write_port(tl.writes[w++].byte);
-            seq.frame(pt.frames, pt.entries);
-        }
-        pt.fatal = seq.fatal;
-        pt.nhost = (uint32_t)seq.host_bytes.size();
-    };
-    const unsigned nth = (unsigned)std::min<size_t>(n, std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
-    if (nth <= 1) for (size_t t = 0; t < n; ++t) work(t);
-    else {
+    std::vector<uint64_t> ebase(n + 1, 0);
+    const unsigned nth_max = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    auto run_threads = [&](size_t t0, size_t t1, const std::function<void(size_t)> &fn) {
+        const unsigned nth = (unsigned)std::min<size_t>(t1 - t0, nth_max);
+        if (nth <= 1) { for (size_t t = t0; t < t1; ++t) fn(t); return; }
         std::vector<std::thread> th;
-        for (unsigned k = 0; k < nth; ++k) th.emplace_back([&, k] { for (size_t t = k; t < n; t += nth) work(t); });
+        for (unsigned j = 0; j < nth; ++j) th.emplace_back([&, j] { for (size_t t = t0 + j; t < t1; t += nth) fn(t); });
         for (auto &x : th) x.join();
-    }
-    lap("sequencers done");
-    std::vector<DcsbSchedFrame> frames;
-    std::vector<DcsbSchedEntry> entries;
-    std::vector<uint32_t> first(n), count(n), skip(n, 0);
-    for (size_t t = 0; t < n; ++t) {
-        first[t] = (uint32_t)frames.size();
-        count[t] = (uint32_t)parts[t].frames.size();
-        const uint32_t ebase = (uint32_t)entries.size();
-        for (DcsbSchedFrame fr : parts[t].frames) { fr.first_entry += ebase; frames.push_back(fr); }
-        entries.insert(entries.end(), parts[t].entries.begin(), parts[t].entries.end());
-    }
-    if (frames.empty()) return DCSB_OK;
-    DcsbRenderBufs bufs;
-    lap("schedule merged");
-    rc = render_schedule(ctx, rom, bufs, frames, entries, first, count, skip, nullptr);
-    lap("uploads + launch queued");
+    };
     cudaError_t e = cudaSuccess;
-    if (rc == DCSB_OK && trace) { e = cudaDeviceSynchronize(); lap("mix kernel done"); }
-    if (rc == DCSB_OK && e == cudaSuccess) {
-        bool packed = true;
-        for (size_t t = 0; t < n && pcm_offsets; ++t) if (pcm_offsets[t] != (uint64_t)first[t] * 240) packed = false;
-        if (packed) e = cudaMemcpy(pcm_out, bufs.d_pcm.p, frames.size() * 480, cudaMemcpyDeviceToHost);
+    for (size_t k = 0; k < nchunks && e == cudaSuccess; ++k) {
+        const size_t t0 = cut[k], t1 = cut[k + 1];
+        if (t0 == t1) continue;
+        // host: one sequencer per timeline
+        run_threads(t0, t1, [&](size_t t) {
+            const dcsb_timeline &tl = timelines[t];
+            Part &pt = parts[t];
+            DcsbSequencer seq(rom);
+            seq.soft_boot();
+            seq.set_master_volume(tl.master_volume);
+            uint32_t w = 0;
+            pt.frames.reserve(tl.n_frames);
+            pt.entries.reserve((size_t)tl.n_frames * 2);
+            for (uint32_t f = 0; f < tl.n_frames; ++f) {
+                while (w < tl.n_writes && tl.writes[w].frame <= f) seq.write_port(tl.writes[w++].byte);
+                seq.frame(pt.frames, pt.entries);
+            }
+            pt.fatal = seq.fatal;
+            pt.nhost = (uint32_t)seq.host_bytes.size();
+        });
+        lap("sequencers done", (int)k);
+        // entries of the chunk are numbered from the chunk's own base; items from 0
+        ebase[t0] = 0;
+        size_t nitems = 0;
+        std::vector<size_t> ibase(t1 - t0 + 1, 0);
+        for (size_t t = t0; t < t1; ++t) {
+            ebase[t + 1] = ebase[t] + parts[t].entries.size();
+            ibase[t - t0 + 1] = ibase[t - t0] + (timelines[t].n_frames + item_len - 1) / item_len;
+        }
+        nitems = ibase[t1 - t0];
+        const size_t nent = (size_t)ebase[t1];
+        ENS(tc.h_entries[k], std::max<size_t>(1, nent) * sizeof(DcsbSchedEntry), true, "cudaMallocHost(schedule entries)");
+        ENS(tc.d_entries[k], std::max<size_t>(1, nent) * sizeof(DcsbSchedEntry), false, "cudaMalloc(schedule entries)");
+        ENS(tc.h_items[k], std::max<size_t>(1, nitems) * sizeof(DcsbMixItem), true, "cudaMallocHost(mix items)");
+        ENS(tc.d_items[k], std::max<size_t>(1, nitems) * sizeof(DcsbMixItem), false, "cudaMalloc(mix items)");
+        DcsbSchedEntry *he = static_cast<DcsbSchedEntry *>(tc.h_entries[k].p);
+        DcsbMixItem *hi = static_cast<DcsbMixItem *>(tc.h_items[k].p);
+        run_threads(t0, t1, [&](size_t t) {
+            Part &pt = parts[t];
+            DcsbSchedFrame *dst = hf + first[t];
+            const uint32_t eb = (uint32_t)ebase[t];
+            for (size_t f = 0; f < pt.frames.size(); ++f) { dst[f] = pt.frames[f]; dst[f].first_entry += eb; }
+            if (!pt.entries.empty()) memcpy(he + ebase[t], pt.entries.data(), pt.entries.size() * sizeof(DcsbSchedEntry));
+            DcsbMixItem *it = hi + ibase[t - t0];
+            const uint32_t nf = timelines[t].n_frames, f0 = (uint32_t)first[t];
+            for (uint32_t f = 0; f < nf; f += item_len) *it++ = DcsbMixItem{ f0 + f, std::min<uint32_t>(item_len, nf - f), f0, (uint32_t)t };
+            std::vector<DcsbSchedFrame>().swap(pt.frames);
+            std::vector<DcsbSchedEntry>().swap(pt.entries);
+        });
+        lap("staged", (int)k);
+        const uint64_t cf0 = first[t0], cfn = first[t1] - first[t0];
+        if (cfn == 0 || nitems == 0) continue;
+        e = cudaMemcpyAsync(static_cast<DcsbSchedFrame *>(tc.d_frames.p) + cf0, hf + cf0, cfn * sizeof(DcsbSchedFrame), cudaMemcpyHostToDevice, tc.st);
+        if (e == cudaSuccess && nent) e = cudaMemcpyAsync(tc.d_entries[k].p, he, nent * sizeof(DcsbSchedEntry), cudaMemcpyHostToDevice, tc.st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(tc.d_items[k].p, hi, nitems * sizeof(DcsbMixItem), cudaMemcpyHostToDevice, tc.st);
+        if (e == cudaSuccess)
+            e = dcsb_launch_mix(fam93, b->d_slab, b->d_recs, tc.d_items[k].p, (int)nitems, tc.d_frames.p, tc.d_entries[k].p, ctx->d_tables,
+                                b->scan, (int16_t *)tc.d_pcm.p, (unsigned long long *)tc.d_csum.p, tc.st);
+        if (e == cudaSuccess && pinned)
+            e = cudaMemcpyAsync(pcm_out + cf0 * 240, (const int16_t *)tc.d_pcm.p + cf0 * 240, cfn * 480, cudaMemcpyDeviceToHost, tc.st);
+        lap("queued", (int)k);
+    }
+#undef ENS
+    if (e == cudaSuccess) e = cudaStreamSynchronize(tc.st);
+    lap("GPU done", -1);
+    if (e == cudaSuccess && !pinned) {
+        if (packed) e = cudaMemcpy(pcm_out, tc.d_pcm.p, total * 480, cudaMemcpyDeviceToHost);
         else
             for (size_t t = 0; t < n && e == cudaSuccess; ++t)
-                if (count[t]) e = cudaMemcpy(pcm_out + pcm_offsets[t], (const int16_t *)bufs.d_pcm.p + (size_t)first[t] * 240,
-                                             (size_t)count[t] * 480, cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess && results) {
-            std::vector<unsigned long long> cs(n);
-            e = cudaMemcpy(cs.data(), bufs.d_csum.p, n * 8, cudaMemcpyDeviceToHost);
-            for (size_t t = 0; t < n; ++t) {
-                results[t].status = parts[t].fatal ? DCSB_E_STOPPED : DCSB_OK;
-                results[t].frames = count[t];
-                results[t].checksum = cs[t];
-                results[t].n_host_bytes = parts[t].nhost;
-                results[t].reserved = 0;
-            }
+                if (timelines[t].n_frames)
+                    e = cudaMemcpy(pcm_out + pcm_offsets[t], (const int16_t *)tc.d_pcm.p + first[t] * 240,
+                                   (size_t)timelines[t].n_frames * 480, cudaMemcpyDeviceToHost);
+        lap("PCM on the host", -1);
+    }
+    if (e == cudaSuccess && results) {
+        std::vector<unsigned long long> cs(n);
+        e = cudaMemcpy(cs.data(), tc.d_csum.p, n * 8, cudaMemcpyDeviceToHost);
+        for (size_t t = 0; t < n; ++t) {
+            results[t].status = parts[t].fatal ? DCSB_E_STOPPED : DCSB_OK;
+            results[t].frames = timelines[t].n_frames;
+            results[t].checksum = cs[t];
+            results[t].n_host_bytes = parts[t].nhost;
+            results[t].reserved = 0;
         }
     }
-    lap("PCM on the host");
-    bufs.release();
-    lap("buffers released");
-    if (rc != DCSB_OK) return rc;
-    if (e != cudaSuccess) return fail(ctx, DCSB_E_CUDA, "dcsb_render_timelines: D2H", e);
+    if (e != cudaSuccess) return fail(ctx, DCSB_E_CUDA, "dcsb_render_timelines", e);
     return DCSB_OK;
 }

@@ -154,14 +154,6 @@ DCSB_HD uint32_t dcsb_tx_load(DcsbTxBase tb, uint32_t v)
     asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(a));
     return r;
 }
-// the multi-symbol half of an entry alone (the high byte)
-DCSB_HD uint32_t dcsb_tx_load8(DcsbTxBase tb, uint32_t v)
-{
-    uint32_t a, r;
-    asm("lop3.b32 %0, %1, 0x3FFE, %2, 0xEA;" : "=r"(a) : "r"(v), "r"(tb));
-    asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(r) : "r"(a));
-    return r;
-}
 typedef uint32_t DcsbRingPtr;
 #else
 typedef const uint8_t *DcsbTxBase;
@@ -171,15 +163,7 @@ DCSB_HD uint32_t dcsb_tx_load(DcsbTxBase tb, uint32_t v)
     memcpy(&r, tb + (v & 0x3FFEu), 2);
     return r;
 }
-DCSB_HD uint32_t dcsb_tx_load8(DcsbTxBase tb, uint32_t v) { return tb[(v & 0x3FFEu) + 1]; }
 typedef uint8_t *DcsbRingPtr;
-#endif
-
-// Huffman loop variant: 1 = while at least 8 slots are left in the band the multi-symbol step
-// cannot overrun it, so it is taken without looking at the single-codeword half (one byte load,
-// no compare / select on the position chain); 0 = every step compares.
-#ifndef DCSB_SCAN_VARIANT_DEFAULT
-#define DCSB_SCAN_VARIANT_DEFAULT 1
 #endif
 
 // Band descriptor: what the band loop needs to know about a band of the current frame.
@@ -220,7 +204,6 @@ DCSB_HD int dcsb_ctz(uint32_t v)
 // from the end checkpoint the previous call left at frame f0 (status DCSB_SCAN_RUNNING); that is
 // what lets dcsb_decode_streams cut a chunk into time slices whose PCM drains over PCIe while
 // the later slices are still being scanned.
-template <int VAR = DCSB_SCAN_VARIANT_DEFAULT>
 DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *streams, int si, const DcsbTables *tab,
                                 const uint16_t *lut, DcsbTxBase tx, const uint32_t *dtab, DcsbRingPtr ring, uint32_t *desc,
                                 const DcsbScanOut &out, uint32_t f0 = 0, uint32_t f1 = 0xFFFFFFFFu)
@@ -355,29 +338,6 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
                 const DcsbTxBase tb = tx + (((d >> 24) & 7u) << 14);
                 int Rs = (int)(d & 0x3FFFFu);
                 int t = 50 - (int)win.s;
-                if (VAR == 1) {
-                    // at least 8 slots left: a multi-symbol step (<= 8 slots) cannot overrun the band.
-                    // Rf = 16 * slots left + 15; two steps per refill while 16 slots are left, then one
-                    int Rf = Rs >> 8;
-                    while (Rf >= 16 * 16 + 15) {
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            DCSB_DBG(++dbg_steps;)
-                            const uint32_t m = dcsb_tx_load8(tb, (uint32_t)((((uint64_t)win.w0 << 32) | win.w1) >> t));
-                            t -= (int)(m & 15u);
-                            Rf -= (int)(m & 0xF0u);
-                        }
-                        win.refill_t(t);
-                    }
-                    if (Rf >= 8 * 16 + 15) {
-                        DCSB_DBG(++dbg_steps;)
-                        const uint32_t m = dcsb_tx_load8(tb, (uint32_t)((((uint64_t)win.w0 << 32) | win.w1) >> t));
-                        t -= (int)(m & 15u);
-                        Rf -= (int)(m & 0xF0u);
-                        win.refill_t(t);
-                    }
-                    Rs = (Rf << 8) | 0xFF;
-                }
                 while (Rs > 0x0FFF) {
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
