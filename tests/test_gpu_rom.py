@@ -112,3 +112,40 @@ def test_gpu_timeline_vs_reference_fresh(ctx, os_version, seed):
     bad = np.nonzero(pcm[0] != want)[0]
     assert bad.size == 0, "first differing frame %d" % (bad[0] // 240)
     rom.close()
+
+
+def test_gpu_render_timelines_output_placements(ctx):
+    """dcsb_render_timelines writes the same PCM whichever way the caller wants it: packed into a
+    pageable buffer (blocking copy), packed into a page-locked buffer (asynchronous chunk-by-chunk
+    download beside the sequencer threads), or at the caller's own offsets; several chunks
+    (> 65 536 frames per chunk boundary) so that the pipeline really has more than one stage."""
+    import ctypes as C
+    import torch
+    import dcsexplorer_b200 as dx
+    sc = romscen.make_scenario(os_version=rb.OS94, seed=88, n_frames=400)
+    rom = dx.Rom(sc["images"])
+    tls = [([(f + i % 7, b) for f, b in sc["writes"]], 380 + (i % 5) * 9, 255 - (i % 50)) for i in range(520)]
+    pcm, res = ctx.render_timelines(rom, tls)                     # pageable, packed
+    total = sum(t[1] for t in tls)
+    assert total > 3 * 65536 and all(r["status"] == 0 for r in res)
+    tl_arr, keep = dx.make_timelines(tls)
+    resarr = (dx.TimelineResult * len(tls))()
+    pinned = torch.zeros(total * 240, dtype=torch.int16).pin_memory()
+    assert ctx._L.dcsb_render_timelines(ctx._h, rom._h, tl_arr, len(tls), pinned.data_ptr(), None, resarr) == 0
+    assert np.array_equal(pinned.numpy(), np.concatenate(pcm))
+    assert [resarr[i].checksum for i in range(len(tls))] == [r["checksum"] for r in res]
+    # caller-chosen offsets: timelines in reverse order with a gap of 100 samples between them
+    offs = np.zeros(len(tls), dtype=np.uint64)
+    o = 0
+    for i in reversed(range(len(tls))):
+        offs[i] = o
+        o += tls[i][1] * 240 + 100
+    out = np.full(o, 0x5A5A, dtype=np.int16)
+    assert ctx._L.dcsb_render_timelines(ctx._h, rom._h, tl_arr, len(tls), out.ctypes.data, offs.ctypes.data, resarr) == 0
+    for i in (0, 1, 257, len(tls) - 1):
+        assert np.array_equal(out[int(offs[i]):int(offs[i]) + tls[i][1] * 240], pcm[i]), i
+        assert (out[int(offs[i]) + tls[i][1] * 240:int(offs[i]) + tls[i][1] * 240 + 100] == 0x5A5A).all()
+    # a sample against the CPU-side simulator
+    want, _, _, _ = simutil.rom_render(sc["images"], [tls[3], tls[519]])
+    assert np.array_equal(pcm[3], want[0]) and np.array_equal(pcm[519], want[1])
+    rom.close()
