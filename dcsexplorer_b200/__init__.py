@@ -241,6 +241,17 @@ class Rom:
         return dict(address=t.address, channel=t.channel, type=t.type, defer_code=t.defer_code,
                     looping=bool(t.looping), time=t.time)
 
+    def decompile_track(self, track, raw=False):
+        """DecompileTrackProgram: list of step dicts (raw=True: the dcsb_opcode records as bytes, and their count)"""
+        n = self._L.dcsb_rom_decompile_track(self._h, track, None, 0)
+        arr = (_capi.Opcode * max(1, n))()
+        self._L.dcsb_rom_decompile_track(self._h, track, arr, n)
+        if raw:
+            return bytes(arr)[:n * C.sizeof(_capi.Opcode)], n
+        return [dict(offset=o.offset, nesting_level=o.nesting_level, loop_parent=o.loop_parent, delay_count=o.delay_count,
+                     opcode=o.opcode, operands=bytes(o.operand_bytes[:o.n_operand_bytes]), desc=o.desc.decode(),
+                     hex_desc=o.hex_desc.decode()) for o in arr[:n]]
+
     def list_streams(self):
         n = self._L.dcsb_rom_list_streams(self._h, None, 0)
         out = np.zeros(max(1, n), dtype=np.uint32)

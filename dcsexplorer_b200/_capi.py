@@ -32,6 +32,12 @@ class TrackInfo(C.Structure):
                 ("looping", C.c_uint8), ("reserved", C.c_uint8), ("time", C.c_uint32)]
 
 
+class Opcode(C.Structure):
+    _fields_ = [("offset", C.c_int32), ("nesting_level", C.c_int32), ("loop_parent", C.c_int32), ("delay_count", C.c_uint16),
+                ("opcode", C.c_uint8), ("n_operand_bytes", C.c_uint8), ("operand_bytes", C.c_uint8 * 8),
+                ("desc", C.c_char * 64), ("hex_desc", C.c_char * 40)]
+
+
 class PortWrite(C.Structure):
     _fields_ = [("frame", C.c_uint32), ("byte", C.c_uint8), ("pad", C.c_uint8 * 3)]
 
@@ -64,6 +70,7 @@ SYMBOLS = {
     "dcsb_rom_check": (C.c_int, [C.c_void_p]),
     "dcsb_rom_get_info": (C.c_int, [C.c_void_p, C.POINTER(RomInfo)]),
     "dcsb_rom_track_info": (C.c_int, [C.c_void_p, C.c_uint16, C.POINTER(TrackInfo)]),
+    "dcsb_rom_decompile_track": (C.c_size_t, [C.c_void_p, C.c_uint16, C.c_void_p, C.c_size_t]),
     "dcsb_rom_list_streams": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "dcsb_rom_pointer": (C.c_void_p, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
     "dcsb_rom_last_error": (C.c_char_p, [C.c_void_p]),

@@ -71,6 +71,14 @@ extern "C" int dcsb_rom_get_info(const dcsb_rom *rom, dcsb_rom_info *info)
     return DCSB_OK;
 }
 
+extern "C" size_t dcsb_rom_decompile_track(const dcsb_rom *rom, uint16_t track, dcsb_opcode *steps, size_t max)
+{
+    if (!rom) return 0;
+    const std::vector<dcsb_opcode> v = rom->decompile_track(track);
+    for (size_t i = 0; i < v.size() && i < max && steps; ++i) steps[i] = v[i];
+    return v.size();
+}
+
 extern "C" int dcsb_rom_track_info(const dcsb_rom *rom, uint16_t track, dcsb_track_info *info)
 {
     if (!rom || !info) return 0;

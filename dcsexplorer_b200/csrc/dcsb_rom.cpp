@@ -277,6 +277,98 @@ bool dcsb_rom::track_info(uint16_t track, dcsb_track_info *ti) const
     return true;
 }
 
+// The steps of a type-1 track program, described the way the reference's decompiler describes them
+// (DCSDecoder.cpp:885-1135): same step boundaries (its operand sizes, incl. the 3-byte opcode 4 of
+// OS93a), same loop bookkeeping (loop_parent = the reference's "parentOffset": the number of steps
+// up to and including the loop's own), same mnemonic and hex wording.  The walk ends behind End,
+// an invalid opcode, or a step that waits forever.
+std::vector<dcsb_opcode> dcsb_rom::decompile_track(uint16_t track) const
+{
+    std::vector<dcsb_opcode> v;
+    dcsb_track_info ti;
+    if (!track_info(track, &ti) || ti.type != 1) return v;
+    DcsbRomPtr p = make_ptr(ti.address);
+    const uint32_t start = p.ofs;
+    p.ofs += 2;
+    std::vector<int> loops;
+    auto chtag = [&](int ch, const char *sep) { char b[24] = ""; if (ch != ti.channel) snprintf(b, sizeof(b), "channel %d,%s", ch, sep); return std::string(b); };
+    for (bool done = false; !done && v.size() < 65536;) {
+        dcsb_opcode e;
+        memset(&e, 0, sizeof(e));
+        e.nesting_level = (int32_t)loops.size();
+        e.loop_parent = loops.empty() ? -1 : loops.back();
+        e.offset = (int32_t)(p.ofs - start);
+        e.delay_count = (uint16_t)be(p, 2);
+        if (e.delay_count == 0xFFFF) done = true;
+        e.opcode = u8(p, 2);
+        p.ofs += 3;
+        // (the decompiler's own operand sizes: unlike GetTrackInfo's walk it takes 2 bytes for $10 and 4 for $11 / $12)
+        const int nops = e.opcode == 0x10 ? 2 : (e.opcode == 0x11 || e.opcode == 0x12) ? 4 : e.opcode < 0x10 ? opcode_operand_bytes(e.opcode) : 0;
+        uint8_t o[8] = { 0 };
+        for (int i = 0; i < nops && i < 8; ++i) o[i] = u8(p, (uint32_t)i);
+        const unsigned w01 = (o[0] << 8) | o[1], w23 = (o[2] << 8) | o[3];
+        char d[96] = "", h[64] = "";
+        switch (e.opcode) {
+        case 0x00: snprintf(d, sizeof(d), "End;"); done = true; break;
+        case 0x01: {
+            const unsigned sp = (o[1] << 16) | (o[2] << 8) | o[3];
+            snprintf(h, sizeof(h), " %02X %06X %02X", o[0], sp, o[4]);
+            const std::string tag = chtag(o[0], "");
+            if (o[4] == 0) snprintf(d, sizeof(d), "Play(%sstream $%06X, repeat forever);", tag.c_str(), sp);
+            else if (o[4] == 1) snprintf(d, sizeof(d), "Play(%sstream $%06X);", tag.c_str(), sp);
+            else snprintf(d, sizeof(d), "Play(%sstream $%06X, repeat %d);", tag.c_str(), sp, o[4]);
+            break;
+        }
+        case 0x02: snprintf(h, sizeof(h), " %02X", o[0]); snprintf(d, sizeof(d), "Stop(channel %d);", o[0]); break;
+        case 0x03: snprintf(h, sizeof(h), " %04X", w01); snprintf(d, sizeof(d), "Queue(track $%0X);", w01); break;
+        case 0x04:
+            if (os == DCSB_OS93A) {
+                const unsigned cnt = (o[1] << 8) | o[2];
+                snprintf(h, sizeof(h), " %02X %04X", o[0], cnt);
+                snprintf(d, sizeof(d), "SetChannelTimer(byte $%02X, counter $%04X);", o[0], cnt);
+            } else {
+                snprintf(h, sizeof(h), " %02X", o[0]);
+                snprintf(d, sizeof(d), "WriteDataPort(byte $%02X);", o[0]);
+            }
+            break;
+        case 0x05: snprintf(h, sizeof(h), " %02X", o[0]); snprintf(d, sizeof(d), "StartDeferred(channel %d);", o[0]); break;
+        case 0x06: snprintf(h, sizeof(h), " %02X %02X", o[0], o[1]); snprintf(d, sizeof(d), "SetVariable(var $%02X, value $%02X);", o[0], o[1]); break;
+        case 0x07: case 0x08: case 0x09:
+            snprintf(h, sizeof(h), " %02X %02X", o[0], o[1]);
+            snprintf(d, sizeof(d), "SetMixingLevel(%s%s %d);", chtag(o[0], " ").c_str(),
+                     e.opcode == 7 ? "level" : e.opcode == 8 ? "increase" : "decrease", o[1]);
+            break;
+        case 0x0A: case 0x0B: case 0x0C:
+            snprintf(h, sizeof(h), " %02X %02X %04X", o[0], o[1], w23);
+            snprintf(d, sizeof(d), "SetMixingLevel(%s%s %u, steps %u);", chtag(o[0], " ").c_str(),
+                     e.opcode == 0x0A ? "level" : e.opcode == 0x0B ? "increase" : "decrease", o[1], w23);
+            break;
+        case 0x0D: snprintf(d, sizeof(d), "NOP;"); break;
+        case 0x0E:
+            snprintf(h, sizeof(h), " %02X", o[0]);
+            if (o[0]) snprintf(d, sizeof(d), "Loop (%d) {", o[0]); else snprintf(d, sizeof(d), "Loop {");
+            loops.push_back((int)v.size() + 1);
+            break;
+        case 0x0F:
+            if (!loops.empty()) { loops.pop_back(); snprintf(d, sizeof(d), "}"); } else snprintf(d, sizeof(d), "LoopEnd");
+            break;
+        case 0x10: snprintf(h, sizeof(h), " %02X %02X", o[0], o[1]); snprintf(d, sizeof(d), "Opcode$10($%02X,$%02X);", o[0], o[1]); break;
+        case 0x11: case 0x12:
+            snprintf(h, sizeof(h), " %02X %02X %04X", o[0], o[1], w23);
+            snprintf(d, sizeof(d), "Opcode$%02x($%02X,$%02X,$%04X);", e.opcode, o[0], o[1], w23);
+            break;
+        default: snprintf(d, sizeof(d), "InvalidOpcode$%02X;", e.opcode); done = true; break;
+        }
+        p.ofs += (uint32_t)nops;
+        e.n_operand_bytes = (uint8_t)nops;
+        memcpy(e.operand_bytes, o, 8);
+        snprintf(e.desc, sizeof(e.desc), "%s", d);
+        snprintf(e.hex_desc, sizeof(e.hex_desc), "%04X %02X%s", e.delay_count, e.opcode, h);
+        v.push_back(e);
+    }
+    return v;
+}
+
 // every stream a Play opcode (0x01) of a type-1 track refers to, ascending.
 // as_executed = false: the reference's ListStreams (DCSDecoder.cpp:1248-1293), which walks the
 // programs with DecompileTrackProgram's operand sizes (:886-1126) -- on 1993 software that

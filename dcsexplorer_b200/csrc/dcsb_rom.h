@@ -72,6 +72,7 @@ struct dcsb_rom {
     uint32_t u2_be(uint32_t ofs, int nbytes) const;
     int num_channels() const;
     bool track_info(uint16_t track, dcsb_track_info *ti) const;
+    std::vector<dcsb_opcode> decompile_track(uint16_t track) const;
     std::vector<uint32_t> list_streams(bool as_executed = false) const;
     int search_opcodes(const char *pattern, uint32_t from, uint32_t nbytes, std::unordered_map<char, uint32_t> *vars) const;
     int opcode_operand_bytes(int opcode) const;     // as GetTrackInfo / the decompiler count them

@@ -99,6 +99,58 @@ public:
         ti.deferCode = t.defer_code; ti.time = t.time; ti.looping = t.looping != 0;
         return true;
     }
+    struct Opcode {                                                                                     // DCSDecoder.h:432-480
+        int offset = 0, nestingLevel = 0, loopParent = -1;
+        uint16_t delayCount = 0;
+        uint8_t opcode = 0;
+        int nOperandBytes = 0;
+        uint8_t operandBytes[8] { 0, 0, 0, 0, 0, 0, 0, 0 };
+        std::string desc, hexDesc;
+    };
+    std::vector<Opcode> DecompileTrackProgram(uint16_t trackNumber) const                               // DCSDecoder.h:481
+    {
+        std::vector<dcsb_opcode> raw(rom ? dcsb_rom_decompile_track(rom, trackNumber, nullptr, 0) : 0);
+        if (!raw.empty()) dcsb_rom_decompile_track(rom, trackNumber, raw.data(), raw.size());
+        std::vector<Opcode> v(raw.size());
+        for (size_t i = 0; i < raw.size(); ++i) {
+            v[i].offset = raw[i].offset; v[i].nestingLevel = raw[i].nesting_level; v[i].loopParent = raw[i].loop_parent;
+            v[i].delayCount = raw[i].delay_count; v[i].opcode = raw[i].opcode; v[i].nOperandBytes = raw[i].n_operand_bytes;
+            for (int k = 0; k < 8; ++k) v[i].operandBytes[k] = raw[i].operand_bytes[k];
+            v[i].desc = raw[i].desc; v[i].hexDesc = raw[i].hex_desc;
+        }
+        return v;
+    }
+    // DCSDecoder.h:418-425 / DCSDecoder.cpp:1137-1228: the listing DCSExplorer prints for a track.  (The reference's
+    // format string for a deferred track, "%Deferred", has a stray conversion; the intended text is produced here.)
+    std::string ExplainTrackProgram(uint16_t trackNumber, const char *linePrefix) const
+    {
+        TrackInfo ti;
+        if (!GetTrackInfo(trackNumber, ti)) return "[Invalid track]";
+        char buf[256];
+        if (ti.type == 2) { snprintf(buf, sizeof(buf), "%sDeferred ($%04x)", linePrefix, ti.deferCode); return buf; }
+        if (ti.type == 3) { snprintf(buf, sizeof(buf), "%sDeferred Indirect ($%02x[$%02x])", linePrefix, ti.deferCode & 0xFF, ti.deferCode >> 8); return buf; }
+        std::string program, loopIndent;
+        for (auto &ele : DecompileTrackProgram(trackNumber)) {
+            if (!program.empty()) program += "\n";
+            std::string wait;
+            if (ele.delayCount == 0xFFFFu) wait = "Wait(Forever) ";
+            else if (ele.delayCount != 0) { snprintf(buf, sizeof(buf), "Wait(%u) ", ele.delayCount); wait = buf; }
+            std::string comment = "// " + ele.hexDesc;
+            if (ele.opcode == 0x0F) {
+                if (ele.delayCount != 0 && !loopIndent.empty()) {
+                    snprintf(buf, sizeof(buf), "%-60s    %s\n", (loopIndent + wait).c_str(), comment.c_str());
+                    program += std::string(linePrefix) + buf;
+                    wait.clear(); comment.clear();
+                }
+                if (!loopIndent.empty()) loopIndent = loopIndent.substr(2);
+                else comment += " Unmatched loop end opcode (0x0F)";
+            }
+            snprintf(buf, sizeof(buf), "%-60s    %s", (loopIndent + wait + ele.desc).c_str(), comment.c_str());
+            program += std::string(linePrefix) + buf;
+            if (ele.opcode == 0x0E) loopIndent += "  ";
+        }
+        return program;
+    }
     std::list<uint32_t> ListStreams() const                                                             // DCSDecoder.h:486
     {
         std::vector<uint32_t> v(rom ? dcsb_rom_list_streams(rom, nullptr, 0) : 0);

@@ -171,6 +171,20 @@ int  dcsb_rom_load_zip(dcsb_rom *rom, const char *zip_path, const char *explicit
 int  dcsb_rom_check(dcsb_rom *rom);                                    /* CheckROMs(): POST code */
 int  dcsb_rom_get_info(const dcsb_rom *rom, dcsb_rom_info *info);
 int  dcsb_rom_track_info(const dcsb_rom *rom, uint16_t track, dcsb_track_info *info);   /* 1 = valid track, 0 = not */
+/* DecompileTrackProgram (DCSDecoder.h:432-481, DCSDecoder.cpp:885-1135): the steps of a type-1 track program.
+ * Writes up to max steps, returns how many the program has (0: no such track / not a type-1 track). */
+typedef struct dcsb_opcode {
+    int32_t  offset;            /* byte offset of the step's delay count inside the track */
+    int32_t  nesting_level;     /* loops around the step */
+    int32_t  loop_parent;       /* as the reference numbers it: 1 + index of the enclosing loop's step, -1 = top level */
+    uint16_t delay_count;       /* frames to wait before the step; 0xFFFF = forever */
+    uint8_t  opcode;
+    uint8_t  n_operand_bytes;
+    uint8_t  operand_bytes[8];
+    char     desc[64];          /* mnemonic form, the reference's wording */
+    char     hex_desc[40];      /* count, opcode and operands as grouped hex numbers */
+} dcsb_opcode;
+size_t dcsb_rom_decompile_track(const dcsb_rom *rom, uint16_t track, dcsb_opcode *steps, size_t max);
 /* distinct stream addresses referenced by Play opcodes, ascending; returns how many exist */
 size_t dcsb_rom_list_streams(const dcsb_rom *rom, uint32_t *addresses, size_t max);
 /* MakeROMPointer: pointer into the rom's own copy of the chip + bytes left in that chip */

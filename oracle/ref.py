@@ -44,6 +44,7 @@ def lib():
         L.dcsref_rom_open_images.restype = C.c_void_p
         L.dcsref_rom_open_images.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.dcsref_rom_track_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.dcsref_rom_decompile.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         _LIB = L
     return _LIB
 
@@ -136,6 +137,12 @@ class RomPlayer:
         out = np.zeros(7, dtype=np.uint32)
         lib().dcsref_rom_track_info(self._h, track, out.ctypes.data)
         return [int(x) for x in out]
+
+    def decompile(self, track, cap=512):
+        """DecompileTrackProgram as raw records (the byte layout of dcsb_opcode, 128 bytes each)"""
+        buf = np.zeros(cap * 128, dtype=np.uint8)
+        n = lib().dcsref_rom_decompile(self._h, track, buf.ctypes.data, cap)
+        return buf[:min(n, cap) * 128].tobytes(), n
 
     def render_timeline(self, writes, n_frames):
         """writes: list of (frame, byte), sorted by frame"""

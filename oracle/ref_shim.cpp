@@ -319,4 +319,27 @@ int dcsref_rom_track_info(void *h, int track, uint32_t *out)
     return ok;
 }
 
+// DecompileTrackProgram (DCSDecoder.h:481): per step 5 ints {offset, nestingLevel, loopParent, delayCount, opcode},
+// nOperandBytes + 8 operand bytes, desc (64 chars), hexDesc (40 chars) -- the layout of dcsb_opcode
+struct RefOpcode { int32_t offset, nesting, parent; uint16_t delay; uint8_t opcode, nops; uint8_t ops[8]; char desc[64]; char hex[40]; };
+int dcsref_rom_decompile(void *h, int track, RefOpcode *out, int cap)
+{
+    auto *c = static_cast<RomCtx *>(h);
+    auto v = c->dec->DecompileTrackProgram(static_cast<uint16_t>(track));
+    int n = 0;
+    for (auto &op : v) {
+        if (n < cap) {
+            RefOpcode &o = out[n];
+            memset(&o, 0, sizeof(o));
+            o.offset = op.offset; o.nesting = op.nestingLevel; o.parent = op.loopParent;
+            o.delay = op.delayCount; o.opcode = op.opcode; o.nops = static_cast<uint8_t>(op.nOperandBytes);
+            memcpy(o.ops, op.operandBytes, 8);
+            snprintf(o.desc, sizeof(o.desc), "%s", op.desc.c_str());
+            snprintf(o.hex, sizeof(o.hex), "%s", op.hexDesc.c_str());
+        }
+        ++n;
+    }
+    return n;
+}
+
 } // extern "C"

@@ -51,6 +51,8 @@ int main(int argc, char **argv)
         auto rp = dec.MakeROMPointer(ti.address);
         printf("track 0: type %d channel %d time %u looping %d first byte %02x\n", ti.type, ti.channel, ti.time, (int)ti.looping, rp.p ? rp.p[0] : 0);
     }
+    printf("%s\n", dec.ExplainTrackProgram(0, "  ").c_str());
+    printf("track 0: %zu steps\n", dec.DecompileTrackProgram(0).size());
     for (uint32_t a : dec.ListStreams()) {
         auto si = dec.GetStreamInfo(dec.MakeROMPointer(a));
         printf("stream $%06x: %d frames, %d bytes, type %d.%d\n", a, si.nFrames, si.nBytes, si.streamType, si.streamSubType);

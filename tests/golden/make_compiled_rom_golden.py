@@ -230,6 +230,9 @@ def main():
             out[name + "/host"] = np.frombuffer(hb, dtype=np.uint8)
             out[name + "/streams"] = np.array(rp.list_streams(), dtype=np.uint32)
             out[name + "/tracks"] = np.array([rp.track_info(t) for t in range(ntracks)], dtype=np.uint32)
+            dec = [rp.decompile(t) for t in range(ntracks)]        # DecompileTrackProgram: dcsb_opcode-shaped records
+            out[name + "/decompile_counts"] = np.array([n for _, n in dec], dtype=np.int32)
+            out[name + "/decompile"] = np.frombuffer(b"".join(b for b, _ in dec), dtype=np.uint8)
             chans = (pcm.reshape(-1, 240) != 0).any(axis=1).sum()
             rp.close()
             # every track on its own: fresh decoder, command at frame 1

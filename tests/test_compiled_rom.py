@@ -32,6 +32,37 @@ def test_compiled_rom_model_through_the_c_abi(built, name):
 
 
 @pytest.mark.parametrize("name", compiledrom.NAMES)
+def test_compiled_rom_decompile_matches_reference(built, name):
+    """DecompileTrackProgram (DCSDecoder.h:481): every step of all 72 track programs -- offsets, loop
+    nesting and parents, delay counts, opcodes, operand bytes, the mnemonic and the hex text -- equals
+    what the reference's decompiler produced (records frozen in the fixture, byte for byte)."""
+    import dcsexplorer_b200 as dx
+    c = compiledrom.load(name)
+    rom = dx.Rom(c["images"])
+    assert rom.check() == 1
+    counts = c["g"][name + "/decompile_counts"]
+    blob = c["g"][name + "/decompile"].tobytes()
+    o = 0
+    kinds = set()
+    for t in range(c["n_tracks"]):
+        raw, n = rom.decompile_track(t, raw=True)
+        assert n == int(counts[t]), hex(t)
+        want = blob[o:o + 128 * n]
+        o += 128 * n
+        if raw != want:
+            for k in range(n):
+                assert raw[128 * k:128 * k + 128] == want[128 * k:128 * k + 128], "track $%04X step %d: %r" % (t, k, want[128 * k + 24:128 * k + 88])
+        for st in rom.decompile_track(t):
+            kinds.add(st["opcode"])
+    assert o == len(blob)
+    assert {0x00, 0x01, 0x02, 0x03, 0x04, 0x05, 0x06, 0x07, 0x08, 0x09, 0x0A, 0x0B, 0x0C, 0x0E, 0x0F} <= kinds
+    assert rom.decompile_track(0x35) == [] and rom.decompile_track(c["n_tracks"]) == []     # deferred track / no such track
+    st = rom.decompile_track(0x2F)[1]
+    assert st["desc"].startswith("Play(channel 4,stream $") and st["desc"].endswith(", repeat 2);") and st["opcode"] == 1
+    rom.close()
+
+
+@pytest.mark.parametrize("name", compiledrom.NAMES)
 def test_compiled_rom_sim_matches_reference(built, name):
     c = compiledrom.load(name)
     pcm, res, info, hb = simutil.rom_render(c["images"], [(c["writes"], c["n_frames"], c["master_volume"])])

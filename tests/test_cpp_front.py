@@ -57,6 +57,9 @@ def test_cpp_front_matches_golden(demo, tmp_path, name, chunk):
     check_rom_golden(g, name, pcm, hb)
     assert "6 channels" in line and ("DCS-95" in line) == (sc["os"] == rb.OS95)
     assert "track 0: type 1 channel 0" in r.stdout and "stream $" in r.stdout
+    # ExplainTrackProgram / DecompileTrackProgram: track 0 = SetMixingLevel(level 100); Play(...); wait forever
+    assert "  SetMixingLevel(level 100);" in r.stdout and "Play(stream $" in r.stdout and "Wait(Forever) " in r.stdout
+    assert "track 0: 3 steps" in r.stdout
 
 
 @pytest.mark.gpu

@@ -137,6 +137,26 @@ def test_zip_loader(built, tmp_path):
 
 
 @needs_ref
+@pytest.mark.parametrize("name", ["os94", "os95-v105", "os93b", "os93a", "os94-errors"])
+def test_decompile_vs_reference(built, name):
+    """DecompileTrackProgram against the reference on the hand-assembled ROM sets: OS93a's 3-byte
+    opcode 4, the $10-$12 opcodes, nops, nested and endless loops, unpopulated and deferred tracks."""
+    import dcsexplorer_b200 as dx
+    sc = romscen.make_scenario(**dict(romscen.SCENARIOS)[name])
+    rp = ref.RomPlayer(sc["images"], 255)
+    rom = dx.Rom(sc["images"])
+    assert rom.check() == 1
+    total = 0
+    for t in range(sc["n_tracks"] + 1):
+        want, n = rp.decompile(t)
+        got, m = rom.decompile_track(t, raw=True)
+        assert (m, got) == (n, want), "track %d" % t
+        total += n
+    assert total > 60
+    rp.close(); rom.close()
+
+
+@needs_ref
 def test_zip_loader_vs_reference_zip_loader(built, tmp_path):
     """The same zip through the reference's LoadROMFromZipFile (DCSDecoderZipLoader.cpp, miniz) and
     through dcsb_rom_load_zip: same chips identified, same version info, same stream list; odd
