@@ -528,7 +528,7 @@ void DcsbSequencer::set_master_volume(int vol) { vol_mult = dcsb_master_multipli
 
 void DcsbSequencer::reset_mix(int ch)
 {
-    for (Channel &c : chan) c.mixer[ch].reset();
+    for (Channel &c : chan) { c.mixer[ch].reset(); c.fading &= (uint8_t)~(1u << ch); }
 }
 
 void DcsbSequencer::clear_tracks()
@@ -622,6 +622,7 @@ void DcsbSequencer::mix_op(int cur, DcsbRomPtr &p, int mode, bool fade)
     if (fade) { steps = (int)rom->be(p, 2); p.ofs += 2; }
     Mixer &m = chan[target_ch].mixer[cur];
     m.steps = steps;
+    if (steps) chan[target_ch].fading |= (uint8_t)(1u << cur); else chan[target_ch].fading &= (uint8_t)~(1u << cur);
     const int old = m.cur;
     int lvl = mode == 0 ? param : (mode == 1 ? old + param : old - param);
     const int delta = lvl - old;                // taken before the range limit, as the original does
@@ -743,17 +744,27 @@ void DcsbSequencer::exec_track(int cur)
 void DcsbSequencer::update_levels()
 {
     for (Channel &c : chan)
-        for (Mixer &m : c.mixer) {
+        for (unsigned f = c.fading; f; f &= f - 1) {        // only the mixers with a fade in progress
+            const int k = __builtin_ctz(f);
+            Mixer &m = c.mixer[k];
             if (m.steps == 1) { m.steps = 0; m.cur = m.target; }
             else if (m.steps > 1) {
                 --m.steps;
                 m.cur = std::max(-8191, std::min(8191, m.cur + m.delta));
             }
+            if (m.steps == 0) c.fading &= (uint8_t)~(1u << k);
         }
     for (Channel &c : chan) {
         int sum = 0;
         for (const Mixer &m : c.mixer) sum += m.cur;
-        c.mult = dcsb_level_multiplier(sum, rom->os, c.volume, c.max_override ? 1 : 0);
+        // the multiplier ladder (16 dependent 1.15 multiplies) only when its inputs moved: most frames no fade is running
+        sum = std::max(-8191, std::min(8191, sum));
+        const uint32_t key = (uint32_t)(sum + 8192) | ((uint32_t)c.volume << 14) | (c.max_override ? 1u << 30 : 0u);
+        if (key != c.level_key) {
+            c.level_key = key;
+            c.level_mult = dcsb_level_multiplier(sum, rom->os, c.volume, c.max_override ? 1 : 0);
+        }
+        c.mult = c.level_mult;
     }
     for (Channel &c : chan) {
         c.track_counter += 1;

@@ -119,8 +119,11 @@ private:
         Stream st;
         int source = -1;
         Mixer mixer[DCSB_MAX_CHANNELS];
+        uint8_t fading = 0;                         // mixers with a fade in progress (steps != 0), one bit each
         bool max_override = false;
         uint16_t mult = 0x7FFF;
+        uint32_t level_key = 0xFFFFFFFFu;           // (level sum, volume, override) the cached level_mult belongs to
+        uint16_t level_mult = 0;
         Timer timer;
         uint16_t volume = 0xFF;
         std::vector<Loop> loops;
