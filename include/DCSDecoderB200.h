@@ -51,6 +51,9 @@ public:
         int chipSelect = 0;
         const uint8_t *p = nullptr;
         uint32_t linearAddress = 0;
+        size_t bytesAvailable = 0;      // standalone mode only: readable bytes at p (the reference's decoder reads as far as the bits go)
+        ROMPointer() {}
+        ROMPointer(int chipSelect, const uint8_t *p, size_t bytesAvailable = 0) : chipSelect(chipSelect), p(p), bytesAvailable(bytesAvailable) {}
         bool IsNull() const { return p == nullptr; }
         int NominalChipNumber() const { return chipSelect + 2; }
     };
@@ -74,7 +77,7 @@ public:
 
     const char *Name() const { return "b200"; }                                 // DCSDecoder.h:210
     bool IsOK() const { return errorMessage.empty(); }                          // DCSDecoder.h:213-222
-    bool IsRunning() const { return IsOK() && player != nullptr; }
+    bool IsRunning() const { return IsOK() && (player != nullptr || standalone); }
     std::string GetErrorMessage() const { return errorMessage; }
 
     // ---- ROM load (DCSDecoder.h:285-347).  Images are copied: the caller may free them.
@@ -192,11 +195,48 @@ public:
         return std::string(h) + ", " + s;
     }
 
+    // ---- standalone mode (DCSDecoderNative.h:19-34): no ROMs, streams played from the caller's memory.  It implements the
+    // protocol the reference's own clients use it for (DCSEncoder.cpp:547-571, DCSExplorer.cpp:1655-1721): InitStandalone(os),
+    // SoftBoot(), SetMasterVolume(v), LoadAudioStream(0, ptr, level), then GetNextSample() for as long as wanted -- one stream,
+    // channel 0, decoded as by a freshly booted decoder (dcsb_decode_streams' contract); after the stream and the overlap
+    // tail of its last frame the output is silence, as the reference's is.
+    void InitStandalone(OSVersion os)
+    {
+        DropPlayer();
+        standalone = true;
+        standaloneOS = os == OSVersion::OS93a ? DCSB_OS93A : os == OSVersion::OS93b ? DCSB_OS93B : os == OSVersion::OS95 ? DCSB_OS95 : DCSB_OS94;
+        standaloneVolume = defaultVolume;
+        buf.clear();
+        bufPos = 0;
+    }
+    void LoadAudioStream(int channel, const uint8_t *data, size_t nbytes, int mixingLevel)
+    {
+        if (!standalone || !IsOK()) return;
+        buf.clear();
+        bufPos = 0;
+        standaloneFrames = 0;
+        if (channel != 0) { Fail("dcsb200: standalone mode plays one stream, on channel 0"); return; }
+        dcsb_stream_desc d = dcsb_stream_desc();
+        d.data = data;
+        d.nbytes = static_cast<uint32_t>(nbytes);
+        d.os_version = static_cast<uint16_t>(standaloneOS);
+        d.master_volume = static_cast<uint8_t>(standaloneVolume < 0 ? 0 : standaloneVolume > 255 ? 255 : standaloneVolume);
+        d.mixing_level = static_cast<uint8_t>(mixingLevel);
+        d.tail_frames = 1;                                  // the frame that carries the last frame's overlap tail
+        const uint32_t nf = nbytes >= 2 ? ((static_cast<uint32_t>(data[0]) << 8) | data[1]) : 0;
+        buf.assign(static_cast<size_t>(nf + 1) * 240, 0);
+        dcsb_result r;
+        const uint64_t off = 0;
+        if (dcsb_decode_streams(ctx, &d, 1, buf.data(), &off, &r) != DCSB_OK) { Fail(std::string("dcsb200: ") + dcsb_last_error(ctx)); buf.clear(); return; }
+        standaloneFrames = nf;
+    }
+
     // ---- boot (DCSDecoder.h:577-594)
     void SetDefaultVolume(int vol) { defaultVolume = vol; }
     void SoftBoot()
     {
         if (!IsOK()) return;
+        if (standalone) { standaloneVolume = defaultVolume; buf.clear(); bufPos = 0; standaloneFrames = 0; return; }
         DropPlayer();
         if (Info().hw_version == 0) CheckROMs();
         if (dcsb_player_create(ctx, rom, &player) != DCSB_OK) { Fail(std::string("dcsb200: ") + dcsb_last_error(ctx)); return; }
@@ -213,10 +253,16 @@ public:
     }
 
     // ---- run time
-    void SetMasterVolume(int vol) { if (player) dcsb_player_set_master_volume(player, vol); }          // DCSDecoder.h:546
+    void SetFastBootMode(bool) {}                                                                       // DCSDecoder.h:541 (always fast here)
+    void SetMasterVolume(int vol)                                                                       // DCSDecoder.h:546
+    {
+        if (standalone) standaloneVolume = vol;
+        else if (player) dcsb_player_set_master_volume(player, vol);
+    }
     void WriteDataPort(uint8_t b) { if (player) dcsb_player_write_data_port(player, b); }               // DCSDecoder.h:663
     int16_t GetNextSample()                                                                             // DCSDecoder.h:565
     {
+        if (standalone) return bufPos < buf.size() ? buf[bufPos++] : 0;
         if (!player) return 0;
         if (bufPos >= buf.size()) {
             buf.resize(static_cast<size_t>(chunk) * 240);
@@ -244,13 +290,41 @@ public:
     // ---- DCSDecoderNative extras (DCSDecoderNative.h:34-129)
     void LoadAudioStream(int channel, const ROMPointer &streamPtr, int mixingLevel)
     {
-        if (player) dcsb_player_load_audio_stream(player, channel, streamPtr.linearAddress, mixingLevel);
+        if (standalone) {
+            if (streamPtr.p && streamPtr.bytesAvailable) LoadAudioStream(channel, streamPtr.p, streamPtr.bytesAvailable, mixingLevel);
+            else Fail("dcsb200: a standalone stream needs its size: ROMPointer(0, data, nbytes)");
+        } else if (player) dcsb_player_load_audio_stream(player, channel, streamPtr.linearAddress, mixingLevel);
     }
-    bool IsStreamPlaying(int channel) const { return player && dcsb_player_is_stream_playing(player, channel) != 0; }
+    bool IsStreamPlaying(int channel) const
+    {
+        if (standalone) return channel == 0 && bufPos < static_cast<size_t>(standaloneFrames) * 240;
+        return player && dcsb_player_is_stream_playing(player, channel) != 0;
+    }
     StreamInfo GetStreamInfo(const ROMPointer &streamPtr) const
     {
         StreamInfo si;
         dcsb_stream_info i;
+        if (standalone) {
+            // the reference finds a stream's size by walking all of its frames (DCSDecoderNative.cpp:1486-1537); so does this
+            if (!streamPtr.p || streamPtr.bytesAvailable < 3 || !IsOK()) return si;
+            dcsb_stream_desc d = dcsb_stream_desc();
+            d.data = streamPtr.p;
+            d.nbytes = static_cast<uint32_t>(streamPtr.bytesAvailable);
+            d.os_version = static_cast<uint16_t>(standaloneOS);
+            d.master_volume = 255;
+            d.mixing_level = 0x64;
+            const uint32_t nf = (static_cast<uint32_t>(streamPtr.p[0]) << 8) | streamPtr.p[1];
+            std::vector<int16_t> scratch(static_cast<size_t>(nf ? nf : 1) * 240);
+            dcsb_result r;
+            const uint64_t off = 0;
+            if (dcsb_decode_streams(ctx, &d, 1, scratch.data(), &off, &r) != DCSB_OK || r.stream_bytes == 0) return si;
+            si.nFrames = static_cast<int>(nf);
+            si.nBytes = static_cast<int>(r.stream_bytes);
+            for (size_t k = 0; k < 16 && 2 + k < streamPtr.bytesAvailable; ++k) si.header[k] = streamPtr.p[2 + k];
+            si.streamType = si.header[0] >> 7;
+            if (standaloneOS == DCSB_OS94 || standaloneOS == DCSB_OS95) si.streamSubType = ((si.header[1] & 0x80) >> 6) | ((si.header[1] & 0x80) >> 7);
+            return si;
+        }
         if (player && dcsb_player_stream_info(player, streamPtr.linearAddress, &i) == DCSB_OK) {
             si.nFrames = i.n_frames; si.nBytes = i.n_bytes; si.streamType = i.stream_type; si.streamSubType = i.stream_subtype;
             for (int k = 0; k < 16; ++k) si.header[k] = i.header[k];
@@ -264,6 +338,9 @@ private:
     Host *host;
     int chunk;
     int defaultVolume = 0x67;                           // DCSDecoder.h:1146
+    bool standalone = false;
+    int standaloneOS = DCSB_OS94, standaloneVolume = 0x67;
+    uint32_t standaloneFrames = 0;
     dcsb_ctx *ctx = nullptr;
     dcsb_rom *rom = nullptr;
     dcsb_player *player = nullptr;

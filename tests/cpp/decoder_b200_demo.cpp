@@ -5,6 +5,7 @@
 // timeline.txt: lines "<frame> <byte>" sorted by frame.  Exit code 3 = no usable GPU.
 #include <stdio.h>
 #include <stdlib.h>
+#include <string>
 #include <vector>
 #include "../../include/DCSDecoderB200.h"
 
@@ -13,8 +14,38 @@ struct RecHost : DCSDecoderB200::Host {
     void ReceiveDataPort(uint8_t b) override { bytes.push_back(b); }
 };
 
+// standalone mode, the reference's stream-extraction protocol (DCSExplorer.cpp:1655-1721):
+//   decoder_b200_demo --standalone <os: 9301|9302|9400|9500> <stream.bin> <master_volume> <mixing_level> <n_frames> <out.pcm>
+static int standalone_main(int argc, char **argv)
+{
+    if (argc < 8) return 2;
+    DCSDecoderB200 dec(nullptr, 0, 1);
+    if (!dec.IsOK()) { fprintf(stderr, "%s\n", dec.GetErrorMessage().c_str()); return 3; }
+    std::vector<uint8_t> data;
+    if (FILE *f = fopen(argv[3], "rb")) { int c; while ((c = fgetc(f)) != EOF) data.push_back((uint8_t)c); fclose(f); }
+    const unsigned os = (unsigned)strtoul(argv[2], nullptr, 16);
+    dec.InitStandalone(os == 0x9301 ? DCSDecoderB200::OSVersion::OS93a : os == 0x9302 ? DCSDecoderB200::OSVersion::OS93b
+                     : os == 0x9500 ? DCSDecoderB200::OSVersion::OS95 : DCSDecoderB200::OSVersion::OS94);
+    dec.SoftBoot();
+    dec.SetMasterVolume(atoi(argv[4]));
+    const DCSDecoderB200::ROMPointer rp(0, data.data(), data.size());
+    dec.LoadAudioStream(0, rp, atoi(argv[5]));
+    if (!dec.IsOK()) { fprintf(stderr, "%s\n", dec.GetErrorMessage().c_str()); return 6; }
+    const unsigned nframes = (unsigned)atoi(argv[6]);
+    std::vector<int16_t> pcm((size_t)nframes * 240);
+    unsigned playing = 0;
+    for (size_t i = 0; i < pcm.size(); ++i) { playing += dec.IsStreamPlaying(0) ? 1 : 0; pcm[i] = dec.GetNextSample(); }
+    FILE *o = fopen(argv[7], "wb");
+    fwrite(pcm.data(), 2, pcm.size(), o);
+    fclose(o);
+    auto si = dec.GetStreamInfo(rp);
+    printf("standalone: %d frames, %d bytes, type %d.%d, playing for %u samples\n", si.nFrames, si.nBytes, si.streamType, si.streamSubType, playing);
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
+    if (argc > 1 && std::string(argv[1]) == "--standalone") return standalone_main(argc, argv);
     if (argc < 7) { fprintf(stderr, "usage: %s rom.zip timeline.txt n_frames volume chunk out.pcm\n", argv[0]); return 2; }
     RecHost host;
     DCSDecoderB200 dec(&host, 0, atoi(argv[5]));

@@ -75,3 +75,30 @@ def test_cpp_front_chunked_latency(demo, tmp_path):
         assert r.returncode == 0, r.stderr
         outs.append(np.fromfile(out, dtype=np.int16))
     assert outs[0].any() and np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.gpu
+def test_cpp_front_standalone_stream_protocol(demo, tmp_path, golden):
+    """InitStandalone -> SoftBoot -> SetMasterVolume -> LoadAudioStream(0, ROMPointer(0, data, n), level) -> GetNextSample:
+    the reference's stream-extraction protocol through the C++ front, against the golden PCM of every layout."""
+    from oracle import ref, orc
+    seen = set()
+    for k, it in enumerate(golden.items):
+        if it["os"] in seen or it["stop"] or it["nframes_out"] * 240 != it["pcm"].size:
+            continue
+        seen.add(it["os"])
+        src = tmp_path / ("s%d.bin" % k)
+        src.write_bytes(it["stream"] + bytes(64))
+        out = tmp_path / ("s%d.pcm" % k)
+        nfr = it["nframes_out"] + 3
+        r = subprocess.run([demo, "--standalone", "%x" % it["os"], str(src), str(it["vol"]), str(it["lvl"]), str(nfr), str(out)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        pcm = np.fromfile(out, dtype=np.int16)
+        want = it["pcm"]
+        n = min(pcm.size, want.size)
+        assert np.array_equal(pcm[:n], want[:n]), it["label"]
+        assert not pcm[want.size:].any()                        # silence behind the stream and its overlap tail
+        nf = (it["stream"][0] << 8) | it["stream"][1]
+        assert ("standalone: %d frames" % nf) in r.stdout and ("playing for %d samples" % (nf * 240)) in r.stdout
+    assert len(seen) >= 3
