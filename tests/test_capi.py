@@ -48,3 +48,50 @@ def test_no_cpu_fallback(built):
     import dcsexplorer_b200 as dx
     with pytest.raises(dx.DcsbError):
         dx.Context(0)
+
+
+def test_null_and_bad_arguments_are_rejected_not_dereferenced(built):
+    """Error behaviour of the boundary: integer status codes, no exceptions, no crashes on NULL
+    handles or malformed arguments (host-only entry points and argument checks: no GPU needed)."""
+    import ctypes as C
+    import numpy as np
+    import dcsexplorer_b200 as dx
+    from dcsexplorer_b200 import _capi
+    L = _capi.lib()
+    E_ARG = dx._capi.E_ARG if hasattr(dx._capi, "E_ARG") else None
+    out = C.c_void_p()
+    assert L.dcsb_create(0, None) != dx.OK
+    assert L.dcsb_create(-1, C.byref(out)) != dx.OK and not out.value
+    L.dcsb_destroy(None)
+    assert L.dcsb_last_error(None) == b"no context"
+    assert L.dcsb_decode_streams(None, None, 0, None, None, None) != dx.OK
+    assert L.dcsb_set_overlap(None, 1) != dx.OK and L.dcsb_set_pipeline(None, 0, 0) != dx.OK
+    assert L.dcsb_render_timelines(None, None, None, 1, None, None, None) != dx.OK
+    # ROM objects
+    L.dcsb_rom_destroy(None)
+    assert L.dcsb_rom_add(None, 2, None, 0) != dx.OK
+    assert L.dcsb_rom_check(None) != 1
+    assert L.dcsb_rom_track_info(None, 0, None) == 0
+    assert L.dcsb_rom_decompile_track(None, 0, None, 0) == 0
+    assert L.dcsb_rom_list_streams(None, None, 0) == 0
+    assert not L.dcsb_rom_pointer(None, 0, None)
+    rom = dx.Rom()
+    img = np.zeros(1 << 19, dtype=np.uint8)
+    for chip, n in ((1, 1 << 19), (10, 1 << 19), (2, 0), (2, 3000)):           # chip numbers 2..9, power-of-two sizes only
+        assert L.dcsb_rom_add(rom._h, chip, img.ctypes.data, n) != dx.OK
+    assert rom.check() != 1 and rom.info()["os"] == 0                          # nothing loaded: POST code 2 = U2 failed
+    assert rom.track_info(0) is None and rom.decompile_track(0) == [] and rom.list_streams() == []
+    assert rom.stream_bytes(0x123456, 4) == b""
+    with pytest.raises(dx.DcsbError):
+        dx.Rom(zip_path="/nonexistent/none.zip")
+    rom.close()
+    # players / batches without a context
+    assert L.dcsb_player_create(None, None, C.byref(out)) != dx.OK
+    L.dcsb_player_destroy(None)
+    assert L.dcsb_player_render(None, 1, None) != dx.OK
+    assert L.dcsb_player_host_bytes(None, None, 0) == 0
+    assert L.dcsb_player_is_stream_playing(None, 0) == 0
+    L.dcsb_batch_destroy(None)
+    # stream partitioning is pure host code
+    part, load = dx.partition_streams([10, 0, 7, 7, 3], 2)
+    assert abs(int(load[0]) - int(load[1])) <= 3 and len(part) == 5 and set(int(x) for x in part) == {0, 1}
