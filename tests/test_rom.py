@@ -221,3 +221,39 @@ def test_sim_rom_bad_track_type_is_fatal(built):
     if ref.available():
         rp = ref.RomPlayer(images, 255)
         assert np.array_equal(rp.render_timeline(writes, 40), pcm[0])
+
+
+def test_damaged_rom_sets_are_survivable(built):
+    """Random damage to the track programs, the track index and the stream heads of U2 (checksum
+    re-balanced so that the set still boots): the ROM model, the decompiler, the sequencer and the
+    scan / mix kernel bodies must get through it -- status codes or silence, never a wild read.
+    (The reference reads wherever a damaged pointer leads; here every ROM access is bounded.)"""
+    import dcsexplorer_b200 as dx
+    rng = np.random.default_rng(11)
+    statuses = set()
+    for k in range(12):
+        osv = [rb.OS94, rb.OS95, rb.OS93B, rb.OS93A][k % 4]
+        sc = romscen.make_scenario(os_version=osv, seed=600 + k % 5, n_frames=150)
+        imgs = {c: bytearray(i) for c, i in sc["images"].items()}
+        u2 = imgs[2]
+        cat = 0x6000 if osv == rb.OS95 else 0x4000
+        for _ in range(int(rng.integers(1, 25))):
+            u2[cat + 0x1000 + int(rng.integers(0, 0x2000))] = int(rng.integers(0, 256))
+        if k % 3 == 0:
+            u2[cat + 0x40 + int(rng.integers(0, 8))] = int(rng.integers(0, 256))        # track index / table pointers
+        u2[cat + 0x32] = u2[cat + 0x33] = 0
+        a = np.frombuffer(bytes(u2), dtype=np.uint8)
+        u2[cat + 0x32] = (-int(a[0::2].sum())) & 0xFF
+        u2[cat + 0x33] = (-int(a[1::2].sum())) & 0xFF
+        images = {c: bytes(i) for c, i in imgs.items()}
+        rom = dx.Rom(images)
+        assert rom.check() == 1
+        for t in range(min(rom.info()["n_tracks"], 400)):
+            rom.track_info(t)
+            rom.decompile_track(t)
+        rom.list_streams()
+        rom.close()
+        pcm, res, info, hb = simutil.rom_render(images, [(sc["writes"], 150, 200)])
+        assert pcm[0].size == 150 * 240
+        statuses.add(res[0]["status"])
+    assert statuses <= {0, -5}
