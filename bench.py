@@ -425,7 +425,7 @@ def _main(out):
             "status": {"streams_with_errors": len(bad), "checksum_xor": "%016x" % xor},
         }
         if not a.no_cpu_baseline:
-            v, kind, thr, sample, secs = cpu_reference_run(streams, vol, lvl, tail, ncores, min(768, len(streams)))
+            v, kind, thr, sample, secs = cpu_reference_run(streams, vol, lvl, tail, ncores, min(2048, len(streams)))     # ~20 s of CPU work on 16 cores
             line["cpu_baseline"] = {"value": v, "unit": "Msamples/s", "cores": thr, "kind": kind, "sample": sample}
         print(json.dumps(line), file=out)
         out.flush()
