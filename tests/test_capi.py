@@ -95,3 +95,16 @@ def test_null_and_bad_arguments_are_rejected_not_dereferenced(built):
     # stream partitioning is pure host code
     part, load = dx.partition_streams([10, 0, 7, 7, 3], 2)
     assert abs(int(load[0]) - int(load[1])) <= 3 and len(part) == 5 and set(int(x) for x in part) == {0, 1}
+
+
+def test_public_header_is_plain_c(built, tmp_path):
+    """include/dcsb200.h is the drop-in boundary: it must compile as C99 (no C++ / torch types)."""
+    import shutil, subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("gcc not available")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "dcsb200.h"\nint main(void) { dcsb_opcode o; dcsb_stream_desc d; dcsb_result r; (void)o; (void)d; (void)r; return 0; }\n')
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
