@@ -1,0 +1,42 @@
+#!/usr/bin/env python3
+"""CPU soak (test infrastructure): fuzzer-made streams of every layout, some truncated or with a flipped bit, through
+the kernel bodies (tests/hostsim), the plain-C oracle and -- for streams that decode without an error status -- the
+compiled reference; prints every mismatch.  usage: tools/soak_cpu.py [seconds=1500]"""
+import os
+import sys
+import time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import dcsfuzz, simutil
+from oracle import orc, ref
+t0=time.time(); n=0; bad=0; seed=10000
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 1500.0
+while time.time()-t0 < budget:
+    rng=np.random.default_rng(seed)
+    streams=[]
+    for os_,d,label in dcsfuzz.corpus(seed, n_each=2, nframes=int(rng.integers(1,120))):
+        streams.append((d, os_, int(rng.integers(0,256)), int(rng.integers(0,256)), int(rng.integers(0,4))))
+    # truncate / corrupt a few
+    for k in range(3):
+        i=int(rng.integers(0,len(streams))); d,os_,v,l,t=streams[i]
+        if k==0 and len(d)>40: d=d[:int(rng.integers(20,len(d)))]
+        elif k==1 and len(d)>40:
+            b=bytearray(d); b[int(rng.integers(18,len(d)))]^=1<<int(rng.integers(0,8)); d=bytes(b)
+        streams[i]=(d,os_,v,l,t)
+    pcm,offs,res,bp,bt=simutil.decode_streams(streams)
+    for i,(d,os_,vol,lvl,tail) in enumerate(streams):
+        nf=(d[0]<<8)|d[1]
+        want,rc=orc.decode(d,os_,vol,lvl,nf+tail)
+        got=pcm[offs[i]:offs[i]+want.size]
+        st=res[i]["status"]
+        if st in (0,-5) and not np.array_equal(got,want):
+            bad+=1; print("MISMATCH seed",seed,"stream",i,hex(os_),"status",st,flush=True)
+        if st==0:
+            w2=ref.decode(d+bytes(8),os_,vol,lvl,nf+tail)
+            if not np.array_equal(got,w2):
+                bad+=1; print("REF MISMATCH seed",seed,"stream",i,hex(os_),flush=True)
+        n+=1
+    seed+=1
+print("soak: %d streams, %d seeds, mismatches %d, %.0f s"%(n,seed-10000,bad,time.time()-t0))
