@@ -1,7 +1,9 @@
 #!/usr/bin/env python3
 """CPU soak (test infrastructure): fuzzer-made streams of every layout, some truncated or with a flipped bit, through
 the kernel bodies (tests/hostsim), the plain-C oracle and -- for streams that decode without an error status -- the
-compiled reference; prints every mismatch.  usage: tools/soak_cpu.py [seconds=1500]"""
+compiled reference; prints every mismatch.  With "rom" as the second argument: seeded ROM-playback scenarios (all four OS
+versions, error streams, software 1.05) through the sequencer + kernel bodies against the reference decoder.
+usage: tools/soak_cpu.py [seconds=1500] [streams|rom]"""
 import os
 import sys
 import time
@@ -11,6 +13,23 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import dcsfuzz, simutil
 from oracle import orc, ref
+if len(sys.argv) > 2 and sys.argv[2] == "rom":
+    from oracle import ref
+    import rombuild as rb, romscen, simutil
+    budget = float(sys.argv[1])
+    t0=time.time(); bad=0; n=0; k=0
+    while time.time()-t0 < budget:
+        osv=[rb.OS94, rb.OS95, rb.OS93B, rb.OS93A][k%4]
+        seed=20000+k
+        sc=romscen.make_scenario(os_version=osv, seed=seed, n_frames=400, with_errors=(k%3==0), version=(0x0105 if (osv==rb.OS95 and k%8==1) else None))
+        rp=ref.RomPlayer(sc["images"], sc["master_volume"])
+        want=rp.render_timeline(sc["writes"], sc["n_frames"]); hbw=rp.host_bytes(); rp.close()
+        pcm,res,info,hb=simutil.rom_render(sc["images"], [(sc["writes"], sc["n_frames"], sc["master_volume"])])
+        if not (np.array_equal(pcm[0],want) and hb==hbw):
+            bad+=1; print("MISMATCH", hex(osv), seed, flush=True)
+        n+=1; k+=1
+    print("rom soak: %d scenarios, mismatches %d, %.0f s"%(n,bad,time.time()-t0))
+    sys.exit(0)
 t0=time.time(); n=0; bad=0; seed=10000
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 1500.0
 while time.time()-t0 < budget:
