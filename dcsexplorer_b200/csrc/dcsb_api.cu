@@ -26,6 +26,12 @@ extern "C" int dcsb_create(int device, dcsb_ctx **out)
     dcsb_ctx *ctx = new dcsb_ctx();
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return DCSB_E_CUDA; }
+    {
+        int sms = 0, major = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess) dcsb_set_num_sms(sms);
+        // the kernels are built for sm_100a only: anything else has no code to run (and there is no CPU fallback)
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess || major != 10) { delete ctx; return DCSB_E_CUDA; }
+    }
     DcsbTables *h = new DcsbTables();
     dcsb_build_tables(h);
     e = cudaMalloc(&ctx->d_tables, sizeof(DcsbTables));
@@ -154,6 +160,7 @@ int dcsb_batch_create_impl(dcsb_ctx *ctx, const dcsb_stream_desc *descs, size_t 
 #endif
     CKB(cudaMalloc(&b->d_checksums, std::max<size_t>(1, n) * sizeof(unsigned long long)), "cudaMalloc(checksums)");
     CKB(cudaMalloc(&b->d_progress, (n + 4) * sizeof(uint32_t)), "cudaMalloc(progress)");
+    CKB(cudaMemset(b->d_progress, 0, (n + 4) * sizeof(uint32_t)), "memset(progress)");
     CKB(cudaMalloc(&b->d_queue, std::max<size_t>(1, (size_t)b->nqueue94) * sizeof(unsigned long long)), "cudaMalloc(queue)");
     for (auto &ev : b->ev) CKB(cudaEventCreate(&ev), "cudaEventCreate");
 #undef CKB
@@ -242,7 +249,14 @@ extern "C" int dcsb_batch_results(dcsb_batch *b, void *cuda_stream, dcsb_result 
     dcsb_ctx *ctx = b->ctx;
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     CK(cudaStreamSynchronize((cudaStream_t)cuda_stream), "stream sync (kernel failure?)");
-    if (!results || b->n == 0) return DCSB_OK;
+    if (b->n == 0) return DCSB_OK;
+    {
+        // a decode warp (or the gate) that gave up waiting for the scan left its mark here: the PCM is incomplete
+        uint32_t errw = 0;
+        CK(cudaMemcpy(&errw, b->d_progress + b->n + 3, 4, cudaMemcpyDeviceToHost), "D2H error word");
+        if (errw) return fail(ctx, DCSB_E_CUDA, "dcsb_batch_results: the decode kernel timed out waiting for the scan (PCM incomplete)");
+    }
+    if (!results) return DCSB_OK;
     std::vector<int32_t> st(b->n);
     std::vector<uint32_t> np(b->n), eb(b->n);
     std::vector<unsigned long long> cs(b->n);
@@ -428,7 +442,7 @@ static int lane_upload(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs
     // (PCM goes to a device buffer and is copied by the DMA engine afterwards: letting the decode
     // warps store straight into the caller's pinned buffer over PCIe measured 86 ms against 70 ms)
     ENS(l.d_pcm, std::max<uint64_t>(2, p.total_out_frames * 480), false, "cudaMalloc(pcm)");
-    ENS(l.h_res, nn * 20, true, "cudaMallocHost(results)");
+    ENS(l.h_res, nn * 20 + 8, true, "cudaMallocHost(results)");
     if (n == 0) return DCSB_OK;
     cudaStream_t up = ctx->up;
     if (in_place) {
@@ -458,6 +472,7 @@ static int lane_upload(dcsb_ctx *ctx, DcsbLane &l, const dcsb_stream_desc *descs
     ctx->trace.mark(lane_id, -1, "h2d", up);
     // (memsets are kernels: they go on the lane's own stream, not between the uploads)
     CK(cudaMemsetAsync(l.d_csum.p, 0, n * 8, l.st), "memset checksums");
+    if (!(!l.slice && ctx->overlap)) CK(cudaMemsetAsync((uint32_t *)l.d_progress.p + n, 0, 4 * 4, l.st), "memset error word");
     if (!l.slice && ctx->overlap) {
         CK(cudaMemsetAsync(l.d_progress.p, 0, (n + 4) * 4, l.st), "memset progress");
         if (p.nqueue94) CK(cudaMemsetAsync(l.d_queue.p, 0, (size_t)p.nqueue94 * 8, l.st), "memset queue");
@@ -556,6 +571,7 @@ static int lane_results(dcsb_ctx *ctx, DcsbLane &l)
     CK(cudaMemcpyAsync(hr + nn * 4, l.d_nplay.p, n * 4, cudaMemcpyDeviceToHost, l.st), "D2H nplay");
     CK(cudaMemcpyAsync(hr + nn * 8, l.d_endbits.p, n * 4, cudaMemcpyDeviceToHost, l.st), "D2H endbits");
     CK(cudaMemcpyAsync(hr + nn * 12, l.d_csum.p, n * 8, cudaMemcpyDeviceToHost, l.st), "D2H checksums");
+    CK(cudaMemcpyAsync(hr + nn * 20, (uint32_t *)l.d_progress.p + n + 3, 4, cudaMemcpyDeviceToHost, l.st), "D2H error word");
     return DCSB_OK;
 }
 #undef ENS
@@ -573,6 +589,9 @@ extern "C" int dcsb_decode_streams(dcsb_ctx *ctx, const dcsb_stream_desc *descs,
         if (descs[i].os_version != DCSB_OS94 && descs[i].os_version != DCSB_OS95 && descs[i].os_version != DCSB_OS93A &&
             descs[i].os_version != DCSB_OS93B)
             return fail(ctx, DCSB_E_ARG, "dcsb_decode_streams: unknown os_version");
+        // DCSB_STREAM_WRAP_EMPTY (a zero frame count plays 65,536 frames) belongs to ROM playback, which sizes its
+        // own buffers; here the caller's buffer is sized from the count as written, so the flag is refused
+        if (descs[i].reserved != 0) return fail(ctx, DCSB_E_ARG, "dcsb_decode_streams: dcsb_stream_desc.reserved must be 0");
         const uint32_t nf = (descs[i].data && descs[i].nbytes >= 2) ? (((uint32_t)descs[i].data[0] << 8) | descs[i].data[1]) : 0;
         off[i + 1] = off[i] + (uint64_t)(nf + descs[i].tail_frames) * 240;
         if (pcm_offsets && pcm_offsets[i] != off[i]) packed = false;
@@ -659,6 +678,11 @@ extern "C" int dcsb_decode_streams(dcsb_ctx *ctx, const dcsb_stream_desc *descs,
         if (e != cudaSuccess && rc == DCSB_OK) rc = fail(ctx, DCSB_E_CUDA, "dcsb_decode_streams: stream sync (kernel failure?)", e);
         if (rc != DCSB_OK) continue;
         const size_t nn = std::max<size_t>(1, l.count);
+        if (l.count) {
+            uint32_t errw;
+            memcpy(&errw, (const uint8_t *)l.h_res.p + nn * 20, 4);
+            if (errw) { rc = fail(ctx, DCSB_E_CUDA, "dcsb_decode_streams: the decode kernel timed out waiting for the scan (PCM incomplete)"); continue; }
+        }
         if (!l.direct_pcm) {
             if (packed) e = cudaMemcpy(pcm_out + l.pcm_base, l.d_pcm.p, l.prep.total_out_frames * 480, cudaMemcpyDeviceToHost);
             else

@@ -141,7 +141,7 @@ DCSB_HD void dcsb_publish(uint32_t *progress, int si, uint32_t v)
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(progress + si), "r"(v) : "memory");
 }
 // returns true when the stream's scan is finished (nplay / stopband are final)
-__device__ __forceinline__ bool dcsb_await(const uint32_t *progress, uint32_t stream, uint32_t need)
+__device__ __forceinline__ bool dcsb_await(const uint32_t *progress, uint32_t stream, uint32_t need, uint32_t *errw = nullptr)
 {
     if (!progress) return true;
     uint32_t v = 0;
@@ -150,7 +150,10 @@ __device__ __forceinline__ bool dcsb_await(const uint32_t *progress, uint32_t st
         for (;;) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(progress + stream) : "memory");
             if ((v & DCSB_SCAN_DONE) || v >= need) break;
-            if (clock64() - t0 > 4000000000ll) break;        // ~2 s: never hang the GPU on a lost producer
+            if (clock64() - t0 > 4000000000ll) {             // ~2 s: never hang the GPU on a lost producer ...
+                if (errw) atomicOr(errw, DCSB_DEV_E_AWAIT);  // ... and never let it pass for a success
+                break;
+            }
             __nanosleep(256);
         }
     }
@@ -175,7 +178,7 @@ __device__ __forceinline__ void dcsb_queue_push(const DcsbScanOut &out, int si, 
 struct DcsbScanOut;
 DCSB_HD void dcsb_queue_push(const DcsbScanOut &, int, uint32_t, uint32_t, bool) {}
 DCSB_HD void dcsb_publish(uint32_t *, int, uint32_t) {}
-DCSB_HD bool dcsb_await(const uint32_t *, uint32_t, uint32_t) { return true; }
+DCSB_HD bool dcsb_await(const uint32_t *, uint32_t, uint32_t, uint32_t * = nullptr) { return true; }
 #define DCSB_LDCG(p) (*(p))
 #endif
 
@@ -682,7 +685,7 @@ DCSB_HD unsigned long long dcsb_decode_tile(const uint8_t *slab, const DcsbStrea
     const DcsbStreamRec *sp = streams + tl.stream;
     const long long out_frames = sp->out_frames;
     // checkpoints first-1 .. first+count-1 (walkers of this layout need no look-ahead entry)
-    const bool fin = dcsb_await(scan.progress, tl.stream, tl.first + tl.count < sp->nframes ? tl.first + tl.count : sp->nframes);
+    const bool fin = dcsb_await(scan.progress, tl.stream, tl.first + tl.count < sp->nframes ? tl.first + tl.count : sp->nframes, scan.qctl ? scan.qctl + 2 : nullptr);
     const long long nplay = fin ? (long long)DCSB_LDCG(scan.nplay + tl.stream) : (long long)sp->nframes;
     const int fmt = sp->fmt;
     uint32_t *tails = rows + 32 * ROWW;             // two 8-word overlap buffers (ping-pong)

@@ -186,83 +186,80 @@ static void stream_gain(const dcsb_stream_desc &d, DcsbStreamRec &r)
 // spread the streams over the SMs first (one CTA per SM), then fill the CTAs up.  `concurrent` = the
 // streams of all the scans that run side by side (a scan CTA's tables fill most of an SM's shared
 // memory: there is room for one per SM, so the launches of a pipelined call share the 148 between them)
-void dcsb_scan_shape(int nstreams, int concurrent, int *spc, int *grid)
+static int g_num_sms = 148;
+int dcsb_num_sms() { return g_num_sms; }
+void dcsb_set_num_sms(int n) { if (n > 0) g_num_sms = n; }
+
+// Scan launch shape.  A lock-step warp walks 32 streams; the scan is as long as its slowest warp's
+// dependent chain, so the warps are spread as thin as the SMs allow: one warp per CTA (150 KB of
+// shared memory, leaving room for a decode CTA beside it) while the groups fit one wave, more
+// warps per CTA (sharing the 96 KB length table) when there are more groups than that.
+// concurrent = streams of all the scans launched side by side (0 = this launch alone).
+void dcsb_scan_shape(int nstreams, int concurrent, int *warps, int *grid)
 {
     if (concurrent < nstreams) concurrent = nstreams;
-    int s = (concurrent + 147) / 148;
-    s = s > DCSB_SCAN_SPC ? DCSB_SCAN_SPC : (s < 1 ? 1 : s);
-    int g = (nstreams + s - 1) / s;
-    *spc = s;
-    *grid = g > 148 ? 148 : g;
-}
-// streams per warp in the scan.  Every stream is its own dependent chain and issues its own
-// instructions (the lanes of a warp take different branches almost all the time), so this only
-// trades warps per scheduler against the cost of switching between a warp's diverged lanes.
-// Measured on the bench workload (28 streams per SM), scan alone / beside the decode kernel:
-// 2: 14.6 / 17.8 ms, 3: 14.2 / 17.1, 4: 14.2 / 16.8, 5: 14.8 / 17.6, 6: 14.6 / 17.1, 8: 15.5 / 18.6.
-int dcsb_scan_lanes(int nstreams)
-{
-    if (const char *e = getenv("DCSB_SCAN_LANES")) {       // tuning override (tools/scan_sweep.py)
+    const int sms = dcsb_num_sms();
+    const int groups = (nstreams + 31) / 32, cgroups = (concurrent + 31) / 32;
+    int w = (cgroups + sms - 1) / sms;
+    w = w > DCSB_SCAN_MAXWARPS ? DCSB_SCAN_MAXWARPS : (w < 1 ? 1 : w);
+    if (const char *e = getenv("DCSB_SCAN_WARPS")) {         // tuning override
         const int v = atoi(e);
-        if (v >= 1 && v <= 32) return v;
+        if (v >= 1 && v <= DCSB_SCAN_MAXWARPS) w = v;
     }
-    (void)nstreams;
-    return 4;
-}
-// how many of a CTA's stream slots get a warp of their own (the most expensive streams of the CTA;
-// the others share warps).  Measured on the bench workload: no gain -- 7 solo + 21 shared slots scan
-// in 17.5-18.1 ms against 16.4 ms with every warp shared by two streams: at 28 streams per SM the
-// scan is bound by the instructions all chains issue together as much as by the slowest chain
-// (13.1 ms alone), and more warps issue more.  Kept as a tuning knob, off by default.
-int dcsb_scan_solo(int nstreams, int spc)
-{
-    if (nstreams > 148 * DCSB_SCAN_SPC) return 0;
-    int v = 0;
-    if (const char *e = getenv("DCSB_SCAN_SOLO")) v = atoi(e);     // tuning override
-    return v < 0 ? 0 : (v > spc ? spc : v);
+    int g = (groups + w - 1) / w;
+    *warps = w;
+    *grid = g > sms ? sms : (g < 1 ? 1 : g);
 }
 
-// Which stream each scan slot takes.  Slot j of CTA c is order[c * spc + j] (then grid-stride).
-// One wave: streams ranked by cost (compressed bytes ~ table steps), dealt round-robin over the
-// CTAs, so every CTA gets the same mix and its slots run from expensive to cheap -- the first
-// dcsb_scan_solo() slots walk alone, and the shared warps hold streams of about the same cost.
-// Several waves: alike streams side by side (same layout, same stream type, similar bits per frame).
+// Which stream each scan lane takes: lane l of group g walks order[32 g + l]; warp w of CTA c takes
+// groups c * warps + w, then grid-stride.  A warp is as slow as its slowest lane in every frame and
+// as long as its longest stream, so a group holds alike streams -- same layout, about the same
+// frame count (buckets of a quarter octave), then ranked by bits per frame -- and the groups run
+// from the most expensive one down, so that the longest chains start first.
 void dcsb_scan_order(DcsbPrepared *p)
 {
     const size_t n = p->recs.size();
     p->scan_order.resize(n);
+    if (!n) return;
     std::vector<uint32_t> rank(n);
-    for (size_t i = 0; i < n; ++i) rank[i] = (uint32_t)i;
-    int spc, grid;
-    dcsb_scan_shape((int)std::min<size_t>(n, 0x7FFFFFFF), (int)std::min<size_t>(p->concurrent_streams, 0x7FFFFFFF), &spc, &grid);
-    if (n <= (size_t)148 * DCSB_SCAN_SPC && n > 0) {
-        std::stable_sort(rank.begin(), rank.end(), [&](uint32_t a, uint32_t b) {
-            const DcsbStreamRec &x = p->recs[a], &y = p->recs[b];
-            const uint64_t kx = x.nframes ? x.nbytes : 0, ky = y.nframes ? y.nbytes : 0;
-            return kx > ky;
-        });
-        // rank r -> CTA r % grid, slot r / grid; CTA c holds order[c * spc .. c * spc + spc) (the last CTAs may hold fewer)
-        std::vector<uint32_t> fill((size_t)grid, 0);
-        std::vector<size_t> base((size_t)grid + 1, 0);
-        for (int c = 0; c < grid; ++c) base[c + 1] = std::min(n, (size_t)(c + 1) * (size_t)spc);
-        int c = 0;
-        for (size_t r = 0; r < n; ++r) {
-            while (base[c] + fill[c] >= base[c + 1]) c = (c + 1) % grid;      // CTA full (short last CTAs): next
-            p->scan_order[base[c] + fill[c]++] = rank[r];
-            c = (c + 1) % grid;
+    std::vector<uint64_t> key(n);
+    for (size_t i = 0; i < n; ++i) {
+        rank[i] = (uint32_t)i;
+        const DcsbStreamRec &x = p->recs[i];
+        uint32_t bucket = 0;                          // quarter-octave bucket of the frame count
+        if (x.nframes) {
+            int lg = 31;
+            while (!(x.nframes >> lg)) --lg;
+            bucket = 1u + (uint32_t)lg * 4u + ((lg >= 2 ? x.nframes >> (lg - 2) : x.nframes << (2 - lg)) & 3u);
         }
-        // (inside a CTA the slots run from expensive to cheap, so a warp holds streams of about the same cost.
-        // Dealing the expensive streams out over the warps instead -- one per warp, filled up with cheap ones --
-        // measured 14.6 ms against 14.2 ms: alike streams in a warp diverge less.)
-        return;
+        const uint64_t bpf = x.nframes ? std::min<uint64_t>((uint64_t)x.nbytes * 8 / x.nframes, 0xFFFFFull) : 0;
+        key[i] = ((uint64_t)(x.fmt == DCSB_FMT_94 ? 1 : 0) << 40) | ((uint64_t)bucket << 20) | bpf;
     }
-    std::stable_sort(rank.begin(), rank.end(), [&](uint32_t a, uint32_t b) {
-        const DcsbStreamRec &x = p->recs[a], &y = p->recs[b];
-        const uint64_t kx = ((uint64_t)x.fmt << 40) | ((uint64_t)(x.hdr[0] >> 7) << 32) | (x.nframes ? (uint64_t)x.nbytes * 8 / x.nframes : 0);
-        const uint64_t ky = ((uint64_t)y.fmt << 40) | ((uint64_t)(y.hdr[0] >> 7) << 32) | (y.nframes ? (uint64_t)y.nbytes * 8 / y.nframes : 0);
-        return kx < ky;
-    });
-    p->scan_order = rank;
+    std::stable_sort(rank.begin(), rank.end(), [&](uint32_t a, uint32_t b) { return key[a] > key[b]; });
+    // groups of 32 by estimated cost (frames of the longest stream x bits per frame of the densest), largest first
+    const size_t ng = (n + 31) / 32;
+    std::vector<uint32_t> gidx(ng);
+    std::vector<uint64_t> gcost(ng, 0);
+    for (size_t g = 0; g < ng; ++g) {
+        gidx[g] = (uint32_t)g;
+        uint64_t mf = 0, mb = 0;
+        for (size_t k = g * 32; k < std::min(n, g * 32 + 32); ++k) {
+            const DcsbStreamRec &x = p->recs[rank[k]];
+            mf = std::max<uint64_t>(mf, x.nframes);
+            mb = std::max<uint64_t>(mb, x.nframes ? (uint64_t)x.nbytes * 8 / x.nframes : 0);
+        }
+        gcost[g] = mf * (mb + 64);
+    }
+    std::stable_sort(gidx.begin(), gidx.end(), [&](uint32_t a, uint32_t b) { return gcost[a] > gcost[b]; });
+    // a short last group must stay the last one (lanes are assigned by position in the order)
+    size_t o = 0;
+    const size_t tail_g = (n % 32) ? ng - 1 : ng;     // index of the short group, if any
+    for (size_t q = 0; q < ng; ++q) {
+        const size_t g = gidx[q];
+        if (g == tail_g) continue;
+        for (size_t k = g * 32; k < g * 32 + 32; ++k) p->scan_order[o++] = rank[k];
+    }
+    if (tail_g < ng) for (size_t k = tail_g * 32; k < n; ++k) p->scan_order[o++] = rank[k];
 }
 
 // Work items covering output frames [fa, fb) of every stream, in frame-major order (item k of every

@@ -67,6 +67,9 @@ struct DcsbTables {
     uint16_t tx[6 * DCSB_T8_CB];
 };
 
+#define DCSB_DEV_E_QUEUE 1u                // decode warp: no work item arrived (scan CTA not resident / lost)
+#define DCSB_DEV_E_AWAIT 2u                // decode warp: the checkpoints of its item never arrived
+#define DCSB_DEV_E_GATE  4u                // gate kernel: the scan CTAs did not become resident
 #define DCSB_SCAN_DONE 0x80000000u
 #define DCSB_SCAN_RUNNING 1                 // DcsbScanOut::status between two time slices of a stream (never seen by callers)
 #define DCSB_QITEM 63u                      // frames per queued work item: with the warm-up frame, two full 32-lane tiles
@@ -89,14 +92,20 @@ struct DcsbScanOut {
     // 1994 layout, overlapped mode: the scan appends a work item to `queue` every DCSB_QITEM frames
     // of a stream (and the rest of the stream when it finishes it); the persistent decode kernel
     // takes the items in that order, so it always works on frames whose checkpoints exist.
-    // qctl[0] = tail (scan side), qctl[1] = head (decode side).
+    // qctl[0] = tail (scan side), qctl[1] = head (decode side), qctl[2] = error word: set when a consumer gave
+    // up waiting for its producer (DCSB_DEV_E_*); the host turns it into DCSB_E_CUDA -- a timeout is never a
+    // silent success.
     unsigned long long *queue;
     uint32_t *qctl;
     uint32_t *dbg;             // tuning builds (-DDCSB_SCAN_DEBUG): [nstreams][4] cycles lo/hi, table steps, header steps; else NULL
 };
 
 void dcsb_build_tables(DcsbTables *t);   // host
-#define DCSB_SCAN_SPC 28                 // most stream slots (1 KB ring each) a scan CTA holds
+#define DCSB_SCAN_MAXWARPS 3              // most lock-step warps (32 streams, 1 KB ring each) a scan CTA holds
+// SM count of the device the context runs on (cudaDevAttrMultiProcessorCount; 148 on a B200): sizes the
+// scan grid and the persistent decode grid
+int dcsb_num_sms();
+void dcsb_set_num_sms(int n);
 
 // host-side batch layout (dcsb_host.cpp)
 #include <vector>
@@ -122,9 +131,8 @@ struct DcsbPrepared {
 int dcsb_prepare(const dcsb_stream_desc *descs, size_t n, DcsbPrepared *p, const uint8_t *in_place_base, size_t in_place_span);
 // work items covering output frames [fa, fb) of every stream (appended to t94 / t93), frame-major
 void dcsb_build_tiles(const DcsbPrepared *p, uint32_t fa, uint32_t fb, std::vector<DcsbTile> *t94, std::vector<DcsbTile> *t93);
-// scan launch shape and stream -> slot assignment (dcsb_host.cpp)
-void dcsb_scan_shape(int nstreams, int concurrent, int *spc, int *grid);
-int dcsb_scan_solo(int nstreams, int spc);
+// scan launch shape (lock-step warps per CTA, CTAs) and stream -> lane assignment (dcsb_host.cpp)
+void dcsb_scan_shape(int nstreams, int concurrent, int *warps, int *grid);
 void dcsb_scan_order(DcsbPrepared *p);
 // copy the streams into `slab` (p->slab_bytes bytes) at their 16-byte aligned offsets, zero padded
 void dcsb_pack_slab(const dcsb_stream_desc *descs, size_t n, const DcsbPrepared *p, uint8_t *slab);
@@ -135,7 +143,6 @@ void dcsb_pack_slab(const dcsb_stream_desc *descs, size_t n, const DcsbPrepared 
 // for [.., f0) left (time-sliced chunks of dcsb_decode_streams)
 cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, const uint32_t *order, int nstreams, int concurrent,
                              const DcsbTables *tables, DcsbScanOut out, cudaStream_t st, uint32_t f0 = 0, uint32_t f1 = 0xFFFFFFFFu);
-int dcsb_scan_lanes(int nstreams);       // streams per warp the scan launch uses (1..32)
 // tiles[0..ntiles94) use the 1994 transform, tiles[ntiles94..ntiles94+ntiles93) the 1993 one
 // enqueue a one-thread kernel that returns once `ctas` scan CTAs are resident (scan.started)
 cudaError_t dcsb_launch_gate(DcsbScanOut scan, int ctas, cudaStream_t st);

@@ -33,52 +33,67 @@ __device__ __forceinline__ void dcsb_load_lut(uint16_t *s_lut, const DcsbTables 
 }
 
 // ------------------------------------------------------------------------------------
-// K1: frame-boundary scan, one thread per stream.  A CTA takes up to DCSB_SCAN_SPC streams (one
-// 1 KB ring each); a warp takes `lanes` of them (every stream is its own dependent chain and its
-// lanes diverge almost always, see dcsb_scan_lanes); the CTA's warps share the tables and walk
-// stream groups grid-stride.
-struct DcsbSmemScan {
-    __align__(16) uint8_t ring[DCSB_SCAN_SPC][DCSB_RING_BYTES];
-    uint16_t lut[DCSB_LUT_WORDS];
-    uint32_t dtab[DCSB_DTAB_WORDS];            // band descriptors by (stream type, half density, band, band type)
-    uint32_t desc[DCSB_SCAN_SPC][17];          // per stream slot: band descriptors of the current frame (+ a zero sentinel)
-};
-// the length table follows at the next multiple of 16 KB of the shared window (dcsb_tx_load)
+// K1: frame-boundary scan.  A warp takes 32 streams of the scan order (alike streams side by
+// side, dcsb_scan_order) and walks them in LOCK STEP, one lane per stream (dcsb_scan94.cuh); a
+// CTA holds `warps` such warps (one in the single-wave case, so that a decode CTA fits beside
+// it) that share the tables and take stream groups grid-stride.  Streams of the 1993 layouts
+// are walked by their lane alone first (dcsb_scan_stream), the lane then idles in the lock-step
+// walk of its warp.
+// Shared memory: the length table tx (96 KB) sits on a 16 KB boundary of the shared window
+// (dcsb_tx_load); the peek LUTs and the band-descriptor table go into the alignment gap in front
+// of it or behind it, whichever is large enough; then one 1 KB ring (+ 16 bytes, so that the
+// rings of a warp start in different banks) and 17 band descriptors per lane.
+#define DCSB_RING_STRIDE (DCSB_RING_BYTES + 16u)
 #define DCSB_TX_BYTES (6 * DCSB_T8_CB * 2)
-#define DCSB_SCAN_SMEM (sizeof(DcsbSmemScan) + DCSB_TX_BYTES + 16384)
+#define DCSB_SCAN_SMALL (((DCSB_LUT_WORDS * 2 + 15) & ~15) + DCSB_DTAB_WORDS * 4)
+#define DCSB_SCAN_WARP_BYTES (32u * DCSB_RING_STRIDE + 32u * 17u * 4u)
+#define DCSB_SCAN_SMEM(warps) (16384u + DCSB_TX_BYTES + (warps) * DCSB_SCAN_WARP_BYTES)
+static_assert(DCSB_SCAN_SMALL <= 8192, "the small tables must fit the smaller alignment gap");
+static_assert(DCSB_SCAN_SMEM(DCSB_SCAN_MAXWARPS) <= 232448, "scan CTA exceeds the shared memory of an SM");
 
-__global__ void __launch_bounds__(DCSB_SCAN_SPC * 32, 1)
+__global__ void __launch_bounds__(DCSB_SCAN_MAXWARPS * 32, 1)
 dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restrict__ streams, const uint32_t *__restrict__ order,
-                 int nstreams, int lanes, int spc, int nsolo, const DcsbTables *__restrict__ tab, DcsbScanOut out, uint32_t f0, uint32_t f1)
+                 int nstreams, const DcsbTables *__restrict__ tab, DcsbScanOut out, uint32_t f0, uint32_t f1)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    DcsbSmemScan &sm = *reinterpret_cast<DcsbSmemScan *>(smem);
+    uint8_t *sm8 = reinterpret_cast<uint8_t *>(smem);
     const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem);
-    const uint32_t tx = (s_base + (uint32_t)sizeof(DcsbSmemScan) + 16383u) & ~16383u;
+    const uint32_t tx = (s_base + 16383u) & ~16383u;
+    const uint32_t tx_off = tx - s_base;
+    const uint32_t small_off = tx_off >= DCSB_SCAN_SMALL ? 0u : tx_off + DCSB_TX_BYTES;
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(sm8 + small_off);
+    uint32_t *s_dtab = reinterpret_cast<uint32_t *>(sm8 + small_off + ((DCSB_LUT_WORDS * 2 + 15) & ~15));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const uint32_t warp_off = 16384u + DCSB_TX_BYTES + (uint32_t)warp * DCSB_SCAN_WARP_BYTES;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(tab->tx);
-        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(smem) + (tx - s_base));
+        uint4 *dst = reinterpret_cast<uint4 *>(sm8 + tx_off);
         for (int i = threadIdx.x; i < DCSB_TX_BYTES / 16; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     if (threadIdx.x == 0 && out.started) atomicAdd(out.started, 1u);       // this CTA is resident (dcsb_gate_kernel)
-    dcsb_load_lut(sm.lut, tab);
-    for (int i = threadIdx.x; i < DCSB_DTAB_WORDS; i += blockDim.x) sm.dtab[i] = dcsb_dtab_entry(sm.lut, i);
+    dcsb_load_lut(s_lut, tab);
+    for (int i = threadIdx.x; i < DCSB_DTAB_WORDS; i += blockDim.x) s_dtab[i] = dcsb_dtab_entry(s_lut, i);
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // stream slot inside the CTA: the first nsolo slots have a warp each, the others share warps
-    const int slot = warp < nsolo ? warp : nsolo + (warp - nsolo) * lanes + lane;
-    if (lane >= (warp < nsolo ? 1 : lanes) || slot >= spc) return;
 #if DCSB_DEVICE_PASS
-    const DcsbRingPtr ring = (uint32_t)__cvta_generic_to_shared(sm.ring[slot]);
+    const DcsbRingPtr ring = s_base + warp_off + (uint32_t)lane * DCSB_RING_STRIDE;
     const DcsbTxBase txb = tx;
 #else       // (nvcc's host pass only type-checks this body)
-    const DcsbRingPtr ring = sm.ring[slot];
-    const DcsbTxBase txb = reinterpret_cast<const uint8_t *>(smem) + (tx - s_base);
+    const DcsbRingPtr ring = sm8 + warp_off + (uint32_t)lane * DCSB_RING_STRIDE;
+    const DcsbTxBase txb = sm8 + tx_off;
 #endif
-    for (int k = blockIdx.x * spc + slot; k < nstreams; k += gridDim.x * spc) {
-        const int si = order ? (int)order[k] : k;
-        if (streams[si].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab, streams, si, tab, sm.lut, txb, sm.dtab, ring, sm.desc[slot], out, f0, f1);
-        else dcsb_scan_stream(slab, streams, si, tab, sm.lut, out, f0, f1);
+    uint32_t *desc = reinterpret_cast<uint32_t *>(sm8 + warp_off + 32u * DCSB_RING_STRIDE) + lane * 17;
+    const int ngroups = (nstreams + 31) >> 5;
+    for (int g = blockIdx.x * warps + warp; g < ngroups; g += gridDim.x * warps) {
+        const int k = g * 32 + lane;
+        int si = -1;
+        if (k < nstreams) si = order ? (int)order[k] : k;
+        if (si >= 0 && streams[si].fmt != DCSB_FMT_94) {
+            dcsb_scan_stream(slab, streams, si, tab, s_lut, out, f0, f1);
+            si = -1;
+        }
+        __syncwarp();
+        dcsb_scan94_stream(slab, streams, si, tab, s_lut, txb, s_dtab, ring, desc, out, f0, f1);
+        __syncwarp();
     }
 }
 
@@ -140,7 +155,7 @@ dcsb_decode94_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__re
     const DcsbTile it = items[item];
     // checkpoints first-1 .. first+count (a frame's own band types are the NEXT entry)
     const uint32_t nfr = streams[it.stream].nframes;
-    const bool fin = dcsb_await(scan.progress, it.stream, it.first + it.count + 1 < nfr + 1 ? it.first + it.count + 1 : nfr + 1);
+    const bool fin = dcsb_await(scan.progress, it.stream, it.first + it.count + 1 < nfr + 1 ? it.first + it.count + 1 : nfr + 1, scan.qctl ? scan.qctl + 2 : nullptr);
     const uint32_t nplay = fin ? __ldcg(scan.nplay + it.stream) : nfr;
     const int stopband = fin ? __ldcg(scan.stopband + it.stream) : 0xFF;
     unsigned long long csum = dcsb_decode94_item(slab, streams, it, tab, sm.lut, &sm.tw, sm.hdr[warp], scan, nplay, stopband, pcm, sm.rows[warp]);
@@ -185,7 +200,11 @@ dcsb_decode94_queue_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec
                 for (;;) {
                     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(e) : "l"(scan.queue + q) : "memory");
                     if (e & DCSB_Q_VALID) break;
-                    if (clock64() - t0 > 4000000000ll) { e = 0; break; }     // never hang the GPU on a lost producer
+                    if (clock64() - t0 > 4000000000ll) {     // never hang the GPU on a lost producer; the host reports DCSB_E_CUDA
+                        atomicOr(scan.qctl + 2, DCSB_DEV_E_QUEUE);
+                        e = 0;
+                        break;
+                    }
                     __nanosleep(256);
                 }
             }
@@ -236,13 +255,13 @@ cudaError_t dcsb_launch_decode_queue(const uint8_t *slab, const DcsbStreamRec *s
     e = cudaFuncSetAttribute(dcsb_decode94_queue_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     int grid = (nitems + DCSB_WARPS94 - 1) / DCSB_WARPS94;
-    // persistent CTAs per SM.  When every stream's scan is resident at once (one wave), the step is
-    // as long as the slowest scan chain and the decode only has to keep up with it: one CTA per SM
-    // does (measured 19.7 ms against 21.0 ms with three, whose warps take issue slots from the
-    // chains).  With more streams than that the decode is the larger part: fill the SMs.
-    int per_sm = nstreams <= 148 * DCSB_SCAN_SPC ? 1 : 3;
+    // persistent CTAs per SM: as many as fit (three of 70 KB; beside a resident scan CTA of 150 KB the
+    // SM takes one, the others follow when the scan CTA has left)
+    const int sms = dcsb_num_sms();
+    int per_sm = 3;
     if (const char *e = getenv("DCSB_DECODE_CTAS")) { const int v = atoi(e); if (v >= 1 && v <= 3) per_sm = v; }   // tuning override
-    if (grid > 148 * per_sm) grid = 148 * per_sm;
+    (void)nstreams;
+    if (grid > sms * per_sm) grid = sms * per_sm;
     dcsb_decode94_queue_kernel<<<grid, DCSB_WARPS94 * 32, smem, st>>>(slab, streams, nitems, tables, scan, pcm, checksums);
     return cudaGetLastError();
 }
@@ -336,33 +355,34 @@ cudaError_t dcsb_launch_mix(bool family93, const uint8_t *slab, const DcsbStream
 }
 
 // ------------------------------------------------------------------------------------
-static void scan_shape(int nstreams, int concurrent, int &spc, int &grid) { dcsb_scan_shape(nstreams, concurrent, &spc, &grid); }
+static void scan_shape(int nstreams, int concurrent, int &warps, int &grid) { dcsb_scan_shape(nstreams, concurrent, &warps, &grid); }
 
 int dcsb_scan_grid(int nstreams, int concurrent)
 {
-    int spc, grid;
-    scan_shape(nstreams, concurrent, spc, grid);
+    int warps, grid;
+    scan_shape(nstreams, concurrent, warps, grid);
     return nstreams > 0 ? grid : 0;
 }
 
 // The decode kernel may only start filling the SMs once every scan CTA is resident: its warps
 // wait for scan progress, and a scan CTA that could not get onto the chip behind them would
 // never deliver it.  One thread polls the counter the scan CTAs bump on entry.
-__global__ void dcsb_gate_kernel(const uint32_t *started, uint32_t ctas)
+__global__ void dcsb_gate_kernel(const uint32_t *started, uint32_t ctas, uint32_t *errw)
 {
     const long long t0 = clock64();
     uint32_t v;
-    do {
+    for (;;) {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(started) : "memory");
         if (v >= ctas) break;
+        if (clock64() - t0 > 4000000000ll) { atomicOr(errw, DCSB_DEV_E_GATE); break; }
         __nanosleep(128);
-    } while (clock64() - t0 < 4000000000ll);
+    }
 }
 
 cudaError_t dcsb_launch_gate(DcsbScanOut scan, int ctas, cudaStream_t st)
 {
-    if (!scan.started || ctas <= 0) return cudaSuccess;
-    dcsb_gate_kernel<<<1, 1, 0, st>>>(scan.started, (uint32_t)ctas);
+    if (!scan.started || !scan.qctl || ctas <= 0) return cudaSuccess;
+    dcsb_gate_kernel<<<1, 1, 0, st>>>(scan.started, (uint32_t)ctas, scan.qctl + 2);
     return cudaGetLastError();
 }
 
@@ -370,19 +390,16 @@ cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, 
                              const DcsbTables *tables, DcsbScanOut out, cudaStream_t st, uint32_t f0, uint32_t f1)
 {
     if (nstreams <= 0) return cudaSuccess;
-    const int lanes = dcsb_scan_lanes(nstreams);
-    int spc, grid;
-    scan_shape(nstreams, concurrent, spc, grid);
-    const int nsolo = dcsb_scan_solo(nstreams, spc);
-    const int warps = nsolo + (spc - nsolo + lanes - 1) / lanes;
-    const size_t smem = DCSB_SCAN_SMEM;
-    cudaError_t e = cudaFuncSetAttribute(dcsb_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int warps, grid;
+    scan_shape(nstreams, concurrent, warps, grid);
+    const size_t smem = DCSB_SCAN_SMEM((size_t)warps);
+    cudaError_t e = cudaFuncSetAttribute(dcsb_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DCSB_SCAN_SMEM(DCSB_SCAN_MAXWARPS));
     if (e != cudaSuccess) return e;
     // keep the SM at its largest shared-memory split, so that CTAs of the other kernel can join
     // this one (the split only changes on an idle SM)
     e = cudaFuncSetAttribute(dcsb_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    dcsb_scan_kernel<<<grid, warps * 32, smem, st>>>(slab, streams, order, nstreams, lanes, spc, nsolo, tables, out, f0, f1);
+    dcsb_scan_kernel<<<grid, warps * 32, smem, st>>>(slab, streams, order, nstreams, tables, out, f0, f1);
     return cudaGetLastError();
 }
 

@@ -424,16 +424,22 @@ bool dcsb_unzip(const char *path, std::vector<DcsbZipEntry> &out, std::string &e
     if (eocd == std::string::npos) { err = "zip directory not found"; return false; }
     const uint32_t count = le16(&z[eocd + 10]);
     size_t p = le32(&z[eocd + 16]);
+    // nothing in the directory is trusted: every length is checked against the file before it is used, and an
+    // entry may not claim more than DCSB_ZIP_MAX_ENTRY bytes (the largest DCS sound ROM chip is 1 MB)
+    const size_t DCSB_ZIP_MAX_ENTRY = 16u << 20;
+    if (p > eocd || (size_t)count * 46 > eocd - p) { err = "corrupt zip directory"; return false; }
     for (uint32_t e = 0; e < count; ++e) {
-        if (p + 46 > z.size() || le32(&z[p]) != 0x02014b50u) { err = "corrupt zip directory"; return false; }
+        if (p + 46 > eocd || le32(&z[p]) != 0x02014b50u) { err = "corrupt zip directory"; return false; }
         const uint32_t method = le16(&z[p + 10]), csize = le32(&z[p + 20]), usize = le32(&z[p + 24]);
         const uint32_t nlen = le16(&z[p + 28]), xlen = le16(&z[p + 30]), clen = le16(&z[p + 32]), lho = le32(&z[p + 42]);
+        if (p + 46 + (size_t)nlen + xlen + clen > eocd) { err = "corrupt zip directory"; return false; }
         std::string name(reinterpret_cast<const char *>(&z[p + 46]), nlen);
         p += 46 + nlen + xlen + clen;
         if (!name.empty() && name.back() == '/') continue;      // directory
         if ((size_t)lho + 30 > z.size() || le32(&z[lho]) != 0x04034b50u) { err = "corrupt zip entry " + name; return false; }
         const size_t data = (size_t)lho + 30 + le16(&z[lho + 26]) + le16(&z[lho + 28]);
-        if (data + csize > z.size()) { err = "truncated zip entry " + name; return false; }
+        if (data > z.size() || (size_t)csize > z.size() - data) { err = "truncated zip entry " + name; return false; }
+        if (usize > DCSB_ZIP_MAX_ENTRY) { err = "zip entry too large: " + name; return false; }
         DcsbZipEntry ent;
         ent.name = name;
         ent.data.resize(usize);

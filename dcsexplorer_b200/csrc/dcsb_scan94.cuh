@@ -200,20 +200,45 @@ DCSB_HD int dcsb_ctz(uint32_t v)
 #endif
 }
 
+// Warp votes: on the device all 32 lanes of a warp walk one stream each in LOCK STEP (one
+// instruction stream serves 32 streams; loops run until every lane is through); the simulator
+// plays a warp of one lane, so a vote is the lane's own predicate.
+#if DCSB_DEVICE_PASS
+#define DCSB_ANY(p) (__any_sync(0xffffffffu, (p)) != 0)
+#else
+#define DCSB_ANY(p) (p)
+#endif
+
 // [f0, f1) = the frames this call walks (0, ~0u = the whole stream).  A call with f0 > 0 resumes
 // from the end checkpoint the previous call left at frame f0 (status DCSB_SCAN_RUNNING); that is
 // what lets dcsb_decode_streams cut a chunk into time slices whose PCM drains over PCIe while
 // the later slices are still being scanned.
+//
+// LOCK STEP.  Called by all lanes of a warp together, lane = stream (si < 0: idle lane).  The
+// lanes run ONE instruction stream: per frame a header loop (one run of "unchanged" codes plus
+// one code per iteration) and a band loop whose iteration is one table step for whichever
+// Huffman band the lane is in -- the switch to the next band is folded in by selects, a lane
+// that has finished its frame executes no-ops until the last lane is through.  What is rare and
+// long (a fixed-width band's closed-form skip needs the bit window re-seeked in the ring; header
+// codes longer than 8 bits) sits behind warp-uniform branches on votes taken one iteration
+// earlier, so the branch resolves at once and the lanes that do not need it pay nothing on their
+// dependent chain.  The window refill is decided from the position BEFORE the current step
+// (the 64-bit window has the room: s <= 44), which takes it off the chain position -> table
+// entry -> next position.  Streams are ordered by cost (dcsb_scan_order), so a warp holds alike
+// streams and waits little for its slowest lane.
 DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *streams, int si, const DcsbTables *tab,
                                 const uint16_t *lut, DcsbTxBase tx, const uint32_t *dtab, DcsbRingPtr ring, uint32_t *desc,
                                 const DcsbScanOut &out, uint32_t f0 = 0, uint32_t f1 = 0xFFFFFFFFu)
 {
-    if (f0 && out.status[si] != DCSB_SCAN_RUNNING) return;      // finished (or failed) in an earlier slice
-    const DcsbStreamRec s = streams[si];
-    const uint8_t *hdr = streams[si].hdr;
-    const int type1 = hdr[0] >> 7;
+    bool mine = si >= 0;
+    if (mine && f0 && out.status[si] != DCSB_SCAN_RUNNING) mine = false;      // finished (or failed) in an earlier slice
+    DcsbStreamRec s;
+    if (mine) s = streams[si];
+    else { s.nframes = 0; s.nbytes = 0; s.hdr_len = 16; s.data_off = 0; s.frame_base = 0; s.out_frames = 0; }
+    const uint8_t *hdr = mine ? streams[si].hdr : streams[0].hdr;
+    const int type1 = mine ? hdr[0] >> 7 : 0;
     int nb = 0;
-    while (nb < 16 && (hdr[nb] & 0x7F) != 0x7F) ++nb;
+    if (mine) while (nb < 16 && (hdr[nb] & 0x7F) != 0x7F) ++nb;
     // bands at half density (:1858-1862) select the other half of the descriptor table
     uint32_t halfmask = 0;
     for (int b = 0; b < nb; ++b) halfmask |= (uint32_t)((hdr[b] >> 6) & 1) << b;
@@ -232,7 +257,7 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
     win.wa = 12u;
     uint32_t pos = 0;
     uint32_t bt_lo = 0, bt_hi = 0;                 // band types, 16 x 4 bits; InitStreamPlayback zeroes them (:1640)
-    if (f0) {
+    if (mine && f0) {
         pos = out.bitpos[s.frame_base + f0];
         const uint2 b2 = out.bt[s.frame_base + f0];
         bt_lo = b2.x;
@@ -248,16 +273,6 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
     rd.w = reinterpret_cast<const uint32_t *>(slab + (start & ~3ull));
     rd.bias = (uint32_t)(start & 3) * 8;
 
-#if defined(DCSB_SCAN_DEBUG) && DCSB_DEVICE_PASS
-    const long long dbg_t0 = clock64();
-    uint32_t dbg_steps = 0, dbg_hdr = 0, dbg_c[4] = { 0, 0, 0, 0 };
-    long long dbg_t = dbg_t0;
-#define DCSB_DBG(x) x
-#define DCSB_DBG_LAP(k) { const long long t_ = clock64(); dbg_c[k] += (uint32_t)(t_ - dbg_t); dbg_t = t_; }
-#else
-#define DCSB_DBG(x)
-#define DCSB_DBG_LAP(k)
-#endif
     uint32_t queued = 0, qnext = DCSB_QITEM;       // output frames already handed to the decode kernel / next hand-over
     int status = s.nframes ? 0 : -1, stopband = 0xFF;    // -1 = DCSB_E_EMPTY (the host refines DCSB_E_SHORT)
     uint32_t nplay = s.nframes, f = f0;
@@ -270,135 +285,168 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
         desc[b] = d;
         live |= (d ? 1u : 0u) << b;
     }
-    desc[16] = 0;
-    for (; f < fe; ++f) {
-        out.bitpos[s.frame_base + f] = pos;
-        out.bt[s.frame_base + f] = make_uint2(bt_lo, bt_hi);
-        DCSB_DBG_LAP(3)
-        if (f != f0) win.topup();
-        DCSB_DBG_LAP(0)
+    for (int b = nb; b <= 16; ++b) desc[b] = 0;
+    bool run = mine && f < fe;                     // this lane still walks frames
+    while (DCSB_ANY(run)) {
+        if (run) {
+            out.bitpos[s.frame_base + f] = pos;
+            out.bt[s.frame_base + f] = make_uint2(bt_lo, bt_hi);
+            if (f != f0) win.topup();
+        }
         // ---- frame header (:1780-1834): per iteration a run of 1-bit "unchanged" codes (count
         // leading ones) and the code behind it
         int rc = 0;
-        for (int b = 0; b < nb;) {
-            DCSB_DBG(++dbg_hdr;)
+        int hb = run ? 0 : nb;
+        while (DCSB_ANY(hb < nb)) {
+            const bool on = hb < nb;
             const uint32_t v = win.peek32();
             const int ones = dcsb_clz(~v);
-            const int left = nb - b;
-            const int run = ones < left ? ones : left;          // <= 16
-            b += run;
-            if (b >= nb) { win.skip((uint32_t)run); break; }
-            const uint32_t e = lut[DCSB_LUT_HDR94 + ((v << run) >> 24)];
-            int delta;
-            if (e == 0) {
+            const int left = nb - hb;
+            const int runl = ones < left ? ones : left;         // <= 16
+            const int b = hb + runl;
+            const bool code = on && b < nb;                     // a code follows the run
+            uint32_t e = lut[DCSB_LUT_HDR94 + ((v << runl) >> 24)];
+            int delta = (int)(e & 0xFF) - 0x2E;
+            uint32_t adv = (uint32_t)runl + (code ? (e >> 8) : 0u);      // <= 24 bits
+            if (DCSB_ANY(code && e == 0)) {
                 // codes longer than 8 bits: rare, matched bit-serially
-                uint32_t q = win.pos() + (uint32_t)run;
-                const int val = dcsb_long_code(rd, q, tab->long94, tab->n_long94);
-                win.seek(q);
-                if (val < 0) { rc = DCSB_WALK_BANDTYPE; break; }
-                delta = val - 0x2E;
-            } else {
-                win.skip((uint32_t)run + (e >> 8));             // <= 24 bits
-                delta = (int)(e & 0xFF) - 0x2E;
-            }
-            const uint32_t sh = (uint32_t)(b & 7) * 4u;
-            const uint32_t w = b < 8 ? bt_lo : bt_hi;
-            const int nbt = (int)((w >> sh) & 15u) + delta;
-            if (nbt & ~15) { rc = DCSB_WALK_BANDTYPE; break; }
-            const uint32_t nw = w + ((uint32_t)delta << sh);    // stays inside the nibble: 0 <= nbt <= 15
-            if (b < 8) bt_lo = nw; else bt_hi = nw;
-            const uint32_t d = dtab[dsel + ((halfmask >> b) & 1u) * 256u + (uint32_t)b * 16u + (uint32_t)nbt];
-            desc[b] = d;
-            live = (live & ~(1u << b)) | ((d ? 1u : 0u) << b);
-            ++b;
-        }
-        // (a code that reaches into the bytes behind the stream is a truncation, whatever those bytes are)
-        if (rc) { status = win.pos() > nbits ? -2 : rc; nplay = f; break; }
-        DCSB_DBG_LAP(1)
-        const uint32_t hpos = win.pos();
-        out.hdrbits[s.frame_base + f] = (uint16_t)(hpos - pos);
-        // ---- bands: lengths only
-        int sb = 99;
-        uint32_t m = live;
-        int b = m ? dcsb_ctz(m) : 16;
-        uint32_t d = desc[b];
-        while (m) {
-            m &= m - 1;
-            const int bn = m ? dcsb_ctz(m) : 16;
-            const uint32_t dn = desc[bn];                       // the next band's descriptor is on its way while this band is walked
-            if (d & DCSB_DESC_HUFF) {
-                // Huffman band (:2186-2225).  A table entry is {m8, m1}: m8 = as many whole codewords as
-                // fit in the next 13 bits (at most 8 slots), m1 = the first codeword alone; each byte is
-                // slots << 4 | bits.  Rs = (16 * slots left + 15) << 8 | 0xFF, so "the multi-symbol step
-                // covers more slots than are left" is one compare on the raw entry, and the single
-                // codeword is taken instead (a 'two zeros' codeword with one slot left leaves Rs < 0:
-                // the reference's error case, :2213-2218).  t = 50 - s: the table index is the 64-bit
-                // window shifted right by t, so the chain per step is shift, mask|base, load, compare,
-                // select, subtract.
-                const DcsbTxBase tb = tx + (((d >> 24) & 7u) << 14);
-                int Rs = (int)(d & 0x3FFFFu);
-                int t = 50 - (int)win.s;
-                while (Rs > 0x0FFF) {
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        DCSB_DBG(++dbg_steps;)
-                        const uint32_t v = (uint32_t)((((uint64_t)win.w0 << 32) | win.w1) >> t);
-                        const uint32_t m16 = dcsb_tx_load(tb, v);
-                        const uint32_t act = (uint32_t)((0x0FFF - Rs) >> 31);      // all ones while slots are left
-                        const uint32_t b8 = (m16 >> 8) & act, b1 = m16 & 0xFFu & act;
-                        const uint32_t mm = Rs >= (int)m16 ? b8 : b1;
-                        t -= (int)(mm & 15u);
-                        Rs -= (int)((mm & 0xF0u) << 8);
-                    }
-                    win.refill_t(t);
+                if (code && e == 0) {
+                    uint32_t q = win.pos() + (uint32_t)runl;
+                    const int val = dcsb_long_code(rd, q, tab->long94, tab->n_long94);
+                    win.seek(q);
+                    adv = 0;
+                    if (val < 0) { rc = DCSB_WALK_BANDTYPE; hb = nb; }
+                    delta = val - 0x2E;
                 }
-                win.s = (uint32_t)(50 - t);
-                if (Rs < 0 && sb > b) sb = b;        // 'two zeros' with one slot left (:2213-2218)
-            } else {
-                // fixed-width band (:2227-2234): count * width bits, closed form
-                const uint32_t fbits = (d >> 16) & 0x3FFu;
-                if (fbits <= 32) win.skip(fbits);
-                else win.seek(win.pos() + fbits);
             }
-            b = bn;
-            d = dn;
+            if (on) win.skip(adv);
+            if (code && !rc) {
+                const uint32_t sh = (uint32_t)(b & 7) * 4u;
+                const uint32_t w = b < 8 ? bt_lo : bt_hi;
+                const int nbt = (int)((w >> sh) & 15u) + delta;
+                if (nbt & ~15) { rc = DCSB_WALK_BANDTYPE; hb = nb; }
+                else {
+                    const uint32_t nw = w + ((uint32_t)delta << sh);    // stays inside the nibble: 0 <= nbt <= 15
+                    if (b < 8) bt_lo = nw; else bt_hi = nw;
+                    const uint32_t d = dtab[dsel + ((halfmask >> b) & 1u) * 256u + (uint32_t)b * 16u + (uint32_t)nbt];
+                    desc[b] = d;
+                    live = (live & ~(1u << b)) | ((d ? 1u : 0u) << b);
+                    hb = b + 1;
+                }
+            } else if (on && !rc) hb = nb;                      // the run reached the last band
         }
-        DCSB_DBG_LAP(2)
-        pos = win.pos();
-        if (pos > nbits) { status = -2; nplay = f; break; }                       // DCSB_E_TRUNCATED
-        if (sb != 99) { status = -5; nplay = f + 1; stopband = sb; ++f; break; }    // DCSB_E_STOPPED
-        if ((f & 15) == 15) {
-            // let the decode warps have the frames so far (entry f + 1 = this frame's own band types)
-            out.bitpos[s.frame_base + f + 1] = pos;
-            out.bt[s.frame_base + f + 1] = make_uint2(bt_lo, bt_hi);
-            dcsb_publish(out.progress, si, f + 2);
+        const uint32_t hpos = win.pos();
+        // (a code that reaches into the bytes behind the stream is a truncation, whatever those bytes are)
+        if (run && rc) { status = hpos > nbits ? -2 : rc; nplay = f; run = false; }
+        if (run) out.hdrbits[s.frame_base + f] = (uint16_t)(hpos - pos);
+        // ---- bands: lengths only.  One table step per iteration for whichever Huffman band the lane
+        // is in (:2186-2225).  A table entry is {m8, m1}: m8 = as many whole codewords as fit in the
+        // next 13 bits (at most 8 slots), m1 = the first codeword alone; each byte is slots << 4 | bits.
+        // Rs = (16 * slots left + 15) << 8 | 0xFF, so "the multi-symbol step covers more slots than are
+        // left" is one compare on the raw entry, and the single codeword is taken instead (a 'two
+        // zeros' codeword with one slot left leaves Rs < 0: the reference's error case, :2213-2218).
+        // t = 50 - s: the table index is the 64-bit window shifted right by t.
+        int sb = 99;
+        {
+            // dn / bn: descriptor and index of the next band to take; m: the bands behind it.  The
+            // descriptor behind dn is loaded every iteration (desc[16] = 0 ends the list), so that a
+            // band switch is a handful of selects on values that are already there.
+            uint32_t m = run ? live : 0u;
+            int bn = m ? dcsb_ctz(m) : 16;
+            m &= m - 1;
+            uint32_t dn = desc[bn];
+            int bcur = 16, Rs = 0;
+            DcsbTxBase tb = tx;
+            int t = 50 - (int)win.s;
+            uint32_t fix = 0;                                   // bits of a fixed-width band waiting for the re-seek
+            bool fin = dn == 0;                                 // nothing (left) to walk in this frame
+            for (;;) {
+                // votes on the state the previous iteration left, consumed at the END of this one: the
+                // branches resolve long before they are reached (one idle iteration per frame and per
+                // fixed-width band is the price)
+                const bool any_fix = DCSB_ANY(fix != 0);
+                const bool alive = DCSB_ANY(!fin);
+                const int bnn = m ? dcsb_ctz(m) : 16;
+                const uint32_t dnn = desc[bnn];
+                const DcsbTxBase tbn = tx + (((dn >> 24) & 7u) << 14);
+                const int Rsn = (int)dn < 0 ? (int)(dn & 0x3FFFFu) : 0;         // Huffman band: its slot budget
+                const uint32_t fixn = (int)dn < 0 ? 0u : (dn >> 16) & 0x3FFu;   // fixed-width band (:2227-2234): count * width bits
+                // -- one table step (a no-op once the band has no slots left)
+                const uint32_t v = (uint32_t)((((uint64_t)win.w0 << 32) | win.w1) >> t);
+                const uint32_t m16 = dcsb_tx_load(tb, v);
+                const uint32_t rmask = (uint32_t)((t - 19) >> 31);              // all ones when s >= 32: drop a word
+                {
+                    const uint32_t nw1 = DcsbBits::be(win.nx), ld = win.ring_word(win.wa);
+                    win.w0 ^= (win.w0 ^ win.w1) & rmask;
+                    win.w1 ^= (win.w1 ^ nw1) & rmask;
+                    win.nx ^= (win.nx ^ ld) & rmask;
+                    win.wa += 4u & rmask;
+                }
+                const uint32_t act = (uint32_t)((0x0FFF - Rs) >> 31);           // all ones while slots are left
+                const uint32_t b8 = (m16 >> 8) & act, b1 = m16 & 0xFFu & act;
+                const uint32_t mm = Rs >= (int)m16 ? b8 : b1;
+                t = t - (int)(mm & 15u) + (int)(32u & rmask);
+                Rs -= (int)((mm & 0xF0u) << 8);
+                sb = (Rs < 0 && sb > bcur) ? bcur : sb;                         // 'two zeros' with one slot left (:2213-2218)
+                // -- band switch: take the next band once this one has no slots left
+                const bool take = Rs <= 0x0FFF && fix == 0 && dn != 0;
+                tb = take ? tbn : tb;
+                Rs = take ? Rsn : Rs;
+                fix = take ? fixn : fix;
+                bcur = take ? bn : bcur;
+                bn = take ? bnn : bn;
+                dn = take ? dnn : dn;
+                m = take ? (m & (m - 1)) : m;
+                fin = Rs <= 0x0FFF && fix == 0 && dn == 0;
+                // -- closed-form skip of a fixed-width band: re-seek the window in the ring
+                if (any_fix) {
+                    if (fix) {
+                        win.s = (uint32_t)(50 - t);
+                        win.seek(win.pos() + fix);
+                        t = 50 - (int)win.s;
+                        fix = 0;
+                        fin = Rs <= 0x0FFF && dn == 0;
+                    }
+                }
+                if (!alive) break;
+            }
+            win.s = (uint32_t)(50 - t);
+            win.refill();
         }
-        if (f + 1 == qnext) {
-            out.bitpos[s.frame_base + f + 1] = pos;
-            out.bt[s.frame_base + f + 1] = make_uint2(bt_lo, bt_hi);
-            dcsb_queue_push(out, si, queued, f + 1, false);
-            queued = f + 1;
-            qnext += DCSB_QITEM;
+        if (run) {
+            pos = win.pos();
+            if (pos > nbits) { status = -2; nplay = f; run = false; }                       // DCSB_E_TRUNCATED
+            else if (sb != 99) { status = -5; nplay = f + 1; stopband = sb; ++f; run = false; }    // DCSB_E_STOPPED
+            else {
+                if ((f & 15) == 15) {
+                    // let the decode warps have the frames so far (entry f + 1 = this frame's own band types)
+                    out.bitpos[s.frame_base + f + 1] = pos;
+                    out.bt[s.frame_base + f + 1] = make_uint2(bt_lo, bt_hi);
+                    dcsb_publish(out.progress, si, f + 2);
+                }
+                if (f + 1 == qnext) {
+                    out.bitpos[s.frame_base + f + 1] = pos;
+                    out.bt[s.frame_base + f + 1] = make_uint2(bt_lo, bt_hi);
+                    dcsb_queue_push(out, si, queued, f + 1, false);
+                    queued = f + 1;
+                    qnext += DCSB_QITEM;
+                }
+                ++f;
+                run = f < fe;
+            }
         }
     }
+#if DCSB_DEVICE_PASS
+    asm volatile("cp.async.wait_group 0;" ::: "memory");    // nothing in flight when the ring is reused
+#endif
+    if (!mine) return;
     // end checkpoint: band types after the last decodable frame (decode lanes read bt[f + 1]).
     // After a truncated / undecodable frame f the checkpoint of f itself already is the end.
     if ((status == 0 && s.nframes) || status == -5) {
         out.bitpos[s.frame_base + f] = pos;
         out.bt[s.frame_base + f] = make_uint2(bt_lo, bt_hi);
     }
-#if DCSB_DEVICE_PASS
-    asm volatile("cp.async.wait_group 0;" ::: "memory");    // nothing in flight when the ring is reused
-#endif
     if (status == 0 && f < s.nframes) status = DCSB_SCAN_RUNNING;       // the next slice carries on from checkpoint f
-#if defined(DCSB_SCAN_DEBUG) && DCSB_DEVICE_PASS
-    if (out.dbg) {
-        const long long dt = clock64() - dbg_t0;
-        out.dbg[8 * si] = (uint32_t)dt; out.dbg[8 * si + 1] = (uint32_t)(dt >> 32);
-        out.dbg[8 * si + 2] = dbg_steps; out.dbg[8 * si + 3] = dbg_hdr;
-        for (int k = 0; k < 4; ++k) out.dbg[8 * si + 4 + k] = dbg_c[k];     // topup, header, huffman loops, rest
-    }
-#endif
     out.status[si] = status;
     out.nplay[si] = nplay;
     out.endbits[si] = status == -2 ? nbits : pos;      // a truncated stream occupies all of its bytes

@@ -58,7 +58,9 @@ typedef struct {
 } dcsb_stream_desc;
 /* a zero frame count plays 65,536 frames, as the reference's wrapped 16-bit frame counter makes it
  * (DCSDecoderNative.cpp:1411-1415, :1565) -- what track playback from a ROM does; without the flag
- * such a stream is rejected with DCSB_E_EMPTY */
+ * such a stream is rejected with DCSB_E_EMPTY.  Honoured by dcsb_batch_create (whose PCM layout comes
+ * from dcsb_batch_pcm_offset / dcsb_batch_total_samples) and used internally by ROM playback;
+ * dcsb_decode_streams, whose caller sizes pcm_out from the count as written, refuses it (DCSB_E_ARG). */
 #define DCSB_STREAM_WRAP_EMPTY 1
 
 typedef struct {

@@ -136,6 +136,45 @@ def test_zip_loader(built, tmp_path):
         dx.Rom(zip_path=z2)
 
 
+def test_zip_loader_malformed(built, tmp_path):
+    """Crafted / damaged zip directories are refused, never read out of bounds (the directory's name length,
+    entry count, directory offset and uncompressed size are all attacker-controlled)."""
+    import struct
+    import dcsexplorer_b200 as dx
+    sc = romscen.make_scenario(os_version=rb.OS95, seed=9)
+    good = tmp_path / "good.zip"
+    with zipfile.ZipFile(good, "w", zipfile.ZIP_DEFLATED) as f:
+        f.writestr("snd_u2.rom", sc["images"][2])
+        f.writestr("snd_u3.rom", sc["images"][3])
+    raw = bytearray(good.read_bytes())
+    eocd = raw.rfind(b"PK\x05\x06")
+    cd = struct.unpack_from("<I", raw, eocd + 16)[0]
+
+    def broken(name, mut):
+        b = bytearray(raw)
+        mut(b)
+        q = tmp_path / name
+        q.write_bytes(bytes(b))
+        with pytest.raises(dx.DcsbError):
+            dx.Rom(zip_path=q)
+
+    broken("namelen.zip", lambda b: struct.pack_into("<H", b, cd + 28, 60000))          # name runs past the file
+    broken("usize.zip", lambda b: struct.pack_into("<I", b, cd + 24, 0xFFFFFFF0))         # 4 GB claimed
+    broken("count.zip", lambda b: struct.pack_into("<H", b, eocd + 10, 5000))             # more entries than bytes
+    broken("cdofs.zip", lambda b: struct.pack_into("<I", b, eocd + 16, len(b) + 100))     # directory outside the file
+    broken("lho.zip", lambda b: struct.pack_into("<I", b, cd + 42, len(b) - 8))           # local header outside the file
+    broken("csize.zip", lambda b: struct.pack_into("<I", b, cd + 20, 0x7FFFFFFF))         # compressed size past the end
+    # the 68-byte shape of the advisor's finding: an end record right behind one directory entry with a huge name length
+    tiny = bytearray(46 + 22)
+    struct.pack_into("<I", tiny, 0, 0x02014b50)
+    struct.pack_into("<H", tiny, 28, 60000)
+    struct.pack_into("<IHHHHII", tiny, 46, 0x06054b50, 0, 0, 1, 1, 46, 0)
+    q = tmp_path / "tiny.zip"
+    q.write_bytes(bytes(tiny))
+    with pytest.raises(dx.DcsbError):
+        dx.Rom(zip_path=q)
+
+
 @needs_ref
 @pytest.mark.parametrize("name", ["os94", "os95-v105", "os93b", "os93a", "os94-errors"])
 def test_decompile_vs_reference(built, name):
