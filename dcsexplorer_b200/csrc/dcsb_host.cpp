@@ -89,7 +89,7 @@ void dcsb_build_tables(DcsbTables *t)
         for (int x = 0; x < DCSB_T8_CB; ++x) {
             uint32_t m[2];
             for (int which = 0; which < 2; ++which) {
-                const int P = which ? DCSB_T1_PEEK : DCSB_T8_PEEK, cap = which ? 1 : 8;
+                const int P = which ? DCSB_T1_PEEK : DCSB_T8_PEEK, cap = which ? 1 : DCSB_T8_CAP;
                 const int xp = x >> (DCSB_T8_PEEK - P);
                 int used = 0, slots = 0;
                 for (;;) {
@@ -105,9 +105,9 @@ void dcsb_build_tables(DcsbTables *t)
                     slots += add;
                     if (slots >= cap) break;
                 }
-                m[which] = (uint32_t)((slots << 4) | used);
+                m[which] = (uint32_t)((slots << 12) | used);
             }
-            t->tx[(k << DCSB_T8_PEEK) + x] = (uint16_t)((m[0] << 8) | m[1]);
+            t->tx[(k << DCSB_T8_PEEK) + x] = (m[1] << 16) | m[0];
         }
 }
 

@@ -43,9 +43,10 @@ struct DcsbTile { uint32_t stream; uint32_t first; uint32_t count; };
 #define DCSB_LUT_XLAT    1772   // 48:  1994 type-1 band translation, 3 groups x 16: (codebook/width << 8) | scale adjust
 #define DCSB_LUT_WORDS   1820
 
-// scan: length table of the 1994 sample codebooks (dcsb_scan94.cuh); entry = m8 << 8 | m1, each slots << 4 | bits
-#define DCSB_T8_PEEK 13
+// scan: length table of the 1994 sample codebooks (dcsb_scan94.cuh); entry = y1 << 16 | y8, each slots << 12 | bits
+#define DCSB_T8_PEEK 12
 #define DCSB_T8_CB   (1 << DCSB_T8_PEEK)            // entries per codebook (16 KB)
+#define DCSB_T8_CAP  15                             // most output slots one multi-codeword step covers
 #define DCSB_T1_PEEK 9                              // the single-codeword part depends on the first 9 bits only
 
 struct DcsbLongCode { uint32_t code; uint8_t len; uint8_t val; uint16_t pad; };
@@ -62,9 +63,9 @@ struct DcsbTables {
     // 1994 fast path
     int tw_c2[64], tw_s2[64];      // butterfly twiddles pre-doubled (2cos, 2sin), partition order
     int pre_c0[64], pre_c1[64];    // pre-pass coefficients pre-doubled, natural order
-    // scan: tx[codebook][next 13 bits] = m8 << 8 | m1; m8 = as many whole codewords as fit (at most 8
-    // output slots), m1 = exactly one codeword; low nibble = bits consumed, high nibble = output slots covered
-    uint16_t tx[6 * DCSB_T8_CB];
+    // scan: tx[codebook][next 12 bits] = y1 << 16 | y8; y8 = as many whole codewords as fit (at most 15
+    // output slots), y1 = exactly one codeword; y = output slots covered << 12 | bits consumed
+    uint32_t tx[6 * DCSB_T8_CB];
 };
 
 #define DCSB_DEV_E_QUEUE 1u                // decode warp: no work item arrived (scan CTA not resident / lost)
@@ -101,7 +102,7 @@ struct DcsbScanOut {
 };
 
 void dcsb_build_tables(DcsbTables *t);   // host
-#define DCSB_SCAN_MAXWARPS 3              // most lock-step warps (32 streams, 1 KB ring each) a scan CTA holds
+#define DCSB_SCAN_MAXWARPS 2              // most lock-step warps (32 streams, 1 KB ring each) a scan CTA holds
 // SM count of the device the context runs on (cudaDevAttrMultiProcessorCount; 148 on a B200): sizes the
 // scan grid and the persistent decode grid
 int dcsb_num_sms();

@@ -40,13 +40,14 @@ __device__ __forceinline__ void dcsb_load_lut(uint16_t *s_lut, const DcsbTables 
 // are walked by their lane alone first (dcsb_scan_stream), the lane then idles in the lock-step
 // walk of its warp.
 // Shared memory: the length table tx (96 KB) sits on a 16 KB boundary of the shared window
-// (dcsb_tx_load); the peek LUTs and the band-descriptor table go into the alignment gap in front
-// of it or behind it, whichever is large enough; then one 1 KB ring (+ 16 bytes, so that the
-// rings of a warp start in different banks) and 17 band descriptors per lane.
-#define DCSB_RING_STRIDE (DCSB_RING_BYTES + 16u)
-#define DCSB_TX_BYTES (6 * DCSB_T8_CB * 2)
-#define DCSB_SCAN_SMALL (((DCSB_LUT_WORDS * 2 + 15) & ~15) + DCSB_DTAB_WORDS * 4)
-#define DCSB_SCAN_WARP_BYTES (32u * DCSB_RING_STRIDE + 32u * 17u * 4u)
+// (table | index is one LOP3), the rings follow it (1 KB each, 1 KB aligned: ring | offset), then
+// 18 band entries of 16 bytes per lane; the peek LUTs, the band-descriptor table and the zero
+// word go into the alignment gap in front of the table or behind everything, whichever is large enough.
+#define DCSB_TX_BYTES (6 * DCSB_T8_CB * 4)
+#define DCSB_SCAN_LUT_BYTES ((DCSB_LUT_WORDS * 2 + 15) & ~15)
+#define DCSB_SCAN_SMALL (DCSB_SCAN_LUT_BYTES + DCSB_DTAB_WORDS * 4 + 16)
+#define DCSB_SCAN_ENT_STRIDE (19u * 16u)        // 18 entries + 16 bytes: lanes start 12 banks apart, LDS.128 conflict-free
+#define DCSB_SCAN_WARP_BYTES (32u * DCSB_RING_BYTES + 32u * DCSB_SCAN_ENT_STRIDE)
 #define DCSB_SCAN_SMEM(warps) (16384u + DCSB_TX_BYTES + (warps) * DCSB_SCAN_WARP_BYTES)
 static_assert(DCSB_SCAN_SMALL <= 8192, "the small tables must fit the smaller alignment gap");
 static_assert(DCSB_SCAN_SMEM(DCSB_SCAN_MAXWARPS) <= 232448, "scan CTA exceeds the shared memory of an SM");
@@ -60,28 +61,36 @@ dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restri
     const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t tx = (s_base + 16383u) & ~16383u;
     const uint32_t tx_off = tx - s_base;
-    const uint32_t small_off = tx_off >= DCSB_SCAN_SMALL ? 0u : tx_off + DCSB_TX_BYTES;
-    uint16_t *s_lut = reinterpret_cast<uint16_t *>(sm8 + small_off);
-    uint32_t *s_dtab = reinterpret_cast<uint32_t *>(sm8 + small_off + ((DCSB_LUT_WORDS * 2 + 15) & ~15));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-    const uint32_t warp_off = 16384u + DCSB_TX_BYTES + (uint32_t)warp * DCSB_SCAN_WARP_BYTES;
+    const uint32_t rings_off = tx_off + DCSB_TX_BYTES;                          // 16 KB aligned in the shared window
+    const uint32_t ents_off = rings_off + (uint32_t)warps * 32u * DCSB_RING_BYTES;
+    const uint32_t small_off = tx_off >= DCSB_SCAN_SMALL ? 0u : ents_off + (uint32_t)warps * 32u * DCSB_SCAN_ENT_STRIDE;
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(sm8 + small_off);
+    uint32_t *s_dtab = reinterpret_cast<uint32_t *>(sm8 + small_off + DCSB_SCAN_LUT_BYTES);
+    const uint32_t zero_off = small_off + DCSB_SCAN_LUT_BYTES + DCSB_DTAB_WORDS * 4;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(tab->tx);
         uint4 *dst = reinterpret_cast<uint4 *>(sm8 + tx_off);
         for (int i = threadIdx.x; i < DCSB_TX_BYTES / 16; i += blockDim.x) dst[i] = __ldg(src + i);
     }
-    if (threadIdx.x == 0 && out.started) atomicAdd(out.started, 1u);       // this CTA is resident (dcsb_gate_kernel)
+    if (threadIdx.x == 0) {
+        *reinterpret_cast<uint4 *>(sm8 + zero_off) = make_uint4(0, 0, 0, 0);
+        if (out.started) atomicAdd(out.started, 1u);       // this CTA is resident (dcsb_gate_kernel)
+    }
     dcsb_load_lut(s_lut, tab);
     for (int i = threadIdx.x; i < DCSB_DTAB_WORDS; i += blockDim.x) s_dtab[i] = dcsb_dtab_entry(s_lut, i);
     __syncthreads();
+    const uint32_t ring_off = rings_off + ((uint32_t)warp * 32u + (uint32_t)lane) * DCSB_RING_BYTES;
+    const uint32_t ent_off = ents_off + ((uint32_t)warp * 32u + (uint32_t)lane) * DCSB_SCAN_ENT_STRIDE;
 #if DCSB_DEVICE_PASS
-    const DcsbRingPtr ring = s_base + warp_off + (uint32_t)lane * DCSB_RING_STRIDE;
+    const DcsbRingPtr ring = s_base + ring_off;
     const DcsbTxBase txb = tx;
+    const DcsbSA ents = s_base + ent_off, zero = s_base + zero_off;
 #else       // (nvcc's host pass only type-checks this body)
-    const DcsbRingPtr ring = sm8 + warp_off + (uint32_t)lane * DCSB_RING_STRIDE;
-    const DcsbTxBase txb = sm8 + tx_off;
+    const DcsbRingPtr ring = reinterpret_cast<DcsbSA>(sm8 + ring_off);
+    const DcsbTxBase txb = reinterpret_cast<DcsbSA>(sm8 + tx_off);
+    const DcsbSA ents = reinterpret_cast<DcsbSA>(sm8 + ent_off), zero = reinterpret_cast<DcsbSA>(sm8 + zero_off);
 #endif
-    uint32_t *desc = reinterpret_cast<uint32_t *>(sm8 + warp_off + 32u * DCSB_RING_STRIDE) + lane * 17;
     const int ngroups = (nstreams + 31) >> 5;
     for (int g = blockIdx.x * warps + warp; g < ngroups; g += gridDim.x * warps) {
         const int k = g * 32 + lane;
@@ -92,7 +101,7 @@ dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restri
             si = -1;
         }
         __syncwarp();
-        dcsb_scan94_stream(slab, streams, si, tab, s_lut, txb, s_dtab, ring, desc, out, f0, f1);
+        dcsb_scan94_stream(slab, streams, si, tab, s_lut, txb, s_dtab, ring, ents, zero, out, f0, f1);
         __syncwarp();
     }
 }

@@ -1,34 +1,40 @@
-// dcsb200 K1 body for the 1994+ frame layout: the frame-boundary scan.
+// dcsb200 K1 body for the 1994+ frame layout: the frame-boundary scan, walked in LOCK STEP.
 //
-// One thread walks one stream (lengths only) and writes one checkpoint per frame plus the end
-// checkpoint:
+// A warp walks 32 streams, lane = stream (lengths only), and writes one checkpoint per frame plus
+// the end checkpoint:
 //   bitpos[f]  bit position of the frame start,   bt[f] band types carried INTO frame f,
 //   hdrbits[f] length of the frame header (the decode lanes start at the first band and take
 //              the frame's own band types from bt[f + 1]).
 // It replaces the frame walk implicit in DecodeStream / GetStreamInfo (DCSDecoderNative.cpp:
 // 1486-1589) and the header part of DecompressFrame (:1780-1834).
 //
-// The scan is one dependent chain per stream (position -> bits at that position -> next
-// position); what counts is the length of that chain and how many instructions hang off it:
-//  * the stream bytes are staged in a per-stream 1 KB shared-memory ring that cp.async fills
-//    a whole frame ahead, so the register bit window refills with LDS (no global latency on the
-//    chain) and a long skip (fixed-width bands) re-seeks inside the ring;
-//  * Huffman bands advance with a multi-symbol length table tx[codebook][next 13 bits] =
-//    {m8, m1}: m8 = {bits consumed, output slots covered} of as many whole codewords as fit in
-//    the peek (at most 8 slots), m1 = the same for the first codeword alone.  When the m8 step
-//    would cover more slots than the band has left, m1 is taken instead, so a step never
-//    overruns the band and the table address depends on the bit position only, not on the slot
-//    count; both come with ONE load (two tables and a predicated second load cost a second
-//    shared-memory latency on the chain).  (A 'two zeros' codeword with one slot left leaves
-//    rem < 0: the reference's error case, :2213-2218);
-//  * band descriptors (kind, codebook, slot count) are kept per band and only looked up again
-//    (one load from a 4 KB table) when a frame header changes the band's type; the band loop
-//    walks the non-empty bands only;
-//  * the frame header's 1-bit "unchanged" codes are skipped as a run (count leading ones);
-//  * fixed-width bands advance in closed form.
+// Every stream is one dependent chain (position -> bits at that position -> next position) and
+// the 32 lanes of a warp run ONE instruction stream, so what the scan costs is (iterations of
+// the slowest lane) x (instructions per iteration): a warp alone on its scheduler issues one
+// ALU instruction every other cycle.  The band loop's iteration is therefore kept to two
+// dozen instructions:
+//  * state of a lane in ONE register S = slots left << 12 | 0xF00 | t, t = 50 - bit offset in the
+//    64-bit window.  A table entry is {y1 << 16 | y8}, y = slots << 12 | bits: y8 = as many whole
+//    codewords as fit in the next 12 bits (at most 15 slots), y1 = the first codeword alone, taken
+//    when y8 would cover more slots than the band has left (one compare S >= y8; the 0xF00 filler
+//    makes the comparison independent of t).  The step is S = S - y + refill: position and slot
+//    budget move with one add.  (A 'two zeros' codeword with one slot left leaves S < 0: the
+//    reference's error case, :2213-2218);
+//  * the window refill is decided from the position BEFORE the step (the 64-bit window has the
+//    room: bit offset <= 43) and done with predicated moves, off the dependent chain;
+//  * the bands of a lane are 16-byte entries {table, slots, mask, fixed bits} in a lane-private
+//    array, pre-expanded when a frame header changes a band's type; the next entry is loaded an
+//    iteration ahead, so the band switch is five predicated moves folded into the iteration;
+//  * a lane without slots (frame finished, or waiting) looks up a zero entry (mask 0): a no-op;
+//  * a fixed-width band's closed-form skip needs the window re-seeked in the ring: that block
+//    is only compiled into the loop variant used for frames in which some lane has such a band;
+//  * the loop's exit vote is taken on the state of the previous iteration, so the branch
+//    resolves long before it is reached.
+// The stream bytes are staged in a per-stream 1 KB shared-memory ring that cp.async fills a whole
+// frame ahead.  Streams are ordered by cost (dcsb_scan_order), so a warp holds alike streams.
 //
 // Compiled by nvcc for sm_100a (the product) and by g++ for the CPU-side kernel simulator
-// (tests/hostsim, test infrastructure only; cp.async becomes an immediate copy there).
+// (tests/hostsim, test infrastructure only: a warp of ONE lane; cp.async becomes an immediate copy).
 #pragma once
 #include <string.h>
 #include "dcsb_core.cuh"
@@ -37,49 +43,92 @@
 #define DCSB_RING_BYTES  1024u
 #define DCSB_RING_CHUNKS (DCSB_RING_BYTES / 16u)
 // the farthest a frame can reach past its first chunk: 16 header codes of up to 23 bits plus
-// 255 samples of up to 15 bits (543 bytes), plus the window's three words and chunk rounding
+// 255 samples of up to 15 bits (543 bytes), plus the window's words and chunk rounding
 #define DCSB_RING_FRAME_CHUNKS 36u
 
+// Shared-memory addresses: 32-bit shared-window addresses on the device (so that table | index
+// is one LOP3 and loads are plain LDS), pointers in the simulator.
+#if DCSB_DEVICE_PASS
+typedef uint32_t DcsbSA;
+DCSB_HD uint32_t dcsb_lds32(DcsbSA a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+DCSB_HD DcsbSA dcsb_sa_or(DcsbSA base, uint32_t off) { return base | off; }     // base is aligned beyond off's range
+#else
+typedef uintptr_t DcsbSA;
+DCSB_HD uint32_t dcsb_lds32(DcsbSA a) { uint32_t v; memcpy(&v, reinterpret_cast<const void *>(a), 4); return v; }
+DCSB_HD DcsbSA dcsb_sa_or(DcsbSA base, uint32_t off) { return base + off; }
+#endif
+typedef DcsbSA DcsbTxBase;
+typedef DcsbSA DcsbRingPtr;
+// (a & b) | c in one LOP3
+DCSB_HD uint32_t dcsb_and_or(uint32_t a, uint32_t b, uint32_t c)
+{
+#if DCSB_DEVICE_PASS
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+#else
+    return (a & b) | c;
+#endif
+}
+
+// One band of a lane's current frame, as the band loop takes it.
+struct DcsbBandEnt {
+    DcsbSA tb;          // length table of the band's codebook (16 KB aligned), or the zero word
+    uint32_t sinit;     // slots << 12 | 0xF00
+    uint32_t amask;     // 0x3FFC (table index bits) or 0 (no table: the lookup reads the zero word)
+    int32_t fix;        // > 0: fixed-width band, bits to skip; -1: end of the frame's list; else 0
+};
+#if DCSB_DEVICE_PASS
+static_assert(sizeof(DcsbBandEnt) == 16, "band entries are loaded with one LDS.128");
+#endif
+#define DCSB_ENT_BYTES ((uint32_t)sizeof(DcsbBandEnt))
+
+DCSB_HD DcsbBandEnt dcsb_ent_load(DcsbSA a)
+{
+    DcsbBandEnt e;
+#if DCSB_DEVICE_PASS
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e.tb), "=r"(e.sinit), "=r"(e.amask), "=r"(e.fix) : "r"(a));
+#else
+    memcpy(&e, reinterpret_cast<const void *>(a), sizeof(e));
+#endif
+    return e;
+}
+DCSB_HD void dcsb_ent_store(DcsbSA a, const DcsbBandEnt &e)
+{
+#if DCSB_DEVICE_PASS
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(e.tb), "r"(e.sinit), "r"(e.amask), "r"(e.fix) : "memory");
+#else
+    memcpy(reinterpret_cast<void *>(a), &e, sizeof(e));
+#endif
+}
+
+// Bit window over the ring: w0:w1 = 64 stream bits (big-endian order), s = bit offset of the next
+// bit inside them, wa = byte offset (from chunk 0, cumulative) of the next word the ring hands out.
 struct DcsbRingWin {
-    uint32_t w0, w1, nx;    // current / next word (big-endian order), prefetched raw word
-    uint32_t s;             // bit offset inside w0
-    uint32_t wa;            // byte offset (from chunk 0) of the next word the ring hands out
+    uint32_t w0, w1;
+    uint32_t s;
+    uint32_t wa;
     uint32_t bias;          // bit offset of the stream's first data bit from chunk 0
     uint32_t fill;          // chunks issued so far
     uint32_t limit;         // chunks that exist (stream bytes + slack)
     const uint8_t *g;       // global address of chunk 0 (16-byte aligned)
-#if DCSB_DEVICE_PASS
-    uint32_t ring;          // shared-window address of this stream's ring (16-byte aligned)
-#else
-    uint8_t *ring;
-#endif
+    DcsbRingPtr ring;       // this stream's ring (1 KB aligned in the shared window)
 
-    DCSB_HD uint32_t ring_word(uint32_t off) const
-    {
-#if DCSB_DEVICE_PASS
-        uint32_t v;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring + (off & (DCSB_RING_BYTES - 1))));
-        return v;
-#else
-        uint32_t v;
-        memcpy(&v, ring + (off & (DCSB_RING_BYTES - 1)), 4);
-        return v;
-#endif
-    }
+    DCSB_HD uint32_t ring_word(uint32_t off) const { return dcsb_lds32(dcsb_sa_or(ring, off & (DCSB_RING_BYTES - 1))); }
     // issue the chunks up to DCSB_RING_CHUNKS - 1 ahead of the window, then make sure everything
-    // the next frame can touch has landed.  Call at a frame start only.
+    // the next frame can touch has landed.  Call at a frame start only (s < 32).
     DCSB_HD void topup()
     {
-        const uint32_t cc = (wa - 12u) >> 4;                       // chunk holding w0
+        const uint32_t cc = (wa - 8u) >> 4;                        // chunk holding w0
         uint32_t target = cc + DCSB_RING_CHUNKS - 1u;
         if (target > limit) target = limit;
         const bool behind = fill < cc + DCSB_RING_FRAME_CHUNKS && fill < limit;
         while (fill < target) {
 #if DCSB_DEVICE_PASS
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ring + ((fill * 16u) & (DCSB_RING_BYTES - 1))),
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ring | ((fill * 16u) & (DCSB_RING_BYTES - 1))),
                          "l"(g + (size_t)fill * 16u) : "memory");
 #else
-            memcpy(ring + ((fill * 16u) & (DCSB_RING_BYTES - 1)), g + (size_t)fill * 16u, 16);
+            memcpy(reinterpret_cast<void *>(ring + ((fill * 16u) & (DCSB_RING_BYTES - 1))), g + (size_t)fill * 16u, 16);
 #endif
             ++fill;
         }
@@ -98,11 +147,10 @@ struct DcsbRingWin {
         s = a & 31u;
         w0 = DcsbBits::be(ring_word(off));
         w1 = DcsbBits::be(ring_word(off + 4u));
-        nx = ring_word(off + 8u);
-        wa = off + 12u;
+        wa = off + 8u;
     }
-    DCSB_HD uint32_t pos() const { return (wa - 12u) * 8u + s - bias; }
-    DCSB_HD uint32_t peek32() const
+    DCSB_HD uint32_t pos() const { return (wa - 8u) * 8u + s - bias; }
+    DCSB_HD uint32_t peek32() const      // s < 32
     {
 #if DCSB_DEVICE_PASS
         return __funnelshift_l(w1, w0, s);
@@ -110,68 +158,23 @@ struct DcsbRingWin {
         return s ? ((w0 << s) | (w1 >> (32 - s))) : w0;
 #endif
     }
-    // valid while s + bits <= 64: two short reads (<= 15 bits each) per refill
-    DCSB_HD uint32_t peek_wide() const { return (uint32_t)((((((uint64_t)w0) << 32) | w1) << s) >> 32); }
-    DCSB_HD void advance(uint32_t n) { s += n; }
-    // select-style on purpose: a compare + predicated block costs a 13-cycle predicate latency on
-    // the position chain; masks cost one ALU hop (the ring is always readable, so the load is
-    // unconditional)
-    DCSB_HD void refill()
+    DCSB_HD void refill()                // s < 64
     {
-        const uint32_t r = s >> 5;                  // 0 or 1
-        const uint32_t mask = 0u - r;
-        const uint32_t nw1 = DcsbBits::be(nx), ld = ring_word(wa);
-        s &= 31u;
-        w0 ^= (w0 ^ w1) & mask;
-        w1 ^= (w1 ^ nw1) & mask;
-        nx ^= (nx ^ ld) & mask;
-        wa += 4u * r;
+        if (s >= 32u) {
+            s -= 32u;
+            w0 = w1;
+            w1 = DcsbBits::be(ring_word(wa));
+            wa += 4u;
+        }
     }
-    DCSB_HD void skip(uint32_t n) { s += n; refill(); }      // n <= 32
-    // the same with the position kept as t = 50 - s (the Huffman loop's form)
-    DCSB_HD void refill_t(int &t)
-    {
-        const uint32_t mask = (uint32_t)((t - 19) >> 31);       // all ones when s >= 32
-        const uint32_t nw1 = DcsbBits::be(nx), ld = ring_word(wa);
-        t += (int)(32u & mask);
-        w0 ^= (w0 ^ w1) & mask;
-        w1 ^= (w1 ^ nw1) & mask;
-        nx ^= (nx ^ ld) & mask;
-        wa += 4u & mask;
-    }
+    DCSB_HD void skip(uint32_t n) { s += n; refill(); }      // s < 32 on entry, n <= 32
 };
 
-// Scan table in shared memory (DcsbTables::tx): the kernel hands over a 32-bit shared-window
-// address that is a multiple of 16 KB (one codebook's table), so that a lookup address is
-// table | byte offset -- one LOP3 -- and the load is one LDS.U16; the simulator passes a pointer.
-#if DCSB_DEVICE_PASS
-typedef uint32_t DcsbTxBase;
-// v: the window shifted so that bits 1..13 are the next 13 stream bits
-DCSB_HD uint32_t dcsb_tx_load(DcsbTxBase tb, uint32_t v)
-{
-    uint32_t a, r;
-    asm("lop3.b32 %0, %1, 0x3FFE, %2, 0xEA;" : "=r"(a) : "r"(v), "r"(tb));      // (v & 0x3FFE) | tb
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(a));
-    return r;
-}
-typedef uint32_t DcsbRingPtr;
-#else
-typedef const uint8_t *DcsbTxBase;
-DCSB_HD uint32_t dcsb_tx_load(DcsbTxBase tb, uint32_t v)
-{
-    uint16_t r;
-    memcpy(&r, tb + (v & 0x3FFEu), 2);
-    return r;
-}
-typedef uint8_t *DcsbRingPtr;
-#endif
-
-// Band descriptor: what the band loop needs to know about a band of the current frame.
-//   bit 31 Huffman band: bits 24..26 = codebook - 1, bits 0..17 = Rs = (16 * slots + 15) << 8 | 0xFF
-//   bit 30 fixed-width band: bits 16..25 = slots * width (bits to skip)
+// Band descriptor (compressed; 4 KB table per CTA): what a band of a frame is, by (stream type,
+// half-density flag of the band, band, band type): dtab[((type1 * 2 + half) * 16 + band) * 16 + type]
+//   bit 31 Huffman band: bits 24..26 = codebook - 1, bits 0..5 = slots
+//   bit 30 fixed-width band: bits 0..9 = slots * width (bits to skip)
 //   0      empty band
-// A descriptor depends on (stream type, half-density flag of the band, band, band type) only:
-// dtab[((type1 * 2 + half) * 16 + band) * 16 + type], 4 KB, built once per CTA.
 #define DCSB_DESC_HUFF  0x80000000u
 #define DCSB_DESC_FIXED 0x40000000u
 #define DCSB_DTAB_WORDS 1024
@@ -179,14 +182,25 @@ DCSB_HD uint32_t dcsb_band_desc94(const uint16_t *lut, int type1, int b, int nib
 {
     int code = nib;
     if (type1) code = (int)(lut[DCSB_LUT_XLAT + (b < 3 ? 0 : (b < 6 ? 16 : 32)) + code] >> 8);      // :1926-1955
-    if (code >= 1 && code <= 6) return DCSB_DESC_HUFF | ((uint32_t)(code - 1) << 24) | ((uint32_t)(count * 16 + 15) << 8) | 0xFFu;
-    if (code > 6 && count) return DCSB_DESC_FIXED | ((uint32_t)(count * code) << 16);
+    if (code >= 1 && code <= 6 && count) return DCSB_DESC_HUFF | ((uint32_t)(code - 1) << 24) | (uint32_t)count;
+    if (code > 6 && count) return DCSB_DESC_FIXED | (uint32_t)(count * code);
     return 0;
 }
 DCSB_HD uint32_t dcsb_dtab_entry(const uint16_t *lut, int i)
 {
     const int nib = i & 15, b = (i >> 4) & 15, half = (i >> 8) & 1, type1 = i >> 9;
     return dcsb_band_desc94(lut, type1, b, nib, dcsb_band_count94(b) >> half);
+}
+// expand a descriptor into the entry the band loop takes
+DCSB_HD DcsbBandEnt dcsb_band_entry(uint32_t d, DcsbTxBase tx, DcsbSA zero)
+{
+    DcsbBandEnt e;
+    const bool huff = (d & DCSB_DESC_HUFF) != 0;
+    e.tb = huff ? tx + (DcsbSA)(((d >> 24) & 7u) << 14) : zero;
+    e.sinit = huff ? ((d & 0x3Fu) << 12) | 0xF00u : 0xF00u;
+    e.amask = huff ? 0x3FFCu : 0u;
+    e.fix = (d & DCSB_DESC_FIXED) ? (int32_t)(d & 0x3FFu) : 0;
+    return e;
 }
 DCSB_HD int dcsb_nib32(uint32_t lo, uint32_t hi, int b) { return (int)(((b < 8 ? lo : hi) >> (4 * (b & 7))) & 15u); }
 DCSB_HD int dcsb_ctz(uint32_t v)
@@ -200,34 +214,121 @@ DCSB_HD int dcsb_ctz(uint32_t v)
 #endif
 }
 
-// Warp votes: on the device all 32 lanes of a warp walk one stream each in LOCK STEP (one
-// instruction stream serves 32 streams; loops run until every lane is through); the simulator
-// plays a warp of one lane, so a vote is the lane's own predicate.
+// Warp votes: the simulator plays a warp of one lane, so a vote is the lane's own predicate.
 #if DCSB_DEVICE_PASS
 #define DCSB_ANY(p) (__any_sync(0xffffffffu, (p)) != 0)
 #else
 #define DCSB_ANY(p) (p)
 #endif
 
+// The band loop of one frame (:2186-2234, lengths only).  ents = the lane's band entries, the list
+// ends with an entry whose fix is -1.  FIX: some lane of the warp has a fixed-width band in this frame.
+// Returns the OR of the slot budgets the bands ended with (negative: some band overran, :2213-2218).
+template <bool FIX>
+DCSB_HD int dcsb_scan94_bands(DcsbRingWin &win, DcsbSA ents, DcsbSA ents_end, DcsbSA zero, bool run)
+{
+    DcsbSA ptr = run ? ents : ents_end;
+    DcsbBandEnt en = dcsb_ent_load(ptr);                    // the entry to take next
+    ptr += DCSB_ENT_BYTES;
+    DcsbSA tb = zero;
+    uint32_t amask = 0;
+    int S = (int)(0xF00u | (50u - win.s));                  // no slots: the first iteration takes the first band
+    int fix = 0, err = 0;
+    uint32_t w0 = win.w0, w1 = win.w1, wa = win.wa;
+    for (;;) {
+        const bool alive = DCSB_ANY(fix >= 0);              // state of the previous iteration: resolves early
+        // -- one table step (a no-op for a lane without table: the zero word)
+        // (the ring word a refill would take is loaded first: its address does not hang on the chain)
+#if DCSB_DEVICE_PASS
+        const uint32_t ld = dcsb_lds32(dcsb_and_or(wa, DCSB_RING_BYTES - 1, win.ring));
+#else
+        const uint32_t ld = dcsb_lds32(win.ring + (wa & (DCSB_RING_BYTES - 1)));
+#endif
+        const int t = S & 0xFF;
+        const uint32_t v = (uint32_t)((((uint64_t)w0 << 32) | w1) >> t);
+#if DCSB_DEVICE_PASS
+        const uint32_t e = dcsb_lds32(dcsb_and_or(v, amask, tb));
+#else
+        const uint32_t e = dcsb_lds32(tb + (v & amask));
+#endif
+        // -- window refill, decided before the step: drop a word once the bit offset has reached 32
+        const bool rf = t < 19;
+        const int r32 = rf ? 32 : 0;
+        const int y8 = (int)(e & 0xFFFFu);
+        const int y = S >= y8 ? y8 : (int)(e >> 16);
+        S = S - y + r32;
+        w0 = rf ? w1 : w0;
+        w1 = rf ? DcsbBits::be(ld) : w1;
+        wa = rf ? wa + 4u : wa;
+        err |= S;                                           // (S is negative only right after a band overran)
+        // -- band switch: take the next band once this one has no slots left.  (The end entry has a
+        // slot and no table: the lane parks on it; the entry behind it is loaded but never taken.)
+        const bool done = S < 0x1000;
+        tb = done ? en.tb : tb;
+        amask = done ? en.amask : amask;
+        fix = done ? en.fix : fix;
+        S = done ? (int)dcsb_and_or((uint32_t)S, 0xFFu, en.sinit) : S;
+        if (done) en = dcsb_ent_load(ptr);
+        ptr = done ? ptr + DCSB_ENT_BYTES : ptr;
+        // -- closed-form skip of a fixed-width band: re-seek the window in the ring
+        if (FIX) {
+            if (fix > 0) {
+                const uint32_t a = (wa - 8u) * 8u + (uint32_t)(50 - (S & 0xFF)) + (uint32_t)fix;
+                const uint32_t off = (a >> 5) * 4u;
+                w0 = DcsbBits::be(win.ring_word(off));
+                w1 = DcsbBits::be(win.ring_word(off + 4u));
+                wa = off + 8u;
+                S = (int)(((uint32_t)S & ~0xFFu) | (50u - (a & 31u)));
+                fix = 0;
+            }
+        }
+        if (!alive) break;
+    }
+    win.w0 = w0;
+    win.w1 = w1;
+    win.wa = wa;
+    win.s = (uint32_t)(50 - (S & 0xFF));
+    win.refill();
+    return err;
+}
+
+// Rare path: which band of frame f overran its slot budget (the decode kernel zeroes that band's
+// contribution and the channel stops, :2213-2218)?  Walks the frame's bands one codeword at a time
+// on global memory.  pos = first band's bit position; returns the band index (99 if none).
+DCSB_HD int dcsb_find_stopband94(const DcsbBits &rd, uint32_t pos, const uint8_t *hdr, const uint16_t *lut, uint32_t bt_lo, uint32_t bt_hi)
+{
+    const int type1 = hdr[0] >> 7;
+    for (int b = 0; b < 16; ++b) {
+        const int hb = hdr[b] & 0x7F;
+        if (hb == 0x7F) break;
+        int count = dcsb_band_count94(b);
+        if (hb & 0x40) count >>= 1;
+        int code = dcsb_nib32(bt_lo, bt_hi, b);
+        if (type1) code = (int)(lut[DCSB_LUT_XLAT + (b < 3 ? 0 : (b < 6 ? 16 : 32)) + code] >> 8);
+        if (code == 0) continue;
+        if (code > 6) { pos += (uint32_t)(count * code); continue; }
+        const uint16_t *cb = lut + DCSB_LUT_CB + dcsb_cb_ofs(code);
+        const int mw = dcsb_cb_maxw(code);
+        int rem = count;
+        while (rem > 0) {
+            const uint32_t e = cb[rd.peek(pos, mw)];
+            pos += e >> 12;
+            const int st = (e & 0x800u) ? 2 : 1;
+            if (st > rem) return b;
+            rem -= st;
+        }
+    }
+    return 99;
+}
+
 // [f0, f1) = the frames this call walks (0, ~0u = the whole stream).  A call with f0 > 0 resumes
 // from the end checkpoint the previous call left at frame f0 (status DCSB_SCAN_RUNNING); that is
 // what lets dcsb_decode_streams cut a chunk into time slices whose PCM drains over PCIe while
 // the later slices are still being scanned.
-//
-// LOCK STEP.  Called by all lanes of a warp together, lane = stream (si < 0: idle lane).  The
-// lanes run ONE instruction stream: per frame a header loop (one run of "unchanged" codes plus
-// one code per iteration) and a band loop whose iteration is one table step for whichever
-// Huffman band the lane is in -- the switch to the next band is folded in by selects, a lane
-// that has finished its frame executes no-ops until the last lane is through.  What is rare and
-// long (a fixed-width band's closed-form skip needs the bit window re-seeked in the ring; header
-// codes longer than 8 bits) sits behind warp-uniform branches on votes taken one iteration
-// earlier, so the branch resolves at once and the lanes that do not need it pay nothing on their
-// dependent chain.  The window refill is decided from the position BEFORE the current step
-// (the 64-bit window has the room: s <= 44), which takes it off the chain position -> table
-// entry -> next position.  Streams are ordered by cost (dcsb_scan_order), so a warp holds alike
-// streams and waits little for its slowest lane.
+// Called by all lanes of a warp together, lane = stream (si < 0: idle lane).
+// ents: the lane's 18 band entries (16 bands, the end entry, one more that is only loaded); zero: address of a zero word in shared memory.
 DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *streams, int si, const DcsbTables *tab,
-                                const uint16_t *lut, DcsbTxBase tx, const uint32_t *dtab, DcsbRingPtr ring, uint32_t *desc,
+                                const uint16_t *lut, DcsbTxBase tx, const uint32_t *dtab, DcsbRingPtr ring, DcsbSA ents, DcsbSA zero,
                                 const DcsbScanOut &out, uint32_t f0 = 0, uint32_t f1 = 0xFFFFFFFFu)
 {
     bool mine = si >= 0;
@@ -254,7 +355,8 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
     // chunks worth reading: the stream, plus the bytes a frame that starts inside it may still
     // reach into the zero padding (the slab keeps >= 1 KB of slack behind the last stream)
     win.limit = s.nframes ? (uint32_t)(((start & 15) + dbytes + 64u + 15u) >> 4) : 0u;
-    win.wa = 12u;
+    win.wa = 8u;
+    win.s = 0;
     uint32_t pos = 0;
     uint32_t bt_lo = 0, bt_hi = 0;                 // band types, 16 x 4 bits; InitStreamPlayback zeroes them (:1640)
     if (mine && f0) {
@@ -263,12 +365,12 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
         bt_lo = b2.x;
         bt_hi = b2.y;
         const uint32_t off = ((pos + win.bias) >> 5) * 4u;
-        win.wa = off + 12u;
+        win.wa = off + 8u;
         win.fill = off >> 4;
     }
     win.topup();
     win.seek(pos);
-    // plain reader on global memory for the rare long header codes
+    // plain reader on global memory for the rare paths (long header codes, the band that overran)
     DcsbBits rd;
     rd.w = reinterpret_cast<const uint32_t *>(slab + (start & ~3ull));
     rd.bias = (uint32_t)(start & 3) * 8;
@@ -277,15 +379,21 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
     int status = s.nframes ? 0 : -1, stopband = 0xFF;    // -1 = DCSB_E_EMPTY (the host refines DCSB_E_SHORT)
     uint32_t nplay = s.nframes, f = f0;
     const uint32_t fe = f1 < s.nframes ? f1 : s.nframes;
-    // band descriptors of the current band types: only a band whose type changes in a frame header
-    // is looked up again, and the band loop walks the non-empty bands only
-    uint32_t live = 0;
+    // band entries of the current band types: only a band whose type changes in a frame header is
+    // expanded again.  fixmask: the bands that are fixed-width right now.
+    uint32_t fixmask = 0;
     for (int b = 0; b < nb; ++b) {
         const uint32_t d = dtab[dsel + ((halfmask >> b) & 1u) * 256u + (uint32_t)b * 16u + (uint32_t)dcsb_nib32(bt_lo, bt_hi, b)];
-        desc[b] = d;
-        live |= (d ? 1u : 0u) << b;
+        dcsb_ent_store(ents + (DcsbSA)b * DCSB_ENT_BYTES, dcsb_band_entry(d, tx, zero));
+        fixmask |= ((d >> 30) & 1u) << b;
     }
-    for (int b = nb; b <= 16; ++b) desc[b] = 0;
+    const DcsbSA ents_end = ents + (DcsbSA)nb * DCSB_ENT_BYTES;
+    {
+        DcsbBandEnt term;
+        term.tb = zero; term.sinit = 0x1F00u; term.amask = 0; term.fix = -1;       // one slot, no table: a lane parks here
+        dcsb_ent_store(ents_end, term);
+        dcsb_ent_store(ents_end + DCSB_ENT_BYTES, term);                            // (loaded behind the end entry, never taken)
+    }
     bool run = mine && f < fe;                     // this lane still walks frames
     while (DCSB_ANY(run)) {
         if (run) {
@@ -329,8 +437,8 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
                     const uint32_t nw = w + ((uint32_t)delta << sh);    // stays inside the nibble: 0 <= nbt <= 15
                     if (b < 8) bt_lo = nw; else bt_hi = nw;
                     const uint32_t d = dtab[dsel + ((halfmask >> b) & 1u) * 256u + (uint32_t)b * 16u + (uint32_t)nbt];
-                    desc[b] = d;
-                    live = (live & ~(1u << b)) | ((d ? 1u : 0u) << b);
+                    dcsb_ent_store(ents + (DcsbSA)b * DCSB_ENT_BYTES, dcsb_band_entry(d, tx, zero));
+                    fixmask = (fixmask & ~(1u << b)) | (((d >> 30) & 1u) << b);
                     hb = b + 1;
                 }
             } else if (on && !rc) hb = nb;                      // the run reached the last band
@@ -339,82 +447,14 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
         // (a code that reaches into the bytes behind the stream is a truncation, whatever those bytes are)
         if (run && rc) { status = hpos > nbits ? -2 : rc; nplay = f; run = false; }
         if (run) out.hdrbits[s.frame_base + f] = (uint16_t)(hpos - pos);
-        // ---- bands: lengths only.  One table step per iteration for whichever Huffman band the lane
-        // is in (:2186-2225).  A table entry is {m8, m1}: m8 = as many whole codewords as fit in the
-        // next 13 bits (at most 8 slots), m1 = the first codeword alone; each byte is slots << 4 | bits.
-        // Rs = (16 * slots left + 15) << 8 | 0xFF, so "the multi-symbol step covers more slots than are
-        // left" is one compare on the raw entry, and the single codeword is taken instead (a 'two
-        // zeros' codeword with one slot left leaves Rs < 0: the reference's error case, :2213-2218).
-        // t = 50 - s: the table index is the 64-bit window shifted right by t.
-        int sb = 99;
-        {
-            // dn / bn: descriptor and index of the next band to take; m: the bands behind it.  The
-            // descriptor behind dn is loaded every iteration (desc[16] = 0 ends the list), so that a
-            // band switch is a handful of selects on values that are already there.
-            uint32_t m = run ? live : 0u;
-            int bn = m ? dcsb_ctz(m) : 16;
-            m &= m - 1;
-            uint32_t dn = desc[bn];
-            int bcur = 16, Rs = 0;
-            DcsbTxBase tb = tx;
-            int t = 50 - (int)win.s;
-            uint32_t fix = 0;                                   // bits of a fixed-width band waiting for the re-seek
-            bool fin = dn == 0;                                 // nothing (left) to walk in this frame
-            for (;;) {
-                // votes on the state the previous iteration left, consumed at the END of this one: the
-                // branches resolve long before they are reached (one idle iteration per frame and per
-                // fixed-width band is the price)
-                const bool any_fix = DCSB_ANY(fix != 0);
-                const bool alive = DCSB_ANY(!fin);
-                const int bnn = m ? dcsb_ctz(m) : 16;
-                const uint32_t dnn = desc[bnn];
-                const DcsbTxBase tbn = tx + (((dn >> 24) & 7u) << 14);
-                const int Rsn = (int)dn < 0 ? (int)(dn & 0x3FFFFu) : 0;         // Huffman band: its slot budget
-                const uint32_t fixn = (int)dn < 0 ? 0u : (dn >> 16) & 0x3FFu;   // fixed-width band (:2227-2234): count * width bits
-                // -- one table step (a no-op once the band has no slots left)
-                const uint32_t v = (uint32_t)((((uint64_t)win.w0 << 32) | win.w1) >> t);
-                const uint32_t m16 = dcsb_tx_load(tb, v);
-                const uint32_t rmask = (uint32_t)((t - 19) >> 31);              // all ones when s >= 32: drop a word
-                {
-                    const uint32_t nw1 = DcsbBits::be(win.nx), ld = win.ring_word(win.wa);
-                    win.w0 ^= (win.w0 ^ win.w1) & rmask;
-                    win.w1 ^= (win.w1 ^ nw1) & rmask;
-                    win.nx ^= (win.nx ^ ld) & rmask;
-                    win.wa += 4u & rmask;
-                }
-                const uint32_t act = (uint32_t)((0x0FFF - Rs) >> 31);           // all ones while slots are left
-                const uint32_t b8 = (m16 >> 8) & act, b1 = m16 & 0xFFu & act;
-                const uint32_t mm = Rs >= (int)m16 ? b8 : b1;
-                t = t - (int)(mm & 15u) + (int)(32u & rmask);
-                Rs -= (int)((mm & 0xF0u) << 8);
-                sb = (Rs < 0 && sb > bcur) ? bcur : sb;                         // 'two zeros' with one slot left (:2213-2218)
-                // -- band switch: take the next band once this one has no slots left
-                const bool take = Rs <= 0x0FFF && fix == 0 && dn != 0;
-                tb = take ? tbn : tb;
-                Rs = take ? Rsn : Rs;
-                fix = take ? fixn : fix;
-                bcur = take ? bn : bcur;
-                bn = take ? bnn : bn;
-                dn = take ? dnn : dn;
-                m = take ? (m & (m - 1)) : m;
-                fin = Rs <= 0x0FFF && fix == 0 && dn == 0;
-                // -- closed-form skip of a fixed-width band: re-seek the window in the ring
-                if (any_fix) {
-                    if (fix) {
-                        win.s = (uint32_t)(50 - t);
-                        win.seek(win.pos() + fix);
-                        t = 50 - (int)win.s;
-                        fix = 0;
-                        fin = Rs <= 0x0FFF && dn == 0;
-                    }
-                }
-                if (!alive) break;
-            }
-            win.s = (uint32_t)(50 - t);
-            win.refill();
-        }
+        // ---- bands: lengths only
+        int err;
+        if (DCSB_ANY(run && fixmask != 0)) err = dcsb_scan94_bands<true>(win, ents, ents_end, zero, run);
+        else err = dcsb_scan94_bands<false>(win, ents, ents_end, zero, run);
         if (run) {
             pos = win.pos();
+            int sb = 99;
+            if (err < 0 && pos <= nbits) sb = dcsb_find_stopband94(rd, hpos, hdr, lut, bt_lo, bt_hi);
             if (pos > nbits) { status = -2; nplay = f; run = false; }                       // DCSB_E_TRUNCATED
             else if (sb != 99) { status = -5; nplay = f + 1; stopband = sb; ++f; run = false; }    // DCSB_E_STOPPED
             else {

@@ -35,8 +35,9 @@ static int sim_decode_streams(const dcsb_stream_desc *descs, size_t n, int16_t *
     std::vector<int32_t> status(n + 1);
     std::vector<uint8_t> stopband(n + 1);
     DcsbScanOut so{ bitpos.data(), bt.data(), hdrbits.data(), status.data(), nplay.data(), endbits.data(), stopband.data(), nullptr, nullptr, nullptr, nullptr, nullptr };
-    std::vector<uint8_t> ring(DCSB_RING_BYTES, 0xA5);                // one K1 thread's shared-memory ring
-    uint32_t desc[17];                                               // ... and its band descriptors
+    std::vector<uint8_t> ring(DCSB_RING_BYTES, 0xA5);                // one K1 lane's shared-memory ring
+    DcsbBandEnt ents[18];                                            // ... and its band entries
+    static const uint32_t zero_word[4] = { 0, 0, 0, 0 };
     static uint32_t dtab[DCSB_DTAB_WORDS];                           // the CTA's descriptor table
     for (int i = 0; i < DCSB_DTAB_WORDS; ++i) dtab[i] = dcsb_dtab_entry(tab.lut, i);
     std::vector<unsigned long long> csum(n + 1, 0);
@@ -49,7 +50,7 @@ static int sim_decode_streams(const dcsb_stream_desc *descs, size_t n, int16_t *
     for (uint32_t fa = 0; fa == 0 || fa < max_out; fa += slice_frames ? slice_frames : 0xFFFFFFFFu) {
         const uint32_t fb = slice_frames && fa + slice_frames < max_out ? fa + slice_frames : 0xFFFFFFFFu;
         for (size_t i = 0; i < n; ++i)                                   // K1 grid
-            if (p.recs[i].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, (const uint8_t *)tab.tx, dtab, ring.data(), desc, so, fa, fb);
+            if (p.recs[i].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, (DcsbSA)tab.tx, dtab, (DcsbSA)ring.data(), (DcsbSA)ents, (DcsbSA)zero_word, so, fa, fb);
             else dcsb_scan_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, so, fa, fb);
         std::vector<DcsbTile> t94, t93;
         if (slice_frames) dcsb_build_tiles(&p, fa, fb, &t94, &t93);
@@ -163,11 +164,12 @@ extern "C" int hostsim_rom_render(const uint8_t *const *imgs, const size_t *size
     std::vector<uint8_t> stopband(ns + 1);
     DcsbScanOut so{ bitpos.data(), bt.data(), hdrbits.data(), status.data(), nplay.data(), endbits.data(), stopband.data(), nullptr, nullptr, nullptr, nullptr, nullptr };
     std::vector<uint8_t> ring(DCSB_RING_BYTES, 0xA5);
-    uint32_t desc[17];
+    DcsbBandEnt ents[18];
+    static const uint32_t zero_word[4] = { 0, 0, 0, 0 };
     static uint32_t dtab[DCSB_DTAB_WORDS];
     for (int i = 0; i < DCSB_DTAB_WORDS; ++i) dtab[i] = dcsb_dtab_entry(tab.lut, i);
     for (size_t i = 0; i < ns; ++i) {
-        if (p.recs[i].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, (const uint8_t *)tab.tx, dtab, ring.data(), desc, so);
+        if (p.recs[i].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, (DcsbSA)tab.tx, dtab, (DcsbSA)ring.data(), (DcsbSA)ents, (DcsbSA)zero_word, so);
         else dcsb_scan_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, so);
         rom.streams[i].status = p.host_status[i] ? p.host_status[i] : status[i];
         rom.streams[i].nplay = p.host_status[i] ? 0 : nplay[i];
