@@ -128,17 +128,51 @@ int dcsb_batch_create_impl(dcsb_ctx *ctx, const dcsb_stream_desc *descs, size_t 
     b->slab_bytes = prep.slab_bytes;
     const uint64_t frames = prep.total_checkpoints;
 
-    // pack the compressed slab in pinned memory (multi-threaded), one H2D copy
+    // pack the compressed slab through pinned staging (multi-threaded) and upload it; a slab larger than the
+    // staging buffer goes piece by piece (whole streams per piece), two buffers so that packing overlaps the copy
     uint8_t *h_slab = nullptr;
-    cudaError_t e = cudaMallocHost(&h_slab, b->slab_bytes);
+    const size_t STAGE = (size_t)256 << 20;
+    const bool whole = in_place_base || b->slab_bytes <= STAGE;
+    const size_t stage_bytes = whole ? b->slab_bytes : STAGE;
+    cudaError_t e = cudaMallocHost(&h_slab, whole ? stage_bytes : 2 * stage_bytes);
     if (e != cudaSuccess) { delete b; return fail(ctx, DCSB_E_NOMEM, "cudaMallocHost(slab)", e); }
-    if (in_place_base) {
-        memcpy(h_slab, in_place_base, in_place_span);
-        memset(h_slab + in_place_span, 0, b->slab_bytes - in_place_span);
-    } else dcsb_pack_slab(descs, n, &prep, h_slab);
 #define CKB(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cudaFreeHost(h_slab); dcsb_batch_destroy(b); return fail(ctx, DCSB_E_CUDA, what, e_); } } while (0)
     CKB(cudaMalloc(&b->d_slab, b->slab_bytes), "cudaMalloc(slab)");
-    CKB(cudaMemcpy(b->d_slab, h_slab, b->slab_bytes, cudaMemcpyHostToDevice), "H2D slab");
+    if (whole) {
+        if (in_place_base) {
+            memcpy(h_slab, in_place_base, in_place_span);
+            memset(h_slab + in_place_span, 0, b->slab_bytes - in_place_span);
+        } else dcsb_pack_slab(descs, n, &prep, h_slab);
+        CKB(cudaMemcpy(b->d_slab, h_slab, b->slab_bytes, cudaMemcpyHostToDevice), "H2D slab");
+    } else {
+        cudaStream_t cs;
+        CKB(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking), "cudaStreamCreate");
+        cudaEvent_t done[2];
+        for (auto &ev : done) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        size_t i0 = 0;
+        int k = 0;
+        cudaError_t ce = cudaSuccess;
+        while (i0 < n && ce == cudaSuccess) {
+            const uint64_t base = prep.recs[i0].data_off;
+            size_t i1 = i0 + 1;
+            auto end_of = [&](size_t i) { return i < n ? prep.recs[i].data_off : (uint64_t)b->slab_bytes; };
+            while (i1 < n && end_of(i1 + 1) - base <= stage_bytes) ++i1;
+            if (end_of(i1) - base > stage_bytes) { ce = cudaErrorInvalidValue; break; }     // (one stream larger than the staging buffer: cannot happen, a stream is < 36 MB)
+            uint8_t *dst = h_slab + (size_t)(k & 1) * stage_bytes;
+            if (k >= 2) ce = cudaEventSynchronize(done[k & 1]);      // the copy that last used this buffer
+            if (ce != cudaSuccess) break;
+            dcsb_pack_slab_range(descs, n, &prep, i0, i1, dst);
+            ce = cudaMemcpyAsync(b->d_slab + base, dst, end_of(i1) - base, cudaMemcpyHostToDevice, cs);
+            if (ce == cudaSuccess) ce = cudaEventRecord(done[k & 1], cs);
+            i0 = i1;
+            ++k;
+        }
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(cs);
+        for (auto &ev : done) cudaEventDestroy(ev);
+        cudaStreamDestroy(cs);
+        if (n && prep.recs[0].data_off) cudaMemset(b->d_slab, 0, prep.recs[0].data_off);
+        CKB(ce, "H2D slab (staged)");
+    }
     cudaFreeHost(h_slab);
     h_slab = nullptr;
     CKB(cudaMalloc(&b->d_recs, std::max<size_t>(1, n) * sizeof(DcsbStreamRec)), "cudaMalloc(recs)");
@@ -178,6 +212,23 @@ extern "C" int dcsb_batch_launches(const dcsb_batch *b)
     if (!b) return 0;
     // scan (+ the one-thread gate when scan and decode overlap) + one decode launch per transform family
     return (b->n ? 1 : 0) + (b->n && b->ctx->overlap ? 1 : 0) + (b->ntiles94 ? 1 : 0) + (b->ntiles93 ? 1 : 0);
+}
+
+extern "C" int dcsb_batch_launch_shape(const dcsb_batch *b, int which, int *grid, int *block)
+{
+    if (!b || !grid || !block || which < 0 || which > 2) return DCSB_E_ARG;
+    if (which == 0) {
+        int warps, g;
+        dcsb_scan_shape((int)b->n, 0, &warps, &g);
+        *grid = b->n ? g : 0;
+        *block = warps * 32;
+        return DCSB_OK;
+    }
+    int gi, gq, blk;
+    dcsb_decode_shapes(which == 1 ? b->ntiles94 : b->nqueue94, &gi, &gq, &blk);
+    *grid = which == 1 ? gi : gq;
+    *block = blk;
+    return DCSB_OK;
 }
 
 extern "C" int dcsb_batch_decode(dcsb_batch *b, void *d_pcm, void *cuda_stream)

@@ -62,6 +62,24 @@ void dcsb_build_tables(DcsbTables *t)
     }
     for (int i = 0; i < NCODES(dcs94_hdr); ++i)
         if (dcs94_hdr[i].len > 8) t->long94[t->n_long94++] = DcsbLongCode{ dcs94_hdr[i].code, dcs94_hdr[i].len, dcs94_hdr[i].val, 0 };
+    {
+        // second level of the 1994 header LUT: every code longer than 8 bits starts with the one 8-bit
+        // pattern the first level has no entry for; codes of 9..16 bits are resolved by the 8 bits behind it
+        uint32_t prefix = 0xFFFFFFFFu;
+        for (int i = 0; i < NCODES(dcs94_hdr); ++i) {
+            const dcs_code_t &c = dcs94_hdr[i];
+            if (c.len <= 8) continue;
+            const uint32_t pre = c.code >> (c.len - 8);
+            if (prefix == 0xFFFFFFFFu) prefix = pre;
+            if (pre != prefix) abort();         // (a property of the format's table, checked once)
+            if (c.len > 16) continue;
+            const int rest = c.len - 8, rep = 1 << (8 - rest);
+            const uint32_t base = (c.code & ((1u << rest) - 1u)) << (8 - rest);
+            for (int r = 0; r < rep; ++r) t->lut[DCSB_LUT_HDR94B + base + r] = (uint16_t)((c.len << 8) | c.val);
+        }
+        for (int x = 0; x < 256; ++x)
+            if ((uint32_t)x != prefix && t->lut[DCSB_LUT_HDR94 + x] == 0) abort();
+    }
     for (int i = 0; i < NCODES(dcs93_hdr); ++i)
         if (dcs93_hdr[i].len > 8) t->long93[t->n_long93++] = DcsbLongCode{ dcs93_hdr[i].code, dcs93_hdr[i].len, dcs93_hdr[i].val, 0 };
     memcpy(t->overlap, dcs_overlap_win, sizeof(t->overlap));
@@ -362,22 +380,29 @@ int dcsb_prepare(const dcsb_stream_desc *descs, size_t n, DcsbPrepared *p, const
     return DCSB_OK;
 }
 
-void dcsb_pack_slab(const dcsb_stream_desc *descs, size_t n, const DcsbPrepared *p, uint8_t *slab)
+void dcsb_pack_slab_range(const dcsb_stream_desc *descs, size_t n, const DcsbPrepared *p, size_t i0, size_t i1, uint8_t *dst)
 {
+    if (i0 >= i1) return;
+    const uint64_t base = p->recs[i0].data_off;
     const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     auto work = [&](unsigned t) {
-        for (size_t i = t; i < n; i += nt) {
+        for (size_t i = i0 + t; i < i1; i += nt) {
             const DcsbStreamRec &r = p->recs[i];
             const uint64_t span = (i + 1 < n ? p->recs[i + 1].data_off : (uint64_t)p->slab_bytes) - r.data_off;
-            if (descs[i].data && descs[i].nbytes) memcpy(slab + r.data_off, descs[i].data, descs[i].nbytes);
-            memset(slab + r.data_off + descs[i].nbytes, 0, span - descs[i].nbytes);
+            if (descs[i].data && descs[i].nbytes) memcpy(dst + (r.data_off - base), descs[i].data, descs[i].nbytes);
+            memset(dst + (r.data_off - base) + descs[i].nbytes, 0, span - descs[i].nbytes);
         }
     };
-    if (n < 64 || nt == 1) { for (unsigned t = 0; t < nt; ++t) work(t); return; }
+    if (i1 - i0 < 64 || nt == 1) { for (unsigned t = 0; t < nt; ++t) work(t); return; }
     std::vector<std::thread> th;
     for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
     work(0);
     for (auto &x : th) x.join();
+}
+
+void dcsb_pack_slab(const dcsb_stream_desc *descs, size_t n, const DcsbPrepared *p, uint8_t *slab)
+{
+    if (n) dcsb_pack_slab_range(descs, n, p, 0, n, slab + p->recs[0].data_off);
 }
 
 // ======================================================================================

@@ -41,7 +41,8 @@ struct DcsbTile { uint32_t stream; uint32_t first; uint32_t count; };
 #define DCSB_LUT_BB93A   1452   // 64:  OS93a band-bits codes, 4 groups x 4-bit peek
 #define DCSB_LUT_SC93A   1516   // 256: OS93a scale-delta code, 8-bit peek
 #define DCSB_LUT_XLAT    1772   // 48:  1994 type-1 band translation, 3 groups x 16: (codebook/width << 8) | scale adjust
-#define DCSB_LUT_WORDS   1820
+#define DCSB_LUT_HDR94B 1820   // 256: 1994 frame-header delta codes of 9..16 bits, by the 8 bits behind their common 8-bit prefix
+#define DCSB_LUT_WORDS   2076
 
 // scan: length table of the 1994 sample codebooks (dcsb_scan94.cuh); entry = y1 << 16 | y8, each slots << 12 | bits
 #define DCSB_T8_PEEK 12
@@ -137,6 +138,9 @@ void dcsb_scan_shape(int nstreams, int concurrent, int *warps, int *grid);
 void dcsb_scan_order(DcsbPrepared *p);
 // copy the streams into `slab` (p->slab_bytes bytes) at their 16-byte aligned offsets, zero padded
 void dcsb_pack_slab(const dcsb_stream_desc *descs, size_t n, const DcsbPrepared *p, uint8_t *slab);
+// the same for streams [i0, i1) only: `dst` stands for slab offset recs[i0].data_off; fills up to the offset of
+// stream i1 (or the slab's end)
+void dcsb_pack_slab_range(const dcsb_stream_desc *descs, size_t n, const DcsbPrepared *p, size_t i0, size_t i1, uint8_t *dst);
 
 // concurrent: streams of all the scans launched side by side (0 = this launch alone), see dcsb_scan_shape
 // order: device array of nstreams stream indices (NULL = identity): which stream each scan lane takes
@@ -148,6 +152,7 @@ cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, 
 // enqueue a one-thread kernel that returns once `ctas` scan CTAs are resident (scan.started)
 cudaError_t dcsb_launch_gate(DcsbScanOut scan, int ctas, cudaStream_t st);
 int dcsb_scan_grid(int nstreams, int concurrent);   // CTAs dcsb_launch_scan uses
+void dcsb_decode_shapes(int nitems, int *grid_items, int *grid_queue, int *block);   // 1994-layout decode kernels: CTAs for nitems work items / of the persistent kernel
 // persistent decode over the scan's ready queue (1994-layout streams, overlapped mode)
 cudaError_t dcsb_launch_decode_queue(const uint8_t *slab, const DcsbStreamRec *streams, int nstreams, int nitems,
                                      const DcsbTables *tables, DcsbScanOut scan, int16_t *pcm,

@@ -45,7 +45,7 @@ __device__ __forceinline__ void dcsb_load_lut(uint16_t *s_lut, const DcsbTables 
 // word go into the alignment gap in front of the table or behind everything, whichever is large enough.
 #define DCSB_TX_BYTES (6 * DCSB_T8_CB * 4)
 #define DCSB_SCAN_LUT_BYTES ((DCSB_LUT_WORDS * 2 + 15) & ~15)
-#define DCSB_SCAN_SMALL (DCSB_SCAN_LUT_BYTES + DCSB_DTAB_WORDS * 4 + 16)
+#define DCSB_SCAN_SMALL (DCSB_SCAN_LUT_BYTES + DCSB_DTAB_WORDS * 2 + 16)
 #define DCSB_SCAN_ENT_STRIDE (19u * 16u)        // 18 entries + 16 bytes: lanes start 12 banks apart, LDS.128 conflict-free
 #define DCSB_SCAN_WARP_BYTES (32u * DCSB_RING_BYTES + 32u * DCSB_SCAN_ENT_STRIDE)
 #define DCSB_SCAN_SMEM(warps) (16384u + DCSB_TX_BYTES + (warps) * DCSB_SCAN_WARP_BYTES)
@@ -66,8 +66,8 @@ dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restri
     const uint32_t ents_off = rings_off + (uint32_t)warps * 32u * DCSB_RING_BYTES;
     const uint32_t small_off = tx_off >= DCSB_SCAN_SMALL ? 0u : ents_off + (uint32_t)warps * 32u * DCSB_SCAN_ENT_STRIDE;
     uint16_t *s_lut = reinterpret_cast<uint16_t *>(sm8 + small_off);
-    uint32_t *s_dtab = reinterpret_cast<uint32_t *>(sm8 + small_off + DCSB_SCAN_LUT_BYTES);
-    const uint32_t zero_off = small_off + DCSB_SCAN_LUT_BYTES + DCSB_DTAB_WORDS * 4;
+    uint16_t *s_dtab = reinterpret_cast<uint16_t *>(sm8 + small_off + DCSB_SCAN_LUT_BYTES);
+    const uint32_t zero_off = small_off + DCSB_SCAN_LUT_BYTES + DCSB_DTAB_WORDS * 2;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(tab->tx);
         uint4 *dst = reinterpret_cast<uint4 *>(sm8 + tx_off);
@@ -78,7 +78,7 @@ dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restri
         if (out.started) atomicAdd(out.started, 1u);       // this CTA is resident (dcsb_gate_kernel)
     }
     dcsb_load_lut(s_lut, tab);
-    for (int i = threadIdx.x; i < DCSB_DTAB_WORDS; i += blockDim.x) s_dtab[i] = dcsb_dtab_entry(s_lut, i);
+    for (int i = threadIdx.x; i < DCSB_DTAB_WORDS; i += blockDim.x) s_dtab[i] = (uint16_t)dcsb_dtab_entry(s_lut, i);
     __syncthreads();
     const uint32_t ring_off = rings_off + ((uint32_t)warp * 32u + (uint32_t)lane) * DCSB_RING_BYTES;
     const uint32_t ent_off = ents_off + ((uint32_t)warp * 32u + (uint32_t)lane) * DCSB_SCAN_ENT_STRIDE;
@@ -251,6 +251,25 @@ dcsb_decode94_queue_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec
     }
 }
 
+static int decode_queue_grid(int nitems)
+{
+    int grid = (nitems + DCSB_WARPS94 - 1) / DCSB_WARPS94;
+    // persistent CTAs per SM: as many as fit (three of 70 KB; beside a resident scan CTA of 150 KB the
+    // SM takes one, the others follow when the scan CTA has left)
+    const int sms = dcsb_num_sms();
+    int per_sm = 3;
+    if (const char *e = getenv("DCSB_DECODE_CTAS")) { const int v = atoi(e); if (v >= 1 && v <= 3) per_sm = v; }   // tuning override
+    if (grid > sms * per_sm) grid = sms * per_sm;
+    return grid;
+}
+
+void dcsb_decode_shapes(int nitems, int *grid_items, int *grid_queue, int *block)
+{
+    *grid_items = (nitems + DCSB_WARPS94 - 1) / DCSB_WARPS94;
+    *grid_queue = nitems > 0 ? decode_queue_grid(nitems) : 0;
+    *block = DCSB_WARPS94 * 32;
+}
+
 cudaError_t dcsb_launch_decode_queue(const uint8_t *slab, const DcsbStreamRec *streams, int nstreams, int nitems,
                                      const DcsbTables *tables, DcsbScanOut scan, int16_t *pcm,
                                      unsigned long long *checksums, cudaStream_t st)
@@ -263,14 +282,8 @@ cudaError_t dcsb_launch_decode_queue(const uint8_t *slab, const DcsbStreamRec *s
     // this one (the split only changes on an idle SM)
     e = cudaFuncSetAttribute(dcsb_decode94_queue_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    int grid = (nitems + DCSB_WARPS94 - 1) / DCSB_WARPS94;
-    // persistent CTAs per SM: as many as fit (three of 70 KB; beside a resident scan CTA of 150 KB the
-    // SM takes one, the others follow when the scan CTA has left)
-    const int sms = dcsb_num_sms();
-    int per_sm = 3;
-    if (const char *e = getenv("DCSB_DECODE_CTAS")) { const int v = atoi(e); if (v >= 1 && v <= 3) per_sm = v; }   // tuning override
     (void)nstreams;
-    if (grid > sms * per_sm) grid = sms * per_sm;
+    const int grid = decode_queue_grid(nitems);
     dcsb_decode94_queue_kernel<<<grid, DCSB_WARPS94 * 32, smem, st>>>(slab, streams, nitems, tables, scan, pcm, checksums);
     return cudaGetLastError();
 }

@@ -74,7 +74,7 @@ DCSB_HD uint32_t dcsb_and_or(uint32_t a, uint32_t b, uint32_t c)
 // One band of a lane's current frame, as the band loop takes it.
 struct DcsbBandEnt {
     DcsbSA tb;          // length table of the band's codebook (16 KB aligned), or the zero word
-    uint32_t sinit;     // slots << 12 | 0xF00
+    int32_t nslots;     // -(slots << 12): the switch is S = dm * nslots + S (dm = -1 when the band is done, else 0)
     uint32_t amask;     // 0x3FFC (table index bits) or 0 (no table: the lookup reads the zero word)
     int32_t fix;        // > 0: fixed-width band, bits to skip; -1: end of the frame's list; else 0
 };
@@ -87,7 +87,7 @@ DCSB_HD DcsbBandEnt dcsb_ent_load(DcsbSA a)
 {
     DcsbBandEnt e;
 #if DCSB_DEVICE_PASS
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e.tb), "=r"(e.sinit), "=r"(e.amask), "=r"(e.fix) : "r"(a));
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e.tb), "=r"(e.nslots), "=r"(e.amask), "=r"(e.fix) : "r"(a));
 #else
     memcpy(&e, reinterpret_cast<const void *>(a), sizeof(e));
 #endif
@@ -96,7 +96,7 @@ DCSB_HD DcsbBandEnt dcsb_ent_load(DcsbSA a)
 DCSB_HD void dcsb_ent_store(DcsbSA a, const DcsbBandEnt &e)
 {
 #if DCSB_DEVICE_PASS
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(e.tb), "r"(e.sinit), "r"(e.amask), "r"(e.fix) : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(e.tb), "r"(e.nslots), "r"(e.amask), "r"(e.fix) : "memory");
 #else
     memcpy(reinterpret_cast<void *>(a), &e, sizeof(e));
 #endif
@@ -172,17 +172,17 @@ struct DcsbRingWin {
 
 // Band descriptor (compressed; 4 KB table per CTA): what a band of a frame is, by (stream type,
 // half-density flag of the band, band, band type): dtab[((type1 * 2 + half) * 16 + band) * 16 + type]
-//   bit 31 Huffman band: bits 24..26 = codebook - 1, bits 0..5 = slots
-//   bit 30 fixed-width band: bits 0..9 = slots * width (bits to skip)
+//   bit 15 Huffman band: bits 10..12 = codebook - 1, bits 0..5 = slots
+//   bit 14 fixed-width band: bits 0..9 = slots * width (bits to skip)
 //   0      empty band
-#define DCSB_DESC_HUFF  0x80000000u
-#define DCSB_DESC_FIXED 0x40000000u
+#define DCSB_DESC_HUFF  0x8000u
+#define DCSB_DESC_FIXED 0x4000u
 #define DCSB_DTAB_WORDS 1024
 DCSB_HD uint32_t dcsb_band_desc94(const uint16_t *lut, int type1, int b, int nib, int count)
 {
     int code = nib;
     if (type1) code = (int)(lut[DCSB_LUT_XLAT + (b < 3 ? 0 : (b < 6 ? 16 : 32)) + code] >> 8);      // :1926-1955
-    if (code >= 1 && code <= 6 && count) return DCSB_DESC_HUFF | ((uint32_t)(code - 1) << 24) | (uint32_t)count;
+    if (code >= 1 && code <= 6 && count) return DCSB_DESC_HUFF | ((uint32_t)(code - 1) << 10) | (uint32_t)count;
     if (code > 6 && count) return DCSB_DESC_FIXED | (uint32_t)(count * code);
     return 0;
 }
@@ -196,10 +196,11 @@ DCSB_HD DcsbBandEnt dcsb_band_entry(uint32_t d, DcsbTxBase tx, DcsbSA zero)
 {
     DcsbBandEnt e;
     const bool huff = (d & DCSB_DESC_HUFF) != 0;
-    e.tb = huff ? tx + (DcsbSA)(((d >> 24) & 7u) << 14) : zero;
-    e.sinit = huff ? ((d & 0x3Fu) << 12) | 0xF00u : 0xF00u;
+    e.tb = huff ? tx + (DcsbSA)(((d >> 10) & 7u) << 14) : zero;
+    const bool fixed = (d & DCSB_DESC_FIXED) != 0;
+    e.nslots = -(int32_t)((huff ? (d & 0x3Fu) : (fixed ? 1u : 0u)) << 12);          // a fixed-width band parks the lane (one slot, no table) until the re-seek
     e.amask = huff ? 0x3FFCu : 0u;
-    e.fix = (d & DCSB_DESC_FIXED) ? (int32_t)(d & 0x3FFu) : 0;
+    e.fix = fixed ? (int32_t)(d & 0x3FFu) : 0;
     return e;
 }
 DCSB_HD int dcsb_nib32(uint32_t lo, uint32_t hi, int b) { return (int)(((b < 8 ? lo : hi) >> (4 * (b & 7))) & 15u); }
@@ -217,68 +218,130 @@ DCSB_HD int dcsb_ctz(uint32_t v)
 // Warp votes: the simulator plays a warp of one lane, so a vote is the lane's own predicate.
 #if DCSB_DEVICE_PASS
 #define DCSB_ANY(p) (__any_sync(0xffffffffu, (p)) != 0)
+#define DCSB_REDUCE_OR(x) __reduce_or_sync(0xffffffffu, (x))
 #else
 #define DCSB_ANY(p) (p)
+#define DCSB_REDUCE_OR(x) (x)
 #endif
+
+// an unconditional 16-bit table load (the compiler would otherwise predicate the second of two
+// dependent-looking loads on the first one's result and serialise them)
+DCSB_HD uint32_t dcsb_lut_load(const uint16_t *lut, uint32_t i)
+{
+#if DCSB_DEVICE_PASS
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(lut + i)));
+    return v;
+#else
+    return lut[i];
+#endif
+}
+
+// Small device/host helpers for the predicate-free inner loop
+DCSB_HD uint32_t dcsb_lds16(DcsbSA a)
+{
+#if DCSB_DEVICE_PASS
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+#else
+    uint16_t v;
+    memcpy(&v, reinterpret_cast<const void *>(a), 2);
+    return v;
+#endif
+}
+DCSB_HD int dcsb_umin(int a, int b) { return (uint32_t)a < (uint32_t)b ? a : b; }
+// m ? a : b for an all-ones / all-zeros mask m, one LOP3
+DCSB_HD uint32_t dcsb_msel(uint32_t m, uint32_t a, uint32_t b)
+{
+#if DCSB_DEVICE_PASS
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xAC;" : "=r"(r) : "r"(m), "r"(b), "r"(a));       // F(m=0xF0, b=0xCC, a=0xAA) = (m & a) | (~m & b)
+    return r;
+#else
+    return (m & a) | (~m & b);
+#endif
+}
 
 // The band loop of one frame (:2186-2234, lengths only).  ents = the lane's band entries, the list
 // ends with an entry whose fix is -1.  FIX: some lane of the warp has a fixed-width band in this frame.
-// Returns the OR of the slot budgets the bands ended with (negative: some band overran, :2213-2218).
+// Returns the OR of the lane states the steps left (negative: some band overran its slot budget,
+// :2213-2218 -- the caller then walks the frame again the slow way, whatever this loop made of it).
+//
+// One iteration, free of predicates on the dependent chain:
+//   e8 / e1   the two halves of the table entry, loaded as two LDS.U16 (no unpacking)
+//   S         = min_unsigned(S - e8, S - e1): the multi-codeword step when it fits the slot budget,
+//             else the single codeword (S - e8 is negative = huge exactly when it does not fit)
+//   dm        all ones when the band has no slots left: the switch to the next entry (reloaded
+//             every iteration from ptr, which only then advances) is four mask selects
+//   t         for the next lookup comes from S BEFORE the switch (the switch keeps the low byte)
+// Four iterations per exit vote and fixed-band check (eight measured the same: fewer votes, more idle iterations at the frame end): a lane that is through parks on its end entry.
+#define DCSB_SCAN_UNROLL 4
 template <bool FIX>
 DCSB_HD int dcsb_scan94_bands(DcsbRingWin &win, DcsbSA ents, DcsbSA ents_end, DcsbSA zero, bool run)
 {
     DcsbSA ptr = run ? ents : ents_end;
-    DcsbBandEnt en = dcsb_ent_load(ptr);                    // the entry to take next
-    ptr += DCSB_ENT_BYTES;
     DcsbSA tb = zero;
     uint32_t amask = 0;
-    int S = (int)(0xF00u | (50u - win.s));                  // no slots: the first iteration takes the first band
+    int t = 50 - (int)win.s;
+    int S = 0xF00 | t;                                      // no slots: the first iteration takes the first band
     int fix = 0, err = 0;
+    (void)fix;
     uint32_t w0 = win.w0, w1 = win.w1, wa = win.wa;
     for (;;) {
-        const bool alive = DCSB_ANY(fix >= 0);              // state of the previous iteration: resolves early
-        // -- one table step (a no-op for a lane without table: the zero word)
-        // (the ring word a refill would take is loaded first: its address does not hang on the chain)
+        // (state the previous group left: resolves early.  A lane is through once it has taken its end entry)
+        const bool alive = DCSB_ANY(FIX ? fix >= 0 : ptr <= ents_end);
+#pragma unroll
+        for (int u = 0; u < DCSB_SCAN_UNROLL; ++u) {
+            // (the ring word a refill would take and the next band entry: addresses off the chain)
 #if DCSB_DEVICE_PASS
-        const uint32_t ld = dcsb_lds32(dcsb_and_or(wa, DCSB_RING_BYTES - 1, win.ring));
+            const uint32_t ld = dcsb_lds32(dcsb_and_or(wa, DCSB_RING_BYTES - 1, win.ring));
 #else
-        const uint32_t ld = dcsb_lds32(win.ring + (wa & (DCSB_RING_BYTES - 1)));
+            const uint32_t ld = dcsb_lds32(win.ring + (wa & (DCSB_RING_BYTES - 1)));
 #endif
-        const int t = S & 0xFF;
-        const uint32_t v = (uint32_t)((((uint64_t)w0 << 32) | w1) >> t);
+            const DcsbBandEnt en = dcsb_ent_load(ptr);
+            // -- one table step (a no-op for a lane without table: the zero word)
 #if DCSB_DEVICE_PASS
-        const uint32_t e = dcsb_lds32(dcsb_and_or(v, amask, tb));
+            const uint32_t v = (uint32_t)((((uint64_t)w0 << 32) | w1) >> t);
+            const DcsbSA ea = dcsb_and_or(v, amask, tb);
 #else
-        const uint32_t e = dcsb_lds32(tb + (v & amask));
+            const uint32_t v = (uint32_t)((((uint64_t)w0 << 32) | w1) >> (t & 63));     // (t < 64 unless the frame is damaged)
+            const DcsbSA ea = tb + (v & amask);
 #endif
-        // -- window refill, decided before the step: drop a word once the bit offset has reached 32
-        const bool rf = t < 19;
-        const int r32 = rf ? 32 : 0;
-        const int y8 = (int)(e & 0xFFFFu);
-        const int y = S >= y8 ? y8 : (int)(e >> 16);
-        S = S - y + r32;
-        w0 = rf ? w1 : w0;
-        w1 = rf ? DcsbBits::be(ld) : w1;
-        wa = rf ? wa + 4u : wa;
-        err |= S;                                           // (S is negative only right after a band overran)
-        // -- band switch: take the next band once this one has no slots left.  (The end entry has a
-        // slot and no table: the lane parks on it; the entry behind it is loaded but never taken.)
-        const bool done = S < 0x1000;
-        tb = done ? en.tb : tb;
-        amask = done ? en.amask : amask;
-        fix = done ? en.fix : fix;
-        S = done ? (int)dcsb_and_or((uint32_t)S, 0xFFu, en.sinit) : S;
-        if (done) en = dcsb_ent_load(ptr);
-        ptr = done ? ptr + DCSB_ENT_BYTES : ptr;
-        // -- closed-form skip of a fixed-width band: re-seek the window in the ring
+            const int e8 = (int)dcsb_lds16(ea), e1 = (int)dcsb_lds16(ea + 2);
+            // -- window refill, decided before the step: drop a word once the bit offset has reached 32
+            const bool rf = t < 19;
+            const int Sr = S + (rf ? 32 : 0);
+            w0 = rf ? w1 : w0;
+            w1 = rf ? DcsbBits::be(ld) : w1;
+            wa = rf ? wa + 4u : wa;
+            S = dcsb_umin(Sr - e8, Sr - e1);
+            err |= S;
+            t = S & 0xFF;
+            // -- band switch: take the next band once this one has no slots left (then the slot field
+            // of S is zero, so the new budget is added: one multiply-add).  (The end entry and a
+            // fixed-width band's entry have a slot and no table: the lane parks on them.)
+            const int dm = (S - 0x1000) >> 31;
+            S = dm * en.nslots + S;
+#if DCSB_DEVICE_PASS
+            tb = dcsb_msel((uint32_t)dm, en.tb, tb);
+#else
+            tb = dm ? en.tb : tb;
+#endif
+            amask = dcsb_msel((uint32_t)dm, en.amask, amask);
+            if (FIX) fix = (int)dcsb_msel((uint32_t)dm, (uint32_t)en.fix, (uint32_t)fix);
+            ptr = ptr - (DcsbSA)dm * (DcsbSA)DCSB_ENT_BYTES;        // dm = -1: the next entry
+        }
+        // -- closed-form skip of a fixed-width band: re-seek the window in the ring, then take the next band
         if (FIX) {
             if (fix > 0) {
-                const uint32_t a = (wa - 8u) * 8u + (uint32_t)(50 - (S & 0xFF)) + (uint32_t)fix;
+                const uint32_t a = (wa - 8u) * 8u + (uint32_t)(50 - t) + (uint32_t)fix;
                 const uint32_t off = (a >> 5) * 4u;
                 w0 = DcsbBits::be(win.ring_word(off));
                 w1 = DcsbBits::be(win.ring_word(off + 4u));
                 wa = off + 8u;
-                S = (int)(((uint32_t)S & ~0xFFu) | (50u - (a & 31u)));
+                t = 50 - (int)(a & 31u);
+                S = 0xF00 | t;
                 fix = 0;
             }
         }
@@ -287,17 +350,20 @@ DCSB_HD int dcsb_scan94_bands(DcsbRingWin &win, DcsbSA ents, DcsbSA ents_end, Dc
     win.w0 = w0;
     win.w1 = w1;
     win.wa = wa;
-    win.s = (uint32_t)(50 - (S & 0xFF));
+    win.s = (uint32_t)(50 - t);
     win.refill();
     return err;
 }
 
-// Rare path: which band of frame f overran its slot budget (the decode kernel zeroes that band's
-// contribution and the channel stops, :2213-2218)?  Walks the frame's bands one codeword at a time
-// on global memory.  pos = first band's bit position; returns the band index (99 if none).
-DCSB_HD int dcsb_find_stopband94(const DcsbBits &rd, uint32_t pos, const uint8_t *hdr, const uint16_t *lut, uint32_t bt_lo, uint32_t bt_hi)
+// Rare path: a band of frame f overran its slot budget (a 'two zeros' codeword with one slot left:
+// the decode kernel zeroes that band's contribution and the channel stops, :2213-2218).  Walks the
+// frame's bands one codeword at a time on global memory, the way the reference does: the overrunning
+// codeword is consumed, the band ends, the walk goes on.  pos = first band's bit position on entry,
+// the frame's end on return; returns the first such band (99 if none).
+DCSB_HD int dcsb_find_stopband94(const DcsbBits &rd, uint32_t &pos, const uint8_t *hdr, const uint16_t *lut, uint32_t bt_lo, uint32_t bt_hi)
 {
     const int type1 = hdr[0] >> 7;
+    int sb = 99;
     for (int b = 0; b < 16; ++b) {
         const int hb = hdr[b] & 0x7F;
         if (hb == 0x7F) break;
@@ -314,11 +380,31 @@ DCSB_HD int dcsb_find_stopband94(const DcsbBits &rd, uint32_t pos, const uint8_t
             const uint32_t e = cb[rd.peek(pos, mw)];
             pos += e >> 12;
             const int st = (e & 0x800u) ? 2 : 1;
-            if (st > rem) return b;
+            if (st > rem && sb > b) sb = b;
             rem -= st;
         }
     }
-    return 99;
+    return sb;
+}
+
+// One frame-header code: band b's type moves by delta (:1822-1834); the band's entry is expanded
+// again.  next = the band the header walk carries on with (nb after an error: rc is set).
+DCSB_HD void dcsb_hdr_apply94(int b, int delta, int nb, uint32_t dsel, uint32_t halfmask, const uint16_t *dtab, DcsbTxBase tx, DcsbSA zero,
+                              DcsbSA ents, uint32_t &bt_lo, uint32_t &bt_hi, uint32_t &fixmask, int &rc, int &next)
+{
+    const uint32_t sh = (uint32_t)(b & 7) * 4u;
+    const bool hi = b >= 8;
+    const uint32_t w = hi ? bt_hi : bt_lo;
+    const int nbt = (int)((w >> sh) & 15u) + delta;
+    const bool bad = (nbt & ~15) != 0;
+    const uint32_t nw = w + ((uint32_t)delta << sh);            // stays inside the nibble when 0 <= nbt <= 15
+    bt_lo = (!bad && !hi) ? nw : bt_lo;
+    bt_hi = (!bad && hi) ? nw : bt_hi;
+    const uint32_t d = dtab[dsel + ((halfmask >> b) & 1u) * 256u + (uint32_t)b * 16u + (uint32_t)(nbt & 15)];
+    if (!bad) dcsb_ent_store(ents + (DcsbSA)b * DCSB_ENT_BYTES, dcsb_band_entry(d, tx, zero));
+    fixmask = bad ? fixmask : ((fixmask & ~(1u << b)) | (((d >> 14) & 1u) << b));
+    rc = bad ? DCSB_WALK_BANDTYPE : rc;
+    next = bad ? nb : b + 1;
 }
 
 // [f0, f1) = the frames this call walks (0, ~0u = the whole stream).  A call with f0 > 0 resumes
@@ -328,7 +414,7 @@ DCSB_HD int dcsb_find_stopband94(const DcsbBits &rd, uint32_t pos, const uint8_t
 // Called by all lanes of a warp together, lane = stream (si < 0: idle lane).
 // ents: the lane's 18 band entries (16 bands, the end entry, one more that is only loaded); zero: address of a zero word in shared memory.
 DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *streams, int si, const DcsbTables *tab,
-                                const uint16_t *lut, DcsbTxBase tx, const uint32_t *dtab, DcsbRingPtr ring, DcsbSA ents, DcsbSA zero,
+                                const uint16_t *lut, DcsbTxBase tx, const uint16_t *dtab, DcsbRingPtr ring, DcsbSA ents, DcsbSA zero,
                                 const DcsbScanOut &out, uint32_t f0 = 0, uint32_t f1 = 0xFFFFFFFFu)
 {
     bool mine = si >= 0;
@@ -385,12 +471,12 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
     for (int b = 0; b < nb; ++b) {
         const uint32_t d = dtab[dsel + ((halfmask >> b) & 1u) * 256u + (uint32_t)b * 16u + (uint32_t)dcsb_nib32(bt_lo, bt_hi, b)];
         dcsb_ent_store(ents + (DcsbSA)b * DCSB_ENT_BYTES, dcsb_band_entry(d, tx, zero));
-        fixmask |= ((d >> 30) & 1u) << b;
+        fixmask |= ((d >> 14) & 1u) << b;
     }
     const DcsbSA ents_end = ents + (DcsbSA)nb * DCSB_ENT_BYTES;
     {
         DcsbBandEnt term;
-        term.tb = zero; term.sinit = 0x1F00u; term.amask = 0; term.fix = -1;       // one slot, no table: a lane parks here
+        term.tb = zero; term.nslots = -0x1000; term.amask = 0; term.fix = -1;       // one slot, no table: a lane parks here
         dcsb_ent_store(ents_end, term);
         dcsb_ent_store(ents_end + DCSB_ENT_BYTES, term);                            // (loaded behind the end entry, never taken)
     }
@@ -402,46 +488,48 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
             if (f != f0) win.topup();
         }
         // ---- frame header (:1780-1834): per iteration a run of 1-bit "unchanged" codes (count
-        // leading ones) and the code behind it
+        // leading ones) and the code behind it.  Branch-free for the lanes (selects, predicated
+        // stores); what is rare -- a code longer than 16 bits -- makes its lane wait one
+        // iteration and is then served behind a warp-uniform branch.
         int rc = 0;
         int hb = run ? 0 : nb;
-        while (DCSB_ANY(hb < nb)) {
-            const bool on = hb < nb;
+        int lng = 0;                                            // 1: a long code waits at band hb
+        while (DCSB_ANY(hb < nb || lng)) {
+            if (lng) {
+                // codes longer than 16 bits: rare, matched bit-serially
+                uint32_t q = win.pos();
+                const int val = dcsb_long_code(rd, q, tab->long94, tab->n_long94);
+                win.seek(q);
+                lng = 0;
+                if (val < 0) { rc = DCSB_WALK_BANDTYPE; hb = nb; }
+                else dcsb_hdr_apply94(hb, val - 0x2E, nb, dsel, halfmask, dtab, tx, zero, ents, bt_lo, bt_hi, fixmask, rc, hb);
+            }
+            const uint32_t ld = win.ring_word(win.wa);
             const uint32_t v = win.peek32();
             const int ones = dcsb_clz(~v);
             const int left = nb - hb;
-            const int runl = ones < left ? ones : left;         // <= 16
+            const int runl = ones < left ? ones : left;         // <= 16; 0 for a lane that is through
             const int b = hb + runl;
-            const bool code = on && b < nb;                     // a code follows the run
-            uint32_t e = lut[DCSB_LUT_HDR94 + ((v << runl) >> 24)];
-            int delta = (int)(e & 0xFF) - 0x2E;
-            uint32_t adv = (uint32_t)runl + (code ? (e >> 8) : 0u);      // <= 24 bits
-            if (DCSB_ANY(code && e == 0)) {
-                // codes longer than 8 bits: rare, matched bit-serially
-                if (code && e == 0) {
-                    uint32_t q = win.pos() + (uint32_t)runl;
-                    const int val = dcsb_long_code(rd, q, tab->long94, tab->n_long94);
-                    win.seek(q);
-                    adv = 0;
-                    if (val < 0) { rc = DCSB_WALK_BANDTYPE; hb = nb; }
-                    delta = val - 0x2E;
-                }
+            const bool code = b < nb;                           // a code follows the run
+            // (codes of 9..16 bits all start with the same 8 bits: a second 8-bit LUT on the bits behind them)
+            const uint32_t e1 = dcsb_lut_load(lut, DCSB_LUT_HDR94 + ((v << runl) >> 24));
+            const uint32_t e2 = dcsb_lut_load(lut, DCSB_LUT_HDR94B + ((v << (runl + 8)) >> 24));     // (both loads in flight together)
+            const uint32_t e = e1 ? e1 : e2;
+            const bool islong = code && e == 0;
+            const bool ok = code && e != 0;
+            // consume the run and the code (a long code: the run only; its lane waits at band b)
+            win.s += (uint32_t)runl + (ok ? (e >> 8) : 0u);      // <= 32 bits
+            {
+                const bool rf = win.s >= 32u;
+                win.w0 = rf ? win.w1 : win.w0;
+                win.w1 = rf ? DcsbBits::be(ld) : win.w1;
+                win.wa = rf ? win.wa + 4u : win.wa;
+                win.s &= 31u;
             }
-            if (on) win.skip(adv);
-            if (code && !rc) {
-                const uint32_t sh = (uint32_t)(b & 7) * 4u;
-                const uint32_t w = b < 8 ? bt_lo : bt_hi;
-                const int nbt = (int)((w >> sh) & 15u) + delta;
-                if (nbt & ~15) { rc = DCSB_WALK_BANDTYPE; hb = nb; }
-                else {
-                    const uint32_t nw = w + ((uint32_t)delta << sh);    // stays inside the nibble: 0 <= nbt <= 15
-                    if (b < 8) bt_lo = nw; else bt_hi = nw;
-                    const uint32_t d = dtab[dsel + ((halfmask >> b) & 1u) * 256u + (uint32_t)b * 16u + (uint32_t)nbt];
-                    dcsb_ent_store(ents + (DcsbSA)b * DCSB_ENT_BYTES, dcsb_band_entry(d, tx, zero));
-                    fixmask = (fixmask & ~(1u << b)) | (((d >> 30) & 1u) << b);
-                    hb = b + 1;
-                }
-            } else if (on && !rc) hb = nb;                      // the run reached the last band
+            lng = islong ? 1 : 0;
+            int nhb = nb;                                       // no code: the run reached the last band
+            if (ok) dcsb_hdr_apply94(b, (int)(e & 0xFF) - 0x2E, nb, dsel, halfmask, dtab, tx, zero, ents, bt_lo, bt_hi, fixmask, rc, nhb);
+            hb = islong ? b : nhb;
         }
         const uint32_t hpos = win.pos();
         // (a code that reaches into the bytes behind the stream is a truncation, whatever those bytes are)
@@ -454,7 +542,11 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
         if (run) {
             pos = win.pos();
             int sb = 99;
-            if (err < 0 && pos <= nbits) sb = dcsb_find_stopband94(rd, hpos, hdr, lut, bt_lo, bt_hi);
+            if (err < 0) {                      // some band overran: the loop's position is not to be trusted
+                pos = hpos;
+                sb = dcsb_find_stopband94(rd, pos, hdr, lut, bt_lo, bt_hi);
+                if (sb == 99 && pos <= nbits) win.seek(pos);
+            }
             if (pos > nbits) { status = -2; nplay = f; run = false; }                       // DCSB_E_TRUNCATED
             else if (sb != 99) { status = -5; nplay = f + 1; stopband = sb; ++f; run = false; }    // DCSB_E_STOPPED
             else {

@@ -116,6 +116,10 @@ uint64_t dcsb_batch_pcm_offset(const dcsb_batch *b, size_t i); /* sample offset 
 int dcsb_batch_decode(dcsb_batch *b, void *d_pcm, void *cuda_stream);
 /* number of kernels one dcsb_batch_decode enqueues */
 int dcsb_batch_launches(const dcsb_batch *b);
+/* launch shape of the batch's kernels, for matching a profiler capture with what runs (which: 0 = the
+ * frame-boundary scan, 1 = the 1994-layout decode kernel of the one-after-the-other mode, 2 = the persistent
+ * 1994-layout decode kernel that runs beside the scan): grid and block size in threads; DCSB_E_ARG if unknown */
+int dcsb_batch_launch_shape(const dcsb_batch *b, int which, int *grid, int *block);
 /* wait for cuda_stream, then fetch per-stream results (status/checksum) */
 int dcsb_batch_results(dcsb_batch *b, void *cuda_stream, dcsb_result *results);
 /* copy stream i's PCM (from the internal buffer) to host */

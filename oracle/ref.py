@@ -31,7 +31,7 @@ def lib():
                                     C.c_float, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]
         L.dcsref_decode_batch_timed.restype = C.c_double
         L.dcsref_decode_batch_timed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
-                                                C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint64)]
+                                                C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]
         L.dcsref_rom_open_zip.restype = C.c_void_p
         L.dcsref_rom_open_zip.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
         L.dcsref_rom_close.argtypes = [C.c_void_p]

@@ -186,9 +186,12 @@ size_t dcsref_encode(const float *pcm, size_t n, int sample_rate, int format_ver
 // streams partitioned round-robin by index; returns wall seconds around the
 // GetNextSample loops only (streams pre-loaded, padded copies made before timing).
 // pcm_out may be null (samples are still pulled and folded into a checksum).
+// per_stream_cs (may be null): for every stream the checksum dcsb_result::checksum is defined as
+// (include/dcsb200.h): sum over samples i of (uint16)s[i] * (2 i + 1) mod 2^64 -- so that a caller can
+// compare the reference's PCM with another decoder's per-stream checksums without keeping the PCM.
 double dcsref_decode_batch_timed(const uint8_t *const *datas, const uint32_t *nbytes,
     const uint32_t *nframes_to_pull, size_t n, int os_version, int master_volume, int mixing_level,
-    int n_threads, int16_t *const *pcm_out, uint64_t *checksum_out)
+    int n_threads, int16_t *const *pcm_out, uint64_t *checksum_out, uint64_t *per_stream_cs)
 {
     std::vector<std::vector<uint8_t>> bufs(n);
     for (size_t i = 0; i < n; ++i) {
@@ -208,11 +211,14 @@ double dcsref_decode_batch_timed(const uint8_t *const *datas, const uint32_t *nb
             dec.LoadAudioStream(0, DCSDecoder::ROMPointer(0, bufs[i].data()), mixing_level);
             size_t ns = (size_t)nframes_to_pull[i] * 240;
             int16_t *o = pcm_out ? pcm_out[i] : nullptr;
+            uint64_t cs = 0;
             for (size_t k = 0; k < ns; ++k) {
                 int16_t s = dec.GetNextSample();
                 h = h * 1099511628211ULL + (uint16_t)s;
+                cs += (uint64_t)(uint16_t)s * (2 * (uint64_t)k + 1);
                 if (o) o[k] = s;
             }
+            if (per_stream_cs) per_stream_cs[i] = cs;
         }
         sums[t] = h;
     };

@@ -38,8 +38,8 @@ static int sim_decode_streams(const dcsb_stream_desc *descs, size_t n, int16_t *
     std::vector<uint8_t> ring(DCSB_RING_BYTES, 0xA5);                // one K1 lane's shared-memory ring
     DcsbBandEnt ents[18];                                            // ... and its band entries
     static const uint32_t zero_word[4] = { 0, 0, 0, 0 };
-    static uint32_t dtab[DCSB_DTAB_WORDS];                           // the CTA's descriptor table
-    for (int i = 0; i < DCSB_DTAB_WORDS; ++i) dtab[i] = dcsb_dtab_entry(tab.lut, i);
+    static uint16_t dtab[DCSB_DTAB_WORDS];                           // the CTA's descriptor table
+    for (int i = 0; i < DCSB_DTAB_WORDS; ++i) dtab[i] = (uint16_t)dcsb_dtab_entry(tab.lut, i);
     std::vector<unsigned long long> csum(n + 1, 0);
     std::vector<uint32_t> rows(DcsbWarpSmem<true>::WORDS + DCSB_WARP94_WORDS);
     static DcsbTw94 tw;
@@ -166,8 +166,8 @@ extern "C" int hostsim_rom_render(const uint8_t *const *imgs, const size_t *size
     std::vector<uint8_t> ring(DCSB_RING_BYTES, 0xA5);
     DcsbBandEnt ents[18];
     static const uint32_t zero_word[4] = { 0, 0, 0, 0 };
-    static uint32_t dtab[DCSB_DTAB_WORDS];
-    for (int i = 0; i < DCSB_DTAB_WORDS; ++i) dtab[i] = dcsb_dtab_entry(tab.lut, i);
+    static uint16_t dtab[DCSB_DTAB_WORDS];
+    for (int i = 0; i < DCSB_DTAB_WORDS; ++i) dtab[i] = (uint16_t)dcsb_dtab_entry(tab.lut, i);
     for (size_t i = 0; i < ns; ++i) {
         if (p.recs[i].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, (DcsbSA)tab.tx, dtab, (DcsbSA)ring.data(), (DcsbSA)ents, (DcsbSA)zero_word, so);
         else dcsb_scan_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, so);
