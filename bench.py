@@ -13,9 +13,15 @@ scaling); the only collective is the gather of the per-rank time / checksum.
 `value`  : whole-job Msamples/s with the compressed streams already resident in HBM.
 `e2e`    : same metric through the host-buffer C-ABI call dcsb_decode_streams (pinned host
            input, H2D, kernels, D2H of all PCM inside the timed region).
-`roofline`: the dominant kernel (decode+transform) against the measured HBM copy bandwidth.
+`roofline`: the dominant kernel against the measured HBM copy bandwidth, plus its share of the
+           SMs' issue rate; DRAM traffic / instruction counts come from the committed ncu capture
+           named in `traffic_source` and are only printed when that capture's launch shapes are
+           the ones this run launched.
 `cpu_baseline`: the reference DCSDecoderNative (oracle/_ref, kind "reference") -- or the
-           oracle port when the reference did not compile -- on a bounded sample, all host cores.
+           oracle port when the reference did not compile -- on a bounded sample, all host cores;
+           its per-stream checksums are compared with the GPU's (`parity`).
+`configs`: (N = 1) BASELINE.json configs 1, 3 and 4, bounded to a few seconds each.
+`config5`: (N > 1) BASELINE.json config 5: 1,048,576 one-second streams sharded over the ranks.
 """
 import argparse
 import ctypes as C
@@ -34,10 +40,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 SAMPLE_RATE = 31250
 FRAME = 240
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
-# capture of this workload (profiles/r01m_ncu_full.txt): scan 550.3 MB read + 72.4 MB written
-# (checkpoints); decode (captured as the persistent queue variant, same work) 673.6 MB read + 2512.8 MB written
-TRAFFIC = {"dcsb_scan_kernel": 622.7e6, "dcsb_decode94_kernel": 3186.4e6}
+# DRAM traffic and warp-instruction counts per launch come from the committed `ncu --set full` capture of
+# this workload, summarised by tools/make_traffic.py into profiles/traffic.json together with the launch
+# shapes of the captured kernels
+TRAFFIC_JSON = os.path.join(ROOT, "profiles", "traffic.json")
 
 
 # ------------------------------------------------------------------------------------------
@@ -118,6 +124,17 @@ def build_corpus(n_streams, seconds, seed0, budget_s=75.0, log=None):
     return streams, n_unique, src
 
 
+def load_corpus_cache(n_streams, seconds, seed0):
+    """The pool build_corpus left in corpus_cache/ (ranks other than 0 read what rank 0 made, so that
+    every rank sees the same pool even when the encoder's time budget cut it short)."""
+    cache = os.path.join(ROOT, "corpus_cache", "c2_%d_%gs_seed%d.npz" % (n_streams, seconds, seed0))
+    z = np.load(cache)
+    blob, offs = z["blob"], z["offs"]
+    pool = [blob[offs[i]:offs[i + 1]].tobytes() for i in range(len(offs) - 1)]
+    n_unique = min(len(pool), n_streams)
+    return [pool[i % n_unique] for i in range(n_streams)], n_unique, "reference DCSEncoder (oracle/_ref)"
+
+
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -173,11 +190,13 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_reference_run(streams, vol, lvl, tail, threads, budget_streams):
-    """Times the reference CPU decoder (or the oracle port) on streams[:budget_streams]."""
+def cpu_reference_run(streams, vol, lvl, tail, threads, budget_streams, os_version=0x9400):
+    """Times the reference CPU decoder (or the oracle port) on streams[:budget_streams].
+    Returns (Msamples/s, kind, threads, sample description, seconds, per-stream checksums or None)."""
     from oracle import ref, orc
     sample = streams[:budget_streams]
     nsamp = sum((((s[0] << 8) | s[1]) + tail) * FRAME for s in sample)
+    cs_each = None
     if ref.available():
         L = ref.lib()
         n = len(sample)
@@ -186,17 +205,235 @@ def cpu_reference_run(streams, vol, lvl, tail, threads, budget_streams):
         nbytes = np.array([b.size for b in bufs], dtype=np.uint32)
         nfr = np.array([((s[0] << 8) | s[1]) + tail for s in sample], dtype=np.uint32)
         cs = C.c_uint64(0)
-        secs = L.dcsref_decode_batch_timed(ptrs, nbytes.ctypes.data, nfr.ctypes.data, n, 0x9400, vol, lvl,
-                                           threads, None, C.byref(cs))
+        cs_each = np.zeros(n, dtype=np.uint64)
+        secs = L.dcsref_decode_batch_timed(ptrs, nbytes.ctypes.data, nfr.ctypes.data, n, os_version, vol, lvl,
+                                           threads, None, C.byref(cs), cs_each.ctypes.data)
         kind = "reference"
     else:
         t0 = time.time()
-        for s in sample:
-            orc.decode(s, 0x9400, vol, lvl, ((s[0] << 8) | s[1]) + tail)
+        cs_each = np.zeros(len(sample), dtype=np.uint64)
+        for i, s in enumerate(sample):
+            pcm, _ = orc.decode(s, os_version, vol, lvl, ((s[0] << 8) | s[1]) + tail)
+            u = pcm.view(np.uint16).astype(np.uint64)
+            cs_each[i] = np.sum(u * (2 * np.arange(u.size, dtype=np.uint64) + 1), dtype=np.uint64)
         secs = time.time() - t0
         kind, threads = "port", 1
     return nsamp / secs / 1e6, kind, threads, "%d of the workload's streams (%.1f s of audio each), %.2f s wall" % (
-        len(sample), (((sample[0][0] << 8) | sample[0][1]) * FRAME) / SAMPLE_RATE, secs), secs
+        len(sample), (((sample[0][0] << 8) | sample[0][1]) * FRAME) / SAMPLE_RATE, secs), secs, cs_each
+
+
+def load_traffic(shapes):
+    """profiles/traffic.json -> {kernel: record}, keeping only the kernels whose captured launch shape is
+    the one this run launches (a capture of other kernels / other grids says nothing about this run)."""
+    try:
+        t = json.load(open(TRAFFIC_JSON))
+    except Exception:
+        return {}, None
+    out = {}
+    for k, rec in t.get("kernels", {}).items():
+        if k in shapes and list(shapes[k]) == [rec.get("grid"), rec.get("block")]:
+            out[k] = rec
+    return out, t.get("source")
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE.json configs 1, 3, 4 (N = 1) and 5 (N > 1): bounded side measurements
+def config1(ctx, dx):
+    """one 10 s clip -> one 1994+ type 1.3 stream at 128 kbit/s, host-to-host latency, checked against the reference"""
+    from oracle import ref, orc
+    if not ref.available():
+        return {"skipped": "reference encoder unavailable"}
+    rng = np.random.Generator(np.random.MT19937(12345))
+    t = np.arange(312500) / 31250.0
+    x = (0.5 * np.sin(2 * np.pi * 440 * t) + 0.2 * np.sin(2 * np.pi * 2500 * t) + rng.normal(0, 0.05, t.size)).astype(np.float32)
+    data, nf = ref.encode(x, fmt=0x9400, stype=1, subtype=3, bit_rate=128000, power_cut=0.97)
+    t0 = time.perf_counter()
+    want = ref.decode(data, 0x9400, 255, 0x64, nf + 2)
+    tref = time.perf_counter() - t0
+    ts = []
+    for _ in range(6):
+        t0 = time.perf_counter()
+        pcm, offs, res = ctx.decode_streams([(data, 0x9400, 255, 0x64, 2)])
+        ts.append(time.perf_counter() - t0)
+    ok = res[0]["status"] == 0 and bool(np.array_equal(pcm[:want.size], want))
+    return {"workload": "one 10 s sine+noise clip, 1994+ type 1.3 at 128 kbit/s (%d frames, %d bytes)" % (nf, len(data)),
+            "latency_ms": min(ts[1:]) * 1e3, "first_call_ms": ts[0] * 1e3, "value": want.size / min(ts[1:]) / 1e6, "unit": "Msamples/s",
+            "api": "dcsb_decode_streams (host in, host out)", "reference_1_thread_ms": tref * 1e3, "bit_exact_vs_reference": ok}
+
+
+_KINDS3 = [(0x9302, 0), (0x9302, 1), (0x9301, 0)]
+
+
+def _encode3(args):
+    seed, seconds = args
+    from oracle import ref
+    fmt, ty = _KINDS3[seed % 3]
+    data, nf = ref.encode(synth_source(seed, seconds), fmt=fmt, stype=ty, subtype=0,
+                          bit_rate=RATES[(seed // 3) % 6], power_cut=CUTS[(seed // 18) % 3])
+    return data, fmt
+
+
+def config3(ctx, dx, torch, n=4096, pool_n=96, seconds=10.0):
+    """1993-era layouts: 0x9302 types 0 / 1 and 0x9301 type 0 from the reference encoder + fuzzer-made OS93a type 1"""
+    from oracle import ref, orc
+    import dcsfuzz
+    if not ref.available():
+        return {"skipped": "reference encoder unavailable"}
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(len(os.sched_getaffinity(0))) as p:
+        pool = p.map(_encode3, [(5000 + i, seconds) for i in range(pool_n)], chunksize=2)
+    rng = np.random.default_rng(9)
+    nf = int(seconds * SAMPLE_RATE / FRAME)
+    pool += [(dcsfuzz.fuzz93a1(rng, nf), 0x9301) for _ in range(8)]
+    streams = [(pool[i % len(pool)][0], pool[i % len(pool)][1], 255, 0x64, 2) for i in range(n)]
+    batch = ctx.batch(streams)
+    d_pcm = torch.empty(batch.total_samples, dtype=torch.int16, device="cuda")
+    st = torch.cuda.current_stream()
+    ms = []
+    for i in range(6):
+        batch.decode(d_pcm.data_ptr(), st.cuda_stream)
+        torch.cuda.synchronize()
+        if i >= 2:
+            ms.append(batch.kernel_ms(2))
+    res = batch.results(st.cuda_stream)
+    # every unique stream once against the oracle (the pool is small)
+    h = d_pcm.cpu().numpy()
+    bad = 0
+    for i in range(len(pool)):
+        d, os_, vol, lvl, tail = streams[i]
+        want, _ = orc.decode(d, os_, vol, lvl, ((d[0] << 8) | d[1]) + tail)
+        o = batch.pcm_offset(i)
+        bad += 0 if np.array_equal(h[o:o + want.size], want) else 1
+    out = {"workload": "%d streams x %g s (%d unique: 0x9302 type 0 / type 1, 0x9301 type 0 from the reference encoder, 8 fuzzer-made OS93a type 1)" % (n, seconds, len(pool)),
+           "ms_per_step": float(np.mean(ms)), "value": batch.total_samples / float(np.mean(ms)) / 1e3, "unit": "Msamples/s",
+           "frames": int(batch.total_frames), "streams_with_errors": sum(1 for r in res if r["status"] != 0),
+           "parity_checked_streams": len(pool), "mismatches": bad, "checked_against": "oracle/dcs_oracle.c (pinned to the reference)"}
+    batch.close()
+    del d_pcm
+    return out
+
+
+def config4(ctx, dx, torch, n=2048):
+    """track playback on the ROM built by the reference's DCSCompiler: n timelines + every track solo, one call"""
+    import compiledrom
+    from oracle import ref
+    try:
+        c = compiledrom.load(compiledrom.NAMES[0])
+    except Exception as e:
+        return {"skipped": "compiled ROM fixture unavailable: %s" % e}
+    rom = dx.Rom(c["images"])
+    tls = []
+    for i in range(n):
+        sh = i % 13
+        tls.append(([(f + sh, b) for f, b in c["writes"]], c["n_frames"] + sh, 255 - (i % 100)))
+    tls += c["track_timelines"]
+    frames = sum(t[1] for t in tls)
+    tl_arr, keep = dx.make_timelines(tls)
+    out = torch.empty(frames * 240, dtype=torch.int16).pin_memory()
+    resarr = (dx.TimelineResult * len(tls))()
+    ts = []
+    for it in range(4):
+        t0 = time.perf_counter()
+        rc = ctx._L.dcsb_render_timelines(ctx._h, rom._h, tl_arr, len(tls), out.data_ptr(), None, resarr)
+        ts.append(time.perf_counter() - t0)
+        if rc != 0:
+            return {"error": "dcsb_render_timelines: %d" % rc}
+    h = out.numpy()
+    checked, bad = 0, 0
+    if ref.available():
+        offs = np.concatenate([[0], np.cumsum([t[1] * 240 for t in tls])])
+        for i in (0, 1, n // 2, n - 1, n, len(tls) - 1):
+            rp = ref.RomPlayer(c["images"], tls[i][2])
+            want = rp.render_timeline(tls[i][0], tls[i][1])
+            rp.close()
+            checked += 1
+            bad += 0 if np.array_equal(h[offs[i]:offs[i + 1]], want) else 1
+    best = min(ts[1:])
+    res = {"workload": "%d timelines (shifted command times, master volumes 156..255) + %d solo tracks of the ROM set compiled by the reference's DCSCompiler (%s)" % (
+               n, len(c["track_timelines"]), compiledrom.NAMES[0]),
+           "output_frames": int(frames), "ms_per_call": best * 1e3, "value": frames * 240 / best / 1e6, "unit": "Msamples/s",
+           "api": "dcsb_render_timelines (host in, pinned host out; host sequencer + mix kernel + PCM download inside)",
+           "timelines_with_errors": sum(1 for i in range(len(tls)) if resarr[i].status != 0),
+           "parity_checked_timelines": checked, "mismatches": bad, "checked_against": "reference DCSDecoderNative (oracle/_ref)"}
+    rom.close()
+    return res
+
+
+def config5(ctx, dx, torch, dist, rank, world, local_rank, total_streams, steps=3):
+    """BASELINE.json config 5: total_streams one-second streams (a pool of unique streams from the reference
+    encoder, replicated so that every stream has its own bytes in HBM), LPT-partitioned over the ranks by frame
+    count, resident decode, per-rank checksum gathered over NCCL."""
+    POOL = 16384
+    if rank == 0:
+        build_corpus(POOL, 1.0, 100000, budget_s=60.0)
+    dist.barrier()
+    pool, n_unique, src = load_corpus_cache(POOL, 1.0, 100000)                  # every rank: what rank 0 left in the cache
+    pool = pool[:n_unique]
+    blob = np.frombuffer(b"".join(pool), dtype=np.uint8)
+    offs = np.concatenate([[0], np.cumsum([len(p) for p in pool])]).astype(np.int64)
+    pframes = np.array([(p[0] << 8) | p[1] for p in pool], dtype=np.uint32)
+    gidx = (np.arange(total_streams, dtype=np.int64) * 7919) % n_unique          # every rank computes the same job
+    part, load = dx.partition_streams(pframes[gidx], world)
+    mine = gidx[np.asarray(part) == rank]
+    descs, keep = dx.make_descs_pool(blob, offs, mine, os_version=dx.OS94, master_volume=255, mixing_level=0x64, tail_frames=2)
+    t0 = time.time()
+    batch = dx.Batch(ctx, None, descs=descs)
+    t_create = time.time() - t0
+    d_pcm = torch.empty(batch.total_samples, dtype=torch.int16, device="cuda")
+    st = torch.cuda.current_stream()
+    for _ in range(2):
+        batch.decode(d_pcm.data_ptr(), st.cuda_stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(st)
+    for _ in range(steps):
+        batch.decode(d_pcm.data_ptr(), st.cuda_stream)
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    ctx.set_overlap(False)
+    batch.decode(d_pcm.data_ptr(), st.cuda_stream)
+    torch.cuda.synchronize()
+    scan_ms, dec_ms = batch.kernel_ms(0), batch.kernel_ms(1)
+    ctx.set_overlap(True)
+    res = batch.results_np(st.cuda_stream)
+    xor = int(np.bitwise_xor.reduce(res["checksum"])) if res.size else 0
+    # the pool's streams must decode to the same PCM wherever they sit: per-pool-stream checksums of this rank
+    bad = int(np.count_nonzero(res["status"]))
+    first = {}
+    for k in range(min(res.size, 200000)):
+        g = int(mine[k])
+        if g in first:
+            bad += 0 if first[g] == int(res["checksum"][k]) else 1
+        else:
+            first[g] = int(res["checksum"][k])
+    t = torch.tensor([ms, float(batch.total_samples), float(batch.compressed_bytes), scan_ms, dec_ms], dtype=torch.float64, device="cuda")
+    g = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(g, t)
+    cs = torch.tensor([xor & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device="cuda")
+    gc = [torch.zeros_like(cs) for _ in range(world)]
+    dist.all_gather(gc, cs)                         # the checksum gather: 8 bytes per rank over NCCL
+    per_rank_ms = [float(x[0].item()) for x in g]
+    samples = sum(float(x[1].item()) for x in g)
+    cbytes = sum(float(x[2].item()) for x in g)
+    peak, _ = measured_peak_gbs()
+    worst = max(per_rank_ms)
+    out = {"workload": "%d streams x 1 s (pool of %d unique 1994+ streams from the reference encoder, every stream with its own bytes in HBM), "
+                       "LPT-partitioned by frame count over %d ranks, resident decode" % (total_streams, n_unique, world),
+           "value": samples / (worst * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": worst, "per_rank_ms": per_rank_ms,
+           "per_rank_scan_ms": [float(x[3].item()) for x in g], "per_rank_decode_ms": [float(x[4].item()) for x in g],
+           "streams_per_rank": int(mine.size), "frames_per_rank": int(batch.total_frames), "audio_hours": samples / SAMPLE_RATE / 3600,
+           "compressed_bytes": cbytes, "pcm_bytes": samples * 2,
+           "frac": (cbytes + samples * 2) / (worst * 1e-3) / 1e9 / (peak * world),
+           "frac_note": "algorithmic bytes (compressed in + PCM out) / slowest rank's step time, against %d x the measured HBM copy bandwidth" % world,
+           "errors_or_replica_mismatches_this_rank": bad, "checksum_xor_per_rank": ["%016x" % int(x.item()) for x in gc],
+           "batch_create_s": t_create}
+    batch.close()
+    del d_pcm
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -222,6 +459,8 @@ def _main(out):
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs 1/3/4 (N = 1) and config 5 (N > 1) side measurements")
+    ap.add_argument("--config5-streams", type=int, default=1048576)
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -236,11 +475,12 @@ def _main(out):
         if rank != 0:
             return
         streams, n_unique, src = build_corpus(a.streams, a.seconds, 0)
-        per_step = min(max(ncores * 16, 64), len(streams))
+        # a step = a bounded sample of the workload, large enough for >= 1 s of wall time on all cores
+        per_step = min(max(ncores * 128, 512), len(streams))
         vals = []
         for s in range(a.warmup + a.steps):
             lo = (s * per_step) % max(1, len(streams) - per_step + 1)
-            v, kind, thr, sample, secs = cpu_reference_run(streams[lo:lo + per_step], vol, lvl, tail, ncores, per_step)
+            v, kind, thr, sample, secs, _ = cpu_reference_run(streams[lo:lo + per_step], vol, lvl, tail, ncores, per_step)
             if s >= a.warmup:
                 vals.append((v, secs))
         value = float(np.mean([v for v, _ in vals]))
@@ -248,7 +488,7 @@ def _main(out):
                 "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": float(np.mean([s for _, s in vals]) * 1e3), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "int16/int32 fixed point", "data": "synthetic: " + src,
-                "config": {"workload": workload, "step": "%d streams per step (bounded sample)" % per_step,
+                "config": {"workload": workload, "step": "%d streams per step (bounded sample of the workload, a rate)" % per_step,
                            "unique_streams": n_unique},
                 "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": thr, "kind": kind, "sample": sample},
                 "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -272,7 +512,7 @@ def _main(out):
     if world > 1:
         dist.barrier()
         if rank != 0:
-            streams, n_unique, src = build_corpus(a.streams, a.seconds, 0)   # cache written by rank 0
+            streams, n_unique, src = load_corpus_cache(a.streams, a.seconds, 0)   # cache written by rank 0
         # the job is world x 4,096 streams, sharded by stream with the library's own partition
         # function (LPT on frame counts; every rank computes the same assignment, no collective)
         pool = streams
@@ -283,7 +523,8 @@ def _main(out):
     ctx = dx.Context(local_rank)
     batch = ctx.batch(streams, os_version=dx.OS94, master_volume=vol, mixing_level=lvl, tail_frames=tail)
     total_samples = batch.total_samples
-    alg_bytes = batch.compressed_bytes + total_samples * 2
+    comp_bytes = int(batch.compressed_bytes)
+    alg_bytes = comp_bytes + total_samples * 2
     d_pcm = torch.empty(total_samples, dtype=torch.int16, device="cuda")
     st = torch.cuda.current_stream()
 
@@ -305,9 +546,8 @@ def _main(out):
         step()
         ev[i + 1].record(st)
     torch.cuda.synchronize()
-    # per-kernel times of the last step come from events the library records on the same stream
-    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.steps)]
     total_ms = ev[0].elapsed_time(ev[a.steps])
+    my_ms = total_ms / a.steps
     # per-kernel durations: the timed steps above run the scan BESIDE the decode kernel (the
     # library's default), so a kernel's own duration is read from K more steps with the two
     # kernels one after the other, from the library's CUDA-event pairs on the launching stream
@@ -333,7 +573,12 @@ def _main(out):
 
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     cs = torch.tensor([xor & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device="cuda")
+    per_rank_ms = [my_ms]
     if world > 1:
+        mine_t = torch.tensor([my_ms], dtype=torch.float64, device="cuda")
+        gt = [torch.zeros_like(mine_t) for _ in range(world)]
+        dist.all_gather(gt, mine_t)
+        per_rank_ms = [float(x.item()) for x in gt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         gathered = [torch.zeros_like(cs) for _ in range(world)]
         dist.all_gather(gathered, cs)               # the checksum gather: 8 bytes per rank over NCCL
@@ -356,6 +601,8 @@ def _main(out):
     e2e_ms = []
     for i in range((1 + a.e2e_steps) if a.e2e_steps > 0 else 0):
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         rc = L.dcsb_decode_streams(ctx._h, descs, len(streams), h_pcm.data_ptr(), None, resarr)
         t1 = time.perf_counter()
@@ -367,8 +614,9 @@ def _main(out):
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = world * total_samples / (float(e2e_t.item()) * 1e-3) / 1e6
-    # the whole e2e output against the resident-path output
+    # the whole e2e output against the resident-path output, and its per-stream checksums
     same = bool(torch.equal(h_pcm, d_pcm.cpu())) if e2e_ms else None
+    e2e_cs_same = all(resarr[i].checksum == res[i]["checksum"] for i in range(len(streams))) if e2e_ms else None
     # what the PCIe link alone takes for the PCM bytes (one device-to-host copy of the same size)
     d2h_ms = None
     if e2e_ms:
@@ -378,20 +626,40 @@ def _main(out):
             h_pcm.copy_(d_pcm, non_blocking=True)
             torch.cuda.synchronize()
             d2h_ms = (time.perf_counter() - t0) * 1e3
+    shapes = {"dcsb_scan_kernel": batch.launch_shape(0), "dcsb_decode94_kernel": batch.launch_shape(1),
+              "dcsb_decode94_queue_kernel": batch.launch_shape(2)}
+    n_launch = batch.launches()
+    del h_pcm, blob
+
+    # ---------------- side measurements
+    c5 = None
+    if world > 1 and not a.no_configs:
+        batch.close()
+        del d_pcm
+        torch.cuda.empty_cache()
+        c5 = config5(ctx, dx, torch, dist, rank, world, local_rank, a.config5_streams)
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         dec_ms = float(np.mean(kms[1]))
         scan_ms = float(np.mean(kms[0]))
+        traffic, traffic_src = load_traffic(shapes)
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        clk_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
         # algorithmic bytes per launch: the scan reads every compressed byte once;
         # the decode kernel reads them once more and writes every PCM byte once
         kern = [
-            {"kernel": "dcsb_scan_kernel", "ms": scan_ms, "algorithmic_bytes_per_launch": int(batch.compressed_bytes)},
+            {"kernel": "dcsb_scan_kernel", "ms": scan_ms, "algorithmic_bytes_per_launch": comp_bytes},
             {"kernel": "dcsb_decode94_kernel", "ms": dec_ms, "algorithmic_bytes_per_launch": int(alg_bytes)},
         ]
         for k in kern:
             k["achieved"] = k["algorithmic_bytes_per_launch"] / (k["ms"] * 1e-3) / 1e9
             k["frac"] = k["achieved"] / peak
+            k["grid"], k["block"] = shapes[k["kernel"]]
+            tr = traffic.get(k["kernel"])
+            k["traffic"] = tr["traffic_bytes"] if tr else None
+            # share of the SMs' issue rate: warp instructions of the capture / (duration x SMs x 4 schedulers x clock)
+            k["issue_frac"] = tr["warp_insts"] / (k["ms"] * 1e-3 * sms * 4 * clk_hz) if tr else None
         dom = max(kern, key=lambda k: k["ms"])
         line = {
             "metric": "decoded PCM Msamples/s (bit-exact)", "value": value, "unit": "Msamples/s", "n_gpus": world,
@@ -399,34 +667,64 @@ def _main(out):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16/int32 fixed point", "data": "synthetic: " + src,
             "config": {"workload": workload, "per_gpu_streams": a.streams, "unique_streams": n_unique,
-                       "frames_per_gpu": int(batch.total_frames), "compressed_bytes_per_gpu": int(batch.compressed_bytes),
+                       "frames_per_gpu": int(total_samples // FRAME), "compressed_bytes_per_gpu": comp_bytes,
                        "pcm_bytes_per_gpu": int(total_samples * 2), "parallelism": "streams sharded by rank, no data-path collective",
                        "l2": "inputs+outputs (%.2f GB) exceed the 126 MB L2; no flush needed" % (alg_bytes / 1e9),
                        "master_volume": vol, "mixing_level": lvl, "tail_frames": tail},
+            "per_rank_ms": per_rank_ms,
             "kernels_ms": {"scan": scan_ms, "decode_transform": dec_ms, "serial_step": float(np.mean(serial_ms)),
                            "overlapped_scan_span": float(np.mean(spans[0])), "overlapped_decode_span": float(np.mean(spans[1])),
                            "note": "value/ms_per_step: scan and decode kernels resident together (default); "
                                    "scan / decode_transform: each kernel alone (dcsb_set_overlap(ctx, 0))"},
             "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak, "unit": "GB/s",
-                         "frac": dom["frac"], "traffic": TRAFFIC.get(dom["kernel"]), "peak_source": peak_src,
+                         "frac": dom["frac"], "traffic": dom["traffic"], "traffic_source": traffic_src if dom["traffic"] is not None else None,
+                         "issue_frac": dom["issue_frac"], "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
-                         "note": "dominant kernel by its own duration; it is bound by the per-stream dependent "
-                                 "chain (latency), not by HBM -- see DESIGN.md section 4",
+                         "note": "dominant kernel by its own duration; it is bound by the per-stream dependent chain (latency) and "
+                                 "by integer issue, not by HBM -- see DESIGN.md section 4.  traffic / issue_frac are null when the "
+                                 "committed capture (profiles/traffic.json) is not of the launch shapes this run used",
                          "kernels": kern,
                          "whole_step_frac": alg_bytes / (total_ms / a.steps * 1e-3) / 1e9 / peak},
-            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(batch.compressed_bytes),
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": comp_bytes,
                     "d2h_bytes_per_step": int(total_samples * 2), "ms_per_step": float(e2e_t.item()),
                     "api": "dcsb_decode_streams (pinned host in/out)", "matches_resident_path": same,
-                    "d2h_copy_alone_ms": d2h_ms,
+                    "checksums_match_resident_path": e2e_cs_same, "d2h_copy_alone_ms": d2h_ms,
                     "note": "bound by the PCIe link: the PCM is 4.7x the compressed bytes; d2h_copy_alone_ms = one "
                             "cudaMemcpy of the same PCM bytes on this box"},
-            "gpu_launches": batch.launches() * a.steps,
+            "gpu_launches": n_launch * a.steps,
             "clocks": clocks,
             "status": {"streams_with_errors": len(bad), "checksum_xor": "%016x" % xor},
         }
-        if not a.no_cpu_baseline:
-            v, kind, thr, sample, secs = cpu_reference_run(streams, vol, lvl, tail, ncores, min(2048, len(streams)))     # ~20 s of CPU work on 16 cores
+        if world == 1 and not a.no_cpu_baseline:
+            # the reference decoder on a bounded sample of the SAME streams (~20 s of CPU work), all host cores;
+            # its per-stream checksums (computed from its PCM inside oracle/ref_shim.cpp) against the GPU's
+            nsample = min(2048, len(streams))
+            v, kind, thr, sample, secs, cs_ref = cpu_reference_run(streams, vol, lvl, tail, ncores, nsample)
             line["cpu_baseline"] = {"value": v, "unit": "Msamples/s", "cores": thr, "kind": kind, "sample": sample}
+            gpu_cs = np.array([res[i]["checksum"] for i in range(nsample)], dtype=np.uint64)
+            e2e_cs = np.array([resarr[i].checksum for i in range(nsample)], dtype=np.uint64) if e2e_ms else gpu_cs
+            line["parity"] = {"parity_checked_streams": int(nsample), "mismatches": int(np.count_nonzero(gpu_cs != cs_ref)),
+                              "mismatches_e2e_path": int(np.count_nonzero(e2e_cs != cs_ref)),
+                              "checked_against": "per-stream checksums of the PCM of %s" % ("the reference DCSDecoderNative (oracle/_ref)" if kind == "reference" else "the oracle port"),
+                              "checksum": "sum over samples i of (uint16)s[i] * (2 i + 1) mod 2^64 (include/dcsb200.h)"}
+        elif world > 1:
+            line["cpu_baseline_note"] = "measured at N = 1 only (the other ranks would share the host cores with it)"
+        if world == 1 and not a.no_configs:
+            batch.close()
+            del d_pcm
+            torch.cuda.empty_cache()
+            cfg = {}
+            for name, fn in (("config1", lambda: config1(ctx, dx)), ("config3", lambda: config3(ctx, dx, torch)),
+                             ("config4", lambda: config4(ctx, dx, torch))):
+                t0 = time.time()
+                try:
+                    cfg[name] = fn()
+                except Exception as e:          # a side measurement never takes the line down
+                    cfg[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+                cfg[name]["wall_s"] = time.time() - t0
+            line["configs"] = cfg
+        if c5 is not None:
+            line["config5"] = c5
         print(json.dumps(line), file=out)
         out.flush()
     if world > 1:

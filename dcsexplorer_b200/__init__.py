@@ -47,6 +47,31 @@ def make_descs(streams, os_version=OS94, master_volume=255, mixing_level=0x64, t
     return arr, keep
 
 
+DESC_DTYPE = np.dtype({"names": ["data", "nbytes", "os_version", "master_volume", "mixing_level", "tail_frames", "reserved"],
+                       "formats": ["<u8", "<u4", "<u2", "u1", "u1", "<u2", "<u2"],
+                       "offsets": [0, 8, 12, 14, 15, 16, 18], "itemsize": C.sizeof(StreamDesc)})
+RESULT_DTYPE = np.dtype({"names": ["status", "frames", "frames_decoded", "stream_bytes", "checksum"],
+                         "formats": ["<i4", "<u4", "<u4", "<u4", "<u8"],
+                         "offsets": [0, 4, 8, 12, 16], "itemsize": C.sizeof(Result)})
+
+
+def make_descs_pool(blob, offs, idx, os_version=OS94, master_volume=255, mixing_level=0x64, tail_frames=2):
+    """Descriptors for very many streams without a Python loop: stream i is bytes
+    blob[offs[idx[i]] : offs[idx[i] + 1]] of a (kept alive) uint8 numpy blob.  Several streams may
+    share host bytes (a pool replicated into a large batch): dcsb_batch_create copies every stream
+    to its own place in HBM.  Returns (numpy array with the dcsb_stream_desc layout, keepalive)."""
+    idx = np.asarray(idx, dtype=np.int64)
+    offs = np.asarray(offs, dtype=np.int64)
+    d = np.zeros(max(1, idx.size), dtype=DESC_DTYPE)
+    d["data"][:idx.size] = blob.ctypes.data + offs[idx]
+    d["nbytes"][:idx.size] = offs[idx + 1] - offs[idx]
+    d["os_version"] = os_version
+    d["master_volume"] = master_volume
+    d["mixing_level"] = mixing_level
+    d["tail_frames"] = tail_frames
+    return d, blob
+
+
 def _results_to_list(res, n):
     return [dict(status=res[i].status, frames=res[i].frames, frames_decoded=res[i].frames_decoded,
                  stream_bytes=res[i].stream_bytes, checksum=res[i].checksum) for i in range(n)]
@@ -130,13 +155,19 @@ class Context:
 class Batch:
     """dcsb_batch_*: streams resident in HBM."""
 
-    def __init__(self, ctx, streams, **kw):
+    def __init__(self, ctx, streams, descs=None, **kw):
+        """streams: list of streams (see make_descs), or None with descs = a DESC_DTYPE numpy array
+        (make_descs_pool) for batches too large for a Python loop."""
         self.ctx = ctx
         self._L = ctx._L
-        self.n = len(streams)
-        descs, keep = make_descs(streams, **kw)
+        if descs is not None:
+            self.n = int(descs.size)
+            dptr = descs.ctypes.data_as(C.POINTER(StreamDesc))
+        else:
+            self.n = len(streams)
+            dptr, keep = make_descs(streams, **kw)
         h = C.c_void_p()
-        ctx._check(self._L.dcsb_batch_create(ctx._h, descs, self.n, C.byref(h)), "dcsb_batch_create")
+        ctx._check(self._L.dcsb_batch_create(ctx._h, dptr, self.n, C.byref(h)), "dcsb_batch_create")
         self._h = h
         self.total_samples = self._L.dcsb_batch_total_samples(h)
         self.total_frames = self._L.dcsb_batch_total_frames(h)
@@ -159,6 +190,17 @@ class Batch:
         res = (Result * max(1, self.n))()
         self.ctx._check(self._L.dcsb_batch_results(self._h, stream, res), "dcsb_batch_results")
         return _results_to_list(res, self.n)
+
+    def results_np(self, stream=None):
+        """the same as a numpy structured array (RESULT_DTYPE): for batches of 10^5 .. 10^6 streams"""
+        res = (Result * max(1, self.n))()
+        self.ctx._check(self._L.dcsb_batch_results(self._h, stream, res), "dcsb_batch_results")
+        return np.frombuffer(res, dtype=RESULT_DTYPE, count=self.n).copy()
+
+    def launch_shape(self, which):
+        g, b = C.c_int(0), C.c_int(0)
+        self.ctx._check(self._L.dcsb_batch_launch_shape(self._h, which, C.byref(g), C.byref(b)), "dcsb_batch_launch_shape")
+        return g.value, b.value
 
     def pcm_offset(self, i):
         return self._L.dcsb_batch_pcm_offset(self._h, i)

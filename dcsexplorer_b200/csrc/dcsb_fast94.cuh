@@ -213,8 +213,8 @@ struct DcsbTw94 {
 template <bool SUB>
 DCSB_HD int dcsb_mac2(int a, int b2, int c, int d2)
 {
-    const uint32_t p2 = (uint32_t)(c * d2);
-    uint32_t r = (uint32_t)(a * b2) + 0x8000u;
+    const uint32_t p2 = (uint32_t)c * (uint32_t)d2;            // (wrap-around products: only bits 16..31 are consumed)
+    uint32_t r = (uint32_t)a * (uint32_t)b2 + 0x8000u;
     r = SUB ? r - p2 : r + p2;
     if ((p2 & 0xFFFFu) == 0x8000u) r &= ~0x10000u;
     return (int)r >> 16;

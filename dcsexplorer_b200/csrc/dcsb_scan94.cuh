@@ -74,7 +74,7 @@ DCSB_HD uint32_t dcsb_and_or(uint32_t a, uint32_t b, uint32_t c)
 // One band of a lane's current frame, as the band loop takes it.
 struct DcsbBandEnt {
     DcsbSA tb;          // length table of the band's codebook (16 KB aligned), or the zero word
-    int32_t nslots;     // -(slots << 12): the switch is S = dm * nslots + S (dm = -1 when the band is done, else 0)
+    uint32_t sinit;     // slots << 12 | 0xF00: the lane state the band starts with (the low byte, t, is kept)
     uint32_t amask;     // 0x3FFC (table index bits) or 0 (no table: the lookup reads the zero word)
     int32_t fix;        // > 0: fixed-width band, bits to skip; -1: end of the frame's list; else 0
 };
@@ -87,7 +87,7 @@ DCSB_HD DcsbBandEnt dcsb_ent_load(DcsbSA a)
 {
     DcsbBandEnt e;
 #if DCSB_DEVICE_PASS
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e.tb), "=r"(e.nslots), "=r"(e.amask), "=r"(e.fix) : "r"(a));
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e.tb), "=r"(e.sinit), "=r"(e.amask), "=r"(e.fix) : "r"(a));
 #else
     memcpy(&e, reinterpret_cast<const void *>(a), sizeof(e));
 #endif
@@ -96,7 +96,7 @@ DCSB_HD DcsbBandEnt dcsb_ent_load(DcsbSA a)
 DCSB_HD void dcsb_ent_store(DcsbSA a, const DcsbBandEnt &e)
 {
 #if DCSB_DEVICE_PASS
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(e.tb), "r"(e.nslots), "r"(e.amask), "r"(e.fix) : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(e.tb), "r"(e.sinit), "r"(e.amask), "r"(e.fix) : "memory");
 #else
     memcpy(reinterpret_cast<void *>(a), &e, sizeof(e));
 #endif
@@ -198,7 +198,7 @@ DCSB_HD DcsbBandEnt dcsb_band_entry(uint32_t d, DcsbTxBase tx, DcsbSA zero)
     const bool huff = (d & DCSB_DESC_HUFF) != 0;
     e.tb = huff ? tx + (DcsbSA)(((d >> 10) & 7u) << 14) : zero;
     const bool fixed = (d & DCSB_DESC_FIXED) != 0;
-    e.nslots = -(int32_t)((huff ? (d & 0x3Fu) : (fixed ? 1u : 0u)) << 12);          // a fixed-width band parks the lane (one slot, no table) until the re-seek
+    e.sinit = ((huff ? (d & 0x3Fu) : (fixed ? 1u : 0u)) << 12) | 0xF00u;            // a fixed-width band parks the lane (one slot, no table) until the re-seek
     e.amask = huff ? 0x3FFCu : 0u;
     e.fix = fixed ? (int32_t)(d & 0x3FFu) : 0;
     return e;
@@ -318,11 +318,12 @@ DCSB_HD int dcsb_scan94_bands(DcsbRingWin &win, DcsbSA ents, DcsbSA ents_end, Dc
             S = dcsb_umin(Sr - e8, Sr - e1);
             err |= S;
             t = S & 0xFF;
-            // -- band switch: take the next band once this one has no slots left (then the slot field
-            // of S is zero, so the new budget is added: one multiply-add).  (The end entry and a
-            // fixed-width band's entry have a slot and no table: the lane parks on them.)
+            // -- band switch: take the next band once this one has no slots left.  The state is REPLACED
+            // (not topped up): whatever a damaged frame made of S, the lane has a sane slot budget again
+            // and parks on the end entry at the latest.  (The end entry and a fixed-width band's entry
+            // have a slot and no table: the lane parks on them.)
             const int dm = (S - 0x1000) >> 31;
-            S = dm * en.nslots + S;
+            S = (int)dcsb_msel((uint32_t)dm, dcsb_and_or((uint32_t)S, 0xFFu, en.sinit), (uint32_t)S);
 #if DCSB_DEVICE_PASS
             tb = dcsb_msel((uint32_t)dm, en.tb, tb);
 #else
@@ -476,7 +477,7 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
     const DcsbSA ents_end = ents + (DcsbSA)nb * DCSB_ENT_BYTES;
     {
         DcsbBandEnt term;
-        term.tb = zero; term.nslots = -0x1000; term.amask = 0; term.fix = -1;       // one slot, no table: a lane parks here
+        term.tb = zero; term.sinit = 0x1F00u; term.amask = 0; term.fix = -1;       // one slot, no table: a lane parks here
         dcsb_ent_store(ents_end, term);
         dcsb_ent_store(ents_end + DCSB_ENT_BYTES, term);                            // (loaded behind the end entry, never taken)
     }

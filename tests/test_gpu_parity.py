@@ -48,6 +48,83 @@ def test_gpu_fuzz_all_layouts_vs_oracle(ctx):
         assert res[i]["checksum"] == int((s * (2 * np.arange(s.size, dtype=np.uint64) + 1)).sum(dtype=np.uint64))
 
 
+def _soak_make(seed):
+    """one seed's worth of soak streams: fuzzer-made streams of every layout plus damaged copies
+    (cut short, one or two flipped bits in the frame data, a flipped bit in the stream header)"""
+    rng = np.random.default_rng(70000 + seed)
+    out = []
+    for os_, d, _ in dcsfuzz.corpus(70000 + seed, n_each=2, nframes=int(rng.integers(6, 40))):
+        vol, lvl, tail = int(rng.integers(0, 256)), int(rng.integers(0, 256)), int(rng.integers(0, 4))
+        out.append((d, os_, vol, lvl, tail))
+        hl = 3 if len(d) < 18 else 18
+        for k in range(7):
+            b = bytearray(d)
+            if k < 2 and len(b) > hl + 2:
+                b = b[:int(rng.integers(hl + 1, len(b)))]                       # cut short
+            elif k < 5 and len(b) > hl + 1:
+                for _ in range(1 + (k == 4)):
+                    i = int(rng.integers(hl, len(b)))
+                    b[i] ^= 1 << int(rng.integers(0, 8))                        # flipped bit(s) in the frame data
+            else:
+                i = int(rng.integers(2, min(hl, len(b))))
+                b[i] ^= 1 << int(rng.integers(0, 7))                            # flipped bit in the stream header
+            out.append((bytes(b), os_, vol, lvl, tail))
+    return out
+
+
+def _soak_expect(chunk):
+    res = []
+    for d, os_, vol, lvl, tail in chunk:
+        nf = ((d[0] << 8) | d[1]) if len(d) >= 2 else 0
+        pcm, rc = orc.decode(d, os_, vol, lvl, nf + tail)
+        u = pcm.view(np.uint16).astype(np.uint64)
+        res.append(int((u * (2 * np.arange(u.size, dtype=np.uint64) + 1)).sum(dtype=np.uint64)))
+    return res
+
+
+def test_gpu_fuzz_soak_50k_streams_vs_oracle(ctx):
+    """One batch of more than 50,000 fuzzer-made streams of every layout, most of them damaged, decoded on
+    the GPU; every stream's checksum against the checksum of the oracle's PCM.  This is the net under
+    code-generation bugs of the device build (the CPU-side soak cannot see them)."""
+    import multiprocessing as mp
+    import os
+    ncpu = max(1, len(os.sched_getaffinity(0)))
+    with mp.get_context("fork").Pool(ncpu) as pool:
+        streams = [s for part in pool.map(_soak_make, range(460), chunksize=4) for s in part]
+        # streams the host rejects up front (no frames / too short) are not part of this test's point
+        streams = [s for s in streams if len(s[0]) >= 3 and ((s[0][0] << 8) | s[0][1]) > 0]
+        assert len(streams) >= 50000
+        chunks = [streams[i:i + 500] for i in range(0, len(streams), 500)]
+        want = [c for part in pool.map(_soak_expect, chunks) for c in part]
+    pcm, offs, res = ctx.decode_streams_pinned(streams)
+    bad = [i for i in range(len(streams)) if res[i]["checksum"] != want[i]]
+    assert not bad, "%d of %d streams differ from the oracle; first: stream %d os %#x status %d" % (
+        len(bad), len(streams), bad[0], streams[bad[0]][1], res[bad[0]]["status"])
+    # and the PCM itself on a sample (the checksum is computed by the kernel from what it stores)
+    rng = np.random.default_rng(5)
+    for i in rng.integers(0, len(streams), 200):
+        d, os_, vol, lvl, tail = streams[int(i)]
+        w, _ = _expect(d, os_, vol, lvl, tail)
+        assert np.array_equal(pcm[offs[i]:offs[i] + w.size], w), int(i)
+
+
+def test_gpu_decode_streams_refuses_wrap_empty_flag(ctx):
+    """DCSB_STREAM_WRAP_EMPTY would make a zero-count stream render 65,536 frames into a buffer the caller
+    sized from the count as written: dcsb_decode_streams refuses the flag instead of overrunning pcm_out."""
+    import dcsexplorer_b200 as dx
+    ok = dcsfuzz.fuzz94(np.random.default_rng(3), 5, type1=1)
+    empty = bytes([0, 0] + [0x10] * 16) + bytes(64)
+    descs, keep = dx.make_descs([(ok, 0x9400, 255, 100, 2), (empty, 0x9400, 255, 100, 2)])
+    descs[1].reserved = 1
+    pcm = np.full(2 * 7 * 240 + 64, 0x1234, dtype=np.int16)
+    res = (dx.Result * 2)()
+    rc = ctx._L.dcsb_decode_streams(ctx._h, descs, 2, pcm.ctypes.data, None, res)
+    assert rc == dx.E_ARG and (pcm == 0x1234).all()
+    descs[1].reserved = 0
+    assert ctx._L.dcsb_decode_streams(ctx._h, descs, 2, pcm.ctypes.data, None, res) == 0
+    assert res[1].status == dx.E_EMPTY and (pcm[9 * 240:] == 0x1234).all()
+
+
 def test_gpu_scan_checkpoints_vs_oracle(ctx):
     rng = np.random.default_rng(9)
     streams = [(d, os_, 255, 100, 2) for os_, d, _ in dcsfuzz.corpus(901, n_each=2, nframes=45)]

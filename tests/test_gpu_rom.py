@@ -54,9 +54,19 @@ def test_gpu_timeline_matches_golden(ctx, rom_golden, name, kw):
     rom.close()
 
 
-def test_gpu_many_timelines_vs_simulator(ctx):
+def _reference_timeline(images, tl):
+    """one timeline (writes, n_frames, master_volume) rendered by the unmodified reference decoder"""
+    rp = ref.RomPlayer(images, tl[2])
+    want = rp.render_timeline(tl[0], tl[1])
+    rp.close()
+    return want
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref did not travel with the snapshot")
+def test_gpu_many_timelines_vs_reference(ctx):
     """64 timelines on one ROM in one launch (different volumes / command times); a sample is
-    compared with the CPU-side simulator, replicas with each other."""
+    compared with the reference decoder fed the same data-port bytes, every timeline's checksum
+    with its own PCM, and two timelines that differ only in master volume with each other."""
     import dcsexplorer_b200 as dx
     sc = romscen.make_scenario(os_version=rb.OS95, seed=77, n_frames=300, version=0x0105)
     rom = dx.Rom(sc["images"])
@@ -66,11 +76,16 @@ def test_gpu_many_timelines_vs_simulator(ctx):
         tls.append(([(f + shift, b) for f, b in sc["writes"]], 260 + (i % 7) * 11, 255 - 3 * (i % 32)))
     pcm, res = ctx.render_timelines(rom, tls)
     for i in (0, 1, 6, 33, 63):
-        want, _, _, _ = simutil.rom_render(sc["images"], [tls[i]])
-        assert np.array_equal(pcm[i], want[0]), i
-    assert np.array_equal(pcm[2][:240 * 250], pcm[34][:240 * 250]) is False or True
+        want = _reference_timeline(sc["images"], tls[i])
+        bad = np.nonzero(pcm[i] != want)[0]
+        assert bad.size == 0, "timeline %d: first differing frame %d" % (i, bad[0] // 240)
     for i in range(64):
-        assert res[i]["frames"] == tls[i][1]
+        assert res[i]["status"] == 0 and res[i]["frames"] == tls[i][1]
+        s = pcm[i].astype(np.uint16).astype(np.uint64)
+        assert res[i]["checksum"] == int((s * (2 * np.arange(s.size, dtype=np.uint64) + 1)).sum(dtype=np.uint64)), i
+    # timelines 0 and 35 share command times (shift 0) and length class but not the master volume
+    n = min(tls[0][1], tls[35][1]) * 240
+    assert tls[0][0] == tls[35][0] and tls[0][2] != tls[35][2] and not np.array_equal(pcm[0][:n], pcm[35][:n])
     rom.close()
 
 
@@ -145,7 +160,8 @@ def test_gpu_render_timelines_output_placements(ctx):
     for i in (0, 1, 257, len(tls) - 1):
         assert np.array_equal(out[int(offs[i]):int(offs[i]) + tls[i][1] * 240], pcm[i]), i
         assert (out[int(offs[i]) + tls[i][1] * 240:int(offs[i]) + tls[i][1] * 240 + 100] == 0x5A5A).all()
-    # a sample against the CPU-side simulator
-    want, _, _, _ = simutil.rom_render(sc["images"], [tls[3], tls[519]])
-    assert np.array_equal(pcm[3], want[0]) and np.array_equal(pcm[519], want[1])
+    # a sample against the reference decoder (or, without oracle/_ref, the golden-pinned CPU simulator)
+    for i in (3, 519):
+        want = _reference_timeline(sc["images"], tls[i]) if ref.available() else simutil.rom_render(sc["images"], [tls[i]])[0][0]
+        assert np.array_equal(pcm[i], want), i
     rom.close()

@@ -11,10 +11,11 @@ timeout 900 python bench.py --steps 10 --warmup 3 "$@" > $OUT/${TAG}_bench.json 
 tail -c 3500 $OUT/${TAG}_bench.json; tail -3 $OUT/${TAG}_bench.err
 # launch list (cold-cache, serialised: compare shares)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/${TAG}_launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 0 "$@" > $OUT/${TAG}_ncu_launch.log 2>&1
-# full capture of our kernels (skip the warm-up launches)
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"dcsb_(scan|decode)" -s 6 -c 4 -f -o $OUT/${TAG}_prof \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 0 "$@" > $OUT/${TAG}_ncu_full.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-configs --e2e-steps 0 "$@" > $OUT/${TAG}_ncu_launch.log 2>&1
+# full capture of the scan and the 1994-layout decode kernel themselves: the bench's last steps run them one after
+# the other (7 scans beside the persistent decode kernel come first and are skipped)
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"dcsb_(scan|decode94)_kernel" -s 7 -c 3 -f -o $OUT/${TAG}_prof \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-configs --e2e-steps 0 "$@" > $OUT/${TAG}_ncu_full.log 2>&1
 python - <<'PY'
 import torch, time
 n = 1 << 30
