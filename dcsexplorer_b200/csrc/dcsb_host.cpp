@@ -213,16 +213,30 @@ void dcsb_set_num_sms(int n) { if (n > 0) g_num_sms = n; }
 // shared memory, leaving room for a decode CTA beside it) while the groups fit one wave, more
 // warps per CTA (sharing the 96 KB length table) when there are more groups than that.
 // concurrent = streams of all the scans launched side by side (0 = this launch alone).
+// More groups than two waves' worth: the rings are given up (DcsbWinT<false>: stream words through L1) and a
+// CTA holds up to eight warps -- in that regime an SM's throughput counts, not a warp's latency.
+bool dcsb_scan_direct(int nstreams, int concurrent)
+{
+    if (concurrent < nstreams) concurrent = nstreams;
+    if (const char *e = getenv("DCSB_SCAN_DIRECT")) return atoi(e) != 0;      // tuning override
+    return (concurrent + 31) / 32 > DCSB_SCAN_MAXWARPS * dcsb_num_sms();
+}
+
 void dcsb_scan_shape(int nstreams, int concurrent, int *warps, int *grid)
 {
     if (concurrent < nstreams) concurrent = nstreams;
     const int sms = dcsb_num_sms();
     const int groups = (nstreams + 31) / 32, cgroups = (concurrent + 31) / 32;
+    const bool direct = dcsb_scan_direct(nstreams, concurrent);
+    const int maxw = direct ? DCSB_SCAN_MAXWARPS_DIRECT : DCSB_SCAN_MAXWARPS;
+    // (measured on 131,072 one-second streams: rings, 2 warps per CTA 13.4 ms; direct, 4 warps 10.9 ms, 8 warps
+    // 20.8 ms -- with eight warps' band entries in shared memory L1 is too small for the lanes' lines)
+    const int defw = direct ? 4 : DCSB_SCAN_MAXWARPS;
     int w = (cgroups + sms - 1) / sms;
-    w = w > DCSB_SCAN_MAXWARPS ? DCSB_SCAN_MAXWARPS : (w < 1 ? 1 : w);
+    w = w > defw ? defw : (w < 1 ? 1 : w);
     if (const char *e = getenv("DCSB_SCAN_WARPS")) {         // tuning override
         const int v = atoi(e);
-        if (v >= 1 && v <= DCSB_SCAN_MAXWARPS) w = v;
+        if (v >= 1 && v <= maxw) w = v;
     }
     int g = (groups + w - 1) / w;
     *warps = w;

@@ -104,6 +104,9 @@ struct DcsbScanOut {
 
 void dcsb_build_tables(DcsbTables *t);   // host
 #define DCSB_SCAN_MAXWARPS 2              // most lock-step warps (32 streams, 1 KB ring each) a scan CTA holds
+#define DCSB_SCAN_MAXWARPS_DIRECT 8       // ... when the stream bytes are read from global memory instead (no rings)
+// multi-wave batches (more 32-stream groups than 2 per SM) read their streams straight from global memory
+bool dcsb_scan_direct(int nstreams, int concurrent);
 // SM count of the device the context runs on (cudaDevAttrMultiProcessorCount; 148 on a B200): sizes the
 // scan grid and the persistent decode grid
 int dcsb_num_sms();

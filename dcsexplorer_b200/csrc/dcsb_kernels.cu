@@ -47,12 +47,16 @@ __device__ __forceinline__ void dcsb_load_lut(uint16_t *s_lut, const DcsbTables 
 #define DCSB_SCAN_LUT_BYTES ((DCSB_LUT_WORDS * 2 + 15) & ~15)
 #define DCSB_SCAN_SMALL (DCSB_SCAN_LUT_BYTES + DCSB_DTAB_WORDS * 2 + 16)
 #define DCSB_SCAN_ENT_STRIDE (19u * 16u)        // 18 entries + 16 bytes: lanes start 12 banks apart, LDS.128 conflict-free
-#define DCSB_SCAN_WARP_BYTES (32u * DCSB_RING_BYTES + 32u * DCSB_SCAN_ENT_STRIDE)
-#define DCSB_SCAN_SMEM(warps) (16384u + DCSB_TX_BYTES + (warps) * DCSB_SCAN_WARP_BYTES)
+#define DCSB_SCAN_WARP_BYTES(ring) ((ring ? 32u * DCSB_RING_BYTES : 0u) + 32u * DCSB_SCAN_ENT_STRIDE)
+#define DCSB_SCAN_SMEM(warps, ring) (16384u + DCSB_TX_BYTES + (warps) * DCSB_SCAN_WARP_BYTES(ring))
 static_assert(DCSB_SCAN_SMALL <= 8192, "the small tables must fit the smaller alignment gap");
-static_assert(DCSB_SCAN_SMEM(DCSB_SCAN_MAXWARPS) <= 232448, "scan CTA exceeds the shared memory of an SM");
+static_assert(DCSB_SCAN_SMEM(DCSB_SCAN_MAXWARPS, 1) <= 232448, "scan CTA exceeds the shared memory of an SM");
+static_assert(DCSB_SCAN_SMEM(DCSB_SCAN_MAXWARPS_DIRECT, 0) <= 232448, "scan CTA exceeds the shared memory of an SM");
 
-__global__ void __launch_bounds__(DCSB_SCAN_MAXWARPS * 32, 1)
+// RING: the lanes' stream bytes staged in shared-memory rings (single wave) / read from global memory
+// through L1 (many waves: more warps per SM), see DcsbWinT.
+template <bool RING>
+__global__ void __launch_bounds__((RING ? DCSB_SCAN_MAXWARPS : DCSB_SCAN_MAXWARPS_DIRECT) * 32, 1)
 dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restrict__ streams, const uint32_t *__restrict__ order,
                  int nstreams, const DcsbTables *__restrict__ tab, DcsbScanOut out, uint32_t f0, uint32_t f1)
 {
@@ -63,7 +67,7 @@ dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restri
     const uint32_t tx_off = tx - s_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
     const uint32_t rings_off = tx_off + DCSB_TX_BYTES;                          // 16 KB aligned in the shared window
-    const uint32_t ents_off = rings_off + (uint32_t)warps * 32u * DCSB_RING_BYTES;
+    const uint32_t ents_off = rings_off + (RING ? (uint32_t)warps * 32u * DCSB_RING_BYTES : 0u);
     const uint32_t small_off = tx_off >= DCSB_SCAN_SMALL ? 0u : ents_off + (uint32_t)warps * 32u * DCSB_SCAN_ENT_STRIDE;
     uint16_t *s_lut = reinterpret_cast<uint16_t *>(sm8 + small_off);
     uint16_t *s_dtab = reinterpret_cast<uint16_t *>(sm8 + small_off + DCSB_SCAN_LUT_BYTES);
@@ -101,7 +105,7 @@ dcsb_scan_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restri
             si = -1;
         }
         __syncwarp();
-        dcsb_scan94_stream(slab, streams, si, tab, s_lut, txb, s_dtab, ring, ents, zero, out, f0, f1);
+        dcsb_scan94_stream<RING>(slab, streams, si, tab, s_lut, txb, s_dtab, ring, ents, zero, out, f0, f1);
         __syncwarp();
     }
 }
@@ -408,21 +412,31 @@ cudaError_t dcsb_launch_gate(DcsbScanOut scan, int ctas, cudaStream_t st)
     return cudaGetLastError();
 }
 
+template <bool RING>
+static cudaError_t launch_scan_t(const uint8_t *slab, const DcsbStreamRec *streams, const uint32_t *order, int nstreams, int warps, int grid,
+                                 const DcsbTables *tables, DcsbScanOut out, cudaStream_t st, uint32_t f0, uint32_t f1)
+{
+    const size_t smem = DCSB_SCAN_SMEM((size_t)warps, RING);
+    cudaError_t e = cudaFuncSetAttribute(dcsb_scan_kernel<RING>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)DCSB_SCAN_SMEM(RING ? DCSB_SCAN_MAXWARPS : DCSB_SCAN_MAXWARPS_DIRECT, RING));
+    if (e != cudaSuccess) return e;
+    // keep the SM at its largest shared-memory split, so that CTAs of the other kernel can join
+    // this one (the split only changes on an idle SM)
+    e = cudaFuncSetAttribute(dcsb_scan_kernel<RING>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             RING ? (int)cudaSharedmemCarveoutMaxShared : (int)((smem + 1024) * 100 / (228 * 1024) + 4));
+    if (e != cudaSuccess) return e;
+    dcsb_scan_kernel<RING><<<grid, warps * 32, smem, st>>>(slab, streams, order, nstreams, tables, out, f0, f1);
+    return cudaGetLastError();
+}
+
 cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, const uint32_t *order, int nstreams, int concurrent,
                              const DcsbTables *tables, DcsbScanOut out, cudaStream_t st, uint32_t f0, uint32_t f1)
 {
     if (nstreams <= 0) return cudaSuccess;
     int warps, grid;
     scan_shape(nstreams, concurrent, warps, grid);
-    const size_t smem = DCSB_SCAN_SMEM((size_t)warps);
-    cudaError_t e = cudaFuncSetAttribute(dcsb_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DCSB_SCAN_SMEM(DCSB_SCAN_MAXWARPS));
-    if (e != cudaSuccess) return e;
-    // keep the SM at its largest shared-memory split, so that CTAs of the other kernel can join
-    // this one (the split only changes on an idle SM)
-    e = cudaFuncSetAttribute(dcsb_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    dcsb_scan_kernel<<<grid, warps * 32, smem, st>>>(slab, streams, order, nstreams, tables, out, f0, f1);
-    return cudaGetLastError();
+    if (dcsb_scan_direct(nstreams, concurrent)) return launch_scan_t<false>(slab, streams, order, nstreams, warps, grid, tables, out, st, f0, f1);
+    return launch_scan_t<true>(slab, streams, order, nstreams, warps, grid, tables, out, st, f0, f1);
 }
 
 static cudaError_t launch_decode93(const uint8_t *slab, const DcsbStreamRec *streams, const DcsbTile *tiles,

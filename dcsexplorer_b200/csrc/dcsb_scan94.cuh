@@ -59,6 +59,7 @@ DCSB_HD DcsbSA dcsb_sa_or(DcsbSA base, uint32_t off) { return base + off; }
 #endif
 typedef DcsbSA DcsbTxBase;
 typedef DcsbSA DcsbRingPtr;
+template <bool RING> struct DcsbWinT;
 // (a & b) | c in one LOP3
 DCSB_HD uint32_t dcsb_and_or(uint32_t a, uint32_t b, uint32_t c)
 {
@@ -102,9 +103,16 @@ DCSB_HD void dcsb_ent_store(DcsbSA a, const DcsbBandEnt &e)
 #endif
 }
 
-// Bit window over the ring: w0:w1 = 64 stream bits (big-endian order), s = bit offset of the next
-// bit inside them, wa = byte offset (from chunk 0, cumulative) of the next word the ring hands out.
-struct DcsbRingWin {
+// Bit window over the stream: w0:w1 = 64 stream bits (big-endian order), s = bit offset of the next
+// bit inside them, wa = byte offset (from chunk 0, cumulative) of the next word to take.
+// RING = true: the words come from the lane's shared-memory ring (cp.async keeps it a frame ahead):
+// the single-wave case, where the scan is as long as its slowest warp's dependent chain and a load's
+// latency sits on it.  RING = false: the words are read from global memory through L1 (a lane reads
+// its stream word by word, so 31 of 32 loads hit the line it has already fetched; the frame's next lines
+// are prefetched at the frame start): no 32 KB of rings per warp, so many more warps fit an SM -- the
+// multi-wave case, where what counts is how many warps an SM keeps in flight.
+template <bool RING>
+struct DcsbWinT {
     uint32_t w0, w1;
     uint32_t s;
     uint32_t wa;
@@ -114,11 +122,31 @@ struct DcsbRingWin {
     const uint8_t *g;       // global address of chunk 0 (16-byte aligned)
     DcsbRingPtr ring;       // this stream's ring (1 KB aligned in the shared window)
 
-    DCSB_HD uint32_t ring_word(uint32_t off) const { return dcsb_lds32(dcsb_sa_or(ring, off & (DCSB_RING_BYTES - 1))); }
+    DCSB_HD uint32_t ring_word(uint32_t off) const
+    {
+        if (RING) return dcsb_lds32(dcsb_sa_or(ring, off & (DCSB_RING_BYTES - 1)));
+#if DCSB_DEVICE_PASS
+        uint32_t v;
+        asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(g + off));
+        return v;
+#else
+        uint32_t v;
+        memcpy(&v, g + off, 4);
+        return v;
+#endif
+    }
     // issue the chunks up to DCSB_RING_CHUNKS - 1 ahead of the window, then make sure everything
     // the next frame can touch has landed.  Call at a frame start only (s < 32).
     DCSB_HD void topup()
     {
+        if (!RING) {
+#if DCSB_DEVICE_PASS
+            // the two lines behind the one the window is in: what an average frame reaches
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(g + wa + 128u));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(g + wa + 256u));
+#endif
+            return;
+        }
         const uint32_t cc = (wa - 8u) >> 4;                        // chunk holding w0
         uint32_t target = cc + DCSB_RING_CHUNKS - 1u;
         if (target > limit) target = limit;
@@ -277,8 +305,8 @@ DCSB_HD uint32_t dcsb_msel(uint32_t m, uint32_t a, uint32_t b)
 //   t         for the next lookup comes from S BEFORE the switch (the switch keeps the low byte)
 // Four iterations per exit vote and fixed-band check (eight measured the same: fewer votes, more idle iterations at the frame end): a lane that is through parks on its end entry.
 #define DCSB_SCAN_UNROLL 4
-template <bool FIX>
-DCSB_HD int dcsb_scan94_bands(DcsbRingWin &win, DcsbSA ents, DcsbSA ents_end, DcsbSA zero, bool run)
+template <bool FIX, bool RING>
+DCSB_HD int dcsb_scan94_bands(DcsbWinT<RING> &win, DcsbSA ents, DcsbSA ents_end, DcsbSA zero, bool run)
 {
     DcsbSA ptr = run ? ents : ents_end;
     DcsbSA tb = zero;
@@ -295,9 +323,9 @@ DCSB_HD int dcsb_scan94_bands(DcsbRingWin &win, DcsbSA ents, DcsbSA ents_end, Dc
         for (int u = 0; u < DCSB_SCAN_UNROLL; ++u) {
             // (the ring word a refill would take and the next band entry: addresses off the chain)
 #if DCSB_DEVICE_PASS
-            const uint32_t ld = dcsb_lds32(dcsb_and_or(wa, DCSB_RING_BYTES - 1, win.ring));
+            const uint32_t ld = RING ? dcsb_lds32(dcsb_and_or(wa, DCSB_RING_BYTES - 1, win.ring)) : win.ring_word(wa);
 #else
-            const uint32_t ld = dcsb_lds32(win.ring + (wa & (DCSB_RING_BYTES - 1)));
+            const uint32_t ld = win.ring_word(wa);
 #endif
             const DcsbBandEnt en = dcsb_ent_load(ptr);
             // -- one table step (a no-op for a lane without table: the zero word)
@@ -414,6 +442,7 @@ DCSB_HD void dcsb_hdr_apply94(int b, int delta, int nb, uint32_t dsel, uint32_t 
 // the later slices are still being scanned.
 // Called by all lanes of a warp together, lane = stream (si < 0: idle lane).
 // ents: the lane's 18 band entries (16 bands, the end entry, one more that is only loaded); zero: address of a zero word in shared memory.
+template <bool RING>
 DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *streams, int si, const DcsbTables *tab,
                                 const uint16_t *lut, DcsbTxBase tx, const uint16_t *dtab, DcsbRingPtr ring, DcsbSA ents, DcsbSA zero,
                                 const DcsbScanOut &out, uint32_t f0 = 0, uint32_t f1 = 0xFFFFFFFFu)
@@ -434,7 +463,7 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
     const uint32_t dbytes = s.nbytes > 2u + s.hdr_len ? s.nbytes - 2u - s.hdr_len : 0u;   // (short streams have nframes == 0)
     const uint32_t nbits = dbytes * 8u;
     const uint64_t start = s.data_off + 2 + s.hdr_len;
-    DcsbRingWin win;
+    DcsbWinT<RING> win;
     win.g = slab + (start & ~15ull);
     win.bias = (uint32_t)(start & 15) * 8u;
     win.ring = ring;
@@ -538,8 +567,8 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
         if (run) out.hdrbits[s.frame_base + f] = (uint16_t)(hpos - pos);
         // ---- bands: lengths only
         int err;
-        if (DCSB_ANY(run && fixmask != 0)) err = dcsb_scan94_bands<true>(win, ents, ents_end, zero, run);
-        else err = dcsb_scan94_bands<false>(win, ents, ents_end, zero, run);
+        if (DCSB_ANY(run && fixmask != 0)) err = dcsb_scan94_bands<true, RING>(win, ents, ents_end, zero, run);
+        else err = dcsb_scan94_bands<false, RING>(win, ents, ents_end, zero, run);
         if (run) {
             pos = win.pos();
             int sb = 99;
@@ -570,7 +599,7 @@ DCSB_HD void dcsb_scan94_stream(const uint8_t *slab, const DcsbStreamRec *stream
         }
     }
 #if DCSB_DEVICE_PASS
-    asm volatile("cp.async.wait_group 0;" ::: "memory");    // nothing in flight when the ring is reused
+    if (RING) asm volatile("cp.async.wait_group 0;" ::: "memory");    // nothing in flight when the ring is reused
 #endif
     if (!mine) return;
     // end checkpoint: band types after the last decodable frame (decode lanes read bt[f + 1]).

@@ -50,7 +50,11 @@ static int sim_decode_streams(const dcsb_stream_desc *descs, size_t n, int16_t *
     for (uint32_t fa = 0; fa == 0 || fa < max_out; fa += slice_frames ? slice_frames : 0xFFFFFFFFu) {
         const uint32_t fb = slice_frames && fa + slice_frames < max_out ? fa + slice_frames : 0xFFFFFFFFu;
         for (size_t i = 0; i < n; ++i)                                   // K1 grid
-            if (p.recs[i].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, (DcsbSA)tab.tx, dtab, (DcsbSA)ring.data(), (DcsbSA)ents, (DcsbSA)zero_word, so, fa, fb);
+            if (p.recs[i].fmt == DCSB_FMT_94) {
+                // both staging variants of the scan (ring in shared memory / straight from global memory): alternate by stream
+                if (i & 1) dcsb_scan94_stream<false>(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, (DcsbSA)tab.tx, dtab, (DcsbSA)ring.data(), (DcsbSA)ents, (DcsbSA)zero_word, so, fa, fb);
+                else dcsb_scan94_stream<true>(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, (DcsbSA)tab.tx, dtab, (DcsbSA)ring.data(), (DcsbSA)ents, (DcsbSA)zero_word, so, fa, fb);
+            }
             else dcsb_scan_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, so, fa, fb);
         std::vector<DcsbTile> t94, t93;
         if (slice_frames) dcsb_build_tiles(&p, fa, fb, &t94, &t93);
@@ -169,7 +173,7 @@ extern "C" int hostsim_rom_render(const uint8_t *const *imgs, const size_t *size
     static uint16_t dtab[DCSB_DTAB_WORDS];
     for (int i = 0; i < DCSB_DTAB_WORDS; ++i) dtab[i] = (uint16_t)dcsb_dtab_entry(tab.lut, i);
     for (size_t i = 0; i < ns; ++i) {
-        if (p.recs[i].fmt == DCSB_FMT_94) dcsb_scan94_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, (DcsbSA)tab.tx, dtab, (DcsbSA)ring.data(), (DcsbSA)ents, (DcsbSA)zero_word, so);
+        if (p.recs[i].fmt == DCSB_FMT_94) dcsb_scan94_stream<true>(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, (DcsbSA)tab.tx, dtab, (DcsbSA)ring.data(), (DcsbSA)ents, (DcsbSA)zero_word, so);
         else dcsb_scan_stream(slab.data(), p.recs.data(), (int)i, &tab, tab.lut, so);
         rom.streams[i].status = p.host_status[i] ? p.host_status[i] : status[i];
         rom.streams[i].nplay = p.host_status[i] ? 0 : nplay[i];

@@ -108,6 +108,32 @@ def test_gpu_fuzz_soak_50k_streams_vs_oracle(ctx):
         assert np.array_equal(pcm[offs[i]:offs[i] + w.size], w), int(i)
 
 
+def test_gpu_scan_direct_variant_vs_oracle(ctx, monkeypatch):
+    """The scan variant multi-wave batches use (stream words read from global memory through L1 instead
+    of shared-memory rings, up to eight warps per CTA), forced onto a small batch: same checkpoints, same
+    PCM as the oracle -- valid streams of every 1994 flavour, damaged ones, and the other layouts riding
+    along in the same warps."""
+    monkeypatch.setenv("DCSB_SCAN_DIRECT", "1")
+    monkeypatch.setenv("DCSB_SCAN_WARPS", "8")
+    streams = []
+    for seed in range(12):
+        streams += [s for s in _soak_make(900 + seed) if len(s[0]) >= 3 and ((s[0][0] << 8) | s[0][1]) > 0]
+    pcm, offs, res = ctx.decode_streams(streams)
+    for i, (d, os_, vol, lvl, tail) in enumerate(streams):
+        want, rc = _expect(d, os_, vol, lvl, tail)
+        assert np.array_equal(pcm[offs[i]:offs[i] + want.size], want), (i, hex(os_))
+    b = ctx.batch(streams[:300])
+    b.decode()
+    bres = b.results()
+    for i, (d, os_, *_r) in enumerate(streams[:300]):
+        rc, obp, obt, ostop = orc.scan(d, os_)
+        nf = (d[0] << 8) | d[1]
+        if rc == nf and bres[i]["status"] == 0:         # every frame decodable: compare the checkpoints
+            bp, bt = b.read_scan(i, nf)
+            assert np.array_equal(bp, obp[:nf]) and np.array_equal(bt, obt[:nf]), i
+    b.close()
+
+
 def test_gpu_decode_streams_refuses_wrap_empty_flag(ctx):
     """DCSB_STREAM_WRAP_EMPTY would make a zero-count stream render 65,536 frames into a buffer the caller
     sized from the count as written: dcsb_decode_streams refuses the flag instead of overrunning pcm_out."""
