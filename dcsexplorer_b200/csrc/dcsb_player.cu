@@ -54,6 +54,18 @@ extern "C" int dcsb_rom_load_zip(dcsb_rom *rom, const char *zip_path, const char
 extern "C" int dcsb_rom_check(dcsb_rom *rom) { return rom ? rom->check() : 2; }
 extern "C" const char *dcsb_rom_last_error(const dcsb_rom *rom) { return rom ? rom->err.c_str() : "no rom"; }
 
+extern "C" size_t dcsb_rom_zip_files(const dcsb_rom *rom, dcsb_zip_file *files, size_t max)
+{
+    if (!rom) return 0;
+    for (size_t i = 0; i < rom->zip_files.size() && i < max && files; ++i) {
+        files[i].name = rom->zip_files[i].name.c_str();
+        files[i].data = rom->zip_files[i].data.data();
+        files[i].size = rom->zip_files[i].data.size();
+        files[i].chip_number = i < rom->zip_chip.size() ? rom->zip_chip[i] : -1;
+    }
+    return rom->zip_files.size();
+}
+
 extern "C" int dcsb_rom_get_info(const dcsb_rom *rom, dcsb_rom_info *info)
 {
     if (!rom || !info) return DCSB_E_ARG;
@@ -240,8 +252,52 @@ struct dcsb_player {
     DcsbSchedFrame prev_frame{ 0, 0, 8, 0, 0 };
     bool have_prev = false;
     size_t host_read = 0;
-    dcsb_player(dcsb_ctx *c, dcsb_rom *r) : ctx(c), rom(r), seq(r) {}
+    // look-ahead (dcsb_player_set_lookahead): frames are rendered `lookahead` at a time and handed out from
+    // `ahead`; `snap*` is the decoder state at the start of that block, so that an input arriving in the middle
+    // takes effect at the frame it arrives at (the block's unconsumed frames are dropped: state restored, the
+    // consumed frames replayed on the host sequencer -- about 200 ns each --, the rest rendered anew)
+    uint32_t lookahead = 0;
+    std::vector<int16_t> ahead;
+    std::vector<uint8_t> ahead_playing;             // per pre-rendered frame: channels with a stream playing after it
+    uint32_t ahead_n = 0, ahead_pos = 0;
+    DcsbSequencer snap;
+    std::vector<DcsbSchedEntry> snap_prev_entries;
+    DcsbSchedFrame snap_prev_frame{ 0, 0, 8, 0, 0 };
+    bool snap_have_prev = false;
+    uint8_t snap_playing = 0;
+    uint64_t served = 0;                            // frames handed out so far
+    size_t host_visible = 0;                        // host bytes of frames handed out (and of inputs taken) so far
+    dcsb_player(dcsb_ctx *c, dcsb_rom *r) : ctx(c), rom(r), seq(r), snap(r) {}
 };
+
+static uint8_t playing_mask(const DcsbSequencer &q)
+{
+    uint8_t m = 0;
+    for (int ch = 0; ch < DCSB_MAX_CHANNELS; ++ch) m |= (uint8_t)((q.stream_playing(ch) ? 1 : 0) << ch);
+    return m;
+}
+
+// bring the sequencer back to the frame the caller has consumed up to (drops what was rendered ahead)
+static void player_sync(dcsb_player *p)
+{
+    if (p->ahead_pos < p->ahead_n) {
+        p->seq = p->snap;
+        p->prev_entries = p->snap_prev_entries;
+        p->prev_frame = p->snap_prev_frame;
+        p->have_prev = p->snap_have_prev;
+        std::vector<DcsbSchedFrame> frames;
+        std::vector<DcsbSchedEntry> entries;
+        for (uint32_t f = 0; f < p->ahead_pos; ++f) p->seq.frame(frames, entries);
+        if (!frames.empty()) {
+            const DcsbSchedFrame last = frames.back();
+            p->prev_entries.assign(entries.begin() + last.first_entry, entries.begin() + last.first_entry + last.n_entries);
+            p->prev_frame = last;
+            p->have_prev = true;
+        }
+    }
+    p->ahead_n = p->ahead_pos = 0;
+    p->host_visible = p->seq.host_bytes.size();     // the sequencer stands exactly where the caller is
+}
 
 extern "C" int dcsb_player_create(dcsb_ctx *ctx, dcsb_rom *rom, dcsb_player **out)
 {
@@ -264,17 +320,32 @@ extern "C" void dcsb_player_destroy(dcsb_player *p)
     delete p;
 }
 
-extern "C" void dcsb_player_set_master_volume(dcsb_player *p, int vol) { if (p) p->seq.set_master_volume(vol); }
-extern "C" void dcsb_player_write_data_port(dcsb_player *p, uint8_t byte) { if (p) p->seq.write_port(byte); }
-extern "C" void dcsb_player_add_track_command(dcsb_player *p, uint16_t track) { if (p) p->seq.add_track_command(track); }
-extern "C" void dcsb_player_clear_tracks(dcsb_player *p) { if (p) p->seq.clear_tracks(); }
-extern "C" int dcsb_player_is_stream_playing(const dcsb_player *p, int channel) { return p && p->seq.stream_playing(channel) ? 1 : 0; }
+extern "C" int dcsb_player_set_lookahead(dcsb_player *p, uint32_t n_frames)
+{
+    if (!p || n_frames > 4096) return DCSB_E_ARG;
+    player_sync(p);
+    p->lookahead = n_frames;
+    return DCSB_OK;
+}
+
+extern "C" void dcsb_player_set_master_volume(dcsb_player *p, int vol) { if (p) { player_sync(p); p->seq.set_master_volume(vol); p->host_visible = p->seq.host_bytes.size(); } }
+extern "C" void dcsb_player_write_data_port(dcsb_player *p, uint8_t byte) { if (p) { player_sync(p); p->seq.write_port(byte); p->host_visible = p->seq.host_bytes.size(); } }
+extern "C" void dcsb_player_add_track_command(dcsb_player *p, uint16_t track) { if (p) { player_sync(p); p->seq.add_track_command(track); } }
+extern "C" void dcsb_player_clear_tracks(dcsb_player *p) { if (p) { player_sync(p); p->seq.clear_tracks(); } }
+extern "C" int dcsb_player_is_stream_playing(const dcsb_player *p, int channel)
+{
+    if (!p || channel < 0 || channel >= DCSB_MAX_CHANNELS) return 0;
+    if (p->ahead_pos < p->ahead_n)          // the sequencer has run ahead: answer for the frame the caller is at
+        return ((p->ahead_pos ? p->ahead_playing[p->ahead_pos - 1] : p->snap_playing) >> channel) & 1;
+    return p->seq.stream_playing(channel) ? 1 : 0;
+}
 
 extern "C" int dcsb_player_load_audio_stream(dcsb_player *p, int channel, uint32_t stream_address, int mixing_level)
 {
     if (!p || channel < 0 || channel >= DCSB_MAX_CHANNELS) return DCSB_E_ARG;
     if (p->rom->stream_by_addr.find(stream_address & 0xFFFFFFu) == p->rom->stream_by_addr.end())
         return fail(p->ctx, DCSB_E_ARG, "dcsb_player_load_audio_stream: not a stream any track of this ROM plays");
+    player_sync(p);
     p->seq.load_stream(channel, stream_address, mixing_level);
     return DCSB_OK;
 }
@@ -299,17 +370,16 @@ extern "C" int dcsb_player_stream_info(const dcsb_player *p, uint32_t stream_add
 extern "C" size_t dcsb_player_host_bytes(dcsb_player *p, uint8_t *out, size_t max)
 {
     if (!p) return 0;
+    const size_t visible = p->lookahead ? p->host_visible : p->seq.host_bytes.size();
     size_t n = 0;
-    while (p->host_read < p->seq.host_bytes.size() && n < max) out[n++] = p->seq.host_bytes[p->host_read++];
+    while (p->host_read < visible && n < max) out[n++] = p->seq.host_bytes[p->host_read++];
     return n;
 }
 
-extern "C" int dcsb_player_render(dcsb_player *p, uint32_t n_frames, int16_t *pcm_out)
+// n_frames main-loop passes: schedule on the host sequencer, one mix launch, PCM to host memory
+static int player_render_block(dcsb_player *p, uint32_t n_frames, int16_t *pcm_out, uint8_t *playing)
 {
-    if (!p || (!pcm_out && n_frames)) return DCSB_E_ARG;
     dcsb_ctx *ctx = p->ctx;
-    if (n_frames == 0) return DCSB_OK;
-    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     std::vector<DcsbSchedFrame> frames;
     std::vector<DcsbSchedEntry> entries;
     const uint32_t lead = p->have_prev ? 1u : 0u;
@@ -317,7 +387,10 @@ extern "C" int dcsb_player_render(dcsb_player *p, uint32_t n_frames, int16_t *pc
         entries = p->prev_entries;
         frames.push_back(DcsbSchedFrame{ 0, (uint8_t)entries.size(), p->prev_frame.vs, p->prev_frame.flags, 0 });
     }
-    for (uint32_t f = 0; f < n_frames; ++f) p->seq.frame(frames, entries);
+    for (uint32_t f = 0; f < n_frames; ++f) {
+        p->seq.frame(frames, entries);
+        if (playing) playing[f] = playing_mask(p->seq);
+    }
     const DcsbSchedFrame last = frames.back();
     p->prev_entries.assign(entries.begin() + last.first_entry, entries.begin() + last.first_entry + last.n_entries);
     p->prev_frame = last;
@@ -326,6 +399,48 @@ extern "C" int dcsb_player_render(dcsb_player *p, uint32_t n_frames, int16_t *pc
     int rc = render_schedule(ctx, p->rom, p->bufs, frames, entries, first, count, skip, nullptr);
     if (rc != DCSB_OK) return rc;
     CK(cudaMemcpy(pcm_out, (const int16_t *)p->bufs.d_pcm.p + (size_t)lead * 240, (size_t)n_frames * 480, cudaMemcpyDeviceToHost), "D2H pcm");
+    return DCSB_OK;
+}
+
+extern "C" int dcsb_player_render(dcsb_player *p, uint32_t n_frames, int16_t *pcm_out)
+{
+    if (!p || (!pcm_out && n_frames)) return DCSB_E_ARG;
+    dcsb_ctx *ctx = p->ctx;
+    if (n_frames == 0) return DCSB_OK;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (p->lookahead == 0 || n_frames >= p->lookahead) {
+        // nothing to gain from rendering ahead: exactly what is asked for, straight into the caller's buffer
+        player_sync(p);
+        const int rc = player_render_block(p, n_frames, pcm_out, nullptr);
+        if (rc == DCSB_OK) { p->served += n_frames; p->host_visible = p->seq.host_bytes.size(); }
+        return rc;
+    }
+    while (n_frames) {
+        if (p->ahead_pos == p->ahead_n) {
+            p->snap = p->seq;
+            p->snap_prev_entries = p->prev_entries;
+            p->snap_prev_frame = p->prev_frame;
+            p->snap_have_prev = p->have_prev;
+            p->snap_playing = playing_mask(p->seq);
+            p->ahead.resize((size_t)p->lookahead * 240);
+            p->ahead_playing.resize(p->lookahead);
+            p->ahead_n = p->ahead_pos = 0;
+            const int rc = player_render_block(p, p->lookahead, p->ahead.data(), p->ahead_playing.data());
+            if (rc != DCSB_OK) return rc;
+            p->ahead_n = p->lookahead;
+        }
+        const uint32_t k = std::min(n_frames, p->ahead_n - p->ahead_pos);
+        memcpy(pcm_out, p->ahead.data() + (size_t)p->ahead_pos * 240, (size_t)k * 480);
+        p->ahead_pos += k;
+        p->served += k;
+        pcm_out += (size_t)k * 240;
+        n_frames -= k;
+    }
+    // host bytes of the frames handed out so far (a frame's bytes carry its number, DcsbSequencer::to_host)
+    const uint32_t upto = p->snap.frame_no + p->ahead_pos;
+    size_t v = p->host_visible;
+    while (v < p->seq.host_bytes.size() && p->seq.host_byte_frames[v] < upto) ++v;
+    p->host_visible = v;
     return DCSB_OK;
 }
 

@@ -500,7 +500,12 @@ int dcsb_rom_load_zip_impl(dcsb_rom *rom, const char *path, const char *explicit
             (explicit_u2 && strcasecmp(f.name.c_str(), explicit_u2) == 0))
             u2 = (int)i;
     }
-    if (u2 < 0) { rom->err = std::string("No file in ") + path + " could be identified as ROM U2"; return DCSB_ZIP_E_NOU2; }
+    if (u2 < 0) {
+        rom->err = std::string("No file in ") + path + " could be identified as ROM U2";
+        rom->zip_chip.assign(files.size(), -1);
+        rom->zip_files = std::move(files);
+        return DCSB_ZIP_E_NOU2;
+    }
     std::vector<int> used(files.size(), 0);
     used[u2] = 2;
     rom->add(2, files[u2].data.data(), files[u2].data.size());
@@ -516,6 +521,9 @@ int dcsb_rom_load_zip_impl(dcsb_rom *rom, const char *path, const char *explicit
             if (cactus && digit && n == 7 && digit == '6') load = true;     // mislabelled chip in the cc_ sets
             if (load) { rom->add(n, files[i].data.data(), files[i].data.size()); used[i] = n; break; }
         }
+    rom->zip_chip.resize(files.size());
+    for (size_t i = 0; i < files.size(); ++i) rom->zip_chip[i] = used[i] ? used[i] : -1;
+    rom->zip_files = std::move(files);
     return DCSB_ZIP_OK;
 }
 

@@ -43,7 +43,10 @@ struct DcsbStreamFacts {
     uint32_t nbytes = 0;        // stream size: count + header + frame bits, rounded up to a byte
 };
 
+struct DcsbZipEntry { std::string name; std::vector<uint8_t> data; };
 struct dcsb_rom {
+    std::vector<DcsbZipEntry> zip_files;    // the files of the zip last loaded (dcsb_rom_zip_files)
+    std::vector<int> zip_chip;              // ... and the chip each one was taken for (-1: none)
     struct Chip {
         std::vector<uint8_t> bytes;     // image + 64 bytes of 0xFF slack
         uint32_t size = 0, mask = 0;
@@ -150,6 +153,5 @@ private:
 };
 
 // zip container (stored / deflate entries) -> named files; false + err on failure
-struct DcsbZipEntry { std::string name; std::vector<uint8_t> data; };
 bool dcsb_unzip(const char *path, std::vector<DcsbZipEntry> &out, std::string &err);
 int dcsb_rom_load_zip_impl(dcsb_rom *rom, const char *path, const char *explicit_u2);

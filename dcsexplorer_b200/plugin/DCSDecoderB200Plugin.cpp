@@ -27,7 +27,7 @@ class DCSDecoderB200Plugin : public DCSDecoder
 {
 public:
     explicit DCSDecoderB200Plugin(Host *host, int cudaDevice = 0)
-        : DCSDecoder(host), impl(&fwd, cudaDevice, /*chunkFrames*/ 1)
+        : DCSDecoder(host), impl(&fwd, cudaDevice, /*chunkFrames: rendered ahead, inputs still land on their frame*/ 16)
     {
         fwd.host = host;
         for (auto &s : frame) s = 0;

@@ -7,19 +7,24 @@
 // Header-only C++17 over the extern "C" boundary of dcsb200.h; link with -ldcsb200.  Method
 // names, argument meaning and error behaviour follow the reference (file:line in the comments);
 // what differs is stated where it does:
-//   * PCM is rendered on the GPU `chunkFrames` frames (7.68 ms each) at a time.  A byte written
-//     to the data port takes effect at the next chunk boundary; with chunkFrames = 1 the timing
-//     is the reference's (data port drained before every main-loop pass, DCSDecoder.cpp:1625).
-//   * there is no ADSP-2105 boot code to run: HardBoot() / StartSelfTests() report the POST code
-//     like the reference (0x79, status) and go straight to the decoder (its fast-boot mode,
-//     DCSDecoder.cpp:1477-1516); no startup "bong" is synthesised.
+//   * PCM is rendered on the GPU `chunkFrames` frames (7.68 ms each) ahead (dcsb_player_set_lookahead).
+//     The timing of inputs is the reference's all the same (data port drained before every main-loop
+//     pass, DCSDecoder.cpp:1625): a byte written to the data port, a volume change or a track command
+//     takes effect at the frame it arrives at -- what was rendered ahead of it is dropped and rendered anew.
+//   * there is no ADSP-2105 boot code to run, but the boot sequence a client sees is the
+//     reference's (DCSDecoder.cpp:1233-1246, :1477-1516, :1579-1619, :1697-1728): HardBoot() gives
+//     250 ms of silence during which a data-port byte soft-boots at once, then the POST code
+//     (0x79, status) goes to the host and the startup "bong" plays once per status count (a decaying
+//     195 Hz square wave, synthesised on the host as the reference does) unless SetFastBootMode(true).
 //   * no CPU fallback: without a usable sm_100 device the object is in the error state
 //     (IsOK() == false, GetErrorMessage() says why), as DCSDecoder reports its own fatal errors
 //     (DCSDecoder.h:213-222).
 #pragma once
 #include <stdint.h>
+#include <string.h>
 #include <functional>
 #include <list>
+#include <memory>
 #include <string>
 #include <vector>
 #include "dcsb200.h"
@@ -36,6 +41,14 @@ public:
     enum class HWVersion { Unknown, Invalid, DCS93, DCS95 };                    // DCSDecoder.h:800-846
     enum class OSVersion { Unknown, Invalid, OS93a, OS93b, OS94, OS95 };
     enum class ZipLoadStatus { Success, OpenFileError, ExtractError, NoU2 };    // DCSDecoder.h:278-284
+    struct ZipFileData {                                                        // DCSDecoder.h:225-235
+        ZipFileData(const char *filename, size_t uncompressedSize)
+            : filename(filename), data(new uint8_t[uncompressedSize ? uncompressedSize : 1]), dataSize(uncompressedSize) {}
+        std::string filename;
+        int chipNum = -1;
+        std::unique_ptr<uint8_t[]> data;
+        size_t dataSize;
+    };
     struct TrackInfo {                                                          // DCSDecoder.h:384-414
         uint32_t address = 0;
         int channel = 0, type = 0;
@@ -80,13 +93,32 @@ public:
     bool IsRunning() const { return IsOK() && (player != nullptr || standalone); }
     std::string GetErrorMessage() const { return errorMessage; }
 
-    // ---- ROM load (DCSDecoder.h:285-347).  Images are copied: the caller may free them.
-    ZipLoadStatus LoadROMFromZipFile(const char *zipFileName, const char *explicitU2 = nullptr, std::string *errorDetails = nullptr)
+    // ---- ROM load (DCSDecoder.h:285-347).  The reference's signature: the zip's files are handed back in
+    // zipFileData (one entry per file, chipNum = 2..9 for the ones taken as ROM images, else -1).  The reference
+    // keeps pointers into that list; this decoder copies the images, so the caller MAY free the list (keeping it,
+    // as the reference requires, is harmless).
+    ZipLoadStatus LoadROMFromZipFile(const char *zipFileName, std::list<ZipFileData> &zipFileData,
+                                     const char *explicitU2 = nullptr, std::string *errorDetails = nullptr)
     {
         DropPlayer();
         const int rc = rom ? dcsb_rom_load_zip(rom, zipFileName, explicitU2) : DCSB_ZIP_E_OPEN;
         if (rc != DCSB_ZIP_OK && errorDetails) *errorDetails = rom ? dcsb_rom_last_error(rom) : "no ROM object";
+        if (rom) {
+            std::vector<dcsb_zip_file> files(dcsb_rom_zip_files(rom, nullptr, 0));
+            if (!files.empty()) dcsb_rom_zip_files(rom, files.data(), files.size());
+            for (const dcsb_zip_file &f : files) {
+                zipFileData.emplace_back(f.name, f.size);
+                zipFileData.back().chipNum = f.chip_number;
+                if (f.size) memcpy(zipFileData.back().data.get(), f.data, f.size);
+            }
+        }
         return static_cast<ZipLoadStatus>(rc);
+    }
+    // convenience form for callers that do not want the file list
+    ZipLoadStatus LoadROMFromZipFile(const char *zipFileName, const char *explicitU2 = nullptr, std::string *errorDetails = nullptr)
+    {
+        std::list<ZipFileData> files;
+        return LoadROMFromZipFile(zipFileName, files, explicitU2, errorDetails);
     }
     void AddROM(int n, const uint8_t *data, size_t size) { DropPlayer(); if (rom) dcsb_rom_add(rom, n, data, size); }
     uint8_t CheckROMs() { return rom ? static_cast<uint8_t>(dcsb_rom_check(rom)) : 2; }
@@ -236,37 +268,68 @@ public:
     void SoftBoot()
     {
         if (!IsOK()) return;
+        if (host) host->BootTimerControl(false);
+        state = State::Running;
         if (standalone) { standaloneVolume = defaultVolume; buf.clear(); bufPos = 0; standaloneFrames = 0; return; }
         DropPlayer();
         if (Info().hw_version == 0) CheckROMs();
         if (dcsb_player_create(ctx, rom, &player) != DCSB_OK) { Fail(std::string("dcsb200: ") + dcsb_last_error(ctx)); return; }
+        dcsb_player_set_lookahead(player, chunk > 1 ? static_cast<uint32_t>(chunk) : 0u);
         dcsb_player_set_master_volume(player, defaultVolume);
         buf.clear();
         bufPos = 0;
     }
-    void HardBoot() { StartSelfTests(); }
-    void StartSelfTests()
+    void HardBoot()                                                                                     // DCSDecoder.cpp:1233-1246
     {
+        DropPlayer();
+        state = State::HardBoot;
+        modeSampleCounter = 0;
+        if (host) host->BootTimerControl(true);
+    }
+    void StartSelfTests()                                                                               // DCSDecoder.cpp:1477-1516
+    {
+        if (host) host->BootTimerControl(false);
+        if (state != State::HardBoot) return;
         const uint8_t post = CheckROMs();
         if (host) { host->ReceiveDataPort(0x79); host->ReceiveDataPort(post); }
-        SoftBoot();
+        if (fastBootMode) { SoftBoot(); return; }
+        BongStart();
+        state = State::Bong;
+        modeSampleCounter = 0;
+        bongCount = post;
     }
 
     // ---- run time
-    void SetFastBootMode(bool) {}                                                                       // DCSDecoder.h:541 (always fast here)
+    void SetFastBootMode(bool fast) { fastBootMode = fast; }                                            // DCSDecoder.h:541
     void SetMasterVolume(int vol)                                                                       // DCSDecoder.h:546
     {
         if (standalone) standaloneVolume = vol;
         else if (player) dcsb_player_set_master_volume(player, vol);
     }
-    void WriteDataPort(uint8_t b) { if (player) dcsb_player_write_data_port(player, b); }               // DCSDecoder.h:663
-    int16_t GetNextSample()                                                                             // DCSDecoder.h:565
+    void WriteDataPort(uint8_t b)                                                                       // DCSDecoder.h:663, DCSDecoder.cpp:1542-1558
     {
+        if (state == State::HardBoot) { SoftBoot(); return; }       // a byte during the 250 ms boot wait cancels the self test; it is not queued
+        if (player) dcsb_player_write_data_port(player, b);
+    }
+    int16_t GetNextSample()                                                                             // DCSDecoder.h:565, DCSDecoder.cpp:1579-1690
+    {
+        if (state == State::HardBoot) {                             // 250 ms = 7812 samples of silence, then the self tests
+            if (++modeSampleCounter >= 7812) StartSelfTests();
+            return 0;
+        }
+        if (state == State::Bong) {                                 // 750 ms per bong, one bong per count of the POST code
+            if (++modeSampleCounter >= 23437) {
+                if (--bongCount <= 0) SoftBoot();
+                else { BongStart(); modeSampleCounter = 0; }
+            }
+            return BongSample();
+        }
         if (standalone) return bufPos < buf.size() ? buf[bufPos++] : 0;
         if (!player) return 0;
         if (bufPos >= buf.size()) {
-            buf.resize(static_cast<size_t>(chunk) * 240);
-            if (dcsb_player_render(player, static_cast<uint32_t>(chunk), buf.data()) != DCSB_OK) {
+            // one frame at a time from the player, which renders `chunk` frames ahead on the GPU
+            buf.resize(240);
+            if (dcsb_player_render(player, 1u, buf.data()) != DCSB_OK) {
                 Fail(std::string("dcsb200: ") + dcsb_last_error(ctx));
                 DropPlayer();
                 return 0;
@@ -291,8 +354,13 @@ public:
     void LoadAudioStream(int channel, const ROMPointer &streamPtr, int mixingLevel)
     {
         if (standalone) {
-            if (streamPtr.p && streamPtr.bytesAvailable) LoadAudioStream(channel, streamPtr.p, streamPtr.bytesAvailable, mixingLevel);
-            else Fail("dcsb200: a standalone stream needs its size: ROMPointer(0, data, nbytes)");
+            // ROMPointer(0, data) without a size is what the reference's clients pass (DCSEncoder.cpp:553): the stream's
+            // extent is then found the way GetStreamInfo finds it, by walking its frames (host side, lengths only; needs
+            // DCSB_EXTENT_SLACK readable bytes behind the stream where the reference needs one)
+            size_t nbytes = streamPtr.bytesAvailable;
+            if (streamPtr.p && !nbytes) nbytes = dcsb_stream_extent(streamPtr.p, standaloneOS);
+            if (streamPtr.p && nbytes) LoadAudioStream(channel, streamPtr.p, nbytes, mixingLevel);
+            else Fail("dcsb200: not a decodable stream");
         } else if (player) dcsb_player_load_audio_stream(player, channel, streamPtr.linearAddress, mixingLevel);
     }
     bool IsStreamPlaying(int channel) const
@@ -306,10 +374,12 @@ public:
         dcsb_stream_info i;
         if (standalone) {
             // the reference finds a stream's size by walking all of its frames (DCSDecoderNative.cpp:1486-1537); so does this
-            if (!streamPtr.p || streamPtr.bytesAvailable < 3 || !IsOK()) return si;
+            if (!streamPtr.p || !IsOK()) return si;
+            const size_t avail = streamPtr.bytesAvailable ? streamPtr.bytesAvailable : dcsb_stream_extent(streamPtr.p, standaloneOS);
+            if (avail < 3) return si;
             dcsb_stream_desc d = dcsb_stream_desc();
             d.data = streamPtr.p;
-            d.nbytes = static_cast<uint32_t>(streamPtr.bytesAvailable);
+            d.nbytes = static_cast<uint32_t>(avail);
             d.os_version = static_cast<uint16_t>(standaloneOS);
             d.master_volume = 255;
             d.mixing_level = 0x64;
@@ -320,7 +390,7 @@ public:
             if (dcsb_decode_streams(ctx, &d, 1, scratch.data(), &off, &r) != DCSB_OK || r.stream_bytes == 0) return si;
             si.nFrames = static_cast<int>(nf);
             si.nBytes = static_cast<int>(r.stream_bytes);
-            for (size_t k = 0; k < 16 && 2 + k < streamPtr.bytesAvailable; ++k) si.header[k] = streamPtr.p[2 + k];
+            for (size_t k = 0; k < 16 && 2 + k < avail; ++k) si.header[k] = streamPtr.p[2 + k];
             si.streamType = si.header[0] >> 7;
             if (standaloneOS == DCSB_OS94 || standaloneOS == DCSB_OS95) si.streamSubType = ((si.header[1] & 0x80) >> 6) | ((si.header[1] & 0x80) >> 7);
             return si;
@@ -335,6 +405,23 @@ public:
     void AddTrackCommand(uint16_t trackNum) { if (player) dcsb_player_add_track_command(player, trackNum); }
 
 private:
+    enum class State { HardBoot, Bong, Running };                               // DCSDecoder.h (decoder state machine)
+    State state = State::Running;
+    int modeSampleCounter = 0, bongCount = 0;
+    bool fastBootMode = false;                                                  // DCSDecoder.h:1290
+    // startup bong (DCSDecoder.cpp:1697-1728): a square wave of about 195 Hz under an exponential decay envelope
+    int bongEnvelopeSamples = 0, bongSignSamples = 0, bongSign = -1;
+    uint16_t bongLevel = 0x0FFF;
+    void BongStart() { bongEnvelopeSamples = 0; bongSignSamples = 0; bongLevel = 0x0FFF; }
+    int16_t BongSample()
+    {
+        if (bongEnvelopeSamples++ >= 31) {                                      // about every millisecond: level *= 0.996 (1.15 fixed point)
+            bongLevel = static_cast<uint16_t>(((static_cast<uint32_t>(bongLevel) * 0x7f80u) << 1) >> 16);
+            bongEnvelopeSamples = 0;
+        }
+        if (bongSignSamples++ >= 80) { bongSign = -bongSign; bongSignSamples = 0; }
+        return static_cast<int16_t>(bongSign * static_cast<int16_t>(bongLevel));
+    }
     Host *host;
     int chunk;
     int defaultVolume = 0x67;                           // DCSDecoder.h:1146

@@ -174,6 +174,12 @@ void dcsb_rom_destroy(dcsb_rom *rom);
 int  dcsb_rom_add(dcsb_rom *rom, int chip_number /* 2..9 */, const uint8_t *image, size_t nbytes);
 /* returns DCSB_ZIP_*; explicit_u2 may be NULL; details in dcsb_rom_last_error */
 int  dcsb_rom_load_zip(dcsb_rom *rom, const char *zip_path, const char *explicit_u2);
+/* the files of the zip most recently loaded, as LoadROMFromZipFile hands them to its caller in its
+ * std::list<ZipFileData> (DCSDecoder.h:225-235, :285-288): name, inflated bytes (owned by the rom object, valid
+ * until the next load / destroy) and the chip the loader took the file for (2..9, or -1: not a ROM image).
+ * Writes up to max records, returns how many files the zip held. */
+typedef struct { const char *name; const uint8_t *data; size_t size; int32_t chip_number; } dcsb_zip_file;
+size_t dcsb_rom_zip_files(const dcsb_rom *rom, dcsb_zip_file *files, size_t max);
 int  dcsb_rom_check(dcsb_rom *rom);                                    /* CheckROMs(): POST code */
 int  dcsb_rom_get_info(const dcsb_rom *rom, dcsb_rom_info *info);
 int  dcsb_rom_track_info(const dcsb_rom *rom, uint16_t track, dcsb_track_info *info);   /* 1 = valid track, 0 = not */
@@ -196,6 +202,15 @@ size_t dcsb_rom_list_streams(const dcsb_rom *rom, uint32_t *addresses, size_t ma
 /* MakeROMPointer: pointer into the rom's own copy of the chip + bytes left in that chip */
 const uint8_t *dcsb_rom_pointer(const dcsb_rom *rom, uint32_t linear_address, uint32_t *bytes_left);
 const char *dcsb_rom_last_error(const dcsb_rom *rom);
+
+/* Size of a stream whose caller does not know it (the reference's clients hand the decoder an unsized
+ * ROMPointer and let it read as far as the bits go: DCSEncoder.cpp:547-571; its own GetStreamInfo,
+ * DCSDecoderNative.cpp:1486-1537, finds the size by walking every frame).  HOST side, lengths only (no PCM is
+ * produced: this is stream validation, like reading the frame count): walks the frames the preamble counts
+ * and returns the bytes the stream occupies, 0 if it is not decodable to its end.  Reads at most
+ * DCSB_EXTENT_SLACK bytes past the stream's last byte (the reference reads 1). */
+#define DCSB_EXTENT_SLACK 16
+size_t dcsb_stream_extent(const uint8_t *data, int os_version);
 
 /* ---- track playback: one decoder instance = one player ------------------------------ */
 /* A player is the control state of one DCSDecoderNative (channels, track programs, command
@@ -225,6 +240,12 @@ int  dcsb_player_stream_info(const dcsb_player *p, uint32_t stream_address, dcsb
 /* render the next n_frames * 240 samples into HOST memory (the GetNextSample pump,
  * DCSDecoder.cpp:1579-1690, n_frames main-loop passes at once) */
 int  dcsb_player_render(dcsb_player *p, uint32_t n_frames, int16_t *pcm_out);
+/* Render ahead: dcsb_player_render then renders n_frames at a time (one launch and one copy per block) and
+ * hands frames out of the block; an input that arrives in the middle of a block (data port, volume, track
+ * command, LoadAudioStream, ClearTracks) still takes effect at the frame it arrives at, as in the reference
+ * (DCSDecoder.cpp:1625-1631: the port is drained before every main-loop pass) -- the unconsumed frames are
+ * dropped and rendered anew.  0 (the default) = render exactly what each call asks for. */
+int  dcsb_player_set_lookahead(dcsb_player *p, uint32_t n_frames);
 /* bytes the decoder sent to the host since the last call (Host::ReceiveDataPort); returns count */
 size_t dcsb_player_host_bytes(dcsb_player *p, uint8_t *out, size_t max);
 

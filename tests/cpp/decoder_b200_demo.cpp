@@ -28,7 +28,11 @@ static int standalone_main(int argc, char **argv)
                      : os == 0x9500 ? DCSDecoderB200::OSVersion::OS95 : DCSDecoderB200::OSVersion::OS94);
     dec.SoftBoot();
     dec.SetMasterVolume(atoi(argv[4]));
-    const DCSDecoderB200::ROMPointer rp(0, data.data(), data.size());
+    // "unsized" as a ninth argument: the pointer the reference's own clients pass (DCSEncoder.cpp:553), no size
+    const bool unsized = argc > 8 && std::string(argv[8]) == "unsized";
+    data.resize(data.size() + DCSB_EXTENT_SLACK, 0);
+    const DCSDecoderB200::ROMPointer rp = unsized ? DCSDecoderB200::ROMPointer(0, data.data())
+                                                  : DCSDecoderB200::ROMPointer(0, data.data(), data.size() - DCSB_EXTENT_SLACK);
     dec.LoadAudioStream(0, rp, atoi(argv[5]));
     if (!dec.IsOK()) { fprintf(stderr, "%s\n", dec.GetErrorMessage().c_str()); return 6; }
     const unsigned nframes = (unsigned)atoi(argv[6]);
@@ -43,9 +47,40 @@ static int standalone_main(int argc, char **argv)
     return 0;
 }
 
+// the boot sequence (DCSDecoder.cpp:1233-1246, :1477-1516, :1579-1619):
+//   decoder_b200_demo --hardboot <rom.zip> <fast: 0|1> <port write at sample, -1 = none> <n_samples> <out.pcm>
+static int hardboot_main(int argc, char **argv)
+{
+    if (argc < 7) return 2;
+    RecHost host;
+    DCSDecoderB200 dec(&host, 0, 1);
+    if (!dec.IsOK()) { fprintf(stderr, "%s\n", dec.GetErrorMessage().c_str()); return 3; }
+    std::list<DCSDecoderB200::ZipFileData> files;
+    std::string err;
+    if (dec.LoadROMFromZipFile(argv[2], files, nullptr, &err) != DCSDecoderB200::ZipLoadStatus::Success) { fprintf(stderr, "%s\n", err.c_str()); return 4; }
+    dec.SetFastBootMode(atoi(argv[3]) != 0);
+    dec.HardBoot();
+    const long at = atol(argv[4]), n = atol(argv[5]);
+    std::vector<int16_t> pcm((size_t)n);
+    for (long i = 0; i < n; ++i) {
+        if (i == at) dec.WriteDataPort(0x55);
+        pcm[(size_t)i] = dec.GetNextSample();
+    }
+    FILE *o = fopen(argv[6], "wb");
+    fwrite(pcm.data(), 2, pcm.size(), o);
+    fclose(o);
+    printf("zip files:");
+    for (auto &f : files) printf(" %s=%d(%zu)", f.filename.c_str(), f.chipNum, f.dataSize);
+    printf(" | host bytes");
+    for (uint8_t b : host.bytes) printf(" %02x", b);
+    printf(" | running %d\n", (int)dec.IsRunning());
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
     if (argc > 1 && std::string(argv[1]) == "--standalone") return standalone_main(argc, argv);
+    if (argc > 1 && std::string(argv[1]) == "--hardboot") return hardboot_main(argc, argv);
     if (argc < 7) { fprintf(stderr, "usage: %s rom.zip timeline.txt n_frames volume chunk out.pcm\n", argv[0]); return 2; }
     RecHost host;
     DCSDecoderB200 dec(&host, 0, atoi(argv[5]));

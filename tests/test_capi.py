@@ -108,3 +108,31 @@ def test_public_header_is_plain_c(built, tmp_path):
     r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
                         "-fsyntax-only", str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_stream_extent_matches_oracle(built, golden):
+    """dcsb_stream_extent (host side: the size of a stream handed over without one) against the oracle's
+    frame walk on every golden stream and on fuzzer-made ones; damaged streams give 0 or a size within the data."""
+    import ctypes as C
+    import numpy as np
+    import dcsfuzz
+    from oracle import orc
+    from dcsexplorer_b200 import _capi
+    L = _capi.lib()
+    items = [(it["stream"], it["os"]) for it in golden.items if not it["stop"]]
+    items += [(d, os_) for os_, d, _ in dcsfuzz.corpus(seed=77, n_each=3, nframes=20)]
+    checked = 0
+    for d, os_ in items:
+        nf = (d[0] << 8) | d[1]
+        rc, bp, bt, stop = orc.scan(d, os_)
+        buf = np.frombuffer(bytes(d) + bytes(32), dtype=np.uint8)
+        ext = L.dcsb_stream_extent(buf.ctypes.data, os_)
+        if rc == nf and nf and stop < 0:
+            hdr_len = 1 if (os_ == 0x9301 and d[2] & 0x80) else 16
+            assert ext == 2 + hdr_len + (int(bp[nf]) + 7) // 8, (hex(os_), nf)
+            assert ext <= len(d)
+            checked += 1
+    assert checked >= 20
+    assert L.dcsb_stream_extent(None, 0x9400) == 0
+    z = np.zeros(64, dtype=np.uint8)
+    assert L.dcsb_stream_extent(z.ctypes.data, 0x9400) == 0          # no frames

@@ -64,9 +64,9 @@ def test_cpp_front_matches_golden(demo, tmp_path, name, chunk):
 
 @pytest.mark.gpu
 def test_cpp_front_chunked_latency(demo, tmp_path):
-    """chunkFrames = 16: same audio as chunk 1 when the data-port bytes arrive on chunk boundaries."""
+    """chunkFrames = 16 (rendered ahead on the GPU): the same audio as frame-at-a-time rendering wherever the
+    data-port bytes arrive -- an input takes effect at its own frame, as in the reference."""
     sc = romscen.make_scenario(os_version=rb.OS94, seed=55, n_frames=320)
-    sc["writes"] = [((f + 15) // 16 * 16, b) for f, b in sc["writes"]]
     z, tl = _write_inputs(tmp_path, sc)
     outs = []
     for chunk in (1, 16):
@@ -102,3 +102,75 @@ def test_cpp_front_standalone_stream_protocol(demo, tmp_path, golden):
         nf = (it["stream"][0] << 8) | it["stream"][1]
         assert ("standalone: %d frames" % nf) in r.stdout and ("playing for %d samples" % (nf * 240)) in r.stdout
     assert len(seen) >= 3
+
+
+@pytest.mark.gpu
+def test_cpp_front_standalone_unsized_pointer(demo, tmp_path, golden):
+    """LoadAudioStream(0, ROMPointer(0, data), level) WITHOUT a size -- what the reference's own client passes
+    (DCSEncoder.cpp:553) -- and GetStreamInfo on it: the front finds the extent by walking the frames on the
+    host (dcsb_stream_extent), then decodes on the GPU; same PCM, and the reference's stream size."""
+    import dcsexplorer_b200 as dx
+    from dcsexplorer_b200 import _capi
+    import ctypes as C
+    seen = set()
+    for k, it in enumerate(golden.items):
+        if it["os"] in seen or it["stop"] or it["nframes_out"] * 240 != it["pcm"].size:
+            continue
+        seen.add(it["os"])
+        src = tmp_path / ("u%d.bin" % k)
+        src.write_bytes(it["stream"])
+        out = tmp_path / ("u%d.pcm" % k)
+        r = subprocess.run([demo, "--standalone", "%x" % it["os"], str(src), str(it["vol"]), str(it["lvl"]), str(it["nframes_out"]), str(out), "unsized"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        pcm = np.fromfile(out, dtype=np.int16)
+        n = min(pcm.size, it["pcm"].size)
+        assert np.array_equal(pcm[:n], it["pcm"][:n]), it["label"]
+        # the extent the host walk reports = the bytes the batch decoder reports for the same stream
+        buf = np.frombuffer(it["stream"] + bytes(32), dtype=np.uint8)
+        ext = _capi.lib().dcsb_stream_extent(buf.ctypes.data, it["os"])
+        nf = (it["stream"][0] << 8) | it["stream"][1]
+        assert ("standalone: %d frames, %d bytes" % (nf, ext)) in r.stdout, (r.stdout, ext)
+        assert 0 < ext <= len(it["stream"])
+    assert len(seen) >= 3
+
+
+@pytest.mark.gpu
+def test_cpp_front_hard_boot_sequence(demo, tmp_path):
+    """HardBoot(): 7812 samples of silence, the POST code to the host, then the startup bong (POST code 1 = one
+    bong of 23437 samples: a square wave flipping every 81 samples under a decay of 0x7f80/0x8000 every 32
+    samples, DCSDecoder.cpp:1584-1619, :1697-1728), then the decoder runs.  Fast-boot mode skips the bong; a
+    data-port byte during the 250 ms wait soft-boots at once and is not queued."""
+    sc = romscen.make_scenario(os_version=rb.OS94, seed=101)
+    z, tl = _write_inputs(tmp_path, sc)
+    out = tmp_path / "boot.pcm"
+    n = 7812 + 23437 + 480
+    r = subprocess.run([demo, "--hardboot", str(z), "0", "-1", str(n), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    pcm = np.fromfile(out, dtype=np.int16)
+    assert not pcm[:7812].any()
+    # the bong, restated: sample k (from 0) of the bong has |level| after k // 32 decays, sign flipping every 81 samples from -1
+    level, want = 0x0FFF, []
+    env = sgn_n = 0
+    sign = -1
+    for k in range(23437):
+        if env >= 31:
+            level = ((level * 0x7F80) << 1 >> 16) & 0xFFFF
+            env = 0
+        else:
+            env += 1
+        if sgn_n >= 80:
+            sign, sgn_n = -sign, 0
+        else:
+            sgn_n += 1
+        want.append(sign * level)
+    assert np.array_equal(pcm[7812:7812 + 23437], np.array(want, dtype=np.int16))
+    assert not pcm[7812 + 23437:].any()                         # running, nothing playing
+    assert "host bytes 79 01 | running 1" in r.stdout
+    assert "snd_u2.rom=2(" in r.stdout and "snd_u3.rom=3(" in r.stdout     # the reference's zip file list: names and chip numbers
+    # fast boot: no bong
+    r = subprocess.run([demo, "--hardboot", str(z), "1", "-1", "9000", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0 and not np.fromfile(out, dtype=np.int16).any() and "host bytes 79 01 | running 1" in r.stdout
+    # a data-port byte during the boot wait: soft boot at once, no POST code, no bong
+    r = subprocess.run([demo, "--hardboot", str(z), "0", "100", "9000", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0 and not np.fromfile(out, dtype=np.int16).any() and "host bytes | running 1" in r.stdout

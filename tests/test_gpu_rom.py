@@ -89,6 +89,36 @@ def test_gpu_many_timelines_vs_reference(ctx):
     rom.close()
 
 
+@pytest.mark.parametrize("name", ["os94", "os95-v105", "os93a"])
+def test_gpu_player_lookahead_is_frame_accurate(ctx, rom_golden, name):
+    """dcsb_player_set_lookahead(16): frames are rendered 16 at a time, yet data-port bytes written between any
+    two frames act on the frame they arrive at -- PCM, host bytes and IsStreamPlaying polls are those of
+    frame-at-a-time rendering, and the PCM is the golden PCM of the reference."""
+    import dcsexplorer_b200 as dx
+    sc = romscen.make_scenario(**dict(romscen.SCENARIOS)[name])
+    rom = dx.Rom(sc["images"])
+    runs = []
+    for look in (0, 16, 5):
+        p = dx.Player(ctx, rom)
+        assert ctx._L.dcsb_player_set_lookahead(p._h, look) == 0
+        p.set_master_volume(sc["master_volume"])
+        out = np.zeros(sc["n_frames"] * 240, dtype=np.int16)
+        hb, playing, w = b"", [], 0
+        for f in range(sc["n_frames"]):
+            while w < len(sc["writes"]) and sc["writes"][w][0] <= f:
+                p.write_data_port(sc["writes"][w][1])
+                w += 1
+            out[f * 240:(f + 1) * 240] = p.render(1)
+            hb += p.host_bytes()
+            playing.append(tuple(p.is_stream_playing(ch) for ch in range(6)))
+        runs.append((out, hb, playing))
+        p.close()
+    for out, hb, playing in runs[1:]:
+        assert np.array_equal(out, runs[0][0]) and hb == runs[0][1] and playing == runs[0][2]
+    check_rom_golden(rom_golden, name, runs[1][0], runs[1][1])
+    rom.close()
+
+
 def test_gpu_player_load_audio_stream_equals_batch_decode(ctx):
     """LoadAudioStream on a player (DCSExplorer's stream extraction protocol) and the batch
     decode of the same stream bytes are two routes to the same PCM."""
