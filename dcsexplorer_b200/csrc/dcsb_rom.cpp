@@ -652,6 +652,11 @@ void DcsbSequencer::exec_track(int cur)
     DcsbRomPtr p = me.track;
     if (p.null()) return;
     for (;;) {
+        // A track program that loops without ever waiting (or queues itself over and over) would keep the
+        // reference's MainLoop -- and a whole dcsb_render_timelines batch with it -- busy for ever.  No
+        // well-formed program comes near this many steps in one 7.68 ms frame: treat it like the other
+        // malformed-program cases (bad opcode / track type): self-reset, fatal after four in a row.
+        if (++steps_this_frame > DCSB_MAX_STEPS_PER_FRAME || cmdq.size() > DCSB_MAX_QUEUED_COMMANDS) throw Reset();
         const uint32_t wait = rom->be(p, 2);
         if (wait == 0xFFFF || me.track_counter != wait) { me.track = p; return; }
         p.ofs += 2;
@@ -788,6 +793,7 @@ void DcsbSequencer::update_levels()
 
 void DcsbSequencer::main_loop(std::vector<DcsbSchedEntry> &entries, DcsbSchedFrame &fr)
 {
+    steps_this_frame = 0;
     // channels the decoder's error path flagged last frame
     for (int ch = 0; ch < DCSB_MAX_CHANNELS; ++ch) {
         Channel &c = chan[ch];
@@ -799,6 +805,7 @@ void DcsbSequencer::main_loop(std::vector<DcsbSchedEntry> &entries, DcsbSchedFra
     }
     // pending commands = indices into the track index
     while (!cmdq.empty()) {
+        if (++steps_this_frame > DCSB_MAX_STEPS_PER_FRAME) { cmdq.clear(); throw Reset(); }
         const uint16_t cmd = cmdq.front();
         cmdq.pop_front();
         if (cmd >= rom->n_tracks) continue;

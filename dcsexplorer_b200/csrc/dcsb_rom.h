@@ -86,6 +86,8 @@ struct DcsbSchedEntry { uint32_t stream; uint16_t frame; uint16_t mult; };
 #define DCSB_FRAME_MUTE 1       // the decoder is in its fatal-error state: pure silence, no overlap tail
 struct DcsbSchedFrame { uint32_t first_entry; uint8_t n_entries; uint8_t vs; uint8_t flags; uint8_t pad; };
 
+#define DCSB_MAX_STEPS_PER_FRAME 65536u        // track-program steps in one frame before the program counts as runaway
+#define DCSB_MAX_QUEUED_COMMANDS 4096u         // queued track commands before the queue counts as runaway
 struct DcsbSequencer {
     explicit DcsbSequencer(const dcsb_rom *rom);
     void soft_boot();                               // Initialize(): channel defaults, default volume
@@ -141,6 +143,7 @@ private:
     uint16_t vol_mult = 0;
     uint16_t reported_version = 0x0106;         // DCSDecoderNative.h:168
     unsigned done_mask = 0;
+    uint32_t steps_this_frame = 0;              // track-program steps + queued commands taken in the current main-loop pass
 
     void main_loop(std::vector<DcsbSchedEntry> &entries, DcsbSchedFrame &fr);
     void exec_track(int ch);

@@ -29,6 +29,8 @@ def lib():
         L.dcsref_encode.restype = C.c_size_t
         L.dcsref_encode.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_float, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]
+        L.dcsref_read_dcs_file.restype = C.c_long
+        L.dcsref_read_dcs_file.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]
         L.dcsref_decode_batch_timed.restype = C.c_double
         L.dcsref_decode_batch_timed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                                 C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]
@@ -161,3 +163,14 @@ class RomPlayer:
             self._h = None
 
     __del__ = close
+
+
+def read_dcs_file(path):
+    """DCSEncoder::IsDCSFile + EncodeDCSFile (pass-through branch): (format version, stream bytes, frames),
+    or None when the reference does not take the file for a DCS stream file"""
+    fmt, nf = C.c_int(0), C.c_int(0)
+    out = np.zeros(1 << 22, dtype=np.uint8)
+    n = lib().dcsref_read_dcs_file(str(path).encode(), C.byref(fmt), out.ctypes.data, out.size, C.byref(nf))
+    if n < 0:
+        return None
+    return fmt.value, out[:n].tobytes(), nf.value

@@ -182,6 +182,26 @@ size_t dcsref_encode(const float *pcm, size_t n, int sample_rate, int format_ver
     return obj.nBytes;
 }
 
+// The reference's reader of raw ".dcs" stream files (DCSEncoder::IsDCSFile / EncodeDCSFile,
+// DCSEncoder.cpp:358-571): is `path` a DCS file, which format version does its header name, and which
+// stream bytes does the reference take from it when the target format is the file's own (the pass-through
+// branch, :507-519).  Returns the stream's byte count (copied to out), -1 not a DCS file, -2 read error.
+long dcsref_read_dcs_file(const char *path, int *format_version, uint8_t *out, size_t cap, int *n_frames)
+{
+    int fmt = 0;
+    if (!DCSEncoder::IsDCSFile(path, &fmt)) return -1;
+    if (format_version) *format_version = fmt;
+    DCSEncoder enc;
+    enc.compressionParams.formatVersion = static_cast<uint16_t>(fmt);
+    DCSEncoder::DCSAudio obj;
+    std::string err;
+    if (!enc.EncodeDCSFile(path, obj, err)) return -2;
+    if (obj.nBytes > cap) return -2;
+    memcpy(out, obj.data.get(), obj.nBytes);
+    if (n_frames) *n_frames = obj.nFrames;
+    return (long)obj.nBytes;
+}
+
 // CPU baseline: decode a batch of streams with one DCSDecoderNative per thread,
 // streams partitioned round-robin by index; returns wall seconds around the
 // GetNextSample loops only (streams pre-loaded, padded copies made before timing).

@@ -46,3 +46,24 @@ def test_dcs_container_roundtrip(built, tmp_path, osv, tag):
         dx.read_dcs_file(tmp_path / "bad.dcs")
     with pytest.raises(dx.DcsbError):
         dx.read_dcs_file(tmp_path / "missing.dcs")
+
+
+@pytest.mark.parametrize("osv,fmt", [(0x9400, 0x9400), (0x9500, 0x9400), (0x9302, 0x9302), (0x9301, 0x9301)])
+def test_dcs_container_is_read_by_the_reference(built, tmp_path, osv, fmt):
+    """A file written by dcsb_write_dcs_file goes through the reference's own reader (DCSEncoder::IsDCSFile /
+    EncodeDCSFile, DCSEncoder.cpp:358-519, compiled unmodified into oracle/_ref): recognised, the format version
+    it names is the stream's, and the stream bytes and frame count it takes from the file are the ones written."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    import dcsexplorer_b200 as dx
+    rng = np.random.default_rng(osv + 1)
+    d = dcsfuzz.fuzz94(rng, 23, type1=1) if osv >= 0x9400 else dcsfuzz.fuzz93(rng, 23, type1=0)
+    p = tmp_path / "r.dcs"
+    dx.write_dcs_file(p, osv, d)
+    got = ref.read_dcs_file(p)
+    assert got is not None, "the reference does not recognise the file"
+    assert got[0] == fmt and got[1] == d and got[2] == ((d[0] << 8) | d[1])
+    # and a WAV file is not mistaken for one
+    dx.write_wav(tmp_path / "x.wav", np.zeros(100, dtype=np.int16))
+    assert ref.read_dcs_file(tmp_path / "x.wav") is None

@@ -262,6 +262,22 @@ def test_sim_rom_bad_track_type_is_fatal(built):
         assert np.array_equal(rp.render_timeline(writes, 40), pcm[0])
 
 
+def test_sim_rom_runaway_track_program_is_fatal_not_a_hang(built):
+    """A track program that loops for ever without waiting (Loop(0) ... EndLoop, both with wait 0) hangs the
+    reference's MainLoop; here the step budget per frame turns it into the decoder's fatal-error state
+    (silence), and the other timelines of the batch render normally."""
+    import dcsfuzz
+    rng = np.random.default_rng(5)
+    t0 = rb.Track(0).mix(0, 0, 100).play("a").wait_forever()
+    spin = rb.Track(1).loop(0).end_loop()
+    images, _ = rb.build_rom(rb.OS94, [t0, spin], {"a": dcsfuzz.fuzz94(rng, 50, type1=1)}, n_chips=1)
+    good = [(1, 0), (1, 0)]
+    bad = good + [(10, 0), (10, 1)]
+    pcm, res, info, hb = simutil.rom_render(images, [(bad, 40, 255), (good, 40, 255)])
+    assert res[0]["status"] == -5 and not pcm[0][240 * 10:].any() and pcm[0][240 * 2:240 * 10].any()
+    assert res[1]["status"] == 0 and pcm[1][240 * 12:240 * 30].any()
+
+
 def test_damaged_rom_sets_are_survivable(built):
     """Random damage to the track programs, the track index and the stream heads of U2 (checksum
     re-balanced so that the set still boots): the ROM model, the decompiler, the sequencer and the
