@@ -399,7 +399,8 @@ def config5(ctx, dx, torch, dist, rank, world, local_rank, total_streams, steps=
     scan_ms, dec_ms = batch.kernel_ms(0), batch.kernel_ms(1)
     ctx.set_overlap(True)
     res = batch.results_np(st.cuda_stream)
-    xor = int(np.bitwise_xor.reduce(res["checksum"])) if res.size else 0
+    # (a sum, not an xor: every pool stream is replicated an even number of times per rank)
+    xor = int(np.sum(res["checksum"], dtype=np.uint64)) if res.size else 0
     # the pool's streams must decode to the same PCM wherever they sit: per-pool-stream checksums of this rank
     bad = int(np.count_nonzero(res["status"]))
     first = {}
@@ -428,7 +429,7 @@ def config5(ctx, dx, torch, dist, rank, world, local_rank, total_streams, steps=
            "compressed_bytes": cbytes, "pcm_bytes": samples * 2,
            "frac": (cbytes + samples * 2) / (worst * 1e-3) / 1e9 / (peak * world),
            "frac_note": "algorithmic bytes (compressed in + PCM out) / slowest rank's step time, against %d x the measured HBM copy bandwidth" % world,
-           "errors_or_replica_mismatches_this_rank": bad, "checksum_xor_per_rank": ["%016x" % int(x.item()) for x in gc],
+           "errors_or_replica_mismatches_this_rank": bad, "checksum_sum_per_rank": ["%016x" % int(x.item()) for x in gc],
            "batch_create_s": t_create}
     batch.close()
     del d_pcm
