@@ -11,6 +11,7 @@
 #include "../../include/dcsb200.h"
 #include "dcsb_internal.h"
 #include "dcs_tables.h"
+#include "dcsb_seq.cuh"
 
 // ======================================================================================
 // tables: prefix-code lists (dcs_tables.h) -> peek LUTs
@@ -131,55 +132,18 @@ void dcsb_build_tables(DcsbTables *t)
 
 // ======================================================================================
 // gain helpers (host side)
-static int calc_exp32(uint32_t x)      // ADSP-2105 EXP on a 32-bit mantissa (DCSDecoderNative.cpp:3447-3459)
-{
-    int res = 0;
-    if (x & 0x80000000u) { while (x & 0x40000000u) { --res; x <<= 1; } }
-    else { while (res > -31 && !(x & 0x40000000u)) { --res; x <<= 1; } }
-    return res;
-}
-
-extern "C" uint16_t dcsb_master_multiplier(int vol)
-{
-    if (vol > 255) vol = 255;
-    if (vol <= 0) return 0;
-    uint32_t x = 0x3fff, y = 0x7d98;       // 0.5 * 0.981201^(255-vol) in 1.15
-    for (int i = 0; i < 8; ++i, vol >>= 1) {
-        if (!(vol & 1)) x = ((x * y) >> 15) & 0xFFFFu;
-        y = ((y * y) >> 15) & 0xFFFFu;
-    }
-    return (uint16_t)(x << 1);
-}
+// (the arithmetic lives in dcsb_seq.cuh, shared with the device-side sequencer)
+extern "C" uint16_t dcsb_master_multiplier(int vol) { return dcsb_seq_master_multiplier(vol); }
 
 extern "C" uint16_t dcsb_level_multiplier(int level_sum, int os_version, int channel_volume, int max_override)
 {
-    level_sum = std::max(-8191, std::min(8191, level_sum));
-    const uint32_t e = (uint32_t)((level_sum >> 6) & 0x3FF) + 0x80;
-    uint32_t m = os_version == DCSB_OS93A ? 0x7FFFu : ((uint32_t)channel_volume << 7) & 0xFFFFu;
-    if (max_override) m = 0xFFu << 7;
-    uint32_t p = 0x7C94;                     // 0.9733^(2^j) ladder
-    for (int j = 0; j < 8; ++j) {
-        if (!(e & (1u << j))) m = ((m * p) >> 15) & 0xFFFFu;
-        p = ((p * p) >> 15) & 0xFFFFu;
-    }
-    return (uint16_t)(m << 1);
+    return dcsb_seq_level_multiplier(level_sum, os_version, channel_volume, max_override);
 }
 
 extern "C" int dcsb_gain_stage(const uint16_t mix_mult[8], unsigned active_mask, unsigned max_override_mask,
                                uint16_t vol_mult, uint16_t eff_mult[8])
 {
-    uint64_t sum = 0;
-    for (int i = 0; i < 8; ++i) {
-        if (max_override_mask & (1u << i)) sum += (uint64_t)mix_mult[i] * 0x7FFE;
-        else if (active_mask & (1u << i)) sum += (uint64_t)mix_mult[i] * vol_mult;
-    }
-    int vs = -(calc_exp32((uint32_t)(sum >> 2)) + 3);
-    vs = std::max(0, std::min(8, vs));
-    for (int i = 0; i < 8; ++i) {
-        const uint64_t v = (max_override_mask & (1u << i)) ? 0x7FFE : vol_mult;
-        eff_mult[i] = (uint16_t)(((((uint64_t)mix_mult[i] * v) << 1) << vs) >> 16);
-    }
-    return vs;
+    return dcsb_seq_gain_stage(mix_mult, active_mask, max_override_mask, vol_mult, eff_mult);
 }
 
 // Per-stream gain schedule of the single-stream protocol: frame 0 still carries the

@@ -164,6 +164,14 @@ cudaError_t dcsb_launch_decode(const uint8_t *slab, const DcsbStreamRec *streams
                                int ntiles94, int ntiles93, const DcsbTables *tables, DcsbScanOut scan,
                                int16_t *pcm, unsigned long long *checksums, cudaStream_t st);
 
+// K5: the track interpreter on the device (dcsb_seq.cuh): one thread per decoder instance (timeline) writes the mix
+// schedule -- frames[first_frame + f], entries[8 * (first_frame + f) ...] -- K4 renders.  tls / writes / out are
+// device pointers (DcsbSeqTimeline[n], dcsb_port_write[], uint32_t[2 n] = {fatal, host bytes} per timeline).
+struct DcsbSeqTimeline { uint32_t first_write, n_writes, n_frames, first_frame; uint32_t master_volume; };
+struct DcsbRomView;
+cudaError_t dcsb_launch_seq(const DcsbRomView *view, const DcsbSeqTimeline *tls, int n, const void *writes,
+                            void *frames, void *entries, uint32_t *out, cudaStream_t st);
+
 // K4 launch (dcsb_mix.cuh): items = DcsbMixItem[], frames = DcsbSchedFrame[], entries = DcsbSchedEntry[]
 // (device pointers; the types live in dcsb_rom.h / dcsb_mix.cuh).  family93 selects the 1993 transform.
 cudaError_t dcsb_launch_mix(bool family93, const uint8_t *slab, const DcsbStreamRec *streams, const void *items, int nitems,

@@ -21,6 +21,7 @@
 #include "dcsb_fast94.cuh"
 #include "dcsb_scan94.cuh"
 #include "dcsb_mix.cuh"
+#include "dcsb_seq.cuh"
 
 #define DCSB_WARPS_PER_CTA 2      // 1993 layouts: 33 KB of rows per warp; 70 KB CTAs: three per SM, or one beside a scan CTA
 
@@ -377,6 +378,48 @@ cudaError_t dcsb_launch_mix(bool family93, const uint8_t *slab, const DcsbStream
         const int grid = (nitems + DCSB_WARPS94 - 1) / DCSB_WARPS94;
         dcsb_mix94_kernel<<<grid, DCSB_WARPS94 * 32, smem, st>>>(slab, streams, it, nitems, sc, tables, scan, pcm, checksums);
     }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
+// K5: device-side track interpreter.  One thread = one decoder instance: it runs the
+// reference's MainLoop control plane (dcsb_seq.cuh: command queue, track byte code, mixer, fades, data-port
+// state machine, gain staging) frame after frame against the ROM image in HBM and writes the mix schedule K4
+// renders -- dcsb_render_timelines needs no host sequencer threads and no schedule upload.  The instance's
+// state (about 4 KB) lives in the thread's local memory; the 32 instances of a warp run their own track
+// programs (they diverge where their programs do).
+__global__ void __launch_bounds__(32)
+dcsb_seq_kernel(DcsbRomView rv, const DcsbSeqTimeline *__restrict__ tls, int n, const dcsb_port_write *__restrict__ writes,
+                DcsbSchedFrame *__restrict__ frames, DcsbSchedEntry *__restrict__ entries, uint32_t *__restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const DcsbSeqTimeline tl = tls[t];
+    DcsbSeqState st;
+    dcsb_seq_init(st);
+    dcsb_seq_set_master_volume(st, (int)tl.master_volume);
+    uint32_t w = 0;
+    for (uint32_t f = 0; f < tl.n_frames; ++f) {
+        while (w < tl.n_writes && writes[tl.first_write + w].frame <= f) dcsb_seq_write_port(st, rv, writes[tl.first_write + w++].byte);
+        DcsbSchedFrame fr;
+        DcsbSchedEntry e[DCSB_MAX_CHANNELS];
+        dcsb_seq_frame(st, rv, &fr, e);
+        const uint32_t gf = tl.first_frame + f;
+        fr.first_entry = gf * DCSB_MAX_CHANNELS;
+        for (int i = 0; i < fr.n_entries; ++i) entries[fr.first_entry + i] = e[i];
+        frames[gf] = fr;
+        st.host_n = 0;
+    }
+    out[2 * t] = st.fatal ? 1u : 0u;
+    out[2 * t + 1] = st.host_total;
+}
+
+cudaError_t dcsb_launch_seq(const DcsbRomView *view, const DcsbSeqTimeline *tls, int n, const void *writes,
+                            void *frames, void *entries, uint32_t *out, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    dcsb_seq_kernel<<<(n + 31) / 32, 32, 0, st>>>(*view, tls, n, static_cast<const dcsb_port_write *>(writes),
+                                                  static_cast<DcsbSchedFrame *>(frames), static_cast<DcsbSchedEntry *>(entries), out);
     return cudaGetLastError();
 }
 

@@ -22,7 +22,9 @@ extern "C" int dcsb_rom_create(dcsb_rom **out)
 static void rom_drop_batch(dcsb_rom *rom)
 {
     if (rom->batch) { dcsb_batch_destroy(rom->batch); rom->batch = nullptr; }
+    if (rom->d_seq_streams) { cudaFree(rom->d_seq_streams); rom->d_seq_streams = nullptr; }
     rom->streams.clear();
+    rom->seq_streams.clear();
     rom->stream_by_addr.clear();
 }
 
@@ -180,6 +182,11 @@ static int rom_prepare(dcsb_ctx *ctx, dcsb_rom *rom)
             rom->streams[i].nplay = b->host_status[i] ? 0 : np[i];
             rom->streams[i].nbytes = b->host_status[i] ? 0 : 2 + b->recs[i].hdr_len + (eb[i] + 7) / 8;
         }
+    }
+    rom->build_seq_streams();
+    if (!rom->seq_streams.empty()) {
+        CK(cudaMalloc(&rom->d_seq_streams, rom->seq_streams.size() * sizeof(DcsbSeqStream)), "cudaMalloc(stream table)");
+        CK(cudaMemcpy(rom->d_seq_streams, rom->seq_streams.data(), rom->seq_streams.size() * sizeof(DcsbSeqStream), cudaMemcpyHostToDevice), "H2D stream table");
     }
     return DCSB_OK;
 }
@@ -460,8 +467,10 @@ static bool is_pinned_host(const void *p)
 }
 #define DCSB_RT_MAX_CHUNKS 8
 struct DcsbTimelineCache {
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, copy = nullptr;
     DcsbBuf d_frames, d_pcm, d_csum, h_frames;
+    DcsbBuf d_all_entries, d_all_items, d_tls, d_writes, d_seqout, h_meta;     // device-side sequencer path
+    cudaEvent_t ev[DCSB_RT_MAX_CHUNKS] = { nullptr };
     DcsbBuf d_entries[DCSB_RT_MAX_CHUNKS], d_items[DCSB_RT_MAX_CHUNKS], h_entries[DCSB_RT_MAX_CHUNKS], h_items[DCSB_RT_MAX_CHUNKS];
 };
 static void timeline_cache_free(void *p)
@@ -469,13 +478,116 @@ static void timeline_cache_free(void *p)
     DcsbTimelineCache *c = static_cast<DcsbTimelineCache *>(p);
     if (!c) return;
     if (c->st) { cudaStreamSynchronize(c->st); cudaStreamDestroy(c->st); }
-    for (DcsbBuf *b : { &c->d_frames, &c->d_pcm, &c->d_csum }) b->release(false);
+    if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
+    for (cudaEvent_t &e : c->ev) if (e) cudaEventDestroy(e);
+    for (DcsbBuf *b : { &c->d_frames, &c->d_pcm, &c->d_csum, &c->d_all_entries, &c->d_all_items, &c->d_tls, &c->d_writes, &c->d_seqout }) b->release(false);
     c->h_frames.release(true);
+    c->h_meta.release(true);
     for (int k = 0; k < DCSB_RT_MAX_CHUNKS; ++k) {
         c->d_entries[k].release(false); c->d_items[k].release(false);
         c->h_entries[k].release(true); c->h_items[k].release(true);
     }
     delete c;
+}
+
+// The device-side route (the default): the track interpreter runs on the GPU, one thread per timeline
+// (dcsb_seq_kernel), straight into the schedule arrays the mix kernel reads.  Host work: flatten the port writes
+// (a few bytes per event), lay out the work items (known from the frame counts alone).  The mix kernel runs chunk
+// by chunk on one stream while the PCM of the chunk before goes down the link on another.
+static int render_timelines_device(dcsb_ctx *ctx, dcsb_rom *rom, DcsbTimelineCache &tc, const dcsb_timeline *timelines, size_t n,
+                                   const std::vector<uint64_t> &first, bool fam93, bool packed, bool pinned,
+                                   int16_t *pcm_out, const uint64_t *pcm_offsets, dcsb_timeline_result *results)
+{
+    dcsb_batch *b = rom->batch;
+    const uint64_t total = first[n];
+    const uint32_t item_len = mix_item_len(fam93, total);
+    if (total * DCSB_MAX_CHANNELS >= 0xFFFFFFFFull) return fail(ctx, DCSB_E_ARG, "dcsb_render_timelines: more than 2^29 frames in one call");
+    size_t nwrites = 0, nitems = 0;
+    for (size_t t = 0; t < n; ++t) { nwrites += timelines[t].n_writes; nitems += (timelines[t].n_frames + item_len - 1) / item_len; }
+#define ENS(buf, bytes, host, what) do { cudaError_t e_ = (buf).ensure((bytes), (host)); if (e_ != cudaSuccess) return fail(ctx, DCSB_E_NOMEM, what, e_); } while (0)
+    const size_t b_tls = n * sizeof(DcsbSeqTimeline), b_wr = std::max<size_t>(1, nwrites) * sizeof(dcsb_port_write), b_it = std::max<size_t>(1, nitems) * sizeof(DcsbMixItem);
+    ENS(tc.h_meta, b_tls + b_wr + b_it + 64, true, "cudaMallocHost(timeline descriptors)");
+    ENS(tc.d_tls, b_tls, false, "cudaMalloc(timelines)");
+    ENS(tc.d_writes, b_wr, false, "cudaMalloc(port writes)");
+    ENS(tc.d_all_items, b_it, false, "cudaMalloc(mix items)");
+    ENS(tc.d_frames, total * sizeof(DcsbSchedFrame), false, "cudaMalloc(schedule frames)");
+    ENS(tc.d_all_entries, total * DCSB_MAX_CHANNELS * sizeof(DcsbSchedEntry), false, "cudaMalloc(schedule entries)");
+    ENS(tc.d_seqout, n * 8, false, "cudaMalloc(sequencer results)");
+    ENS(tc.d_pcm, total * 480, false, "cudaMalloc(pcm)");
+    ENS(tc.d_csum, n * 8, false, "cudaMalloc(checksums)");
+#undef ENS
+    if (!tc.copy) CK(cudaStreamCreateWithFlags(&tc.copy, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (cudaEvent_t &ev : tc.ev) if (!ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate");
+    uint8_t *hm = static_cast<uint8_t *>(tc.h_meta.p);
+    DcsbSeqTimeline *htl = reinterpret_cast<DcsbSeqTimeline *>(hm);
+    dcsb_port_write *hw = reinterpret_cast<dcsb_port_write *>(hm + b_tls);
+    DcsbMixItem *hi = reinterpret_cast<DcsbMixItem *>(hm + b_tls + b_wr);
+    // chunks of about equal frame counts (whole timelines); small calls are one chunk
+    const size_t nchunks = (size_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(DCSB_RT_MAX_CHUNKS, n), total / 65536));
+    std::vector<size_t> cut(nchunks + 1, n), icut(nchunks + 1, 0);
+    cut[0] = 0;
+    for (size_t k = 1, t = 0; k < nchunks; ++k) {
+        while (t < n && first[t] < total * k / nchunks) ++t;
+        cut[k] = t;
+    }
+    size_t w = 0, it = 0, k = 0;
+    for (size_t t = 0; t < n; ++t) {
+        while (k + 1 <= nchunks && t == cut[k]) icut[k++] = it;
+        const dcsb_timeline &tl = timelines[t];
+        htl[t] = DcsbSeqTimeline{ (uint32_t)w, tl.n_writes, tl.n_frames, (uint32_t)first[t], tl.master_volume };
+        for (uint32_t i = 0; i < tl.n_writes; ++i) hw[w++] = tl.writes[i];
+        const uint32_t f0 = (uint32_t)first[t];
+        for (uint32_t f = 0; f < tl.n_frames; f += item_len) hi[it++] = DcsbMixItem{ f0 + f, std::min<uint32_t>(item_len, tl.n_frames - f), f0, (uint32_t)t };
+    }
+    while (k <= nchunks) icut[k++] = it;
+    CK(cudaMemsetAsync(tc.d_csum.p, 0, n * 8, tc.st), "memset checksums");
+    CK(cudaMemcpyAsync(tc.d_tls.p, htl, b_tls, cudaMemcpyHostToDevice, tc.st), "H2D timelines");
+    if (nwrites) CK(cudaMemcpyAsync(tc.d_writes.p, hw, nwrites * sizeof(dcsb_port_write), cudaMemcpyHostToDevice, tc.st), "H2D port writes");
+    CK(cudaMemcpyAsync(tc.d_all_items.p, hi, nitems * sizeof(DcsbMixItem), cudaMemcpyHostToDevice, tc.st), "H2D mix items");
+    DcsbRomView dv = rom->view();
+    dv.image = b->d_slab;
+    dv.streams = rom->d_seq_streams;
+    CK(dcsb_launch_seq(&dv, static_cast<const DcsbSeqTimeline *>(tc.d_tls.p), (int)n, tc.d_writes.p, tc.d_frames.p, tc.d_all_entries.p,
+                       static_cast<uint32_t *>(tc.d_seqout.p), tc.st), "sequencer kernel launch");
+    cudaError_t e = cudaSuccess;
+    for (size_t c = 0; c < nchunks && e == cudaSuccess; ++c) {
+        const size_t t0 = cut[c], t1 = cut[c + 1];
+        if (t0 == t1 || icut[c + 1] == icut[c]) continue;
+        e = dcsb_launch_mix(fam93, b->d_slab, b->d_recs, static_cast<DcsbMixItem *>(tc.d_all_items.p) + icut[c], (int)(icut[c + 1] - icut[c]),
+                            tc.d_frames.p, tc.d_all_entries.p, ctx->d_tables, b->scan, (int16_t *)tc.d_pcm.p, (unsigned long long *)tc.d_csum.p, tc.st);
+        if (e == cudaSuccess && pinned) {
+            const uint64_t cf0 = first[t0], cfn = first[t1] - first[t0];
+            e = cudaEventRecord(tc.ev[c], tc.st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(tc.copy, tc.ev[c], 0);
+            if (e == cudaSuccess && cfn)
+                e = cudaMemcpyAsync(pcm_out + cf0 * 240, (const int16_t *)tc.d_pcm.p + cf0 * 240, cfn * 480, cudaMemcpyDeviceToHost, tc.copy);
+        }
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(tc.st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(tc.copy);
+    if (e == cudaSuccess && !pinned) {
+        if (packed) e = cudaMemcpy(pcm_out, tc.d_pcm.p, total * 480, cudaMemcpyDeviceToHost);
+        else
+            for (size_t t = 0; t < n && e == cudaSuccess; ++t)
+                if (timelines[t].n_frames)
+                    e = cudaMemcpy(pcm_out + pcm_offsets[t], (const int16_t *)tc.d_pcm.p + first[t] * 240,
+                                   (size_t)timelines[t].n_frames * 480, cudaMemcpyDeviceToHost);
+    }
+    if (e == cudaSuccess && results) {
+        std::vector<unsigned long long> cs(n);
+        std::vector<uint32_t> so(2 * n);
+        e = cudaMemcpy(cs.data(), tc.d_csum.p, n * 8, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(so.data(), tc.d_seqout.p, n * 8, cudaMemcpyDeviceToHost);
+        for (size_t t = 0; t < n; ++t) {
+            results[t].status = so[2 * t] ? DCSB_E_STOPPED : DCSB_OK;
+            results[t].frames = timelines[t].n_frames;
+            results[t].checksum = cs[t];
+            results[t].n_host_bytes = so[2 * t + 1];
+            results[t].reserved = 0;
+        }
+    }
+    if (e != cudaSuccess) return fail(ctx, DCSB_E_CUDA, "dcsb_render_timelines", e);
+    return DCSB_OK;
 }
 
 extern "C" int dcsb_render_timelines(dcsb_ctx *ctx, dcsb_rom *rom, const dcsb_timeline *timelines, size_t n,
@@ -508,6 +620,12 @@ extern "C" int dcsb_render_timelines(dcsb_ctx *ctx, dcsb_rom *rom, const dcsb_ti
     bool packed = true;
     for (size_t t = 0; t < n && pcm_offsets; ++t) if (pcm_offsets[t] != first[t] * 240) packed = false;
     const bool pinned = packed && is_pinned_host(pcm_out) && is_pinned_host(pcm_out + total * 240 - 1);
+    // DCSB_SEQ_HOST=1: the track interpreters on host threads (the route of round 1; kept for comparison and tests)
+    if (!getenv("DCSB_SEQ_HOST")) {
+        const int drc = render_timelines_device(ctx, rom, tc, timelines, n, first, fam93, packed, pinned, pcm_out, pcm_offsets, results);
+        lap("device route done", -1);
+        return drc;
+    }
     const uint32_t item_len = mix_item_len(fam93, total);
 #define ENS(buf, bytes, host, what) do { cudaError_t e_ = (buf).ensure((bytes), (host)); if (e_ != cudaSuccess) return fail(ctx, DCSB_E_NOMEM, what, e_); } while (0)
     ENS(tc.d_frames, total * sizeof(DcsbSchedFrame), false, "cudaMalloc(schedule frames)");

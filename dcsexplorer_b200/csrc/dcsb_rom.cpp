@@ -528,358 +528,74 @@ int dcsb_rom_load_zip_impl(dcsb_rom *rom, const char *path, const char *explicit
 }
 
 // ======================================================================================
-// sequencer
-DcsbSequencer::DcsbSequencer(const dcsb_rom *r) : rom(r) { memset(vars, 0, sizeof(vars)); }
+// sequencer: the core lives in dcsb_seq.cuh (shared with the device build); this is the player's instance of it
+DcsbRomView dcsb_rom::view() const
+{
+    DcsbRomView v;
+    memset(&v, 0, sizeof(v));
+    v.image = image.data();
+    for (int i = 0; i < 8; ++i) {
+        v.chip_ofs[i] = image_ofs[i];
+        v.chip_size[i] = chip[i].size;
+        v.chip_mask[i] = chip[i].mask;
+        v.present[i] = chip[i].present ? 1 : 0;
+    }
+    v.hw = hw;
+    v.os = os;
+    v.nominal_version = nominal_version;
+    v.n_tracks = n_tracks;
+    v.totan = totan ? 1 : 0;
+    v.track_index = track_index;
+    v.indirect_index = indirect_index;
+    v.streams = seq_streams.data();
+    v.n_streams = (uint32_t)seq_streams.size();
+    return v;
+}
+
+void dcsb_rom::build_seq_streams()
+{
+    seq_streams.resize(streams.size());
+    for (size_t i = 0; i < streams.size(); ++i)
+        seq_streams[i] = DcsbSeqStream{ streams[i].linear & 0xFFFFFFu, streams[i].nplay, streams[i].status, (uint32_t)i };
+    std::sort(seq_streams.begin(), seq_streams.end(), [](const DcsbSeqStream &a, const DcsbSeqStream &b) { return a.linear < b.linear; });
+}
+
+DcsbSequencer::DcsbSequencer(const dcsb_rom *r) : rom(r) { dcsb_seq_init(st); }
+
+void DcsbSequencer::drain_host_bytes()
+{
+    // (a frame hands back at most DCSB_SEQ_FRAME_HOST_BYTES bytes with their values; a well-formed program sends a few)
+    const uint32_t n = st.host_n < DCSB_SEQ_FRAME_HOST_BYTES ? st.host_n : DCSB_SEQ_FRAME_HOST_BYTES;
+    for (uint32_t i = 0; i < n; ++i) { host_bytes.push_back(st.host_buf[i]); host_byte_frames.push_back(st.frame_no); }
+    st.host_n = 0;
+}
 
 void DcsbSequencer::soft_boot()
 {
-    for (Channel &c : chan) { c.stop = false; c.volume = 0xFF; }
-    set_master_volume(0x67);            // DCSDecoder's default volume until the host says otherwise
-    port_bytes = 0;
+    for (int i = 0; i < DCSB_MAX_CHANNELS; ++i) { st.chan[i].stop = false; st.chan[i].volume = 0xFF; }
+    dcsb_seq_set_master_volume(st, 0x67);       // DCSDecoder's default volume until the host says otherwise
+    st.port_bytes = 0;
 }
 
-void DcsbSequencer::set_master_volume(int vol) { vol_mult = dcsb_master_multiplier(vol); }
-
-void DcsbSequencer::reset_mix(int ch)
-{
-    for (Channel &c : chan) { c.mixer[ch].reset(); c.fading &= (uint8_t)~(1u << ch); }
-}
-
-void DcsbSequencer::clear_tracks()
-{
-    for (Channel &c : chan) { c.track.clear(); c.st.active = false; }
-}
-
-void DcsbSequencer::write_port(uint8_t data)
-{
-    if (port_timeout >= 13) port_bytes = 0;
-    switch (port_bytes) {
-    case 0:
-        port_word = (uint16_t)(data << 8);
-        port_bytes = 1;
-        break;
-    case 1:
-        port_word |= data;
-        if ((port_word >= 0x55AA && port_word <= 0x55B2) || (port_word >= 0x55BA && port_word <= 0x55C1)) {
-            port_ext = port_word;
-            port_bytes = 2;
-        } else if (port_word > 0x55B2 && port_word < 0x55BA) port_bytes = 0;
-        else if (port_word == 0x55C2 || port_word == 0x55C3) {
-            const uint16_t rep = reported_version;
-            to_host((uint8_t)((port_word == 0x55C2 ? rep >> 8 : rep) & 0xFF));
-            port_bytes = 0;
-        } else if (port_word & 0x8000) port_bytes = 0;
-        else if (port_word == 0x03E7 && rom->totan) { to_host(0x11); port_bytes = 0; }
-        else { cmdq.push_back(port_word); port_bytes = 0; }
-        break;
-    case 2:
-        port_word = data;
-        port_bytes = 3;
-        break;
-    default:
-        if (port_word == (uint16_t)(data ^ 0xFF)) {
-            if (port_ext == 0x55AA) set_master_volume((uint8_t)port_word);
-            else if (port_ext <= 0x55B2) { const int ch = port_ext - 0x55AB; if (ch >= 0 && ch < DCSB_MAX_CHANNELS) chan[ch].volume = (uint8_t)port_word; }
-            // 55BA..55C1 only touch state no audio path reads
-        }
-        port_bytes = 0;
-        break;
-    }
-    port_timeout = 0;
-}
-
-void DcsbSequencer::load_track(int ch, DcsbRomPtr p)
-{
-    Channel &c = chan[ch];
-    c.track = p;
-    c.st.active = false;
-    c.track_counter = 0;
-    c.timer.clear();
-    c.loops.clear();
-    done_mask &= ~(1u << ch);
-    reset_mix(ch);
-}
-
-void DcsbSequencer::start_stream(int sch, int source, int loops, uint32_t linear)
-{
-    Channel &c = chan[sch];
-    const DcsbRomPtr sp = rom->make_ptr(linear);
-    Stream &s = c.st;
-    s.nframes = s.counter = (uint16_t)rom->be(sp, 2);
-    s.active = true;
-    s.at_start = true;
-    s.pos = 0;
-    auto it = rom->stream_by_addr.find(linear & 0xFFFFFFu);
-    s.id = it == rom->stream_by_addr.end() ? 0xFFFFFFFFu : it->second;
-    if (s.nframes == 0) return;             // the reference leaves such a stream playing: its uint16 counter wraps to 65,536 frames
-    s.loops = (uint16_t)loops;
-    if (c.source >= 0 && c.source != source) c.mixer[c.source].reset();
-    c.source = source;
-}
-
-void DcsbSequencer::load_stream(int ch, uint32_t linear, int level)
-{
-    if (ch < 0 || ch >= DCSB_MAX_CHANNELS) return;
-    chan[ch].track.clear();
-    start_stream(ch, ch, 1, linear);
-    Mixer &m = chan[ch].mixer[ch];
-    m.reset();
-    m.cur = m.target = level << 6;
-}
-
-void DcsbSequencer::mix_op(int cur, DcsbRomPtr &p, int mode, bool fade)
-{
-    const int target_ch = rom->u8(p) & 7;       // (the reference indexes with the raw byte)
-    const int param = (int)(int8_t)rom->u8(p, 1) << 6;
-    p.ofs += 2;
-    int steps = 0;
-    if (fade) { steps = (int)rom->be(p, 2); p.ofs += 2; }
-    Mixer &m = chan[target_ch].mixer[cur];
-    m.steps = steps;
-    if (steps) chan[target_ch].fading |= (uint8_t)(1u << cur); else chan[target_ch].fading &= (uint8_t)~(1u << cur);
-    const int old = m.cur;
-    int lvl = mode == 0 ? param : (mode == 1 ? old + param : old - param);
-    const int delta = lvl - old;                // taken before the range limit, as the original does
-    lvl = std::max(-8191, std::min(8191, lvl));
-    m.target = lvl;
-    if (steps != 0) m.delta = delta / steps;
-    else m.cur = lvl;
-}
-
-void DcsbSequencer::exec_track(int cur)
-{
-    Channel &me = chan[cur];
-    DcsbRomPtr p = me.track;
-    if (p.null()) return;
-    for (;;) {
-        // A track program that loops without ever waiting (or queues itself over and over) would keep the
-        // reference's MainLoop -- and a whole dcsb_render_timelines batch with it -- busy for ever.  No
-        // well-formed program comes near this many steps in one 7.68 ms frame: treat it like the other
-        // malformed-program cases (bad opcode / track type): self-reset, fatal after four in a row.
-        if (++steps_this_frame > DCSB_MAX_STEPS_PER_FRAME || cmdq.size() > DCSB_MAX_QUEUED_COMMANDS) throw Reset();
-        const uint32_t wait = rom->be(p, 2);
-        if (wait == 0xFFFF || me.track_counter != wait) { me.track = p; return; }
-        p.ofs += 2;
-        me.track_counter = 0;
-        const int op = rom->u8(p);
-        p.ofs += 1;
-        switch (op) {
-        case 0x00:
-            me.track.clear();
-            me.st.active = false;
-            me.loops.clear();
-            me.timer.clear();
-            reset_mix(cur);
-            return;
-        case 0x01: {
-            const int sch = rom->u8(p) & 7;
-            if (sch == 5) chan[5].max_override = false;
-            const uint32_t addr = rom->be(p, 3, 1);
-            const int loops = rom->u8(p, 4);
-            p.ofs += 5;
-            start_stream(sch, cur, loops, addr);
-            break;
-        }
-        case 0x02: {
-            const int t = rom->u8(p) & 7;
-            p.ofs += 1;
-            if (chan[t].st.active) { chan[t].st.active = false; reset_mix(t); }
-            chan[t].track.clear();
-            chan[t].timer.clear();
-            if (me.track.null()) return;
-            break;
-        }
-        case 0x03:
-            cmdq.push_back((uint16_t)rom->be(p, 2));
-            p.ofs += 2;
-            break;
-        case 0x04:
-            if (rom->os == DCSB_OS93A) {
-                const uint8_t b = rom->u8(p);
-                const uint16_t counter = (uint16_t)rom->be(p, 2, 1);
-                p.ofs += 3;
-                if (b == 0) me.timer.clear();
-                else {
-                    to_host(b);
-                    if (counter) { me.timer.data = b; me.timer.interval = me.timer.counter = counter; }
-                    else me.timer.clear();
-                }
-            } else {
-                const uint8_t b = rom->u8(p);
-                p.ofs += 1;
-                to_host(b);
-                if (rom->nominal_version == 0x0105) {
-                    if (b == 0x69) chan[5].max_override = true;
-                    else if (b == 0x6A) chan[5].max_override = false;
-                }
-            }
-            break;
-        case 0x05: {
-            const int t = rom->u8(p) & 7;
-            p.ofs += 1;
-            const int type = chan[t].next_type;
-            if (type == 0) break;
-            chan[t].next_type = 0;
-            if (type == 2) cmdq.push_back(chan[t].next_link);
-            else if (type == 3) {
-                // Catalog[$43][low byte][variables[high byte]] -> track number
-                const uint16_t link = chan[t].next_link;
-                const uint32_t table = rom->u2_be(rom->indirect_index + 3u * (link & 0xFF), 3);
-                DcsbRomPtr tp = rom->make_ptr(table);
-                cmdq.push_back((uint16_t)rom->be(tp, 2, 2u * vars[(link >> 8) & 0xFF]));
-            }
-            break;
-        }
-        case 0x06:
-            if (rom->os != DCSB_OS93A && rom->os != DCSB_OS93B) {
-                vars[rom->u8(p)] = rom->u8(p, 1);
-                p.ofs += 2;
-            }
-            break;
-        case 0x07: case 0x08: case 0x09: mix_op(cur, p, op - 0x07, false); break;
-        case 0x0A: case 0x0B: case 0x0C: mix_op(cur, p, op - 0x0A, true); break;
-        case 0x0D: break;
-        case 0x0E: {
-            const uint16_t n = rom->u8(p);
-            p.ofs += 1;
-            me.loops.push_back(Loop{ n, p });
-            break;
-        }
-        case 0x0F:
-            if (!me.loops.empty()) {
-                Loop &l = me.loops.back();
-                if (l.counter == 0) p = l.pos;
-                else if (l.counter == 1) me.loops.pop_back();
-                else { --l.counter; p = l.pos; }
-            }
-            break;
-        case 0x10: p.ofs += 2; break;           // 0x10-0x12 set parameters nothing audible reads
-        case 0x11: case 0x12: p.ofs += 4; break;
-        default: throw Reset();
-        }
-    }
-}
-
-void DcsbSequencer::update_levels()
-{
-    for (Channel &c : chan)
-        for (unsigned f = c.fading; f; f &= f - 1) {        // only the mixers with a fade in progress
-            const int k = __builtin_ctz(f);
-            Mixer &m = c.mixer[k];
-            if (m.steps == 1) { m.steps = 0; m.cur = m.target; }
-            else if (m.steps > 1) {
-                --m.steps;
-                m.cur = std::max(-8191, std::min(8191, m.cur + m.delta));
-            }
-            if (m.steps == 0) c.fading &= (uint8_t)~(1u << k);
-        }
-    for (Channel &c : chan) {
-        int sum = 0;
-        for (const Mixer &m : c.mixer) sum += m.cur;
-        // the multiplier ladder (16 dependent 1.15 multiplies) only when its inputs moved: most frames no fade is running
-        sum = std::max(-8191, std::min(8191, sum));
-        const uint32_t key = (uint32_t)(sum + 8192) | ((uint32_t)c.volume << 14) | (c.max_override ? 1u << 30 : 0u);
-        if (key != c.level_key) {
-            c.level_key = key;
-            c.level_mult = dcsb_level_multiplier(sum, rom->os, c.volume, c.max_override ? 1 : 0);
-        }
-        c.mult = c.level_mult;
-    }
-    for (Channel &c : chan) {
-        c.track_counter += 1;
-        if (c.timer.interval != 0 && --c.timer.counter == 0) { c.timer.counter = c.timer.interval; to_host(c.timer.data); }
-    }
-}
-
-void DcsbSequencer::main_loop(std::vector<DcsbSchedEntry> &entries, DcsbSchedFrame &fr)
-{
-    steps_this_frame = 0;
-    // channels the decoder's error path flagged last frame
-    for (int ch = 0; ch < DCSB_MAX_CHANNELS; ++ch) {
-        Channel &c = chan[ch];
-        if (!c.stop) continue;
-        c.stop = false;
-        if (c.st.active) { c.st.active = false; reset_mix(ch); }
-        c.timer.clear();
-        c.track.clear();
-    }
-    // pending commands = indices into the track index
-    while (!cmdq.empty()) {
-        if (++steps_this_frame > DCSB_MAX_STEPS_PER_FRAME) { cmdq.clear(); throw Reset(); }
-        const uint16_t cmd = cmdq.front();
-        cmdq.pop_front();
-        if (cmd >= rom->n_tracks) continue;
-        const uint32_t ofs = rom->u2_be(rom->track_index + 3u * cmd, 3);
-        if ((ofs & 0xFF0000u) == 0xFF0000u) continue;
-        DcsbRomPtr tp = rom->make_ptr(ofs);
-        const int type = rom->u8(tp), ch = rom->u8(tp, 1) & 7;
-        tp.ofs += 2;
-        if (type == 1) load_track(ch, tp);
-        else if (type <= 3) { chan[ch].next_type = (uint8_t)type; chan[ch].next_link = (uint16_t)rom->be(tp, 2); }
-        else throw Reset();
-    }
-    // run the track programs until every channel has had its turn
-    done_mask = 0;
-    for (int ch = 0; done_mask != 0xFFu; ch = (ch + 1) % DCSB_MAX_CHANNELS)
-        if (!(done_mask & (1u << ch))) { exec_track(ch); done_mask |= 1u << ch; }
-    // gain staging (MainLoop :227-269)
-    uint16_t mix[8], eff[8];
-    unsigned active = 0, maxo = 0;
-    for (int i = 0; i < DCSB_MAX_CHANNELS; ++i) {
-        mix[i] = chan[i].mult;
-        if (chan[i].st.active) active |= 1u << i;
-        if (chan[i].max_override) maxo |= 1u << i;
-    }
-    fr.vs = (uint8_t)dcsb_gain_stage(mix, active, maxo, vol_mult, eff);
-    for (int i = 0; i < DCSB_MAX_CHANNELS; ++i) chan[i].mult = eff[i];
-    // one frame from each active stream, channel order (DecodeStream :1546-1589)
-    for (int ch = 0; ch < DCSB_MAX_CHANNELS; ++ch) {
-        Channel &c = chan[ch];
-        Stream &s = c.st;
-        if (!s.active) continue;
-        s.at_start = false;
-        bool decodes = false;
-        if (s.id != 0xFFFFFFFFu) {
-            const DcsbStreamFacts &sf = rom->streams[s.id];
-            if (s.pos < sf.nplay) {
-                decodes = true;
-                if (sf.status == DCSB_E_STOPPED && s.pos + 1u == sf.nplay) c.stop = true;      // decoder error path: partial frame, channel stops
-            } else c.stop = true;               // frame cannot be decoded (truncated / invalid band type): silence, channel stops
-        } else c.stop = true;                   // a stream the ROM scan never saw: nothing to decode
-        if (decodes) entries.push_back(DcsbSchedEntry{ s.id, s.pos, c.mult });
-        ++s.pos;
-        if (--s.counter != 0) continue;
-        s.counter = s.nframes;
-        s.pos = 0;
-        s.at_start = true;
-        if (s.loops == 0) continue;
-        if (--s.loops != 0) continue;
-        s.active = false;
-        c.source = -1;
-    }
-    update_levels();
-    if (++port_timeout > 13) port_timeout = 13;
-}
+void DcsbSequencer::set_master_volume(int vol) { dcsb_seq_set_master_volume(st, vol); }
+void DcsbSequencer::clear_tracks() { dcsb_seq_clear_tracks(st); }
+void DcsbSequencer::write_port(uint8_t data) { dcsb_seq_write_port(st, rom->view(), data); drain_host_bytes(); }
+void DcsbSequencer::load_stream(int ch, uint32_t linear, int level) { dcsb_seq_load_stream(st, rom->view(), ch, linear, level); }
 
 bool DcsbSequencer::frame(std::vector<DcsbSchedFrame> &frames, std::vector<DcsbSchedEntry> &entries)
 {
     DcsbSchedFrame fr{ (uint32_t)entries.size(), 0, 8, 0, 0 };
-    if (!fatal) {
-        // a self-reset (bad track type / opcode) is retried; four in a row are fatal (DCSDecoder.cpp:1631-1668)
-        for (int tries = 0;; ++tries) {
-            const size_t mark = entries.size();
-            try {
-                main_loop(entries, fr);
-                break;
-            } catch (const Reset &) {
-                entries.resize(mark);
-                if (tries >= 3) { fatal = true; break; }
-            }
-        }
-    }
-    if (fatal) { entries.resize(fr.first_entry); fr.vs = 8; fr.flags = DCSB_FRAME_MUTE; }
-    fr.n_entries = (uint8_t)(entries.size() - fr.first_entry);
+    DcsbSchedEntry e[DCSB_MAX_CHANNELS];
+    // (host bytes of this frame carry its number: the core counts the frame at the end of the pass)
+    const DcsbRomView v = rom->view();
+    const uint32_t this_frame = st.frame_no;
+    const bool ok = dcsb_seq_frame(st, v, &fr, e);
+    for (int i = 0; i < fr.n_entries; ++i) entries.push_back(e[i]);
     frames.push_back(fr);
-    ++frame_no;
-    return !fatal;
+    const uint32_t n = st.host_n < DCSB_SEQ_FRAME_HOST_BYTES ? st.host_n : DCSB_SEQ_FRAME_HOST_BYTES;
+    for (uint32_t i = 0; i < n; ++i) { host_bytes.push_back(st.host_buf[i]); host_byte_frames.push_back(this_frame); }
+    st.host_n = 0;
+    fatal = st.fatal;
+    frame_no = st.frame_no;
+    return ok;
 }

@@ -20,17 +20,7 @@
 #include <vector>
 #include "../../include/dcsb200.h"
 
-enum { DCSB_HW_UNKNOWN = 0, DCSB_HW_INVALID = 1, DCSB_HW_DCS93 = 2, DCSB_HW_DCS95 = 3 };
-#define DCSB_MAX_CHANNELS 8
-
-// cursor into one chip image; chip < 0 is the null pointer
-struct DcsbRomPtr {
-    int chip = -1;
-    uint32_t ofs = 0;
-    bool null() const { return chip < 0; }
-    void clear() { chip = -1; ofs = 0; }
-    bool operator==(const DcsbRomPtr &o) const { return chip == o.chip && ofs == o.ofs; }
-};
+#include "dcsb_seq.cuh"      // DcsbRomPtr, DcsbRomView, the sequencer core (shared with the device build)
 
 // what the sequencer needs to know about a stream without decoding it: its length and where
 // (if anywhere) the decoder's error path stops the channel.  Filled from the GPU scan.
@@ -66,6 +56,11 @@ struct dcsb_rom {
     struct dcsb_batch *batch = nullptr; // the streams resident in HBM (owned; dcsb_api.cu)
     std::vector<uint8_t> image;         // all chips back to back (what the device slab mirrors)
     uint32_t image_ofs[8] = { 0 };
+    std::vector<DcsbSeqStream> seq_streams;     // `streams` as the sequencer core looks them up: sorted by address
+    DcsbRomView view() const;           // the ROM set as the sequencer core reads it (host pointers)
+    void build_seq_streams();           // seq_streams from streams (call when the scan results are in)
+    // the same on the device (dcsb_player.cu; owned: freed with the batch)
+    DcsbSeqStream *d_seq_streams = nullptr;
 
     void add(int n, const uint8_t *data, size_t size);
     int check();
@@ -81,22 +76,17 @@ struct dcsb_rom {
     int opcode_operand_bytes(int opcode) const;     // as GetTrackInfo / the decompiler count them
 };
 
-// One output frame's worth of mixing work
-struct DcsbSchedEntry { uint32_t stream; uint16_t frame; uint16_t mult; };
-#define DCSB_FRAME_MUTE 1       // the decoder is in its fatal-error state: pure silence, no overlap tail
-struct DcsbSchedFrame { uint32_t first_entry; uint8_t n_entries; uint8_t vs; uint8_t flags; uint8_t pad; };
-
-#define DCSB_MAX_STEPS_PER_FRAME 65536u        // track-program steps in one frame before the program counts as runaway
-#define DCSB_MAX_QUEUED_COMMANDS 4096u         // queued track commands before the queue counts as runaway
+// The decoder instance the player drives: the sequencer core (dcsb_seq.cuh) plus the host-side conveniences --
+// host bytes kept with the frame they belong to, copyable as a whole (the render-ahead player snapshots it).
 struct DcsbSequencer {
     explicit DcsbSequencer(const dcsb_rom *rom);
     void soft_boot();                               // Initialize(): channel defaults, default volume
     void set_master_volume(int vol);
     void write_port(uint8_t b);                     // WriteDataPort + IRQ2Handler (taken before the next frame)
-    void add_track_command(uint16_t track) { cmdq.push_back(track); }
+    void add_track_command(uint16_t track) { dcsb_seq_q_push(st, track); }
     void load_stream(int ch, uint32_t linear, int level);   // LoadAudioStream(ch, ptr, level)
     void clear_tracks();
-    bool stream_playing(int ch) const { return ch >= 0 && ch < DCSB_MAX_CHANNELS && chan[ch].st.active; }
+    bool stream_playing(int ch) const { return ch >= 0 && ch < DCSB_MAX_CHANNELS && st.chan[ch].st.active; }
     // run one main-loop pass; appends the frame to `frames` / `entries`.  Returns false once the
     // decoder is in its fatal-error state (the frame is then silent).
     bool frame(std::vector<DcsbSchedFrame> &frames, std::vector<DcsbSchedEntry> &entries);
@@ -106,53 +96,9 @@ struct DcsbSequencer {
     uint32_t frame_no = 0;
 
 private:
-    struct Mixer { int cur = 0, target = 0, delta = 0, steps = 0; void reset() { cur = target = steps = 0; } };
-    struct Timer { uint8_t data = 0; uint16_t interval = 0, counter = 0; void clear() { interval = counter = 0; } };
-    struct Loop { uint16_t counter; DcsbRomPtr pos; };
-    struct Stream {
-        bool active = false;
-        bool at_start = false;
-        uint32_t id = 0xFFFFFFFFu;                  // index into rom->streams (0xFFFFFFFF: unknown address, plays silence)
-        uint16_t nframes = 0, counter = 0, loops = 0, pos = 0;
-    };
-    struct Channel {
-        DcsbRomPtr track;
-        uint16_t track_counter = 0;
-        uint8_t next_type = 0;
-        uint16_t next_link = 0;
-        bool stop = false;
-        Stream st;
-        int source = -1;
-        Mixer mixer[DCSB_MAX_CHANNELS];
-        uint8_t fading = 0;                         // mixers with a fade in progress (steps != 0), one bit each
-        bool max_override = false;
-        uint16_t mult = 0x7FFF;
-        uint32_t level_key = 0xFFFFFFFFu;           // (level sum, volume, override) the cached level_mult belongs to
-        uint16_t level_mult = 0;
-        Timer timer;
-        uint16_t volume = 0xFF;
-        std::vector<Loop> loops;
-    };
-    struct Reset {};
     const dcsb_rom *rom;
-    Channel chan[DCSB_MAX_CHANNELS];
-    uint8_t vars[256];
-    std::deque<uint16_t> cmdq;
-    uint16_t port_word = 0, port_ext = 0;
-    int port_bytes = 0, port_timeout = 0;
-    uint16_t vol_mult = 0;
-    uint16_t reported_version = 0x0106;         // DCSDecoderNative.h:168
-    unsigned done_mask = 0;
-    uint32_t steps_this_frame = 0;              // track-program steps + queued commands taken in the current main-loop pass
-
-    void main_loop(std::vector<DcsbSchedEntry> &entries, DcsbSchedFrame &fr);
-    void exec_track(int ch);
-    void load_track(int ch, DcsbRomPtr p);
-    void start_stream(int stream_ch, int source_ch, int loops, uint32_t linear);
-    void reset_mix(int ch);
-    void mix_op(int cur, DcsbRomPtr &p, int mode, bool fade);
-    void update_levels();
-    void to_host(uint8_t b) { host_bytes.push_back(b); host_byte_frames.push_back(frame_no); }
+    DcsbSeqState st;
+    void drain_host_bytes();
 };
 
 // zip container (stored / deflate entries) -> named files; false + err on failure

@@ -179,6 +179,7 @@ extern "C" int hostsim_rom_render(const uint8_t *const *imgs, const size_t *size
         rom.streams[i].nplay = p.host_status[i] ? 0 : nplay[i];
         if (p.host_status[i]) nplay[i] = 0;
     }
+    rom.build_seq_streams();
     // schedules
     std::vector<DcsbSchedFrame> frames;
     std::vector<DcsbSchedEntry> entries;

@@ -54,6 +54,29 @@ def test_gpu_timeline_matches_golden(ctx, rom_golden, name, kw):
     rom.close()
 
 
+@pytest.mark.parametrize("name,kw", romscen.SCENARIOS)
+def test_gpu_device_sequencer_equals_host_sequencer(ctx, monkeypatch, name, kw):
+    """dcsb_render_timelines runs the track interpreter on the GPU (one thread per timeline, dcsb_seq_kernel);
+    DCSB_SEQ_HOST=1 runs the same core on host threads.  Same PCM, checksums, status and host-byte counts, for
+    many timelines with shifted command times, different volumes and lengths (so that the 32 instances of a warp
+    are not in step)."""
+    import dcsexplorer_b200 as dx
+    sc = romscen.make_scenario(**kw)
+    rom = dx.Rom(sc["images"])
+    tls = [([(f + (i * 7) % 23, b) for f, b in sc["writes"]], sc["n_frames"] - (i % 5) * 17, 255 - (i * 3) % 120) for i in range(70)]
+    tls.append(([], 40, 255))                                   # nothing ever happens
+    tls.append(([(0, 0x7F), (0, 0x7F)] * 3, 30, 200))           # commands for tracks that do not exist
+    pcm_d, res_d = ctx.render_timelines(rom, tls)
+    monkeypatch.setenv("DCSB_SEQ_HOST", "1")
+    pcm_h, res_h = ctx.render_timelines(rom, tls)
+    monkeypatch.delenv("DCSB_SEQ_HOST")
+    for i in range(len(tls)):
+        assert np.array_equal(pcm_d[i], pcm_h[i]), (name, i)
+        assert res_d[i] == res_h[i], (name, i, res_d[i], res_h[i])
+    assert any(r["n_host_bytes"] for r in res_d) or name == "os93b"
+    rom.close()
+
+
 def _reference_timeline(images, tl):
     """one timeline (writes, n_frames, master_volume) rendered by the unmodified reference decoder"""
     rp = ref.RomPlayer(images, tl[2])
