@@ -181,6 +181,7 @@ int dcsb_batch_create_impl(dcsb_ctx *ctx, const dcsb_stream_desc *descs, size_t 
     CKB(cudaMemcpy(b->d_tiles, b->tiles.data(), b->tiles.size() * sizeof(DcsbTile), cudaMemcpyHostToDevice), "H2D tiles");
     CKB(cudaMalloc(&b->d_order, std::max<size_t>(1, n) * sizeof(uint32_t)), "cudaMalloc(order)");
     CKB(cudaMemcpy(b->d_order, prep.scan_order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice), "H2D order");
+    b->n94 = prep.n_scan94;
     CKB(cudaMalloc(&b->scan.bitpos, std::max<uint64_t>(1, frames) * sizeof(uint32_t)), "cudaMalloc(bitpos)");
     CKB(cudaMalloc(&b->scan.bt, std::max<uint64_t>(1, frames) * sizeof(uint2)), "cudaMalloc(bt)");
     CKB(cudaMalloc(&b->scan.hdrbits, std::max<uint64_t>(1, frames) * sizeof(uint16_t)), "cudaMalloc(hdrbits)");
@@ -211,7 +212,8 @@ extern "C" int dcsb_batch_launches(const dcsb_batch *b)
 {
     if (!b) return 0;
     // scan (+ the one-thread gate when scan and decode overlap) + one decode launch per transform family
-    return (b->n ? 1 : 0) + (b->n && b->ctx->overlap ? 1 : 0) + (b->ntiles94 ? 1 : 0) + (b->ntiles93 ? 1 : 0);
+    // (the scan is one kernel per layout family: lock-step warps for the 1994 layout, a lane per stream for the 1993 ones)
+    return (b->n94 ? 1 : 0) + (b->n > b->n94 ? 1 : 0) + (b->n && b->ctx->overlap ? 1 : 0) + (b->ntiles94 ? 1 : 0) + (b->ntiles93 ? 1 : 0);
 }
 
 extern "C" int dcsb_batch_launch_shape(const dcsb_batch *b, int which, int *grid, int *block)
@@ -219,8 +221,8 @@ extern "C" int dcsb_batch_launch_shape(const dcsb_batch *b, int which, int *grid
     if (!b || !grid || !block || which < 0 || which > 2) return DCSB_E_ARG;
     if (which == 0) {
         int warps, g;
-        dcsb_scan_shape((int)b->n, 0, &warps, &g);
-        *grid = b->n ? g : 0;
+        dcsb_scan_shape((int)b->n94, 0, &warps, &g);
+        *grid = b->n94 ? g : 0;
         *block = warps * 32;
         return DCSB_OK;
     }
@@ -250,7 +252,7 @@ extern "C" int dcsb_batch_decode(dcsb_batch *b, void *d_pcm, void *cuda_stream)
         so.progress = so.started = so.qctl = nullptr;
         so.queue = nullptr;
         CK(cudaEventRecord(b->ev[0], st), "event");
-        CK(dcsb_launch_scan(b->d_slab, b->d_recs, b->d_order, (int)b->n, 0, ctx->d_tables, so, st), "scan kernel launch");
+        CK(dcsb_launch_scan(b->d_slab, b->d_recs, b->d_order, (int)b->n, (int)b->n94, 0, ctx->d_tables, so, st), "scan kernel launch");
         CK(cudaEventRecord(b->ev[1], st), "event");
         CK(cudaEventRecord(b->ev[3], st), "event");
         CK(dcsb_launch_decode(b->d_slab, b->d_recs, b->d_tiles, b->ntiles94, b->ntiles93, ctx->d_tables, so,
@@ -269,9 +271,9 @@ extern "C" int dcsb_batch_decode(dcsb_batch *b, void *d_pcm, void *cuda_stream)
         if (b->nqueue94) CK(cudaMemsetAsync(b->d_queue, 0, (size_t)b->nqueue94 * sizeof(unsigned long long), st), "memset queue");
         CK(cudaEventRecord(b->ev[0], st), "event");
         CK(cudaStreamWaitEvent(ctx->aux, b->ev[0], 0), "stream wait");
-        CK(dcsb_launch_scan(b->d_slab, b->d_recs, b->d_order, (int)b->n, 0, ctx->d_tables, so, ctx->aux), "scan kernel launch");
+        CK(dcsb_launch_scan(b->d_slab, b->d_recs, b->d_order, (int)b->n, (int)b->n94, 0, ctx->d_tables, so, ctx->aux), "scan kernel launch");
         CK(cudaEventRecord(b->ev[1], ctx->aux), "event");
-        CK(dcsb_launch_gate(so, dcsb_scan_grid((int)b->n, 0), st), "gate kernel launch");
+        CK(dcsb_launch_gate(so, dcsb_scan_grid((int)b->n, (int)b->n94, 0), st), "gate kernel launch");
         CK(cudaEventRecord(b->ev[3], st), "event");
         CK(dcsb_launch_decode_queue(b->d_slab, b->d_recs, (int)b->n, b->nqueue94, ctx->d_tables, so, pcm, b->d_checksums, st), "decode kernel launch");
         CK(dcsb_launch_decode(b->d_slab, b->d_recs, b->d_tiles + b->ntiles94, 0, b->ntiles93, ctx->d_tables, so,
@@ -550,7 +552,7 @@ static int lane_slice(dcsb_ctx *ctx, DcsbLane &l, uint32_t k, int16_t *pcm_out, 
     if (l.slice) {
         const uint32_t U = l.sl_bound.back();
         const uint32_t fa = l.sl_bound[k], fb = l.sl_bound[k + 1];
-        CK(dcsb_launch_scan(slab, recs, (const uint32_t *)l.d_order.p, (int)n, concurrent, ctx->d_tables, so, l.st, fa,
+        CK(dcsb_launch_scan(slab, recs, (const uint32_t *)l.d_order.p, (int)n, (int)p.n_scan94, concurrent, ctx->d_tables, so, l.st, fa,
                             k + 1 == l.nslices ? 0xFFFFFFFFu : fb), "scan kernel launch");
         ctx->trace.mark(lane_id, (int)k, "scan", l.st);
         CK(dcsb_launch_decode(slab, recs, tiles + l.sl_off[2 * k], (int)(l.sl_off[2 * k + 1] - l.sl_off[2 * k]),
@@ -592,14 +594,14 @@ static int lane_slice(dcsb_ctx *ctx, DcsbLane &l, uint32_t k, int16_t *pcm_out, 
         so.queue = (unsigned long long *)l.d_queue.p;
         CK(cudaStreamWaitEvent(l.aux, l.ev_go, 0), "stream wait");
         CK(cudaStreamWaitEvent(l.aux, l.ev_scan, 0), "stream wait");
-        CK(dcsb_launch_scan(slab, recs, (const uint32_t *)l.d_order.p, (int)n, concurrent, ctx->d_tables, so, l.aux), "scan kernel launch");
+        CK(dcsb_launch_scan(slab, recs, (const uint32_t *)l.d_order.p, (int)n, (int)p.n_scan94, concurrent, ctx->d_tables, so, l.aux), "scan kernel launch");
         CK(cudaEventRecord(l.ev_scan, l.aux), "event");
-        CK(dcsb_launch_gate(so, dcsb_scan_grid((int)n, concurrent), l.st), "gate kernel launch");
+        CK(dcsb_launch_gate(so, dcsb_scan_grid((int)n, (int)p.n_scan94, concurrent), l.st), "gate kernel launch");
         CK(dcsb_launch_decode_queue(slab, recs, (int)n, p.nqueue94, ctx->d_tables, so, d_pcm, d_csum, l.st), "decode kernel launch");
         CK(dcsb_launch_decode(slab, recs, tiles + p.ntiles94, 0, p.ntiles93, ctx->d_tables, so, d_pcm, d_csum, l.st), "decode kernel launch");
         CK(cudaStreamWaitEvent(l.st, l.ev_scan, 0), "stream wait");
     } else {
-        CK(dcsb_launch_scan(slab, recs, (const uint32_t *)l.d_order.p, (int)n, concurrent, ctx->d_tables, so, l.st), "scan kernel launch");
+        CK(dcsb_launch_scan(slab, recs, (const uint32_t *)l.d_order.p, (int)n, (int)p.n_scan94, concurrent, ctx->d_tables, so, l.st), "scan kernel launch");
         CK(dcsb_launch_decode(slab, recs, tiles, p.ntiles94, p.ntiles93, ctx->d_tables, so, d_pcm, d_csum, l.st), "decode kernel launch");
     }
     ctx->trace.mark(lane_id, -1, "kernels", l.st);

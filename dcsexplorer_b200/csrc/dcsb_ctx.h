@@ -111,7 +111,8 @@ struct dcsb_batch {
     uint8_t *d_slab = nullptr;
     DcsbStreamRec *d_recs = nullptr;
     DcsbTile *d_tiles = nullptr;
-    uint32_t *d_order = nullptr;             // scan order (dcsb_prepare)
+    uint32_t *d_order = nullptr;             // scan order (dcsb_prepare): the n94 streams of the 1994 layout first
+    size_t n94 = 0;
     DcsbScanOut scan{};
     int16_t *d_pcm = nullptr;                // internal PCM buffer (lazy)
     unsigned long long *d_checksums = nullptr;

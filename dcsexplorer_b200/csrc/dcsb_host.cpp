@@ -216,12 +216,15 @@ void dcsb_scan_order(DcsbPrepared *p)
 {
     const size_t n = p->recs.size();
     p->scan_order.resize(n);
+    p->n_scan94 = 0;
     if (!n) return;
-    std::vector<uint32_t> rank(n);
+    // 1994-layout streams first (lock-step warps), the 1993 layouts behind them (one lane each, dcsb_scan93_kernel)
+    std::vector<uint32_t> rank, rank93;
     std::vector<uint64_t> key(n);
     for (size_t i = 0; i < n; ++i) {
-        rank[i] = (uint32_t)i;
         const DcsbStreamRec &x = p->recs[i];
+        if (x.fmt != DCSB_FMT_94) { rank93.push_back((uint32_t)i); key[i] = x.nbytes; continue; }
+        rank.push_back((uint32_t)i);
         uint32_t bucket = 0;                          // quarter-octave bucket of the frame count
         if (x.nframes) {
             int lg = 31;
@@ -229,17 +232,19 @@ void dcsb_scan_order(DcsbPrepared *p)
             bucket = 1u + (uint32_t)lg * 4u + ((lg >= 2 ? x.nframes >> (lg - 2) : x.nframes << (2 - lg)) & 3u);
         }
         const uint64_t bpf = x.nframes ? std::min<uint64_t>((uint64_t)x.nbytes * 8 / x.nframes, 0xFFFFFull) : 0;
-        key[i] = ((uint64_t)(x.fmt == DCSB_FMT_94 ? 1 : 0) << 40) | ((uint64_t)bucket << 20) | bpf;
+        key[i] = ((uint64_t)bucket << 20) | bpf;
     }
+    const size_t n94 = rank.size();
+    p->n_scan94 = n94;
     std::stable_sort(rank.begin(), rank.end(), [&](uint32_t a, uint32_t b) { return key[a] > key[b]; });
     // groups of 32 by estimated cost (frames of the longest stream x bits per frame of the densest), largest first
-    const size_t ng = (n + 31) / 32;
+    const size_t ng = (n94 + 31) / 32;
     std::vector<uint32_t> gidx(ng);
     std::vector<uint64_t> gcost(ng, 0);
     for (size_t g = 0; g < ng; ++g) {
         gidx[g] = (uint32_t)g;
         uint64_t mf = 0, mb = 0;
-        for (size_t k = g * 32; k < std::min(n, g * 32 + 32); ++k) {
+        for (size_t k = g * 32; k < std::min(n94, g * 32 + 32); ++k) {
             const DcsbStreamRec &x = p->recs[rank[k]];
             mf = std::max<uint64_t>(mf, x.nframes);
             mb = std::max<uint64_t>(mb, x.nframes ? (uint64_t)x.nbytes * 8 / x.nframes : 0);
@@ -249,13 +254,16 @@ void dcsb_scan_order(DcsbPrepared *p)
     std::stable_sort(gidx.begin(), gidx.end(), [&](uint32_t a, uint32_t b) { return gcost[a] > gcost[b]; });
     // a short last group must stay the last one (lanes are assigned by position in the order)
     size_t o = 0;
-    const size_t tail_g = (n % 32) ? ng - 1 : ng;     // index of the short group, if any
+    const size_t tail_g = (n94 % 32) ? ng - 1 : ng;   // index of the short group, if any
     for (size_t q = 0; q < ng; ++q) {
         const size_t g = gidx[q];
         if (g == tail_g) continue;
         for (size_t k = g * 32; k < g * 32 + 32; ++k) p->scan_order[o++] = rank[k];
     }
-    if (tail_g < ng) for (size_t k = tail_g * 32; k < n; ++k) p->scan_order[o++] = rank[k];
+    if (tail_g < ng) for (size_t k = tail_g * 32; k < n94; ++k) p->scan_order[o++] = rank[k];
+    // 1993 layouts: the longest chains first
+    std::stable_sort(rank93.begin(), rank93.end(), [&](uint32_t a, uint32_t b) { return key[a] > key[b]; });
+    for (uint32_t i : rank93) p->scan_order[o++] = i;
 }
 
 // Work items covering output frames [fa, fb) of every stream, in frame-major order (item k of every

@@ -120,7 +120,9 @@ struct DcsbPrepared {
     std::vector<int32_t> host_status;     // host-side rejections (0 = let the scan decide)
     std::vector<DcsbTile> tiles;          // 1994-family items first, then 1993-family tiles
     size_t concurrent_streams = 0;        // in: streams of all scans running side by side (0 = this batch alone)
-    std::vector<uint32_t> scan_order;     // streams in the order the scan assigns them to lanes: alike streams side by side
+    std::vector<uint32_t> scan_order;     // streams in the order the scan assigns them to lanes: alike streams side by side;
+                                          // the n_scan94 streams of the 1994 layout first, the 1993 layouts behind them
+    size_t n_scan94 = 0;
     int ntiles94 = 0, ntiles93 = 0;
     uint32_t item_len = 31;               // output frames per 1994-family work item
     int nqueue94 = 0;                     // work items the scan queues for the 1994-layout streams (overlapped mode)
@@ -149,12 +151,14 @@ void dcsb_pack_slab_range(const dcsb_stream_desc *descs, size_t n, const DcsbPre
 // order: device array of nstreams stream indices (NULL = identity): which stream each scan lane takes
 // [f0, f1): frames of every stream this launch walks; f0 > 0 resumes from the checkpoints the launch
 // for [.., f0) left (time-sliced chunks of dcsb_decode_streams)
-cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, const uint32_t *order, int nstreams, int concurrent,
+// n94: order[0..n94) are the streams of the 1994 layout (lock-step kernel), order[n94..nstreams) those of the 1993
+// layouts (dcsb_scan93_kernel, launched behind it on the same stream)
+cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, const uint32_t *order, int nstreams, int n94, int concurrent,
                              const DcsbTables *tables, DcsbScanOut out, cudaStream_t st, uint32_t f0 = 0, uint32_t f1 = 0xFFFFFFFFu);
 // tiles[0..ntiles94) use the 1994 transform, tiles[ntiles94..ntiles94+ntiles93) the 1993 one
 // enqueue a one-thread kernel that returns once `ctas` scan CTAs are resident (scan.started)
 cudaError_t dcsb_launch_gate(DcsbScanOut scan, int ctas, cudaStream_t st);
-int dcsb_scan_grid(int nstreams, int concurrent);   // CTAs dcsb_launch_scan uses
+int dcsb_scan_grid(int nstreams, int n94, int concurrent);   // CTAs dcsb_launch_scan uses (both kernels)
 void dcsb_decode_shapes(int nitems, int *grid_items, int *grid_queue, int *block);   // 1994-layout decode kernels: CTAs for nitems work items / of the persistent kernel
 // persistent decode over the scan's ready queue (1994-layout streams, overlapped mode)
 cudaError_t dcsb_launch_decode_queue(const uint8_t *slab, const DcsbStreamRec *streams, int nstreams, int nitems,

@@ -418,7 +418,10 @@ cudaError_t dcsb_launch_seq(const DcsbRomView *view, const DcsbSeqTimeline *tls,
                             void *frames, void *entries, uint32_t *out, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
-    dcsb_seq_kernel<<<(n + 31) / 32, 32, 0, st>>>(*view, tls, n, static_cast<const dcsb_port_write *>(writes),
+    // The interpreter is a chain of dependent loads per timeline and the lanes of a warp serialise wherever their
+    // programs part: narrow CTAs spread the timelines over every SM's schedulers and keep the serialisation short.
+    static const int block = [] { const char *e = getenv("DCSB_SEQ_BLOCK"); const int b = e ? atoi(e) : 4; return b < 1 ? 1 : (b > 32 ? 32 : b); }();
+    dcsb_seq_kernel<<<(n + block - 1) / block, block, 0, st>>>(*view, tls, n, static_cast<const dcsb_port_write *>(writes),
                                                   static_cast<DcsbSchedFrame *>(frames), static_cast<DcsbSchedEntry *>(entries), out);
     return cudaGetLastError();
 }
@@ -426,11 +429,40 @@ cudaError_t dcsb_launch_seq(const DcsbRomView *view, const DcsbSeqTimeline *tls,
 // ------------------------------------------------------------------------------------
 static void scan_shape(int nstreams, int concurrent, int &warps, int &grid) { dcsb_scan_shape(nstreams, concurrent, &warps, &grid); }
 
-int dcsb_scan_grid(int nstreams, int concurrent)
+// K1 for the 1993 layouts: one lane walks one stream by itself (dcsb_scan_stream: the four layouts share no
+// control flow worth keeping in step), `lanes` streams to a warp -- the lanes of a warp serialise wherever their
+// streams part, so a warp holds few of them and a CTA holds several such warps around one copy of the peek tables.
+#define DCSB_SCAN93_MAXWARPS 16
+__global__ void __launch_bounds__(DCSB_SCAN93_MAXWARPS * 32)
+dcsb_scan93_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restrict__ streams, const uint32_t *__restrict__ order,
+                   int nstreams, int lanes, const DcsbTables *__restrict__ tab, DcsbScanOut out, uint32_t f0, uint32_t f1)
 {
-    int warps, grid;
-    scan_shape(nstreams, concurrent, warps, grid);
-    return nstreams > 0 ? grid : 0;
+    __shared__ __align__(16) uint16_t s_lut[DCSB_LUT_WORDS];
+    if (threadIdx.x == 0 && out.started) atomicAdd(out.started, 1u);       // this CTA is resident (dcsb_gate_kernel)
+    dcsb_load_lut(s_lut, tab);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    if (lane >= lanes) return;
+    for (int k = (blockIdx.x * warps + warp) * lanes + lane; k < nstreams; k += gridDim.x * warps * lanes)
+        dcsb_scan_stream(slab, streams, order ? (int)order[k] : k, tab, s_lut, out, f0, f1);
+}
+
+static void scan93_shape(int n93, int &lanes, int &warps, int &grid)
+{
+    static const int env = [] { const char *e = getenv("DCSB_SCAN93_LANES"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > 32 ? 32 : v); }();
+    lanes = env;
+    const int sms = dcsb_num_sms(), groups = (n93 + lanes - 1) / lanes;
+    warps = (groups + sms - 1) / sms;
+    warps = warps < 1 ? 1 : (warps > DCSB_SCAN93_MAXWARPS ? DCSB_SCAN93_MAXWARPS : warps);
+    const int want = (groups + warps - 1) / warps;                             // one CTA per SM: all resident (the gate waits for them)
+    grid = n93 > 0 ? (want < sms ? want : sms) : 0;
+}
+
+int dcsb_scan_grid(int nstreams, int n94, int concurrent)
+{
+    int warps, grid = 0, lanes, warps93, grid93;
+    if (n94 > 0) scan_shape(n94, concurrent, warps, grid);
+    scan93_shape(nstreams - n94, lanes, warps93, grid93);
+    return grid + grid93;
 }
 
 // The decode kernel may only start filling the SMs once every scan CTA is resident: its warps
@@ -472,14 +504,27 @@ static cudaError_t launch_scan_t(const uint8_t *slab, const DcsbStreamRec *strea
     return cudaGetLastError();
 }
 
-cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, const uint32_t *order, int nstreams, int concurrent,
+cudaError_t dcsb_launch_scan(const uint8_t *slab, const DcsbStreamRec *streams, const uint32_t *order, int nstreams, int n94, int concurrent,
                              const DcsbTables *tables, DcsbScanOut out, cudaStream_t st, uint32_t f0, uint32_t f1)
 {
     if (nstreams <= 0) return cudaSuccess;
-    int warps, grid;
-    scan_shape(nstreams, concurrent, warps, grid);
-    if (dcsb_scan_direct(nstreams, concurrent)) return launch_scan_t<false>(slab, streams, order, nstreams, warps, grid, tables, out, st, f0, f1);
-    return launch_scan_t<true>(slab, streams, order, nstreams, warps, grid, tables, out, st, f0, f1);
+    if (n94 < 0 || n94 > nstreams || (!order && n94 > 0 && n94 < nstreams)) return cudaErrorInvalidValue;
+    if (n94 > 0) {
+        int warps, grid;
+        scan_shape(n94, concurrent, warps, grid);
+        const cudaError_t e = dcsb_scan_direct(n94, concurrent) ? launch_scan_t<false>(slab, streams, order, n94, warps, grid, tables, out, st, f0, f1)
+                                                               : launch_scan_t<true>(slab, streams, order, n94, warps, grid, tables, out, st, f0, f1);
+        if (e != cudaSuccess) return e;
+    }
+    if (nstreams > n94) {
+        int lanes, warps, grid;
+        scan93_shape(nstreams - n94, lanes, warps, grid);
+        // keep the SM at its largest shared-memory split, so that CTAs of the decode kernel can join this one
+        const cudaError_t e = cudaFuncSetAttribute(dcsb_scan93_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        dcsb_scan93_kernel<<<grid, warps * 32, 0, st>>>(slab, streams, order ? order + n94 : nullptr, nstreams - n94, lanes, tables, out, f0, f1);
+    }
+    return cudaGetLastError();
 }
 
 static cudaError_t launch_decode93(const uint8_t *slab, const DcsbStreamRec *streams, const DcsbTile *tiles,

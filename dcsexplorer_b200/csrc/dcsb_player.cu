@@ -170,7 +170,7 @@ static int rom_prepare(dcsb_ctx *ctx, dcsb_rom *rom)
     if (rc != DCSB_OK) return rc;
     dcsb_batch *b = rom->batch;
     if (b->n) {
-        CK(dcsb_launch_scan(b->d_slab, b->d_recs, b->d_order, (int)b->n, 0, ctx->d_tables, b->scan, nullptr), "scan kernel launch");
+        CK(dcsb_launch_scan(b->d_slab, b->d_recs, b->d_order, (int)b->n, (int)b->n94, 0, ctx->d_tables, b->scan, nullptr), "scan kernel launch");
         CK(cudaDeviceSynchronize(), "ROM stream scan");
         std::vector<int32_t> st(b->n);
         std::vector<uint32_t> np(b->n), eb(b->n);
