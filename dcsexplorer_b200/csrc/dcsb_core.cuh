@@ -95,6 +95,44 @@ DCSB_HD int dcsb_mac_round(int a, int b, int c, int d)
     return (int)r >> 16;
 }
 
+// The same value as dcsb_mac_round(a, b, c, d) for b2 = 2b, d2 = 2d, left in bits 16..31 of the result (the low half is
+// unspecified).  The rounding constant rides on the second product (an IMAD addend), so the tie -- low word of the
+// second product exactly 0x8000 -- shows as a zero low word of q, and clearing bit 16 is one AND with a mask made
+// from it: 0xFFFE0000 | -low has bit 16 set for every low in 1..0xFFFF.  No shift, no predicate.
+template <bool SUB>
+DCSB_HD uint32_t dcsb_mac_hi(int a, int b2, int c, int d2)
+{
+    const uint32_t q = (uint32_t)c * (uint32_t)d2 + (SUB ? 0xFFFF8000u : 0x8000u);
+    const uint32_t r = SUB ? (uint32_t)a * (uint32_t)b2 - q : (uint32_t)a * (uint32_t)b2 + q;
+    return r & (0xFFFE0000u | (0u - (q & 0xFFFFu)));
+}
+// (high half of lo) | (high half of hi) << 16
+DCSB_HD uint32_t dcsb_hi_pair(uint32_t lo, uint32_t hi)
+{
+#if DCSB_DEVICE_PASS
+    return __byte_perm(lo, hi, 0x7632);
+#else
+    return (lo >> 16) | (hi & 0xFFFF0000u);
+#endif
+}
+// halfword-wise wrapping add / subtract
+DCSB_HD uint32_t dcsb_add2(uint32_t x, uint32_t y)
+{
+#if DCSB_DEVICE_PASS
+    return __vadd2(x, y);
+#else
+    return ((x + y) & 0xFFFFu) | (((x >> 16) + (y >> 16)) << 16);
+#endif
+}
+DCSB_HD uint32_t dcsb_sub2(uint32_t x, uint32_t y)
+{
+#if DCSB_DEVICE_PASS
+    return __vsub2(x, y);
+#else
+    return ((x - y) & 0xFFFFu) | (((x >> 16) - (y >> 16)) << 16);
+#endif
+}
+
 // scale mantissa table {0x8000,0x9838,0xb505,0xd745} >> (15 - exponent)  (:1978-1979, :2337-2343)
 DCSB_HD uint32_t dcsb_scale_factor(int code)
 {
@@ -404,6 +442,17 @@ DCSB_HD void dcsb_butterfly(uint32_t &u, uint32_t &a, uint32_t tw)
     }
 }
 
+// The 1993 (wrapping) butterfly on packed elements with pre-doubled twiddles: the products stay in the high halves,
+// one byte permute packs t, the two results are halfword-wise add / subtract (:742-778)
+DCSB_HD void dcsb_butterfly93(uint32_t &u, uint32_t &a, int c2, int s2)
+{
+    const int ar = dcsb_re(a), ai = dcsb_im(a);
+    const uint32_t t = dcsb_hi_pair(dcsb_mac_hi<true>(ar, c2, ai, s2), dcsb_mac_hi<false>(ai, c2, ar, s2));
+    const uint32_t nu = dcsb_sub2(u, t);
+    a = dcsb_add2(u, t);
+    u = nu;
+}
+
 // 1994 transform, one warp per frame, in place on c[0..128] (word 128 is the always-zero
 // phantom element the reference reads at frameBuffer[0x100], :405-418).  After the call
 // c[k] holds complex element k of the finished IFFT (before volume shift / reordering).
@@ -525,7 +574,8 @@ DCSB_HD void dcsb_transform93_warp(uint32_t *c, const DcsbTables *tab)
             const int p = b >> (6 - st), j = b & (span - 1);
             const int e0 = p * 2 * span + j;
             uint32_t u = c[e0], a = c[e0 + span];
-            dcsb_butterfly<false>(u, a, tab->twiddle[p]);
+            const DcsbTw2 tw = tab->tw93[p];
+            dcsb_butterfly93(u, a, tw.c2, tw.s2);
             c[e0] = u;
             c[e0 + span] = a;
         }
@@ -536,7 +586,7 @@ DCSB_HD void dcsb_transform93_warp(uint32_t *c, const DcsbTables *tab)
 // The same transform with one LANE per frame: every lane works on its own row (row stride 257 words,
 // so equal offsets in different rows hit different banks), no warp synchronisation; three radix-2
 // stages at a time on 8 points held in registers (stages 0-2, 3-5), then stage 6.
-DCSB_HD void dcsb_transform93_lane(uint32_t *c, const uint32_t *twiddle)
+DCSB_HD void dcsb_transform93_lane(uint32_t *c, const DcsbTw2 *tw2)
 {
     {
         const uint32_t AR = dcsb_magnitude93(c[0]);
@@ -567,19 +617,21 @@ DCSB_HD void dcsb_transform93_lane(uint32_t *c, const uint32_t *twiddle)
 #pragma unroll
             for (int k = 0; k < 8; ++k) x[k] = c[base + k * step];
             {   // stage s0: pairs (k, k + 4), twiddle p
-                const uint32_t tw = twiddle[p];
+                const DcsbTw2 tw = tw2[p];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) dcsb_butterfly<false>(x[k], x[k + 4], tw);
+                for (int k = 0; k < 4; ++k) dcsb_butterfly93(x[k], x[k + 4], tw.c2, tw.s2);
             }
 #pragma unroll
             for (int q = 0; q < 2; ++q) {   // stage s0 + 1: pairs (4q + k, 4q + k + 2), twiddle 2p + q
-                const uint32_t tw = twiddle[2 * p + q];
+                const DcsbTw2 tw = tw2[2 * p + q];
 #pragma unroll
-                for (int k = 0; k < 2; ++k) dcsb_butterfly<false>(x[4 * q + k], x[4 * q + k + 2], tw);
+                for (int k = 0; k < 2; ++k) dcsb_butterfly93(x[4 * q + k], x[4 * q + k + 2], tw.c2, tw.s2);
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q)     // stage s0 + 2: pairs (2q, 2q + 1), twiddle 4p + q
-                dcsb_butterfly<false>(x[2 * q], x[2 * q + 1], twiddle[4 * p + q]);
+            for (int q = 0; q < 4; ++q) {   // stage s0 + 2: pairs (2q, 2q + 1), twiddle 4p + q
+                const DcsbTw2 tw = tw2[4 * p + q];
+                dcsb_butterfly93(x[2 * q], x[2 * q + 1], tw.c2, tw.s2);
+            }
 #pragma unroll
             for (int k = 0; k < 8; ++k) c[base + k * step] = x[k];
             (void)nparts;
@@ -589,7 +641,8 @@ DCSB_HD void dcsb_transform93_lane(uint32_t *c, const uint32_t *twiddle)
 #pragma unroll 4
     for (int p = 0; p < 128; ++p) {
         uint32_t u = c[2 * p], a = c[2 * p + 1];
-        dcsb_butterfly<false>(u, a, twiddle[p]);
+        const DcsbTw2 tw = tw2[p];
+        dcsb_butterfly93(u, a, tw.c2, tw.s2);
         c[2 * p] = u;
         c[2 * p + 1] = a;
     }
@@ -678,14 +731,14 @@ template <bool T93> struct DcsbWarpSmem { static constexpr int WORDS = 32 * Dcsb
 template <bool T93>
 DCSB_HD unsigned long long dcsb_decode_tile(const uint8_t *slab, const DcsbStreamRec *streams, DcsbTile tl,
                                             const DcsbTables *tab, const uint16_t *lut, const DcsbScanOut &scan,
-                                            int16_t *pcm, uint32_t *rows, const uint32_t *twiddle = nullptr)
+                                            int16_t *pcm, uint32_t *rows)
 {
-    if (!twiddle) twiddle = tab->twiddle;           // (the kernel passes a shared-memory copy)
     constexpr int ROWW = DcsbRow<T93>::WORDS;
     const DcsbStreamRec *sp = streams + tl.stream;
     const long long out_frames = sp->out_frames;
-    // checkpoints first-1 .. first+count-1 (walkers of this layout need no look-ahead entry)
-    const bool fin = dcsb_await(scan.progress, tl.stream, tl.first + tl.count < sp->nframes ? tl.first + tl.count : sp->nframes, scan.qctl ? scan.qctl + 2 : nullptr);
+    // progress f + 2 = frame f walked and found whole (its checkpoint alone says nothing about the frame itself: a
+    // stream cut short inside frame f has a checkpoint for it); the last frame of a stream is only known with DONE
+    const bool fin = dcsb_await(scan.progress, tl.stream, tl.first + tl.count + 1 < sp->nframes + 1 ? tl.first + tl.count + 1 : sp->nframes + 1, scan.qctl ? scan.qctl + 2 : nullptr);
     const long long nplay = fin ? (long long)DCSB_LDCG(scan.nplay + tl.stream) : (long long)sp->nframes;
     const int fmt = sp->fmt;
     uint32_t *tails = rows + 32 * ROWW;             // two 8-word overlap buffers (ping-pong)
@@ -721,7 +774,7 @@ DCSB_HD unsigned long long dcsb_decode_tile(const uint8_t *slab, const DcsbStrea
     if (T93) {
         DCSB_FOR_LANES(l, 32) {
             const long long f = (long long)tl.first - 1 + l;
-            if (f >= 0 && f < nplay && f < out_frames && l <= (int)tl.count) dcsb_transform93_lane(rows + l * ROWW, twiddle);
+            if (f >= 0 && f < nplay && f < out_frames && l <= (int)tl.count) dcsb_transform93_lane(rows + l * ROWW, tab->tw93);
         }
         DCSB_SYNCWARP();
     }

@@ -209,16 +209,9 @@ struct DcsbTw94 {
     int pre_c0[64], pre_c1[64];    // pre-pass coefficients, natural order i
 };
 
-// sext16( MR1( a*b2 -/+ c*d2 + rounding ) ), rounding tie rule on the low word of c*d2 (:3503-3554)
+// sext16( MR1( a*b2 -/+ c*d2 + rounding ) ), rounding tie rule on the low word of c*d2 (:3503-3554); see dcsb_mac_hi
 template <bool SUB>
-DCSB_HD int dcsb_mac2(int a, int b2, int c, int d2)
-{
-    const uint32_t p2 = (uint32_t)c * (uint32_t)d2;            // (wrap-around products: only bits 16..31 are consumed)
-    uint32_t r = (uint32_t)a * (uint32_t)b2 + 0x8000u;
-    r = SUB ? r - p2 : r + p2;
-    if ((p2 & 0xFFFFu) == 0x8000u) r &= ~0x10000u;
-    return (int)r >> 16;
-}
+DCSB_HD int dcsb_mac2(int a, int b2, int c, int d2) { return (int)dcsb_mac_hi<SUB>(a, b2, c, d2) >> 16; }
 DCSB_HD int dcsb_negw(int v) { return dcsb_s16((uint32_t)-v); }      // MulSS(v, 0x8000): wrap16(-v)
 
 // pre-pass on the pair (element i = x, element 128-i = y) (:405-456)

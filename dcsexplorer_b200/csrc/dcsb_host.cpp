@@ -84,8 +84,10 @@ void dcsb_build_tables(DcsbTables *t)
     for (int i = 0; i < NCODES(dcs93_hdr); ++i)
         if (dcs93_hdr[i].len > 8) t->long93[t->n_long93++] = DcsbLongCode{ dcs93_hdr[i].code, dcs93_hdr[i].len, dcs93_hdr[i].val, 0 };
     memcpy(t->overlap, dcs_overlap_win, sizeof(t->overlap));
-    for (int p = 0; p < 128; ++p)
+    for (int p = 0; p < 128; ++p) {
         t->twiddle[p] = ((uint32_t)dcs_twiddle[128 + p] << 16) | dcs_twiddle[p];
+        t->tw93[p] = DcsbTw2{ 2 * (int)(int16_t)dcs_twiddle[128 + p], 2 * (int)(int16_t)dcs_twiddle[p] };
+    }
     for (int i = 0; i < 64; ++i) {
         // twiddle pass coefficients c0 = table[bitrev9(2+4i)], c1 = table[bitrev9(4i)] (DCSDecoderNative.cpp:428-429)
         const uint16_t c0 = dcs_twiddle[rev_bits(2 + 4 * i, 9)], c1 = dcs_twiddle[rev_bits(4 * i, 9)];

@@ -52,6 +52,7 @@ struct DcsbTile { uint32_t stream; uint32_t first; uint32_t count; };
 
 struct DcsbLongCode { uint32_t code; uint8_t len; uint8_t val; uint16_t pad; };
 
+struct alignas(8) DcsbTw2 { int c2, s2; };      // a butterfly twiddle pre-doubled: 2 cos, 2 sin
 struct DcsbTables {
     uint16_t lut[DCSB_LUT_WORDS];
     uint16_t overlap[16];
@@ -64,6 +65,7 @@ struct DcsbTables {
     // 1994 fast path
     int tw_c2[64], tw_s2[64];      // butterfly twiddles pre-doubled (2cos, 2sin), partition order
     int pre_c0[64], pre_c1[64];    // pre-pass coefficients pre-doubled, natural order
+    DcsbTw2 tw93[128];             // 1993 lane transform: the twiddles of `twiddle` pre-doubled
     // scan: tx[codebook][next 12 bits] = y1 << 16 | y8; y8 = as many whole codewords as fit (at most 15
     // output slots), y1 = exactly one codeword; y = output slots covered << 12 | bits consumed
     uint32_t tx[6 * DCSB_T8_CB];
