@@ -204,14 +204,51 @@ DCSB_HD void dcsb_lane_decode94(const uint8_t *hdr, const uint16_t *lut, DcsbWin
 // K2 phase B: TransformFrame for the 1994 layout (DCSDecoderNative.cpp:397-576), one lane
 // per frame.  Twiddles come pre-doubled (2*cos, 2*sin) so that a multiply-accumulate
 // produces the ADSP's left-shifted MR directly.
+//
+// Between the pre-pass and the last store the elements are held BIASED (v + 0x8000, 0..0xFFFF): the saturating
+// add of a biased and a plain value is max(min(x + t, 0xFFFF), 0), ONE instruction (VIADDMNMX.RELU) where the
+// symmetric clamp takes two.  The multiply-accumulates take the biased operands as they are: the bias times a
+// twiddle is a constant per twiddle, kept beside it (kr / ki) and added where the rounding constant is added
+// anyway; 0x8000 * (2 cos) has a zero low word, so the tie rule still reads the low word of the second product.
+struct DcsbTw4 { int c2, s2, kr, ki; };
 struct DcsbTw94 {
-    int tw_c2[64], tw_s2[64];      // butterfly twiddles, reference table order (partition index)
+    DcsbTw4 tw[64];                // butterfly twiddles, reference table order (partition index)
     int pre_c0[64], pre_c1[64];    // pre-pass coefficients, natural order i
 };
+#define DCSB_BIAS 0x8000
+// fill element i of a (shared-memory) copy from the context's tables
+DCSB_HD void dcsb_tw94_fill(DcsbTw94 *dst, const DcsbTables *tab, int i)
+{
+    const int c2 = tab->tw_c2[i], s2 = tab->tw_s2[i];
+    dst->tw[i].c2 = c2;
+    dst->tw[i].s2 = s2;
+    dst->tw[i].kr = (int)(((uint32_t)(c2 - s2) << 15) - 0x8000u);       // tr: q = ai' s2 + kr, r = ar' c2 - q
+    dst->tw[i].ki = (int)(0x8000u - ((uint32_t)(c2 + s2) << 15));       // ti: q = ar' s2 + ki, r = ai' c2 + q
+    dst->pre_c0[i] = tab->pre_c0[i];
+    dst->pre_c1[i] = tab->pre_c1[i];
+}
 
 // sext16( MR1( a*b2 -/+ c*d2 + rounding ) ), rounding tie rule on the low word of c*d2 (:3503-3554); see dcsb_mac_hi
 template <bool SUB>
 DCSB_HD int dcsb_mac2(int a, int b2, int c, int d2) { return (int)dcsb_mac_hi<SUB>(a, b2, c, d2) >> 16; }
+// the same on biased a, c: k carries the rounding constant and the bias terms
+template <bool SUB>
+DCSB_HD int dcsb_mac2k(int a, int b2, int c, int d2, int k)
+{
+    const uint32_t q = (uint32_t)c * (uint32_t)d2 + (uint32_t)k;
+    const uint32_t r = SUB ? (uint32_t)a * (uint32_t)b2 - q : (uint32_t)a * (uint32_t)b2 + q;
+    return (int)(r & (0xFFFE0000u | (0u - (q & 0xFFFFu)))) >> 16;
+}
+// saturating add of a biased element and a plain value, biased
+DCSB_HD int dcsb_addb(int xb, int t)
+{
+#if DCSB_DEVICE_PASS
+    return __viaddmin_s32_relu(xb, t, 0xFFFF);          // max(min(xb + t, 0xFFFF), 0): VIADDMNMX.RELU
+#else
+    const int v = xb + t;
+    return v > 0xFFFF ? 0xFFFF : (v < 0 ? 0 : v);
+#endif
+}
 DCSB_HD int dcsb_negw(int v) { return dcsb_s16((uint32_t)-v); }      // MulSS(v, 0x8000): wrap16(-v)
 
 // pre-pass on the pair (element i = x, element 128-i = y) (:405-456)
@@ -226,21 +263,22 @@ DCSB_HD void dcsb_prepair94(int &xr, int &xi, int &yr, int &yi, int c0x2, int c1
     yr = dcsb_sat16(p0r - prod1);
     yi = dcsb_sat16(prod0 - p0i);
 }
-// half fold (:458-471)
+// half fold (:458-471); plain in, BIASED out
 DCSB_HD void dcsb_fold94(int &ur, int &ui, int &ar, int &ai)
 {
-    const int sr = dcsb_sat16(ur + ar), si = dcsb_sat16(ui + ai);
-    const int dr = dcsb_sat16(ur - ar), di = dcsb_sat16(ui - ai);
+    const int ubr = ur + DCSB_BIAS, ubi = ui + DCSB_BIAS;
+    const int sr = dcsb_addb(ubr, ar), si = dcsb_addb(ubi, ai);
+    const int dr = dcsb_addb(ubr, -ar), di = dcsb_addb(ubi, -ai);
     ur = sr; ui = si; ar = dr; ai = di;
 }
-// radix-2 butterfly, saturating (:480-524): u' = u - t, a' = u + t, t = a * (cos + i sin)
-DCSB_HD void dcsb_bfly94(int &ur, int &ui, int &ar, int &ai, int c2, int s2)
+// radix-2 butterfly, saturating (:480-524): u' = u - t, a' = u + t, t = a * (cos + i sin); biased in and out
+DCSB_HD void dcsb_bfly94(int &ur, int &ui, int &ar, int &ai, const DcsbTw4 &w)
 {
-    const int tr = dcsb_mac2<true>(ar, c2, ai, s2);
-    const int ti = dcsb_mac2<false>(ai, c2, ar, s2);
-    const int nur = dcsb_sat16(ur - tr), nui = dcsb_sat16(ui - ti);
-    ar = dcsb_sat16(ur + tr);
-    ai = dcsb_sat16(ui + ti);
+    const int tr = dcsb_mac2k<true>(ar, w.c2, ai, w.s2, w.kr);
+    const int ti = dcsb_mac2k<false>(ai, w.c2, ar, w.s2, w.ki);
+    const int nur = dcsb_addb(ur, -tr), nui = dcsb_addb(ui, -ti);
+    ar = dcsb_addb(ur, tr);
+    ai = dcsb_addb(ui, ti);
     ur = nur;
     ui = nui;
 }
@@ -248,20 +286,20 @@ DCSB_HD void dcsb_bfly94(int &ur, int &ui, int &ar, int &ai, int c2, int s2)
 DCSB_HD void dcsb_fft8_94(int *xr, int *xi, const DcsbTw94 *tw, int iA, int iB, int iC)
 {
     {
-        const int c = tw->tw_c2[iA], s = tw->tw_s2[iA];
+        const DcsbTw4 w = tw->tw[iA];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) dcsb_bfly94(xr[k], xi[k], xr[k + 4], xi[k + 4], c, s);
+        for (int k = 0; k < 4; ++k) dcsb_bfly94(xr[k], xi[k], xr[k + 4], xi[k + 4], w);
     }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-        const int c = tw->tw_c2[iB + q], s = tw->tw_s2[iB + q];
+        const DcsbTw4 w = tw->tw[iB + q];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) dcsb_bfly94(xr[4 * q + k], xi[4 * q + k], xr[4 * q + k + 2], xi[4 * q + k + 2], c, s);
+        for (int k = 0; k < 2; ++k) dcsb_bfly94(xr[4 * q + k], xi[4 * q + k], xr[4 * q + k + 2], xi[4 * q + k + 2], w);
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const int c = tw->tw_c2[iC + q], s = tw->tw_s2[iC + q];
-        dcsb_bfly94(xr[2 * q], xi[2 * q], xr[2 * q + 1], xi[2 * q + 1], c, s);
+        const DcsbTw4 w = tw->tw[iC + q];
+        dcsb_bfly94(xr[2 * q], xi[2 * q], xr[2 * q + 1], xi[2 * q + 1], w);
     }
 }
 
@@ -309,7 +347,7 @@ DCSB_HD void dcsb_lane_transform94(int16_t *r16, const DcsbTw94 *tw, int vs)
         const int base = rg * 16 + h;
         int xr[8], xi[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { xr[k] = re[base + 2 * dcsb_rev3(k)]; xi[k] = im[base + 2 * dcsb_rev3(k)]; }
+        for (int k = 0; k < 8; ++k) { xr[k] = (uint16_t)re[base + 2 * dcsb_rev3(k)]; xi[k] = (uint16_t)im[base + 2 * dcsb_rev3(k)]; }
         dcsb_fft8_94(xr, xi, tw, h, 2 * h, 4 * h);
 #pragma unroll
         for (int k = 0; k < 8; ++k) { re[base + 2 * dcsb_rev3(k)] = (int16_t)xr[k]; im[base + 2 * dcsb_rev3(k)] = (int16_t)xi[k]; }
@@ -322,12 +360,12 @@ DCSB_HD void dcsb_lane_transform94(int16_t *r16, const DcsbTw94 *tw, int vs)
         const int base = rg * 2 + h;
         int xr[8], xi[8];
 #pragma unroll
-        for (int b = 0; b < 8; ++b) { xr[b] = re[base + 16 * dcsb_rev3(b)]; xi[b] = im[base + 16 * dcsb_rev3(b)]; }
+        for (int b = 0; b < 8; ++b) { xr[b] = (uint16_t)re[base + 16 * dcsb_rev3(b)]; xi[b] = (uint16_t)im[base + 16 * dcsb_rev3(b)]; }
         dcsb_fft8_94(xr, xi, tw, 8 * h + g, 16 * h + 2 * g, 32 * h + 4 * g);
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            re[base + 16 * dcsb_rev3(b)] = (int16_t)(xr[b] >> vs);
-            im[base + 16 * dcsb_rev3(b)] = (int16_t)(xi[b] >> vs);
+        for (int b = 0; b < 8; ++b) {           // bias off and volume shift in one: ((x' << 16) - 2^31) >> (16 + vs)
+            re[base + 16 * dcsb_rev3(b)] = (int16_t)((int)((uint32_t)xr[b] * 0x10000u + 0x80000000u) >> (16 + vs));
+            im[base + 16 * dcsb_rev3(b)] = (int16_t)((int)((uint32_t)xi[b] * 0x10000u + 0x80000000u) >> (16 + vs));
         }
     }
 }

@@ -158,10 +158,7 @@ dcsb_decode94_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__re
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item = blockIdx.x * DCSB_WARPS94 + warp;
     {
-        int *dst = reinterpret_cast<int *>(&sm.tw);
-        for (int i = threadIdx.x; i < 64; i += blockDim.x) {
-            dst[i] = tab->tw_c2[i]; dst[64 + i] = tab->tw_s2[i]; dst[128 + i] = tab->pre_c0[i]; dst[192 + i] = tab->pre_c1[i];
-        }
+        for (int i = threadIdx.x; i < 64; i += blockDim.x) dcsb_tw94_fill(&sm.tw, tab, i);
         if (item < nitems && lane < 16) sm.hdr[warp][lane] = streams[items[item].stream].hdr[lane];
     }
     dcsb_load_lut(sm.lut, tab);
@@ -191,10 +188,7 @@ dcsb_decode94_queue_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec
     DcsbSmem94 &sm = *reinterpret_cast<DcsbSmem94 *>(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     {
-        int *dst = reinterpret_cast<int *>(&sm.tw);
-        for (int i = threadIdx.x; i < 64; i += blockDim.x) {
-            dst[i] = tab->tw_c2[i]; dst[64 + i] = tab->tw_s2[i]; dst[128 + i] = tab->pre_c0[i]; dst[192 + i] = tab->pre_c1[i];
-        }
+        for (int i = threadIdx.x; i < 64; i += blockDim.x) dcsb_tw94_fill(&sm.tw, tab, i);
     }
     dcsb_load_lut(sm.lut, tab);
 #ifdef DCSB_SCAN_DEBUG
@@ -313,10 +307,7 @@ dcsb_mix94_kernel(const uint8_t *__restrict__ slab, const DcsbStreamRec *__restr
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item = blockIdx.x * DCSB_WARPS94 + warp;
     {
-        int *dst = reinterpret_cast<int *>(&sm.tw);
-        for (int i = threadIdx.x; i < 64; i += blockDim.x) {
-            dst[i] = tab->tw_c2[i]; dst[64 + i] = tab->tw_s2[i]; dst[128 + i] = tab->pre_c0[i]; dst[192 + i] = tab->pre_c1[i];
-        }
+        for (int i = threadIdx.x; i < 64; i += blockDim.x) dcsb_tw94_fill(&sm.tw, tab, i);
     }
     dcsb_load_lut(sm.lut, tab);
     if (item >= nitems) return;

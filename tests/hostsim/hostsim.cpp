@@ -43,8 +43,7 @@ static int sim_decode_streams(const dcsb_stream_desc *descs, size_t n, int16_t *
     std::vector<unsigned long long> csum(n + 1, 0);
     std::vector<uint32_t> rows(DcsbWarpSmem<true>::WORDS + DCSB_WARP94_WORDS);
     static DcsbTw94 tw;
-    memcpy(tw.tw_c2, tab.tw_c2, sizeof(tw.tw_c2)); memcpy(tw.tw_s2, tab.tw_s2, sizeof(tw.tw_s2));
-    memcpy(tw.pre_c0, tab.pre_c0, sizeof(tw.pre_c0)); memcpy(tw.pre_c1, tab.pre_c1, sizeof(tw.pre_c1));
+    for (int i = 0; i < 64; ++i) dcsb_tw94_fill(&tw, &tab, i);
     uint32_t max_out = 0;
     for (size_t i = 0; i < n; ++i) max_out = std::max(max_out, p.recs[i].out_frames);
     for (uint32_t fa = 0; fa == 0 || fa < max_out; fa += slice_frames ? slice_frames : 0xFFFFFFFFu) {
@@ -209,8 +208,7 @@ extern "C" int hostsim_rom_render(const uint8_t *const *imgs, const size_t *size
     const bool fam93 = rom.os == DCSB_OS93A || rom.os == DCSB_OS93B;
     DcsbMixSched sc{ frames.data(), entries.data() };
     static DcsbTw94 tw;
-    memcpy(tw.tw_c2, tab.tw_c2, sizeof(tw.tw_c2)); memcpy(tw.tw_s2, tab.tw_s2, sizeof(tw.tw_s2));
-    memcpy(tw.pre_c0, tab.pre_c0, sizeof(tw.pre_c0)); memcpy(tw.pre_c1, tab.pre_c1, sizeof(tw.pre_c1));
+    for (int i = 0; i < 64; ++i) dcsb_tw94_fill(&tw, &tab, i);
     std::vector<uint32_t> rows(DcsbWarpSmem<true>::WORDS + DCSB_WARP94_WORDS);
     std::vector<uint8_t> hdrs(32 * 16);
     for (size_t t = 0; t < n; ++t) {
