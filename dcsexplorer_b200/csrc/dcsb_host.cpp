@@ -195,9 +195,10 @@ void dcsb_scan_shape(int nstreams, int concurrent, int *warps, int *grid)
     const int groups = (nstreams + 31) / 32, cgroups = (concurrent + 31) / 32;
     const bool direct = dcsb_scan_direct(nstreams, concurrent);
     const int maxw = direct ? DCSB_SCAN_MAXWARPS_DIRECT : DCSB_SCAN_MAXWARPS;
-    // (measured on 131,072 one-second streams: rings, 2 warps per CTA 13.4 ms; direct, 4 warps 10.9 ms, 8 warps
-    // 20.8 ms -- with eight warps' band entries in shared memory L1 is too small for the lanes' lines)
-    const int defw = direct ? 4 : DCSB_SCAN_MAXWARPS;
+    // (measured on 131,072 one-second streams, scan beside the decode kernel: rings, 2 warps per CTA 13.4 ms; direct,
+    // 4 warps 10.9 ms, 6 warps 8.7 ms, 7 warps 7.7 ms, 8 warps 20.9 ms -- with eight warps' band entries in shared
+    // memory L1 is too small for the lanes' lines; profiles/r03a_scan_warps.txt, r03b_scan_warps.txt)
+    const int defw = direct ? 7 : DCSB_SCAN_MAXWARPS;
     int w = (cgroups + sms - 1) / sms;
     w = w > defw ? defw : (w < 1 ? 1 : w);
     if (const char *e = getenv("DCSB_SCAN_WARPS")) {         // tuning override
