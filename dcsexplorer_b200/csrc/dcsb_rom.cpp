@@ -575,6 +575,7 @@ void DcsbSequencer::soft_boot()
     for (int i = 0; i < DCSB_MAX_CHANNELS; ++i) { st.chan[i].stop = false; st.chan[i].volume = 0xFF; }
     dcsb_seq_set_master_volume(st, 0x67);       // DCSDecoder's default volume until the host says otherwise
     st.port_bytes = 0;
+    st.quiet = 0;
 }
 
 void DcsbSequencer::set_master_volume(int vol) { dcsb_seq_set_master_volume(st, vol); }

@@ -214,6 +214,8 @@ struct DcsbSeqState {
     uint32_t gs_key;                            // active mask | max-override mask << 8 | volume multiplier << 16
     uint8_t gs_vs;
     bool gs_valid;
+    // main-loop passes ahead in which nothing but counters moves (dcsb_seq_horizon); any input zeroes it
+    uint32_t quiet;
 };
 
 DCSB_SEQ_HD void dcsb_seq_to_host(DcsbSeqState &s, uint8_t b)
@@ -224,6 +226,7 @@ DCSB_SEQ_HD void dcsb_seq_to_host(DcsbSeqState &s, uint8_t b)
 }
 DCSB_SEQ_HD bool dcsb_seq_q_push(DcsbSeqState &s, uint16_t v)      // false: the queue is full (a runaway program)
 {
+    s.quiet = 0;
     if (s.q_count >= DCSB_SEQ_QCAP) return false;
     s.cmdq[(s.q_head + s.q_count) % DCSB_SEQ_QCAP] = v;
     ++s.q_count;
@@ -232,7 +235,7 @@ DCSB_SEQ_HD bool dcsb_seq_q_push(DcsbSeqState &s, uint16_t v)      // false: the
 DCSB_SEQ_HD void dcsb_seq_mixer_reset(DcsbSeqMixer &m) { m.cur = m.target = m.steps = 0; }
 DCSB_SEQ_HD void dcsb_seq_timer_clear(DcsbSeqTimer &t) { t.interval = t.counter = 0; }
 
-DCSB_SEQ_HD void dcsb_seq_set_master_volume(DcsbSeqState &s, int vol) { s.vol_mult = dcsb_seq_master_multiplier(vol); }
+DCSB_SEQ_HD void dcsb_seq_set_master_volume(DcsbSeqState &s, int vol) { s.vol_mult = dcsb_seq_master_multiplier(vol); s.quiet = 0; }
 
 DCSB_SEQ_HD void dcsb_seq_init(DcsbSeqState &s)        // a freshly constructed decoder + Initialize() (SoftBoot)
 {
@@ -261,6 +264,7 @@ DCSB_SEQ_HD void dcsb_seq_init(DcsbSeqState &s)        // a freshly constructed 
         c.level_sum = 0;
     }
     s.gs_valid = false;
+    s.quiet = 0;
     for (int i = 0; i < 256; ++i) s.vars[i] = 0;
     s.q_head = s.q_count = 0;
     s.port_word = s.port_ext = 0;
@@ -285,12 +289,14 @@ DCSB_SEQ_HD void dcsb_seq_reset_mix(DcsbSeqState &s, int ch)
 }
 DCSB_SEQ_HD void dcsb_seq_clear_tracks(DcsbSeqState &s)
 {
+    s.quiet = 0;
     for (int i = 0; i < DCSB_MAX_CHANNELS; ++i) { s.chan[i].track.clear(); s.chan[i].st.active = false; }
 }
 
 // WriteDataPort + IRQ2Handler: a byte from the host, taken before the next frame (:3297-3437)
 DCSB_SEQ_HD void dcsb_seq_write_port(DcsbSeqState &s, const DcsbRomView &rv, uint8_t data)
 {
+    s.quiet = 0;
     if (s.port_timeout >= 13) s.port_bytes = 0;
     switch (s.port_bytes) {
     case 0:
@@ -359,6 +365,7 @@ DCSB_SEQ_HD void dcsb_seq_start_stream(DcsbSeqState &s, const DcsbRomView &rv, i
 DCSB_SEQ_HD void dcsb_seq_load_stream(DcsbSeqState &s, const DcsbRomView &rv, int ch, uint32_t linear, int level)
 {
     if (ch < 0 || ch >= DCSB_MAX_CHANNELS) return;
+    s.quiet = 0;
     s.chan[ch].track.clear();
     dcsb_seq_start_stream(s, rv, ch, ch, 1, linear);
     DcsbSeqMixer &m = s.chan[ch].mixer[ch];
@@ -642,11 +649,77 @@ DCSB_SEQ_HD bool dcsb_seq_main_loop(DcsbSeqState &s, const DcsbRomView &rv, Dcsb
     return true;
 }
 
+// How many of the next main-loop passes are QUIET: no stop flag, no queued command, no track program whose wait
+// runs out, no stream that ends, wraps or hits a damaged frame, no fade, no timer firing, gain staging unchanged.
+// Such a pass moves counters and emits the same channels one frame further (dcsb_seq_quiet_frame); what it would
+// compute is already in the state.  Conservative: 0 whenever in doubt.
+DCSB_SEQ_HD uint32_t dcsb_seq_horizon(const DcsbSeqState &s, const DcsbRomView &rv)
+{
+    if (s.fatal || s.q_count || !s.gs_valid) return 0;
+    uint32_t h = 0xFFFFu;
+    unsigned active = 0, maxo = 0;
+    for (int i = 0; i < DCSB_MAX_CHANNELS; ++i) {
+        const DcsbSeqChannel &c = s.chan[i];
+        if (c.stop || c.fading || c.levels_dirty) return 0;
+        if (c.mult != c.level_mult || c.level_mult != s.gs_mix[i]) return 0;
+        if (!c.track.null()) {
+            const uint32_t wait = dcsb_rv_be(rv, c.track, 2);
+            if (wait != 0xFFFFu) {                  // acts in the pass that finds the counter at `wait`
+                const uint32_t d = (wait - c.track_counter) & 0xFFFFu;
+                if (d < h) h = d;
+            }
+        }
+        if (c.st.active) {
+            active |= 1u << i;
+            if (c.st.id == 0xFFFFFFFFu) return 0;
+            const uint32_t np = rv.streams[c.st.id].nplay;
+            const uint32_t left = np > (uint32_t)c.st.pos + 1u ? np - 1u - c.st.pos : 0u;      // whole frames before the last one
+            if (left < h) h = left;
+            const uint32_t cnt = c.st.counter ? c.st.counter - 1u : 0u;                         // passes before the counter runs out
+            if (cnt < h) h = cnt;
+        }
+        if (c.max_override) maxo |= 1u << i;
+        if (c.timer.interval != 0) {
+            const uint32_t t = c.timer.counter ? c.timer.counter - 1u : 0u;
+            if (t < h) h = t;
+        }
+    }
+    if (s.gs_key != (active | (maxo << 8) | ((uint32_t)s.vol_mult << 16))) return 0;
+    return h;
+}
+DCSB_SEQ_HD void dcsb_seq_quiet_frame(DcsbSeqState &s, const DcsbRomView &rv, DcsbSchedFrame *fr, DcsbSchedEntry *entries)
+{
+    int n = 0;
+    for (int ch = 0; ch < DCSB_MAX_CHANNELS; ++ch) {
+        DcsbSeqChannel &c = s.chan[ch];
+        if (c.st.active) {
+            DcsbSchedEntry &e = entries[n++];
+            e.stream = rv.streams[c.st.id].id; e.frame = c.st.pos; e.mult = s.gs_eff[ch];
+            c.st.at_start = false;
+            ++c.st.pos;
+            --c.st.counter;
+        }
+        c.track_counter += 1;
+        if (c.timer.interval != 0) --c.timer.counter;
+    }
+    if (++s.port_timeout > 13) s.port_timeout = 13;
+    fr->flags = 0;
+    fr->pad = 0;
+    fr->n_entries = (uint8_t)n;
+    fr->vs = s.gs_vs;
+    ++s.frame_no;
+}
+
 // One output frame: the main loop with the reference's self-reset retries (a reset is retried; four in a row are
 // fatal, DCSDecoder.cpp:1631-1668).  entries: room for DCSB_MAX_CHANNELS.  fr->first_entry is left to the caller.
 // Returns false once the decoder is in its fatal-error state (the frame is then silent).
 DCSB_SEQ_HD bool dcsb_seq_frame(DcsbSeqState &s, const DcsbRomView &rv, DcsbSchedFrame *fr, DcsbSchedEntry *entries)
 {
+    if (s.quiet) {
+        --s.quiet;
+        dcsb_seq_quiet_frame(s, rv, fr, entries);
+        return true;
+    }
     int n = 0;
     uint8_t vs = 8;
     fr->flags = 0;
@@ -663,5 +736,6 @@ DCSB_SEQ_HD bool dcsb_seq_frame(DcsbSeqState &s, const DcsbRomView &rv, DcsbSche
     fr->n_entries = (uint8_t)n;
     fr->vs = vs;
     ++s.frame_no;
+    s.quiet = dcsb_seq_horizon(s, rv);
     return !s.fatal;
 }

@@ -192,7 +192,7 @@ int main(int argc, char **argv)
     std::vector<int> ord(ns);
     for (int i = 0; i < ns; ++i) ord[i] = i;
     std::sort(ord.begin(), ord.end(), [&](int a, int b2) { return bpf[a] < bpf[b2]; });
-    for (int L : { 32 })
+    for (int L : { 32, 16, 8, 4 })
         for (int sc = 0; sc < NSCH; ++sc) {
             double worst = 0, sum = 0;
             int nw = 0;
