@@ -352,7 +352,7 @@ def config4(ctx, dx, torch, n=2048):
     res = {"workload": "%d timelines (shifted command times, master volumes 156..255) + %d solo tracks of the ROM set compiled by the reference's DCSCompiler (%s)" % (
                n, len(c["track_timelines"]), compiledrom.NAMES[0]),
            "output_frames": int(frames), "ms_per_call": best * 1e3, "value": frames * 240 / best / 1e6, "unit": "Msamples/s",
-           "api": "dcsb_render_timelines (host in, pinned host out; host sequencer + mix kernel + PCM download inside)",
+           "api": "dcsb_render_timelines (host in, pinned host out; track-program interpreter kernel + mix kernel + PCM download inside)",
            "timelines_with_errors": sum(1 for i in range(len(tls)) if resarr[i].status != 0),
            "parity_checked_timelines": checked, "mismatches": bad, "checked_against": "reference DCSDecoderNative (oracle/_ref)"}
     rom.close()
@@ -568,12 +568,13 @@ def _main(out):
     clocks = sampler.stop()
     res = batch.results(st.cuda_stream)
     bad = [r["status"] for r in res if r["status"] != 0]
-    xor = 0
+    xor, csum = 0, 0
     for r in res:
         xor ^= r["checksum"]
+        csum = (csum + r["checksum"]) & 0xFFFFFFFFFFFFFFFF     # (N > 1: a rank may hold both copies of a stream, which cancel in the xor)
 
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    cs = torch.tensor([xor & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device="cuda")
+    cs = torch.tensor([csum & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device="cuda")
     per_rank_ms = [my_ms]
     if world > 1:
         mine_t = torch.tensor([my_ms], dtype=torch.float64, device="cuda")
@@ -583,6 +584,9 @@ def _main(out):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         gathered = [torch.zeros_like(cs) for _ in range(world)]
         dist.all_gather(gathered, cs)               # the checksum gather: 8 bytes per rank over NCCL
+        rank_sums = [int(x.item()) for x in gathered]
+    else:
+        rank_sums = [csum & 0x7FFFFFFFFFFFFFFF]
     total_ms = float(t.item())
     value = world * total_samples * a.steps / (total_ms * 1e-3) / 1e6
 
@@ -694,7 +698,10 @@ def _main(out):
                             "cudaMemcpy of the same PCM bytes on this box"},
             "gpu_launches": n_launch * a.steps,
             "clocks": clocks,
-            "status": {"streams_with_errors": len(bad), "checksum_xor": "%016x" % xor},
+            "status": {"streams_with_errors": len(bad), "checksum_xor": "%016x" % xor,
+                       "checksum_sum_per_rank": ["%016x" % v for v in rank_sums],
+                       "note": "checksum_xor: xor of rank 0's per-stream checksums (at N > 1 a rank may hold both copies of a "
+                               "stream, which cancel); checksum_sum_per_rank: their sum mod 2^63, gathered over NCCL"},
         }
         if world == 1 and not a.no_cpu_baseline:
             # the reference decoder on a bounded sample of the SAME streams (~20 s of CPU work), all host cores;

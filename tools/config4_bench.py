@@ -2,8 +2,9 @@
 """GPU measurement aid: BASELINE config 4 -- track playback on the ROM sets built by the
 reference's DCSCompiler (tests/golden/compiled_rom.npz): N decoder instances (timelines with
 shifted command times and different master volumes, plus every track on its own) rendered by ONE
-dcsb_render_timelines call (host sequencer -> mix schedule -> K1 scan of the ROM's streams -> K4
-mix kernel -> PCM to host), against the unmodified reference decoder on the host cores.
+dcsb_render_timelines call (K5 track-program interpreter kernel -> mix schedule -> K4 mix kernel -> PCM to
+host; the ROM's streams are scanned once per ROM; DCSB_SEQ_HOST=1 runs the sequencers on host threads instead),
+against the unmodified reference decoder on the host cores.
   config4_bench.py [n_timelines=2048]"""
 import os
 import sys
@@ -59,7 +60,7 @@ for name in compiledrom.NAMES:
     tref = time.perf_counter() - t0
     best = min(ts[1:])
     print("%s: %d timelines + %d solo tracks, %d output frames (%.1f h of audio), one call: %.1f ms (first %.1f) = %.2f Gsamples/s "
-          "incl. host sequencer and PCM download; reference decoder, 1 thread: %.2f Msamples/s; spot checks bit-exact" % (
+          "incl. sequencer and PCM download; reference decoder, 1 thread: %.2f Msamples/s; spot checks bit-exact" % (
               name, n, len(c["track_timelines"]), frames, frames * 240 / 31250 / 3600, best * 1e3, ts[0] * 1e3,
               frames * 240 / best / 1e9, nref * 240 / tref / 1e6), flush=True)
     rom.close()

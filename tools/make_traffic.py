@@ -19,6 +19,7 @@ for r in rows[2:]:
     if len(r) != len(hdr):
         continue
     name = r[col["Kernel Name"]].split("(")[0]
+    name = name.replace("void ", "").split("<")[0].strip()      # template instances under the kernel's plain name
 
     def num(k):
         return float(r[col[k]].replace(",", ""))
