@@ -218,3 +218,37 @@ def test_gpu_render_timelines_output_placements(ctx):
         want = _reference_timeline(sc["images"], tls[i]) if ref.available() else simutil.rom_render(sc["images"], [tls[i]])[0][0]
         assert np.array_equal(pcm[i], want), i
     rom.close()
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref did not travel with the snapshot")
+def test_gpu_device_sequencer_soak_vs_reference(ctx):
+    """The GPU track interpreter against the unmodified reference decoder on freshly seeded ROM scenarios (all four
+    OS versions, every third with malformed programs / damaged streams, some with the 1.05 opcode set): for each
+    scenario a few timelines with shifted command times and different volumes in ONE dcsb_render_timelines call;
+    PCM and host-byte counts must be the reference's.  (The CPU twin of this test, tools/soak_cpu.py rom, runs the
+    same core on the host; this one is the net under code-generation differences of the device build.)"""
+    import time
+    import dcsexplorer_b200 as dx
+    import simutil
+    t0, n, checked = time.time(), 0, 0
+    for k in range(400):
+        if time.time() - t0 > 60:
+            break
+        osv = (rb.OS94, rb.OS95, rb.OS93B, rb.OS93A)[k % 4]
+        sc = romscen.make_scenario(os_version=osv, seed=7000 + k, n_frames=240, with_errors=(k % 3 == 0),
+                                   version=(0x0105 if (osv == rb.OS95 and k % 8 == 1) else None))
+        rom = dx.Rom(sc["images"])
+        tls = [([(f + sh, b) for f, b in sc["writes"]], sc["n_frames"] + sh, vol) for sh, vol in ((0, sc["master_volume"]), (3, 255), (11, 140))]
+        pcm, res = ctx.render_timelines(rom, tls)
+        for i, tl in enumerate(tls):
+            rp = ref.RomPlayer(sc["images"], tl[2])
+            want = rp.render_timeline(tl[0], tl[1])
+            nhost = len(rp.host_bytes()) if hasattr(rp, "host_bytes") else None
+            rp.close()
+            assert np.array_equal(pcm[i], want), (k, hex(osv), i)
+            if nhost is not None:
+                assert res[i]["n_host_bytes"] == nhost, (k, i, res[i], nhost)
+            checked += 1
+        rom.close()
+        n += 1
+    assert n >= 40, n
