@@ -201,6 +201,12 @@ void dcsb_scan_shape(int nstreams, int concurrent, int *warps, int *grid)
     const int defw = direct ? 7 : DCSB_SCAN_MAXWARPS;
     int w = (cgroups + sms - 1) / sms;
     w = w > defw ? defw : (w < 1 ? 1 : w);
+    // Single wave with rings: two warps per CTA even when every group could have an SM of its own.  A one-warp scan
+    // CTA (153.5 KB) leaves room for ONE decode CTA beside it, so the 128 SMs under config 2's scan run the decode
+    // kernel at a third of their rate and the step waits for the DECODE kernel (14.1 ms); two-warp CTAs (195 KB, no
+    // decode CTA beside them) take half as many SMs and leave the others to three decode CTAs each: 13.0 ms, the
+    // scan's own 12.8 ms chain plus the tail (profiles/r03h_scan_shape.txt).
+    if (!direct && cgroups >= 2 && w < 2) w = 2;
     if (const char *e = getenv("DCSB_SCAN_WARPS")) {         // tuning override
         const int v = atoi(e);
         if (v >= 1 && v <= maxw) w = v;

@@ -36,8 +36,9 @@ __device__ __forceinline__ void dcsb_load_lut(uint16_t *s_lut, const DcsbTables 
 // ------------------------------------------------------------------------------------
 // K1: frame-boundary scan.  A warp takes 32 streams of the scan order (alike streams side by
 // side, dcsb_scan_order) and walks them in LOCK STEP, one lane per stream (dcsb_scan94.cuh); a
-// CTA holds `warps` such warps (one in the single-wave case, so that a decode CTA fits beside
-// it) that share the tables and take stream groups grid-stride.  Streams of the 1993 layouts
+// CTA holds `warps` such warps (two in the single-wave case: the CTA then fills its SM's shared
+// memory and the SMs it does not need run three decode CTAs each, dcsb_scan_shape) that share
+// the tables and take stream groups grid-stride.  Streams of the 1993 layouts
 // are walked by their lane alone first (dcsb_scan_stream), the lane then idles in the lock-step
 // walk of its warp.
 // Shared memory: the length table tx (96 KB) sits on a 16 KB boundary of the shared window
