@@ -314,6 +314,13 @@ DCSB_HD int dcsb_walk93(const DcsbWalkCtx &cx, uint32_t &pos, uint64_t &bt, int1
             }
         } else {                                                         // :2548-2603
             const int width = code + (type1 ? 0 : 1);
+            if (!DECODE) {
+                // length-only walk (the scan): the band is n samples of `width` bits, and no sample value steers the
+                // walk -- band types, subtype changes and reuse flags all come from header codes
+                pos += (uint32_t)(width * n);
+                idx += n * inc + fixup;
+                continue;
+            }
             uint32_t last = 0, last2 = 0;
             for (int i = 0; i < n; ++i) {
                 uint32_t in = (uint32_t)dcsb_sext(cx.rd.peek(pos, width), width) & 0xFFFFu;

@@ -232,7 +232,13 @@ void dcsb_scan_order(DcsbPrepared *p)
     std::vector<uint64_t> key(n);
     for (size_t i = 0; i < n; ++i) {
         const DcsbStreamRec &x = p->recs[i];
-        if (x.fmt != DCSB_FMT_94) { rank93.push_back((uint32_t)i); key[i] = x.nbytes; continue; }
+        if (x.fmt != DCSB_FMT_94) {
+            // alike streams side by side here too (the lanes of a warp serialise where their walks part): layout and
+            // stream type first, then size
+            rank93.push_back((uint32_t)i);
+            key[i] = ((uint64_t)x.fmt << 41) | ((uint64_t)(x.hdr[0] >> 7) << 40) | std::min<uint64_t>(x.nbytes, 0xFFFFFFFFFFull);
+            continue;
+        }
         rank.push_back((uint32_t)i);
         uint32_t bucket = 0;                          // quarter-octave bucket of the frame count
         if (x.nframes) {
