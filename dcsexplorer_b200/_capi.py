@@ -101,6 +101,8 @@ SYMBOLS = {
     "dcsb_batch_pcm_offset": (C.c_uint64, [C.c_void_p, C.c_size_t]),
     "dcsb_batch_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcsb_stream_extent": (C.c_size_t, [C.c_void_p, C.c_int]),
+    "dcsb_encode_bound": (C.c_uint64, [C.c_uint64]),
+    "dcsb_encode_streams": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "dcsb_player_set_lookahead": (C.c_int, [C.c_void_p, C.c_uint32]),
     "dcsb_rom_zip_files": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "dcsb_batch_launches": (C.c_int, [C.c_void_p]),

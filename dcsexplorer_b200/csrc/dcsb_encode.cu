@@ -1,0 +1,635 @@
+// dcsb200 forward path: PCM -> 1994-layout DCS streams, in batch, on the GPU.
+//
+// What it restates is the reference's DCSEncoder minus its resampler (DCSEncoder/DCSEncoder.cpp; "Enc.cpp" below):
+// frames of 16 + 240 samples, window, the float transform DFTAlgorithmOrig (:1218-1357) over DualFFT (:1360-1499),
+// per-band power / range (:2535-2565), the power cut and the header's scale codes (CloseStream :738-770,
+// CompressStream :859-974), the per-band search for the narrowest band type within the quantisation-error limit
+// (FindBestBandEncoding :1502-1621), header delta codes and sample codes with the 'two zeros' codeword
+// (CompressFrame94 :1623-2051), the bit packing (BitWriter :2589-2705).  Every float operation is done in the
+// reference's order with round-to-nearest single operations (no fused multiply-add), so the decisions -- and with them
+// the stream BYTES -- are the reference's for the same frames (tests/test_gpu_encode.py compares with
+// oracle/_ref's encoder fed the same framing).
+//
+// Kernels: K6a transform (a thread per frame), K6s per-stream band statistics, K6b band-type search (a thread per
+// frame and band), K6c code resolution (a thread per stream: a band's choice depends on the previous frame's code only
+// through two small rules, so K6b tabulates the alternatives and K6c picks), K6d frame sizes, K6e bit packing.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "dcsb_internal.h"
+#include "dcsb_ctx.h"
+#include "dcs_tables.h"
+
+#define ENC_THREADS 128
+#define ENC_NV 5                    // scale pre-adjustment alternatives a type-1 band 0..2 can meet (Enc.cpp:710-716)
+
+struct EncStream {                  // per stream, device copy
+    uint64_t pcm_off;               // first sample in the concatenated PCM
+    uint64_t n_samples;
+    uint32_t frame0;                // first frame in the frame arrays
+    uint32_t n_frames;
+    int32_t type, subtype;
+    float max_err2;                 // maximumQuantizationError squared
+    float min_range;
+    uint8_t hdr[16];                // stream header as stored (scale codes, 0xFF behind the kept bands, flag bits)
+    int32_t bands;                  // bands kept
+};
+
+struct EncTables {
+    float coeff[896];               // DualFFT twiddles in the reference's order (:1384-1398), made on the host with its libm
+    float tw2[128];                 // second twiddle table of DFTAlgorithmOrig (:1263-1280)
+    float window[16];               // :1010-1013
+    int scale[64];                  // scalingFactors (:78-143) = the decoder's scale table
+    uint16_t xlat[48];              // type-1 band translation (:1871-1917): width << 8 | scale adjustment
+    uint32_t cb_code[6][64];        // sample codebooks 1..6 by stored value: code word, length
+    uint8_t cb_len[6][64];
+    uint32_t dz_code[6];            // 'two zeros' codeword
+    uint8_t dz_len[6];
+    uint32_t hdr_code[31];          // header delta codes, delta + 16
+    uint8_t hdr_len[31];
+};
+__constant__ EncTables c_enc;
+
+__device__ __forceinline__ int enc_band_count(int b) { return b == 0 ? 7 : (b == 1 ? 8 : (b == 15 ? 32 : 16)); }
+__device__ __forceinline__ int enc_band_first(int b) { return b == 0 ? 0 : (b == 1 ? 7 : 15 + 16 * (b - 2)); }
+__device__ __forceinline__ float enc_half_sum(float a, float b) { return __fmul_rn(__fadd_rn(a, b), 0.5f); }
+__device__ __forceinline__ float enc_half_diff(float a, float b) { return __fmul_rn(__fsub_rn(a, b), 0.5f); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// K6a: one frame per thread.  f[frame][0..255] = the reference's Stream::Frame::f; power / lo / hi per band.
+__global__ void __launch_bounds__(ENC_THREADS)
+dcsb_enc_transform_kernel(const float *__restrict__ pcm, const EncStream *__restrict__ streams, const uint32_t *__restrict__ frame_stream,
+                          uint32_t n_frames_total, float *__restrict__ f_out, float *__restrict__ power, float *__restrict__ lo, float *__restrict__ hi)
+{
+    const uint32_t fr = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fr >= n_frames_total) return;
+    const EncStream s = streams[frame_stream[fr]];
+    const uint32_t k = fr - s.frame0;
+    float in[256];
+    float buf[258];
+    // framing: 16 samples of overlap (raw, zero in front of the first frame), 240 new ones, zeros behind the end (:693-703, :724-737)
+    const long long base = (long long)k * 240 - 16;
+    for (int j = 0; j < 256; ++j) {
+        const long long x = base + j;
+        in[j] = (x >= 0 && (uint64_t)x < s.n_samples) ? pcm[s.pcm_off + (uint64_t)x] : 0.0f;
+    }
+    for (int i = 0; i < 16; ++i) {                                           // window (:1014-1018)
+        in[i] = __fmul_rn(in[i], c_enc.window[i]);
+        in[255 - i] = __fmul_rn(in[255 - i], c_enc.window[i]);
+    }
+    // DualFFT: bit-reversed load of (re, im) pairs, six radix-2 stages on 128 complex points (:1362-1471)
+    for (int i = 0; i < 128; ++i) {
+        const int idx = 2 * i;
+        const int bi = (int)(__brev((unsigned)idx) >> 23);
+        buf[bi] = in[idx];
+        buf[bi + 1] = in[idx + 1];
+    }
+    {
+        int cp = 0;
+        for (int st = 1; st <= 6; ++st) {
+            const int m = 1 << st;
+            for (int kk = 0; kk < 128; kk += m)
+                for (int j = 0; j < m / 2; ++j) {
+                    const float c = c_enc.coeff[cp], sn = c_enc.coeff[cp + 1];
+                    cp += 2;
+                    const int t = (kk + j + m / 2) * 2, u = (kk + j) * 2;
+                    const float ar = buf[t], ai = buf[t + 1];
+                    const float tr = __fsub_rn(__fmul_rn(ar, c), __fmul_rn(ai, sn));
+                    const float ti = __fadd_rn(__fmul_rn(ar, sn), __fmul_rn(ai, c));
+                    const float ur = buf[u], ui = buf[u + 1];
+                    buf[u] = __fadd_rn(tr, ur);
+                    buf[u + 1] = __fadd_rn(ti, ui);
+                    buf[t] = __fsub_rn(ur, tr);
+                    buf[t + 1] = __fsub_rn(ui, ti);
+                }
+        }
+        // the rotation of the seventh stage on the upper half only (:1473-1490), then the 1/64 scale
+        cp = 896 - 126;
+        for (int j = 1; j < 64; ++j) {
+            const float c = c_enc.coeff[cp], sn = c_enc.coeff[cp + 1];
+            cp += 2;
+            const int t = 128 + 2 * j;
+            const float ar = buf[t], ai = buf[t + 1];
+            buf[t] = __fsub_rn(__fmul_rn(ar, c), __fmul_rn(ai, sn));
+            buf[t + 1] = __fadd_rn(__fmul_rn(ar, sn), __fmul_rn(ai, c));
+        }
+        for (int i = 0; i < 256; ++i) buf[i] = __fmul_rn(buf[i], 1.0f / 64.0f);
+    }
+    // DFTAlgorithmOrig: the decoder's pre-pass steps undone in float (:1220-1356)
+    buf[1] = enc_half_sum(buf[0], buf[0x80]);
+    buf[0x81] = buf[1];
+    buf[0x100] = buf[1];
+    buf[0x101] = buf[1];
+    for (int i = 0; i < 64; ++i) {
+        const int p0 = 2 * i, p1 = 0x80 + 2 * i;
+        const float x0 = buf[p0], y0 = buf[p0 + 1], x1 = buf[p1], y1 = buf[p1 + 1];
+        buf[p0] = enc_half_sum(x0, x1);
+        buf[p0 + 1] = enc_half_sum(y0, y1);
+        buf[p1] = enc_half_diff(x0, x1);
+        buf[p1 + 1] = enc_half_diff(y0, y1);
+    }
+    for (int i = 0; i < 64; ++i) {
+        const int p0 = 2 * i, p1 = 0x100 - 2 * i;
+        const float x0 = buf[p0], y0 = buf[p0 + 1], x1 = buf[p1], y1 = buf[p1 + 1];
+        const float xs = enc_half_diff(x0, x1), ys = enc_half_sum(y0, y1);
+        const float c = c_enc.tw2[2 * i], sn = c_enc.tw2[2 * i + 1];
+        buf[p0] = enc_half_sum(x0, x1);
+        buf[p0 + 1] = enc_half_diff(y0, y1);
+        buf[p1] = __fsub_rn(__fmul_rn(xs, sn), __fmul_rn(ys, c));
+        buf[p1 + 1] = __fadd_rn(__fmul_rn(xs, c), __fmul_rn(ys, sn));
+    }
+    for (int i = 0; i < 64; ++i) {
+        const int p0 = 2 * i, p1 = 0x100 - 2 * i;
+        const float x0 = -buf[p0], y0 = -buf[p0 + 1], x1 = -buf[p1], y1 = -buf[p1 + 1];
+        buf[p0] = enc_half_sum(x0, x1);
+        buf[p0 + 1] = enc_half_sum(y0, y1);
+        buf[p1] = enc_half_diff(x0, x1);
+        buf[p1 + 1] = enc_half_diff(y0, y1);
+    }
+    buf[0x80] = -buf[0x80];
+    buf[0x81] = -buf[0x81];
+    for (int i = 129; i < 256; i += 2) buf[i] = -buf[i];
+    buf[1] = buf[0];                                                         // TransformFrame :1045
+    // the frame as kept: fbuf[1..256]; band power and range (:2545-2564)
+    float *fo = f_out + (size_t)fr * 256;
+    for (int i = 0; i < 256; ++i) fo[i] = buf[1 + i];
+    int p = 1;
+    for (int b = 0; b < 16; ++b) {
+        float l = buf[p], h = l, pw = __fmul_rn(l, l);
+        ++p;
+        for (int j = enc_band_count(b); j > 1; --j) {
+            const float v = buf[p++];
+            pw = __fadd_rn(pw, __fmul_rn(v, v));
+            if (v < l) l = v;
+            if (v > h) h = v;
+        }
+        power[(size_t)fr * 16 + b] = pw;
+        lo[(size_t)fr * 16 + b] = l;
+        hi[(size_t)fr * 16 + b] = h;
+    }
+}
+
+// K6s: per stream and band, over the frames in order: power sum (float adds in frame order, :1056-1063), extremes
+__global__ void dcsb_enc_stats_kernel(const EncStream *__restrict__ streams, int n, const float *__restrict__ power, const float *__restrict__ lo,
+                                      const float *__restrict__ hi, float *__restrict__ out /* n x 48: power sum, lo, hi */)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * 16) return;
+    const int si = t >> 4, b = t & 15;
+    const EncStream s = streams[si];
+    float ps = 0.0f, l = 0.0f, h = 0.0f;
+    for (uint32_t k = 0; k < s.n_frames; ++k) {
+        const size_t i = (size_t)(s.frame0 + k) * 16 + b;
+        ps = __fadd_rn(ps, power[i]);
+        const float fl = lo[i], fh = hi[i];
+        if (k == 0 || fl < l) l = fl;
+        if (k == 0 || fh > h) h = fh;
+    }
+    out[(size_t)si * 48 + b] = ps;
+    out[(size_t)si * 48 + 16 + b] = l;
+    out[(size_t)si * 48 + 32 + b] = h;
+}
+
+// what a band type code means for band `band` of a stream (InterpretBandTypeCode, :1840-1921): width, scale code
+__device__ __forceinline__ void enc_interpret(const EncStream &s, int band, int code, int padj, int &width, int &scale_code)
+{
+    const int sc = s.hdr[band] & 0x3F;
+    if (s.type == 0) { width = code; scale_code = sc; return; }
+    const uint32_t x = c_enc.xlat[(band < 3 ? 0 : (band < 6 ? 16 : 32)) + code];
+    width = (int)(x >> 8);
+    scale_code = sc + (int)(x & 0xFF) + (band < 3 ? padj : 0);
+}
+__device__ __forceinline__ float enc_scale(int scale_code) { return (float)c_enc.scale[scale_code < 0 ? 0 : (scale_code > 63 ? 63 : scale_code)]; }
+__device__ __forceinline__ int enc_quant(float v, float scale) { return (int)roundf(__fdiv_rn(__fmul_rn(v, 32768.0f), scale)); }
+
+// K6b: the search of FindBestBandEncoding for one band of one frame, tabulated for every scale pre-adjustment the band
+// can meet (type-1 streams, bands 0..2) and for "code 15 allowed / not allowed" (the delta code reaches old + 14 only).
+// best[frame][band][v][a]; 0 = the band's dynamic range is below the threshold (:1951-1955)
+__global__ void __launch_bounds__(ENC_THREADS)
+dcsb_enc_search_kernel(const EncStream *__restrict__ streams, const uint32_t *__restrict__ frame_stream, uint32_t n_frames_total,
+                       const float *__restrict__ f, const float *__restrict__ lo, const float *__restrict__ hi, uint8_t *__restrict__ best)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_frames_total * 16u) return;
+    const uint32_t fr = t >> 4;
+    const int band = (int)(t & 15);
+    const EncStream s = streams[frame_stream[fr]];
+    uint8_t *bo = best + (size_t)t * (ENC_NV * 2);
+    for (int i = 0; i < ENC_NV * 2; ++i) bo[i] = 0;
+    if (band >= s.bands) return;
+    if (__fsub_rn(hi[(size_t)fr * 16 + band], lo[(size_t)fr * 16 + band]) < s.min_range) return;
+    const int n = enc_band_count(band);
+    const float *x = f + (size_t)fr * 256 + enc_band_first(band);
+    const float err_max = __fmul_rn(s.max_err2, (float)n);
+    const int nv = (s.type != 0 && band < 3) ? (s.subtype == 0 ? 2 : ENC_NV) : 1;
+    for (int v = 0; v < nv; ++v) {
+        float err[16];
+        int wid[16];
+        bool pass[16];
+        for (int code = 1; code <= 15; ++code) {
+            int width, sc;
+            enc_interpret(s, band, code, v, width, sc);
+            const float scale = enc_scale(sc);
+            const int ref = width != 0 ? 1 << (width - 1) : 0;
+            const int mask = 0xFFFF >> (16 - width);
+            float sum = 0.0f;
+            for (int i = 0; i < n; ++i) {
+                const float o = x[i];
+                const int stored = (enc_quant(o, scale) + ref) & mask;
+                const float rec = __fdiv_rn(__fmul_rn((float)(stored - ref), scale), 32768.0f);
+                const float e = __fsub_rn(rec, o);
+                sum = __fadd_rn(sum, __fmul_rn(e, e));
+            }
+            err[code] = sum;
+            wid[code] = width;
+            pass[code] = sum <= err_max;
+        }
+        for (int a = 0; a < 2; ++a) {                   // FindBestResult (:1574-1621) over codes 1..15 / 1..14
+            const int top = a ? 14 : 15;
+            int narrow = -1;
+            for (int c = 1; c <= top; ++c)
+                if (pass[c] && (narrow == -1 || wid[c] < narrow)) narrow = wid[c];
+            float min_err = -1.0f;
+            int pick = 0;
+            for (int c = 1; c <= top; ++c)
+                if (narrow == -1 || wid[c] == narrow)
+                    if (min_err < 0 || err[c] < min_err) { pick = c; min_err = err[c]; }
+            bo[v * 2 + a] = (uint8_t)pick;
+        }
+    }
+}
+
+__device__ __forceinline__ int enc_preadj(const EncStream &s, int old_code)       // preAdjMap0 / preAdjMap3 (:710-716)
+{
+    if (s.type == 0) return 0;
+    if (s.subtype == 0) return old_code < 4 ? 0 : 1;
+    return old_code < 4 ? 0 : (old_code > 7 ? 4 : old_code - 3);
+}
+
+// K6c: the band type codes of every frame, in order (the previous frame's code picks the alternative)
+__global__ void dcsb_enc_resolve_kernel(const EncStream *__restrict__ streams, int n, const uint8_t *__restrict__ best,
+                                        uint8_t *__restrict__ codes /* frame x 16 */, uint8_t *__restrict__ padj /* frame x 4 */)
+{
+    const int si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= n) return;
+    const EncStream s = streams[si];
+    int old[16];
+    for (int b = 0; b < 16; ++b) old[b] = 0;
+    for (uint32_t k = 0; k < s.n_frames; ++k) {
+        const size_t fr = (size_t)s.frame0 + k;
+        int pa[3];
+        for (int b = 0; b < 3; ++b) { pa[b] = enc_preadj(s, old[b]); padj[fr * 4 + b] = (uint8_t)pa[b]; }
+        padj[fr * 4 + 3] = 0;
+        for (int b = 0; b < 16; ++b) {
+            int c = 0;
+            if (b < s.bands) {
+                const int v = b < 3 ? pa[b] : 0;
+                c = best[(fr * 16 + b) * (ENC_NV * 2) + v * 2 + (old[b] == 0 ? 1 : 0)];
+            }
+            codes[fr * 16 + b] = (uint8_t)c;
+            old[b] = c;
+        }
+    }
+}
+
+// One frame's bits (CompressFrame94 :1936-2048).  WRITE = false: count only.
+struct EncBitSink {
+    uint32_t *words;            // the stream's data words (big-endian byte order in memory)
+    unsigned long long acc;
+    int nacc;
+    uint64_t widx;
+    uint64_t count;
+    template <bool WRITE> __device__ __forceinline__ void put(uint32_t code, int len)
+    {
+        count += (uint64_t)len;
+        if (!WRITE) return;
+        acc = (acc << len) | (unsigned long long)code;
+        nacc += len;
+        while (nacc >= 32) {
+            const uint32_t w = (uint32_t)(acc >> (nacc - 32));
+            atomicOr(words + widx, __byte_perm(w, 0, 0x0123));
+            ++widx;
+            nacc -= 32;
+            acc &= (1ull << nacc) - 1ull;
+        }
+    }
+    __device__ __forceinline__ void flush()
+    {
+        if (nacc > 0) atomicOr(words + widx, __byte_perm((uint32_t)(acc << (32 - nacc)), 0, 0x0123));
+    }
+};
+
+template <bool WRITE>
+__global__ void __launch_bounds__(ENC_THREADS)
+dcsb_enc_emit_kernel(const EncStream *__restrict__ streams, const uint32_t *__restrict__ frame_stream, uint32_t n_frames_total,
+                     const float *__restrict__ f, const uint8_t *__restrict__ codes, const uint8_t *__restrict__ padj,
+                     uint32_t *__restrict__ frame_bits, const uint64_t *__restrict__ frame_pos, uint32_t *__restrict__ out_words,
+                     const uint64_t *__restrict__ stream_word0)
+{
+    const uint32_t fr = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fr >= n_frames_total) return;
+    const uint32_t si = frame_stream[fr];
+    const EncStream s = streams[si];
+    EncBitSink sink;
+    sink.count = 0;
+    sink.acc = 0;
+    sink.nacc = 0;
+    sink.widx = 0;
+    sink.words = nullptr;
+    if (WRITE) {
+        const uint64_t p = frame_pos[fr];
+        sink.words = out_words + stream_word0[si];
+        sink.widx = p >> 5;
+        sink.nacc = (int)(p & 31);          // (leading zero bits: the words line up with the stream)
+    }
+    const bool first = fr == s.frame0;
+    for (int b = 0; b < s.bands; ++b) {
+        const int oldc = first ? 0 : codes[(size_t)(fr - 1) * 16 + b];
+        const int d = (int)codes[(size_t)fr * 16 + b] - oldc + 16;
+        sink.put<WRITE>(c_enc.hdr_code[d], c_enc.hdr_len[d]);
+    }
+    for (int b = 0; b < s.bands; ++b) {
+        const int code = codes[(size_t)fr * 16 + b];
+        if (code == 0) continue;
+        int width, sc;
+        enc_interpret(s, b, code, b < 3 ? padj[(size_t)fr * 4 + b] : 0, width, sc);
+        if (width == 0) continue;
+        const float scale = enc_scale(sc);
+        const int mask = 0xFFFF >> (16 - width);
+        const bool book = width <= 6;
+        const int ref = book ? 1 << (width - 1) : 0;
+        const int n = enc_band_count(b);
+        const float *x = f + (size_t)fr * 256 + enc_band_first(b);
+        int q[32];
+        for (int i = 0; i < n; ++i) q[i] = enc_quant(x[i], scale);
+        for (int i = 0; i < n; ++i) {
+            if (book && q[i] == 0 && i + 1 < n && q[i + 1] == 0) {
+                sink.put<WRITE>(c_enc.dz_code[width - 1], c_enc.dz_len[width - 1]);
+                ++i;
+            } else {
+                const int v = (q[i] + ref) & mask;
+                if (book) sink.put<WRITE>(c_enc.cb_code[width - 1][v], c_enc.cb_len[width - 1][v]);
+                else sink.put<WRITE>((uint32_t)v, width);
+            }
+        }
+    }
+    if (WRITE) sink.flush();
+    else frame_bits[fr] = (uint32_t)sink.count;
+}
+
+// per stream: bit position of every frame, total bits
+__global__ void dcsb_enc_scan_kernel(const EncStream *__restrict__ streams, int n, const uint32_t *__restrict__ frame_bits,
+                                     uint64_t *__restrict__ frame_pos, uint64_t *__restrict__ stream_bits)
+{
+    const int si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= n) return;
+    const EncStream s = streams[si];
+    uint64_t p = 0;
+    for (uint32_t k = 0; k < s.n_frames; ++k) {
+        frame_pos[s.frame0 + k] = p;
+        p += frame_bits[s.frame0 + k];
+    }
+    stream_bits[si] = p;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+static void enc_build_tables(EncTables *t)
+{
+    // DualFFT twiddles exactly as the reference makes them: float theta, cosf / sinf (:1384-1398)
+    {
+        const float PI = 3.1415926536f;
+        float *cp = t->coeff;
+        for (int s = 1; s <= 7; ++s) {
+            const int m = 1 << s;
+            for (int k = 0; k < 128; k += m)
+                for (int j = 0; j < m / 2; ++j) {
+                    const float theta = -2 * PI * static_cast<float>(j) / static_cast<float>(m);
+                    *cp++ = cosf(theta);
+                    *cp++ = sinf(theta);
+                }
+        }
+    }
+    // the second table is the decoder's 1.15 twiddles printed with seven decimals (:1263-1280): -cos, -sin of i pi / 128
+    for (int i = 0; i < 64; ++i) {
+        const double th = 3.14159265358979323846 * i / 128.0;
+        const long c = lround(cos(th) * 32768.0), s = lround(sin(th) * 32768.0);
+        char tmp[32];
+        snprintf(tmp, sizeof(tmp), "%.7f", -(double)c / 32768.0);
+        t->tw2[2 * i] = strtof(tmp, nullptr);
+        snprintf(tmp, sizeof(tmp), "%.7f", -(double)s / 32768.0);
+        t->tw2[2 * i + 1] = strtof(tmp, nullptr);
+    }
+    static const float window[16] = { 0.010179f, 0.040507f, 0.090368f, 0.158746f, 0.244250f, 0.345139f, 0.459359f, 0.584585f,
+                                      0.647178f, 0.752018f, 0.829799f, 0.888221f, 0.932184f, 0.964581f, 0.986700f, 0.998439f };
+    memcpy(t->window, window, sizeof(window));
+    for (int j = 0; j < 64; ++j) {
+        const uint32_t m = (j & 2) ? ((j & 1) ? 0xd745u : 0xb505u) : ((j & 1) ? 0x9838u : 0x8000u);
+        t->scale[j] = (int)(m >> (15 - ((j >> 2) & 15)));
+    }
+    static const uint16_t xl[48] = {
+        0x0000, 0x0100, 0x0200, 0x0300, 0x0400, 0x0402, 0x0405, 0x0505, 0x0509, 0x050d, 0x060d, 0x0611, 0x0615, 0x0719, 0x071d, 0x081d,
+        0x0000, 0x0100, 0x0200, 0x0300, 0x0400, 0x0402, 0x0407, 0x040b, 0x050b, 0x050f, 0x0513, 0x0517, 0x0617, 0x061b, 0x061f, 0x071f,
+        0x0000, 0x0100, 0x0200, 0x0300, 0x0302, 0x0402, 0x0407, 0x040b, 0x050b, 0x050f, 0x0513, 0x0517, 0x0617, 0x061b, 0x061f, 0x0723 };
+    memcpy(t->xlat, xl, sizeof(xl));
+    const dcs_code_t *cbs[6] = { dcs94_cb1, dcs94_cb2, dcs94_cb3, dcs94_cb4, dcs94_cb5, dcs94_cb6 };
+    const int ncb[6] = { 3, 5, 9, 17, 33, 65 };
+    memset(t->cb_code, 0, sizeof(t->cb_code));
+    memset(t->cb_len, 0, sizeof(t->cb_len));
+    for (int k = 0; k < 6; ++k)
+        for (int i = 0; i < ncb[k]; ++i) {
+            const dcs_code_t &e = cbs[k][i];
+            if (e.val == 0x80) { t->dz_code[k] = e.code; t->dz_len[k] = e.len; }
+            else { t->cb_code[k][e.val & 63] = e.code; t->cb_len[k][e.val & 63] = e.len; }
+        }
+    for (int i = 0; i < 31; ++i) {
+        const dcs_code_t &e = dcs94_hdr[i];
+        const int d = (int)e.val - 0x2E + 16;
+        t->hdr_code[d] = e.code;
+        t->hdr_len[d] = e.len;
+    }
+}
+
+// CloseStream's power cut (:738-770) and CompressStream's header (:866-974) for one stream
+static void enc_stream_header(const float *stats /* 48 */, const dcsb_encode_params &pr, const EncTables &tab, EncStream *s)
+{
+    static const float norm[16] = { 16.0f / 7, 16.0f / 8, 16.0f / 16, 16.0f / 16, 16.0f / 16, 16.0f / 16, 16.0f / 16, 16.0f / 16,
+                                    16.0f / 16, 16.0f / 16, 16.0f / 16, 16.0f / 16, 16.0f / 16, 16.0f / 16, 16.0f / 16, 16.0f / 32 };
+    static const int counts[16] = { 7, 8, 16, 16, 16, 16, 16, 16, 16, 16, 16, 16, 16, 16, 16, 32 };
+    float rms[16], total = 0.0f;
+    for (int i = 0; i < 16; ++i) {
+        rms[i] = sqrtf(stats[i] * norm[i]);
+        total += rms[i];
+    }
+    const float pn = 1.0f / total;
+    int keep = 16;
+    if (total != 0.0f) {
+        float below = 0.0f;
+        for (int i = 0; i < 16; ++i) {
+            below += rms[i] * pn;
+            if (below >= pr.power_band_cutoff) { keep = i; break; }
+        }
+    }
+    const float fps = 31250.0f / 240.0f;
+    const float bpf = static_cast<float>(pr.target_bit_rate) / fps;
+    static const int share[16] = { 16, 14, 12, 10, 9, 8, 6, 5, 4, 4, 3, 3, 3, 3, 2, 2 };
+    float share_norm = 0;
+    for (int i = 0; i < keep; ++i) share_norm += static_cast<float>(share[i] * counts[i]);
+    uint8_t *h = s->hdr;
+    for (int band = 0; band < keep; ++band) {
+        const int bits = static_cast<int>(static_cast<float>(share[band]) / share_norm * bpf);
+        float lo = stats[16 + band] * -32768.0f, hi = stats[32 + band] * 32768.0f;
+        if (lo < 0) lo = 0;
+        if (hi < 0) hi = 0;
+        const float full = hi > lo ? hi : lo;
+        const int divider = 1 << bits;
+        const int target = full != 0 ? static_cast<int>(ceil(full / divider)) : 1;
+        h[band] = 0;
+        for (int j = 0; j < 64; ++j) {
+            if (tab.scale[j] < target) h[band] = (uint8_t)j;
+            else break;
+        }
+        if (pr.stream_type == 1) {
+            int adjust = (band < 3) ? 0x0d : 0x17;
+            adjust += pr.stream_subtype == 0 ? 1 : 3;
+            if (h[band] > adjust) h[band] = (uint8_t)(h[band] - adjust);
+            else h[band] = 0;
+        }
+    }
+    for (int band = keep; band < 16; ++band) h[band] = 0xFF;
+    if (pr.stream_type != 0) h[0] |= 0x80;
+    h[1] |= (uint8_t)((pr.stream_subtype & 0x02) << 6);
+    h[2] |= (uint8_t)((pr.stream_subtype & 0x01) << 7);
+    // (the frame compressor stops at the first band whose low seven bits are all set, :1936)
+    int bands = 0;
+    while (bands < 16 && (h[bands] & 0x7F) != 0x7F) ++bands;
+    s->bands = bands;
+}
+
+#define CKE(x, what) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = fail(ctx, DCSB_E_CUDA, what, e_); goto done; } } while (0)
+
+extern "C" uint64_t dcsb_encode_bound(uint64_t n_samples)
+{
+    const uint64_t frames = (n_samples + 239) / 240;
+    return 18 + frames * ((16 * 23 + 255 * 15 + 7) / 8 + 1) + 8;
+}
+
+extern "C" int dcsb_encode_streams(dcsb_ctx *ctx, const float *const *pcm, const uint64_t *n_samples, size_t n,
+                                   const dcsb_encode_params *params, uint8_t *out, uint64_t out_capacity, uint64_t *out_offsets,
+                                   float *frames_out)
+{
+    if (!ctx || (n && (!pcm || !n_samples || !params || !out || !out_offsets))) return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: bad argument");
+    if (n == 0) return DCSB_OK;
+    uint64_t total_samples = 0, total_frames = 0;
+    std::vector<EncStream> hs(n);
+    for (size_t i = 0; i < n; ++i) {
+        const dcsb_encode_params &p = params[i];
+        if (!pcm[i] || n_samples[i] == 0) return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: empty clip");
+        if ((p.stream_type != 0 && p.stream_type != 1) || (p.stream_subtype != 0 && p.stream_subtype != 3) || p.target_bit_rate <= 0)
+            return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: stream type must be 0 or 1, subtype 0 or 3, bit rate positive");
+        const uint64_t nf = (n_samples[i] + 239) / 240;
+        if (nf > 65535) return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: a stream holds at most 65535 frames");
+        EncStream &s = hs[i];
+        memset(&s, 0, sizeof(s));
+        s.pcm_off = total_samples;
+        s.n_samples = n_samples[i];
+        s.frame0 = (uint32_t)total_frames;
+        s.n_frames = (uint32_t)nf;
+        s.type = p.stream_type;
+        s.subtype = p.stream_subtype;
+        s.max_err2 = p.max_quantization_error * p.max_quantization_error;
+        s.min_range = p.min_dynamic_range;
+        total_samples += n_samples[i];
+        total_frames += nf;
+    }
+    if (total_frames >= 0x0FFFFFFFull) return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: more than 2^28 frames in one call");
+    int rc = DCSB_OK;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, DCSB_E_CUDA, "cudaSetDevice");
+    static EncTables tab;
+    static bool tab_ready = false;
+    if (!tab_ready) { enc_build_tables(&tab); tab_ready = true; }
+    float *d_pcm = nullptr, *d_f = nullptr, *d_power = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_stats = nullptr;
+    EncStream *d_streams = nullptr;
+    uint32_t *d_frame_stream = nullptr, *d_frame_bits = nullptr, *d_words = nullptr;
+    uint8_t *d_best = nullptr, *d_codes = nullptr, *d_padj = nullptr;
+    uint64_t *d_frame_pos = nullptr, *d_stream_bits = nullptr, *d_word0 = nullptr;
+    std::vector<uint32_t> frame_stream(total_frames);
+    std::vector<float> stats(n * 48);
+    std::vector<uint64_t> sbits(n), word0(n + 1, 0);
+    std::vector<uint32_t> words;
+    const uint32_t nfr = (uint32_t)total_frames;
+    const unsigned gf = (nfr + ENC_THREADS - 1) / ENC_THREADS, gfb = (unsigned)(((uint64_t)nfr * 16 + ENC_THREADS - 1) / ENC_THREADS);
+    const unsigned gs = (unsigned)((n + 63) / 64), gsb = (unsigned)((n * 16 + 63) / 64);
+    for (size_t i = 0; i < n; ++i)
+        for (uint32_t k = 0; k < hs[i].n_frames; ++k) frame_stream[hs[i].frame0 + k] = (uint32_t)i;
+    CKE(cudaMemcpyToSymbol(c_enc, &tab, sizeof(tab)), "H2D encoder tables");
+    CKE(cudaMalloc(&d_pcm, total_samples * sizeof(float)), "cudaMalloc(pcm)");
+    for (size_t i = 0; i < n; ++i)
+        CKE(cudaMemcpy(d_pcm + hs[i].pcm_off, pcm[i], n_samples[i] * sizeof(float), cudaMemcpyHostToDevice), "H2D pcm");
+    CKE(cudaMalloc(&d_streams, n * sizeof(EncStream)), "cudaMalloc(streams)");
+    CKE(cudaMemcpy(d_streams, hs.data(), n * sizeof(EncStream), cudaMemcpyHostToDevice), "H2D streams");
+    CKE(cudaMalloc(&d_frame_stream, total_frames * 4), "cudaMalloc(frame map)");
+    CKE(cudaMemcpy(d_frame_stream, frame_stream.data(), total_frames * 4, cudaMemcpyHostToDevice), "H2D frame map");
+    CKE(cudaMalloc(&d_f, total_frames * 256 * sizeof(float)), "cudaMalloc(frames)");
+    CKE(cudaMalloc(&d_power, total_frames * 16 * sizeof(float)), "cudaMalloc(power)");
+    CKE(cudaMalloc(&d_lo, total_frames * 16 * sizeof(float)), "cudaMalloc(lo)");
+    CKE(cudaMalloc(&d_hi, total_frames * 16 * sizeof(float)), "cudaMalloc(hi)");
+    CKE(cudaMalloc(&d_stats, n * 48 * sizeof(float)), "cudaMalloc(stats)");
+    dcsb_enc_transform_kernel<<<gf, ENC_THREADS>>>(d_pcm, d_streams, d_frame_stream, nfr, d_f, d_power, d_lo, d_hi);
+    dcsb_enc_stats_kernel<<<gsb, 64>>>(d_streams, (int)n, d_power, d_lo, d_hi, d_stats);
+    CKE(cudaGetLastError(), "encoder kernel launch");
+    CKE(cudaMemcpy(stats.data(), d_stats, n * 48 * sizeof(float), cudaMemcpyDeviceToHost), "D2H band statistics");
+    if (frames_out) CKE(cudaMemcpy(frames_out, d_f, total_frames * 256 * sizeof(float), cudaMemcpyDeviceToHost), "D2H frames");
+    for (size_t i = 0; i < n; ++i) enc_stream_header(&stats[i * 48], params[i], tab, &hs[i]);
+    CKE(cudaMemcpy(d_streams, hs.data(), n * sizeof(EncStream), cudaMemcpyHostToDevice), "H2D streams");
+    CKE(cudaMalloc(&d_best, total_frames * 16 * ENC_NV * 2), "cudaMalloc(search table)");
+    CKE(cudaMalloc(&d_codes, total_frames * 16), "cudaMalloc(codes)");
+    CKE(cudaMalloc(&d_padj, total_frames * 4), "cudaMalloc(pre-adjustments)");
+    CKE(cudaMalloc(&d_frame_bits, total_frames * 4), "cudaMalloc(frame sizes)");
+    CKE(cudaMalloc(&d_frame_pos, total_frames * 8), "cudaMalloc(frame positions)");
+    CKE(cudaMalloc(&d_stream_bits, n * 8), "cudaMalloc(stream sizes)");
+    CKE(cudaMalloc(&d_word0, (n + 1) * 8), "cudaMalloc(stream offsets)");
+    dcsb_enc_search_kernel<<<gfb, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, d_lo, d_hi, d_best);
+    dcsb_enc_resolve_kernel<<<gs, 64>>>(d_streams, (int)n, d_best, d_codes, d_padj);
+    dcsb_enc_emit_kernel<false><<<gf, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, d_codes, d_padj, d_frame_bits, nullptr, nullptr, nullptr);
+    dcsb_enc_scan_kernel<<<gs, 64>>>(d_streams, (int)n, d_frame_bits, d_frame_pos, d_stream_bits);
+    CKE(cudaGetLastError(), "encoder kernel launch");
+    CKE(cudaMemcpy(sbits.data(), d_stream_bits, n * 8, cudaMemcpyDeviceToHost), "D2H stream sizes");
+    {
+        uint64_t need = 0;
+        for (size_t i = 0; i < n; ++i) {
+            word0[i + 1] = word0[i] + (sbits[i] + 31) / 32 + 1;
+            need += 18 + (sbits[i] + 7) / 8;
+        }
+        if (need > out_capacity) { rc = fail(ctx, DCSB_E_NOMEM, "dcsb_encode_streams: output buffer too small (see dcsb_encode_bound)"); goto done; }
+    }
+    CKE(cudaMalloc(&d_words, word0[n] * 4), "cudaMalloc(stream data)");
+    CKE(cudaMemset(d_words, 0, word0[n] * 4), "memset stream data");
+    CKE(cudaMemcpy(d_word0, word0.data(), (n + 1) * 8, cudaMemcpyHostToDevice), "H2D stream offsets");
+    dcsb_enc_emit_kernel<true><<<gf, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, d_codes, d_padj, nullptr, d_frame_pos, d_words, d_word0);
+    CKE(cudaGetLastError(), "encoder kernel launch");
+    words.resize(word0[n]);
+    CKE(cudaMemcpy(words.data(), d_words, word0[n] * 4, cudaMemcpyDeviceToHost), "D2H stream data");
+    {
+        uint64_t o = 0;
+        for (size_t i = 0; i < n; ++i) {                  // BitWriter::Store (:2665-2703): frame count, header, data
+            out_offsets[i] = o;
+            out[o++] = (uint8_t)(hs[i].n_frames >> 8);
+            out[o++] = (uint8_t)(hs[i].n_frames & 0xFF);
+            memcpy(out + o, hs[i].hdr, 16);
+            o += 16;
+            const uint64_t nb = (sbits[i] + 7) / 8;
+            memcpy(out + o, reinterpret_cast<const uint8_t *>(words.data() + word0[i]), nb);
+            o += nb;
+        }
+        out_offsets[n] = o;
+    }
+done:
+    cudaFree(d_pcm); cudaFree(d_f); cudaFree(d_power); cudaFree(d_lo); cudaFree(d_hi); cudaFree(d_stats); cudaFree(d_streams);
+    cudaFree(d_frame_stream); cudaFree(d_frame_bits); cudaFree(d_words); cudaFree(d_best); cudaFree(d_codes); cudaFree(d_padj);
+    cudaFree(d_frame_pos); cudaFree(d_stream_bits); cudaFree(d_word0);
+    return rc;
+}

@@ -182,6 +182,51 @@ size_t dcsref_encode(const float *pcm, size_t n, int sample_rate, int format_ver
     return obj.nBytes;
 }
 
+// The reference encoder WITHOUT its resampler: the samples are framed directly (16 samples of overlap, 240 new ones
+// per frame, the last frame zero padded -- what WriteStream does with the resampler's output, DCSEncoder.cpp:693-703)
+// and handed to the reference's own TransformFrame / CloseStream.  This is the oracle for the GPU encoder, which has no
+// resampler either.  frames_out (may be NULL): the 256 floats the reference keeps per frame (Stream::Frame::f,
+// DCSEncoder.h:322), n_frames_cap of them at most.  Returns the stream's byte count (0 on failure).
+struct EncProbe : DCSEncoder {
+    size_t encode_framed(const float *pcm, size_t n, uint8_t *out, size_t cap, int *n_frames, float *frames_out, size_t n_frames_cap)
+    {
+        std::string err;
+        Stream *s = OpenStream(31250, err);
+        if (s == nullptr) return 0;
+        for (size_t i = 0; i < n; ++i) {
+            s->inputBuf[s->nInputBuf++] = pcm[i];
+            if (s->nInputBuf == 256) TransformFrame(s);
+        }
+        DCSAudio obj;
+        if (!CloseStream(s, obj, err)) return 0;
+        if (frames_out) {
+            size_t k = 0;
+            for (auto &f : s->frames) {
+                if (k >= n_frames_cap) break;
+                memcpy(frames_out + 256 * k, f.f, 256 * sizeof(float));
+                ++k;
+            }
+        }
+        if (n_frames) *n_frames = obj.nFrames;
+        if (obj.nBytes > cap) return 0;
+        memcpy(out, obj.data.get(), obj.nBytes);
+        return obj.nBytes;
+    }
+};
+size_t dcsref_encode_framed(const float *pcm, size_t n, int type, int subtype, int bit_rate, float power_cut,
+    float max_quant_error, float min_dynamic_range, uint8_t *out, size_t cap, int *n_frames, float *frames_out, size_t n_frames_cap)
+{
+    EncProbe enc;
+    enc.compressionParams.formatVersion = 0x9400;
+    enc.compressionParams.streamFormatType = type;
+    enc.compressionParams.streamFormatSubType = subtype;
+    enc.compressionParams.targetBitRate = bit_rate;
+    enc.compressionParams.powerBandCutoff = power_cut;
+    if (max_quant_error >= 0) enc.compressionParams.maximumQuantizationError = max_quant_error;
+    if (min_dynamic_range >= 0) enc.compressionParams.minimumDynamicRange = min_dynamic_range;
+    return enc.encode_framed(pcm, n, out, cap, n_frames, frames_out, n_frames_cap);
+}
+
 // The reference's reader of raw ".dcs" stream files (DCSEncoder::IsDCSFile / EncodeDCSFile,
 // DCSEncoder.cpp:358-571): is `path` a DCS file, which format version does its header name, and which
 // stream bytes does the reference take from it when the target format is the file's own (the pass-through

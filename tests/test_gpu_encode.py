@@ -1,0 +1,79 @@
+"""GPU forward path (dcsb_encode_streams) against the reference's DCSEncoder fed the same framing
+(oracle/ref_shim.cpp: dcsref_encode_framed -- the reference minus its resampler): the transformed frames and the
+stream BYTES must be the reference's; the streams must decode, and decode to the same PCM through our decoder and the
+reference's."""
+import numpy as np
+import pytest
+from oracle import ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(built):
+    import dcsexplorer_b200 as dx
+    c = dx.Context(0)
+    yield c
+    c.close()
+
+
+def _clips():
+    import bench
+    rng = np.random.default_rng(11)
+    clips = [bench.synth_source(40 + i, 1.5 + 0.37 * i) for i in range(6)]
+    clips.append(np.zeros(1000, dtype=np.float32))                                  # silence
+    clips.append((0.9 * np.sin(np.arange(5000) * 0.05)).astype(np.float32))         # loud tone
+    clips.append((rng.standard_normal(240 * 7) * 0.3).astype(np.float32))           # a whole number of frames
+    clips.append((rng.standard_normal(17) * 0.01).astype(np.float32))               # less than one frame
+    return clips
+
+
+PARAMS = [(0, 0, 128000, 0.97), (0, 3, 64000, 0.90), (1, 0, 128000, 0.97), (1, 3, 256000, 1.0), (1, 3, 32000, 0.97), (0, 0, 96000, 1.0)]
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref did not travel with the snapshot")
+def test_gpu_encode_frames_and_bytes_equal_the_reference(ctx):
+    clips = _clips()
+    jobs = [(c, p) for c in clips for p in PARAMS]
+    streams, frames = ctx.encode_streams([j[0] for j in jobs], [j[1] for j in jobs], want_frames=True)
+    nbad_frames = nbad_bytes = 0
+    for (clip, p), got, fr in zip(jobs, streams, frames):
+        want, nf, wfr = ref.encode_framed(clip, p[0], p[1], p[2], p[3], want_frames=True)
+        assert fr.shape[0] == nf
+        if not np.array_equal(fr.view(np.uint32), wfr.view(np.uint32)):
+            nbad_frames += 1
+        if got != want:
+            nbad_bytes += 1
+    assert nbad_frames == 0, "%d of %d clips: transformed frames differ from the reference's (bit pattern)" % (nbad_frames, len(jobs))
+    assert nbad_bytes == 0, "%d of %d streams differ from the reference encoder's bytes" % (nbad_bytes, len(jobs))
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref did not travel with the snapshot")
+def test_gpu_encoded_streams_decode_like_the_reference(ctx):
+    clips = _clips()[:6]
+    params = [PARAMS[i % len(PARAMS)] for i in range(len(clips))]
+    streams = ctx.encode_streams(clips, params)
+    pcm, offs, res = ctx.decode_streams([(s, 0x9400, 255, 0x64, 2) for s in streams])
+    for i, s in enumerate(streams):
+        assert res[i]["status"] == 0
+        want = ref.decode(s)
+        assert np.array_equal(pcm[offs[i]:offs[i] + want.size], want)
+        # and it is the clip (the codec delays it by its 16-sample overlap; lossy, so only loosely): best correlation
+        # with the source over small lags
+        n = min(len(clips[i]), want.size) - 64
+        a = clips[i][:n].astype(np.float64)
+        best = max(np.corrcoef(a, want[lag:lag + n].astype(np.float64))[0, 1] for lag in range(0, 48))
+        assert best > 0.5, (i, best)
+
+
+def test_gpu_encode_rejects_bad_arguments(ctx):
+    import dcsexplorer_b200 as dx
+    clip = np.zeros(480, dtype=np.float32)
+    with pytest.raises(dx.DcsbError):
+        ctx.encode_streams([clip], [(2, 0, 128000, 0.97)])
+    with pytest.raises(dx.DcsbError):
+        ctx.encode_streams([clip], [(0, 1, 128000, 0.97)])
+    with pytest.raises(dx.DcsbError):
+        ctx.encode_streams([np.zeros(0, dtype=np.float32)], [(0, 0, 128000, 0.97)])
+    with pytest.raises(dx.DcsbError):
+        ctx.encode_streams([np.zeros(240 * 65536 + 1, dtype=np.float32)], [(0, 0, 128000, 0.97)])
