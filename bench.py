@@ -313,6 +313,44 @@ def config3(ctx, dx, torch, n=4096, pool_n=96, seconds=10.0):
     return out
 
 
+def _ref_encode_framed(args):
+    from oracle import ref
+    seed, seconds = args
+    ty, sub = TYPES[seed % 3]
+    d, nf = ref.encode_framed(synth_source(seed, seconds), ty, sub, RATES[(seed // 3) % 6], CUTS[(seed // 18) % 3])
+    return d
+
+
+def encoder_record(ctx, dx, n=128, seconds=10.0):
+    """SURVEY 8(f)4, the forward path: n clips of the corpus' parameter grid through dcsb_encode_streams, every stream's
+    bytes against the reference DCSEncoder fed the same framing (a bounded sample on the host cores)"""
+    from oracle import ref
+    seeds = [9000 + i for i in range(n)]
+    clips = [synth_source(sd, seconds) for sd in seeds]
+    pl = [(TYPES[sd % 3][0], TYPES[sd % 3][1], RATES[(sd // 3) % 6], CUTS[(sd // 18) % 3]) for sd in seeds]
+    ts = []
+    for it in range(3):
+        t0 = time.perf_counter()
+        got = ctx.encode_streams(clips, pl)
+        ts.append(time.perf_counter() - t0)
+    samples = sum(c.size for c in clips)
+    res = {"workload": "%d clips x %.0f s, stream types {0.0, 1.0, 1.3} x bit rates 32k..256k x power cut {.90, .97, 1}" % (n, seconds),
+           "ms_per_call": min(ts[1:]) * 1e3, "value": samples / min(ts[1:]) / 1e6, "unit": "Msamples/s encoded",
+           "api": "dcsb_encode_streams (host PCM in, host stream bytes out)", "stream_bytes": int(sum(len(g) for g in got))}
+    if ref.available():
+        import multiprocessing as mp
+        ncpu = max(1, len(os.sched_getaffinity(0)))
+        k = min(n, 4 * ncpu)
+        t0 = time.perf_counter()
+        with mp.get_context("fork").Pool(ncpu) as pool:
+            want = pool.map(_ref_encode_framed, [(sd, seconds) for sd in seeds[:k]], chunksize=1)
+        tref = time.perf_counter() - t0
+        res.update({"parity_checked_streams": k, "mismatches": sum(1 for a, b in zip(got[:k], want) if a != b),
+                    "checked_against": "stream bytes of the reference DCSEncoder fed the same framing (oracle/_ref, dcsref_encode_framed)",
+                    "reference_host_threads": ncpu, "reference_value": sum(c.size for c in clips[:k]) / tref / 1e6})
+    return res
+
+
 def config4(ctx, dx, torch, n=2048):
     """track playback on the ROM built by the reference's DCSCompiler: n timelines + every track solo, one call"""
     import compiledrom
@@ -723,7 +761,7 @@ def _main(out):
             torch.cuda.empty_cache()
             cfg = {}
             for name, fn in (("config1", lambda: config1(ctx, dx)), ("config3", lambda: config3(ctx, dx, torch)),
-                             ("config4", lambda: config4(ctx, dx, torch))):
+                             ("config4", lambda: config4(ctx, dx, torch)), ("encoder", lambda: encoder_record(ctx, dx))):
                 t0 = time.time()
                 try:
                     cfg[name] = fn()

@@ -66,6 +66,42 @@ def test_gpu_encoded_streams_decode_like_the_reference(ctx):
         assert best > 0.5, (i, best)
 
 
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref did not travel with the snapshot")
+def test_gpu_encode_random_clips_and_parameters_equal_the_reference(ctx):
+    """seeded clips of several kinds (noise, tones, sweeps, bursts, near-silence, clipped) with random stream types, bit rates
+    8k..512k, power cuts, quantisation-error and dynamic-range thresholds: every stream byte-identical to the reference's"""
+    rng = np.random.default_rng(2024)
+    clips, params = [], []
+    for i in range(160):
+        n = int(rng.integers(100, 40000))
+        t = np.arange(n)
+        kind = i % 6
+        if kind == 0:
+            x = rng.standard_normal(n) * rng.uniform(0.001, 0.5)
+        elif kind == 1:
+            x = rng.uniform(0.05, 1.0) * np.sin(t * rng.uniform(0.001, 3.0))
+        elif kind == 2:
+            x = 0.5 * np.sin(t * t * rng.uniform(1e-6, 1e-4))
+        elif kind == 3:
+            x = (rng.standard_normal(n) * 0.4) * (np.sin(t * 0.002) > 0.7)
+        elif kind == 4:
+            x = rng.standard_normal(n) * 1e-4
+        else:
+            x = np.clip(rng.standard_normal(n) * 1.5, -1.0, 1.0)
+        clips.append(x.astype(np.float32))
+        ty = int(rng.integers(0, 2))
+        params.append((ty, int(rng.choice([0, 3])), int(rng.choice([8000, 32000, 64000, 128000, 256000, 512000])),
+                       float(rng.choice([0.5, 0.9, 0.97, 1.0])), float(rng.choice([1.0, 10.0, 100.0])) / 32768.0,
+                       float(rng.choice([0.0, 10.0, 200.0])) / 32768.0))
+    streams = ctx.encode_streams(clips, params)
+    bad = []
+    for i, (c, p) in enumerate(zip(clips, params)):
+        want, nf = ref.encode_framed(c, p[0], p[1], p[2], p[3], p[4], p[5])
+        if streams[i] != want:
+            bad.append((i, p, len(streams[i]), len(want)))
+    assert not bad, "%d of %d streams differ from the reference encoder's: %s" % (len(bad), len(clips), bad[:5])
+
+
 def test_gpu_encode_rejects_bad_arguments(ctx):
     import dcsexplorer_b200 as dx
     clip = np.zeros(480, dtype=np.float32)
