@@ -3,7 +3,7 @@
 synccheck) on the GPU box:  compute-sanitizer --tool memcheck python tools/sanitize_run.py
 Paths: resident batch with the scan beside the persistent decode kernel (ready queue, gate kernel), the two
 kernels one after the other, dcsb_decode_streams with pinned buffers (time-sliced, resumed scans), the same with
-a pageable buffer, the scan variant without rings, 1993 layouts, damaged streams, ROM timeline rendering."""
+a pageable buffer, the scan variant without rings, 1993 layouts, damaged streams, ROM timeline rendering, the encoder."""
 import os
 import sys
 import numpy as np
@@ -57,5 +57,11 @@ for f in range(40):
     p.render(1)
 p.close()
 rom.close()
+# the forward path: a few clips of every stream type (incl. one shorter than a frame), decoded again
+erng = np.random.default_rng(3)
+clips = [(erng.standard_normal(n) * 0.2).astype(np.float32) for n in (17, 240, 1000, 5000, 12345)]
+enc = ctx.encode_streams(clips * 4, [(t, u, 96000, 0.97) for t, u in ((0, 0), (0, 3), (1, 0), (1, 3)) for _ in clips])
+pcm, offs, res = ctx.decode_streams([(e, 0x9400, 255, 0x64, 2) for e in enc])
+assert all(r["status"] == 0 for r in res)
 ctx.close()
 print("sanitize_run: ok, %d streams" % len(streams))
