@@ -58,6 +58,7 @@ extern "C" void dcsb_destroy(dcsb_ctx *ctx)
                             &l.d_endbits, &l.d_stopband, &l.d_csum, &l.d_pcm, &l.d_queue, &l.d_order }) b->release(false);
     }
     if (ctx->timeline_cache && ctx->timeline_cache_free) ctx->timeline_cache_free(ctx->timeline_cache);
+    if (ctx->encode_cache && ctx->encode_cache_free) ctx->encode_cache_free(ctx->encode_cache);
     if (ctx->aux) { cudaStreamSynchronize(ctx->aux); cudaStreamDestroy(ctx->aux); }
     if (ctx->up) { cudaStreamSynchronize(ctx->up); cudaStreamDestroy(ctx->up); }
     if (ctx->down) { cudaStreamSynchronize(ctx->down); cudaStreamDestroy(ctx->down); }

@@ -93,6 +93,8 @@ struct dcsb_ctx {
     // dcsb_render_timelines: stream, device buffers and pinned staging kept for the next call (dcsb_player.cu owns the type)
     void *timeline_cache = nullptr;
     void (*timeline_cache_free)(void *) = nullptr;
+    void *encode_cache = nullptr;                // buffers of dcsb_encode_streams, kept between calls (dcsb_encode.cu)
+    void (*encode_cache_free)(void *) = nullptr;
     std::string err;
 };
 

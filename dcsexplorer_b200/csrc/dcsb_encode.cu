@@ -15,9 +15,12 @@
 // through two small rules, so K6b tabulates the alternatives and K6c picks), K6d frame sizes, K6e bit packing.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
+#include <chrono>
 #include <vector>
 #include "dcsb_internal.h"
 #include "dcsb_ctx.h"
@@ -509,6 +512,23 @@ static void enc_stream_header(const float *stats /* 48 */, const dcsb_encode_par
     s->bands = bands;
 }
 
+// device / pinned buffers kept in the context between calls (no allocation in the steady state)
+struct EncCache {
+    DcsbBuf pcm, f, power, lo, hi, stats, streams, frame_stream, frame_bits, words, best, codes, padj, frame_pos, stream_bits, word0;
+    DcsbBuf h_words, h_pcm;          // pinned staging: stream data on its way out, PCM on its way in
+    bool tables_up = false;
+};
+static void enc_cache_free(void *p)
+{
+    EncCache *c = static_cast<EncCache *>(p);
+    if (!c) return;
+    for (DcsbBuf *b : { &c->pcm, &c->f, &c->power, &c->lo, &c->hi, &c->stats, &c->streams, &c->frame_stream, &c->frame_bits, &c->words,
+                        &c->best, &c->codes, &c->padj, &c->frame_pos, &c->stream_bits, &c->word0 }) b->release(false);
+    c->h_words.release(true);
+    c->h_pcm.release(true);
+    delete c;
+}
+
 #define CKE(x, what) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = fail(ctx, DCSB_E_CUDA, what, e_); goto done; } } while (0)
 
 extern "C" uint64_t dcsb_encode_bound(uint64_t n_samples)
@@ -548,88 +568,139 @@ extern "C" int dcsb_encode_streams(dcsb_ctx *ctx, const float *const *pcm, const
     if (total_frames >= 0x0FFFFFFFull) return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: more than 2^28 frames in one call");
     int rc = DCSB_OK;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, DCSB_E_CUDA, "cudaSetDevice");
+    const bool trace = getenv("DCSB_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {            // DCSB_TRACE=1: host-side phases of the call
+        if (!trace) return;
+        cudaDeviceSynchronize();
+        fprintf(stderr, "[dcsb trace] encode_streams %-28s at %8.3f ms\n", what,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
     static EncTables tab;
     static bool tab_ready = false;
     if (!tab_ready) { enc_build_tables(&tab); tab_ready = true; }
-    float *d_pcm = nullptr, *d_f = nullptr, *d_power = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_stats = nullptr;
-    EncStream *d_streams = nullptr;
-    uint32_t *d_frame_stream = nullptr, *d_frame_bits = nullptr, *d_words = nullptr;
-    uint8_t *d_best = nullptr, *d_codes = nullptr, *d_padj = nullptr;
-    uint64_t *d_frame_pos = nullptr, *d_stream_bits = nullptr, *d_word0 = nullptr;
+    if (!ctx->encode_cache) { ctx->encode_cache = new EncCache(); ctx->encode_cache_free = enc_cache_free; }
+    EncCache &ec = *static_cast<EncCache *>(ctx->encode_cache);
     std::vector<uint32_t> frame_stream(total_frames);
     std::vector<float> stats(n * 48);
     std::vector<uint64_t> sbits(n), word0(n + 1, 0);
-    std::vector<uint32_t> words;
     const uint32_t nfr = (uint32_t)total_frames;
     const unsigned gf = (nfr + ENC_THREADS - 1) / ENC_THREADS, gfb = (unsigned)(((uint64_t)nfr * 16 + ENC_THREADS - 1) / ENC_THREADS);
     const unsigned gs = (unsigned)((n + 63) / 64), gsb = (unsigned)((n * 16 + 63) / 64);
-    for (size_t i = 0; i < n; ++i)
-        for (uint32_t k = 0; k < hs[i].n_frames; ++k) frame_stream[hs[i].frame0 + k] = (uint32_t)i;
-    CKE(cudaMemcpyToSymbol(c_enc, &tab, sizeof(tab)), "H2D encoder tables");
-    CKE(cudaMalloc(&d_pcm, total_samples * sizeof(float)), "cudaMalloc(pcm)");
-    for (size_t i = 0; i < n; ++i)
-        CKE(cudaMemcpy(d_pcm + hs[i].pcm_off, pcm[i], n_samples[i] * sizeof(float), cudaMemcpyHostToDevice), "H2D pcm");
-    CKE(cudaMalloc(&d_streams, n * sizeof(EncStream)), "cudaMalloc(streams)");
-    CKE(cudaMemcpy(d_streams, hs.data(), n * sizeof(EncStream), cudaMemcpyHostToDevice), "H2D streams");
-    CKE(cudaMalloc(&d_frame_stream, total_frames * 4), "cudaMalloc(frame map)");
-    CKE(cudaMemcpy(d_frame_stream, frame_stream.data(), total_frames * 4, cudaMemcpyHostToDevice), "H2D frame map");
-    CKE(cudaMalloc(&d_f, total_frames * 256 * sizeof(float)), "cudaMalloc(frames)");
-    CKE(cudaMalloc(&d_power, total_frames * 16 * sizeof(float)), "cudaMalloc(power)");
-    CKE(cudaMalloc(&d_lo, total_frames * 16 * sizeof(float)), "cudaMalloc(lo)");
-    CKE(cudaMalloc(&d_hi, total_frames * 16 * sizeof(float)), "cudaMalloc(hi)");
-    CKE(cudaMalloc(&d_stats, n * 48 * sizeof(float)), "cudaMalloc(stats)");
-    dcsb_enc_transform_kernel<<<gf, ENC_THREADS>>>(d_pcm, d_streams, d_frame_stream, nfr, d_f, d_power, d_lo, d_hi);
-    dcsb_enc_stats_kernel<<<gsb, 64>>>(d_streams, (int)n, d_power, d_lo, d_hi, d_stats);
-    CKE(cudaGetLastError(), "encoder kernel launch");
-    CKE(cudaMemcpy(stats.data(), d_stats, n * 48 * sizeof(float), cudaMemcpyDeviceToHost), "D2H band statistics");
-    if (frames_out) CKE(cudaMemcpy(frames_out, d_f, total_frames * 256 * sizeof(float), cudaMemcpyDeviceToHost), "D2H frames");
-    for (size_t i = 0; i < n; ++i) enc_stream_header(&stats[i * 48], params[i], tab, &hs[i]);
-    CKE(cudaMemcpy(d_streams, hs.data(), n * sizeof(EncStream), cudaMemcpyHostToDevice), "H2D streams");
-    CKE(cudaMalloc(&d_best, total_frames * 16 * ENC_NV * 2), "cudaMalloc(search table)");
-    CKE(cudaMalloc(&d_codes, total_frames * 16), "cudaMalloc(codes)");
-    CKE(cudaMalloc(&d_padj, total_frames * 4), "cudaMalloc(pre-adjustments)");
-    CKE(cudaMalloc(&d_frame_bits, total_frames * 4), "cudaMalloc(frame sizes)");
-    CKE(cudaMalloc(&d_frame_pos, total_frames * 8), "cudaMalloc(frame positions)");
-    CKE(cudaMalloc(&d_stream_bits, n * 8), "cudaMalloc(stream sizes)");
-    CKE(cudaMalloc(&d_word0, (n + 1) * 8), "cudaMalloc(stream offsets)");
-    dcsb_enc_search_kernel<<<gfb, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, d_lo, d_hi, d_best);
-    dcsb_enc_resolve_kernel<<<gs, 64>>>(d_streams, (int)n, d_best, d_codes, d_padj);
-    dcsb_enc_emit_kernel<false><<<gf, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, d_codes, d_padj, d_frame_bits, nullptr, nullptr, nullptr);
-    dcsb_enc_scan_kernel<<<gs, 64>>>(d_streams, (int)n, d_frame_bits, d_frame_pos, d_stream_bits);
-    CKE(cudaGetLastError(), "encoder kernel launch");
-    CKE(cudaMemcpy(sbits.data(), d_stream_bits, n * 8, cudaMemcpyDeviceToHost), "D2H stream sizes");
+#define ENSE(buf, bytes, host, what) do { cudaError_t e_ = (buf).ensure((bytes), (host)); if (e_ != cudaSuccess) { rc = fail(ctx, DCSB_E_NOMEM, what, e_); goto done; } } while (0)
+    ENSE(ec.pcm, total_samples * sizeof(float), false, "cudaMalloc(pcm)");
+    ENSE(ec.streams, n * sizeof(EncStream), false, "cudaMalloc(streams)");
+    ENSE(ec.frame_stream, total_frames * 4, false, "cudaMalloc(frame map)");
+    ENSE(ec.f, total_frames * 256 * sizeof(float), false, "cudaMalloc(frames)");
+    ENSE(ec.power, total_frames * 16 * sizeof(float), false, "cudaMalloc(power)");
+    ENSE(ec.lo, total_frames * 16 * sizeof(float), false, "cudaMalloc(lo)");
+    ENSE(ec.hi, total_frames * 16 * sizeof(float), false, "cudaMalloc(hi)");
+    ENSE(ec.stats, n * 48 * sizeof(float), false, "cudaMalloc(stats)");
+    ENSE(ec.best, total_frames * 16 * ENC_NV * 2, false, "cudaMalloc(search table)");
+    ENSE(ec.codes, total_frames * 16, false, "cudaMalloc(codes)");
+    ENSE(ec.padj, total_frames * 4, false, "cudaMalloc(pre-adjustments)");
+    ENSE(ec.frame_bits, total_frames * 4, false, "cudaMalloc(frame sizes)");
+    ENSE(ec.frame_pos, total_frames * 8, false, "cudaMalloc(frame positions)");
+    ENSE(ec.stream_bits, n * 8, false, "cudaMalloc(stream sizes)");
+    ENSE(ec.word0, (n + 1) * 8, false, "cudaMalloc(stream offsets)");
     {
-        uint64_t need = 0;
-        for (size_t i = 0; i < n; ++i) {
-            word0[i + 1] = word0[i] + (sbits[i] + 31) / 32 + 1;
-            need += 18 + (sbits[i] + 7) / 8;
+        float *d_pcm = static_cast<float *>(ec.pcm.p), *d_f = static_cast<float *>(ec.f.p), *d_power = static_cast<float *>(ec.power.p);
+        float *d_lo = static_cast<float *>(ec.lo.p), *d_hi = static_cast<float *>(ec.hi.p), *d_stats = static_cast<float *>(ec.stats.p);
+        EncStream *d_streams = static_cast<EncStream *>(ec.streams.p);
+        uint32_t *d_frame_stream = static_cast<uint32_t *>(ec.frame_stream.p), *d_frame_bits = static_cast<uint32_t *>(ec.frame_bits.p);
+        uint8_t *d_best = static_cast<uint8_t *>(ec.best.p), *d_codes = static_cast<uint8_t *>(ec.codes.p), *d_padj = static_cast<uint8_t *>(ec.padj.p);
+        uint64_t *d_frame_pos = static_cast<uint64_t *>(ec.frame_pos.p), *d_stream_bits = static_cast<uint64_t *>(ec.stream_bits.p);
+        uint64_t *d_word0 = static_cast<uint64_t *>(ec.word0.p);
+        for (size_t i = 0; i < n; ++i)
+            for (uint32_t k = 0; k < hs[i].n_frames; ++k) frame_stream[hs[i].frame0 + k] = (uint32_t)i;
+        if (!ec.tables_up) { CKE(cudaMemcpyToSymbol(c_enc, &tab, sizeof(tab)), "H2D encoder tables"); ec.tables_up = true; }
+        // PCM through two pinned staging halves: the host copies clip data into one while the other is on the link
+        {
+            const size_t half = (size_t)8 << 20;                // samples per half (32 MB)
+            ENSE(ec.h_pcm, 2 * half * sizeof(float), true, "cudaMallocHost(pcm staging)");
+            float *hp = static_cast<float *>(ec.h_pcm.p);
+            cudaEvent_t evh[2];
+            CKE(cudaEventCreateWithFlags(&evh[0], cudaEventDisableTiming), "cudaEventCreate");
+            CKE(cudaEventCreateWithFlags(&evh[1], cudaEventDisableTiming), "cudaEventCreate");
+            uint64_t done_samples = 0;
+            size_t ci = 0, co = 0;                               // clip, offset inside it
+            int hb = 0;
+            bool used[2] = { false, false };
+            cudaError_t ee = cudaSuccess;
+            while (done_samples < total_samples && ee == cudaSuccess) {
+                if (used[hb]) ee = cudaEventSynchronize(evh[hb]);
+                size_t fill = 0;
+                while (fill < half && ci < n) {
+                    const size_t take = std::min<size_t>(half - fill, (size_t)(n_samples[ci] - co));
+                    memcpy(hp + hb * half + fill, pcm[ci] + co, take * sizeof(float));
+                    fill += take;
+                    co += take;
+                    if (co == n_samples[ci]) { ++ci; co = 0; }
+                }
+                if (ee == cudaSuccess) ee = cudaMemcpyAsync(d_pcm + done_samples, hp + hb * half, fill * sizeof(float), cudaMemcpyHostToDevice, 0);
+                if (ee == cudaSuccess) ee = cudaEventRecord(evh[hb], 0);
+                used[hb] = true;
+                done_samples += fill;
+                hb ^= 1;
+            }
+            if (ee == cudaSuccess) ee = cudaStreamSynchronize(0);
+            cudaEventDestroy(evh[0]);
+            cudaEventDestroy(evh[1]);
+            CKE(ee, "H2D pcm");
         }
-        if (need > out_capacity) { rc = fail(ctx, DCSB_E_NOMEM, "dcsb_encode_streams: output buffer too small (see dcsb_encode_bound)"); goto done; }
-    }
-    CKE(cudaMalloc(&d_words, word0[n] * 4), "cudaMalloc(stream data)");
-    CKE(cudaMemset(d_words, 0, word0[n] * 4), "memset stream data");
-    CKE(cudaMemcpy(d_word0, word0.data(), (n + 1) * 8, cudaMemcpyHostToDevice), "H2D stream offsets");
-    dcsb_enc_emit_kernel<true><<<gf, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, d_codes, d_padj, nullptr, d_frame_pos, d_words, d_word0);
-    CKE(cudaGetLastError(), "encoder kernel launch");
-    words.resize(word0[n]);
-    CKE(cudaMemcpy(words.data(), d_words, word0[n] * 4, cudaMemcpyDeviceToHost), "D2H stream data");
-    {
-        uint64_t o = 0;
-        for (size_t i = 0; i < n; ++i) {                  // BitWriter::Store (:2665-2703): frame count, header, data
-            out_offsets[i] = o;
-            out[o++] = (uint8_t)(hs[i].n_frames >> 8);
-            out[o++] = (uint8_t)(hs[i].n_frames & 0xFF);
-            memcpy(out + o, hs[i].hdr, 16);
-            o += 16;
-            const uint64_t nb = (sbits[i] + 7) / 8;
-            memcpy(out + o, reinterpret_cast<const uint8_t *>(words.data() + word0[i]), nb);
-            o += nb;
+        lap("pcm uploaded");
+        CKE(cudaMemcpy(d_streams, hs.data(), n * sizeof(EncStream), cudaMemcpyHostToDevice), "H2D streams");
+        CKE(cudaMemcpy(d_frame_stream, frame_stream.data(), total_frames * 4, cudaMemcpyHostToDevice), "H2D frame map");
+        dcsb_enc_transform_kernel<<<gf, ENC_THREADS>>>(d_pcm, d_streams, d_frame_stream, nfr, d_f, d_power, d_lo, d_hi);
+        dcsb_enc_stats_kernel<<<gsb, 64>>>(d_streams, (int)n, d_power, d_lo, d_hi, d_stats);
+        CKE(cudaGetLastError(), "encoder kernel launch");
+        CKE(cudaMemcpy(stats.data(), d_stats, n * 48 * sizeof(float), cudaMemcpyDeviceToHost), "D2H band statistics");
+        lap("transform + statistics");
+        if (frames_out) CKE(cudaMemcpy(frames_out, d_f, total_frames * 256 * sizeof(float), cudaMemcpyDeviceToHost), "D2H frames");
+        for (size_t i = 0; i < n; ++i) enc_stream_header(&stats[i * 48], params[i], tab, &hs[i]);
+        CKE(cudaMemcpy(d_streams, hs.data(), n * sizeof(EncStream), cudaMemcpyHostToDevice), "H2D streams");
+        dcsb_enc_search_kernel<<<gfb, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, d_lo, d_hi, d_best);
+        dcsb_enc_resolve_kernel<<<gs, 64>>>(d_streams, (int)n, d_best, d_codes, d_padj);
+        dcsb_enc_emit_kernel<false><<<gf, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, d_codes, d_padj, d_frame_bits, nullptr, nullptr, nullptr);
+        dcsb_enc_scan_kernel<<<gs, 64>>>(d_streams, (int)n, d_frame_bits, d_frame_pos, d_stream_bits);
+        CKE(cudaGetLastError(), "encoder kernel launch");
+        CKE(cudaMemcpy(sbits.data(), d_stream_bits, n * 8, cudaMemcpyDeviceToHost), "D2H stream sizes");
+        lap("search + resolve + sizes");
+        {
+            uint64_t need = 0;
+            for (size_t i = 0; i < n; ++i) {
+                word0[i + 1] = word0[i] + (sbits[i] + 31) / 32 + 1;
+                need += 18 + (sbits[i] + 7) / 8;
+            }
+            if (need > out_capacity) { rc = fail(ctx, DCSB_E_NOMEM, "dcsb_encode_streams: output buffer too small (see dcsb_encode_bound)"); goto done; }
         }
-        out_offsets[n] = o;
+        ENSE(ec.words, word0[n] * 4, false, "cudaMalloc(stream data)");
+        ENSE(ec.h_words, word0[n] * 4, true, "cudaMallocHost(stream data)");
+        uint32_t *d_words = static_cast<uint32_t *>(ec.words.p);
+        CKE(cudaMemset(d_words, 0, word0[n] * 4), "memset stream data");
+        CKE(cudaMemcpy(d_word0, word0.data(), (n + 1) * 8, cudaMemcpyHostToDevice), "H2D stream offsets");
+        dcsb_enc_emit_kernel<true><<<gf, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, d_codes, d_padj, nullptr, d_frame_pos, d_words, d_word0);
+        CKE(cudaGetLastError(), "encoder kernel launch");
+        lap("packed");
+        CKE(cudaMemcpy(ec.h_words.p, d_words, word0[n] * 4, cudaMemcpyDeviceToHost), "D2H stream data");
+        {
+            const uint32_t *words = static_cast<const uint32_t *>(ec.h_words.p);
+            uint64_t o = 0;
+            for (size_t i = 0; i < n; ++i) {                  // BitWriter::Store (:2665-2703): frame count, header, data
+                out_offsets[i] = o;
+                out[o++] = (uint8_t)(hs[i].n_frames >> 8);
+                out[o++] = (uint8_t)(hs[i].n_frames & 0xFF);
+                memcpy(out + o, hs[i].hdr, 16);
+                o += 16;
+                const uint64_t nb = (sbits[i] + 7) / 8;
+                memcpy(out + o, reinterpret_cast<const uint8_t *>(words + word0[i]), nb);
+                o += nb;
+            }
+            out_offsets[n] = o;
+        }
+        lap("streams stored");
     }
 done:
-    cudaFree(d_pcm); cudaFree(d_f); cudaFree(d_power); cudaFree(d_lo); cudaFree(d_hi); cudaFree(d_stats); cudaFree(d_streams);
-    cudaFree(d_frame_stream); cudaFree(d_frame_bits); cudaFree(d_words); cudaFree(d_best); cudaFree(d_codes); cudaFree(d_padj);
-    cudaFree(d_frame_pos); cudaFree(d_stream_bits); cudaFree(d_word0);
+#undef ENSE
     return rc;
 }
