@@ -537,9 +537,10 @@ extern "C" uint64_t dcsb_encode_bound(uint64_t n_samples)
     return 18 + frames * ((16 * 23 + 255 * 15 + 7) / 8 + 1) + 8;
 }
 
-extern "C" int dcsb_encode_streams(dcsb_ctx *ctx, const float *const *pcm, const uint64_t *n_samples, size_t n,
-                                   const dcsb_encode_params *params, uint8_t *out, uint64_t out_capacity, uint64_t *out_offsets,
-                                   float *frames_out)
+// the call for explicit stream types; consecutive entries with the same pcm pointer and length share one upload
+static int encode_impl(dcsb_ctx *ctx, const float *const *pcm, const uint64_t *n_samples, size_t n,
+                       const dcsb_encode_params *params, uint8_t *out, uint64_t out_capacity, uint64_t *out_offsets,
+                       float *frames_out)
 {
     if (!ctx || (n && (!pcm || !n_samples || !params || !out || !out_offsets))) return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: bad argument");
     if (n == 0) return DCSB_OK;
@@ -554,7 +555,8 @@ extern "C" int dcsb_encode_streams(dcsb_ctx *ctx, const float *const *pcm, const
         if (nf > 65535) return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: a stream holds at most 65535 frames");
         EncStream &s = hs[i];
         memset(&s, 0, sizeof(s));
-        s.pcm_off = total_samples;
+        const bool shared = i > 0 && pcm[i] == pcm[i - 1] && n_samples[i] == n_samples[i - 1];
+        s.pcm_off = shared ? hs[i - 1].pcm_off : total_samples;
         s.n_samples = n_samples[i];
         s.frame0 = (uint32_t)total_frames;
         s.n_frames = (uint32_t)nf;
@@ -562,7 +564,7 @@ extern "C" int dcsb_encode_streams(dcsb_ctx *ctx, const float *const *pcm, const
         s.subtype = p.stream_subtype;
         s.max_err2 = p.max_quantization_error * p.max_quantization_error;
         s.min_range = p.min_dynamic_range;
-        total_samples += n_samples[i];
+        if (!shared) total_samples += n_samples[i];
         total_frames += nf;
     }
     if (total_frames >= 0x0FFFFFFFull) return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: more than 2^28 frames in one call");
@@ -631,6 +633,7 @@ extern "C" int dcsb_encode_streams(dcsb_ctx *ctx, const float *const *pcm, const
                 if (used[hb]) ee = cudaEventSynchronize(evh[hb]);
                 size_t fill = 0;
                 while (fill < half && ci < n) {
+                    if (co == 0 && ci > 0 && hs[ci].pcm_off == hs[ci - 1].pcm_off) { ++ci; continue; }      // shares the previous clip's samples
                     const size_t take = std::min<size_t>(half - fill, (size_t)(n_samples[ci] - co));
                     memcpy(hp + hb * half + fill, pcm[ci] + co, take * sizeof(float));
                     fill += take;
@@ -703,4 +706,61 @@ extern "C" int dcsb_encode_streams(dcsb_ctx *ctx, const float *const *pcm, const
 done:
 #undef ENSE
     return rc;
+}
+
+// Public entry: explicit stream types go straight through; -1 in stream_type / stream_subtype is the reference's
+// wildcard (CloseStream :779-836): the clip is encoded with every matching format of {0.0, 0.3, 1.0, 1.3} in that
+// order -- one upload of its samples -- and the first of the smallest streams is kept.
+extern "C" int dcsb_encode_streams(dcsb_ctx *ctx, const float *const *pcm, const uint64_t *n_samples, size_t n,
+                                   const dcsb_encode_params *params, uint8_t *out, uint64_t out_capacity, uint64_t *out_offsets,
+                                   float *frames_out)
+{
+    if (!ctx || (n && (!pcm || !n_samples || !params || !out || !out_offsets))) return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: bad argument");
+    bool wild = false;
+    for (size_t i = 0; i < n; ++i) {
+        const dcsb_encode_params &p = params[i];
+        if (p.stream_type < -1 || p.stream_type > 1 || (p.stream_subtype != -1 && p.stream_subtype != 0 && p.stream_subtype != 3))
+            return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: stream type must be -1, 0 or 1, subtype -1, 0 or 3");
+        wild = wild || p.stream_type < 0 || p.stream_subtype < 0;
+    }
+    if (!wild) return encode_impl(ctx, pcm, n_samples, n, params, out, out_capacity, out_offsets, frames_out);
+    if (frames_out) return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: frames_out needs explicit stream types");
+    static const int formats[4][2] = { { 0, 0 }, { 0, 3 }, { 1, 0 }, { 1, 3 } };
+    std::vector<const float *> jp;
+    std::vector<uint64_t> jn;
+    std::vector<dcsb_encode_params> jpar;
+    std::vector<size_t> first(n + 1, 0);
+    uint64_t cap = 0;
+    for (size_t i = 0; i < n; ++i) {
+        first[i] = jp.size();
+        for (const auto &f : formats) {
+            const dcsb_encode_params &p = params[i];
+            if ((p.stream_type >= 0 && p.stream_type != f[0]) || (p.stream_subtype >= 0 && p.stream_subtype != f[1])) continue;
+            dcsb_encode_params q = p;
+            q.stream_type = f[0];
+            q.stream_subtype = f[1];
+            jp.push_back(pcm[i]);
+            jn.push_back(n_samples[i]);
+            jpar.push_back(q);
+            cap += dcsb_encode_bound(n_samples[i]);
+        }
+    }
+    first[n] = jp.size();
+    std::vector<uint8_t> tmp(cap + 64);
+    std::vector<uint64_t> joffs(jp.size() + 1, 0);
+    const int rc = encode_impl(ctx, jp.data(), jn.data(), jp.size(), jpar.data(), tmp.data(), tmp.size(), joffs.data(), nullptr);
+    if (rc != DCSB_OK) return rc;
+    uint64_t o = 0;
+    for (size_t i = 0; i < n; ++i) {
+        size_t best = first[i];
+        for (size_t j = first[i] + 1; j < first[i + 1]; ++j)
+            if (joffs[j + 1] - joffs[j] < joffs[best + 1] - joffs[best]) best = j;
+        const uint64_t nb = joffs[best + 1] - joffs[best];
+        if (o + nb > out_capacity) return fail(ctx, DCSB_E_NOMEM, "dcsb_encode_streams: output buffer too small (see dcsb_encode_bound)");
+        out_offsets[i] = o;
+        memcpy(out + o, tmp.data() + joffs[best], nb);
+        o += nb;
+    }
+    out_offsets[n] = o;
+    return DCSB_OK;
 }

@@ -288,11 +288,12 @@ long long dcsb_read_dcs_file(const char *path, uint16_t *os_version, uint8_t *ou
  * band-type search, header and sample codes, bit packing -- runs on the GPU with the reference's float operations
  * in the reference's order, so the stream BYTES are the ones the reference's CloseStream() produces from the same
  * frames (DCSEncoder.cpp:717-858; checked by tests/test_gpu_encode.py against oracle/_ref).
- * The fields mirror DCSEncoder::CompressionParams (DCSEncoder.h:70-180); the stream type / subtype must be given
- * (0 or 1 / 0 or 3: the reference's wildcard -1 = "encode all four, keep the smallest" is the caller's loop). */
+ * The fields mirror DCSEncoder::CompressionParams (DCSEncoder.h:70-180), including the wildcard: -1 as stream type
+ * and / or subtype encodes the clip with every matching format of {0.0, 0.3, 1.0, 1.3} and keeps the first of the
+ * smallest streams, as CloseStream() does (DCSEncoder.cpp:779-836). */
 typedef struct dcsb_encode_params {
-    int32_t stream_type;            /* 0 | 1 */
-    int32_t stream_subtype;         /* 0 | 3 */
+    int32_t stream_type;            /* 0 | 1 | -1 (any) */
+    int32_t stream_subtype;         /* 0 | 3 | -1 (any) */
     int32_t target_bit_rate;        /* bits per second, default 128000 */
     float power_band_cutoff;        /* default 0.97 */
     float max_quantization_error;   /* default 10 / 32768 */
@@ -304,7 +305,7 @@ uint64_t dcsb_encode_bound(uint64_t n_samples);
  * written back to back into out (capacity out_capacity bytes); stream i occupies [out_offsets[i], out_offsets[i + 1])
  * (out_offsets has n + 1 entries) and starts with the U16BE frame count and the 16 header bytes, ready for
  * dcsb_decode_streams / the reference decoder.  frames_out (may be NULL): the transformed frames, 256 floats each
- * (DCSEncoder.h:322), all clips back to back -- for tests.
+ * (DCSEncoder.h:322), all clips back to back -- for tests; explicit stream types only.
  * DCSB_OK, DCSB_E_ARG (empty clip, more than 65,535 frames, bad type), DCSB_E_NOMEM (out too small), DCSB_E_CUDA. */
 int dcsb_encode_streams(dcsb_ctx *ctx, const float *const *pcm, const uint64_t *n_samples, size_t n,
                         const dcsb_encode_params *params, uint8_t *out, uint64_t out_capacity, uint64_t *out_offsets,

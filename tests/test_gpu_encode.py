@@ -102,6 +102,18 @@ def test_gpu_encode_random_clips_and_parameters_equal_the_reference(ctx):
     assert not bad, "%d of %d streams differ from the reference encoder's: %s" % (len(bad), len(clips), bad[:5])
 
 
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref did not travel with the snapshot")
+def test_gpu_encode_wildcard_stream_type_picks_like_the_reference(ctx):
+    """-1 as stream type / subtype: every matching format is tried and the first of the smallest streams kept
+    (CloseStream, DCSEncoder.cpp:779-836)"""
+    clips = _clips()[:8]
+    jobs = [(c, p) for c in clips for p in ((-1, -1, 128000, 0.97), (-1, 3, 64000, 0.9), (1, -1, 96000, 1.0), (-1, 0, 256000, 0.97))]
+    streams = ctx.encode_streams([j[0] for j in jobs], [j[1] for j in jobs])
+    for (clip, p), got in zip(jobs, streams):
+        want, nf = ref.encode_framed(clip, p[0], p[1], p[2], p[3])
+        assert got == want, p
+
+
 def test_gpu_encode_rejects_bad_arguments(ctx):
     import dcsexplorer_b200 as dx
     clip = np.zeros(480, dtype=np.float32)
@@ -109,6 +121,8 @@ def test_gpu_encode_rejects_bad_arguments(ctx):
         ctx.encode_streams([clip], [(2, 0, 128000, 0.97)])
     with pytest.raises(dx.DcsbError):
         ctx.encode_streams([clip], [(0, 1, 128000, 0.97)])
+    with pytest.raises(dx.DcsbError):
+        ctx.encode_streams([clip], [(-2, 0, 128000, 0.97)])
     with pytest.raises(dx.DcsbError):
         ctx.encode_streams([np.zeros(0, dtype=np.float32)], [(0, 0, 128000, 0.97)])
     with pytest.raises(dx.DcsbError):
