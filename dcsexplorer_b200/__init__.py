@@ -150,16 +150,17 @@ class Context:
 
     def encode_streams(self, clips, params, want_frames=False):
         """dcsb_encode_streams: clips = list of float32 arrays (mono, 31,250 Hz), params = list of
-        (stream_type, stream_subtype, bit_rate, power_cut[, max_quantization_error, min_dynamic_range]).
+        (stream_type, stream_subtype, bit_rate, power_cut[, max_quantization_error, min_dynamic_range[, format_version]]).
         Returns the list of stream bytes (and the transformed frames, float32 [n_frames, 256] per clip)."""
         import numpy as np
         n = len(clips)
         keep = [np.ascontiguousarray(c, dtype=np.float32) for c in clips]
         ptrs = (C.c_void_p * max(1, n))(*[k.ctypes.data for k in keep])
         ns = (C.c_uint64 * max(1, n))(*[k.size for k in keep])
-        pa = np.zeros(max(1, n), dtype=np.dtype([("t", "<i4"), ("s", "<i4"), ("r", "<i4"), ("c", "<f4"), ("q", "<f4"), ("d", "<f4")]))
+        pa = np.zeros(max(1, n), dtype=np.dtype([("t", "<i4"), ("s", "<i4"), ("r", "<i4"), ("c", "<f4"), ("q", "<f4"), ("d", "<f4"), ("v", "<i4")]))
         for i, p in enumerate(params):
-            pa[i] = (p[0], p[1], p[2], p[3], p[4] if len(p) > 4 else 10.0 / 32768.0, p[5] if len(p) > 5 else 10.0 / 32768.0)
+            pa[i] = (p[0], p[1], p[2], p[3], p[4] if len(p) > 4 else 10.0 / 32768.0, p[5] if len(p) > 5 else 10.0 / 32768.0,
+                     p[6] if len(p) > 6 else 0)
         cap = sum(int(self._L.dcsb_encode_bound(int(k.size))) for k in keep) + 64
         out = np.zeros(cap, dtype=np.uint8)
         offs = (C.c_uint64 * (n + 1))()

@@ -39,6 +39,7 @@ struct EncStream {                  // per stream, device copy
     float min_range;
     uint8_t hdr[16];                // stream header as stored (scale codes, 0xFF behind the kept bands, flag bits)
     int32_t bands;                  // bands kept
+    int32_t fmt93;                  // 1: 1993 layout (16 bands of 16 samples, CompressFrame93b), stream type 0
 };
 
 struct EncTables {
@@ -58,6 +59,7 @@ __constant__ EncTables c_enc;
 
 __device__ __forceinline__ int enc_band_count(int b) { return b == 0 ? 7 : (b == 1 ? 8 : (b == 15 ? 32 : 16)); }
 __device__ __forceinline__ int enc_band_first(int b) { return b == 0 ? 0 : (b == 1 ? 7 : 15 + 16 * (b - 2)); }
+__device__ __forceinline__ int enc_band_count_f(int fmt93, int b) { return fmt93 ? 16 : enc_band_count(b); }
 __device__ __forceinline__ float enc_half_sum(float a, float b) { return __fmul_rn(__fadd_rn(a, b), 0.5f); }
 __device__ __forceinline__ float enc_half_diff(float a, float b) { return __fmul_rn(__fsub_rn(a, b), 0.5f); }
 
@@ -163,7 +165,7 @@ dcsb_enc_transform_kernel(const float *__restrict__ pcm, const EncStream *__rest
     for (int b = 0; b < 16; ++b) {
         float l = buf[p], h = l, pw = __fmul_rn(l, l);
         ++p;
-        for (int j = enc_band_count(b); j > 1; --j) {
+        for (int j = enc_band_count_f(s.fmt93, b); j > 1; --j) {
             const float v = buf[p++];
             pw = __fadd_rn(pw, __fmul_rn(v, v));
             if (v < l) l = v;
@@ -222,7 +224,7 @@ dcsb_enc_search_kernel(const EncStream *__restrict__ streams, const uint32_t *__
     const EncStream s = streams[frame_stream[fr]];
     uint8_t *bo = best + (size_t)t * (ENC_NV * 2);
     for (int i = 0; i < ENC_NV * 2; ++i) bo[i] = 0;
-    if (band >= s.bands) return;
+    if (band >= s.bands || s.fmt93) return;
     if (__fsub_rn(hi[(size_t)fr * 16 + band], lo[(size_t)fr * 16 + band]) < s.min_range) return;
     const int n = enc_band_count(band);
     const float *x = f + (size_t)fr * 256 + enc_band_first(band);
@@ -279,6 +281,7 @@ __global__ void dcsb_enc_resolve_kernel(const EncStream *__restrict__ streams, i
     const int si = blockIdx.x * blockDim.x + threadIdx.x;
     if (si >= n) return;
     const EncStream s = streams[si];
+    if (s.fmt93) return;
     int old[16];
     for (int b = 0; b < 16; ++b) old[b] = 0;
     for (uint32_t k = 0; k < s.n_frames; ++k) {
@@ -336,6 +339,7 @@ dcsb_enc_emit_kernel(const EncStream *__restrict__ streams, const uint32_t *__re
     if (fr >= n_frames_total) return;
     const uint32_t si = frame_stream[fr];
     const EncStream s = streams[si];
+    if (s.fmt93) return;
     EncBitSink sink;
     sink.count = 0;
     sink.acc = 0;
@@ -378,6 +382,120 @@ dcsb_enc_emit_kernel(const EncStream *__restrict__ streams, const uint32_t *__re
                 else sink.put<WRITE>((uint32_t)v, width);
             }
         }
+    }
+    if (WRITE) sink.flush();
+    else frame_bits[fr] = (uint32_t)sink.count;
+}
+
+// One frame of the 1993 layout, stream type 0 (CompressFrame93b, :2053-2473): the bands of a frame hang together --
+// every band may be stored as values, first or second differences against the samples before it, and says so relative
+// to the band before -- but frames do not (type 0 carries nothing from frame to frame), so a thread takes a frame.
+template <bool WRITE>
+__global__ void __launch_bounds__(ENC_THREADS)
+dcsb_enc_frame93_kernel(const EncStream *__restrict__ streams, const uint32_t *__restrict__ frame_stream, uint32_t n_frames_total,
+                        const float *__restrict__ f, uint32_t *__restrict__ frame_bits, const uint64_t *__restrict__ frame_pos,
+                        uint32_t *__restrict__ out_words, const uint64_t *__restrict__ stream_word0)
+{
+    const uint32_t fr = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fr >= n_frames_total) return;
+    const uint32_t si = frame_stream[fr];
+    const EncStream s = streams[si];
+    if (!s.fmt93) return;
+    EncBitSink sink;
+    sink.count = 0;
+    sink.acc = 0;
+    sink.nacc = 0;
+    sink.widx = 0;
+    sink.words = nullptr;
+    if (WRITE) {
+        const uint64_t p = frame_pos[fr];
+        sink.words = out_words + stream_word0[si];
+        sink.widx = p >> 5;
+        sink.nacc = (int)(p & 31);
+    }
+    int last_code = -1, last_sub = 2, prv = 0, prvd = 0;
+    for (int band = 0; band < s.bands; ++band) {
+        const float *x = f + (size_t)fr * 256 + 16 * band;
+        const float scale = enc_scale(s.hdr[band] & 0x3F);
+        const int band_prv = prv, band_prvd = prvd;
+        int b0[16], b1[16], b2[16];
+        for (int i = 0; i < 16; ++i) {
+            const int cur = enc_quant(x[i], scale);
+            b0[i] = cur;
+            b1[i] = cur - prv;
+            b2[i] = cur - prv - prvd;
+            prvd = b1[i];
+            prv = cur;
+        }
+        // values as they are: the narrowest width within the error limit (FindBestBandEncoding, codes 1..15, width code + 1)
+        int c0 = 0;
+        {
+            const float err_max = __fmul_rn(s.max_err2, 16.0f);
+            float err[16];
+            bool pass[16];
+            for (int code = 1; code <= 15; ++code) {
+                const int width = code + 1, ref = 1 << (width - 1), mask = 0xFFFF >> (16 - width);
+                float sum = 0.0f;
+                for (int i = 0; i < 16; ++i) {
+                    const float o = x[i];
+                    const int stored = (enc_quant(o, scale) + ref) & mask;
+                    const float rec = __fdiv_rn(__fmul_rn((float)(stored - ref), scale), 32768.0f);
+                    const float e = __fsub_rn(rec, o);
+                    sum = __fadd_rn(sum, __fmul_rn(e, e));
+                }
+                err[code] = sum;
+                pass[code] = sum <= err_max;
+            }
+            int narrow = -1;
+            for (int c = 1; c <= 15; ++c)
+                if (pass[c] && (narrow == -1 || c + 1 < narrow)) narrow = c + 1;
+            float min_err = -1.0f;
+            for (int c = 1; c <= 15; ++c)
+                if (narrow == -1 || c + 1 == narrow)
+                    if (min_err < 0 || err[c] < min_err) { c0 = c; min_err = err[c]; }
+        }
+        // differences: the width their extremes need (:2224-2256)
+        int cd[2];
+        for (int k = 0; k < 2; ++k) {
+            const int *b = k ? b2 : b1;
+            int lo = b[0], hi = b[0];
+            for (int i = 1; i < 16; ++i) { lo = b[i] < lo ? b[i] : lo; hi = b[i] > hi ? b[i] : hi; }
+            if (hi < 0) hi = -hi;
+            if (lo < 0) lo = -lo;
+            if (lo > hi) hi = lo;
+            int code = 0;
+            if (hi != 0) {
+                int nb = 1;
+                for (; hi != 0; hi >>= 1) ++nb;
+                code = nb - 1;
+            }
+            cd[k] = code;
+        }
+        int code = c0, sub = 0;
+        if (cd[0] < code || (cd[0] == code && last_sub == 1)) { sub = 1; code = cd[0]; }
+        if (cd[1] < code) { sub = 2; code = cd[1]; }
+        if (last_code == 0 && code == 0 && last_sub == sub) {
+            sink.put<WRITE>(1u, 1);                             // "the same again" (:2283-2288)
+        } else {
+            if (last_code == 0) sink.put<WRITE>(0u, 1);
+            if (sub == last_sub) sink.put<WRITE>(0u, 1);
+            else {
+                sink.put<WRITE>(1u, 1);
+                sink.put<WRITE>((uint32_t)(((sub - last_sub + 3) % 3) == 1 ? 1 : 0), 1);     // up / down modulo 3 (:2307-2311)
+            }
+            sink.put<WRITE>((uint32_t)code, 4);
+            if (code == 0) {
+                if (sub == 0) { prv = 0; prvd = 0; }
+                else if (sub == 1) { prv = band_prv; prvd = 0; }
+                else { prv = band_prv; prvd = band_prvd; }
+            } else {
+                const int nb = code + 1, mask = (1 << nb) - 1;
+                const int *b = sub == 0 ? b0 : (sub == 1 ? b1 : b2);
+                for (int i = 0; i < 16; ++i) sink.put<WRITE>((uint32_t)(b[i] & mask), nb);
+            }
+        }
+        last_code = code;
+        last_sub = sub;
     }
     if (WRITE) sink.flush();
     else frame_bits[fr] = (uint32_t)sink.count;
@@ -459,9 +577,13 @@ static void enc_build_tables(EncTables *t)
 // CloseStream's power cut (:738-770) and CompressStream's header (:866-974) for one stream
 static void enc_stream_header(const float *stats /* 48 */, const dcsb_encode_params &pr, const EncTables &tab, EncStream *s)
 {
-    static const float norm[16] = { 16.0f / 7, 16.0f / 8, 16.0f / 16, 16.0f / 16, 16.0f / 16, 16.0f / 16, 16.0f / 16, 16.0f / 16,
+    const bool f93 = s->fmt93 != 0;
+    static const float norm94[16] = { 16.0f / 7, 16.0f / 8, 16.0f / 16, 16.0f / 16, 16.0f / 16, 16.0f / 16, 16.0f / 16, 16.0f / 16,
                                     16.0f / 16, 16.0f / 16, 16.0f / 16, 16.0f / 16, 16.0f / 16, 16.0f / 16, 16.0f / 16, 16.0f / 32 };
-    static const int counts[16] = { 7, 8, 16, 16, 16, 16, 16, 16, 16, 16, 16, 16, 16, 16, 16, 32 };
+    static const int counts94[16] = { 7, 8, 16, 16, 16, 16, 16, 16, 16, 16, 16, 16, 16, 16, 16, 32 };
+    float norm[16];
+    int counts[16];
+    for (int i = 0; i < 16; ++i) { norm[i] = f93 ? 1.0f : norm94[i]; counts[i] = f93 ? 16 : counts94[i]; }
     float rms[16], total = 0.0f;
     for (int i = 0; i < 16; ++i) {
         rms[i] = sqrtf(stats[i] * norm[i]);
@@ -495,7 +617,7 @@ static void enc_stream_header(const float *stats /* 48 */, const dcsb_encode_par
             if (tab.scale[j] < target) h[band] = (uint8_t)j;
             else break;
         }
-        if (pr.stream_type == 1) {
+        if (!f93 && pr.stream_type == 1) {
             int adjust = (band < 3) ? 0x0d : 0x17;
             adjust += pr.stream_subtype == 0 ? 1 : 3;
             if (h[band] > adjust) h[band] = (uint8_t)(h[band] - adjust);
@@ -545,12 +667,18 @@ static int encode_impl(dcsb_ctx *ctx, const float *const *pcm, const uint64_t *n
     if (!ctx || (n && (!pcm || !n_samples || !params || !out || !out_offsets))) return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: bad argument");
     if (n == 0) return DCSB_OK;
     uint64_t total_samples = 0, total_frames = 0;
+    bool any93 = false;
     std::vector<EncStream> hs(n);
     for (size_t i = 0; i < n; ++i) {
         const dcsb_encode_params &p = params[i];
         if (!pcm[i] || n_samples[i] == 0) return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: empty clip");
         if ((p.stream_type != 0 && p.stream_type != 1) || (p.stream_subtype != 0 && p.stream_subtype != 3) || p.target_bit_rate <= 0)
             return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: stream type must be 0 or 1, subtype 0 or 3, bit rate positive");
+        const bool f93 = p.format_version == DCSB_OS93A || p.format_version == DCSB_OS93B;
+        if (p.format_version != 0 && p.format_version != DCSB_OS94 && !f93)
+            return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: format version must be 0 / $9400, $9301 or $9302");
+        if (f93 && (p.stream_type != 0 || p.stream_subtype != 0))
+            return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: the 1993 layouts are encoded as stream type 0 only");
         const uint64_t nf = (n_samples[i] + 239) / 240;
         if (nf > 65535) return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: a stream holds at most 65535 frames");
         EncStream &s = hs[i];
@@ -564,6 +692,8 @@ static int encode_impl(dcsb_ctx *ctx, const float *const *pcm, const uint64_t *n
         s.subtype = p.stream_subtype;
         s.max_err2 = p.max_quantization_error * p.max_quantization_error;
         s.min_range = p.min_dynamic_range;
+        s.fmt93 = f93 ? 1 : 0;
+        any93 = any93 || f93;
         if (!shared) total_samples += n_samples[i];
         total_frames += nf;
     }
@@ -665,6 +795,7 @@ static int encode_impl(dcsb_ctx *ctx, const float *const *pcm, const uint64_t *n
         dcsb_enc_search_kernel<<<gfb, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, d_lo, d_hi, d_best);
         dcsb_enc_resolve_kernel<<<gs, 64>>>(d_streams, (int)n, d_best, d_codes, d_padj);
         dcsb_enc_emit_kernel<false><<<gf, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, d_codes, d_padj, d_frame_bits, nullptr, nullptr, nullptr);
+        if (any93) dcsb_enc_frame93_kernel<false><<<gf, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, d_frame_bits, nullptr, nullptr, nullptr);
         dcsb_enc_scan_kernel<<<gs, 64>>>(d_streams, (int)n, d_frame_bits, d_frame_pos, d_stream_bits);
         CKE(cudaGetLastError(), "encoder kernel launch");
         CKE(cudaMemcpy(sbits.data(), d_stream_bits, n * 8, cudaMemcpyDeviceToHost), "D2H stream sizes");
@@ -683,6 +814,7 @@ static int encode_impl(dcsb_ctx *ctx, const float *const *pcm, const uint64_t *n
         CKE(cudaMemset(d_words, 0, word0[n] * 4), "memset stream data");
         CKE(cudaMemcpy(d_word0, word0.data(), (n + 1) * 8, cudaMemcpyHostToDevice), "H2D stream offsets");
         dcsb_enc_emit_kernel<true><<<gf, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, d_codes, d_padj, nullptr, d_frame_pos, d_words, d_word0);
+        if (any93) dcsb_enc_frame93_kernel<true><<<gf, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, nullptr, d_frame_pos, d_words, d_word0);
         CKE(cudaGetLastError(), "encoder kernel launch");
         lap("packed");
         CKE(cudaMemcpy(ec.h_words.p, d_words, word0[n] * 4, cudaMemcpyDeviceToHost), "D2H stream data");
@@ -721,6 +853,8 @@ extern "C" int dcsb_encode_streams(dcsb_ctx *ctx, const float *const *pcm, const
         const dcsb_encode_params &p = params[i];
         if (p.stream_type < -1 || p.stream_type > 1 || (p.stream_subtype != -1 && p.stream_subtype != 0 && p.stream_subtype != 3))
             return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: stream type must be -1, 0 or 1, subtype -1, 0 or 3");
+        const bool f93 = p.format_version == DCSB_OS93A || p.format_version == DCSB_OS93B;
+        if (f93 && p.stream_type != 0) return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: the 1993 layouts are encoded as stream type 0 only (give the type)");
         wild = wild || p.stream_type < 0 || p.stream_subtype < 0;
     }
     if (!wild) return encode_impl(ctx, pcm, n_samples, n, params, out, out_capacity, out_offsets, frames_out);
@@ -735,7 +869,9 @@ extern "C" int dcsb_encode_streams(dcsb_ctx *ctx, const float *const *pcm, const
         first[i] = jp.size();
         for (const auto &f : formats) {
             const dcsb_encode_params &p = params[i];
-            if ((p.stream_type >= 0 && p.stream_type != f[0]) || (p.stream_subtype >= 0 && p.stream_subtype != f[1])) continue;
+            const bool f93 = p.format_version == DCSB_OS93A || p.format_version == DCSB_OS93B;
+            if (f93 && (f[0] != 0 || f[1] != 0)) continue;                 // (no subtypes there, :798-806)
+            if ((p.stream_type >= 0 && p.stream_type != f[0]) || (!f93 && p.stream_subtype >= 0 && p.stream_subtype != f[1])) continue;
             dcsb_encode_params q = p;
             q.stream_type = f[0];
             q.stream_subtype = f[1];

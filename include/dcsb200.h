@@ -281,7 +281,7 @@ int dcsb_write_dcs_file(const char *path, uint16_t os_version, const uint8_t *st
  * (up to max); returns the stream size in bytes, or a negative DCSB_E_* (not a DCSa file / unreadable). */
 long long dcsb_read_dcs_file(const char *path, uint16_t *os_version, uint8_t *out, size_t max);
 
-/* ---- forward path: PCM -> 1994-layout streams, in batch ----------------------------------
+/* ---- forward path: PCM -> DCS streams, in batch ------------------------------------------
  * The reference's DCSEncoder (DCSEncoder/DCSEncoder.cpp) minus its resampler: the clip must already be mono float
  * PCM at 31,250 Hz (full scale = 1.0), and is framed directly (16 samples of overlap + 240 new ones per frame, the
  * last frame zero padded).  Everything behind that -- window, transform, per-band statistics, power cut, scale codes,
@@ -298,6 +298,8 @@ typedef struct dcsb_encode_params {
     float power_band_cutoff;        /* default 0.97 */
     float max_quantization_error;   /* default 10 / 32768 */
     float min_dynamic_range;        /* default 10 / 32768 */
+    int32_t format_version;         /* 0 or DCSB_OS94: the 1994 layout; DCSB_OS93A / DCSB_OS93B: the 1993 layout, stream type 0
+                                     * only (CompressFrame93b, DCSEncoder.cpp:2053-2473; the subtype is ignored there) */
 } dcsb_encode_params;
 /* bytes a stream of n_samples samples can need at most (size `out` with the sum over the clips) */
 uint64_t dcsb_encode_bound(uint64_t n_samples);

@@ -64,7 +64,7 @@ def encode(pcm, sample_rate=31250, fmt=0x9400, stype=1, subtype=3, bit_rate=1280
 
 
 def encode_framed(pcm, stype=1, subtype=3, bit_rate=128000, power_cut=0.97, max_quant_error=-1.0, min_dynamic_range=-1.0,
-                  want_frames=False):
+                  want_frames=False, fmt=0x9400):
     """The reference encoder without its resampler (samples framed directly, then the reference's own TransformFrame /
     CloseStream): the oracle for the GPU encoder.  Returns (stream bytes, n_frames[, frames float32 [n_frames, 256]])."""
     pcm = np.ascontiguousarray(pcm, dtype=np.float32)
@@ -76,9 +76,9 @@ def encode_framed(pcm, stype=1, subtype=3, bit_rate=128000, power_cut=0.97, max_
     L = lib()
     L.dcsref_encode_framed.restype = C.c_size_t
     L.dcsref_encode_framed.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
-                                       C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.c_void_p, C.c_size_t]
+                                       C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.c_void_p, C.c_size_t, C.c_int]
     n = L.dcsref_encode_framed(pcm.ctypes.data, pcm.size, stype, subtype, bit_rate, power_cut, max_quant_error, min_dynamic_range,
-                               out.ctypes.data, cap, C.byref(nf), frames.ctypes.data if want_frames else None, nfr)
+                               out.ctypes.data, cap, C.byref(nf), frames.ctypes.data if want_frames else None, nfr, fmt)
     if n == 0:
         raise RuntimeError("reference encoder refused the stream")
     if want_frames:

@@ -214,10 +214,11 @@ struct EncProbe : DCSEncoder {
     }
 };
 size_t dcsref_encode_framed(const float *pcm, size_t n, int type, int subtype, int bit_rate, float power_cut,
-    float max_quant_error, float min_dynamic_range, uint8_t *out, size_t cap, int *n_frames, float *frames_out, size_t n_frames_cap)
+    float max_quant_error, float min_dynamic_range, uint8_t *out, size_t cap, int *n_frames, float *frames_out, size_t n_frames_cap,
+    int format_version)
 {
     EncProbe enc;
-    enc.compressionParams.formatVersion = 0x9400;
+    enc.compressionParams.formatVersion = static_cast<uint16_t>(format_version ? format_version : 0x9400);
     enc.compressionParams.streamFormatType = type;
     enc.compressionParams.streamFormatSubType = subtype;
     enc.compressionParams.targetBitRate = bit_rate;

@@ -114,6 +114,31 @@ def test_gpu_encode_wildcard_stream_type_picks_like_the_reference(ctx):
         assert got == want, p
 
 
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref did not travel with the snapshot")
+def test_gpu_encode_1993_layout_type0_equals_the_reference(ctx):
+    """format versions $9302 / $9301, stream type 0 (CompressFrame93b): bytes identical to the reference's, and the
+    streams decode through our 1993 path like the oracle decodes them"""
+    from oracle import orc
+    rng = np.random.default_rng(93)
+    clips = _clips() + [(rng.standard_normal(int(rng.integers(300, 20000))) * rng.uniform(0.001, 0.6)).astype(np.float32) for _ in range(40)]
+    jobs = []
+    for i, c in enumerate(clips):
+        fmt = 0x9302 if i % 2 else 0x9301
+        jobs.append((c, (0, 0, int(rng.choice([32000, 96000, 128000, 256000])), float(rng.choice([0.9, 0.97, 1.0])),
+                         float(rng.choice([1.0, 10.0, 100.0])) / 32768.0, 10.0 / 32768.0, fmt)))
+    streams = ctx.encode_streams([j[0] for j in jobs], [j[1] for j in jobs])
+    bad = []
+    for i, ((clip, p), got) in enumerate(zip(jobs, streams)):
+        want, nf = ref.encode_framed(clip, p[0], p[1], p[2], p[3], p[4], p[5], fmt=p[6])
+        if got != want:
+            bad.append((i, hex(p[6]), len(got), len(want)))
+    assert not bad, "%d of %d streams differ from the reference encoder's: %s" % (len(bad), len(jobs), bad[:5])
+    pcm, offs, res = ctx.decode_streams([(s, j[1][6], 255, 0x64, 2) for s, j in zip(streams, jobs)])
+    for i, s_ in enumerate(streams):
+        want, rc = orc.decode(s_, jobs[i][1][6], 255, 0x64, ((s_[0] << 8) | s_[1]) + 2)
+        assert res[i]["status"] == 0 and np.array_equal(pcm[offs[i]:offs[i] + want.size], want), i
+
+
 def test_gpu_encode_rejects_bad_arguments(ctx):
     import dcsexplorer_b200 as dx
     clip = np.zeros(480, dtype=np.float32)
@@ -123,6 +148,10 @@ def test_gpu_encode_rejects_bad_arguments(ctx):
         ctx.encode_streams([clip], [(0, 1, 128000, 0.97)])
     with pytest.raises(dx.DcsbError):
         ctx.encode_streams([clip], [(-2, 0, 128000, 0.97)])
+    with pytest.raises(dx.DcsbError):
+        ctx.encode_streams([clip], [(1, 0, 128000, 0.97, 10 / 32768, 10 / 32768, 0x9302)])      # 1993 layout: type 0 only
+    with pytest.raises(dx.DcsbError):
+        ctx.encode_streams([clip], [(0, 0, 128000, 0.97, 10 / 32768, 10 / 32768, 0x9500)])
     with pytest.raises(dx.DcsbError):
         ctx.encode_streams([np.zeros(0, dtype=np.float32)], [(0, 0, 128000, 0.97)])
     with pytest.raises(dx.DcsbError):

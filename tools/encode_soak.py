@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""GPU soak of the forward path: seeded random clips (noise, tones, sweeps, bursts, near-silence, clipped; 100..60000
+"""GPU soak of the forward path (1994 layout with all four stream types; 1993 layouts as type 0): seeded random clips (noise, tones, sweeps, bursts, near-silence, clipped; 100..60000
 samples) with random parameters through dcsb_encode_streams, every stream's bytes against the reference DCSEncoder fed
 the same framing (oracle/_ref) on the host cores.   usage: tools/encode_soak.py [n_clips=4000] [seed=1]"""
 import multiprocessing as mp
@@ -33,12 +33,15 @@ def make(args):
         x = np.clip(rng.standard_normal(n) * 1.5, -1.0, 1.0)
     p = (int(rng.integers(0, 2)), int(rng.choice([0, 3])), int(rng.choice([8000, 32000, 64000, 96000, 128000, 192000, 256000, 512000])),
          float(rng.choice([0.5, 0.9, 0.97, 1.0])), float(rng.choice([1.0, 10.0, 100.0])) / 32768.0, float(rng.choice([0.0, 10.0, 200.0])) / 32768.0)
-    return x.astype(np.float32), p
+    fmt = int(rng.choice([0x9400, 0x9400, 0x9302, 0x9301]))
+    if fmt != 0x9400:
+        p = (0, 0) + p[2:]                      # the 1993 layouts: stream type 0
+    return x.astype(np.float32), p + (fmt,)
 
 
 def want(args):
     x, p = make(args)
-    return ref.encode_framed(x, p[0], p[1], p[2], p[3], p[4], p[5])[0]
+    return ref.encode_framed(x, p[0], p[1], p[2], p[3], p[4], p[5], fmt=p[6])[0]
 
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
