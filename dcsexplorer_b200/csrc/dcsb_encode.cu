@@ -54,6 +54,8 @@ struct EncTables {
     uint8_t dz_len[6];
     uint32_t hdr_code[31];          // header delta codes, delta + 16
     uint8_t hdr_len[31];
+    uint32_t h93_code[2][32];       // 1993b type-1 band-type delta codes, [0] same subtype / [1] subtype inverts, delta + 16 (:2058-2127)
+    uint8_t h93_len[2][32];
 };
 __constant__ EncTables c_enc;
 
@@ -387,14 +389,127 @@ dcsb_enc_emit_kernel(const EncStream *__restrict__ streams, const uint32_t *__re
     else frame_bits[fr] = (uint32_t)sink.count;
 }
 
-// One frame of the 1993 layout, stream type 0 (CompressFrame93b, :2053-2473): the bands of a frame hang together --
-// every band may be stored as values, first or second differences against the samples before it, and says so relative
-// to the band before -- but frames do not (type 0 carries nothing from frame to frame), so a thread takes a frame.
+// ---- the 1993 layouts (CompressFrame93b, :2053-2473) -----------------------------------------------------------------
+// The bands of a frame hang together: every band may be stored as values, first or (type 0) second differences against
+// the samples before it, takes the narrowest of them, and says so relative to the band before.  Type 0 carries nothing
+// from frame to frame, so a thread takes a frame and decides as it goes.  Type 1 delta-codes a band's type against the
+// SAME band of the frame before (and the search's upper limit follows that old code), so its decisions are made by a
+// thread per stream walking the frames (dcsb_enc_resolve93_kernel) from a table of the two possible search outcomes
+// (dcsb_enc_search93_kernel), and the frame kernel only writes what was decided.
+__device__ __forceinline__ int enc93_count(const EncStream &s, int band) { return (s.type == 1 && band == 0) ? 15 : 16; }
+__device__ __forceinline__ int enc93_first(const EncStream &s, int band) { return s.type == 1 ? (band == 0 ? 0 : 16 * band - 1) : 16 * band; }
+
+// FindBestBandEncoding for one band of a 1993-layout frame: codes 1..top, width = code + wadd
+__device__ __forceinline__ int enc93_search(const float *x, int n, float scale, float err_max, int wadd, int top)
+{
+    float err[16];
+    bool pass[16];
+    for (int code = 1; code <= 15; ++code) {
+        const int width = code + wadd, ref = 1 << (width - 1), mask = 0xFFFF >> (16 - width);
+        float sum = 0.0f;
+        for (int i = 0; i < n; ++i) {
+            const float o = x[i];
+            const int stored = (enc_quant(o, scale) + ref) & mask;
+            const float rec = __fdiv_rn(__fmul_rn((float)(stored - ref), scale), 32768.0f);
+            const float e = __fsub_rn(rec, o);
+            sum = __fadd_rn(sum, __fmul_rn(e, e));
+        }
+        err[code] = sum;
+        pass[code] = sum <= err_max;
+    }
+    int narrow = -1, pick = 0;
+    for (int c = 1; c <= top; ++c)
+        if (pass[c] && (narrow == -1 || c + wadd < narrow)) narrow = c + wadd;
+    float min_err = -1.0f;
+    for (int c = 1; c <= top; ++c)
+        if (narrow == -1 || c + wadd == narrow)
+            if (min_err < 0 || err[c] < min_err) { pick = c; min_err = err[c]; }
+    return pick;
+}
+// the band type a run of differences needs (GetDeltaBandCode, :2224-2256)
+__device__ __forceinline__ int enc93_delta_code(const int *b, int n, int type)
+{
+    int lo = b[0], hi = b[0];
+    for (int i = 1; i < n; ++i) { lo = b[i] < lo ? b[i] : lo; hi = b[i] > hi ? b[i] : hi; }
+    if (hi < 0) hi = -hi;
+    if (lo < 0) lo = -lo;
+    if (lo > hi) hi = lo;
+    if (hi == 0) return 0;
+    int nb = 1;
+    for (; hi != 0; hi >>= 1) ++nb;
+    return nb - (type == 0 ? 1 : 0);
+}
+
+// type 1: the two outcomes of the search a band can have (code 15 within reach of the delta code or not)
+__global__ void __launch_bounds__(ENC_THREADS)
+dcsb_enc_search93_kernel(const EncStream *__restrict__ streams, const uint32_t *__restrict__ frame_stream, uint32_t n_frames_total,
+                         const float *__restrict__ f, uint8_t *__restrict__ best)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_frames_total * 16u) return;
+    const uint32_t fr = t >> 4;
+    const int band = (int)(t & 15);
+    const EncStream s = streams[frame_stream[fr]];
+    if (!s.fmt93 || s.type != 1 || band >= s.bands) return;
+    const int n = enc93_count(s, band);
+    const float *x = f + (size_t)fr * 256 + enc93_first(s, band);
+    const float scale = enc_scale(s.hdr[band] & 0x3F), err_max = __fmul_rn(s.max_err2, (float)n);
+    uint8_t *bo = best + (size_t)t * (ENC_NV * 2);
+    bo[0] = (uint8_t)enc93_search(x, n, scale, err_max, 0, 15);
+    bo[1] = (uint8_t)enc93_search(x, n, scale, err_max, 0, 14);
+}
+
+// type 1: decisions of every band of every frame, in order.  dec[frame][band] = code | subtype << 4 | "same again" << 5 |
+// (delta + 16) << 8
+__global__ void dcsb_enc_resolve93_kernel(const EncStream *__restrict__ streams, int n, const float *__restrict__ f,
+                                          const uint8_t *__restrict__ best, uint16_t *__restrict__ dec)
+{
+    const int si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= n) return;
+    const EncStream s = streams[si];
+    if (!s.fmt93 || s.type != 1) return;
+    int old[16];
+    for (int b = 0; b < 16; ++b) old[b] = 0;
+    for (uint32_t k = 0; k < s.n_frames; ++k) {
+        const size_t fr = (size_t)s.frame0 + k;
+        int last_code = -1, last_sub = 0, prv = 0;
+        for (int band = 0; band < s.bands; ++band) {
+            const int cnt = enc93_count(s, band);
+            const float *x = f + fr * 256 + enc93_first(s, band);
+            const float scale = enc_scale(s.hdr[band] & 0x3F);
+            const int band_prv = prv;
+            int b1[16];
+            for (int i = 0; i < cnt; ++i) {
+                const int cur = enc_quant(x[i], scale);
+                b1[i] = cur - prv;
+                prv = cur;
+            }
+            // values: the search reaches old + 14 when the subtype stays 0, old + 15 when it changes to 0 (:2151-2172)
+            const int top_is_14 = (last_sub == 0 && old[band] == 0) ? 1 : 0;
+            int code = best[(fr * 16 + band) * (ENC_NV * 2) + top_is_14], sub = 0;
+            const int c1 = enc93_delta_code(b1, cnt, 1);
+            if (c1 < code || (c1 == code && last_sub == 1)) { sub = 1; code = c1; }
+            uint16_t d;
+            if (last_code == 0 && code == 0 && last_sub == sub) d = (uint16_t)(code | (sub << 4) | 0x20);
+            else {
+                int delta = code - old[band] + 16;
+                delta = delta < 0 ? 0 : (delta > 31 ? 31 : delta);
+                d = (uint16_t)(code | (sub << 4) | (delta << 8));
+                old[band] = code;
+                if (code == 0) prv = sub == 0 ? 0 : band_prv;
+            }
+            dec[fr * 16 + band] = d;
+            last_code = code;
+            last_sub = sub;
+        }
+    }
+}
+
 template <bool WRITE>
 __global__ void __launch_bounds__(ENC_THREADS)
 dcsb_enc_frame93_kernel(const EncStream *__restrict__ streams, const uint32_t *__restrict__ frame_stream, uint32_t n_frames_total,
-                        const float *__restrict__ f, uint32_t *__restrict__ frame_bits, const uint64_t *__restrict__ frame_pos,
-                        uint32_t *__restrict__ out_words, const uint64_t *__restrict__ stream_word0)
+                        const float *__restrict__ f, const uint16_t *__restrict__ dec, uint32_t *__restrict__ frame_bits,
+                        const uint64_t *__restrict__ frame_pos, uint32_t *__restrict__ out_words, const uint64_t *__restrict__ stream_word0)
 {
     const uint32_t fr = blockIdx.x * blockDim.x + threadIdx.x;
     if (fr >= n_frames_total) return;
@@ -413,13 +528,15 @@ dcsb_enc_frame93_kernel(const EncStream *__restrict__ streams, const uint32_t *_
         sink.widx = p >> 5;
         sink.nacc = (int)(p & 31);
     }
-    int last_code = -1, last_sub = 2, prv = 0, prvd = 0;
+    const int type = s.type;
+    int last_code = -1, last_sub = type == 1 ? 0 : 2, prv = 0, prvd = 0;
     for (int band = 0; band < s.bands; ++band) {
-        const float *x = f + (size_t)fr * 256 + 16 * band;
+        const int cnt = enc93_count(s, band);
+        const float *x = f + (size_t)fr * 256 + enc93_first(s, band);
         const float scale = enc_scale(s.hdr[band] & 0x3F);
         const int band_prv = prv, band_prvd = prvd;
         int b0[16], b1[16], b2[16];
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < cnt; ++i) {
             const int cur = enc_quant(x[i], scale);
             b0[i] = cur;
             b1[i] = cur - prv;
@@ -427,71 +544,45 @@ dcsb_enc_frame93_kernel(const EncStream *__restrict__ streams, const uint32_t *_
             prvd = b1[i];
             prv = cur;
         }
-        // values as they are: the narrowest width within the error limit (FindBestBandEncoding, codes 1..15, width code + 1)
-        int c0 = 0;
-        {
-            const float err_max = __fmul_rn(s.max_err2, 16.0f);
-            float err[16];
-            bool pass[16];
-            for (int code = 1; code <= 15; ++code) {
-                const int width = code + 1, ref = 1 << (width - 1), mask = 0xFFFF >> (16 - width);
-                float sum = 0.0f;
-                for (int i = 0; i < 16; ++i) {
-                    const float o = x[i];
-                    const int stored = (enc_quant(o, scale) + ref) & mask;
-                    const float rec = __fdiv_rn(__fmul_rn((float)(stored - ref), scale), 32768.0f);
-                    const float e = __fsub_rn(rec, o);
-                    sum = __fadd_rn(sum, __fmul_rn(e, e));
-                }
-                err[code] = sum;
-                pass[code] = sum <= err_max;
-            }
-            int narrow = -1;
-            for (int c = 1; c <= 15; ++c)
-                if (pass[c] && (narrow == -1 || c + 1 < narrow)) narrow = c + 1;
-            float min_err = -1.0f;
-            for (int c = 1; c <= 15; ++c)
-                if (narrow == -1 || c + 1 == narrow)
-                    if (min_err < 0 || err[c] < min_err) { c0 = c; min_err = err[c]; }
+        int code, sub, hidx = 0;
+        bool same;
+        if (type == 0) {
+            code = enc93_search(x, cnt, scale, __fmul_rn(s.max_err2, (float)cnt), 1, 15);
+            sub = 0;
+            const int c1 = enc93_delta_code(b1, cnt, 0), c2 = enc93_delta_code(b2, cnt, 0);
+            if (c1 < code || (c1 == code && last_sub == 1)) { sub = 1; code = c1; }
+            if (c2 < code) { sub = 2; code = c2; }
+            same = last_code == 0 && code == 0 && last_sub == sub;
+        } else {
+            const uint16_t d = dec[(size_t)fr * 16 + band];
+            code = d & 15;
+            sub = (d >> 4) & 1;
+            same = (d & 0x20) != 0;
+            hidx = d >> 8;
         }
-        // differences: the width their extremes need (:2224-2256)
-        int cd[2];
-        for (int k = 0; k < 2; ++k) {
-            const int *b = k ? b2 : b1;
-            int lo = b[0], hi = b[0];
-            for (int i = 1; i < 16; ++i) { lo = b[i] < lo ? b[i] : lo; hi = b[i] > hi ? b[i] : hi; }
-            if (hi < 0) hi = -hi;
-            if (lo < 0) lo = -lo;
-            if (lo > hi) hi = lo;
-            int code = 0;
-            if (hi != 0) {
-                int nb = 1;
-                for (; hi != 0; hi >>= 1) ++nb;
-                code = nb - 1;
-            }
-            cd[k] = code;
-        }
-        int code = c0, sub = 0;
-        if (cd[0] < code || (cd[0] == code && last_sub == 1)) { sub = 1; code = cd[0]; }
-        if (cd[1] < code) { sub = 2; code = cd[1]; }
-        if (last_code == 0 && code == 0 && last_sub == sub) {
+        if (same) {
             sink.put<WRITE>(1u, 1);                             // "the same again" (:2283-2288)
         } else {
             if (last_code == 0) sink.put<WRITE>(0u, 1);
-            if (sub == last_sub) sink.put<WRITE>(0u, 1);
-            else {
-                sink.put<WRITE>(1u, 1);
-                sink.put<WRITE>((uint32_t)(((sub - last_sub + 3) % 3) == 1 ? 1 : 0), 1);     // up / down modulo 3 (:2307-2311)
+            if (type == 0) {
+                if (sub == last_sub) sink.put<WRITE>(0u, 1);
+                else {
+                    sink.put<WRITE>(1u, 1);
+                    sink.put<WRITE>((uint32_t)(((sub - last_sub + 3) % 3) == 1 ? 1 : 0), 1);     // up / down modulo 3 (:2307-2311)
+                }
+                sink.put<WRITE>((uint32_t)code, 4);
+            } else {
+                const int inv = sub == last_sub ? 0 : 1;
+                sink.put<WRITE>(c_enc.h93_code[inv][hidx], c_enc.h93_len[inv][hidx]);
             }
-            sink.put<WRITE>((uint32_t)code, 4);
             if (code == 0) {
                 if (sub == 0) { prv = 0; prvd = 0; }
                 else if (sub == 1) { prv = band_prv; prvd = 0; }
                 else { prv = band_prv; prvd = band_prvd; }
             } else {
-                const int nb = code + 1, mask = (1 << nb) - 1;
+                const int nb = code + (type == 0 ? 1 : 0), mask = (1 << nb) - 1;
                 const int *b = sub == 0 ? b0 : (sub == 1 ? b1 : b2);
-                for (int i = 0; i < 16; ++i) sink.put<WRITE>((uint32_t)(b[i] & mask), nb);
+                for (int i = 0; i < cnt; ++i) sink.put<WRITE>((uint32_t)(b[i] & mask), nb);
             }
         }
         last_code = code;
@@ -566,6 +657,13 @@ static void enc_build_tables(EncTables *t)
             if (e.val == 0x80) { t->dz_code[k] = e.code; t->dz_len[k] = e.len; }
             else { t->cb_code[k][e.val & 63] = e.code; t->cb_len[k][e.val & 63] = e.len; }
         }
+    memset(t->h93_code, 0, sizeof(t->h93_code));
+    memset(t->h93_len, 0, sizeof(t->h93_len));
+    for (int i = 0; i < 62; ++i) {
+        const dcs_code_t &e = dcs93_hdr[i];
+        const int inv = e.val >= 0x1E ? 1 : 0, d = (int)e.val - (inv ? 0x2E : 0x0F) + 16;
+        if (d >= 0 && d < 32) { t->h93_code[inv][d] = e.code; t->h93_len[inv][d] = e.len; }
+    }
     for (int i = 0; i < 31; ++i) {
         const dcs_code_t &e = dcs94_hdr[i];
         const int d = (int)e.val - 0x2E + 16;
@@ -584,6 +682,7 @@ static void enc_stream_header(const float *stats /* 48 */, const dcsb_encode_par
     float norm[16];
     int counts[16];
     for (int i = 0; i < 16; ++i) { norm[i] = f93 ? 1.0f : norm94[i]; counts[i] = f93 ? 16 : counts94[i]; }
+    if (f93 && pr.stream_type == 1) counts[0] = 15;          // bandSampleCounts93b_Type1 (:53-55, :866-868)
     float rms[16], total = 0.0f;
     for (int i = 0; i < 16; ++i) {
         rms[i] = sqrtf(stats[i] * norm[i]);
@@ -636,7 +735,7 @@ static void enc_stream_header(const float *stats /* 48 */, const dcsb_encode_par
 
 // device / pinned buffers kept in the context between calls (no allocation in the steady state)
 struct EncCache {
-    DcsbBuf pcm, f, power, lo, hi, stats, streams, frame_stream, frame_bits, words, best, codes, padj, frame_pos, stream_bits, word0;
+    DcsbBuf pcm, f, power, lo, hi, stats, streams, frame_stream, frame_bits, words, best, codes, padj, frame_pos, stream_bits, word0, dec;
     DcsbBuf h_words, h_pcm;          // pinned staging: stream data on its way out, PCM on its way in
     bool tables_up = false;
 };
@@ -645,7 +744,7 @@ static void enc_cache_free(void *p)
     EncCache *c = static_cast<EncCache *>(p);
     if (!c) return;
     for (DcsbBuf *b : { &c->pcm, &c->f, &c->power, &c->lo, &c->hi, &c->stats, &c->streams, &c->frame_stream, &c->frame_bits, &c->words,
-                        &c->best, &c->codes, &c->padj, &c->frame_pos, &c->stream_bits, &c->word0 }) b->release(false);
+                        &c->best, &c->codes, &c->padj, &c->frame_pos, &c->stream_bits, &c->word0, &c->dec }) b->release(false);
     c->h_words.release(true);
     c->h_pcm.release(true);
     delete c;
@@ -667,7 +766,7 @@ static int encode_impl(dcsb_ctx *ctx, const float *const *pcm, const uint64_t *n
     if (!ctx || (n && (!pcm || !n_samples || !params || !out || !out_offsets))) return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: bad argument");
     if (n == 0) return DCSB_OK;
     uint64_t total_samples = 0, total_frames = 0;
-    bool any93 = false;
+    bool any93 = false, any93t1 = false;
     std::vector<EncStream> hs(n);
     for (size_t i = 0; i < n; ++i) {
         const dcsb_encode_params &p = params[i];
@@ -677,8 +776,8 @@ static int encode_impl(dcsb_ctx *ctx, const float *const *pcm, const uint64_t *n
         const bool f93 = p.format_version == DCSB_OS93A || p.format_version == DCSB_OS93B;
         if (p.format_version != 0 && p.format_version != DCSB_OS94 && !f93)
             return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: format version must be 0 / $9400, $9301 or $9302");
-        if (f93 && (p.stream_type != 0 || p.stream_subtype != 0))
-            return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: the 1993 layouts are encoded as stream type 0 only");
+        if (f93 && (p.stream_subtype != 0 || (p.stream_type == 1 && p.format_version != DCSB_OS93B)))
+            return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: 1993 layouts: subtype 0; stream type 1 only with format version $9302");
         const uint64_t nf = (n_samples[i] + 239) / 240;
         if (nf > 65535) return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: a stream holds at most 65535 frames");
         EncStream &s = hs[i];
@@ -694,6 +793,7 @@ static int encode_impl(dcsb_ctx *ctx, const float *const *pcm, const uint64_t *n
         s.min_range = p.min_dynamic_range;
         s.fmt93 = f93 ? 1 : 0;
         any93 = any93 || f93;
+        any93t1 = any93t1 || (f93 && p.stream_type == 1);
         if (!shared) total_samples += n_samples[i];
         total_frames += nf;
     }
@@ -731,6 +831,7 @@ static int encode_impl(dcsb_ctx *ctx, const float *const *pcm, const uint64_t *n
     ENSE(ec.best, total_frames * 16 * ENC_NV * 2, false, "cudaMalloc(search table)");
     ENSE(ec.codes, total_frames * 16, false, "cudaMalloc(codes)");
     ENSE(ec.padj, total_frames * 4, false, "cudaMalloc(pre-adjustments)");
+    if (any93t1) ENSE(ec.dec, total_frames * 32, false, "cudaMalloc(band decisions)");
     ENSE(ec.frame_bits, total_frames * 4, false, "cudaMalloc(frame sizes)");
     ENSE(ec.frame_pos, total_frames * 8, false, "cudaMalloc(frame positions)");
     ENSE(ec.stream_bits, n * 8, false, "cudaMalloc(stream sizes)");
@@ -795,7 +896,11 @@ static int encode_impl(dcsb_ctx *ctx, const float *const *pcm, const uint64_t *n
         dcsb_enc_search_kernel<<<gfb, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, d_lo, d_hi, d_best);
         dcsb_enc_resolve_kernel<<<gs, 64>>>(d_streams, (int)n, d_best, d_codes, d_padj);
         dcsb_enc_emit_kernel<false><<<gf, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, d_codes, d_padj, d_frame_bits, nullptr, nullptr, nullptr);
-        if (any93) dcsb_enc_frame93_kernel<false><<<gf, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, d_frame_bits, nullptr, nullptr, nullptr);
+        if (any93t1) {
+            dcsb_enc_search93_kernel<<<gfb, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, d_best);
+            dcsb_enc_resolve93_kernel<<<gs, 64>>>(d_streams, (int)n, d_f, d_best, static_cast<uint16_t *>(ec.dec.p));
+        }
+        if (any93) dcsb_enc_frame93_kernel<false><<<gf, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, static_cast<const uint16_t *>(ec.dec.p), d_frame_bits, nullptr, nullptr, nullptr);
         dcsb_enc_scan_kernel<<<gs, 64>>>(d_streams, (int)n, d_frame_bits, d_frame_pos, d_stream_bits);
         CKE(cudaGetLastError(), "encoder kernel launch");
         CKE(cudaMemcpy(sbits.data(), d_stream_bits, n * 8, cudaMemcpyDeviceToHost), "D2H stream sizes");
@@ -814,7 +919,7 @@ static int encode_impl(dcsb_ctx *ctx, const float *const *pcm, const uint64_t *n
         CKE(cudaMemset(d_words, 0, word0[n] * 4), "memset stream data");
         CKE(cudaMemcpy(d_word0, word0.data(), (n + 1) * 8, cudaMemcpyHostToDevice), "H2D stream offsets");
         dcsb_enc_emit_kernel<true><<<gf, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, d_codes, d_padj, nullptr, d_frame_pos, d_words, d_word0);
-        if (any93) dcsb_enc_frame93_kernel<true><<<gf, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, nullptr, d_frame_pos, d_words, d_word0);
+        if (any93) dcsb_enc_frame93_kernel<true><<<gf, ENC_THREADS>>>(d_streams, d_frame_stream, nfr, d_f, static_cast<const uint16_t *>(ec.dec.p), nullptr, d_frame_pos, d_words, d_word0);
         CKE(cudaGetLastError(), "encoder kernel launch");
         lap("packed");
         CKE(cudaMemcpy(ec.h_words.p, d_words, word0[n] * 4, cudaMemcpyDeviceToHost), "D2H stream data");
@@ -853,8 +958,6 @@ extern "C" int dcsb_encode_streams(dcsb_ctx *ctx, const float *const *pcm, const
         const dcsb_encode_params &p = params[i];
         if (p.stream_type < -1 || p.stream_type > 1 || (p.stream_subtype != -1 && p.stream_subtype != 0 && p.stream_subtype != 3))
             return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: stream type must be -1, 0 or 1, subtype -1, 0 or 3");
-        const bool f93 = p.format_version == DCSB_OS93A || p.format_version == DCSB_OS93B;
-        if (f93 && p.stream_type != 0) return fail(ctx, DCSB_E_ARG, "dcsb_encode_streams: the 1993 layouts are encoded as stream type 0 only (give the type)");
         wild = wild || p.stream_type < 0 || p.stream_subtype < 0;
     }
     if (!wild) return encode_impl(ctx, pcm, n_samples, n, params, out, out_capacity, out_offsets, frames_out);
@@ -870,7 +973,7 @@ extern "C" int dcsb_encode_streams(dcsb_ctx *ctx, const float *const *pcm, const
         for (const auto &f : formats) {
             const dcsb_encode_params &p = params[i];
             const bool f93 = p.format_version == DCSB_OS93A || p.format_version == DCSB_OS93B;
-            if (f93 && (f[0] != 0 || f[1] != 0)) continue;                 // (no subtypes there, :798-806)
+            if (f93 && (f[1] != 0 || (f[0] == 1 && p.format_version != DCSB_OS93B))) continue;       // (no subtypes there; no encoder for OS93a type 1, :798-815)
             if ((p.stream_type >= 0 && p.stream_type != f[0]) || (!f93 && p.stream_subtype >= 0 && p.stream_subtype != f[1])) continue;
             dcsb_encode_params q = p;
             q.stream_type = f[0];

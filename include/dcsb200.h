@@ -298,8 +298,9 @@ typedef struct dcsb_encode_params {
     float power_band_cutoff;        /* default 0.97 */
     float max_quantization_error;   /* default 10 / 32768 */
     float min_dynamic_range;        /* default 10 / 32768 */
-    int32_t format_version;         /* 0 or DCSB_OS94: the 1994 layout; DCSB_OS93A / DCSB_OS93B: the 1993 layout, stream type 0
-                                     * only (CompressFrame93b, DCSEncoder.cpp:2053-2473; the subtype is ignored there) */
+    int32_t format_version;         /* 0 or DCSB_OS94: the 1994 layout; DCSB_OS93A / DCSB_OS93B: the 1993 layout (CompressFrame93b,
+                                     * DCSEncoder.cpp:2053-2473): subtype 0 (or -1), stream type 0, or 1 with DCSB_OS93B (the
+                                     * reference has no encoder for OS93a type 1 either, :808-815) */
 } dcsb_encode_params;
 /* bytes a stream of n_samples samples can need at most (size `out` with the sum over the clips) */
 uint64_t dcsb_encode_bound(uint64_t n_samples);

@@ -115,16 +115,17 @@ def test_gpu_encode_wildcard_stream_type_picks_like_the_reference(ctx):
 
 
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref did not travel with the snapshot")
-def test_gpu_encode_1993_layout_type0_equals_the_reference(ctx):
-    """format versions $9302 / $9301, stream type 0 (CompressFrame93b): bytes identical to the reference's, and the
-    streams decode through our 1993 path like the oracle decodes them"""
+def test_gpu_encode_1993_layouts_equal_the_reference(ctx):
+    """format versions $9302 / $9301 (CompressFrame93b), stream type 0 and -- $9302 -- type 1 and the wildcard: bytes
+    identical to the reference's, and the streams decode through our 1993 path like the oracle decodes them"""
     from oracle import orc
     rng = np.random.default_rng(93)
     clips = _clips() + [(rng.standard_normal(int(rng.integers(300, 20000))) * rng.uniform(0.001, 0.6)).astype(np.float32) for _ in range(40)]
     jobs = []
     for i, c in enumerate(clips):
         fmt = 0x9302 if i % 2 else 0x9301
-        jobs.append((c, (0, 0, int(rng.choice([32000, 96000, 128000, 256000])), float(rng.choice([0.9, 0.97, 1.0])),
+        ty = (0, 1, -1)[(i // 2) % 3] if fmt == 0x9302 else 0
+        jobs.append((c, (ty, 0, int(rng.choice([32000, 96000, 128000, 256000])), float(rng.choice([0.9, 0.97, 1.0])),
                          float(rng.choice([1.0, 10.0, 100.0])) / 32768.0, 10.0 / 32768.0, fmt)))
     streams = ctx.encode_streams([j[0] for j in jobs], [j[1] for j in jobs])
     bad = []
@@ -149,7 +150,7 @@ def test_gpu_encode_rejects_bad_arguments(ctx):
     with pytest.raises(dx.DcsbError):
         ctx.encode_streams([clip], [(-2, 0, 128000, 0.97)])
     with pytest.raises(dx.DcsbError):
-        ctx.encode_streams([clip], [(1, 0, 128000, 0.97, 10 / 32768, 10 / 32768, 0x9302)])      # 1993 layout: type 0 only
+        ctx.encode_streams([clip], [(1, 0, 128000, 0.97, 10 / 32768, 10 / 32768, 0x9301)])      # no encoder for OS93a type 1
     with pytest.raises(dx.DcsbError):
         ctx.encode_streams([clip], [(0, 0, 128000, 0.97, 10 / 32768, 10 / 32768, 0x9500)])
     with pytest.raises(dx.DcsbError):

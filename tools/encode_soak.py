@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""GPU soak of the forward path (1994 layout with all four stream types; 1993 layouts as type 0): seeded random clips (noise, tones, sweeps, bursts, near-silence, clipped; 100..60000
+"""GPU soak of the forward path (1994 layout: the four stream types and the wildcard; $9302: types 0, 1 and the wildcard; $9301: type 0): seeded random clips (noise, tones, sweeps, bursts, near-silence, clipped; 100..60000
 samples) with random parameters through dcsb_encode_streams, every stream's bytes against the reference DCSEncoder fed
 the same framing (oracle/_ref) on the host cores.   usage: tools/encode_soak.py [n_clips=4000] [seed=1]"""
 import multiprocessing as mp
@@ -34,8 +34,13 @@ def make(args):
     p = (int(rng.integers(0, 2)), int(rng.choice([0, 3])), int(rng.choice([8000, 32000, 64000, 96000, 128000, 192000, 256000, 512000])),
          float(rng.choice([0.5, 0.9, 0.97, 1.0])), float(rng.choice([1.0, 10.0, 100.0])) / 32768.0, float(rng.choice([0.0, 10.0, 200.0])) / 32768.0)
     fmt = int(rng.choice([0x9400, 0x9400, 0x9302, 0x9301]))
-    if fmt != 0x9400:
-        p = (0, 0) + p[2:]                      # the 1993 layouts: stream type 0
+    if fmt == 0x9400:
+        if i % 11 == 0:
+            p = (-1, -1) + p[2:]                # the wildcard: every format tried, the first of the smallest kept
+    elif fmt == 0x9302:
+        p = (int(rng.choice([0, 1, -1])), 0) + p[2:]
+    else:
+        p = (0, 0) + p[2:]                      # $9301: stream type 0 (nobody encodes OS93a type 1)
     return x.astype(np.float32), p + (fmt,)
 
 
