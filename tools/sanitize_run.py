@@ -63,5 +63,9 @@ clips = [(erng.standard_normal(n) * 0.2).astype(np.float32) for n in (17, 240, 1
 enc = ctx.encode_streams(clips * 4, [(t, u, 96000, 0.97) for t, u in ((0, 0), (0, 3), (1, 0), (1, 3)) for _ in clips])
 pcm, offs, res = ctx.decode_streams([(e, 0x9400, 255, 0x64, 2) for e in enc])
 assert all(r["status"] == 0 for r in res)
+enc = ctx.encode_streams(clips * 3 + clips[:2], [(t, 0, 96000, 0.97, 10 / 32768, 10 / 32768, v) for t, v in ((0, 0x9301), (0, 0x9302), (1, 0x9302)) for _ in clips]
+                         + [(-1, -1, 64000, 0.9), (-1, 0, 64000, 0.9, 10 / 32768, 10 / 32768, 0x9302)])
+pcm, offs, res = ctx.decode_streams([(e, v, 255, 0x64, 2) for e, v in zip(enc, [0x9301] * 5 + [0x9302] * 10 + [0x9400, 0x9302])])
+assert all(r["status"] == 0 for r in res)
 ctx.close()
 print("sanitize_run: ok, %d streams" % len(streams))
