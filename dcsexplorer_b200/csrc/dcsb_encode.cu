@@ -219,12 +219,14 @@ __global__ void __launch_bounds__(ENC_THREADS)
 dcsb_enc_search_kernel(const EncStream *__restrict__ streams, const uint32_t *__restrict__ frame_stream, uint32_t n_frames_total,
                        const float *__restrict__ f, const float *__restrict__ lo, const float *__restrict__ hi, uint8_t *__restrict__ best)
 {
+    // (band-major: the threads of a warp work on the SAME band of 32 consecutive frames -- same sample count, same
+    // number of alternatives -- instead of on the 16 different bands of two frames: 6.9 -> ~30 active threads per instruction)
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_frames_total * 16u) return;
-    const uint32_t fr = t >> 4;
-    const int band = (int)(t & 15);
+    const uint32_t fr = t % n_frames_total;
+    const int band = (int)(t / n_frames_total);
     const EncStream s = streams[frame_stream[fr]];
-    uint8_t *bo = best + (size_t)t * (ENC_NV * 2);
+    uint8_t *bo = best + ((size_t)fr * 16 + band) * (ENC_NV * 2);
     for (int i = 0; i < ENC_NV * 2; ++i) bo[i] = 0;
     if (band >= s.bands || s.fmt93) return;
     if (__fsub_rn(hi[(size_t)fr * 16 + band], lo[(size_t)fr * 16 + band]) < s.min_range) return;
@@ -447,14 +449,14 @@ dcsb_enc_search93_kernel(const EncStream *__restrict__ streams, const uint32_t *
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_frames_total * 16u) return;
-    const uint32_t fr = t >> 4;
-    const int band = (int)(t & 15);
+    const uint32_t fr = t % n_frames_total;             // band-major, as in dcsb_enc_search_kernel
+    const int band = (int)(t / n_frames_total);
     const EncStream s = streams[frame_stream[fr]];
     if (!s.fmt93 || s.type != 1 || band >= s.bands) return;
     const int n = enc93_count(s, band);
     const float *x = f + (size_t)fr * 256 + enc93_first(s, band);
     const float scale = enc_scale(s.hdr[band] & 0x3F), err_max = __fmul_rn(s.max_err2, (float)n);
-    uint8_t *bo = best + (size_t)t * (ENC_NV * 2);
+    uint8_t *bo = best + ((size_t)fr * 16 + band) * (ENC_NV * 2);
     bo[0] = (uint8_t)enc93_search(x, n, scale, err_max, 0, 15);
     bo[1] = (uint8_t)enc93_search(x, n, scale, err_max, 0, 14);
 }
