@@ -92,6 +92,9 @@ def test_null_and_bad_arguments_are_rejected_not_dereferenced(built):
     assert L.dcsb_player_host_bytes(None, None, 0) == 0
     assert L.dcsb_player_is_stream_playing(None, 0) == 0
     L.dcsb_batch_destroy(None)
+    # the forward path: no context, no work; its size bound is pure host code (18 bytes of preamble + 526 per frame at most)
+    assert L.dcsb_encode_streams(None, None, None, 1, None, None, 0, None, None) != dx.OK
+    assert int(L.dcsb_encode_bound(0)) >= 18 and int(L.dcsb_encode_bound(240)) >= 18 + 526 and int(L.dcsb_encode_bound(241)) >= 18 + 2 * 526
     # stream partitioning is pure host code
     part, load = dx.partition_streams([10, 0, 7, 7, 3], 2)
     assert abs(int(load[0]) - int(load[1])) <= 3 and len(part) == 5 and set(int(x) for x in part) == {0, 1}
