@@ -17,6 +17,27 @@ def ctx(built):
     c.close()
 
 
+def test_gpu_encode_matches_the_committed_reference_hashes(ctx):
+    """tests/golden/encode_golden.json (made by make_encode_golden.py from the unmodified reference encoder in the build
+    container): SHA-256 of the stream of every case -- every format the reference writes, wildcards included.  Needs
+    nothing but the fixture on the GPU box."""
+    import hashlib
+    import json
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    import make_encode_golden as mg
+    cases = json.load(open(os.path.join(here, "encode_golden.json")))
+    assert len(cases) == len(mg.CASES) >= 48
+    clips = [mg.clip(c["seed"]) for c in cases]
+    params = [(c["type"], c["subtype"], c["bit_rate"], c["power_cut"], c["max_err"], c["min_range"], c["fmt"]) for c in cases]
+    streams = ctx.encode_streams(clips, params)
+    bad = [(c["seed"], hex(c["fmt"]), c["type"]) for c, s_ in zip(cases, streams)
+           if len(s_) != c["n_bytes"] or hashlib.sha256(s_).hexdigest() != c["sha256"]]
+    assert not bad, bad
+
+
 def _clips():
     import bench
     rng = np.random.default_rng(11)
