@@ -223,3 +223,72 @@ extern "C" int hostsim_rom_render(const uint8_t *const *imgs, const size_t *size
     }
     return DCSB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// The forward path on the CPU: the kernel bodies of dcsb_encode.cuh with loops playing the grids, in the order
+// dcsb_encode_streams launches them (explicit stream types; the wildcard is host logic of the product's entry point).
+#include "../../dcsexplorer_b200/csrc/dcsb_encode.cuh"
+extern "C" int hostsim_encode_streams(const float *const *pcm, const uint64_t *n_samples, size_t n, const dcsb_encode_params *params,
+                                      uint8_t *out, uint64_t out_capacity, uint64_t *out_offsets, float *frames_out)
+{
+    enc_build_tables(&g_enc_host);
+    std::vector<EncStream> hs(n);
+    std::vector<float> all;
+    uint64_t total_frames = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const dcsb_encode_params &p = params[i];
+        const bool f93 = p.format_version == DCSB_OS93A || p.format_version == DCSB_OS93B;
+        if (n_samples[i] == 0 || (p.stream_type != 0 && p.stream_type != 1)) return DCSB_E_ARG;
+        EncStream &s = hs[i];
+        memset(&s, 0, sizeof(s));
+        s.pcm_off = all.size();
+        s.n_samples = n_samples[i];
+        s.frame0 = (uint32_t)total_frames;
+        s.n_frames = (uint32_t)((n_samples[i] + 239) / 240);
+        s.type = p.stream_type;
+        s.subtype = p.stream_subtype;
+        s.max_err2 = p.max_quantization_error * p.max_quantization_error;
+        s.min_range = p.min_dynamic_range;
+        s.fmt93 = f93 ? 1 : 0;
+        all.insert(all.end(), pcm[i], pcm[i] + n_samples[i]);
+        total_frames += s.n_frames;
+    }
+    const uint32_t nfr = (uint32_t)total_frames;
+    std::vector<uint32_t> frame_stream(nfr), frame_bits(nfr, 0);
+    for (size_t i = 0; i < n; ++i)
+        for (uint32_t k = 0; k < hs[i].n_frames; ++k) frame_stream[hs[i].frame0 + k] = (uint32_t)i;
+    std::vector<float> f((size_t)nfr * 256), power((size_t)nfr * 16), lo((size_t)nfr * 16), hi((size_t)nfr * 16), stats(n * 48);
+    for (uint32_t t = 0; t < nfr; ++t) dcsb_enc_transform_body(t, all.data(), hs.data(), frame_stream.data(), nfr, f.data(), power.data(), lo.data(), hi.data());
+    for (uint32_t t = 0; t < n * 16; ++t) dcsb_enc_stats_body(t, hs.data(), (int)n, power.data(), lo.data(), hi.data(), stats.data());
+    if (frames_out) memcpy(frames_out, f.data(), f.size() * sizeof(float));
+    for (size_t i = 0; i < n; ++i) enc_stream_header(&stats[i * 48], params[i], g_enc_host, &hs[i]);
+    std::vector<uint8_t> best((size_t)nfr * 16 * ENC_NV * 2, 0), codes((size_t)nfr * 16, 0), padj((size_t)nfr * 4, 0);
+    std::vector<uint16_t> dec((size_t)nfr * 16, 0);
+    std::vector<uint64_t> frame_pos(nfr, 0), sbits(n, 0), word0(n + 1, 0);
+    for (uint32_t t = 0; t < nfr * 16u; ++t) dcsb_enc_search_body(t, hs.data(), frame_stream.data(), nfr, f.data(), lo.data(), hi.data(), best.data());
+    for (uint32_t t = 0; t < n; ++t) dcsb_enc_resolve_body(t, hs.data(), (int)n, best.data(), codes.data(), padj.data());
+    for (uint32_t t = 0; t < nfr; ++t) dcsb_enc_emit_body<false>(t, hs.data(), frame_stream.data(), nfr, f.data(), codes.data(), padj.data(), frame_bits.data(), nullptr, nullptr, nullptr);
+    for (uint32_t t = 0; t < nfr * 16u; ++t) dcsb_enc_search93_body(t, hs.data(), frame_stream.data(), nfr, f.data(), best.data());
+    for (uint32_t t = 0; t < n; ++t) dcsb_enc_resolve93_body(t, hs.data(), (int)n, f.data(), best.data(), dec.data());
+    for (uint32_t t = 0; t < nfr; ++t) dcsb_enc_frame93_body<false>(t, hs.data(), frame_stream.data(), nfr, f.data(), dec.data(), frame_bits.data(), nullptr, nullptr, nullptr);
+    for (uint32_t t = 0; t < n; ++t) dcsb_enc_scan_body(t, hs.data(), (int)n, frame_bits.data(), frame_pos.data(), sbits.data());
+    uint64_t need = 0;
+    for (size_t i = 0; i < n; ++i) { word0[i + 1] = word0[i] + (sbits[i] + 31) / 32 + 1; need += 18 + (sbits[i] + 7) / 8; }
+    if (need > out_capacity) return DCSB_E_NOMEM;
+    std::vector<uint32_t> words(word0[n], 0);
+    for (uint32_t t = 0; t < nfr; ++t) dcsb_enc_emit_body<true>(t, hs.data(), frame_stream.data(), nfr, f.data(), codes.data(), padj.data(), nullptr, frame_pos.data(), words.data(), word0.data());
+    for (uint32_t t = 0; t < nfr; ++t) dcsb_enc_frame93_body<true>(t, hs.data(), frame_stream.data(), nfr, f.data(), dec.data(), nullptr, frame_pos.data(), words.data(), word0.data());
+    uint64_t o = 0;
+    for (size_t i = 0; i < n; ++i) {
+        out_offsets[i] = o;
+        out[o++] = (uint8_t)(hs[i].n_frames >> 8);
+        out[o++] = (uint8_t)(hs[i].n_frames & 0xFF);
+        memcpy(out + o, hs[i].hdr, 16);
+        o += 16;
+        const uint64_t nb = (sbits[i] + 7) / 8;
+        memcpy(out + o, reinterpret_cast<const uint8_t *>(words.data() + word0[i]), nb);
+        o += nb;
+    }
+    out_offsets[n] = o;
+    return DCSB_OK;
+}

@@ -116,3 +116,34 @@ def rom_render(images, timelines):
     inf = dict(os=info.os_version, hw=info.hw_version, channels=info.n_channels, n_tracks=info.n_tracks,
                catalog=info.catalog_offset, post=info.post_code, version=info.version_number)
     return out, results, inf, hb[:nh].tobytes()
+
+
+def encode_streams(clips, params, want_frames=False):
+    """hostsim_encode_streams: the encoder's kernel bodies on the CPU (explicit stream types).  clips / params as for
+    dcsexplorer_b200.Context.encode_streams; returns the list of stream bytes (and the frames per clip)."""
+    L = lib()
+    n = len(clips)
+    keep = [np.ascontiguousarray(c, dtype=np.float32) for c in clips]
+    ptrs = (C.c_void_p * max(1, n))(*[k.ctypes.data for k in keep])
+    ns = (C.c_uint64 * max(1, n))(*[k.size for k in keep])
+    pa = np.zeros(max(1, n), dtype=np.dtype([("t", "<i4"), ("s", "<i4"), ("r", "<i4"), ("c", "<f4"), ("q", "<f4"), ("d", "<f4"), ("v", "<i4")]))
+    for i, p in enumerate(params):
+        pa[i] = (p[0], p[1], p[2], p[3], p[4] if len(p) > 4 else 10.0 / 32768.0, p[5] if len(p) > 5 else 10.0 / 32768.0, p[6] if len(p) > 6 else 0)
+    nfr = [(int(k.size) + 239) // 240 for k in keep]
+    cap = sum(18 + 527 * f + 8 for f in nfr) + 64
+    out = np.zeros(cap, dtype=np.uint8)
+    offs = (C.c_uint64 * (n + 1))()
+    frames = np.zeros((max(1, sum(nfr)), 256), dtype=np.float32) if want_frames else None
+    L.hostsim_encode_streams.restype = C.c_int
+    L.hostsim_encode_streams.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    rc = L.hostsim_encode_streams(ptrs, ns, n, pa.ctypes.data, out.ctypes.data, cap, offs, frames.ctypes.data if want_frames else None)
+    if rc != 0:
+        raise RuntimeError("hostsim_encode_streams: %d" % rc)
+    streams = [out[offs[i]:offs[i + 1]].tobytes() for i in range(n)]
+    if not want_frames:
+        return streams
+    fl, o = [], 0
+    for k in nfr:
+        fl.append(frames[o:o + k])
+        o += k
+    return streams, fl
