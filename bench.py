@@ -337,6 +337,22 @@ def encoder_record(ctx, dx, n=128, seconds=10.0):
     res = {"workload": "%d clips x %.0f s, stream types {0.0, 1.0, 1.3} x bit rates 32k..256k x power cut {.90, .97, 1}" % (n, seconds),
            "ms_per_call": min(ts[1:]) * 1e3, "value": samples / min(ts[1:]) / 1e6, "unit": "Msamples/s encoded",
            "api": "dcsb_encode_streams (host PCM in, host stream bytes out)", "stream_bytes": int(sum(len(g) for g in got))}
+    # round trip: every encoded stream back through the decode path; signal-to-noise ratio against the source (the codec
+    # is lossy and delays the clip by its 16-sample overlap: best lag of 0..31) on a sample of the clips
+    pcm, offs, dres = ctx.decode_streams_pinned([(g, 0x9400, 255, 0x64, 2) for g in got])
+    snr = []
+    for i in range(0, n, max(1, n // 16)):
+        a = clips[i].astype(np.float64)
+        best = -1e9
+        for lag in range(32):
+            b = pcm[offs[i] + lag:offs[i] + lag + a.size].astype(np.float64) / 32768.0
+            m = min(a.size, b.size)
+            g_ = np.dot(a[:m], b[:m]) / max(np.dot(b[:m], b[:m]), 1e-30)          # (the decoder's output gain is not unity)
+            e = a[:m] - g_ * b[:m]
+            best = max(best, 10.0 * np.log10(max(np.dot(a[:m], a[:m]), 1e-30) / max(np.dot(e, e), 1e-30)))
+        snr.append(best)
+    res["round_trip"] = {"decoded_streams": n, "streams_with_errors": sum(1 for r in dres if r["status"] != 0),
+                         "median_snr_db_of_sample": float(np.median(snr)), "min_snr_db_of_sample": float(np.min(snr)), "sampled_clips": len(snr)}
     if ref.available():
         import multiprocessing as mp
         ncpu = max(1, len(os.sched_getaffinity(0)))
