@@ -3,7 +3,7 @@
 the kernel bodies (tests/hostsim), the plain-C oracle and -- for streams that decode without an error status -- the
 compiled reference; prints every mismatch.  With "rom" as the second argument: seeded ROM-playback scenarios (all four OS
 versions, error streams, software 1.05) through the sequencer + kernel bodies against the reference decoder.
-usage: tools/soak_cpu.py [seconds=1500] [streams|rom]"""
+usage: tools/soak_cpu.py [seconds=1500] [streams|rom|encode]"""
 import os
 import sys
 import time
@@ -13,6 +13,26 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import dcsfuzz, simutil
 from oracle import orc, ref
+if len(sys.argv) > 2 and sys.argv[2] == "encode":
+    # the encoder's kernel bodies (hostsim) against the reference encoder fed the same framing: seeded clips and parameters
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import simutil
+    import encode_soak_cases as esc
+    budget = float(sys.argv[1])
+    t0, n, bad, k = time.time(), 0, 0, 0
+    while time.time() - t0 < budget:
+        cp = [esc.make((97, k * 40 + j)) for j in range(40)]
+        cp = [(x[:6000], p if p[0] >= 0 and p[1] >= 0 else (0, 0) + p[2:]) for x, p in cp]       # (the wildcard is host logic of the product)
+        got = simutil.encode_streams([c for c, _ in cp], [p for _, p in cp])
+        for (x, p), g in zip(cp, got):
+            w = ref.encode_framed(x, p[0], p[1], p[2], p[3], p[4], p[5], fmt=p[6])[0]
+            n += 1
+            if g != w:
+                bad += 1
+                print("MISMATCH clip", k, p)
+        k += 1
+    print("encode soak (cpu): %d clips, mismatches %d, %.0f s" % (n, bad, time.time() - t0))
+    sys.exit(1 if bad else 0)
 if len(sys.argv) > 2 and sys.argv[2] == "rom":
     from oracle import ref
     import rombuild as rb, romscen, simutil
